@@ -1,0 +1,64 @@
+"""CPU suite: the NumPy oracle (oracle/np_oracle.py) against the golden vectors produced by the
+live reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+
+@pytest.fixture(scope="module")
+def gref(golden_dir):
+    return np.load(os.path.join(golden_dir, "get_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def gpred(golden_dir):
+    return np.load(os.path.join(golden_dir, "newref_predict.npz"), allow_pickle=True)
+
+
+@pytest.mark.parametrize("case,part,parts,k", [("A_p11", 1, 1, 30), ("A_p23", 2, 3, 30),
+                                                ("G", 1, 1, 30), ("T", 1, 1, 12), ("S", 1, 1, 20)])
+def test_get_reference_bit_exact(gref, case, part, parts, k):
+    base = case.split("_")[0]
+    x, per, cum = gref[base + "_x"], gref[base + "_per"], gref[base + "_cum"]
+    idx, dist, nr = O.get_reference(x, per, cum, k, part, parts, gref[case + "_ids"].tolist())
+    assert idx.dtype == np.int32
+    assert np.array_equal(idx, gref[case + "_idx"])
+    assert np.array_equal(dist, gref[case + "_dist"])  # same NumPy expression -> bit exact
+    assert np.array_equal(nr, gref[case + "_nr"], equal_nan=True)
+
+
+def _ref(gpred):
+    return {k[5:]: gpred[k] for k in gpred.files if k.startswith("ref__")}
+
+
+@pytest.mark.parametrize("si,g", [(0, "F"), (1, "M")])
+def test_normalize_matches_reference(gpred, si, g):
+    ref = _ref(gpred)
+    sample = {str(c): gpred[f"t{si}_sample_{c}"].copy() for c in range(1, 25)}
+    if g == "M":  # overall_tools.py:48-53
+        sample["23"] = sample["23"] * 2
+        sample["24"] = sample["24"] * 2
+    assert np.isclose(O.get_optimal_cutoff(ref["distances"], 5), gpred[f"t{si}_cutoff"], rtol=1e-12)
+    for rg in ["A", g]:
+        r, z, w, n, m_lr, m_z = O.normalize(sample, ref, rg)
+        np.testing.assert_allclose(r, gpred[f"t{si}_{rg}_r"], rtol=1e-9, equal_nan=True)
+        np.testing.assert_allclose(z, gpred[f"t{si}_{rg}_z"], rtol=1e-7, atol=1e-9, equal_nan=True)
+        np.testing.assert_allclose(w, gpred[f"t{si}_{rg}_w"], rtol=1e-12)
+        assert np.array_equal(n, gpred[f"t{si}_{rg}_n"])
+        np.testing.assert_allclose([m_lr, m_z], gpred[f"t{si}_{rg}_m"], rtol=1e-7, atol=1e-10)
+
+
+def test_get_z_score_matches_reference(gpred):
+    bpc = gpred["zs_bpc"]
+    offs = np.concatenate([[0], np.cumsum(bpc)])
+    r, w, nr, has = gpred["zs_r"], gpred["zs_w"], gpred["zs_nr"], gpred["zs_has_nr"]
+    res_r = [r[offs[c]:offs[c + 1]] for c in range(len(bpc))]
+    res_w = [w[offs[c]:offs[c + 1]] for c in range(len(bpc))]
+    res_nr = [[nr[i] if has[i] else 0 for i in range(offs[c], offs[c + 1])] for c in range(len(bpc))]
+    segs = [[int(s[0]), int(s[1]), int(s[2]), float(s[3])] for s in gpred["zs_segs"]]
+    zs = O.get_z_score(segs, res_nr, res_r, res_w)
+    got = np.array([np.nan if isinstance(z, str) else z for z in zs])
+    np.testing.assert_allclose(got, gpred["zs_z"], rtol=1e-9, equal_nan=True)
