@@ -1,0 +1,98 @@
+/* wcx_b200 -- C-ABI of the B200-native WisecondorX numeric core (libwcx_b200.so).
+ *
+ * The reference (CenterForMedicalGeneticsGhent/WisecondorX v1.2.10) is pure Python + R and has
+ * no FFI of its own; the seams this library replaces are ordinary Python call sites.  Each entry
+ * point below names the reference function (file:line under src/wisecondorx/) whose arithmetic
+ * it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; wcx_last_error() gives the text
+ *     (thread-local).  There is NO CPU fallback: without a usable sm_100 device wcx_create fails.
+ *   - the caller owns every buffer.  Pointers are C-contiguous.  `on_device` flags say whether a
+ *     pointer is a host pointer (0) or a device pointer on the context's device (1).
+ *   - all work of a context is issued on one CUDA stream (own stream by default, or the one given
+ *     to wcx_set_stream, e.g. torch's current stream); calls with host outputs synchronise it.
+ *   - a context is not re-entrant; use one context per host thread / per GPU.
+ */
+#ifndef WCX_B200_H
+#define WCX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wcx_ctx wcx_ctx;
+
+/* kernel selector for the distance sweep */
+#define WCX_KERNEL_AUTO 0 /* tcgen05 tensor-core kernel */
+#define WCX_KERNEL_TC 1   /* tcgen05 / TMEM / TMA kernel (dist_topk_tc.cu) */
+#define WCX_KERNEL_SIMT 2 /* CUDA-core fp32 kernel (dist_topk_simt.cu), cross-check path */
+#define WCX_KERNEL_EXACT 3 /* brute-force float64 rows only (exact_rows_kernel), slow, for tests */
+
+int wcx_version(void);
+const char* wcx_last_error(void);
+
+/* Creates a context on CUDA device `device` (must be compute capability 10.x). */
+int wcx_create(int32_t device, wcx_ctx** out);
+void wcx_destroy(wcx_ctx* ctx);
+/* Issue subsequent work on `cuda_stream` (a cudaStream_t); NULL restores the context's own stream. */
+int wcx_set_stream(wcx_ctx* ctx, void* cuda_stream);
+int wcx_sync(wcx_ctx* ctx);
+
+/* ---- newref ------------------------------------------------------------------------------
+ * Replaces get_reference (newref_tools.py:155-224): get_ref_for_bins (:255-278) and the
+ * null-ratio loop (:210-224).
+ *
+ * wcx_newref_load: X = pca_corrected_data [N, S] float64 row-major (newref_control.py:68 / :91),
+ *   per/cum = masked_bins_per_chr(_cum) (C entries; C > 22 selects the gonosomal behaviour of
+ *   newref_tools.py:186-191).  Copies (or borrows, if x_on_device) X and prepares the
+ *   tensor-core operands.  A borrowed device X must stay alive until the next load/destroy.
+ */
+int wcx_newref_load(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, const int64_t* per,
+                    const int64_t* cum, int32_t c, int32_t x_on_device);
+
+/* indexes int32 [rows, k] and distances float64 [rows, k] for target bins [row_begin, row_end)
+ * == the part handled by get_reference(part, split_parts) (newref_tools.py:168, :244-247).
+ * Bit-exact with the reference: same distances (NumPy summation order), same (distance,
+ * position) order, -1 / 1e10 fillers, placeholder rows (0, 1.0) in gonosomal mode.
+ * Either output may be NULL (the result stays on the device for wcx_newref_null_ratios). */
+int wcx_newref_topk(wcx_ctx* ctx, int64_t row_begin, int64_t row_end, int32_t k, int32_t kernel,
+                    int32_t* idx_out, double* dist_out, int32_t out_on_device);
+
+/* null_ratios float64 [rows, M]: log2(col[b] / median(col[idx[b, :]])) for the M sample columns
+ * `sample_ids` (host int32; the reference draws them with random.sample at newref_tools.py:215).
+ * idx == NULL uses the indexes left on the device by the last wcx_newref_topk call for the same
+ * row range and k. */
+int wcx_newref_null_ratios(wcx_ctx* ctx, const int32_t* idx, int32_t idx_on_device, int64_t row_begin,
+                           int64_t row_end, int32_t k, const int32_t* sample_ids, int32_t m,
+                           double* out, int32_t out_on_device);
+
+/* One-call host-to-host form of get_reference: load + topk + null ratios. */
+int wcx_get_reference(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, const int64_t* per,
+                      const int64_t* cum, int32_t c, int32_t k, int64_t row_begin, int64_t row_end,
+                      const int32_t* sample_ids, int32_t m, int32_t kernel, int32_t* idx_out,
+                      double* dist_out, double* null_out);
+
+/* Counters of the last wcx_newref_topk call: out[0] = work items, out[1] = rows recomputed by the
+ * exact brute-force path, out[2] = kernel launches issued since wcx_create, out[3] = column
+ * splits per row, out[4] = sweep kernel used, out[5..7] reserved. */
+int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
+
+/* Device time in milliseconds of the stages of the last wcx_newref_topk call, measured with CUDA
+ * events on the context's stream: out[0] = sweep (distance + approximate top-k), out[1] = exact
+ * re-rank, out[2] = brute-force rows, out[3] = last wcx_newref_null_ratios, out[4] = last
+ * wcx_newref_load preparation kernels, out[5..7] reserved. */
+int wcx_newref_stage_ms(wcx_ctx* ctx, double* out8);
+
+/* Test hook: raw tensor-core accumulators <Xc[row0 + i], Xc[col0 + j]> of one 128 x 256 tile,
+ * written to acc_out [128 * 256] (host). */
+int wcx_debug_tc_tile(wcx_ctx* ctx, int64_t row0, int64_t col0, float* acc_out);
+/* Test hook: prepared operands.  xc_out [n, k_pad] (host, may be NULL), norm_out [n] (host). */
+int wcx_debug_prep(wcx_ctx* ctx, float* xc_out, float* norm_out, int32_t* k_pad_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WCX_B200_H */

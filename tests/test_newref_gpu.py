@@ -1,0 +1,183 @@
+"""GPU parity tests for the newref path (get_reference): the CUDA library, called through the
+C-ABI (ctypes), against the oracle and the golden vectors of the live reference.
+
+Bars (BASELINE.json north_star): indexes bit-exact; distances / null ratios within 1e-5 -- the
+distance tests below assert the stronger bit-exact equality, which the exact re-rank guarantees.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle, np_oracle  # noqa: E402
+from wisecondorx_b200 import _lib, newref_tools, synth  # noqa: E402
+
+KERNELS = {"tc": _lib.KERNEL_TC, "simt": _lib.KERNEL_SIMT, "exact": _lib.KERNEL_EXACT}
+
+
+@pytest.fixture(scope="module")
+def gref(golden_dir):
+    return np.load(os.path.join(golden_dir, "get_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return newref_tools.NewrefEngine(0)
+
+
+def tf32_round(a):
+    """round-to-nearest (ties away) to 10 mantissa bits, like cvt.rna.tf32.f32"""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x1000) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_prep_centres_and_rounds(eng):
+    x, per, cum = synth.make_corrected_matrix([300, 200, 100] + [10] * 19, 37, seed=3)
+    eng.load(x, per, cum)
+    import ctypes
+    n, s = x.shape
+    kp = ctypes.c_int32()
+    L = _lib.load()
+    _lib.check(L.wcx_debug_prep(eng.ctx.handle, None, None, ctypes.byref(kp)))
+    assert kp.value == 64
+    xc = np.empty((n, kp.value), dtype=np.float32)
+    nrm = np.empty(n, dtype=np.float32)
+    _lib.check(L.wcx_debug_prep(eng.ctx.handle, xc.ctypes.data, nrm.ctypes.data, None))
+    want = tf32_round((x - x.mean(axis=0)).astype(np.float32))
+    assert np.array_equal(xc[:, :s], want)
+    assert not xc[:, s:].any()
+    np.testing.assert_allclose(nrm, (want.astype(np.float64) ** 2).sum(1), rtol=1e-6)
+
+
+def test_tensor_core_tile_matches_fp64_matmul(eng):
+    """Raw tcgen05 accumulators of one 128 x 256 tile vs a float64 product of the same rounded operands."""
+    import ctypes
+    x, per, cum = synth.make_corrected_matrix([500, 400, 300] + [20] * 19, 100, seed=4)
+    eng.load(x, per, cum)
+    L = _lib.load()
+    n, s = x.shape
+    kp = ctypes.c_int32()
+    _lib.check(L.wcx_debug_prep(eng.ctx.handle, None, None, ctypes.byref(kp)))
+    xc = np.empty((n, kp.value), dtype=np.float32)
+    nrm = np.empty(n, dtype=np.float32)
+    _lib.check(L.wcx_debug_prep(eng.ctx.handle, xc.ctypes.data, nrm.ctypes.data, None))
+    for row0, col0 in [(0, 0), (128, 256), (900, 1024)]:
+        acc = np.empty((128, 256), dtype=np.float32)
+        _lib.check(L.wcx_debug_tc_tile(eng.ctx.handle, row0, col0, acc.ctypes.data))
+        a = np.zeros((128, kp.value)); b = np.zeros((256, kp.value))
+        ra = xc[row0:row0 + 128]; rb = xc[col0:col0 + 256]
+        a[:len(ra)] = ra; b[:len(rb)] = rb
+        want = a @ b.T
+        scale = np.abs(a).sum(1)[:, None] * np.abs(b).max()
+        err = np.abs(acc - want).max()
+        assert err < 1e-5 * max(1.0, np.abs(want).max()), (row0, col0, err, np.abs(want).max())
+
+
+@pytest.mark.parametrize("kernel", ["tc", "simt", "exact"])
+@pytest.mark.parametrize("case,part,parts,k", [("A_p11", 1, 1, 30), ("A_p23", 2, 3, 30), ("G", 1, 1, 30),
+                                                ("T", 1, 1, 12), ("S", 1, 1, 20)])
+def test_golden_get_reference(gref, kernel, case, part, parts, k):
+    base = case.split("_")[0]
+    x, per, cum = gref[base + "_x"], gref[base + "_per"], gref[base + "_cum"]
+    idx, dist, nr = newref_tools.get_reference(x, per, cum, k, part, parts, kernel=KERNELS[kernel],
+                                               sample_ids=gref[case + "_ids"].tolist())
+    assert idx.dtype == np.int32 and dist.dtype == np.float64
+    assert np.array_equal(idx, gref[case + "_idx"])
+    assert np.array_equal(dist, gref[case + "_dist"])
+    np.testing.assert_allclose(nr, gref[case + "_nr"], rtol=1e-12, atol=1e-14, equal_nan=True)
+
+
+def test_random_draw_follows_python_random(gref):
+    """Without explicit sample_ids the wrapper draws like the reference (newref_tools.py:214-217)."""
+    x, per, cum = gref["A_x"], gref["A_per"], gref["A_cum"]
+    random.seed(7)
+    idx, dist, nr = newref_tools.get_reference(x, per, cum, 30, 1, 1)
+    np.testing.assert_allclose(nr, gref["A_p11_nr"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("kernel", ["tc", "simt"])
+def test_config1_full_vs_c_oracle(eng, kernel):
+    """BASELINE config 1: 1 Mb bins (2887 autosomal), 20 samples, refsize 300 -- full parity."""
+    per = synth.config_bins(1)
+    x, per, cum = synth.make_corrected_matrix(per, 20, seed=11)
+    n = x.shape[0]
+    eng.load(x, per, cum)
+    idx, dist = eng.topk(0, n, 300, KERNELS[kernel])
+    oi, od = c_oracle.topk(x, per, cum, 300, 0, n)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)
+    ids = list(range(20))
+    nr = eng.null_ratios(0, n, 300, ids)
+    onr = c_oracle.null_ratios(x, oi, 0, n, ids)
+    np.testing.assert_allclose(nr, onr, rtol=1e-12, atol=1e-14)
+    st = eng.stats()
+    assert st["exact_fallback_rows"] <= n // 50, st
+
+
+@pytest.mark.parametrize("kernel", ["tc", "simt"])
+def test_config2_parts_vs_c_oracle(eng, kernel):
+    """BASELINE config 2: 100 kb bins (28760), 100 samples, refsize 300; parts compared in full."""
+    per = synth.config_bins(2)
+    x, per, cum = synth.make_corrected_matrix(per, 100, seed=12)
+    n = x.shape[0]
+    eng.load(x, per, cum)
+    parts = 100
+    for part in (1, 37, 100):
+        s, e = newref_tools._get_part(part - 1, parts, n)
+        idx, dist = eng.topk(s, e, 300, KERNELS[kernel])
+        oi, od = c_oracle.topk(x, per, cum, 300, s, e)
+        assert np.array_equal(idx, oi), part
+        assert np.array_equal(dist, od), part
+        ids = list(range(0, 100, 7))
+        nr = eng.null_ratios(s, e, 300, ids)
+        onr = c_oracle.null_ratios(x, oi, s, e, ids)
+        np.testing.assert_allclose(nr, onr, rtol=1e-12, atol=1e-14)
+        assert eng.stats()["exact_fallback_rows"] <= (e - s) // 20
+
+
+def test_tc_equals_simt_whole_config2(eng):
+    per = synth.config_bins(2)
+    x, per, cum = synth.make_corrected_matrix(per, 100, seed=13)
+    n = x.shape[0]
+    eng.load(x, per, cum)
+    i1, d1 = eng.topk(0, n, 300, KERNELS["tc"])
+    st1 = eng.stats()
+    i2, d2 = eng.topk(0, n, 300, KERNELS["simt"])
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert st1["exact_fallback_rows"] <= n // 100, st1
+    # sortedness + index range: size-independent properties
+    assert (np.diff(d1, axis=1) >= 0).all()
+    assert i1.min() >= 0 and i1.max() < n
+
+
+def test_edge_cases(eng):
+    # ties everywhere (quantised data), NaN row, fewer candidates than refsize, empty range
+    per = np.array([40, 30, 20, 10] + [0] * 18)
+    x, per, cum = synth.make_corrected_matrix(per, 9, seed=21)
+    x = np.round(x * 16) / 16
+    x[5, 3] = np.nan
+    n = x.shape[0]
+    oi, od = c_oracle.topk(x, per, cum, 64, 0, n)
+    for kernel in ("tc", "simt", "exact"):
+        eng.load(x, per, cum)
+        idx, dist = eng.topk(0, n, 64, KERNELS[kernel])
+        assert np.array_equal(idx, oi), kernel
+        assert np.array_equal(dist, od), kernel
+        idx0, dist0 = eng.topk(7, 7, 64, KERNELS[kernel])
+        assert idx0.shape == (0, 64)
+    assert (oi[5] == -1).all() and (od[5] == 1e10).all()
+
+
+def test_bad_arguments_raise(eng):
+    x, per, cum = synth.make_corrected_matrix([50, 40] + [5] * 20, 8, seed=2)
+    eng.load(x, per, cum)
+    with pytest.raises(_lib.WcxError):
+        eng.topk(0, x.shape[0] + 1, 10)
+    with pytest.raises(_lib.WcxError):
+        eng.topk(0, 10, 0)
+    with pytest.raises(_lib.WcxError):
+        eng.null_ratios(0, 10, 10, [99])

@@ -62,3 +62,16 @@ def test_get_z_score_matches_reference(gpred):
     zs = O.get_z_score(segs, res_nr, res_r, res_w)
     got = np.array([np.nan if isinstance(z, str) else z for z in zs])
     np.testing.assert_allclose(got, gpred["zs_z"], rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("case,part,parts,k", [("A_p11", 1, 1, 30), ("A_p23", 2, 3, 30),
+                                                ("G", 1, 1, 30), ("T", 1, 1, 12), ("S", 1, 1, 20)])
+def test_c_oracle_get_reference(gref, case, part, parts, k):
+    from oracle import c_oracle
+    c_oracle.build()
+    base = case.split("_")[0]
+    x, per, cum = gref[base + "_x"], gref[base + "_per"], gref[base + "_cum"]
+    idx, dist, nr = c_oracle.get_reference(x, per, cum, k, part, parts, gref[case + "_ids"])
+    assert np.array_equal(idx, gref[case + "_idx"])
+    assert np.array_equal(dist, gref[case + "_dist"])  # NumPy pairwise order replicated
+    np.testing.assert_allclose(nr, gref[case + "_nr"], rtol=1e-13, atol=1e-15, equal_nan=True)

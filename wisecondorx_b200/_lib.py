@@ -1,0 +1,102 @@
+"""ctypes binding of libwcx_b200.so (include/wcx_b200.h).  There is no CPU fallback: if the
+library is missing or no sm_100 device is usable, every entry point raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libwcx_b200.so")
+HEADER = os.path.abspath(os.path.join(HERE, "..", "include", "wcx_b200.h"))
+
+KERNEL_AUTO, KERNEL_TC, KERNEL_SIMT, KERNEL_EXACT = 0, 1, 2, 3
+
+_lib = None
+
+
+class WcxError(RuntimeError):
+    pass
+
+
+def declared_symbols(header: str = HEADER):
+    """Function names declared in include/wcx_b200.h (used by the symbol-export test)."""
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(wcx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise WcxError(f"{SO_PATH} not built: run `python -m wisecondorx_b200.build` "
+                       "(or __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(SO_PATH)
+    vp, i64, i32, dp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p
+    L.wcx_version.restype = ctypes.c_int
+    L.wcx_last_error.restype = ctypes.c_char_p
+    L.wcx_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.wcx_destroy.argtypes = [vp]
+    L.wcx_destroy.restype = None
+    L.wcx_set_stream.argtypes = [vp, vp]
+    L.wcx_sync.argtypes = [vp]
+    L.wcx_newref_load.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32]
+    L.wcx_newref_topk.argtypes = [vp, i64, i64, i32, i32, vp, vp, i32]
+    L.wcx_newref_null_ratios.argtypes = [vp, vp, i32, i64, i64, i32, vp, i32, vp, i32]
+    L.wcx_get_reference.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32, i64, i64, vp, i32, i32, vp, vp, vp]
+    L.wcx_newref_stats.argtypes = [vp, vp]
+    L.wcx_newref_stage_ms.argtypes = [vp, vp]
+    L.wcx_debug_tc_tile.argtypes = [vp, i64, i64, vp]
+    L.wcx_debug_prep.argtypes = [vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise WcxError(load().wcx_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """One wcx_ctx (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0):
+        L = load()
+        h = ctypes.c_void_p()
+        check(L.wcx_create(device, ctypes.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().wcx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise WcxError("context closed")
+        return self._h
+
+    def set_stream(self, cuda_stream_ptr: int):
+        check(load().wcx_set_stream(self.handle, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        check(load().wcx_sync(self.handle))
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

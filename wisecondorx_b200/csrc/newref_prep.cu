@@ -1,0 +1,120 @@
+// Preparation kernels for the newref distance sweep (reference: newref_tools.py:192-203, the
+// `chr_data - row` operand of get_ref_for_bins).  All bandwidth-bound single passes over X.
+//
+//  * col_stats       per-sample (column) mean over finite entries: the centring vector.  Squared
+//                    distances are invariant under a per-column shift, and centring removes the
+//                    catastrophic cancellation of |a|^2 + |b|^2 - 2ab for data around 1.0.
+//  * center_round    Xc = tf32_round(float(X - mean)), zero padded to [n_pad, k_pad], plus the
+//                    row norms of the ROUNDED values (so the tensor-core dot products of the
+//                    rounded operands are exact products; only accumulation rounds).
+//  * transpose_cols  XT[m, :] = X[:, ids[m]] -- column-contiguous copies of the null-ratio sample
+//                    columns (newref_tools.py:213-219).
+#include "wcx_common.cuh"
+
+namespace wcx {
+
+__global__ void col_stats_kernel(const double* __restrict__ x, int64_t n, int32_t s, int64_t rows_per_block,
+                                 double* __restrict__ colsum, double* __restrict__ colcnt) {
+  __shared__ double ssum[8][33];
+  __shared__ double scnt[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > n) r1 = n;
+  double acc = 0.0, cnt = 0.0;
+  if (col < s) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      double v = x[r * s + col];
+      if (isfinite(v)) { acc += v; cnt += 1.0; }
+    }
+  }
+  ssum[threadIdx.y][threadIdx.x] = acc;
+  scnt[threadIdx.y][threadIdx.x] = cnt;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < s) {
+    for (int y = 1; y < 8; y++) { acc += ssum[y][threadIdx.x]; cnt += scnt[y][threadIdx.x]; }
+    atomicAdd(&colsum[col], acc);
+    atomicAdd(&colcnt[col], cnt);
+  }
+}
+
+int launch_col_stats(const double* x, int64_t n, int32_t s, double* colsum, double* colcnt, cudaStream_t st) {
+  WCX_CUDA_OK(cudaMemsetAsync(colsum, 0, sizeof(double) * s, st));
+  WCX_CUDA_OK(cudaMemsetAsync(colcnt, 0, sizeof(double) * s, st));
+  if (n == 0 || s == 0) return 0;
+  int64_t rows_per_block = 512;
+  dim3 grid((s + 31) / 32, (unsigned)((n + rows_per_block - 1) / rows_per_block));
+  col_stats_kernel<<<grid, dim3(32, 8), 0, st>>>(x, n, s, rows_per_block, colsum, colcnt);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// one warp per row
+__global__ void center_round_kernel(const double* __restrict__ x, int64_t n, int32_t s,
+                                    const double* __restrict__ colsum, const double* __restrict__ colcnt,
+                                    float* __restrict__ xc, float* __restrict__ norm, int64_t n_pad, int32_t k_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  float* out = xc + row * k_pad;
+  double acc = 0.0;
+  for (int c = lane; c < k_pad; c += 32) {
+    float v = 0.f;
+    if (row < n && c < s) {
+      double cnt = colcnt[c];
+      double mean = cnt > 0.0 ? colsum[c] / cnt : 0.0;
+      v = round_tf32((float)(x[row * s + c] - mean));
+    }
+    out[c] = v;
+    acc += (double)v * (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) norm[row] = (float)acc;
+}
+
+int launch_center_round(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
+                        float* xc, float* norm, int64_t n_pad, int32_t k_pad, cudaStream_t st) {
+  if (n_pad == 0) return 0;
+  const int warps = 8;
+  unsigned grid = (unsigned)((n_pad + warps - 1) / warps);
+  center_round_kernel<<<grid, warps * 32, 0, st>>>(x, n, s, colsum, colcnt, xc, norm, n_pad, k_pad);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// XT[m, r] = X[r, ids[m]]; tile 32 rows x 32 chosen columns through shared memory
+__global__ void transpose_cols_kernel(const double* __restrict__ x, int64_t n, int32_t s,
+                                      const int32_t* __restrict__ ids, int32_t m, double* __restrict__ xt) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int m0 = blockIdx.y * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int64_t r = r0 + y;
+    int mm = m0 + threadIdx.x;
+    if (r < n && mm < m) tile[y][threadIdx.x] = x[r * s + ids[mm]];
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int mm = m0 + y;
+    int64_t r = r0 + threadIdx.x;
+    if (r < n && mm < m) xt[(int64_t)mm * n + r] = tile[threadIdx.x][y];
+  }
+}
+
+int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m, double* xt,
+                          cudaStream_t st) {
+  if (n == 0 || m == 0) return 0;
+  dim3 grid((unsigned)((n + 31) / 32), (m + 31) / 32);
+  transpose_cols_kernel<<<grid, dim3(32, 8), 0, st>>>(x, n, s, ids, m, xt);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace wcx

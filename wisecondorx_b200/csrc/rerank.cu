@@ -1,0 +1,490 @@
+// Exact re-rank of the approximate candidate lists ("K2b") and the exact brute-force row path.
+//
+// Reference semantics reproduced bit for bit (newref_tools.py:255-278):
+//   * distance d_j = np.sum(np.power(chr_data[j] - row, 2)) in float64 with three separate
+//     roundings per term (subtract, square, add) and NumPy's pairwise summation order along the
+//     contiguous sample axis -- realised here with __dsub_rn/__dmul_rn/__dadd_rn (no FMA
+//     contraction) and a per-S "summation plan" that replays NumPy's recursion tree;
+//   * selection = first ref_size entries of a stable ascending sort, i.e. ordered by
+//     (distance, position), position = index in the chromosome-excluded array, values >= 1e10
+//     never inserted, missing entries (-1, 1e10).
+//
+// Completeness proof obligation of the fast path.  The sweep kernels hand over, per row, lists
+// of approximate values v~_j = |b^_j|^2 - 2<a^,b^_j> (tf32-rounded operands, fp32 accumulate)
+// and a cut such that every candidate NOT listed has v~ >= cut.  With eps >= |d~_j - d_j| for
+// every relevant j, the exact top-k is contained in { j : v~_j <= v~_(k) + 2 eps }.  The
+// kernel evaluates exact distances for that prefix only, and flags the row for the brute-force
+// path whenever the prefix is not strictly below the cut or the a-posteriori check
+// (exact d_(k) + eps < bound) fails.  Flagged rows are recomputed by exact_rows_kernel, so the
+// final indexes never depend on the approximation.
+#include <vector>
+
+#include "wcx_common.cuh"
+
+namespace wcx {
+
+// ------------------------------------------------------------------------------------------
+// NumPy pairwise-sum plan: postfix program of int32 triples (op, a, b):
+//   op 0: LEAF  a = offset, b = length (<= 128)  -> push
+//   op 1: ADD   pop r, pop l, push l + r
+// ------------------------------------------------------------------------------------------
+static void plan_rec(int32_t off, int32_t n, std::vector<int32_t>& p) {
+  if (n <= 128) {
+    p.push_back(0); p.push_back(off); p.push_back(n);
+  } else {
+    int32_t n2 = n / 2;
+    n2 -= n2 % 8;
+    plan_rec(off, n2, p);
+    plan_rec(off + n2, n - n2, p);
+    p.push_back(1); p.push_back(0); p.push_back(0);
+  }
+}
+
+int build_sum_plan(int32_t s, int32_t* plan, int32_t cap) {
+  std::vector<int32_t> p;
+  plan_rec(0, s, p);
+  if ((int32_t)p.size() > cap) return -1;
+  for (size_t i = 0; i < p.size(); i++) plan[i] = p[i];
+  return (int32_t)(p.size() / 3);
+}
+
+namespace {
+
+constexpr int RR_THREADS = 256;
+constexpr int RR_MAXC = 2048;  // max candidates merged per row (nsplit * KEEP)
+constexpr int PLAN_STACK = 16;
+
+__device__ __forceinline__ uint64_t f64_key(double d) {
+  uint64_t u = (uint64_t)__double_as_longlong(d);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ uint32_t f32_key_(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32_(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// Exact reference distance between the target row `a` (shared memory) and candidate row `b`
+// (global), evaluated cooperatively by the 4 lanes of a quad (l = lane & 3).  All four lanes
+// return the same value.  `gmask` = shuffle mask of the quad's warp (full warp participates).
+__device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a, const double* __restrict__ b,
+                                                    const int32_t* __restrict__ plan, int plan_len, int l) {
+  double stack[PLAN_STACK];
+  int sp = 0;
+  for (int op = 0; op < plan_len; op++) {
+    const int code = plan[3 * op];
+    if (code == 0) {
+      const int off = plan[3 * op + 1], len = plan[3 * op + 2];
+      double res;
+      if (len < 8) {
+        res = 0.0;
+        for (int i = 0; i < len; i++) {
+          double t = __dsub_rn(b[off + i], a[off + i]);
+          res = __dadd_rn(res, __dmul_rn(t, t));
+        }
+      } else {
+        const int nblk = len >> 3;
+        const double* bp = b + off + 2 * l;
+        const double* ap = a + off + 2 * l;
+        double t0 = __dsub_rn(bp[0], ap[0]);
+        double t1 = __dsub_rn(bp[1], ap[1]);
+        double r0 = __dmul_rn(t0, t0), r1 = __dmul_rn(t1, t1);
+#pragma unroll 4
+        for (int blk = 1; blk < nblk; blk++) {
+          double u0 = __dsub_rn(bp[8 * blk], ap[8 * blk]);
+          double u1 = __dsub_rn(bp[8 * blk + 1], ap[8 * blk + 1]);
+          r0 = __dadd_rn(r0, __dmul_rn(u0, u0));
+          r1 = __dadd_rn(r1, __dmul_rn(u1, u1));
+        }
+        double s1 = __dadd_rn(r0, r1);
+        double s2 = __dadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, 1));
+        res = __dadd_rn(s2, __shfl_xor_sync(0xffffffffu, s2, 2));
+        for (int i = nblk << 3; i < len; i++) {
+          double t = __dsub_rn(b[off + i], a[off + i]);
+          res = __dadd_rn(res, __dmul_rn(t, t));
+        }
+      }
+      stack[sp++] = res;
+    } else {
+      double r = stack[--sp];
+      double lft = stack[--sp];
+      stack[sp++] = __dadd_rn(lft, r);
+    }
+  }
+  return stack[0];
+}
+
+// in-place bitonic sort of n_pow2 uint64 keys in shared memory (ascending)
+__device__ void bitonic_sort_u64(uint64_t* keys, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t a = keys[i], b = keys[ixj];
+          bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// sort (d, pos) pairs ascending by (d, pos); arrays in shared memory, n_pow2 entries
+__device__ void bitonic_sort_dpos(uint64_t* dkey, int32_t* pos, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t a = dkey[i], b = dkey[ixj];
+          int32_t pa = pos[i], pb = pos[ixj];
+          bool gt = (a > b) || (a == b && pa > pb);
+          bool up = ((i & k) == 0);
+          if (gt == up) { dkey[i] = b; dkey[ixj] = a; pos[i] = pb; pos[ixj] = pa; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// rigorous bound on |d~ - d| for candidates with d <= ~D seen from a row with |a|^2 = an
+__device__ __forceinline__ double approx_eps(double an, double D, int k_pad) {
+  const double u = 4.8852e-4;  // 2^-11 * (1 + 2^-10): tf32 round-to-nearest of an fp32-rounded value
+  double na = sqrt(an);
+  double sD = sqrt(D * 1.02 + 1e-300);
+  double nb = na + sD;                         // |b| <= |a| + sqrt(d)
+  double e = u * (na + nb);                    // | |a^-b^| - |a-b| | <= |da| + |db|
+  double rounding = 2.0 * sD * e + e * e;
+  double gamma = ((double)k_pad + 64.0) * 1.1920929e-7;  // fp32 accumulation, (k_pad + 64) * 2^-23
+  double accum = 2.0 * gamma * na * nb;
+  double misc = 4.77e-7 * (an + nb * nb + 2.0 * na * nb);  // fp32 norm + final fma roundings
+  return 1.5 * (rounding + accum + misc) + 1e-300;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// rerank kernel: one CTA per target row
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RR_THREADS)
+rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nsplit, const int64_t* __restrict__ cum,
+              int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
+              double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
+              int plan_len) {
+  extern __shared__ unsigned char rr_smem[];
+  // layout: a[S] doubles | keys[RR_MAXC] u64 | pos[RR_MAXC] i32 | plan
+  double* a_s = reinterpret_cast<double*>(rr_smem);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((pv.s + 1) & ~1));
+  int32_t* pos_s = reinterpret_cast<int32_t*>(keys + RR_MAXC);
+  int32_t* plan = pos_s + RR_MAXC;
+  __shared__ int s_tot, s_m, s_fail;
+  __shared__ int s_cs, s_ce;
+  __shared__ float s_cut;
+  __shared__ double s_bound, s_eps;
+
+  const int tid = threadIdx.x;
+  const int64_t lrow = blockIdx.x;
+  const int64_t row = row_begin + lrow;
+  int32_t* oi = idx_out + lrow * k;
+  double* od = dist_out + lrow * k;
+
+  if (tid == 0) {
+    int c = 0;
+    while (c < nchr && cum[c] <= row) c++;
+    s_cs = (int)(c == 0 ? 0 : cum[c - 1]);
+    s_ce = (int)cum[c];
+    s_fail = 0;
+    if (gonosomal && c != 22 && c != 23) s_cs = -1;
+  }
+  __syncthreads();
+  if (s_cs < 0) {  // placeholder rows of gonosomal references (newref_tools.py:186-191)
+    for (int t = tid; t < k; t += RR_THREADS) { oi[t] = 0; od[t] = 1.0; }
+    return;
+  }
+  const int cs = s_cs, ce = s_ce;
+  for (int i = tid; i < pv.s; i += RR_THREADS) a_s[i] = x[row * pv.s + i];
+  for (int i = tid; i < 3 * plan_len; i += RR_THREADS) plan[i] = plan_g[i];
+
+  // gather the split lists: key = (orderable(v) << 32) | j
+  if (tid == 0) {
+    int tot = 0;
+    float cut = __int_as_float(0x7f800000);
+    for (int q = 0; q < nsplit; q++) {
+      int64_t slot = lrow * nsplit + q;
+      tot += cv.cnt[slot];
+      cut = fminf(cut, cv.cut[slot]);
+    }
+    s_tot = tot;
+    s_cut = cut;
+  }
+  __syncthreads();
+  const int tot = s_tot;
+  {
+    int base = 0;
+    for (int q = 0; q < nsplit; q++) {
+      int64_t slot = lrow * nsplit + q;
+      int c = cv.cnt[slot];
+      for (int i = tid; i < c; i += RR_THREADS)
+        keys[base + i] = ((uint64_t)f32_key_(cv.val[slot * WCX_CAND_CAP + i]) << 32) |
+                         (uint32_t)cv.idx[slot * WCX_CAND_CAP + i];
+      base += c;
+    }
+  }
+  const int p2 = next_pow2(tot < 2 ? 2 : tot);
+  for (int i = tot + tid; i < p2; i += RR_THREADS) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(keys, p2);
+
+  // prefix that can contain the exact top-k
+  if (tid == 0) {
+    int m = tot;
+    double bound = 1e300, eps = 0.0;
+    if (tot > k) {
+      float vk = key_f32_((uint32_t)(keys[k - 1] >> 32));
+      double an = (double)pv.norm[row];
+      double D = fmax((double)vk + an, 0.0);
+      eps = approx_eps(an, D, pv.k_pad);
+      bound = (double)vk + 2.0 * eps;
+      // count v <= bound (sorted ascending): binary search
+      int lo = k, hi = tot;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((double)key_f32_((uint32_t)(keys[mid] >> 32)) <= bound) lo = mid + 1; else hi = mid;
+      }
+      m = lo;
+    }
+    // every unlisted candidate has v >= cut: need cut strictly above the bound
+    if (!((double)s_cut > bound)) s_fail = 1;
+    s_m = m;
+    s_bound = bound;
+    s_eps = eps;
+  }
+  __syncthreads();
+  const int m = s_m;
+  if (s_fail) {
+    if (tid == 0) fail_flags[lrow] = 1;
+    return;
+  }
+
+  // exact distances of the first m candidates, one quad per candidate
+  const int quad = tid >> 2, l = tid & 3;
+  const int rounds = (m + (RR_THREADS / 4) - 1) / (RR_THREADS / 4);
+  for (int rd = 0; rd < rounds; rd++) {
+    const int ci = rd * (RR_THREADS / 4) + quad;
+    const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
+    const int j = (int)(uint32_t)(keys[cc] & 0xffffffffu);
+    double d = exact_sqdist_quad(a_s, x + (int64_t)j * pv.s, plan, plan_len, l);
+    __syncthreads();  // every quad of this round has read its keys[cc]
+    if (l == 0 && ci < m) { keys[ci] = f64_key(d); pos_s[ci] = j; }
+    __syncthreads();
+  }
+  // keys[0..m) = orderable exact distance, pos_s[0..m) = global bin j -> chromosome-excluded position
+  for (int i = tid; i < m; i += RR_THREADS) {
+    int j = pos_s[i];
+    pos_s[i] = j < cs ? j : j - (ce - cs);
+  }
+  const int p2m = next_pow2(m < 2 ? 2 : m);
+  for (int i = m + tid; i < p2m; i += RR_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
+  __syncthreads();
+  bitonic_sort_dpos(keys, pos_s, p2m);
+
+  // a-posteriori completeness check: exact d_(k) + eps must stay below bound + |a|^2 - eps
+  if (tid == 0 && tot > k) {
+    uint64_t kk = keys[k - 1];
+    uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
+    double dk = __longlong_as_double((long long)u);
+    double an = (double)pv.norm[row];
+    if (!(dk - an + s_eps < s_bound)) s_fail = 1;
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) fail_flags[lrow] = 1;
+    return;
+  }
+  const uint64_t key_1e10 = f64_key(1e10);
+  for (int t = tid; t < k; t += RR_THREADS) {
+    bool have = t < m && keys[t] < key_1e10;
+    if (have) {
+      uint64_t kk = keys[t];
+      uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
+      od[t] = __longlong_as_double((long long)u);
+      oi[t] = pos_s[t];
+    } else {
+      od[t] = 1e10;
+      oi[t] = -1;
+    }
+  }
+}
+
+int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nsplit, const int64_t* cum_dev,
+                  int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
+                  int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
+                  int32_t plan_len, cudaStream_t st) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0) return 0;
+  if (nsplit * WCX_CAND_KEEP > RR_MAXC) { set_error("rerank: nsplit too large"); return 1; }
+  size_t smem = sizeof(double) * ((pv.s + 1) & ~1) + RR_MAXC * (8 + 4) + sizeof(int32_t) * 3 * plan_len;
+  static size_t attr = 0;
+  if (smem > attr) {
+    WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  WCX_CUDA_OK(cudaMemsetAsync(fail_flags, 0, sizeof(int32_t) * rows, st));
+  rerank_kernel<<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nsplit, cum_dev, nchr, row_begin, k, gonosomal,
+                                                          idx_out, dist_out, fail_flags, sum_plan, plan_len);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// brute-force exact rows: one CTA per listed row; all N candidate distances in float64 into
+// `scratch`, then an exact (distance, position) top-k by 64-bit key bisection.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RR_THREADS)
+exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t* __restrict__ cum, int nchr,
+                  int64_t row_begin, const int32_t* __restrict__ rows_list, int k, int32_t* __restrict__ idx_out,
+                  double* __restrict__ dist_out, double* __restrict__ scratch, const int32_t* __restrict__ plan_g,
+                  int plan_len) {
+  extern __shared__ unsigned char rr_smem[];
+  double* a_s = reinterpret_cast<double*>(rr_smem);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((s + 1) & ~1));  // [1024]
+  int32_t* pos_s = reinterpret_cast<int32_t*>(keys + 1024);              // [1024]
+  int32_t* plan = pos_s + 1024;
+  __shared__ int s_cs, s_ce, s_cnt;
+  __shared__ unsigned long long s_count;
+  __shared__ int s_scan[RR_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t lrow = rows_list[blockIdx.x];
+  const int64_t row = row_begin + lrow;
+  uint64_t* dk = reinterpret_cast<uint64_t*>(scratch) + (int64_t)blockIdx.x * n;  // orderable keys of d
+
+  if (tid == 0) {
+    int c = 0;
+    while (c < nchr && cum[c] <= row) c++;
+    s_cs = (int)(c == 0 ? 0 : cum[c - 1]);
+    s_ce = (int)cum[c];
+  }
+  for (int i = tid; i < s; i += RR_THREADS) a_s[i] = x[row * s + i];
+  for (int i = tid; i < 3 * plan_len; i += RR_THREADS) plan[i] = plan_g[i];
+  __syncthreads();
+  const int cs = s_cs, ce = s_ce;
+  const int quad = tid >> 2, l = tid & 3;
+  const uint64_t key_1e10 = f64_key(1e10);
+  for (int64_t j0 = 0; j0 < n; j0 += RR_THREADS / 4) {
+    int64_t j = j0 + quad;
+    int64_t jj = j < n ? j : n - 1;
+    double d = exact_sqdist_quad(a_s, x + jj * s, plan, plan_len, l);
+    if (l == 0 && j < n) {
+      bool excluded = (j >= cs && j < ce) || !(d < 1e10);  // own chromosome, NaN, >= 1e10: never inserted
+      dk[j] = excluded ? ~0ull : f64_key(d);
+    }
+  }
+  __syncthreads();
+  // number of valid candidates
+  unsigned long long loc = 0;
+  for (int64_t j = tid; j < n; j += RR_THREADS) loc += (dk[j] < key_1e10) ? 1 : 0;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  atomicAdd(&s_count, loc);
+  __syncthreads();
+  const long long valid = (long long)s_count;
+  const int kk = valid < k ? (int)valid : k;  // entries to emit
+  uint64_t T = 0;                             // kk-th smallest key
+  if (kk > 0) {
+    for (int bit = 63; bit >= 0; bit--) {
+      uint64_t trial = T | (1ull << bit);
+      loc = 0;
+      for (int64_t j = tid; j < n; j += RR_THREADS) loc += (dk[j] < trial) ? 1 : 0;
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+      atomicAdd(&s_count, loc);
+      __syncthreads();
+      if ((long long)s_count < kk) T = trial;
+    }
+  }
+  // collect: strictly below T (any order), then ties in ascending position until kk entries
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (kk > 0) {
+    for (int64_t j = tid; j < n; j += RR_THREADS) {
+      if (dk[j] < T) {
+        int p = atomicAdd(&s_cnt, 1);
+        keys[p] = dk[j];
+        pos_s[p] = (int)(j < cs ? j : j - (ce - cs));
+      }
+    }
+    __syncthreads();
+    int have = s_cnt;
+    for (int64_t j0 = 0; j0 < n && have < kk; j0 += RR_THREADS) {
+      int64_t j = j0 + tid;
+      int f = (j < n && dk[j] == T) ? 1 : 0;
+      s_scan[tid] = f;
+      __syncthreads();
+      // inclusive scan (Hillis-Steele)
+      for (int o = 1; o < RR_THREADS; o <<= 1) {
+        int v = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+      }
+      int p = have + s_scan[tid] - 1;
+      if (f && p < kk) {
+        keys[p] = T;
+        pos_s[p] = (int)(j < cs ? j : j - (ce - cs));
+      }
+      have += s_scan[RR_THREADS - 1];
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  const int p2 = next_pow2(kk < 2 ? 2 : kk);
+  for (int i = kk + tid; i < p2; i += RR_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
+  __syncthreads();
+  bitonic_sort_dpos(keys, pos_s, p2);
+  int32_t* oi = idx_out + lrow * k;
+  double* od = dist_out + lrow * k;
+  for (int t = tid; t < k; t += RR_THREADS) {
+    if (t < kk) {
+      uint64_t q = keys[t];
+      uint64_t u = (q & 0x8000000000000000ull) ? (q & 0x7fffffffffffffffull) : ~q;
+      od[t] = __longlong_as_double((long long)u);
+      oi[t] = pos_s[t];
+    } else {
+      od[t] = 1e10;
+      oi[t] = -1;
+    }
+  }
+}
+
+int launch_exact_rows(const double* x, int64_t n, int32_t s, const int64_t* cum_dev, int32_t nchr,
+                      int64_t row_begin, const int32_t* fail_rows, int32_t nfail, int32_t k, int32_t* idx_out,
+                      double* dist_out, double* scratch, const int32_t* sum_plan, int32_t plan_len,
+                      cudaStream_t st) {
+  if (nfail <= 0) return 0;
+  if (k > 1024) { set_error("exact_rows: k > 1024 unsupported"); return 1; }
+  size_t smem = sizeof(double) * ((s + 1) & ~1) + 1024 * (8 + 4) + sizeof(int32_t) * 3 * plan_len;
+  static size_t attr = 0;
+  if (smem > attr) {
+    WCX_CUDA_OK(cudaFuncSetAttribute(exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  exact_rows_kernel<<<nfail, RR_THREADS, smem, st>>>(x, n, s, cum_dev, nchr, row_begin, fail_rows, k, idx_out,
+                                                     dist_out, scratch, sum_plan, plan_len);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace wcx

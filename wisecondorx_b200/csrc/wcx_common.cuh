@@ -1,0 +1,83 @@
+// Shared declarations for the wisecondorx_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#define WCX_CAND_CAP 1024   // per (row, column-split) candidate buffer capacity
+#define WCX_CAND_KEEP 512   // entries kept by a compaction (approximate top-KEEP)
+#define WCX_TILE_M 128      // target rows per work item
+#define WCX_TILE_N_SIMT 128 // candidate columns per tile, CUDA-core kernel
+#define WCX_TILE_N_TC 256   // candidate columns per tile, tcgen05 kernel
+#define WCX_KBLOCK 32       // K elements (tf32) per pipeline stage = one 128-byte swizzle row
+
+namespace wcx {
+
+void set_error(const std::string& msg);
+
+#define WCX_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      wcx::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +  \
+                     __FILE__ + ":" + std::to_string(__LINE__));                           \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+// One work item of the distance/top-k sweep: TILE_M target rows of one chromosome against the
+// candidate column tiles [ct_begin, ct_end) (tile width depends on the kernel).
+struct WorkItem {
+  int32_t row0;     // first target row (global bin index)
+  int32_t nrows;    // <= WCX_TILE_M
+  int32_t chr_s;    // [chr_s, chr_e) = the target rows' own chromosome: excluded candidates
+  int32_t chr_e;
+  int32_t ct_begin; // candidate column tile range of this split
+  int32_t ct_end;
+  int32_t slot0;    // candidate-list slot of row0 (slot = (row - row_begin) * nsplit + split)
+  int32_t slot_stride;  // = nsplit
+};
+
+// Device-side view of the prepared (centred, tf32-rounded) matrix
+struct PrepView {
+  const float* xc;     // [n_pad, k_pad] row-major, zero padded
+  const float* norm;   // [n_pad]  sum_s xc^2 (fp32)
+  int64_t n;           // bins
+  int64_t n_pad;
+  int32_t s;           // samples
+  int32_t k_pad;       // S rounded up to WCX_KBLOCK
+};
+
+struct CandView {
+  float* val;      // [slots, CAP]   v = norm[j] - 2 * dot(i, j)
+  int32_t* idx;    // [slots, CAP]   global candidate bin j
+  int32_t* cnt;    // [slots]
+  float* cut;      // [slots]        every non-listed candidate of the slot has v >= cut
+};
+
+// ---- newref kernels (host launchers; all asynchronous on `st`) ---------------------------
+int launch_col_stats(const double* x, int64_t n, int32_t s, double* colsum, double* colcnt, cudaStream_t st);
+int launch_center_round(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
+                        float* xc, float* norm, int64_t n_pad, int32_t k_pad, cudaStream_t st);
+int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m,
+                          double* xt, cudaStream_t st);
+int launch_dist_topk_simt(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
+                          int32_t* work_counter, cudaStream_t st);
+int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
+                        int32_t* work_counter, void* tmap_storage, cudaStream_t st);
+int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host);
+int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nsplit, const int64_t* cum_dev,
+                  int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
+                  int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
+                  int32_t plan_len, cudaStream_t st);
+int launch_exact_rows(const double* x, int64_t n, int32_t s, const int64_t* cum_dev, int32_t nchr,
+                      int64_t row_begin, const int32_t* fail_rows, int32_t nfail, int32_t k,
+                      int32_t* idx_out, double* dist_out, double* scratch, const int32_t* sum_plan,
+                      int32_t plan_len, cudaStream_t st);
+int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t row_begin, int64_t row_end,
+                       int32_t k, int32_t m, double* out, cudaStream_t st);
+
+// NumPy pairwise-summation plan for a reduction of length s (see rerank.cu)
+int build_sum_plan(int32_t s, int32_t* plan, int32_t cap);
+
+}  // namespace wcx

@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference's newref numeric tools (newref_tools.py) on top of the
+C-ABI.  Same names, argument meaning and return types as the reference:
+
+    get_reference(pca_corrected_data, masked_bins_per_chr, masked_bins_per_chr_cum,
+                  ref_size, part, split_parts) -> (int32[rows,k], float64[rows,k], float64[rows,M])
+
+(reference newref_tools.py:155-224).  The null-sample draw uses Python's global ``random`` exactly
+like the reference (``random.sample(range(S), min(S, 100))``, one draw per call, :214-217), so a
+caller that seeds ``random`` gets the reference's columns.
+"""
+from __future__ import annotations
+
+import ctypes
+import random
+
+import numpy as np
+
+from . import _lib
+
+
+def _get_part(partnum, outof, bincount):
+    """Row range of part ``partnum`` (0-based) of ``outof`` (reference newref_tools.py:244-247)."""
+    start_bin = int(bincount / float(outof) * partnum)
+    end_bin = int(bincount / float(outof) * (partnum + 1))
+    return start_bin, end_bin
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class NewrefEngine:
+    """Device-resident state for repeated get_reference calls on one matrix."""
+
+    def __init__(self, device: int = 0, ctx: _lib.Context | None = None):
+        self.ctx = ctx or _lib.default_context(device)
+        self.n = self.s = 0
+
+    def load(self, x, per, cum, on_device_ptr: int | None = None, shape=None):
+        L = _lib.load()
+        per = np.ascontiguousarray(per, dtype=np.int64)
+        cum = np.ascontiguousarray(cum, dtype=np.int64)
+        if on_device_ptr is not None:
+            n, s = shape
+            _lib.check(L.wcx_newref_load(self.ctx.handle, ctypes.c_void_p(on_device_ptr), n, s, _ptr(per),
+                                         _ptr(cum), len(cum), 1))
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            n, s = x.shape
+            _lib.check(L.wcx_newref_load(self.ctx.handle, _ptr(x), n, s, _ptr(per), _ptr(cum), len(cum), 0))
+        self.n, self.s = int(n), int(s)
+
+    def topk(self, row_begin, row_end, ref_size, kernel=_lib.KERNEL_AUTO, out=None, device_out=None):
+        L = _lib.load()
+        rows = row_end - row_begin
+        if device_out is not None:
+            ip, dp = device_out
+            _lib.check(L.wcx_newref_topk(self.ctx.handle, row_begin, row_end, ref_size, kernel,
+                                         ctypes.c_void_p(ip), ctypes.c_void_p(dp), 1))
+            return None
+        if out is None:
+            idx = np.empty((rows, ref_size), dtype=np.int32)
+            dist = np.empty((rows, ref_size), dtype=np.float64)
+        else:
+            idx, dist = out
+        _lib.check(L.wcx_newref_topk(self.ctx.handle, row_begin, row_end, ref_size, kernel, _ptr(idx), _ptr(dist), 0))
+        return idx, dist
+
+    def null_ratios(self, row_begin, row_end, ref_size, sample_ids, idx=None, out=None, device_out=None):
+        L = _lib.load()
+        ids = np.ascontiguousarray(sample_ids, dtype=np.int32)
+        rows = row_end - row_begin
+        iptr = None if idx is None else _ptr(np.ascontiguousarray(idx, dtype=np.int32))
+        if device_out is not None:
+            _lib.check(L.wcx_newref_null_ratios(self.ctx.handle, iptr, 0, row_begin, row_end, ref_size, _ptr(ids),
+                                                len(ids), ctypes.c_void_p(device_out), 1))
+            return None
+        if out is None:
+            out = np.empty((rows, len(ids)), dtype=np.float64)
+        _lib.check(L.wcx_newref_null_ratios(self.ctx.handle, iptr, 0, row_begin, row_end, ref_size, _ptr(ids),
+                                            len(ids), _ptr(out), 0))
+        return out
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        _lib.check(_lib.load().wcx_newref_stats(self.ctx.handle, _ptr(out)))
+        return {"work_items": int(out[0]), "exact_fallback_rows": int(out[1]), "launches": int(out[2]),
+                "column_splits": int(out[3]), "kernel": int(out[4])}
+
+    def stage_ms(self):
+        out = np.zeros(8, dtype=np.float64)
+        _lib.check(_lib.load().wcx_newref_stage_ms(self.ctx.handle, _ptr(out)))
+        return {"sweep": out[0], "rerank": out[1], "exact_rows": out[2], "null_ratios": out[3], "prep": out[4]}
+
+
+def get_reference(pca_corrected_data, masked_bins_per_chr, masked_bins_per_chr_cum, ref_size, part,
+                  split_parts, kernel=_lib.KERNEL_AUTO, device: int = 0, sample_ids=None):
+    """Drop-in for the reference's get_reference (newref_tools.py:155): within-sample reference
+    bins, their distances and the null ratios for part ``part`` (1-based) of ``split_parts``."""
+    x = np.ascontiguousarray(pca_corrected_data, dtype=np.float64)
+    cum = np.asarray(masked_bins_per_chr_cum, dtype=np.int64)
+    bincount = int(cum[-1])
+    start_num, end_num = _get_part(part - 1, split_parts, bincount)
+    n_samples = x.shape[1]
+    if sample_ids is None:
+        # same draw as the reference: one random.sample per get_reference call (:214-217)
+        sample_ids = random.sample(range(n_samples), min(n_samples, 100))
+    eng = NewrefEngine(device)
+    eng.load(x, masked_bins_per_chr, cum)
+    idx, dist = eng.topk(start_num, end_num, ref_size, kernel)
+    nr = eng.null_ratios(start_num, end_num, ref_size, sample_ids)
+    return idx, dist, nr
