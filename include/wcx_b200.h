@@ -77,7 +77,8 @@ int wcx_get_reference(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, const
 
 /* Counters of the last wcx_newref_topk call: out[0] = work items, out[1] = rows recomputed by the
  * exact brute-force path, out[2] = kernel launches issued since wcx_create, out[3] = column
- * splits per row, out[4] = sweep kernel used, out[5..7] reserved. */
+ * splits per row, out[4] = sweep kernel used, out[5] = exact list compactions, out[6] = streamed
+ * (overflow) compactions, out[7] = ladder threshold steps. */
 int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
 
 /* Device time in milliseconds of the stages of the last wcx_newref_topk call, measured with CUDA
@@ -86,9 +87,49 @@ int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
  * wcx_newref_load preparation kernels, out[5..7] reserved. */
 int wcx_newref_stage_ms(wcx_ctx* ctx, double* out8);
 
+/* ---- predict ------------------------------------------------------------------------------
+ * Replaces normalize (predict_control.py:21-39) = coverage_normalize_and_mask (predict_tools.py:32),
+ * project_pc (:56), get_weights (:152), get_optimal_cutoff (:74), normalize_repeat/_normalize_once
+ * (:94-142); and get_z_score (overall_tools.py:88-119).  All float64.
+ *
+ * A context holds up to three device-resident reference sets (set_id 0 = autosomal keys "",
+ * 1 = ".F", 2 = ".M" of the reference .npz): indexes int32 [n, k], distances float64 [n, k],
+ * masked_bins_per_chr(_cum) (nchr), pca_components float64 [ncomp, n], pca_mean [n], and
+ * mask_pos int32 [n] = positions of the True entries of the set's `mask` (np.flatnonzero) in the
+ * concatenated unmasked bin axis of length bins_total = sum(bins_per_chr). */
+int wcx_predict_load_ref(wcx_ctx* ctx, int32_t set_id, const int32_t* idx, const double* dist, int64_t n,
+                         int32_t k, const int64_t* per, const int64_t* cum, int32_t nchr,
+                         const double* pca_components, const double* pca_mean, int32_t ncomp,
+                         const int32_t* mask_pos, int64_t bins_total);
+/* get_weights: out[i] = 1 / mean(sqrt(distances[i, :])), out float64 [n] (host). */
+int wcx_predict_weights(wcx_ctx* ctx, int32_t set_id, double* out);
+/* get_optimal_cutoff over the set's distances (the reference always uses set 0). */
+int wcx_predict_optimal_cutoff(wcx_ctx* ctx, int32_t set_id, int32_t repeats, double* cutoff_out);
+/* coverage normalisation + PCA projection + the three within-sample normalisation passes for a
+ * batch of B samples.  raw float64 [B, bins_total]: per-chromosome read counts padded/truncated to
+ * the set's bins_per_chr and concatenated (predict_tools.py:37-44).  cp/ct as in
+ * predict_control.py:22-29 (cp = 0, ct = 0 for autosomes; cp = 22, ct = cum[21] for gonosomes).
+ * Outputs (host): z, r, nref float64 [B, n - ct]; m_lr, m_z float64 [B]. */
+int wcx_predict_normalize(wcx_ctx* ctx, int32_t set_id, const double* raw, int32_t b, double cutoff,
+                          int32_t cp, int64_t ct, double* z, double* r, double* nref, double* m_lr,
+                          double* m_z);
+/* get_z_score: nr = null ratios float64 [n_masked, m]; inflate_pos int32 [bins_total] = row of nr
+ * for each unmasked bin or -1; r, w float64 [bins_total] = post-processed log2 ratios (0 = no
+ * data) and weights; segments as [start, end) offsets into the concatenated bin axis with their
+ * ratio seg_r.  z_out float64 [nseg]; NaN where the reference returns the string "nan". */
+int wcx_segment_zscore(wcx_ctx* ctx, const double* nr, int64_t n_masked, int32_t m,
+                       const int32_t* inflate_pos, const double* r, const double* w, int64_t bins_total,
+                       const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out);
+/* Device milliseconds of the last predict calls: out[0] = coverage + projection, out[1] = the
+ * three normalisation passes + medians, out[2] = segment z-score, out[3] reserved. */
+int wcx_predict_stage_ms(wcx_ctx* ctx, double* out4);
+
 /* Test hook: raw tensor-core accumulators <Xc[row0 + i], Xc[col0 + j]> of one 128 x 256 tile,
  * written to acc_out [128 * 256] (host). */
 int wcx_debug_tc_tile(wcx_ctx* ctx, int64_t row0, int64_t col0, float* acc_out);
+/* Test hook: final length of the first `nslots` candidate lists of the last wcx_newref_topk call
+ * (lists per row = out[3] of wcx_newref_stats x 2 for the tcgen05 kernel). */
+int wcx_debug_list_counts(wcx_ctx* ctx, int32_t* cnt_out, int64_t nslots);
 /* Test hook: prepared operands.  xc_out [n, k_pad] (host, may be NULL), norm_out [n] (host). */
 int wcx_debug_prep(wcx_ctx* ctx, float* xc_out, float* norm_out, int32_t* k_pad_out);
 

@@ -50,6 +50,14 @@ def load():
     L.wcx_newref_stage_ms.argtypes = [vp, vp]
     L.wcx_debug_tc_tile.argtypes = [vp, i64, i64, vp]
     L.wcx_debug_prep.argtypes = [vp, vp, vp, vp]
+    L.wcx_debug_list_counts.argtypes = [vp, vp, i64]
+    f64 = ctypes.c_double
+    L.wcx_predict_load_ref.argtypes = [vp, i32, vp, vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, i64]
+    L.wcx_predict_weights.argtypes = [vp, i32, vp]
+    L.wcx_predict_optimal_cutoff.argtypes = [vp, i32, i32, ctypes.POINTER(f64)]
+    L.wcx_predict_normalize.argtypes = [vp, i32, vp, i32, f64, i32, i64, vp, vp, vp, vp, vp]
+    L.wcx_segment_zscore.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, vp, i32, vp]
+    L.wcx_predict_stage_ms.argtypes = [vp, vp]
     _lib = L
     return L
 

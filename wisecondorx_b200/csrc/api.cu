@@ -7,6 +7,7 @@
 
 #include "../../include/wcx_b200.h"
 #include "wcx_common.cuh"
+#include "predict.cuh"
 
 namespace wcx {
 static thread_local std::string g_error;
@@ -40,6 +41,14 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct RefSet {
+  DevBuf idx, dist, cum, comps, mean, mask_pos;
+  int64_t n = 0, bins_total = 0;
+  int32_t k = 0, nchr = 0, ncomp = 0;
+  std::vector<int64_t> cum_h;
+  bool loaded = false;
+};
+
 struct wcx_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -47,8 +56,8 @@ struct wcx_ctx {
   cudaEvent_t ev[8] = {};
   // newref state
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
-  DevBuf x_buf, xc, norm, colsum, colcnt, cum_dev, items_dev, counter, cand_val, cand_idx, cand_cnt, cand_cut;
-  DevBuf fail, fail_rows, plan_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg;
+  DevBuf x_buf, xc, norm, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
+  DevBuf fail, fail_rows, plan_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg, diag;
   int64_t n = 0, n_pad = 0;
   int32_t s = 0, k_pad = 0, nchr = 0;
   std::vector<int64_t> per, cum;
@@ -61,6 +70,11 @@ struct wcx_ctx {
   int64_t stats[8] = {};
   double stage_ms[8] = {};
   int64_t launches = 0;
+  // predict state
+  RefSet ref[3];
+  DevBuf p_partial, p_totals, p_tdots, p_state, p_raw, p_x, p_copy_a, p_copy_b, p_z, p_r, p_n, p_mlr, p_mz, p_w;
+  DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out;
+  double predict_ms[4] = {};
 };
 
 static PrepView prep_view(const wcx_ctx* c) {
@@ -110,9 +124,13 @@ void wcx_destroy(wcx_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
-                    &c->cand_val, &c->cand_idx, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev,
-                    &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg})
+                    &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev,
+                    &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->p_partial,
+                    &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
+                    &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out})
     b->release();
+  for (auto& r : c->ref)
+    for (DevBuf* b : {&r.idx, &r.dist, &r.cum, &r.comps, &r.mean, &r.mask_pos}) b->release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -189,7 +207,8 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   return 0;
 }
 
-static void build_items(const wcx_ctx* c, int64_t rb, int64_t re, int tile_n, int nsplit, std::vector<WorkItem>& items) {
+static void build_items(const wcx_ctx* c, int64_t rb, int64_t re, int tile_n, int nsplit, int lists_per_split,
+                        std::vector<WorkItem>& items) {
   const int64_t n = c->n;
   const int nct = (int)((n + tile_n - 1) / tile_n);
   const bool gon = c->nchr > 22;
@@ -207,8 +226,8 @@ static void build_items(const wcx_ctx* c, int64_t rb, int64_t re, int tile_n, in
         w.chr_e = (int32_t)ce;
         w.ct_begin = (int)((int64_t)nct * q / nsplit);
         w.ct_end = (int)((int64_t)nct * (q + 1) / nsplit);
-        w.slot0 = (int32_t)((r0 - rb) * nsplit + q);
-        w.slot_stride = nsplit;
+        w.slot0 = (int32_t)((r0 - rb) * nsplit * lists_per_split + q * lists_per_split);
+        w.slot_stride = nsplit * lists_per_split;
         items.push_back(w);
       }
     }
@@ -243,14 +262,12 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
       fail_list.push_back((int32_t)(r - rb));
     }
     if (gon) {
-      CandView cv0{nullptr, nullptr, nullptr, nullptr};
       // rerank kernel with nsplit = 0 would touch lists; fill placeholders on the host side instead
       std::vector<int32_t> hi((size_t)rows * k, 0);
       std::vector<double> hd((size_t)rows * k, 1.0);
       WCX_CUDA_OK(cudaMemcpyAsync(c->idx_dev.p, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, st));
       WCX_CUDA_OK(cudaMemcpyAsync(c->dist_dev.p, hd.data(), hd.size() * 8, cudaMemcpyHostToDevice, st));
       WCX_CUDA_OK(cudaStreamSynchronize(st));
-      (void)cv0;
     }
   } else {
     const int tile_n = kernel == WCX_KERNEL_SIMT ? WCX_TILE_N_SIMT : WCX_TILE_N_TC;
@@ -258,23 +275,25 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device);
     // column splits: enough work items to balance a persistent grid when the part has few row tiles
     std::vector<WorkItem> items;
-    build_items(c, rb, re, tile_n, 1, items);
+    const int lps = kernel == WCX_KERNEL_SIMT ? 1 : 2;  // the tcgen05 kernel keeps one list per epilogue group
+    build_items(c, rb, re, tile_n, 1, lps, items);
     const int64_t row_tiles = (int64_t)items.size();
     int nsplit = 1;
     const int nct = (int)((c->n + tile_n - 1) / tile_n);
-    while (nsplit < 4 && row_tiles * nsplit < 4 * dev_sms && nct / (nsplit * 2) >= 4) nsplit *= 2;
+    while (nsplit < 2 && row_tiles * nsplit < 4 * dev_sms && nct / (nsplit * 2) >= 8) nsplit *= 2;
     if (nsplit > 1) {
       items.clear();
-      build_items(c, rb, re, tile_n, nsplit, items);
+      build_items(c, rb, re, tile_n, nsplit, lps, items);
     }
-    const size_t slots = (size_t)rows * nsplit;
-    if (c->cand_val.ensure(sizeof(float) * slots * WCX_CAND_CAP) || c->cand_idx.ensure(sizeof(int32_t) * slots * WCX_CAND_CAP) ||
-        c->cand_cnt.ensure(sizeof(int32_t) * slots) || c->cand_cut.ensure(sizeof(float) * slots))
+    const size_t slots = (size_t)rows * nsplit * lps;
+    if (c->cand_ent.ensure(sizeof(uint2) * slots * WCX_CAND_CAP) || c->cand_cnt.ensure(sizeof(int32_t) * slots) || c->cand_cut.ensure(sizeof(float) * slots))
       return 1;
     if (c->items_dev.ensure(sizeof(WorkItem) * std::max<size_t>(items.size(), 1)) || c->counter.ensure(sizeof(int32_t))) return 1;
     if (!items.empty())
       WCX_CUDA_OK(cudaMemcpyAsync(c->items_dev.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
-    CandView cv{c->cand_val.as<float>(), c->cand_idx.as<int32_t>(), c->cand_cnt.as<int32_t>(), c->cand_cut.as<float>()};
+    if (c->diag.ensure(sizeof(int32_t) * 8)) return 1;
+    WCX_CUDA_OK(cudaMemsetAsync(c->diag.p, 0, sizeof(int32_t) * 8, st));
+    CandView cv{c->cand_ent.as<uint2>(), c->cand_cnt.as<int32_t>(), c->cand_cut.as<float>(), c->diag.as<int32_t>()};
     WCX_CUDA_OK(cudaMemsetAsync(c->cand_cnt.p, 0, sizeof(int32_t) * slots, st));
     WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
     if (kernel == WCX_KERNEL_SIMT) {
@@ -283,12 +302,14 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
       if (launch_dist_topk_tc(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), c->tmap, st)) return 1;
     }
     WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
-    if (launch_rerank(c->d_x, pv, cv, nsplit, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
+    if (launch_rerank(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
                       c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->plan_dev.as<int32_t>(), c->plan_len, st))
       return 1;
     WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
     c->launches += 2;
     std::vector<int32_t> flags((size_t)rows);
+    int32_t diag_h[8] = {};
+    WCX_CUDA_OK(cudaMemcpyAsync(diag_h, c->diag.p, sizeof(diag_h), cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaMemcpyAsync(flags.data(), c->fail.p, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < rows; i++)
@@ -300,6 +321,9 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     c->stage_ms[1] = ms;
     c->stats[0] = (int64_t)items.size();
     c->stats[3] = nsplit;
+    c->stats[5] = diag_h[0];
+    c->stats[6] = diag_h[1];
+    c->stats[7] = diag_h[2];
   }
   c->stats[4] = kernel;
   c->stats[1] = (int64_t)fail_list.size();
@@ -410,19 +434,27 @@ int wcx_debug_tc_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) {
   cudaStream_t st = c->stream;
   WorkItem w;
   w.row0 = (int32_t)row0; w.nrows = WCX_TILE_M; w.chr_s = -1; w.chr_e = -1;
-  w.ct_begin = (int)(col0 / WCX_TILE_N_TC); w.ct_end = w.ct_begin + 1; w.slot0 = 0; w.slot_stride = 1;
-  const size_t slots = WCX_TILE_M;
-  if (c->cand_val.ensure(sizeof(float) * slots * WCX_CAND_CAP) || c->cand_idx.ensure(sizeof(int32_t) * slots * WCX_CAND_CAP) ||
-      c->cand_cnt.ensure(sizeof(int32_t) * slots) || c->cand_cut.ensure(sizeof(float) * slots) ||
+  w.ct_begin = (int)(col0 / WCX_TILE_N_TC); w.ct_end = w.ct_begin + 1; w.slot0 = 0; w.slot_stride = 2;
+  const size_t slots = 2 * WCX_TILE_M;
+  if (c->cand_ent.ensure(sizeof(uint2) * slots * WCX_CAND_CAP) || c->cand_cnt.ensure(sizeof(int32_t) * slots) || c->cand_cut.ensure(sizeof(float) * slots) ||
       c->items_dev.ensure(sizeof(WorkItem)) || c->dbg.ensure(sizeof(float) * WCX_TILE_M * WCX_TILE_N_TC))
     return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->items_dev.p, &w, sizeof(w), cudaMemcpyHostToDevice, st));
-  CandView cv{c->cand_val.as<float>(), c->cand_idx.as<int32_t>(), c->cand_cnt.as<int32_t>(), c->cand_cut.as<float>()};
+  CandView cv{c->cand_ent.as<uint2>(), c->cand_cnt.as<int32_t>(), c->cand_cut.as<float>(), nullptr};
   PrepView pv = prep_view(c);
   if (launch_dist_topk_tc_debug(pv, c->items_dev.as<WorkItem>(), 1, cv, c->tmap, c->dbg.as<float>(), st)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(acc_out, c->dbg.p, sizeof(float) * WCX_TILE_M * WCX_TILE_N_TC, cudaMemcpyDeviceToHost, st));
   WCX_CUDA_OK(cudaStreamSynchronize(st));
   c->last_rb = c->last_re = -1;
+  return 0;
+}
+
+int wcx_debug_list_counts(wcx_ctx* c, int32_t* cnt_out, int64_t nslots) {
+  if (!c || !cnt_out) { set_error("wcx_debug_list_counts: bad argument"); return 1; }
+  if ((size_t)nslots * sizeof(int32_t) > c->cand_cnt.cap) { set_error("wcx_debug_list_counts: more slots than allocated"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  WCX_CUDA_OK(cudaMemcpyAsync(cnt_out, c->cand_cnt.p, sizeof(int32_t) * (size_t)nslots, cudaMemcpyDeviceToHost, c->stream));
+  WCX_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -433,6 +465,165 @@ int wcx_debug_prep(wcx_ctx* c, float* xc_out, float* norm_out, int32_t* k_pad_ou
   if (xc_out) WCX_CUDA_OK(cudaMemcpyAsync(xc_out, c->xc.p, sizeof(float) * (size_t)c->n * c->k_pad, cudaMemcpyDeviceToHost, c->stream));
   if (norm_out) WCX_CUDA_OK(cudaMemcpyAsync(norm_out, c->norm.p, sizeof(float) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
   WCX_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ================================================================================================
+// predict
+// ================================================================================================
+static int h2d(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
+  if (b.ensure(bytes ? bytes : 1)) return 1;
+  if (bytes) WCX_CUDA_OK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+int wcx_predict_load_ref(wcx_ctx* c, int32_t set_id, const int32_t* idx, const double* dist, int64_t n, int32_t k,
+                         const int64_t* per, const int64_t* cum, int32_t nchr, const double* comps, const double* mean,
+                         int32_t ncomp, const int32_t* mask_pos, int64_t bins_total) {
+  if (!c || set_id < 0 || set_id > 2 || !idx || !dist || !per || !cum || !comps || !mean || !mask_pos) {
+    set_error("wcx_predict_load_ref: bad argument");
+    return 1;
+  }
+  if (n <= 0 || k <= 0 || k > 512 || nchr <= 0 || ncomp <= 0 || ncomp > 8 || cum[nchr - 1] != n) {
+    set_error("wcx_predict_load_ref: inconsistent shapes (need 0 < k <= 512, ncomp <= 8, cum[-1] == n)");
+    return 1;
+  }
+  for (int i = 0; i < nchr; i++)
+    if (cum[i] - (i ? cum[i - 1] : 0) != per[i]) { set_error("wcx_predict_load_ref: per/cum inconsistent"); return 1; }
+  for (int64_t i = 0; i < n; i++)
+    if (mask_pos[i] < 0 || mask_pos[i] >= bins_total) { set_error("wcx_predict_load_ref: mask position out of range"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  RefSet& r = c->ref[set_id];
+  r.loaded = false;
+  if (h2d(r.idx, idx, sizeof(int32_t) * (size_t)n * k, st) || h2d(r.dist, dist, sizeof(double) * (size_t)n * k, st) ||
+      h2d(r.cum, cum, sizeof(int64_t) * nchr, st) || h2d(r.comps, comps, sizeof(double) * (size_t)ncomp * n, st) ||
+      h2d(r.mean, mean, sizeof(double) * (size_t)n, st) || h2d(r.mask_pos, mask_pos, sizeof(int32_t) * (size_t)n, st))
+    return 1;
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  r.n = n; r.k = k; r.nchr = nchr; r.ncomp = ncomp; r.bins_total = bins_total;
+  r.cum_h.assign(cum, cum + nchr);
+  r.loaded = true;
+  return 0;
+}
+
+static RefSet* get_ref(wcx_ctx* c, int32_t set_id) {
+  if (!c || set_id < 0 || set_id > 2 || !c->ref[set_id].loaded) {
+    set_error("predict: reference set not loaded (wcx_predict_load_ref)");
+    return nullptr;
+  }
+  return &c->ref[set_id];
+}
+
+int wcx_predict_weights(wcx_ctx* c, int32_t set_id, double* out) {
+  RefSet* r = get_ref(c, set_id);
+  if (!r || !out) { if (r) set_error("wcx_predict_weights: null output"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (c->p_w.ensure(sizeof(double) * (size_t)r->n)) return 1;
+  if (launch_weights(r->dist.as<double>(), r->n, r->k, c->p_w.as<double>(), st)) return 1;
+  WCX_CUDA_OK(cudaMemcpyAsync(out, c->p_w.p, sizeof(double) * (size_t)r->n, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  c->launches += 1;
+  return 0;
+}
+
+int wcx_predict_optimal_cutoff(wcx_ctx* c, int32_t set_id, int32_t repeats, double* cutoff_out) {
+  RefSet* r = get_ref(c, set_id);
+  if (!r || !cutoff_out || repeats < 0) { if (r) set_error("wcx_predict_optimal_cutoff: bad argument"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (c->p_state.ensure(sizeof(double) * 4) || c->p_partial.ensure(sizeof(double) * (size_t)predict_red_blocks() * 8 * 128)) return 1;
+  if (launch_optimal_cutoff(r->dist.as<double>(), r->n * (int64_t)r->k, repeats, c->p_state.as<double>(), c->p_partial.as<double>(), st)) return 1;
+  WCX_CUDA_OK(cudaMemcpyAsync(cutoff_out, c->p_state.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  c->launches += 4 * repeats;
+  return 0;
+}
+
+int wcx_predict_normalize(wcx_ctx* c, int32_t set_id, const double* raw, int32_t B, double cutoff, int32_t cp, int64_t ct,
+                          double* z, double* rr, double* nref, double* m_lr, double* m_z) {
+  RefSet* r = get_ref(c, set_id);
+  if (!r) return 1;
+  if (!raw || !z || !rr || !nref || !m_lr || !m_z || B <= 0 || B > 128) { set_error("wcx_predict_normalize: bad argument (1 <= B <= 128)"); return 1; }
+  if (cp < 0 || cp > r->nchr || ct != (cp == 0 ? 0 : r->cum_h[cp - 1])) {
+    set_error("wcx_predict_normalize: ct must equal masked_bins_per_chr_cum[cp - 1]");
+    return 1;
+  }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t n = r->n, nout = n - ct;
+  const size_t bn = sizeof(double) * (size_t)B * n, bo = sizeof(double) * (size_t)B * (nout > 0 ? nout : 1);
+  if (c->p_raw.ensure(sizeof(double) * (size_t)B * r->bins_total) || c->p_x.ensure(bn) || c->p_copy_a.ensure(bn) || c->p_copy_b.ensure(bn) ||
+      c->p_z.ensure(bo) || c->p_r.ensure(bo) || c->p_n.ensure(bo) || c->p_mlr.ensure(sizeof(double) * B) || c->p_mz.ensure(sizeof(double) * B) ||
+      c->p_state.ensure(sizeof(double) * 4) || c->p_partial.ensure(sizeof(double) * (size_t)predict_red_blocks() * 8 * 128) ||
+      c->p_totals.ensure(sizeof(double) * 128) || c->p_tdots.ensure(sizeof(double) * 128 * 8))
+    return 1;
+  WCX_CUDA_OK(cudaMemcpyAsync(c->p_raw.p, raw, sizeof(double) * (size_t)B * r->bins_total, cudaMemcpyHostToDevice, st));
+  // the cutoff travels through device memory (state[3]) so the kernels read one source of truth
+  WCX_CUDA_OK(cudaMemcpyAsync(c->p_state.as<double>() + 3, &cutoff, sizeof(double), cudaMemcpyHostToDevice, st));
+  WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
+  if (launch_coverage_project(c->p_raw.as<double>(), B, r->bins_total, r->mask_pos.as<int32_t>(), n, r->comps.as<double>(),
+                              r->mean.as<double>(), r->ncomp, c->p_x.as<double>(), c->p_partial.as<double>(),
+                              c->p_totals.as<double>(), c->p_tdots.as<double>(), st))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
+  if (launch_normalize_repeat(c->p_x.as<double>(), c->p_copy_a.as<double>(), c->p_copy_b.as<double>(), B, n, r->idx.as<int32_t>(),
+                              r->dist.as<double>(), r->k, c->p_state.as<double>() + 3, r->cum.as<int64_t>(), r->nchr, ct,
+                              c->p_z.as<double>(), c->p_r.as<double>(), c->p_n.as<double>(), c->p_mlr.as<double>(),
+                              c->p_mz.as<double>(), st))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
+  if (nout > 0) {
+    WCX_CUDA_OK(cudaMemcpyAsync(z, c->p_z.p, sizeof(double) * (size_t)B * nout, cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaMemcpyAsync(rr, c->p_r.p, sizeof(double) * (size_t)B * nout, cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaMemcpyAsync(nref, c->p_n.p, sizeof(double) * (size_t)B * nout, cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaMemcpyAsync(m_lr, c->p_mlr.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaMemcpyAsync(m_z, c->p_mz.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  }
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->predict_ms[0] = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+  c->predict_ms[1] = ms;
+  c->launches += 13;
+  return 0;
+}
+
+int wcx_segment_zscore(wcx_ctx* c, const double* nr, int64_t n_masked, int32_t m, const int32_t* inflate_pos, const double* r,
+                       const double* w, int64_t bins_total, const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out) {
+  if (!c || !nr || !inflate_pos || !r || !w || !seg_se || !seg_r || !z_out || m <= 0 || m > 128 || nseg < 0) {
+    set_error("wcx_segment_zscore: bad argument (1 <= null samples <= 128)");
+    return 1;
+  }
+  for (int i = 0; i < nseg; i++)
+    if (seg_se[2 * i] < 0 || seg_se[2 * i + 1] > bins_total || seg_se[2 * i] > seg_se[2 * i + 1]) { set_error("wcx_segment_zscore: segment out of range"); return 1; }
+  if (nseg == 0) return 0;
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (h2d(c->z_nr, nr, sizeof(double) * (size_t)n_masked * m, st) || h2d(c->z_pos, inflate_pos, sizeof(int32_t) * (size_t)bins_total, st) ||
+      h2d(c->z_r, r, sizeof(double) * (size_t)bins_total, st) || h2d(c->z_w, w, sizeof(double) * (size_t)bins_total, st) ||
+      h2d(c->z_se, seg_se, sizeof(int64_t) * 2 * (size_t)nseg, st) || h2d(c->z_segr, seg_r, sizeof(double) * (size_t)nseg, st) ||
+      c->z_out.ensure(sizeof(double) * (size_t)nseg))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
+  if (launch_segment_z(c->z_nr.as<double>(), m, c->z_pos.as<int32_t>(), c->z_r.as<double>(), c->z_w.as<double>(),
+                       c->z_se.as<int64_t>(), c->z_segr.as<double>(), nseg, c->z_out.as<double>(), st))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
+  WCX_CUDA_OK(cudaMemcpyAsync(z_out, c->z_out.p, sizeof(double) * (size_t)nseg, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->predict_ms[2] = ms;
+  c->launches += 1;
+  return 0;
+}
+
+int wcx_predict_stage_ms(wcx_ctx* c, double* out4) {
+  if (!c || !out4) { set_error("null argument"); return 1; }
+  std::memcpy(out4, c->predict_ms, sizeof(c->predict_ms));
   return 0;
 }
 

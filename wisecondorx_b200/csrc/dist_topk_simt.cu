@@ -97,8 +97,7 @@ dist_topk_simt_kernel(PrepView pv, const WorkItem* __restrict__ items, int nitem
         float thr = s_thr[row];
         int cnt = s_cnt[row];
         const int64_t slot = (int64_t)w.slot0 + (int64_t)row * w.slot_stride;
-        float* bv = cv.val + slot * WCX_CAND_CAP;
-        int32_t* bi = cv.idx + slot * WCX_CAND_CAP;
+        uint2* be = cv.ent + slot * WCX_CAND_CAP;
 #pragma unroll
         for (int q = 0; q < TN / 32; q++) {
           const int c = q * 32 + lane;
@@ -106,16 +105,13 @@ dist_topk_simt_kernel(PrepView pv, const WorkItem* __restrict__ items, int nitem
           const float v = fmaf(-2.f, Dt[row * LDD + c], pv.norm[gcol]);
           const bool ok = (gcol < pv.n) && !(gcol >= w.chr_s && gcol < w.chr_e) && (v < thr);
           const uint32_t b = __ballot_sync(0xffffffffu, ok);
-          if (ok) {
-            int p = cnt + __popc(b & lt_mask);
-            bv[p] = v;
-            bi[p] = gcol;
-          }
+          if (ok) be[cnt + __popc(b & lt_mask)] = make_uint2(__float_as_uint(v), (uint32_t)gcol);
           cnt += __popc(b);
         }
-        if (cnt > WCX_CAND_CAP - TN) {
-          thr = warp_compact(bv, bi, cnt);
-          cnt = WCX_CAND_KEEP;
+        if (cnt > 1024 - TN) {  // warp_compact handles at most 1024 entries
+          const CompactResult cr = warp_compact<WCX_CAND_KEEP>(be, cnt);
+          thr = cr.thr;
+          cnt = cr.kept;
         }
         if (lane == 0) { s_thr[row] = thr; s_cnt[row] = cnt; }
       }
@@ -129,10 +125,6 @@ dist_topk_simt_kernel(PrepView pv, const WorkItem* __restrict__ items, int nitem
       float thr = s_thr[row];
       int cnt = s_cnt[row];
       const int64_t slot = (int64_t)w.slot0 + (int64_t)row * w.slot_stride;
-      if (cnt > WCX_CAND_KEEP) {
-        thr = warp_compact(cv.val + slot * WCX_CAND_CAP, cv.idx + slot * WCX_CAND_CAP, cnt);
-        cnt = WCX_CAND_KEEP;
-      }
       if (lane == 0) { cv.cnt[slot] = cnt; cv.cut[slot] = thr; }
     }
   }

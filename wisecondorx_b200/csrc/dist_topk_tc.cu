@@ -9,16 +9,25 @@
 // memory tiles.  The epilogue never writes the distance tile anywhere: each epilogue thread
 // owns one target row (= one TMEM lane), pulls 32 accumulator columns at a time with
 // tcgen05.ld, forms v = |b_j|^2 - 2 acc and appends (v, j) to the row's candidate list only if
-// v is below the row's running threshold (about 1 % of the elements).  Lists are compacted
-// warp-cooperatively (candidates.cuh) and finished exactly by rerank.cu.
+// v is below the row's running threshold (1-2 % of the elements).
 //
-// Warp roles (192 + 64 threads, one CTA per SM, persistent over work items):
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      MMA issuer   (one elected lane, tcgen05.mma cta_group::1 kind::tf32, M128 N256 K8)
-//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
-//   warps 4..7  epilogue, warp w owns TMEM lanes 32*(w%4) .. +31
+// Threshold maintenance (candidates.cuh states the invariant).  After the first 768 entries an
+// exact warp-cooperative selection fixes thr and a ladder of four probe values below it; every
+// append counts itself against the probes (4 compares), and when the first probe has seen
+// WCX_CAND_KEEP entries below it thr drops to that probe -- no list traffic at all.  Entries that
+// end up above thr stay in the list (lazy deletion, filtered by rerank.cu); a physical compaction
+// happens only if a list is about to overflow its 2048 slots (rare).
+//
+// Warp roles (384 threads, one CTA per SM, persistent over work items):
+//   warp 0        TMA producer (one elected lane)
+//   warp 1        MMA issuer   (one elected lane, tcgen05.mma cta_group::1 kind::tf32, M128 N256 K8)
+//   warp 2        TMEM allocator (512 columns = two 128x256 fp32 accumulators)
+//   warps 4..7    epilogue group 0: tiles 0,2,4,.. of the CTA (TMEM buffer 0)
+//   warps 8..11   epilogue group 1: tiles 1,3,5,.. of the CTA (TMEM buffer 1)
+//                 warp w owns TMEM lanes 32*(w%4)..+31; each group keeps its own list per row and
+//                 the two groups exchange thresholds through shared memory.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA, 4 stages of 48 KB) and TMEM full/empty
-// mbarriers (MMA <-> epilogue, 2 accumulator buffers).
+// mbarriers (MMA <-> epilogue group).
 #include <cuda.h>
 
 #include "candidates.cuh"
@@ -35,8 +44,12 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * BK * 4;    // 16 KB
 constexpr int B_BYTES = TN * BK * 4;    // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TC_THREADS = 256;
-constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 384;
+constexpr int NORM_BYTES = 8 * TN * 4;  // per-epilogue-warp copy of the tile's candidate norms
+constexpr int THR_BYTES = 2 * TM * 8;   // (item, thr) words exchanged between the two epilogue groups
+constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NORM_BYTES + THR_BYTES;
+constexpr int INIT_N = 512;             // entries collected before the first exact selection
+constexpr int KEEP = WCX_CAND_KEEP_TC;  // per-list guarantee; the row's two lists together hold >= 2 * KEEP
 constexpr uint32_t TMEM_COLS = 512;
 
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=TF32, K-major both,
@@ -125,6 +138,84 @@ __device__ __forceinline__ bool tile_skipped(const WorkItem& w, int ct) {
 
 }  // namespace
 
+// per-row threshold state of one epilogue thread
+struct RowState {
+  float thr, lo;
+  float p0, p1, p2, p3;  // probe ladder, p0 > p1 > p2 > p3, all below thr
+  int c0, c1, c2, c3;    // lower bounds on the number of list entries below each probe
+  int cnt;
+  bool ladder;
+};
+
+// lower thr to the first probe while that probe has enough entries below it
+__device__ __forceinline__ void ladder_advance(RowState& st) {
+  while (st.ladder && st.c0 >= KEEP) {
+    st.thr = st.p0;
+    st.p0 = st.p1; st.p1 = st.p2; st.p2 = st.p3;
+    st.c0 = st.c1; st.c1 = st.c2; st.c2 = st.c3;
+    const float d = (st.thr - st.lo) * 0.125f;
+    st.p3 = st.p2 - d;
+    st.c3 = 0;
+    if (!(d > 0.f)) break;
+  }
+}
+// adopt a lower threshold published by the partner group (valid: it has >= KEEP entries below it)
+__device__ __forceinline__ void ladder_adopt(RowState& st, float t) {
+  if (t < st.thr) {
+    st.thr = t;
+    while (st.ladder && st.p0 >= st.thr) {  // probes at or above thr are useless: shift them out
+      st.p0 = st.p1; st.p1 = st.p2; st.p2 = st.p3;
+      st.c0 = st.c1; st.c1 = st.c2; st.c2 = st.c3;
+      const float d = (st.thr - st.lo) * 0.125f;
+      st.p3 = st.p2 - d;
+      st.c3 = 0;
+      if (!(d > 0.f)) break;
+    }
+  }
+}
+
+__device__ __forceinline__ void append(RowState& st, uint2* be, float v, int g) {
+  be[st.cnt] = make_uint2(__float_as_uint(v), (uint32_t)g);
+  st.cnt++;
+  st.lo = fminf(st.lo, v);
+  st.c0 += (v < st.p0) ? 1 : 0;
+  st.c1 += (v < st.p1) ? 1 : 0;
+  st.c2 += (v < st.p2) ? 1 : 0;
+  st.c3 += (v < st.p3) ? 1 : 0;
+}
+
+// 32 accumulator columns of one row against the staged norms
+template <bool ALL_VALID>
+__device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], const float* __restrict__ snorm, int g0,
+                                             const WorkItem& w, int64_t n, RowState& st, uint2* be) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; j4++) {
+    const float4 nb = *reinterpret_cast<const float4*>(snorm + 4 * j4);
+    const float v0 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 0]), nb.x);
+    const float v1 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 1]), nb.y);
+    const float v2 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 2]), nb.z);
+    const float v3 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 3]), nb.w);
+    const float mn = fminf(fminf(v0, v1), fminf(v2, v3));
+    if (mn < st.thr) {
+      const int g = g0 + 4 * j4;
+      if (ALL_VALID) {
+        if (v0 < st.thr) append(st, be, v0, g);
+        if (v1 < st.thr) append(st, be, v1, g + 1);
+        if (v2 < st.thr) append(st, be, v2, g + 2);
+        if (v3 < st.thr) append(st, be, v3, g + 3);
+      } else {
+        const float vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int gg = g + e;
+          const bool ok = (gg < n) && !(gg >= w.chr_s && gg < w.chr_e);
+          if (ok && vv[e] < st.thr) append(st, be, vv[e], gg);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const WorkItem* __restrict__ items,
                     int nitems, CandView cv, float* __restrict__ dbg_acc) {
@@ -132,11 +223,14 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
   // 1024-byte alignment for the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                   // [STAGES]
-  uint64_t* empty = bars + STAGES;         // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;     // [2]
+  uint64_t* full = bars;                     // [STAGES]
+  uint64_t* empty = bars + STAGES;           // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_norm = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [8 warps][TN]
+  // [2 groups][TM] words (item << 32 | float bits of thr): a threshold is only adopted from the same work item
+  volatile unsigned long long* s_thr = reinterpret_cast<volatile unsigned long long*>(s_norm + 8 * TN);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -218,93 +312,102 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: thread owns one target row =====================
+    // ===================== epilogue: thread owns one target row of every second tile =====================
+    const int grp = (warp - 4) >> 2;  // 0 / 1 -> TMEM buffer and tile parity
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    int buf = 0;
+    float* snorm = s_norm + (warp - 4) * TN;
     uint32_t tphase = 0;
+    int tile_no = 0;  // running count of non-skipped tiles of this CTA (parity selects the group)
     bool dbg_done = false;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const WorkItem w = items[item];
       const bool row_ok = row < w.nrows;
-      const int64_t slot = (int64_t)w.slot0 + (int64_t)row * w.slot_stride;
-      float* bv = cv.val + (row_ok ? slot : 0) * WCX_CAND_CAP;
-      int32_t* bi = cv.idx + (row_ok ? slot : 0) * WCX_CAND_CAP;
-      float thr = row_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);  // +inf / -inf
-      int cnt = 0;
+      const int64_t slot = (int64_t)w.slot0 + (int64_t)row * w.slot_stride + grp;
+      uint2* be = cv.ent + (row_ok ? slot : 0) * WCX_CAND_CAP;
+      RowState st;
+      st.thr = row_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);  // +inf / -inf
+      st.lo = __int_as_float(0x7f800000);
+      st.p0 = st.p1 = st.p2 = st.p3 = __int_as_float(0xff800000);
+      st.c0 = st.c1 = st.c2 = st.c3 = 0;
+      st.cnt = 0;
+      st.ladder = false;
+      s_thr[grp * TM + row] = ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr);
       for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
         if (tile_skipped(w, ct)) continue;
+        const bool mine = (tile_no & 1) == grp;
+        tile_no++;
+        if (!mine) continue;
         const int col0 = ct * TN;
-        mbar_wait(&tfull[buf], tphase);
+        // stage the candidate norms of this tile (issued before waiting for the accumulator)
+        const float4 n0 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0) + lane);
+        const float4 n1 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0) + 32 + lane);
+        {
+          const unsigned long long pw = s_thr[(grp ^ 1) * TM + row];
+          if ((uint32_t)(pw >> 32) == (uint32_t)item && row_ok) ladder_adopt(st, __uint_as_float((uint32_t)pw));
+        }
+        __syncwarp();
+        reinterpret_cast<float4*>(snorm)[lane] = n0;
+        reinterpret_cast<float4*>(snorm)[32 + lane] = n1;
+        __syncwarp();
+        mbar_wait(&tfull[grp], tphase);
+        tphase ^= 1;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * TN);
+        const bool tile_valid = (col0 + TN <= pv.n) && (col0 + TN <= w.chr_s || col0 >= w.chr_e);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + (uint32_t)c0, r);
+        for (int c0 = 0; c0 < TN; c0 += 64) {
           tmem_ld_wait();
-          const int g0 = col0 + c0;
+          tmem_ld32(taddr + (uint32_t)(c0 + 32), rb);
           if (dbg_acc != nullptr && !dbg_done && blockIdx.x == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + j] = __uint_as_float(ra[j]);
           }
-          // column validity is warp-uniform: inside the matrix and outside the own chromosome
-          const bool all_valid = (g0 + 32 <= pv.n) && (g0 + 32 <= w.chr_s || g0 >= w.chr_e);
-          const float4* nrm4 = reinterpret_cast<const float4*>(pv.norm + g0);
-          if (all_valid) {
+          if (tile_valid) filter_chunk<true>(ra, snorm + c0, col0 + c0, w, pv.n, st, be);
+          else filter_chunk<false>(ra, snorm + c0, col0 + c0, w, pv.n, st, be);
+          tmem_ld_wait();
+          if (c0 + 64 < TN) tmem_ld32(taddr + (uint32_t)(c0 + 64), ra);
+          if (dbg_acc != nullptr && !dbg_done && blockIdx.x == 0) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; j4++) {
-              const float4 nb = __ldg(nrm4 + j4);
-              const float nbs[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const float v = fmaf(-2.f, __uint_as_float(r[4 * j4 + e]), nbs[e]);
-                if (v < thr) { bv[cnt] = v; bi[cnt] = g0 + 4 * j4 + e; cnt++; }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; j4++) {
-              const float4 nb = __ldg(nrm4 + j4);
-              const float nbs[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const int g = g0 + 4 * j4 + e;
-                const bool ok = (g < pv.n) && !(g >= w.chr_s && g < w.chr_e);
-                const float v = fmaf(-2.f, __uint_as_float(r[4 * j4 + e]), nbs[e]);
-                if (ok && v < thr) { bv[cnt] = v; bi[cnt] = g; cnt++; }
-              }
-            }
+            for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + 32 + j] = __uint_as_float(rb[j]);
           }
+          if (tile_valid) filter_chunk<true>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be);
+          else filter_chunk<false>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be);
         }
         dbg_done = true;
-        // accumulator buffer drained: hand it back to the MMA warp before the (rare) compaction
+        // accumulator buffer drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-        if (++buf == 2) { buf = 0; tphase ^= 1; }
-        // lists that could overflow on the next tile get compacted, one row at a time, warp-cooperatively
-        uint32_t need = __ballot_sync(0xffffffffu, cnt > WCX_CAND_CAP - TN);
+        if (lane == 0) mbar_arrive(&tempty[grp]);
+        // threshold maintenance
+        const float thr_before = st.thr;
+        ladder_advance(st);
+        if (cv.diag && st.thr < thr_before) atomicAdd(cv.diag + 2, 1);
+        // first exact selection once INIT_N entries are in, and overflow protection afterwards
+        uint32_t need = __ballot_sync(0xffffffffu, (!st.ladder && st.cnt >= INIT_N) || st.cnt > WCX_CAND_CAP - TN);
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
-          const int64_t s_slot = (int64_t)w.slot0 + (int64_t)(q * 32 + src) * w.slot_stride;
-          const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
-          const float t = warp_compact(cv.val + s_slot * WCX_CAND_CAP, cv.idx + s_slot * WCX_CAND_CAP, s_cnt);
-          if (lane == src) { thr = t; cnt = WCX_CAND_KEEP; }
+          const int64_t s_slot = (int64_t)w.slot0 + (int64_t)(q * 32 + src) * w.slot_stride + grp;
+          const int s_cnt = __shfl_sync(0xffffffffu, st.cnt, src);
+          CompactResult cr;
+          if (s_cnt <= 1024) cr = warp_compact<KEEP>(cv.ent + s_slot * WCX_CAND_CAP, s_cnt);
+          else cr = warp_compact_stream<KEEP>(cv.ent + s_slot * WCX_CAND_CAP, s_cnt);
+          if (lane == src) {
+            st.thr = fminf(st.thr, cr.thr);
+            st.lo = cr.lo;
+            st.cnt = cr.kept;
+            st.p0 = cr.probe[0]; st.p1 = cr.probe[1]; st.p2 = cr.probe[2]; st.p3 = cr.probe[3];
+            st.c0 = cr.below[0]; st.c1 = cr.below[1]; st.c2 = cr.below[2]; st.c3 = cr.below[3];
+            st.ladder = true;
+            if (cv.diag) atomicAdd(cv.diag + (s_cnt <= 1024 ? 0 : 1), 1);
+          }
         }
+        if (st.thr < thr_before) s_thr[grp * TM + row] = ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr);
       }
-      // finalize this work item's lists
-      uint32_t need = __ballot_sync(0xffffffffu, cnt > WCX_CAND_KEEP);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int64_t s_slot = (int64_t)w.slot0 + (int64_t)(q * 32 + src) * w.slot_stride;
-        const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
-        const float t = warp_compact(cv.val + s_slot * WCX_CAND_CAP, cv.idx + s_slot * WCX_CAND_CAP, s_cnt);
-        if (lane == src) { thr = t; cnt = WCX_CAND_KEEP; }
-      }
-      if (row_ok) { cv.cnt[slot] = cnt; cv.cut[slot] = thr; }
+      if (row_ok) { cv.cnt[slot] = st.cnt; cv.cut[slot] = st.thr; }
     }
   }
 

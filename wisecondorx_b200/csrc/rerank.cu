@@ -51,7 +51,7 @@ int build_sum_plan(int32_t s, int32_t* plan, int32_t cap) {
 namespace {
 
 constexpr int RR_THREADS = 256;
-constexpr int RR_MAXC = 2048;  // max candidates merged per row (nsplit * KEEP)
+constexpr int RR_MAXM = 1024;  // max candidates whose exact distance is evaluated per row
 constexpr int PLAN_STACK = 16;
 
 __device__ __forceinline__ uint64_t f64_key(double d) {
@@ -68,8 +68,20 @@ __device__ __forceinline__ float key_f32_(uint32_t k) {
 }
 
 // Exact reference distance between the target row `a` (shared memory) and candidate row `b`
-// (global), evaluated cooperatively by the 4 lanes of a quad (l = lane & 3).  All four lanes
-// return the same value.  `gmask` = shuffle mask of the quad's warp (full warp participates).
+// (global), evaluated cooperatively by the 4 lanes of a quad (l = lane & 3); lane l owns the
+// NumPy accumulator chains r[2l], r[2l+1].  All four lanes return the same value.
+// VEC: rows are 16-byte aligned (S even) -> one 128-bit load per 8-element block.
+template <bool VEC>
+__device__ __forceinline__ void load_pair(const double* p, double& x0, double& x1) {
+  if (VEC) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    x0 = v.x; x1 = v.y;
+  } else {
+    x0 = __ldg(p); x1 = __ldg(p + 1);
+  }
+}
+
+template <bool VEC>
 __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a, const double* __restrict__ b,
                                                     const int32_t* __restrict__ plan, int plan_len, int l) {
   double stack[PLAN_STACK];
@@ -82,20 +94,37 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
       if (len < 8) {
         res = 0.0;
         for (int i = 0; i < len; i++) {
-          double t = __dsub_rn(b[off + i], a[off + i]);
+          double t = __dsub_rn(__ldg(b + off + i), a[off + i]);
           res = __dadd_rn(res, __dmul_rn(t, t));
         }
       } else {
         const int nblk = len >> 3;
         const double* bp = b + off + 2 * l;
         const double* ap = a + off + 2 * l;
-        double t0 = __dsub_rn(bp[0], ap[0]);
-        double t1 = __dsub_rn(bp[1], ap[1]);
+        double x0, x1;
+        load_pair<VEC>(bp, x0, x1);
+        double t0 = __dsub_rn(x0, ap[0]);
+        double t1 = __dsub_rn(x1, ap[1]);
         double r0 = __dmul_rn(t0, t0), r1 = __dmul_rn(t1, t1);
-#pragma unroll 4
-        for (int blk = 1; blk < nblk; blk++) {
-          double u0 = __dsub_rn(bp[8 * blk], ap[8 * blk]);
-          double u1 = __dsub_rn(bp[8 * blk + 1], ap[8 * blk + 1]);
+        int blk = 1;
+        // batches of 5 blocks: all loads first (memory-level parallelism), then the ordered adds
+        for (; blk + 5 <= nblk; blk += 5) {
+          double y0[5], y1[5];
+#pragma unroll
+          for (int u = 0; u < 5; u++) load_pair<VEC>(bp + 8 * (blk + u), y0[u], y1[u]);
+#pragma unroll
+          for (int u = 0; u < 5; u++) {
+            const double u0 = __dsub_rn(y0[u], ap[8 * (blk + u)]);
+            const double u1 = __dsub_rn(y1[u], ap[8 * (blk + u) + 1]);
+            r0 = __dadd_rn(r0, __dmul_rn(u0, u0));
+            r1 = __dadd_rn(r1, __dmul_rn(u1, u1));
+          }
+        }
+        for (; blk < nblk; blk++) {
+          double y0, y1;
+          load_pair<VEC>(bp + 8 * blk, y0, y1);
+          const double u0 = __dsub_rn(y0, ap[8 * blk]);
+          const double u1 = __dsub_rn(y1, ap[8 * blk + 1]);
           r0 = __dadd_rn(r0, __dmul_rn(u0, u0));
           r1 = __dadd_rn(r1, __dmul_rn(u1, u1));
         }
@@ -103,7 +132,7 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
         double s2 = __dadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, 1));
         res = __dadd_rn(s2, __shfl_xor_sync(0xffffffffu, s2, 2));
         for (int i = nblk << 3; i < len; i++) {
-          double t = __dsub_rn(b[off + i], a[off + i]);
+          double t = __dsub_rn(__ldg(b + off + i), a[off + i]);
           res = __dadd_rn(res, __dmul_rn(t, t));
         }
       }
@@ -115,23 +144,6 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
     }
   }
   return stack[0];
-}
-
-// in-place bitonic sort of n_pow2 uint64 keys in shared memory (ascending)
-__device__ void bitonic_sort_u64(uint64_t* keys, int n_pow2) {
-  for (int k = 2; k <= n_pow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          uint64_t a = keys[i], b = keys[ixj];
-          bool up = ((i & k) == 0);
-          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 // sort (d, pos) pairs ascending by (d, pos); arrays in shared memory, n_pow2 entries
@@ -151,6 +163,22 @@ __device__ void bitonic_sort_dpos(uint64_t* dkey, int32_t* pos, int n_pow2) {
       __syncthreads();
     }
   }
+}
+
+// block-wide sum of a per-thread count; result valid in every thread (two barriers)
+__device__ __forceinline__ int __syncthreads_count_sum(int c) {
+  __shared__ int s_red[RR_THREADS / 32];
+  __shared__ int s_total;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < RR_THREADS / 32; w++) t += s_red[w];
+    s_total = t;
+  }
+  __syncthreads();
+  return s_total;
 }
 
 __device__ __forceinline__ int next_pow2(int v) {
@@ -178,21 +206,24 @@ __device__ __forceinline__ double approx_eps(double an, double D, int k_pad) {
 // ------------------------------------------------------------------------------------------
 // rerank kernel: one CTA per target row
 // ------------------------------------------------------------------------------------------
+// shared memory: a[S] doubles | keys[maxc] u64 (later: exact distance keys) | sel[RR_MAXM] i32 |
+//                pos[RR_MAXM] i32 | plan
+template <bool VEC>
 __global__ void __launch_bounds__(RR_THREADS)
-rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nsplit, const int64_t* __restrict__ cum,
+rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists, int maxc, const int64_t* __restrict__ cum,
               int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
               double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
               int plan_len) {
   extern __shared__ unsigned char rr_smem[];
-  // layout: a[S] doubles | keys[RR_MAXC] u64 | pos[RR_MAXC] i32 | plan
   double* a_s = reinterpret_cast<double*>(rr_smem);
   uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((pv.s + 1) & ~1));
-  int32_t* pos_s = reinterpret_cast<int32_t*>(keys + RR_MAXC);
-  int32_t* plan = pos_s + RR_MAXC;
-  __shared__ int s_tot, s_m, s_fail;
+  int32_t* sel = reinterpret_cast<int32_t*>(keys + maxc);
+  int32_t* pos_s = sel + RR_MAXM;
+  int32_t* plan = pos_s + RR_MAXM;
+  __shared__ int s_tot, s_m, s_fail, s_cnt;
   __shared__ int s_cs, s_ce;
   __shared__ float s_cut;
-  __shared__ double s_bound, s_eps;
+  __shared__ uint32_t s_vk;
 
   const int tid = threadIdx.x;
   const int64_t lrow = blockIdx.x;
@@ -206,7 +237,11 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nsplit
     s_cs = (int)(c == 0 ? 0 : cum[c - 1]);
     s_ce = (int)cum[c];
     s_fail = 0;
+    s_tot = 0;
     if (gonosomal && c != 22 && c != 23) s_cs = -1;
+    float cut = __int_as_float(0x7f800000);
+    for (int q = 0; q < nlists; q++) cut = fminf(cut, cv.cut[lrow * nlists + q]);
+    s_cut = cut;
   }
   __syncthreads();
   if (s_cs < 0) {  // placeholder rows of gonosomal references (newref_tools.py:186-191)
@@ -214,99 +249,100 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nsplit
     return;
   }
   const int cs = s_cs, ce = s_ce;
+  const float cut = s_cut;
   for (int i = tid; i < pv.s; i += RR_THREADS) a_s[i] = x[row * pv.s + i];
   for (int i = tid; i < 3 * plan_len; i += RR_THREADS) plan[i] = plan_g[i];
 
-  // gather the split lists: key = (orderable(v) << 32) | j
-  if (tid == 0) {
-    int tot = 0;
-    float cut = __int_as_float(0x7f800000);
-    for (int q = 0; q < nsplit; q++) {
-      int64_t slot = lrow * nsplit + q;
-      tot += cv.cnt[slot];
-      cut = fminf(cut, cv.cut[slot]);
+  // gather the list entries below the common cut: key = (orderable(v) << 32) | j
+  for (int q = 0; q < nlists; q++) {
+    const int64_t slot = lrow * nlists + q;
+    const int c = cv.cnt[slot];
+    const uint2* le = cv.ent + slot * WCX_CAND_CAP;
+    for (int i = tid; i < c; i += RR_THREADS) {
+      const uint2 e = le[i];
+      const float v = __uint_as_float(e.x);
+      if (v < cut) {
+        const int p = atomicAdd(&s_tot, 1);
+        if (p < maxc) keys[p] = ((uint64_t)f32_key_(v) << 32) | e.y;
+      }
     }
-    s_tot = tot;
-    s_cut = cut;
   }
   __syncthreads();
   const int tot = s_tot;
-  {
-    int base = 0;
-    for (int q = 0; q < nsplit; q++) {
-      int64_t slot = lrow * nsplit + q;
-      int c = cv.cnt[slot];
-      for (int i = tid; i < c; i += RR_THREADS)
-        keys[base + i] = ((uint64_t)f32_key_(cv.val[slot * WCX_CAND_CAP + i]) << 32) |
-                         (uint32_t)cv.idx[slot * WCX_CAND_CAP + i];
-      base += c;
-    }
-  }
-  const int p2 = next_pow2(tot < 2 ? 2 : tot);
-  for (int i = tot + tid; i < p2; i += RR_THREADS) keys[i] = ~0ull;
-  __syncthreads();
-  bitonic_sort_u64(keys, p2);
-
-  // prefix that can contain the exact top-k
-  if (tid == 0) {
-    int m = tot;
-    double bound = 1e300, eps = 0.0;
-    if (tot > k) {
-      float vk = key_f32_((uint32_t)(keys[k - 1] >> 32));
-      double an = (double)pv.norm[row];
-      double D = fmax((double)vk + an, 0.0);
-      eps = approx_eps(an, D, pv.k_pad);
-      bound = (double)vk + 2.0 * eps;
-      // count v <= bound (sorted ascending): binary search
-      int lo = k, hi = tot;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if ((double)key_f32_((uint32_t)(keys[mid] >> 32)) <= bound) lo = mid + 1; else hi = mid;
-      }
-      m = lo;
-    }
-    // every unlisted candidate has v >= cut: need cut strictly above the bound
-    if (!((double)s_cut > bound)) s_fail = 1;
-    s_m = m;
-    s_bound = bound;
-    s_eps = eps;
-  }
-  __syncthreads();
-  const int m = s_m;
-  if (s_fail) {
+  if (tot > maxc) {
     if (tid == 0) fail_flags[lrow] = 1;
     return;
   }
 
-  // exact distances of the first m candidates, one quad per candidate
-  const int quad = tid >> 2, l = tid & 3;
-  const int rounds = (m + (RR_THREADS / 4) - 1) / (RR_THREADS / 4);
-  for (int rd = 0; rd < rounds; rd++) {
-    const int ci = rd * (RR_THREADS / 4) + quad;
-    const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
-    const int j = (int)(uint32_t)(keys[cc] & 0xffffffffu);
-    double d = exact_sqdist_quad(a_s, x + (int64_t)j * pv.s, plan, plan_len, l);
-    __syncthreads();  // every quad of this round has read its keys[cc]
-    if (l == 0 && ci < m) { keys[ci] = f64_key(d); pos_s[ci] = j; }
-    __syncthreads();
+  // k-th smallest approximate value by bisection over the 32-bit value keys
+  if (tot > k) {
+    uint32_t res = 0;
+    for (int bit = 31; bit >= 0; bit--) {
+      const uint32_t trial = res | (1u << bit);
+      int c = 0;
+      for (int i = tid; i < tot; i += RR_THREADS) c += ((uint32_t)(keys[i] >> 32) < trial) ? 1 : 0;
+      c = __syncthreads_count_sum(c);
+      if (c < k) res = trial;
+    }
+    if (tid == 0) s_vk = res;
   }
-  // keys[0..m) = orderable exact distance, pos_s[0..m) = global bin j -> chromosome-excluded position
-  for (int i = tid; i < m; i += RR_THREADS) {
-    int j = pos_s[i];
-    pos_s[i] = j < cs ? j : j - (ce - cs);
+  if (tid == 0) {
+    s_m = 0;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  double bound = 1e300, eps = 0.0;
+  if (tot > k) {
+    const float vk = key_f32_(s_vk);
+    const double an = (double)pv.norm[row];
+    const double D = fmax((double)vk + an, 0.0);
+    eps = approx_eps(an, D, pv.k_pad);
+    bound = (double)vk + 2.0 * eps;
+  }
+  // every unlisted candidate has v >= cut: the prefix {v <= bound} must lie strictly below it
+  if (!((double)cut > bound)) {
+    if (tid == 0) fail_flags[lrow] = 1;
+    return;
+  }
+  // select the candidates with v <= bound
+  for (int i = tid; i < tot; i += RR_THREADS) {
+    const uint64_t kk = keys[i];
+    if ((double)key_f32_((uint32_t)(kk >> 32)) <= bound) {
+      const int p = atomicAdd(&s_m, 1);
+      if (p < RR_MAXM) sel[p] = (int32_t)(uint32_t)(kk & 0xffffffffu);
+    }
+  }
+  __syncthreads();
+  const int m = s_m;
+  if (m > RR_MAXM) {
+    if (tid == 0) fail_flags[lrow] = 1;
+    return;
+  }
+
+  // exact distances, one quad per candidate; results overwrite keys[0..m)
+  const int quad = tid >> 2, l = tid & 3;
+  for (int c0 = 0; c0 < m; c0 += RR_THREADS / 4) {
+    const int ci = c0 + quad;
+    const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
+    const int j = sel[cc];
+    const double d = exact_sqdist_quad<VEC>(a_s, x + (int64_t)j * pv.s, plan, plan_len, l);
+    if (l == 0 && ci < m) {
+      keys[ci] = f64_key(d);
+      pos_s[ci] = j < cs ? j : j - (ce - cs);  // position in the chromosome-excluded array
+    }
   }
   const int p2m = next_pow2(m < 2 ? 2 : m);
   for (int i = m + tid; i < p2m; i += RR_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
   __syncthreads();
   bitonic_sort_dpos(keys, pos_s, p2m);
 
-  // a-posteriori completeness check: exact d_(k) + eps must stay below bound + |a|^2 - eps
+  // a-posteriori completeness check: exact d_(k) + eps must stay below bound + |a|^2
   if (tid == 0 && tot > k) {
-    uint64_t kk = keys[k - 1];
-    uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
-    double dk = __longlong_as_double((long long)u);
-    double an = (double)pv.norm[row];
-    if (!(dk - an + s_eps < s_bound)) s_fail = 1;
+    const uint64_t kk = keys[k - 1];
+    const uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
+    const double dk = __longlong_as_double((long long)u);
+    const double an = (double)pv.norm[row];
+    if (!(dk - an + eps < bound)) s_fail = 1;
   }
   __syncthreads();
   if (s_fail) {
@@ -315,10 +351,10 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nsplit
   }
   const uint64_t key_1e10 = f64_key(1e10);
   for (int t = tid; t < k; t += RR_THREADS) {
-    bool have = t < m && keys[t] < key_1e10;
+    const bool have = t < m && keys[t] < key_1e10;
     if (have) {
-      uint64_t kk = keys[t];
-      uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
+      const uint64_t kk = keys[t];
+      const uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
       od[t] = __longlong_as_double((long long)u);
       oi[t] = pos_s[t];
     } else {
@@ -328,22 +364,29 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nsplit
   }
 }
 
-int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nsplit, const int64_t* cum_dev,
+int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
                   int32_t plan_len, cudaStream_t st) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0) return 0;
-  if (nsplit * WCX_CAND_KEEP > RR_MAXC) { set_error("rerank: nsplit too large"); return 1; }
-  size_t smem = sizeof(double) * ((pv.s + 1) & ~1) + RR_MAXC * (8 + 4) + sizeof(int32_t) * 3 * plan_len;
-  static size_t attr = 0;
-  if (smem > attr) {
-    WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  if (nlists < 1 || nlists > 4) { set_error("rerank: bad number of candidate lists per row"); return 1; }
+  const int maxc = nlists <= 2 ? 4096 : 8192;  // list entries below the common cut that fit in shared memory
+  const size_t smem = sizeof(double) * ((pv.s + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 8 + sizeof(int32_t) * 3 * plan_len;
+  const bool vec = (pv.s % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[vec]) {
+    if (vec) WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[vec] = smem;
   }
   WCX_CUDA_OK(cudaMemsetAsync(fail_flags, 0, sizeof(int32_t) * rows, st));
-  rerank_kernel<<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nsplit, cum_dev, nchr, row_begin, k, gonosomal,
-                                                          idx_out, dist_out, fail_flags, sum_plan, plan_len);
+  if (vec)
+    rerank_kernel<true><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
+                                                                idx_out, dist_out, fail_flags, sum_plan, plan_len);
+  else
+    rerank_kernel<false><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
+                                                                 idx_out, dist_out, fail_flags, sum_plan, plan_len);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -385,7 +428,7 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
   for (int64_t j0 = 0; j0 < n; j0 += RR_THREADS / 4) {
     int64_t j = j0 + quad;
     int64_t jj = j < n ? j : n - 1;
-    double d = exact_sqdist_quad(a_s, x + jj * s, plan, plan_len, l);
+    double d = exact_sqdist_quad<false>(a_s, x + jj * s, plan, plan_len, l);
     if (l == 0 && j < n) {
       bool excluded = (j >= cs && j < ce) || !(d < 1e10);  // own chromosome, NaN, >= 1e10: never inserted
       dk[j] = excluded ? ~0ull : f64_key(d);

@@ -4,8 +4,9 @@
 #include <stdint.h>
 #include <string>
 
-#define WCX_CAND_CAP 1024   // per (row, column-split) candidate buffer capacity
-#define WCX_CAND_KEEP 512   // entries kept by a compaction (approximate top-KEEP)
+#define WCX_CAND_CAP 4096   // per candidate-list capacity (entries)
+#define WCX_CAND_KEEP 512   // SIMT kernel (one list per row and split): thr is only lowered to t when >= KEEP entries are known below t
+#define WCX_CAND_KEEP_TC 256  // tcgen05 kernel: per list of one epilogue group (two lists per row and split share thresholds)
 #define WCX_TILE_M 128      // target rows per work item
 #define WCX_TILE_N_SIMT 128 // candidate columns per tile, CUDA-core kernel
 #define WCX_TILE_N_TC 256   // candidate columns per tile, tcgen05 kernel
@@ -49,10 +50,10 @@ struct PrepView {
 };
 
 struct CandView {
-  float* val;      // [slots, CAP]   v = norm[j] - 2 * dot(i, j)
-  int32_t* idx;    // [slots, CAP]   global candidate bin j
+  uint2* ent;      // [slots, CAP]   .x = float bits of v = norm[j] - 2 * dot(i, j), .y = global candidate bin j
   int32_t* cnt;    // [slots]
   float* cut;      // [slots]        every non-listed candidate of the slot has v >= cut
+  int32_t* diag;   // [8] counters: 0 exact compactions, 1 streamed compactions, 2 ladder steps, 3 adoptions
 };
 
 // ---- newref kernels (host launchers; all asynchronous on `st`) ---------------------------
@@ -66,7 +67,7 @@ int launch_dist_topk_simt(const PrepView& pv, const WorkItem* items, int32_t nit
 int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                         int32_t* work_counter, void* tmap_storage, cudaStream_t st);
 int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host);
-int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nsplit, const int64_t* cum_dev,
+int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
                   int32_t plan_len, cudaStream_t st);

@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference's predict numeric tools (predict_tools.py, overall_tools.py)
+on top of the C-ABI.  Function names and return values follow the reference; the arithmetic runs in
+the CUDA kernels of csrc/predict.cu.
+
+    coverage_normalize_and_mask + project_pc + normalize_repeat  -> PredictEngine.normalize_set
+    get_weights(ref_file, ap)                                    (predict_tools.py:152-155)
+    get_optimal_cutoff(ref_file, repeats)                        (predict_tools.py:74-82)
+    get_z_score(results_c, results)                              (overall_tools.py:88-119)
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+SET_ID = {"": 0, ".F": 1, ".M": 2}
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def raw_vector(sample, bins_per_chr):
+    """Per-chromosome read counts padded / truncated to the reference's bins_per_chr and
+    concatenated (the host half of coverage_normalize_and_mask, predict_tools.py:35-44); the
+    division by the total and the masking happen on the device."""
+    out = np.zeros(int(np.sum(bins_per_chr)), dtype=np.float64)
+    off = 0
+    for c, nb in enumerate(bins_per_chr):
+        nb = int(nb)
+        a = np.asarray(sample[str(c + 1)])
+        m = min(nb, len(a))
+        out[off:off + m] = a[:m]
+        off += nb
+    return out
+
+
+class PredictEngine:
+    """Keeps the reference arrays of one reference .npz resident on the device between calls
+    (the reference re-inflates them from the .npz on every access)."""
+
+    def __init__(self, device: int = 0, ctx: _lib.Context | None = None):
+        self.ctx = ctx or _lib.default_context(device)
+        self._loaded = {}
+        self._ref_token = None
+        self.meta = {}
+
+    def _ensure_ref(self, ref_file, ap: str):
+        token = id(ref_file)
+        if self._ref_token != token:
+            self._loaded = {}
+            self.meta = {}
+            self._ref_token = token
+        if ap in self._loaded:
+            return
+        L = _lib.load()
+        idx = np.ascontiguousarray(ref_file["indexes" + ap], dtype=np.int32)
+        dist = np.ascontiguousarray(ref_file["distances" + ap], dtype=np.float64)
+        per = np.ascontiguousarray(ref_file["masked_bins_per_chr" + ap], dtype=np.int64)
+        cum = np.ascontiguousarray(ref_file["masked_bins_per_chr_cum" + ap], dtype=np.int64)
+        comps = np.ascontiguousarray(ref_file["pca_components" + ap], dtype=np.float64)
+        mean = np.ascontiguousarray(ref_file["pca_mean" + ap], dtype=np.float64)
+        mask = np.asarray(ref_file["mask" + ap], dtype=bool)
+        bpc = np.asarray(ref_file["bins_per_chr" + ap])
+        mask_pos = np.ascontiguousarray(np.flatnonzero(mask), dtype=np.int32)
+        n, k = idx.shape
+        _lib.check(L.wcx_predict_load_ref(self.ctx.handle, SET_ID[ap], _ptr(idx), _ptr(dist), n, k, _ptr(per), _ptr(cum),
+                                          len(cum), _ptr(comps), _ptr(mean), comps.shape[0], _ptr(mask_pos), int(len(mask))))
+        self._loaded[ap] = True
+        self.meta[ap] = {"n": n, "k": k, "cum": cum, "bins_per_chr": bpc, "bins_total": int(len(mask))}
+
+    def get_weights(self, ref_file, ap):
+        self._ensure_ref(ref_file, ap)
+        out = np.empty(self.meta[ap]["n"], dtype=np.float64)
+        _lib.check(_lib.load().wcx_predict_weights(self.ctx.handle, SET_ID[ap], _ptr(out)))
+        return out
+
+    def get_optimal_cutoff(self, ref_file, repeats):
+        self._ensure_ref(ref_file, "")  # always the autosomal distances (predict_tools.py:75)
+        out = ctypes.c_double()
+        _lib.check(_lib.load().wcx_predict_optimal_cutoff(self.ctx.handle, 0, int(repeats), ctypes.byref(out)))
+        return float(out.value)
+
+    def normalize_set(self, samples, ref_file, ap, cutoff, cp, ct):
+        """Batch form: samples = list of sample dicts -> (z, r, nref [B, n - ct], m_lr [B], m_z [B])."""
+        self._ensure_ref(ref_file, ap)
+        meta = self.meta[ap]
+        raw = np.stack([raw_vector(s, meta["bins_per_chr"]) for s in samples])
+        b = raw.shape[0]
+        nout = meta["n"] - ct
+        z = np.empty((b, nout)); r = np.empty((b, nout)); nref = np.empty((b, nout))
+        m_lr = np.empty(b); m_z = np.empty(b)
+        _lib.check(_lib.load().wcx_predict_normalize(self.ctx.handle, SET_ID[ap], _ptr(raw), b, float(cutoff), int(cp), int(ct),
+                                                     _ptr(z), _ptr(r), _ptr(nref), _ptr(m_lr), _ptr(m_z)))
+        return z, r, nref, m_lr, m_z
+
+    def stage_ms(self):
+        out = np.zeros(4)
+        _lib.check(_lib.load().wcx_predict_stage_ms(self.ctx.handle, _ptr(out)))
+        return {"coverage_project": out[0], "normalize_repeat": out[1], "segment_z": out[2]}
+
+    def segment_zscore(self, nr, inflate_pos, r, w, seg_se, seg_r):
+        nr = np.ascontiguousarray(nr, dtype=np.float64)
+        inflate_pos = np.ascontiguousarray(inflate_pos, dtype=np.int32)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        seg_se = np.ascontiguousarray(seg_se, dtype=np.int64).reshape(-1, 2)
+        seg_r = np.ascontiguousarray(seg_r, dtype=np.float64)
+        out = np.empty(len(seg_r), dtype=np.float64)
+        _lib.check(_lib.load().wcx_segment_zscore(self.ctx.handle, _ptr(nr), nr.shape[0], nr.shape[1], _ptr(inflate_pos), _ptr(r),
+                                                  _ptr(w), len(r), _ptr(seg_se), _ptr(seg_r), len(seg_r), _ptr(out)))
+        return out
+
+
+_engines = {}
+
+
+def default_engine(device: int = 0) -> PredictEngine:
+    if device not in _engines:
+        _engines[device] = PredictEngine(device)
+    return _engines[device]
+
+
+def get_weights(ref_file, ap, engine: PredictEngine | None = None):
+    """Drop-in for predict_tools.get_weights (reference predict_tools.py:152-155)."""
+    return (engine or default_engine()).get_weights(ref_file, ap)
+
+
+def get_optimal_cutoff(ref_file, repeats, engine: PredictEngine | None = None):
+    """Drop-in for predict_tools.get_optimal_cutoff (reference predict_tools.py:74-82)."""
+    return (engine or default_engine()).get_optimal_cutoff(ref_file, repeats)
+
+
+def get_z_score(results_c, results, engine: PredictEngine | None = None):
+    """Drop-in for overall_tools.get_z_score (reference overall_tools.py:88-119): takes the
+    reference's per-chromosome list structures and returns a list of floats / the string "nan"."""
+    results_nr, results_r, results_w = results["results_nr"], results["results_r"], results["results_w"]
+    r = np.concatenate([np.asarray(x, dtype=np.float64) for x in results_r])
+    w = np.concatenate([np.asarray(x, dtype=np.float64) for x in results_w])
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r])]).astype(np.int64)
+    rows = []
+    inflate = np.full(len(r), -1, dtype=np.int32)
+    g = 0
+    for chrom in results_nr:
+        for row in chrom:
+            if not isinstance(row, (int, float)):
+                inflate[g] = len(rows)
+                rows.append(row)
+            g += 1
+    if not rows:
+        return ["nan" for _ in results_c]
+    nr = np.asarray(rows, dtype=np.float64)
+    seg_se = np.array([[offs[s[0]] + s[1], offs[s[0]] + s[2]] for s in results_c], dtype=np.int64).reshape(-1, 2)
+    seg_r = np.array([s[3] for s in results_c], dtype=np.float64)
+    z = (engine or default_engine()).segment_zscore(nr, inflate, r, w, seg_se, seg_r)
+    return [("nan" if np.isnan(v) else float(v)) for v in z]
