@@ -84,7 +84,8 @@ int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
 /* Device time in milliseconds of the stages of the last wcx_newref_topk call, measured with CUDA
  * events on the context's stream: out[0] = sweep (distance + approximate top-k), out[1] = exact
  * re-rank, out[2] = brute-force rows, out[3] = last wcx_newref_null_ratios, out[4] = last
- * wcx_newref_load preparation kernels, out[5..7] reserved. */
+ * wcx_newref_load preparation kernels; out[5] = exact float64 distances evaluated by the re-rank,
+ * out[6] = list entries below the cut gathered by the re-rank (counters, not times), out[7] reserved. */
 int wcx_newref_stage_ms(wcx_ctx* ctx, double* out8);
 
 /* ---- predict ------------------------------------------------------------------------------

@@ -70,6 +70,7 @@ struct wcx_ctx {
   int64_t stats[8] = {};
   double stage_ms[8] = {};
   int64_t launches = 0;
+  int64_t exact_evals = 0, gathered = 0;
   // predict state
   RefSet ref[3];
   DevBuf p_partial, p_totals, p_tdots, p_state, p_raw, p_x, p_copy_a, p_copy_b, p_z, p_r, p_n, p_mlr, p_mz, p_w;
@@ -308,7 +309,7 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
     c->launches += 2;
     std::vector<int32_t> flags((size_t)rows);
-    int32_t diag_h[8] = {};
+    uint32_t diag_h[8] = {};
     WCX_CUDA_OK(cudaMemcpyAsync(diag_h, c->diag.p, sizeof(diag_h), cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaMemcpyAsync(flags.data(), c->fail.p, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaStreamSynchronize(st));
@@ -324,6 +325,8 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     c->stats[5] = diag_h[0];
     c->stats[6] = diag_h[1];
     c->stats[7] = diag_h[2];
+    c->exact_evals = diag_h[4];
+    c->gathered = (int64_t)diag_h[5] * 16;
   }
   c->stats[4] = kernel;
   c->stats[1] = (int64_t)fail_list.size();
@@ -379,7 +382,7 @@ int wcx_newref_null_ratios(wcx_ctx* c, const int32_t* idx, int32_t idx_on_device
     d_idx = c->idx_dev.as<int32_t>();
     c->last_rb = rb; c->last_re = re; c->last_k = k;
   }
-  if (c->xt.ensure(sizeof(double) * (size_t)m * c->n) || c->ids_dev.ensure(sizeof(int32_t) * m)) return 1;
+  if (c->xt.ensure(sizeof(double) * (size_t)null_ratio_staging_doubles(c->n, m)) || c->ids_dev.ensure(sizeof(int32_t) * m)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->ids_dev.p, sample_ids, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
   double* d_out = out;
   if (!out_on_device) {
@@ -420,6 +423,8 @@ int wcx_newref_stats(wcx_ctx* c, int64_t* out8) {
 
 int wcx_newref_stage_ms(wcx_ctx* c, double* out8) {
   if (!c || !out8) { set_error("null argument"); return 1; }
+  c->stage_ms[5] = (double)c->exact_evals;
+  c->stage_ms[6] = (double)c->gathered;
   std::memcpy(out8, c->stage_ms, sizeof(c->stage_ms));
   return 0;
 }

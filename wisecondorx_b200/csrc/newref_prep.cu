@@ -7,8 +7,6 @@
 //  * center_round    Xc = tf32_round(float(X - mean)), zero padded to [n_pad, k_pad], plus the
 //                    row norms of the ROUNDED values (so the tensor-core dot products of the
 //                    rounded operands are exact products; only accumulation rounds).
-//  * transpose_cols  XT[m, :] = X[:, ids[m]] -- column-contiguous copies of the null-ratio sample
-//                    columns (newref_tools.py:213-219).
 #include "wcx_common.cuh"
 
 namespace wcx {
@@ -85,34 +83,6 @@ int launch_center_round(const double* x, int64_t n, int32_t s, const double* col
   const int warps = 8;
   unsigned grid = (unsigned)((n_pad + warps - 1) / warps);
   center_round_kernel<<<grid, warps * 32, 0, st>>>(x, n, s, colsum, colcnt, xc, norm, n_pad, k_pad);
-  WCX_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// XT[m, r] = X[r, ids[m]]; tile 32 rows x 32 chosen columns through shared memory
-__global__ void transpose_cols_kernel(const double* __restrict__ x, int64_t n, int32_t s,
-                                      const int32_t* __restrict__ ids, int32_t m, double* __restrict__ xt) {
-  __shared__ double tile[32][33];
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
-  const int m0 = blockIdx.y * 32;
-  for (int y = threadIdx.y; y < 32; y += 8) {
-    int64_t r = r0 + y;
-    int mm = m0 + threadIdx.x;
-    if (r < n && mm < m) tile[y][threadIdx.x] = x[r * s + ids[mm]];
-  }
-  __syncthreads();
-  for (int y = threadIdx.y; y < 32; y += 8) {
-    int mm = m0 + y;
-    int64_t r = r0 + threadIdx.x;
-    if (r < n && mm < m) xt[(int64_t)mm * n + r] = tile[threadIdx.x][y];
-  }
-}
-
-int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m, double* xt,
-                          cudaStream_t st) {
-  if (n == 0 || m == 0) return 0;
-  dim3 grid((unsigned)((n + 31) / 32), (m + 31) / 32);
-  transpose_cols_kernel<<<grid, dim3(32, 8), 0, st>>>(x, n, s, ids, m, xt);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

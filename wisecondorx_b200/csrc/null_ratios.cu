@@ -6,77 +6,107 @@
 // Quirk reproduced: `indexes` are positions in the chromosome-EXCLUDED array but
 // are applied to the FULL column; -1 wraps to the last bin (Python negative index).
 //
-// One warp per target bin: the warp keeps the bin's k indexes in registers (read once per
-// m-chunk), gathers the k column values from the column-contiguous copy XT[m, :] (L2-resident:
-// one column is N * 8 bytes), and selects the two middle order statistics with a 32+32-bit
-// bisection over orderable keys -- no sort.  np.median returns NaN when any value is NaN.
+// Layout: the chosen sample columns are copied chunk-wise into XM[chunk][n][8] (one 64-byte row of
+// 8 sample values per bin), so one chunk (n * 64 bytes) stays L2-resident while the whole grid
+// works on it and a gather of two adjacent samples is a single 16-byte load.
+// One warp per target bin: the bin's k indexes live in registers (R = ceil(k / 32) per lane); per
+// pair of samples the warp gathers k double2 values and selects the two middle order statistics
+// of each with a bisection over order-preserving 64-bit keys (select.cuh) -- no sort.
+// np.median returns NaN when any value is NaN.
 #include "select.cuh"
 #include "wcx_common.cuh"
 
 namespace wcx {
 
 namespace {
-constexpr int NR_MAXK = 512;
-constexpr int NR_R = NR_MAXK / 32;
+constexpr int NR_CHUNK = 8;
 
-}  // namespace
-
-// xt: [m, n] column copies; idx: [rows, k]; out: [rows, m_total] written at columns m_off..m_off+m
+// xm: [n][8] sample values of this chunk; idx: [rows, k]; out: [rows, m_total] at columns m_off..
+template <int R>
 __global__ void __launch_bounds__(256)
-null_ratios_kernel(const double* __restrict__ xt, int64_t n, const int32_t* __restrict__ idx, int64_t row_begin,
-                   int64_t rows, int k, int m, int m_off, int m_total, double* __restrict__ out) {
+null_ratios_kernel(const double* __restrict__ xm, int64_t n, const int32_t* __restrict__ idx, int64_t row_begin,
+                   int64_t rows, int k, int mc, int m_off, int m_total, double* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t lrow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (lrow >= rows) return;
-  int64_t g[NR_R];
+  int32_t g[R];
 #pragma unroll
-  for (int r = 0; r < NR_R; r++) {
-    int t = r * 32 + lane;
+  for (int r = 0; r < R; r++) {
+    const int t = r * 32 + lane;
     int64_t v = -1;
     if (t < k) {
       v = idx[lrow * k + t];
       if (v < 0) v += n;  // Python negative index
     }
-    g[r] = (t < k) ? v : -1;
+    g[r] = (int32_t)v;
   }
   const int64_t b = row_begin + lrow;
-  for (int mm = 0; mm < m; mm++) {
-    const double* col = xt + (int64_t)mm * n;
-    uint64_t key[NR_R];
-    bool has_nan = false;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  for (int mp = 0; mp < mc; mp += 2) {
+    uint64_t key0[R], key1[R];
+    bool nan0 = false, nan1 = false;
 #pragma unroll
-    for (int r = 0; r < NR_R; r++) {
+    for (int r = 0; r < R; r++) {
       if (g[r] >= 0) {
-        double v = col[g[r]];
-        has_nan |= (v != v);
-        key[r] = dkey(v);
+        const double2 v = __ldg(reinterpret_cast<const double2*>(xm + (int64_t)g[r] * NR_CHUNK + mp));
+        nan0 |= (v.x != v.x);
+        nan1 |= (v.y != v.y);
+        key0[r] = dkey(v.x);
+        key1[r] = dkey(v.y);
       } else {
-        key[r] = ~0ull;
+        key0[r] = ~0ull;
+        key1[r] = ~0ull;
       }
     }
-    has_nan = __any_sync(0xffffffffu, has_nan);
-    double med;
-    if (has_nan || k == 0) {
-      med = __longlong_as_double(0x7ff8000000000000ll);
-    } else {
-      med = warp_median<NR_R>(key, k);
+    nan0 = __any_sync(0xffffffffu, nan0);
+    nan1 = __any_sync(0xffffffffu, nan1);
+    const double2 own = __ldg(reinterpret_cast<const double2*>(xm + b * NR_CHUNK + mp));
+    const double med0 = (nan0 || k == 0) ? nan : warp_median<R>(key0, k);
+    if (lane == 0) out[lrow * m_total + m_off + mp] = log2(own.x / med0);
+    if (mp + 1 < mc) {
+      const double med1 = (nan1 || k == 0) ? nan : warp_median<R>(key1, k);
+      if (lane == 0) out[lrow * m_total + m_off + mp + 1] = log2(own.y / med1);
     }
-    if (lane == 0) out[lrow * m_total + m_off + mm] = log2(col[b] / med);
   }
 }
+
+// XM[c][r][j] = X[r, ids[8c + j]] (zero padded past m); tile 32 rows per block, threads over (row, j)
+__global__ void gather_cols_kernel(const double* __restrict__ x, int64_t n, int32_t s, const int32_t* __restrict__ ids,
+                                   int32_t m, double* __restrict__ xm) {
+  const int j = threadIdx.x & 7;
+  const int64_t r = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int c = blockIdx.y;
+  if (r >= n) return;
+  const int mm = c * NR_CHUNK + j;
+  xm[((int64_t)c * n + r) * NR_CHUNK + j] = mm < m ? x[r * s + ids[mm]] : 0.0;
+}
+}  // namespace
+
+int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m, double* xt,
+                          cudaStream_t st) {
+  if (n == 0 || m == 0) return 0;
+  dim3 grid((unsigned)((n + 31) / 32), (m + NR_CHUNK - 1) / NR_CHUNK);
+  gather_cols_kernel<<<grid, 256, 0, st>>>(x, n, s, ids, m, xt);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int64_t null_ratio_staging_doubles(int64_t n, int32_t m) { return (int64_t)((m + NR_CHUNK - 1) / NR_CHUNK) * n * NR_CHUNK; }
 
 int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t row_begin, int64_t row_end,
                        int32_t k, int32_t m, double* out, cudaStream_t st) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0 || m <= 0) return 0;
-  if (k > NR_MAXK) { set_error("null_ratios: ref_size > 512 unsupported"); return 1; }
+  if (k > 512) { set_error("null_ratios: ref_size > 512 unsupported"); return 1; }
   const int warps = 8;
-  unsigned grid = (unsigned)((rows + warps - 1) / warps);
-  // chunks of 8 sample columns keep the gathered columns L2-resident across the grid
-  const int chunk = 8;
-  for (int m0 = 0; m0 < m; m0 += chunk) {
-    int mc = m - m0 < chunk ? m - m0 : chunk;
-    null_ratios_kernel<<<grid, warps * 32, 0, st>>>(xt + (int64_t)m0 * n, n, idx, row_begin, rows, k, mc, m0, m, out);
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  for (int m0 = 0; m0 < m; m0 += NR_CHUNK) {
+    const int mc = m - m0 < NR_CHUNK ? m - m0 : NR_CHUNK;
+    const double* xm = xt + (int64_t)(m0 / NR_CHUNK) * n * NR_CHUNK;
+    if (k <= 320)
+      null_ratios_kernel<10><<<grid, warps * 32, 0, st>>>(xm, n, idx, row_begin, rows, k, mc, m0, m, out);
+    else
+      null_ratios_kernel<16><<<grid, warps * 32, 0, st>>>(xm, n, idx, row_begin, rows, k, mc, m0, m, out);
   }
   WCX_CUDA_OK(cudaGetLastError());
   return 0;

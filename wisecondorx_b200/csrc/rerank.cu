@@ -209,7 +209,7 @@ __device__ __forceinline__ double approx_eps(double an, double D, int k_pad) {
 // shared memory: a[S] doubles | keys[maxc] u64 (later: exact distance keys) | sel[RR_MAXM] i32 |
 //                pos[RR_MAXM] i32 | plan
 template <bool VEC>
-__global__ void __launch_bounds__(RR_THREADS)
+__global__ void __launch_bounds__(RR_THREADS, 4)  // min 4 CTAs/SM: lets ptxas keep the batched loads in flight (64 regs)
 rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists, int maxc, const int64_t* __restrict__ cum,
               int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
               double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
@@ -314,6 +314,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   __syncthreads();
   const int m = s_m;
+  if (tid == 0 && cv.diag) { atomicAdd(cv.diag + 4, m); atomicAdd(cv.diag + 5, tot >> 4); }
   if (m > RR_MAXM) {
     if (tid == 0) fail_flags[lrow] = 1;
     return;

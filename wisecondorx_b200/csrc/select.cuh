@@ -18,9 +18,24 @@ __device__ __forceinline__ double key_d(uint64_t k) {
 // key of sorted rank `rank` (0-based) among the warp-distributed keys
 template <int R>
 __device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int rank) {
-  uint32_t hi = 0;
+  // the high words of all real keys share a prefix (values of similar magnitude): skip those bits
+  uint32_t hmin = 0xffffffffu, hmax = 0u;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if (key[r] != ~0ull) {
+      const uint32_t h = (uint32_t)(key[r] >> 32);
+      hmin = h < hmin ? h : hmin;
+      hmax = h > hmax ? h : hmax;
+    }
+  }
+  hmin = __reduce_min_sync(0xffffffffu, hmin);
+  hmax = __reduce_max_sync(0xffffffffu, hmax);
+  const uint32_t diff = hmin ^ hmax;
+  const int top = diff ? (31 - __clz(diff)) : -1;  // highest differing bit
+  uint32_t hi = top >= 31 ? 0u : (hmin & ~((top >= 0 ? (2u << top) : 1u) - 1u));
+  if (top < 0) hi = hmin;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; bit--) {
+  for (int bit = top; bit >= 0; bit--) {
     uint32_t trial = hi | (1u << bit);
     int c = 0;
 #pragma unroll

@@ -91,7 +91,8 @@ class NewrefEngine:
     def stage_ms(self):
         out = np.zeros(8, dtype=np.float64)
         _lib.check(_lib.load().wcx_newref_stage_ms(self.ctx.handle, _ptr(out)))
-        return {"sweep": out[0], "rerank": out[1], "exact_rows": out[2], "null_ratios": out[3], "prep": out[4]}
+        return {"sweep": out[0], "rerank": out[1], "exact_rows": out[2], "null_ratios": out[3], "prep": out[4],
+                "exact_evals": out[5], "gathered_entries": out[6]}
 
 
 def get_reference(pca_corrected_data, masked_bins_per_chr, masked_bins_per_chr_cum, ref_size, part,
