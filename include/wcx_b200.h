@@ -122,8 +122,25 @@ int wcx_segment_zscore(wcx_ctx* ctx, const double* nr, int64_t n_masked, int32_t
                        const int32_t* inflate_pos, const double* r, const double* w, int64_t bins_total,
                        const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out);
 /* Device milliseconds of the last predict calls: out[0] = coverage + projection, out[1] = the
- * three normalisation passes + medians, out[2] = segment z-score, out[3] reserved. */
+ * three normalisation passes + medians, out[2] = segment z-score, out[3] = last wcx_cbs_segment. */
 int wcx_predict_stage_ms(wcx_ctx* ctx, double* out4);
+
+/* ---- CBS -----------------------------------------------------------------------------------
+ * Replaces the R bridge: exec_cbs (predict_tools.py:242-263) -> exec_R (overall_tools.py:65-80) ->
+ * include/CBS.R:70-73, DNAcopy::segment(CNA(y, chrom, x), alpha = alpha, weights = w) with DNAcopy
+ * 1.76 defaults (nperm = 10000, hybrid p-value, kmax = 25, nmin = 200, min.width = 2, no undo).
+ * Input: `nseries` NA-free series (one per chromosome [and sample]) concatenated in y / w (host,
+ * weights > 0), off[nseries + 1] offsets, series_ids[nseries] (chromosome id mixed into the
+ * permutation streams; NULL = 0..nseries-1).  Output: ends_out (capacity off[nseries]) receives, series
+ * after series, the ascending exclusive end positions of the segments of each series (relative to the
+ * series start); nseg_out[nseries] their counts.  The NA handling, the split of segments over long
+ * NA runs and the weighted segment means of CBS.R:80-127 are host code (wisecondorx_b200/cbs.py). */
+int wcx_cbs_segment(wcx_ctx* ctx, const double* y, const double* w, const int64_t* off, int32_t nseries,
+                    const int32_t* series_ids, double alpha, int32_t nperm, uint32_t seed,
+                    int32_t* ends_out, int32_t* nseg_out);
+/* Counters of the last wcx_cbs_segment: rounds, segments tested, permutation tests, edge t-tests
+ * with permutations, permutations evaluated, kernel launches. */
+int wcx_cbs_stats(wcx_ctx* ctx, int64_t* out6);
 
 /* Test hook: raw tensor-core accumulators <Xc[row0 + i], Xc[col0 + j]> of one 128 x 256 tile,
  * written to acc_out [128 * 256] (host). */

@@ -151,6 +151,27 @@ def golden_newref_predict(R):
     print("newref_predict.npz written", {k: v.shape for k, v in ref.items() if hasattr(v, "shape")})
 
 
+def golden_example_bed():
+    """Soft known answer for CBS: the per-bin log2 ratios of the reference's
+    shipped example output docs/include/example.bed/ID_bins.bed (100 kb, T21 NIPT, older version)
+    and its ID_segments.bed.  NaN -> 0 (the reference's "no data" sentinel)."""
+    base = "/root/reference/docs/include/example.bed/"
+    chrs, ratio = [], []
+    for line in open(base + "ID_bins.bed").read().splitlines()[1:]:
+        f = line.split("\t")
+        c = {"X": 23, "Y": 24}.get(f[0], None) or int(f[0])
+        chrs.append(c)
+        ratio.append(0.0 if f[4] in ("NaN", "nan") else float(f[4]))
+    segs = []
+    for line in open(base + "ID_segments.bed").read().splitlines()[1:]:
+        f = line.split("\t")
+        c = {"X": 23, "Y": 24}.get(f[0], None) or int(f[0])
+        segs.append([c, (int(f[1]) - 1) // 100000, int(f[2]) // 100000, float(f[3])])
+    np.savez_compressed(os.path.join(HERE, "example_bed.npz"), chr=np.array(chrs, dtype=np.int8),
+                        ratio=np.array(ratio, dtype=np.float32), segments=np.array(segs, dtype=np.float64))
+    print("example_bed.npz written", len(ratio), len(segs))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -160,3 +181,5 @@ if __name__ == "__main__":
         golden_get_reference(R)
     if a.only in (None, "predict"):
         golden_newref_predict(R)
+    if a.only in (None, "example_bed"):
+        golden_example_bed()

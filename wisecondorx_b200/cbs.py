@@ -1,0 +1,98 @@
+"""Host side of the CUDA circular binary segmentation: the reference's `exec_cbs`
+(predict_tools.py:242-275) with the R bridge (`exec_R`, overall_tools.py:65-80 -> include/CBS.R)
+replaced by `wcx_cbs_segment`.  The pre-/post-processing of CBS.R (ratio == 0 -> NA, weight == 0 ->
+1, all-NA chromosomes dropped, segments split over NA runs longer than int(2e6 / binsize), weighted
+segment means, 0-based half-open coordinates) is restated here line by line."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib, predict_tools
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx: _lib.Context | None = None):
+    """Segments a batch of NA-free (y, w) series on the GPU.  Returns a list of int32 arrays with
+    the ascending exclusive segment ends of each series."""
+    ctx = ctx or _lib.default_context(0)
+    L = _lib.load()
+    ns = len(series)
+    lens = [len(y) for y, _ in series]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    total = int(off[-1])
+    y = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a, _ in series]) if ns else np.zeros(0))
+    w = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.float64) for _, b in series]) if ns else np.zeros(0))
+    ids = np.ascontiguousarray(np.arange(ns) if series_ids is None else series_ids, dtype=np.int32)
+    ends = np.zeros(max(total, 1), dtype=np.int32)
+    nseg = np.zeros(max(ns, 1), dtype=np.int32)
+    _lib.check(L.wcx_cbs_segment(ctx.handle, _ptr(y), _ptr(w), _ptr(off), ns, _ptr(ids), float(alpha), int(nperm),
+                                 int(seed) & 0xFFFFFFFF, _ptr(ends), _ptr(nseg)))
+    out, o = [], 0
+    for s in range(ns):
+        out.append(ends[o:o + nseg[s]].copy())
+        o += int(nseg[s])
+    return out
+
+
+def cbs_stats(ctx: _lib.Context | None = None):
+    ctx = ctx or _lib.default_context(0)
+    out = np.zeros(6, dtype=np.int64)
+    _lib.check(_lib.load().wcx_cbs_stats(ctx.handle, _ptr(out)))
+    return dict(zip(["rounds", "segments_tested", "perm_tests", "t_tests", "permutations", "launches"], out.tolist()))
+
+
+def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, nperm=10000, ctx=None):
+    """CBS.R as a function: [[chr (0-based), s, e (exclusive), r], ...]."""
+    nchr = 24 if ref_gender == "M" else 23  # CBS.R:30-34
+    seed_i = 0 if seed is None else int(seed)
+    na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
+    prepared, series, ids = [], [], []
+    for c in range(nchr):
+        ratio = np.asarray(results_r[c], dtype=np.float64)
+        wts = np.asarray(results_w[c], dtype=np.float64).copy()
+        na = ratio == 0  # CBS.R:41
+        wts[wts == 0] = 1.0  # CBS.R:42 -- 1^-99 is 1 in R
+        if na.all():  # CBS.R:56-63
+            continue
+        keep = np.flatnonzero(~na)
+        prepared.append((c, ratio, wts, na, keep))
+        series.append((ratio[keep], wts[keep]))
+        ids.append(c)
+    all_ends = segment_series(series, ids, alpha, nperm, seed_i, ctx)
+    out = []
+    for (c, ratio, wts, na, keep), ends in zip(prepared, all_ends):
+        starts = np.concatenate([[0], ends[:-1]]).astype(np.int64)
+        for a, b in zip(starts, ends):
+            start_i, end_i = int(keep[a]) + 1, int(keep[b - 1]) + 1  # DNAcopy loc.start / loc.end (1-based)
+            seg_na = na[start_i - 1:end_i]
+            d = np.diff(seg_na.astype(np.int8))
+            start_pos = np.flatnonzero(d == 1) + start_i  # CBS.R:92
+            end_pos = np.flatnonzero(d == -1) + start_i  # CBS.R:93
+            sel = (end_pos - start_pos) > na_thresh  # CBS.R:95
+            start_pos, end_pos = start_pos[sel], end_pos[sel]
+            inv_start = np.concatenate([[start_i], end_pos])  # CBS.R:100-101
+            inv_end = np.concatenate([start_pos, [end_i]])
+            ok = (inv_end - inv_start) > 0  # CBS.R:103
+            for s1, e1 in zip(inv_start[ok], inv_end[ok]):
+                yy, ww = ratio[s1 - 1:e1], wts[s1 - 1:e1]
+                m = yy != 0
+                r = float(np.sum(yy[m] * ww[m]) / np.sum(ww[m])) if m.any() else float("nan")  # CBS.R:122-127
+                out.append([c, int(s1) - 1, int(e1), r])  # CBS.R:129, predict_tools.py:266-275
+    return out
+
+
+def exec_cbs(rem_input, results, engine: predict_tools.PredictEngine | None = None, nperm=10000):
+    """Drop-in for predict_tools.exec_cbs (reference predict_tools.py:242-263): segments
+    results["results_r"] with weights results["results_w"], then attaches the between-sample
+    segment z-scores -> [[chr, s, e, z, r], ...]."""
+    args = rem_input["args"]
+    results_c = cbs_segments(results["results_r"], results["results_w"], str(rem_input["ref_gender"]), float(args.alpha),
+                             float(rem_input["binsize"]), getattr(args, "seed", None), nperm,
+                             engine.ctx if engine else None)
+    segment_z = predict_tools.get_z_score(results_c, results, engine)
+    return [results_c[i][:3] + [segment_z[i]] + [results_c[i][3]] for i in range(len(results_c))]

@@ -1,6 +1,7 @@
 // C-ABI of libwcx_b200.so (see include/wcx_b200.h).  Host-side orchestration only: buffer
 // management, work-item construction, stage timing; all arithmetic is in the kernels.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -8,6 +9,7 @@
 #include "../../include/wcx_b200.h"
 #include "wcx_common.cuh"
 #include "predict.cuh"
+#include "cbs.cuh"
 
 namespace wcx {
 static thread_local std::string g_error;
@@ -76,6 +78,8 @@ struct wcx_ctx {
   DevBuf p_partial, p_totals, p_tdots, p_state, p_raw, p_x, p_copy_a, p_copy_b, p_z, p_r, p_n, p_mlr, p_mz, p_w;
   DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out;
   double predict_ms[4] = {};
+  CbsWorkspace* cbs = nullptr;
+  CbsStats cbs_stats = {};
 };
 
 static PrepView prep_view(const wcx_ctx* c) {
@@ -132,6 +136,7 @@ void wcx_destroy(wcx_ctx* c) {
     b->release();
   for (auto& r : c->ref)
     for (DevBuf* b : {&r.idx, &r.dist, &r.cum, &r.comps, &r.mean, &r.mask_pos}) b->release();
+  if (c->cbs) cbs_workspace_destroy(c->cbs);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -629,6 +634,40 @@ int wcx_segment_zscore(wcx_ctx* c, const double* nr, int64_t n_masked, int32_t m
 int wcx_predict_stage_ms(wcx_ctx* c, double* out4) {
   if (!c || !out4) { set_error("null argument"); return 1; }
   std::memcpy(out4, c->predict_ms, sizeof(c->predict_ms));
+  return 0;
+}
+
+// ================================================================================================
+// CBS
+// ================================================================================================
+int wcx_cbs_segment(wcx_ctx* c, const double* y, const double* w, const int64_t* off, int32_t nseries,
+                    const int32_t* series_ids, double alpha, int32_t nperm, uint32_t seed, int32_t* ends_out,
+                    int32_t* nseg_out) {
+  if (!c || !y || !w || !off || !ends_out || !nseg_out || nseries < 0) { set_error("wcx_cbs_segment: bad argument"); return 1; }
+  if (!(alpha > 0.0) || alpha > 1.0 || nperm < 1) { set_error("wcx_cbs_segment: alpha must be in (0, 1], nperm >= 1"); return 1; }
+  for (int s = 0; s < nseries; s++)
+    if (off[s + 1] < off[s]) { set_error("wcx_cbs_segment: offsets must be ascending"); return 1; }
+  for (int64_t i = 0; i < off[nseries]; i++)
+    if (!(w[i] > 0.0) || !std::isfinite(y[i])) { set_error("wcx_cbs_segment: weights must be positive and values finite"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  if (!c->cbs) c->cbs = cbs_workspace_create();
+  WCX_CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+  // DNAcopy 1.76 defaults of segment(): kmax = 25, nmin = 200, min.width = 2 (CBS.R:73 overrides only alpha / weights)
+  if (cbs_segment(c->cbs, y, w, off, nseries, series_ids, alpha, nperm, 25, 200, 2, seed, ends_out, nseg_out, &c->cbs_stats, c->stream))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+  WCX_CUDA_OK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->predict_ms[3] = ms;
+  c->launches += c->cbs_stats.launches;
+  return 0;
+}
+
+int wcx_cbs_stats(wcx_ctx* c, int64_t* out6) {
+  if (!c || !out6) { set_error("null argument"); return 1; }
+  out6[0] = c->cbs_stats.rounds; out6[1] = c->cbs_stats.segments_tested; out6[2] = c->cbs_stats.perm_tests;
+  out6[3] = c->cbs_stats.t_tests; out6[4] = c->cbs_stats.permutations; out6[5] = c->cbs_stats.launches;
   return 0;
 }
 

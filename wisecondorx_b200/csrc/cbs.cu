@@ -1,0 +1,578 @@
+// CUDA circular binary segmentation -- replaces the R / DNAcopy call of the reference:
+//   exec_cbs (predict_tools.py:242-263) -> exec_R (overall_tools.py:65-80) -> include/CBS.R:70-73
+//   DNAcopy::segment(CNA(...), alpha = alpha, weights = w)      [DNAcopy 1.76, conda.yml:14]
+//
+// DNAcopy is not part of the reference tree; the algorithm restated here is the published one
+// (Olshen et al. 2004; Venkatraman & Olshen 2007) with DNAcopy's documented defaults and decision
+// flow (weighted `changepoints` / `wfindcpt`): maximal weighted t-statistic over all arcs, the
+// |t| <= 0.1 / |t| >= 7 shortcuts, hybrid p-value (Siegmund tail approximation + permutation of the
+// short-arc statistic) for segments longer than nmin, full permutation test otherwise, and the
+// permutation t-tests that trim a two-change-point arc.  See oracle/cbs_oracle.py for the spec
+// this file is compared with bit for bit (same Philox4x32-10 streams, same summation order).
+//
+// Mapping.  The recursion over segments is driven by the host in rounds; in every round ALL
+// pending segments of ALL chromosome series (any number of samples x chromosomes) are processed
+// together:
+//   cbs_prepare_kernel   one thread per segment: weighted mean, centring, tss and the sequential
+//                        prefix sums sx / cw (sequential on purpose: every rounding is specified)
+//   cbs_maxarc_kernel    the O(n^2) all-arcs maximum, brute force, split into balanced chunks of
+//                        start positions over the whole grid; block reduce with the tie rule
+//                        (largest bss, then smallest start, then smallest end)
+//   cbs_perm_kernel      one thread per permutation (Fisher-Yates in a private scratch column,
+//                        re-centred prefix sums, short-arc or all-arc maximum) -- only for the rare
+//                        segments whose statistic falls between the tail-probability and |t| >= 7 gates
+//   cbs_tperm_kernel     one thread per permutation of the edge t-tests
+// The scalar decisions (tail probability, thresholds) run on the host between the kernels.
+// This file is compiled with -fmad=false: no FMA contraction, IEEE division.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "wcx_common.cuh"
+#include "cbs.cuh"
+
+namespace wcx {
+
+namespace {
+
+// ---------------- Philox4x32-10 ----------------
+__host__ __device__ inline void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                            uint32_t out[4]) {
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct PermStream {
+  uint32_t k0, k1, b0, b1, b2, t;
+  uint32_t buf[4];
+  __device__ PermStream(uint32_t seed, uint32_t test, uint32_t lo, uint32_t hi, uint32_t perm)
+      : k0(seed), k1(test), b0(perm), b1(lo), b2(hi), t(0) {}
+  __device__ uint32_t below(uint32_t i) {
+    if ((t & 3) == 0) philox4x32(t >> 2, b0, b1, b2, k0, k1, buf);
+    const uint32_t v = buf[t & 3];
+    t++;
+    return (uint32_t)(((uint64_t)v * i) >> 32);
+  }
+};
+
+// one segment of one series
+struct Seg {
+  int64_t lo, hi;   // absolute point range [lo, hi)
+  int32_t series;   // chromosome series id
+  int32_t pad;
+};
+
+struct SegPrep {  // written by cbs_prepare_kernel
+  double tot_w, rtw, tss, tss_y;
+  int32_t flat;   // 1: all values (numerically) equal -> no split
+  int32_t pad;
+};
+
+struct ArcBest {
+  double bss;
+  int32_t i, j;
+};
+
+struct Chunk {
+  int32_t seg;
+  int32_t i0, i1;  // start positions [i0, i1)
+  int32_t pad;
+};
+
+__device__ __forceinline__ bool arc_better(double b, int i, int j, double bb, int bi, int bj) {
+  return (b > bb) || (b == bb && (i < bi || (i == bi && j < bj)));
+}
+
+// ------------------------------------------------------------------------------------------
+// prepare: xc = x - weighted mean, sx[t] = sum_{u < t} w x (stored at t-1 for t = 1..n), cw likewise
+// ------------------------------------------------------------------------------------------
+__global__ void cbs_prepare_kernel(const double* __restrict__ y, const double* __restrict__ w, const Seg* __restrict__ segs,
+                                   int nseg, double* __restrict__ xc, double* __restrict__ sx, double* __restrict__ cw,
+                                   double* __restrict__ yy, SegPrep* __restrict__ prep) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const int64_t lo = segs[s].lo, hi = segs[s].hi;
+  double tw = 0.0, twx = 0.0, mn = y[lo], mx = y[lo];
+  for (int64_t t = lo; t < hi; t++) {
+    const double v = y[t], ww = w[t];
+    twx += v * ww;
+    tw += ww;
+    mn = v < mn ? v : mn;
+    mx = v > mx ? v : mx;
+  }
+  const double avg = twx / tw;
+  const double rtw = sqrt(tw);
+  double tss = 0.0, tssy = 0.0, asx = 0.0, acw = 0.0;
+  for (int64_t t = lo; t < hi; t++) {
+    const double ww = w[t];
+    const double x = y[t] - avg;
+    xc[t] = x;
+    tss += ww * x * x;          // (ww * x) * x, as numpy evaluates ws * x * x
+    const double rw = sqrt(ww);
+    const double yv = x * rw;
+    yy[t] = yv;
+    tssy += yv * yv;
+    asx += ww * x;
+    acw += ww;
+    sx[t] = asx;
+    cw[t] = acw / rtw;
+  }
+  SegPrep p;
+  p.tot_w = tw; p.rtw = rtw; p.tss = tss; p.tss_y = tssy;
+  p.flat = (fabs(mx - mn) < 1.5e-8) ? 1 : 0;
+  p.pad = 0;
+  prep[s] = p;
+}
+
+// ------------------------------------------------------------------------------------------
+// all-arcs maximum.  arcs 0 <= i < j <= n with al0 <= j - i <= n - al0.
+// prefix arrays are stored shifted: P(t) = t == 0 ? 0 : arr[lo + t - 1]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cbs_maxarc_kernel(const double* __restrict__ sx, const double* __restrict__ cw, const Seg* __restrict__ segs,
+                  const Chunk* __restrict__ chunks, int al0, ArcBest* __restrict__ partial) {
+  __shared__ double s_b[256];
+  __shared__ int s_i[256], s_j[256];
+  const Chunk ch = chunks[blockIdx.x];
+  const int64_t lo = segs[ch.seg].lo;
+  const int n = (int)(segs[ch.seg].hi - lo);
+  const double* psx = sx + lo - 1;  // psx[t] valid for t >= 1
+  const double* pcw = cw + lo - 1;
+  const double cwn = pcw[n];
+  double best = -1.0;
+  int bi = 0, bj = 0;
+  for (int i = ch.i0; i < ch.i1; i++) {
+    const double sxi = i == 0 ? 0.0 : psx[i];
+    const double cwi = i == 0 ? 0.0 : pcw[i];
+    const int jlo = i + al0;
+    const int jhi = min(n, i + n - al0);
+    for (int j = jlo + (int)threadIdx.x; j <= jhi; j += 256) {
+      const double s = psx[j] - sxi;
+      const double dw = pcw[j] - cwi;
+      const double bss = (s * s) / (dw * (cwn - dw));
+      if (bss > best) { best = bss; bi = i; bj = j; }  // i, j ascend per thread: strict > keeps the smallest
+    }
+  }
+  s_b[threadIdx.x] = best; s_i[threadIdx.x] = bi; s_j[threadIdx.x] = bj;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const int t = threadIdx.x + o;
+      if (arc_better(s_b[t], s_i[t], s_j[t], s_b[threadIdx.x], s_i[threadIdx.x], s_j[threadIdx.x])) {
+        s_b[threadIdx.x] = s_b[t]; s_i[threadIdx.x] = s_i[t]; s_j[threadIdx.x] = s_j[t];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { partial[blockIdx.x].bss = s_b[0]; partial[blockIdx.x].i = s_i[0]; partial[blockIdx.x].j = s_j[0]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// permutation statistic (hybrid: arcs of at most `max_width` points or their complements;
+// max_width < 0: all arcs).  One thread per permutation; scratch layout [n][stride] so that
+// the sequential index is coalesced across the permutations of a batch.
+// ------------------------------------------------------------------------------------------
+struct PermJob {
+  int64_t lo;
+  int32_t n, max_width;
+  uint32_t seed, lo_id, hi_id;
+  int32_t perm0;      // first permutation index of this batch
+  double ostat, rtw, tot_w, tss_y;
+};
+
+__global__ void __launch_bounds__(128)
+cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, const double* __restrict__ cw, PermJob job,
+                int nperm_batch, int al0, double* __restrict__ scratch, int stride, int* __restrict__ nrej) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nperm_batch) return;
+  const int n = job.n;
+  const double* y = yy + job.lo;
+  const double* ws = w + job.lo;
+  const double* pcw = cw + job.lo - 1;
+  double* py = scratch + p;                    // py[i * stride]
+  double* sxp = scratch + (int64_t)n * stride + p;  // second plane: re-centred prefix sums, index t = 1..n at (t-1)
+  for (int i = 0; i < n; i++) py[(int64_t)i * stride] = y[i];
+  PermStream st(job.seed, 0u, job.lo_id, job.hi_id, (uint32_t)(job.perm0 + p));
+  // wxperm: Fisher-Yates from the top; px[i] = py[i] / rw[i]; accumulate sum(ws * px) on the fly is
+  // not order-compatible with the oracle (which runs cumsum ascending), so store px first
+  for (int i = n - 1; i >= 0; i--) {
+    const uint32_t j = st.below((uint32_t)i + 1u);
+    const double tmp = py[(int64_t)i * stride];
+    const double vj = py[(int64_t)j * stride];
+    py[(int64_t)j * stride] = tmp;
+    py[(int64_t)i * stride] = vj / sqrt(ws[i]);  // position i is final: holds px[i] from now on
+  }
+  // prefix sums of ws * px (ascending), then re-centre
+  double acc = 0.0;
+  for (int i = 0; i < n; i++) {
+    acc += ws[i] * py[(int64_t)i * stride];
+    sxp[(int64_t)i * stride] = acc;
+  }
+  const double xbar = acc / job.tot_w;
+  const double tss = job.tss_y - job.tot_w * xbar * xbar;
+  for (int t = 1; t <= n; t++) sxp[(int64_t)(t - 1) * stride] = sxp[(int64_t)(t - 1) * stride] - xbar * (pcw[t] * job.rtw);
+  const double cwn = pcw[n];
+  double best = -1.0;
+  const int mw = job.max_width;
+  for (int i = 0; i < n; i++) {
+    const double sxi = i == 0 ? 0.0 : sxp[(int64_t)(i - 1) * stride];
+    const double cwi = i == 0 ? 0.0 : pcw[i];
+    const int jlo = i + al0, jhi = min(n, i + n - al0);
+    if (mw < 0) {
+      for (int j = jlo; j <= jhi; j++) {
+        const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
+        const double dw = pcw[j] - cwi;
+        const double bss = (s * s) / (dw * (cwn - dw));
+        best = bss > best ? bss : best;
+      }
+    } else {
+      // short arcs and, through the complement, long ones: width <= mw or width >= n - mw
+      const int j1 = min(jhi, i + mw);
+      for (int j = jlo; j <= j1; j++) {
+        const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
+        const double dw = pcw[j] - cwi;
+        const double bss = (s * s) / (dw * (cwn - dw));
+        best = bss > best ? bss : best;
+      }
+      const int j2 = max(max(jlo, i + n - mw), j1 + 1);
+      for (int j = j2; j <= jhi; j++) {
+        const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
+        const double dw = pcw[j] - cwi;
+        const double bss = (s * s) / (dw * (cwn - dw));
+        best = bss > best ? bss : best;
+      }
+    }
+  }
+  const double pstat = best / ((tss - best) / ((double)n - 2.0));
+  if (job.ostat <= pstat) atomicAdd(nrej, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// edge t-tests (DNAcopy wtpermp restated for weights)
+// ------------------------------------------------------------------------------------------
+struct TJob {
+  int64_t lo;        // absolute start of the tested sub-range
+  int32_t n1, n2;
+  uint32_t seed, test, lo_id, hi_id;
+  // filled by cbs_tprep_kernel
+  double ostat, xbar, wp;
+  int32_t m1, pos0, skip;  // skip: 1 -> p = 1 (n1 or n2 == 1), 2 -> p = 0 (|t| > 5 shortcut)
+  int32_t nrej;
+};
+
+__global__ void cbs_tprep_kernel(const double* __restrict__ xc, const double* __restrict__ w, TJob* __restrict__ jobs, int njobs) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= njobs) return;
+  TJob jb = jobs[q];
+  const int n1 = jb.n1, n2 = jb.n2, n = n1 + n2;
+  jb.nrej = 0;
+  if (n1 == 1 || n2 == 1) { jb.skip = 1; jobs[q] = jb; return; }
+  const double* x = xc + jb.lo;
+  const double* ws = w + jb.lo;
+  double w1 = 0, w2 = 0, s1 = 0, s2 = 0, q2 = 0;
+  for (int i = 0; i < n1; i++) { w1 += ws[i]; s1 += ws[i] * x[i]; }
+  for (int i = n1; i < n; i++) { w2 += ws[i]; s2 += ws[i] * x[i]; }
+  for (int i = 0; i < n; i++) q2 += ws[i] * x[i] * x[i];
+  const double wt = w1 + w2;
+  const double xbar = (s1 + s2) / wt;
+  const double tss = q2 - wt * xbar * xbar;
+  double ostat, tstat;
+  if (n1 <= n2) {
+    jb.m1 = n1; jb.pos0 = 0; jb.wp = w1;
+    ostat = 0.99999 * fabs(s1 / w1 - xbar);
+    tstat = (ostat * ostat) * w1 * wt / w2;
+  } else {
+    jb.m1 = n2; jb.pos0 = n1; jb.wp = w2;
+    ostat = 0.99999 * fabs(s2 / w2 - xbar);
+    tstat = (ostat * ostat) * w2 * wt / w1;
+  }
+  tstat = tstat / ((tss - tstat) / ((double)n - 2.0));
+  jb.ostat = ostat; jb.xbar = xbar;
+  jb.skip = (tstat > 25.0 && jb.m1 >= 10) ? 2 : 0;
+  jobs[q] = jb;
+}
+
+__global__ void __launch_bounds__(128)
+cbs_tperm_kernel(const double* __restrict__ xc, const double* __restrict__ w, TJob* __restrict__ jobs, int q, int nperm,
+                 double* __restrict__ scratch, int stride) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nperm) return;
+  const TJob jb = jobs[q];
+  const int n = jb.n1 + jb.n2;
+  const double* x = xc + jb.lo;
+  const double* ws = w + jb.lo;
+  double* py = scratch + p;
+  for (int i = 0; i < n; i++) py[(int64_t)i * stride] = x[i] * sqrt(ws[i]);
+  PermStream st(jb.seed, jb.test, jb.lo_id, jb.hi_id, (uint32_t)p);
+  double acc = 0.0;
+  for (int t = 0; t < jb.m1; t++) {
+    const int i = n - 1 - t;
+    const uint32_t j = st.below((uint32_t)i + 1u);
+    const double tmp = py[(int64_t)i * stride];
+    const double vj = py[(int64_t)j * stride];
+    py[(int64_t)j * stride] = tmp;
+    py[(int64_t)i * stride] = vj;
+    acc += sqrt(ws[jb.pos0 + t]) * vj;
+  }
+  const double pstat = fabs(acc / jb.wp - jb.xbar);
+  if (jb.ostat <= pstat) atomicAdd(&jobs[q].nrej, 1);
+}
+
+// ---------------- host-side scalar maths (DNAcopy tailp / nu / it1tsq) ----------------
+double pnorm_(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
+
+double nu_(double x, double tol) {
+  double lnu1;
+  if (x > 0.01) {
+    lnu1 = std::log(2.0) - 2.0 * std::log(x);
+    double lnu0 = lnu1;
+    int k = 2;
+    double dk = 0.0;
+    for (int i = 0; i < k; i++) { dk += 1.0; lnu1 -= 2.0 * pnorm_(-x * std::sqrt(dk) / 2.0) / dk; }
+    while (std::fabs((lnu1 - lnu0) / lnu1) > tol) {
+      lnu0 = lnu1;
+      for (int i = 0; i < k; i++) { dk += 1.0; lnu1 -= 2.0 * pnorm_(-x * std::sqrt(dk) / 2.0) / dk; }
+      k *= 2;
+    }
+  } else {
+    lnu1 = -0.583 * x;
+  }
+  return std::exp(lnu1);
+}
+
+double it1tsq_(double x, double a) {
+  double y = x + a - 0.5;
+  double v = (8.0 * y) / (1.0 - 4.0 * y * y) + 2.0 * std::log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+  y = x - 0.5;
+  return v - (8.0 * y) / (1.0 - 4.0 * y * y) - 2.0 * std::log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+}
+
+double tailp_(double b, double delta, int m, int ngrid, double tol) {
+  const double dincr = (0.5 - delta) / ngrid;
+  const double bsqrtm = b / std::sqrt((double)m);
+  double tl = 0.5 - dincr, t = 0.5 - 0.5 * dincr, acc = 0.0;
+  for (int i = 0; i < ngrid; i++) {
+    tl += dincr;
+    t += dincr;
+    const double x = bsqrtm / std::sqrt(t * (1.0 - t));
+    const double nux = nu_(x, tol);
+    acc += (nux * nux) * it1tsq_(tl, dincr);
+  }
+  return 9.973557e-2 * (b * b * b) * std::exp(-b * b / 2.0) * acc;
+}
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { set_error("cbs: cudaMalloc failed"); return 1; }
+    cap = bytes;
+    return 0;
+  }
+  ~DBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct CbsWorkspace {
+  DBuf y, w, xc, sx, cw, yy, segs, prep, chunks, partial, scratch, nrej, tjobs;
+};
+
+CbsWorkspace* cbs_workspace_create() { return new CbsWorkspace(); }
+void cbs_workspace_destroy(CbsWorkspace* ws) { delete ws; }
+
+int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_t* off, int32_t nseries,
+                const int32_t* series_ids, double alpha, int32_t nperm, int32_t kmax, int32_t nmin, int32_t min_width,
+                uint32_t seed, int32_t* ends_out, int32_t* nseg_out, CbsStats* stats, cudaStream_t st) {
+  const int64_t total = off[nseries];
+  for (int s = 0; s < nseries; s++) nseg_out[s] = 0;
+  if (total == 0) return 0;
+  if (ws->y.ensure(8 * total) || ws->w.ensure(8 * total) || ws->xc.ensure(8 * total) || ws->sx.ensure(8 * total) ||
+      ws->cw.ensure(8 * total) || ws->yy.ensure(8 * total) || ws->nrej.ensure(64))
+    return 1;
+  WCX_CUDA_OK(cudaMemcpyAsync(ws->y.p, y, 8 * total, cudaMemcpyHostToDevice, st));
+  WCX_CUDA_OK(cudaMemcpyAsync(ws->w.p, w, 8 * total, cudaMemcpyHostToDevice, st));
+  std::vector<std::vector<int32_t>> ends(nseries);
+  std::vector<Seg> pending;
+  for (int s = 0; s < nseries; s++)
+    if (off[s + 1] > off[s]) pending.push_back(Seg{off[s], off[s + 1], s, 0});
+  const int al0 = min_width;
+  const int64_t CHUNK_ARCS = 1 << 21;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  while (!pending.empty()) {
+    // segments too short to split are final
+    std::vector<Seg> work;
+    for (const Seg& sg : pending) {
+      if (sg.hi - sg.lo >= 2 * (int64_t)min_width) work.push_back(sg);
+      else ends[sg.series].push_back((int32_t)(sg.hi - off[sg.series]));
+    }
+    pending.clear();
+    if (work.empty()) break;
+    const int nseg = (int)work.size();
+    if (stats) { stats->rounds++; stats->segments_tested += nseg; }
+    if (ws->segs.ensure(sizeof(Seg) * nseg) || ws->prep.ensure(sizeof(SegPrep) * nseg)) return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(ws->segs.p, work.data(), sizeof(Seg) * nseg, cudaMemcpyHostToDevice, st));
+    cbs_prepare_kernel<<<(nseg + 63) / 64, 64, 0, st>>>(ws->y.as<double>(), ws->w.as<double>(), ws->segs.as<Seg>(), nseg,
+                                                       ws->xc.as<double>(), ws->sx.as<double>(), ws->cw.as<double>(),
+                                                       ws->yy.as<double>(), ws->prep.as<SegPrep>());
+    // balanced chunks of start positions
+    std::vector<Chunk> chunks;
+    for (int s = 0; s < nseg; s++) {
+      const int n = (int)(work[s].hi - work[s].lo);
+      int i0 = 0;
+      int64_t acc = 0;
+      for (int i = 0; i < n; i++) {
+        const int jlo = i + al0, jhi = std::min(n, i + n - al0);
+        acc += jhi >= jlo ? (jhi - jlo + 1) : 0;
+        if (acc >= CHUNK_ARCS || i == n - 1) {
+          chunks.push_back(Chunk{s, i0, i + 1, 0});
+          i0 = i + 1;
+          acc = 0;
+        }
+      }
+    }
+    const int nchunks = (int)chunks.size();
+    if (ws->chunks.ensure(sizeof(Chunk) * nchunks) || ws->partial.ensure(sizeof(ArcBest) * nchunks)) return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(ws->chunks.p, chunks.data(), sizeof(Chunk) * nchunks, cudaMemcpyHostToDevice, st));
+    cbs_maxarc_kernel<<<nchunks, 256, 0, st>>>(ws->sx.as<double>(), ws->cw.as<double>(), ws->segs.as<Seg>(),
+                                               ws->chunks.as<Chunk>(), al0, ws->partial.as<ArcBest>());
+    WCX_CUDA_OK(cudaGetLastError());
+    std::vector<ArcBest> partial(nchunks);
+    std::vector<SegPrep> prep(nseg);
+    WCX_CUDA_OK(cudaMemcpyAsync(partial.data(), ws->partial.p, sizeof(ArcBest) * nchunks, cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaMemcpyAsync(prep.data(), ws->prep.p, sizeof(SegPrep) * nseg, cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaStreamSynchronize(st));
+    if (stats) stats->launches += 2;
+    std::vector<ArcBest> best(nseg, ArcBest{-1.0, 0, 0});
+    for (int c = 0; c < nchunks; c++) {
+      ArcBest& b = best[chunks[c].seg];
+      const ArcBest& p = partial[c];
+      if ((p.bss > b.bss) || (p.bss == b.bss && (p.i < b.i || (p.i == b.i && p.j < b.j)))) b = p;
+    }
+    // decisions
+    for (int s = 0; s < nseg; s++) {
+      const Seg& sg = work[s];
+      const int n = (int)(sg.hi - sg.lo);
+      const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
+      const uint32_t sseed = (uint32_t)((uint64_t)seed * 1000003ull + (uint64_t)(uint32_t)sid);
+      const uint32_t lo_id = (uint32_t)(sg.lo - off[sg.series]), hi_id = (uint32_t)(sg.hi - off[sg.series]);
+      std::vector<int> cpts;
+      bool split = false;
+      const SegPrep& pr = prep[s];
+      const int i1 = best[s].i, i2 = best[s].j;
+      if (!pr.flat && best[s].bss >= 0.0) {
+        double ostat = best[s].bss / ((pr.tss - best[s].bss) / ((double)n - 2.0));
+        const double ostat1 = ostat > 0 ? std::sqrt(ostat) : 0.0;
+        ostat *= 0.99999;
+        if (ostat1 > 0.1) {
+          const int width = i2 - i1;
+          const int l = std::min(width, n - width);
+          split = (ostat1 >= 7.0 && l >= 10);
+          if (!split) {
+            const bool hybrid = n > nmin;
+            int nrejc;
+            bool run = true;
+            int mw = -1;
+            if (hybrid) {
+              const double delta = ((double)kmax + 1.0) / (double)n;
+              const double pval1 = tailp_(ostat1, delta, n, 100, 1e-6);
+              if (pval1 > alpha) run = false;
+              nrejc = (int)((alpha - pval1) * (double)nperm);
+              mw = kmax;
+            } else {
+              nrejc = (int)(alpha * (double)nperm);
+            }
+            if (run) {
+              if (stats) stats->perm_tests++;
+              const int PB = 2048;
+              const size_t need = sizeof(double) * 2 * (size_t)n * PB;
+              if (ws->scratch.ensure(need)) return 1;
+              int nrej = 0;
+              split = true;
+              for (int p0 = 0; p0 < nperm; p0 += PB) {
+                const int nb = std::min(PB, nperm - p0);
+                WCX_CUDA_OK(cudaMemsetAsync(ws->nrej.p, 0, sizeof(int), st));
+                PermJob job;
+                job.lo = sg.lo; job.n = n; job.max_width = mw; job.seed = sseed; job.lo_id = lo_id; job.hi_id = hi_id;
+                job.perm0 = p0; job.ostat = ostat; job.rtw = pr.rtw; job.tot_w = pr.tot_w; job.tss_y = pr.tss_y;
+                cbs_perm_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(), job,
+                                                                  nb, al0, ws->scratch.as<double>(), PB, ws->nrej.as<int>());
+                int h = 0;
+                WCX_CUDA_OK(cudaMemcpyAsync(&h, ws->nrej.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                WCX_CUDA_OK(cudaStreamSynchronize(st));
+                if (stats) { stats->launches++; stats->permutations += nb; }
+                nrej += h;
+                if (nrej > nrejc) { split = false; break; }
+              }
+            }
+          }
+        }
+      }
+      if (split) {
+        if (i2 == n) cpts.push_back(i1);
+        else if (i1 == 0) cpts.push_back(i2);
+        else {
+          // two edge t-tests on the centred data of this segment
+          TJob jobs[2];
+          std::memset(jobs, 0, sizeof(jobs));
+          jobs[0].lo = sg.lo; jobs[0].n1 = i1; jobs[0].n2 = i2 - i1; jobs[0].test = 1;
+          jobs[1].lo = sg.lo + i1; jobs[1].n1 = i2 - i1; jobs[1].n2 = n - i2; jobs[1].test = 2;
+          for (auto& jb : jobs) { jb.seed = sseed; jb.lo_id = lo_id; jb.hi_id = hi_id; }
+          if (ws->tjobs.ensure(sizeof(jobs))) return 1;
+          WCX_CUDA_OK(cudaMemcpyAsync(ws->tjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, st));
+          cbs_tprep_kernel<<<1, 32, 0, st>>>(ws->xc.as<double>(), ws->w.as<double>(), ws->tjobs.as<TJob>(), 2);
+          WCX_CUDA_OK(cudaMemcpyAsync(jobs, ws->tjobs.p, sizeof(jobs), cudaMemcpyDeviceToHost, st));
+          WCX_CUDA_OK(cudaStreamSynchronize(st));
+          if (stats) stats->launches++;
+          for (int q = 0; q < 2; q++) {
+            double pval;
+            if (jobs[q].skip == 1) pval = 1.0;
+            else if (jobs[q].skip == 2) pval = 0.0;
+            else {
+              const int nn = jobs[q].n1 + jobs[q].n2;
+              if (ws->scratch.ensure(sizeof(double) * (size_t)nn * nperm)) return 1;
+              cbs_tperm_kernel<<<(nperm + 127) / 128, 128, 0, st>>>(ws->xc.as<double>(), ws->w.as<double>(), ws->tjobs.as<TJob>(), q,
+                                                                    nperm, ws->scratch.as<double>(), nperm);
+              TJob back;
+              WCX_CUDA_OK(cudaMemcpyAsync(&back, ws->tjobs.as<TJob>() + q, sizeof(TJob), cudaMemcpyDeviceToHost, st));
+              WCX_CUDA_OK(cudaStreamSynchronize(st));
+              if (stats) { stats->launches++; stats->permutations += nperm; stats->t_tests++; }
+              pval = (double)back.nrej / (double)nperm;
+            }
+            if (pval <= alpha) cpts.push_back(q == 0 ? i1 : i2);
+          }
+        }
+      }
+      if (cpts.empty()) {
+        ends[sg.series].push_back((int32_t)(sg.hi - off[sg.series]));
+      } else {
+        int64_t a = sg.lo;
+        for (int c : cpts) { pending.push_back(Seg{a, sg.lo + c, sg.series, 0}); a = sg.lo + c; }
+        pending.push_back(Seg{a, sg.hi, sg.series, 0});
+      }
+    }
+  }
+  int64_t o = 0;
+  for (int s = 0; s < nseries; s++) {
+    std::sort(ends[s].begin(), ends[s].end());
+    nseg_out[s] = (int32_t)ends[s].size();
+    for (int32_t e : ends[s]) ends_out[o++] = e;
+  }
+  return 0;
+}
+
+}  // namespace wcx

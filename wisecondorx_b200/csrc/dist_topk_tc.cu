@@ -131,7 +131,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ bool tile_skipped(const WorkItem& w, int ct) {
+// A tile that lies entirely inside the target rows' own chromosome yields no candidates.  It is
+// still loaded and multiplied (5-6 % extra tensor work on a whole genome) so that all CTAs walk
+// the candidate axis in lockstep and every B tile is fetched from HBM once and then served from L2
+// to the other 147 CTAs; skipping it de-phases the CTAs and the sweep becomes HBM-latency bound
+// (profiles/r01b: 209 GB DRAM reads per launch with skipping).  Only the epilogue filter is skipped.
+__device__ __forceinline__ bool tile_own(const WorkItem& w, int ct) {
   const int col0 = ct * TN;
   return col0 >= w.chr_s && col0 + TN <= w.chr_e;
 }
@@ -263,7 +268,6 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const WorkItem w = items[item];
         for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
-          if (tile_skipped(w, ct)) continue;
           const int col0 = ct * TN;
           for (int kb = 0; kb < kblocks; kb++) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -288,7 +292,6 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const WorkItem w = items[item];
         for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
-          if (tile_skipped(w, ct)) continue;
           mbar_wait(&tempty[buf], tphase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TN);
@@ -318,7 +321,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
     const int row = q * 32 + lane;
     float* snorm = s_norm + (warp - 4) * TN;
     uint32_t tphase = 0;
-    int tile_no = 0;  // running count of non-skipped tiles of this CTA (parity selects the group)
+    int tile_no = 0;  // running count of tiles of this CTA (parity selects the group)
     bool dbg_done = false;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const WorkItem w = items[item];
@@ -334,11 +337,19 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       st.ladder = false;
       s_thr[grp * TM + row] = ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr);
       for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
-        if (tile_skipped(w, ct)) continue;
         const bool mine = (tile_no & 1) == grp;
         tile_no++;
         if (!mine) continue;
         const int col0 = ct * TN;
+        if (tile_own(w, ct)) {  // nothing to filter: just hand the accumulator back
+          mbar_wait(&tfull[grp], tphase);
+          tphase ^= 1;
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[grp]);
+          continue;
+        }
         // stage the candidate norms of this tile (issued before waiting for the accumulator)
         const float4 n0 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0) + lane);
         const float4 n1 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0) + 32 + lane);
