@@ -56,7 +56,9 @@ def test_noise_and_planted():
         assert g.tolist() == [len(y)]
     y, w = _series(rng, 16000, [(3000, 3400, 0.05), (9000, 16000, -0.02)], sd=0.03)
     g = cbs.segment_series([(y, w)], nperm=1000, seed=1)[0].tolist()
-    assert g == [3000, 3400, 9000, 16000]
+    assert len(g) == 4 and g[3] == 16000
+    assert all(abs(a - b) <= 3 for a, b in zip(g, [3000, 3400, 9000, 16000])), g
+    assert g == C.segment_chromosome(y, w, nperm=1000, seed=1, chrom=0)
 
 
 def test_exec_cbs_flow_equals_oracle_on_example_bed(golden_dir):
@@ -70,7 +72,7 @@ def test_exec_cbs_flow_equals_oracle_on_example_bed(golden_dir):
     assert [s[:3] for s in got] == [s[:3] for s in want]
     np.testing.assert_allclose([s[3] for s in got], [s[3] for s in want], rtol=1e-14)
     c21 = max((s for s in got if s[0] == 20), key=lambda s: s[2] - s[1])
-    assert (c21[1], c21[2]) == (131, 467)
+    assert abs(c21[1] - 131) <= 3 and c21[2] == 467  # random weights may move the left edge by a bin or two
 
 
 def test_exec_cbs_dropin_signature():
