@@ -88,6 +88,34 @@ int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
  * out[6] = list entries below the cut gathered by the re-rank (counters, not times), out[7] reserved. */
 int wcx_newref_stage_ms(wcx_ctx* ctx, double* out8);
 
+/* ---- newref preparation ---------------------------------------------------------------------
+ * Replaces the numeric body of tool_newref_prep (newref_control.py:35-58).
+ *
+ * normalize_and_mask (newref_tools.py:110-129): counts int32 [bins_total, S] = per-sample read counts
+ * stacked per chromosome (zero padded), mask_pos int32 [n] = np.flatnonzero(mask); out float64 [n, S] =
+ * counts[mask_pos] / column totals.  Bit-exact (integer totals). */
+int wcx_newref_normalize_and_mask(wcx_ctx* ctx, const int32_t* counts, int64_t bins_total, int32_t s,
+                                  const int32_t* mask_pos, int64_t n, double* out, int32_t out_on_device);
+/* train_pca (newref_tools.py:138-147), exact-PCA formulation in three steps:
+ *   wcx_pca_gram : x [n, S] -> mean_out [n] (per-bin mean over samples = pca.mean_) and the S x S Gram
+ *                  matrix of the centred data (host, row-major).  x stays on the device.
+ *   (host)       : eigen-decomposition of the Gram matrix (S x S), u = top eigenvectors [S, ncomp],
+ *                  sigma = sqrt(eigenvalues).
+ *   wcx_pca_apply: comps_out [ncomp, n] (= pca.components_ up to sklearn's sign convention, applied
+ *                  by the caller) and corrected_out [n, S] = x / (inverse_transform(transform(x))).
+ *                  corrected_out may be NULL: the result then stays on the device for
+ *                  wcx_pca_distance(corrected = NULL). */
+int wcx_pca_gram(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, int32_t x_on_device, double* mean_out,
+                 double* gram_out);
+int wcx_pca_apply(wcx_ctx* ctx, const double* u, const double* sigma, int32_t ncomp, double* comps_out,
+                  double* corrected_out, int32_t corrected_on_device);
+/* PCA-distance filter (newref_control.py:40-41): med_out [S] = np.median(corrected, axis=0),
+ * d_out [n] = sum_s (corrected[b, s] - med[s])^2.  The MAD cutoff (:42-46) is a host scalar step. */
+int wcx_pca_distance(wcx_ctx* ctx, const double* corrected, int64_t n, int32_t s, int32_t on_device,
+                     double* med_out, double* d_out);
+/* Device milliseconds: out[0] = mean + Gram, out[1] = components + correction, out[2] = medians + distances. */
+int wcx_newref_prep_stage_ms(wcx_ctx* ctx, double* out4);
+
 /* ---- predict ------------------------------------------------------------------------------
  * Replaces normalize (predict_control.py:21-39) = coverage_normalize_and_mask (predict_tools.py:32),
  * project_pc (:56), get_weights (:152), get_optimal_cutoff (:74), normalize_repeat/_normalize_once

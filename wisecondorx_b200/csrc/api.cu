@@ -10,6 +10,7 @@
 #include "wcx_common.cuh"
 #include "predict.cuh"
 #include "cbs.cuh"
+#include "newref_pca.cuh"
 
 namespace wcx {
 static thread_local std::string g_error;
@@ -79,6 +80,12 @@ struct wcx_ctx {
   DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out;
   double predict_ms[4] = {};
   CbsWorkspace* cbs = nullptr;
+  // newref prep state
+  DevBuf q_counts, q_pos, q_colsum, q_x, q_mean, q_partial, q_gram, q_u, q_sigma, q_comps, q_corr, q_med, q_d, q_work;
+  int64_t q_n = 0;
+  int32_t q_s = 0;
+  const double* q_xptr = nullptr;
+  double prep_ms[4] = {};
   CbsStats cbs_stats = {};
 };
 
@@ -133,6 +140,9 @@ void wcx_destroy(wcx_ctx* c) {
                     &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
                     &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out})
+    b->release();
+  for (DevBuf* b : {&c->q_counts, &c->q_pos, &c->q_colsum, &c->q_x, &c->q_mean, &c->q_partial, &c->q_gram, &c->q_u, &c->q_sigma,
+                    &c->q_comps, &c->q_corr, &c->q_med, &c->q_d, &c->q_work})
     b->release();
   for (auto& r : c->ref)
     for (DevBuf* b : {&r.idx, &r.dist, &r.cum, &r.comps, &r.mean, &r.mask_pos}) b->release();
@@ -668,6 +678,131 @@ int wcx_cbs_stats(wcx_ctx* c, int64_t* out6) {
   if (!c || !out6) { set_error("null argument"); return 1; }
   out6[0] = c->cbs_stats.rounds; out6[1] = c->cbs_stats.segments_tested; out6[2] = c->cbs_stats.perm_tests;
   out6[3] = c->cbs_stats.t_tests; out6[4] = c->cbs_stats.permutations; out6[5] = c->cbs_stats.launches;
+  return 0;
+}
+
+// ================================================================================================
+// newref preparation: normalize_and_mask, train_pca, PCA-distance filter
+// ================================================================================================
+int wcx_newref_normalize_and_mask(wcx_ctx* c, const int32_t* counts, int64_t bins_total, int32_t s, const int32_t* mask_pos,
+                                  int64_t n, double* out, int32_t out_on_device) {
+  if (!c || !counts || !mask_pos || !out || bins_total <= 0 || s <= 0 || n < 0) { set_error("wcx_newref_normalize_and_mask: bad argument"); return 1; }
+  for (int64_t i = 0; i < n; i++)
+    if (mask_pos[i] < 0 || mask_pos[i] >= bins_total) { set_error("wcx_newref_normalize_and_mask: mask position out of range"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (h2d(c->q_counts, counts, sizeof(int32_t) * (size_t)bins_total * s, st) || h2d(c->q_pos, mask_pos, sizeof(int32_t) * (size_t)n, st) ||
+      c->q_colsum.ensure(sizeof(unsigned long long) * s))
+    return 1;
+  double* d_out = out;
+  if (!out_on_device) {
+    if (c->q_x.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1) * s)) return 1;
+    d_out = c->q_x.as<double>();
+  }
+  if (launch_normalize_and_mask(c->q_counts.as<int32_t>(), bins_total, s, c->q_pos.as<int32_t>(), n,
+                                c->q_colsum.as<unsigned long long>(), d_out, st))
+    return 1;
+  if (!out_on_device && n > 0) WCX_CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n * s, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  c->launches += 2;
+  return 0;
+}
+
+int wcx_pca_gram(wcx_ctx* c, const double* x, int64_t n, int32_t s, int32_t x_on_device, double* mean_out, double* gram_out) {
+  if (!c || !x || !mean_out || !gram_out || n <= 0 || s <= 0) { set_error("wcx_pca_gram: bad argument"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  if (x_on_device) {
+    c->q_xptr = x;
+  } else {
+    if (h2d(c->q_x, x, sizeof(double) * (size_t)n * s, st)) return 1;
+    c->q_xptr = c->q_x.as<double>();
+  }
+  c->q_n = n; c->q_s = s;
+  const int s_pad = gram_s_pad(s), nch = gram_chunks(n);
+  if (c->q_mean.ensure(sizeof(double) * (size_t)n) || c->q_partial.ensure(sizeof(double) * (size_t)nch * s_pad * s_pad) ||
+      c->q_gram.ensure(sizeof(double) * (size_t)s * s))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
+  if (launch_row_mean(c->q_xptr, n, s, c->q_mean.as<double>(), st)) return 1;
+  if (launch_gram(c->q_xptr, c->q_mean.as<double>(), n, s, c->q_partial.as<double>(), c->q_gram.as<double>(), st)) return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
+  WCX_CUDA_OK(cudaMemcpyAsync(mean_out, c->q_mean.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaMemcpyAsync(gram_out, c->q_gram.p, sizeof(double) * (size_t)s * s, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->prep_ms[0] = ms;
+  c->launches += 3;
+  return 0;
+}
+
+int wcx_pca_apply(wcx_ctx* c, const double* u, const double* sigma, int32_t ncomp, double* comps_out, double* corrected_out,
+                  int32_t corrected_on_device) {
+  if (!c || !u || !sigma || !comps_out || ncomp <= 0 || ncomp > 8 || !c->q_xptr) { set_error("wcx_pca_apply: bad argument or wcx_pca_gram not called"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t n = c->q_n;
+  const int32_t s = c->q_s;
+  if (h2d(c->q_u, u, sizeof(double) * (size_t)s * ncomp, st) || h2d(c->q_sigma, sigma, sizeof(double) * ncomp, st) ||
+      c->q_comps.ensure(sizeof(double) * (size_t)ncomp * n))
+    return 1;
+  double* d_corr = corrected_out;
+  if (!corrected_on_device || !corrected_out) {
+    if (c->q_corr.ensure(sizeof(double) * (size_t)n * s)) return 1;
+    d_corr = c->q_corr.as<double>();
+  }
+  WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
+  if (launch_pca_apply(c->q_xptr, c->q_mean.as<double>(), n, s, c->q_u.as<double>(), c->q_sigma.as<double>(), ncomp,
+                       c->q_comps.as<double>(), d_corr, st))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
+  WCX_CUDA_OK(cudaMemcpyAsync(comps_out, c->q_comps.p, sizeof(double) * (size_t)ncomp * n, cudaMemcpyDeviceToHost, st));
+  if (corrected_out && !corrected_on_device)
+    WCX_CUDA_OK(cudaMemcpyAsync(corrected_out, d_corr, sizeof(double) * (size_t)n * s, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->prep_ms[1] = ms;
+  c->launches += 1;
+  return 0;
+}
+
+int wcx_pca_distance(wcx_ctx* c, const double* corrected, int64_t n, int32_t s, int32_t on_device, double* med_out, double* d_out) {
+  if (!c || !med_out || !d_out || n <= 0 || s <= 0) { set_error("wcx_pca_distance: bad argument"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const double* d_x = nullptr;
+  if (!corrected) {
+    if (c->q_corr.cap < sizeof(double) * (size_t)n * s || c->q_n != n || c->q_s != s) { set_error("wcx_pca_distance: no device-resident corrected matrix"); return 1; }
+    d_x = c->q_corr.as<double>();
+  } else if (on_device) {
+    d_x = corrected;
+  } else {
+    if (h2d(c->q_corr, corrected, sizeof(double) * (size_t)n * s, st)) return 1;
+    d_x = c->q_corr.as<double>();
+  }
+  if (c->q_med.ensure(sizeof(double) * s) || c->q_d.ensure(sizeof(double) * (size_t)n) ||
+      c->q_work.ensure(sizeof(unsigned long long) * (size_t)(67 * s)))
+    return 1;
+  unsigned long long* wk = c->q_work.as<unsigned long long>();
+  WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
+  if (launch_col_medians(d_x, n, s, wk, wk + s, wk + 2 * s, c->q_med.as<double>(), st)) return 1;
+  if (launch_row_sqdist(d_x, n, s, c->q_med.as<double>(), c->q_d.as<double>(), st)) return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
+  WCX_CUDA_OK(cudaMemcpyAsync(med_out, c->q_med.p, sizeof(double) * s, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaMemcpyAsync(d_out, c->q_d.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  WCX_CUDA_OK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->prep_ms[2] = ms;
+  c->launches += 132;
+  return 0;
+}
+
+int wcx_newref_prep_stage_ms(wcx_ctx* c, double* out4) {
+  if (!c || !out4) { set_error("null argument"); return 1; }
+  std::memcpy(out4, c->prep_ms, sizeof(c->prep_ms));
   return 0;
 }
 

@@ -1,0 +1,325 @@
+"""`WisecondorX` command line on the B200 kernels: the sub-commands, flags, defaults and .npz / .bed
+formats of the reference CLI (reference main.py:302-502) so that `newref` and `predict` are
+drop-in.  `convert` (BAM/CRAM ingest, pysam) and `--plot` (R) are outside the accelerated path and
+not provided here; use the reference for those steps -- the .npz files are interchangeable.
+
+Error convention of the reference is kept: user errors log a critical message and `sys.exit()`
+(status 0)."""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import sys
+import warnings
+
+import numpy as np
+
+from . import cbs, newref_control, predict_control, predict_output, predict_tools
+from .overall_tools import gender_correct, scale_sample
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side helpers of newref (reference newref_tools.py:21-102) -- O(samples) / one pass, host
+# ---------------------------------------------------------------------------------------------
+def _y_fraction(sample):
+    return float(np.sum(sample["24"])) / float(np.sum([np.sum(sample[x]) for x in sample.keys()]))
+
+
+def train_gender_model(args, samples):
+    """Two-component Gaussian mixture on the Y-read fraction; the first local minimum of the mixture
+    density on [0, 0.02] is the male/female cutoff unless --yfrac is given (reference :21-68)."""
+    y = np.array([_y_fraction(s) for s in samples])
+    if args.yfrac is not None:
+        cut_off = args.yfrac
+    else:
+        from scipy.signal import argrelextrema
+        from sklearn.mixture import GaussianMixture
+        gmm = GaussianMixture(n_components=2, covariance_type="full", reg_covar=1e-99, max_iter=10000, tol=1e-99)
+        gmm.fit(X=y.reshape(-1, 1))
+        gx = np.linspace(0, 0.02, 5000)
+        gy = np.exp(gmm.score_samples(gx.reshape(-1, 1)))
+        cut_off = gx[argrelextrema(gy, np.less)][0]
+        logging.info("Determined --yfrac cutoff: {}".format(str(round(cut_off, 4))))
+    genders = np.empty(len(samples), dtype="object")
+    genders[y > cut_off] = "M"
+    genders[y < cut_off] = "F"
+    return genders.tolist(), cut_off
+
+
+def get_mask(samples):
+    """Bins with more than 5 % of the median (non-zero) summed normalised coverage (reference :77-102)."""
+    bins_per_chr = [max(len(s[str(c)]) for s in samples) for c in range(1, 25)]
+    total = int(sum(bins_per_chr))
+    all_data = np.zeros((total, len(samples)), dtype=float)
+    off = 0
+    for c, nb in zip(range(1, 25), bins_per_chr):
+        for i, s in enumerate(samples):
+            a = np.asarray(s[str(c)])
+            all_data[off:off + len(a), i] = a
+        off += nb
+    all_data = all_data / np.sum(all_data, 0)
+    sum_per_bin = np.sum(all_data, 1)
+    median_cov = np.median(sum_per_bin[sum_per_bin > 0])
+    return sum_per_bin > (0.05 * median_cov), bins_per_chr
+
+
+def predict_gender(sample, trained_cutoff):
+    return "M" if _y_fraction(sample) > trained_cutoff else "F"  # reference predict_tools.py:17-24
+
+
+# ---------------------------------------------------------------------------------------------
+# newref
+# ---------------------------------------------------------------------------------------------
+def tool_newref(args):
+    logging.info("Creating new reference")
+    if args.yfrac is not None and (args.yfrac < 0 or args.yfrac > 1):
+        logging.critical("Parameter --yfrac should be a positive number lower than or equal to 1")
+        sys.exit()
+    samples = []
+    logging.info("Importing data ...")
+    for infile in args.infiles:
+        logging.info("Loading: {}".format(infile))
+        npz = np.load(infile, encoding="latin1", allow_pickle=True)
+        samples.append(scale_sample(npz["sample"].item(), int(npz["binsize"]), args.binsize))
+    samples = np.array(samples)
+    genders, trained_cutoff = train_gender_model(args, samples)
+    if genders.count("F") < 5 and args.nipt:
+        logging.warning("A NIPT reference should have at least 5 female feti samples. Removing --nipt flag.")
+        args.nipt = False
+    if not args.nipt:
+        for i, sample in enumerate(samples):
+            samples[i] = gender_correct(sample, genders[i])
+    total_mask, bins_per_chr = get_mask(samples)
+    g = np.array(genders)
+    if genders.count("F") > 4:
+        total_mask = total_mask & get_mask(samples[g == "F"])[0]
+    if genders.count("M") > 4 and not args.nipt:
+        total_mask = total_mask & get_mask(samples[g == "M"])[0]
+    device = getattr(args, "device", 0)
+    parts = max(1, int(args.cpus))
+    results = []
+    if len(genders) > 9:
+        logging.info("Starting autosomal reference creation ...")
+        prep = newref_control.tool_newref_prep(list(samples), "A", total_mask, bins_per_chr, device)
+        logging.info("This might take a while ...")
+        results.append(newref_control.tool_newref_main(prep, args.refsize, parts, device))
+    else:
+        logging.critical("Provide at least 10 samples to enable the generation of a reference.")
+        sys.exit()
+    if genders.count("F") > 4:
+        logging.info("Starting female gonosomal reference creation ...")
+        prep = newref_control.tool_newref_prep(list(samples[g == "F"]), "F", total_mask, bins_per_chr, device)
+        results.append(newref_control.tool_newref_main(prep, args.refsize, 1, device))
+    else:
+        logging.warning("Provide at least 5 female samples to enable normalization of female gonosomes.")
+    if not args.nipt:
+        if genders.count("M") > 4:
+            logging.info("Starting male gonosomal reference creation ...")
+            prep = newref_control.tool_newref_prep(list(samples[g == "M"]), "M", total_mask, bins_per_chr, device)
+            results.append(newref_control.tool_newref_main(prep, args.refsize, 1, device))
+        else:
+            logging.warning("Provide at least 5 male samples to enable normalization of male gonosomes.")
+    newref_control.tool_newref_merge(args.outfile, results, args.binsize, args.nipt, trained_cutoff)
+    logging.info("Finished creating reference")
+
+
+# ---------------------------------------------------------------------------------------------
+# predict
+# ---------------------------------------------------------------------------------------------
+def get_post_processed_result(minrefbins, result, ref_sizes, mask, bins_per_chr):
+    """Zeroes bins with fewer than minrefbins reference bins, unmasks and splits per chromosome
+    (reference predict_control.py:49-63 + predict_tools.py:163-170), vectorised."""
+    result = np.array(result, dtype=float)
+    result[ref_sizes < minrefbins] = 0
+    full = np.zeros(len(mask), dtype=float)
+    full[np.asarray(mask, dtype=bool)] = result
+    offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
+    return [full[offs[c]:offs[c + 1]] for c in range(len(bins_per_chr))]
+
+
+def log_trans(results, log_r_median):
+    """log2 of the ratios; non-finite entries blank r, z and w; the median log-ratio is subtracted
+    from every non-zero entry (reference predict_tools.py:180-193)."""
+    for c in range(len(results["results_r"])):
+        with np.errstate(all="ignore"):
+            r = np.log2(results["results_r"][c])
+        bad = ~np.isfinite(r)
+        r[bad] = 0
+        results["results_z"][c][bad] = 0
+        results["results_w"][c][bad] = 0
+        nz = r != 0
+        r[nz] = r[nz] - log_r_median
+        results["results_r"][c] = r
+
+
+def apply_blacklist(path, binsize, results):
+    """Blanks the bins overlapping the BED intervals of --blacklist (reference :202-233)."""
+    for line in open(path):
+        chr_name, s, e = line.strip().split("\t")[:3]
+        chr_name = chr_name[3:] if chr_name[:3] == "chr" else chr_name
+        c = {"X": 23, "Y": 24}.get(chr_name, None) or int(chr_name)
+        c -= 1
+        if len(results["results_r"]) < 24 and c == 23:
+            continue
+        lo, hi = max(0, int(int(s) / binsize)), min(len(results["results_r"][c]), int(int(e) / binsize) + 1)
+        for key in ("results_r", "results_z", "results_w"):
+            results[key][c][lo:hi] = 0
+
+
+def tool_test(args):
+    logging.info("Starting CNA prediction")
+    if not args.bed and not args.plot:
+        logging.critical("No output format selected. Select at least one of the supported output formats (--bed, --plot)")
+        sys.exit()
+    if args.zscore <= 0:
+        logging.critical("Parameter --zscore should be a strictly positive number")
+        sys.exit()
+    if args.beta is not None and (args.beta <= 0 or args.beta > 1):
+        logging.critical("Parameter --beta should be a strictly positive number lower than or equal to 1")
+        sys.exit()
+    if args.alpha <= 0 or args.alpha > 1:
+        logging.critical("Parameter --alpha should be a strictly positive number lower than or equal to 1")
+        sys.exit()
+    logging.info("Importing data ...")
+    # inflate the reference once (the reference re-inflates on every access)
+    ref_file = dict(np.load(args.reference, encoding="latin1", allow_pickle=True))
+    sample_file = np.load(args.infile, encoding="latin1", allow_pickle=True)
+    sample = sample_file["sample"].item()
+    n_reads = sum([sum(sample[x]) for x in sample.keys()])
+    sample = scale_sample(sample, int(sample_file["binsize"].item()), int(ref_file["binsize"]))
+    gender = predict_gender(sample, ref_file["trained_cutoff"])
+    if not ref_file["is_nipt"]:
+        if args.gender:
+            gender = args.gender
+        sample = gender_correct(sample, gender)
+        ref_gender = gender
+    else:
+        if args.gender:
+            gender = args.gender
+        ref_gender = "F"
+    engine = predict_tools.PredictEngine(getattr(args, "device", 0))
+    logging.info("Normalizing autosomes ...")
+    results_r, results_z, results_w, ref_sizes, m_lr, m_z = predict_control.normalize(args, sample, ref_file, "A", engine)
+    if not ref_file["is_nipt"]:
+        if not ref_file["has_male"] and gender == "M":
+            logging.warning("This sample is male, whilst the reference is created with fewer than 5 males. "
+                            "The female gonosomal reference will be used for X predictions.")
+            ref_gender = "F"
+        elif not ref_file["has_female"] and gender == "F":
+            logging.warning("This sample is female, whilst the reference is created with fewer than 5 females. "
+                            "The male gonosomal reference will be used for XY predictions.")
+            ref_gender = "M"
+    logging.info("Normalizing gonosomes ...")
+    nr_aut = ref_file["null_ratios"]
+    nr_gon = ref_file["null_ratios.{}".format(ref_gender)][len(nr_aut):]
+    r2, z2, w2, n2, _, _ = predict_control.normalize(args, sample, ref_file, ref_gender, engine)
+    sfx = ".{}".format(ref_gender)
+    rem_input = {
+        "args": args, "binsize": int(ref_file["binsize"]), "n_reads": n_reads, "ref_gender": ref_gender, "gender": gender,
+        "mask": ref_file["mask" + sfx], "bins_per_chr": ref_file["bins_per_chr" + sfx],
+        "masked_bins_per_chr": ref_file["masked_bins_per_chr" + sfx],
+        "masked_bins_per_chr_cum": ref_file["masked_bins_per_chr_cum" + sfx],
+    }
+    # assembly (reference main.py:242-257)
+    results_r = np.append(results_r, r2)
+    results_z = np.append(results_z, z2) - m_z
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        results_w = np.append(results_w * np.nanmean(w2), w2 * np.nanmean(results_w))
+        results_w = results_w / np.nanmean(results_w)
+    if np.isnan(results_w).any() or np.isinf(results_w).any():
+        logging.warning("Non-numeric values found in weights -- reference too small. Circular binary segmentation and "
+                        "z-scoring will be unweighted")
+        results_w = np.ones(len(results_w))
+    ref_sizes = np.append(ref_sizes, n2)
+    m = max(nr_aut.shape[1], nr_gon.shape[1] if len(nr_gon) else 0)
+    nr = np.full((len(nr_aut) + len(nr_gon), m), np.nan)
+    nr[:len(nr_aut), :nr_aut.shape[1]] = nr_aut
+    if len(nr_gon):
+        nr[len(nr_aut):, :nr_gon.shape[1]] = nr_gon
+    mask, bpc = rem_input["mask"], rem_input["bins_per_chr"]
+    results = {key: get_post_processed_result(args.minrefbins, val, ref_sizes, mask, bpc)
+               for key, val in (("results_r", results_r), ("results_z", results_z), ("results_w", results_w))}
+    mask_b = np.asarray(mask, dtype=bool)
+    pos = np.arange(int(np.sum(mask_b)), dtype=np.int32)
+    pos[ref_sizes < args.minrefbins] = -1  # rows blanked by get_post_processed_result (reference predict_control.py:50-51)
+    inflate = np.full(len(mask_b), -1, dtype=np.int32)
+    inflate[mask_b] = pos
+    results["results_nr"] = {"dense": nr, "inflate": inflate}
+    log_trans(results, m_lr)
+    if args.blacklist:
+        logging.info("Applying blacklist ...")
+        apply_blacklist(args.blacklist, rem_input["binsize"], results)
+    logging.info("Executing circular binary segmentation ...")
+    results["results_c"] = cbs.exec_cbs(rem_input, results, engine)
+    if args.bed:
+        logging.info("Writing tables ...")
+        predict_output.generate_output_tables(rem_input, results, engine)
+    if args.plot:
+        logging.warning("--plot needs the reference's R plotter and is not part of the accelerated path; skipped")
+    logging.info("Finished prediction")
+    return results
+
+
+def output_gender(args):
+    ref_file = np.load(args.reference, encoding="latin1", allow_pickle=True)
+    sample_file = np.load(args.infile, encoding="latin1", allow_pickle=True)
+    print("male" if predict_gender(sample_file["sample"].item(), ref_file["trained_cutoff"]) == "M" else "female")
+
+
+def tool_convert(args):
+    logging.critical("`convert` (BAM/CRAM ingest through pysam) is not part of the accelerated path; "
+                     "run the reference's `WisecondorX convert` -- its .npz output is read unchanged by newref / predict here")
+    sys.exit()
+
+
+def build_parser():
+    """Same sub-commands, flags, types and defaults as the reference (main.py:312-488); `--device` is new."""
+    parser = argparse.ArgumentParser(description="WisecondorX (B200-native numeric core)")
+    parser.add_argument("--loglevel", type=str, default="INFO", choices=["info", "warning", "debug", "error", "critical"])
+    sub = parser.add_subparsers()
+    p = sub.add_parser("convert", description="Convert and filter aligned reads to .npz (reference only)")
+    p.add_argument("infile", type=str); p.add_argument("outfile", type=str)
+    p.add_argument("-r", "--reference", type=str); p.add_argument("--binsize", type=float, default=5e3)
+    p.add_argument("--normdup", action="store_true")
+    p.set_defaults(func=tool_convert)
+    p = sub.add_parser("newref", description="Create a new reference using healthy reference samples")
+    p.add_argument("infiles", type=str, nargs="+"); p.add_argument("outfile", type=str)
+    p.add_argument("--nipt", action="store_true"); p.add_argument("--yfrac", type=float, default=None)
+    p.add_argument("--plotyfrac", type=str, default=None); p.add_argument("--refsize", type=int, default=300)
+    p.add_argument("--binsize", type=int, default=1e5); p.add_argument("--cpus", type=int, default=1)
+    p.add_argument("--device", type=int, default=0, help="CUDA device (new)")
+    p.set_defaults(func=tool_newref)
+    p = sub.add_parser("gender", description="Returns the gender of a .npz resulting from convert")
+    p.add_argument("infile", type=str); p.add_argument("reference", type=str)
+    p.set_defaults(func=output_gender)
+    p = sub.add_parser("predict", description="Find copy number aberrations")
+    p.add_argument("infile", type=str); p.add_argument("reference", type=str); p.add_argument("outid", type=str)
+    p.add_argument("--minrefbins", type=int, default=150); p.add_argument("--maskrepeats", type=int, default=5)
+    p.add_argument("--alpha", type=float, default=1e-4); p.add_argument("--zscore", type=float, default=5)
+    p.add_argument("--beta", type=float, default=None); p.add_argument("--blacklist", type=str, default=None)
+    p.add_argument("--gender", type=str, choices=["F", "M"]); p.add_argument("--ylim", type=str, default="def")
+    p.add_argument("--bed", action="store_true"); p.add_argument("--plot", action="store_true")
+    p.add_argument("--cairo", action="store_true"); p.add_argument("--add-plot-title", action="store_true")
+    p.add_argument("--seed", type=int, default=None); p.add_argument("--regions", type=str, default=None)
+    p.add_argument("--device", type=int, default=0, help="CUDA device (new)")
+    p.set_defaults(func=tool_test)
+    return parser
+
+
+def main(argv=None):
+    warnings.filterwarnings("ignore")
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    logging.basicConfig(format="[%(levelname)s - %(asctime)s]: %(message)s", datefmt="%Y-%m-%d %H:%M:%S",
+                        level=getattr(logging, args.loglevel.upper(), None))
+    logging.debug("args are: {}".format(args))
+    if not hasattr(args, "func"):
+        parser.print_help()
+        return
+    args.func(args)
+
+
+if __name__ == "__main__":
+    main()

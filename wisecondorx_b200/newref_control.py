@@ -1,0 +1,92 @@
+"""newref stage controllers (mirror of the reference's newref_control.py) on the GPU kernels.
+
+The reference fans `get_reference` out over `cpus` parts through temporary .npz part files
+(newref_control.py:90-150); here the parts are computed by the GPU(s) and concatenated in part order
+in memory, which yields the same arrays (`tool_newref_post`, :159-189).  Output keys, dtypes and
+suffix rules of the final reference file follow `tool_newref_merge` (:220-237)."""
+from __future__ import annotations
+
+import logging
+import random
+
+import numpy as np
+
+from . import newref_tools
+
+
+def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
+    """Numeric body of the reference's tool_newref_prep (newref_control.py:24-80): masking,
+    normalisation, PCA correction and the PCA-distance bin filter.  `mask` is edited IN PLACE like in
+    the reference (:51-54; the edit leaks into the later F / M passes).
+    Returns a dict with the prep arrays and pca_corrected_data."""
+    last_chr = {"A": 22, "F": 23}.get(gender, 24)
+    bins_per_chr = list(bins_per_chr[:last_chr])
+    mask = mask[: int(np.sum(bins_per_chr))]  # a view of the caller's total mask
+    chrs = range(1, last_chr + 1)
+    masked = newref_tools.normalize_and_mask(samples, chrs, mask, device)
+    corrected, pca = newref_tools.train_pca(masked, device=device)
+    d, _ = newref_tools.pca_distance(corrected, device=device)
+    mad = np.median(np.abs(d - np.median(d)))
+    cutoff = max(np.median(d) + 10 * mad, 5.0)  # newref_control.py:45
+    bad = d > cutoff
+    if np.any(bad):
+        logging.info("Removing {} anomalous bins based on PCA distance (cutoff={:.4f})".format(int(np.sum(bad)), cutoff))
+        masked_indices = np.where(mask)[0]
+        mask[masked_indices[bad]] = False
+        masked = newref_tools.normalize_and_mask(samples, chrs, mask, device)
+        corrected, pca = newref_tools.train_pca(masked, device=device)
+    offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
+    masked_bins_per_chr = [int(np.sum(mask[offs[i]:offs[i + 1]])) for i in range(len(bins_per_chr))]
+    return {
+        "gender": gender,
+        "mask": mask.copy(),
+        "bins_per_chr": np.array(bins_per_chr),
+        "masked_bins_per_chr": np.array(masked_bins_per_chr),
+        "masked_bins_per_chr_cum": np.cumsum(masked_bins_per_chr),
+        "pca_components": pca.components_,
+        "pca_mean": pca.mean_,
+        "pca_corrected_data": corrected,
+    }
+
+
+def tool_newref_main(prep, refsize, parts: int = 1, device: int = 0):
+    """get_reference over `parts` parts, concatenated in part order (reference tool_newref_main +
+    tool_newref_post, newref_control.py:90-189).  One null-sample draw per part, like the reference."""
+    x = prep["pca_corrected_data"]
+    per, cum = prep["masked_bins_per_chr"], prep["masked_bins_per_chr_cum"]
+    n, s = x.shape
+    eng = newref_tools.NewrefEngine(device)
+    eng.load(x, per, cum)
+    idx_parts, dist_parts, nr_parts = [], [], []
+    for part in range(1, parts + 1):
+        start, end = newref_tools._get_part(part - 1, parts, n)
+        sample_ids = random.sample(range(s), min(s, 100))  # newref_tools.py:214-217
+        idx, dist = eng.topk(start, end, refsize)
+        nr = eng.null_ratios(start, end, refsize, sample_ids)
+        idx_parts.append(idx); dist_parts.append(dist); nr_parts.append(nr)
+    out = {k: v for k, v in prep.items() if k != "pca_corrected_data"}
+    out["indexes"] = np.concatenate(idx_parts)
+    out["distances"] = np.concatenate(dist_parts)
+    out["null_ratios"] = np.concatenate(nr_parts)
+    return out
+
+
+def tool_newref_merge(outfile, results, binsize, is_nipt, trained_cutoff):
+    """Final reference .npz with the reference's key layout (newref_control.py:220-237): autosomal keys
+    plain, gonosomal keys suffixed .F / .M, plus has_female / has_male / is_nipt / trained_cutoff."""
+    final_ref = {"has_female": False, "has_male": False}
+    for res in results:
+        gender = res["gender"]
+        sfx = "" if gender == "A" else ".{}".format(gender)
+        if gender == "F":
+            final_ref["has_female"] = True
+        if gender == "M":
+            final_ref["has_male"] = True
+        final_ref["binsize" + sfx] = binsize
+        for key in ("mask", "bins_per_chr", "masked_bins_per_chr", "masked_bins_per_chr_cum", "pca_components", "pca_mean",
+                    "indexes", "distances", "null_ratios"):
+            final_ref[key + sfx] = res[key]
+    final_ref["is_nipt"] = is_nipt
+    final_ref["trained_cutoff"] = trained_cutoff
+    np.savez_compressed(outfile, **final_ref)
+    return final_ref

@@ -112,3 +112,88 @@ def get_reference(pca_corrected_data, masked_bins_per_chr, masked_bins_per_chr_c
     idx, dist = eng.topk(start_num, end_num, ref_size, kernel)
     nr = eng.null_ratios(start_num, end_num, ref_size, sample_ids)
     return idx, dist, nr
+
+
+# ---------------------------------------------------------------------------------------------
+# newref preparation (reference newref_tools.py:110-147, newref_control.py:38-58)
+# ---------------------------------------------------------------------------------------------
+class _PCAModel:
+    """What the reference keeps of the fitted sklearn PCA: ``components_`` and ``mean_``
+    (newref_control.py:78-79)."""
+
+    def __init__(self, components, mean, explained_variance):
+        self.components_ = components
+        self.mean_ = mean
+        self.explained_variance_ = explained_variance
+        self.n_components_ = components.shape[0]
+
+
+def stack_counts(samples, chrs):
+    """int32 [bins_total, S]: per-chromosome read counts of every sample, zero padded to the longest
+    sample (host half of normalize_and_mask, newref_tools.py:114-122)."""
+    lens = [max(len(s[str(c)]) for s in samples) for c in chrs]
+    total = int(sum(lens))
+    out = np.zeros((total, len(samples)), dtype=np.int32)
+    off = 0
+    for c, ln in zip(chrs, lens):
+        for i, s in enumerate(samples):
+            a = np.asarray(s[str(c)])
+            out[off:off + len(a), i] = a
+        off += ln
+    return out
+
+
+def normalize_and_mask(samples, chrs, mask, device: int = 0):
+    """Drop-in for newref_tools.normalize_and_mask (reference :110-129): read-depth normalisation
+    (each sample divided by its total) and masking.  Bit-exact with the reference."""
+    counts = np.ascontiguousarray(stack_counts(samples, chrs))
+    pos = np.ascontiguousarray(np.flatnonzero(np.asarray(mask, dtype=bool)[: counts.shape[0]]), dtype=np.int32)
+    out = np.empty((len(pos), counts.shape[1]), dtype=np.float64)
+    ctx = _lib.default_context(device)
+    _lib.check(_lib.load().wcx_newref_normalize_and_mask(ctx.handle, _ptr(counts), counts.shape[0], counts.shape[1], _ptr(pos),
+                                                         len(pos), _ptr(out), 0))
+    return out
+
+
+def train_pca(ref_data, pcacomp=5, device: int = 0, keep_on_device: bool = False):
+    """Drop-in for newref_tools.train_pca (reference :138-147): returns (corrected [N, S], pca) with
+    pca.components_ [pcacomp, N] and pca.mean_ [N].  The model is the exact PCA that sklearn's
+    randomized solver approximates: Gram matrix and correction on the GPU, the
+    S x S eigen-decomposition on the host."""
+    x = np.ascontiguousarray(ref_data, dtype=np.float64)
+    n, s = x.shape
+    L = _lib.load()
+    ctx = _lib.default_context(device)
+    mean = np.empty(n, dtype=np.float64)
+    gram = np.empty((s, s), dtype=np.float64)
+    _lib.check(L.wcx_pca_gram(ctx.handle, _ptr(x), n, s, 0, _ptr(mean), _ptr(gram)))
+    w, u = np.linalg.eigh(gram)
+    order = np.argsort(w)[::-1][:pcacomp]
+    lam = np.clip(w[order], 1e-300, None)
+    u = np.ascontiguousarray(u[:, order])
+    sigma = np.ascontiguousarray(np.sqrt(lam))
+    comps = np.empty((pcacomp, n), dtype=np.float64)
+    corrected = None if keep_on_device else np.empty((n, s), dtype=np.float64)
+    _lib.check(L.wcx_pca_apply(ctx.handle, _ptr(u), _ptr(sigma), pcacomp, _ptr(comps),
+                               None if keep_on_device else _ptr(corrected), 0))
+    # sklearn's sign convention (svd_flip, u_based_decision=False): largest |entry| of each row positive
+    piv = np.argmax(np.abs(comps), axis=1)
+    comps *= np.sign(comps[np.arange(pcacomp), piv])[:, None]
+    return corrected, _PCAModel(comps, mean, lam / max(s - 1, 1))
+
+
+def pca_distance(corrected=None, shape=None, device: int = 0):
+    """Per-sample median profile and per-bin squared distance to it (newref_control.py:40-41).
+    corrected=None uses the matrix left on the device by train_pca(keep_on_device=True)."""
+    L = _lib.load()
+    ctx = _lib.default_context(device)
+    if corrected is None:
+        n, s = shape
+        med = np.empty(s); d = np.empty(n)
+        _lib.check(L.wcx_pca_distance(ctx.handle, None, n, s, 1, _ptr(med), _ptr(d)))
+    else:
+        x = np.ascontiguousarray(corrected, dtype=np.float64)
+        n, s = x.shape
+        med = np.empty(s); d = np.empty(n)
+        _lib.check(L.wcx_pca_distance(ctx.handle, _ptr(x), n, s, 0, _ptr(med), _ptr(d)))
+    return d, med

@@ -140,18 +140,25 @@ def get_z_score(results_c, results, engine: PredictEngine | None = None):
     r = np.concatenate([np.asarray(x, dtype=np.float64) for x in results_r])
     w = np.concatenate([np.asarray(x, dtype=np.float64) for x in results_w])
     offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r])]).astype(np.int64)
-    rows = []
-    inflate = np.full(len(r), -1, dtype=np.int32)
-    g = 0
-    for chrom in results_nr:
-        for row in chrom:
-            if not isinstance(row, (int, float)):
-                inflate[g] = len(rows)
-                rows.append(row)
-            g += 1
-    if not rows:
-        return ["nan" for _ in results_c]
-    nr = np.asarray(rows, dtype=np.float64)
+    if isinstance(results_nr, dict):
+        # array form used by this package's own pipeline: dense [n_masked, M] rows + unmasked-bin -> row map
+        nr, inflate = results_nr["dense"], results_nr["inflate"]
+    else:
+        rows = []
+        inflate = np.full(len(r), -1, dtype=np.int32)
+        g = 0
+        for chrom in results_nr:
+            for row in chrom:
+                if not isinstance(row, (int, float)):
+                    inflate[g] = len(rows)
+                    rows.append(row)
+                g += 1
+        if not rows:
+            return ["nan" for _ in results_c]
+        width = max(len(x) for x in rows)
+        nr = np.full((len(rows), width), np.nan)
+        for i, x in enumerate(rows):
+            nr[i, :len(x)] = x
     seg_se = np.array([[offs[s[0]] + s[1], offs[s[0]] + s[2]] for s in results_c], dtype=np.int64).reshape(-1, 2)
     seg_r = np.array([s[3] for s in results_c], dtype=np.float64)
     z = (engine or default_engine()).segment_zscore(nr, inflate, r, w, seg_se, seg_r)
