@@ -16,15 +16,15 @@ BINSIZE = 1_000_000
 @pytest.fixture(scope="module")
 def workdir(tmp_path_factory):
     d = tmp_path_factory.mktemp("cli")
-    samples, genders = synth.make_samples(30, BINSIZE, seed=31, depth=6e6)
+    # 31 samples from one generative model (same bin profile / bias factors); the last one carries the CNV
+    samples, genders = synth.make_samples(31, BINSIZE, seed=31, depth=6e6, cnv=[(30, 5, 40, 90, 1.5)])
     files = []
-    for i, s in enumerate(samples):
+    for i, s in enumerate(samples[:30]):
         f = os.path.join(d, f"s{i}.npz")
         np.savez_compressed(f, binsize=BINSIZE, sample=s, quality={})
         files.append(f)
-    test, _ = synth.make_samples(1, BINSIZE, seed=77, depth=6e6, cnv=[(0, 5, 40, 90, 1.5)])
     tf = os.path.join(d, "test.npz")
-    np.savez_compressed(tf, binsize=BINSIZE, sample=test[0], quality={})
+    np.savez_compressed(tf, binsize=BINSIZE, sample=samples[30], quality={})
     return d, files, tf
 
 
