@@ -262,31 +262,30 @@ def run_ours(args, rank, world, local_rank):
     else:
         # rank 0 owns the host matrix: H2D on rank 0, NCCL broadcast over NVLink, sharded compute,
         # gather of the row blocks to rank 0, D2H on rank 0
+        from wisecondorx_b200 import parallel
         x_pin = torch.from_numpy(x).pin_memory() if rank == 0 else None
         xd = torch.empty((n, s), dtype=torch.float64, device=dev)
-        bounds = [newref_tools._get_part(r, world, n) for r in range(world)]
+        bounds = parallel.shard_bounds(n, world)
+        max_rows = max(b[1] - b[0] for b in bounds)
+        pads = [torch.zeros((max_rows, k), dtype=torch.int32, device=dev), torch.zeros((max_rows, k), dtype=torch.float64, device=dev),
+                torch.zeros((max_rows, m), dtype=torch.float64, device=dev)]
         if rank == 0:
-            g_idx = [torch.empty((b[1] - b[0], k), dtype=torch.int32, device=dev) for b in bounds]
-            g_dist = [torch.empty((b[1] - b[0], k), dtype=torch.float64, device=dev) for b in bounds]
-            g_nr = [torch.empty((b[1] - b[0], m), dtype=torch.float64, device=dev) for b in bounds]
-            idx_pin = torch.empty((n, k), dtype=torch.int32).pin_memory()
-            dist_pin = torch.empty((n, k), dtype=torch.float64).pin_memory()
-            nr_pin = torch.empty((n, m), dtype=torch.float64).pin_memory()
+            bufs = [[torch.empty_like(p) for _ in bounds] for p in pads]
+            pins = [torch.empty((n, k), dtype=torch.int32).pin_memory(), torch.empty((n, k), dtype=torch.float64).pin_memory(),
+                    torch.empty((n, m), dtype=torch.float64).pin_memory()]
 
         def step_e2e():
             if rank == 0:
                 xd.copy_(x_pin, non_blocking=True)
             dist.broadcast(xd, 0)
             eng.load(None, per, cum, on_device_ptr=xd.data_ptr(), shape=(n, s))
-            eng.topk(rb, re, k, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr()))
-            eng.null_ratios(rb, re, k, ids, device_out=nr_dev.data_ptr())
-            dist.gather(idx_dev, g_idx if rank == 0 else None, 0)
-            dist.gather(dist_dev, g_dist if rank == 0 else None, 0)
-            dist.gather(nr_dev, g_nr if rank == 0 else None, 0)
+            eng.topk(rb, re, k, device_out=(pads[0].data_ptr(), pads[1].data_ptr()))
+            eng.null_ratios(rb, re, k, ids, device_out=pads[2].data_ptr())
+            for i, p in enumerate(pads):
+                dist.gather(p, bufs[i] if rank == 0 else None, 0)
             if rank == 0:
-                idx_pin.copy_(torch.cat(g_idx), non_blocking=True)
-                dist_pin.copy_(torch.cat(g_dist), non_blocking=True)
-                nr_pin.copy_(torch.cat(g_nr), non_blocking=True)
+                for i in range(3):
+                    pins[i].copy_(torch.cat([bf[: b[1] - b[0]] for bf, b in zip(bufs[i], bounds)]), non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
         h2d = x.nbytes
