@@ -138,6 +138,61 @@ def cpu_reference_sample(x, per, cum, target_seconds=20.0):
                       f"C restatement of get_reference with OpenMP, {t_total:.1f} s"}
 
 
+def predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, device):
+    """BASELINE configs 4 / 5 (reported beside the headline metric): `normalize` (coverage + PCA projection +
+    3 within-sample passes) and the CUDA CBS for 1 and 96 test samples against the reference just built."""
+    import types
+    from wisecondorx_b200 import cbs, predict_control, predict_tools
+    n, s = x.shape
+    rng = np.random.default_rng(99)
+    comps = np.linalg.qr(rng.standard_normal((n, 5)))[0].T.copy()
+    ref = {"indexes": idx_dev.cpu().numpy(), "distances": dist_dev.cpu().numpy(), "masked_bins_per_chr": per,
+           "masked_bins_per_chr_cum": cum, "pca_components": comps, "pca_mean": np.full(n, 1.0 / n),
+           "mask": np.ones(n, dtype=bool), "bins_per_chr": per}
+    offs = np.concatenate([[0], cum]).astype(int)
+
+    def sample(i):
+        lam = 60.0 * np.clip(x[:, i % s], 0, None)
+        lam[offs[4] + 2000: offs[4] + 2400] *= 1.5  # planted 6 Mb gain on chr5
+        c = rng.poisson(lam).astype(np.int32)
+        return {str(k + 1): c[offs[k]:offs[k + 1]] for k in range(22)}
+
+    args = types.SimpleNamespace(maskrepeats=5)
+    pe = predict_tools.PredictEngine(device, eng.ctx)
+    out = {}
+    for b in (1, 96):
+        samples = [sample(i) for i in range(b)]
+        predict_control.normalize_batch(args, samples[:1], ref, "A", pe)  # load the reference arrays once, warm up
+        t0 = time.perf_counter()
+        r, z, w, nref, m_lr, m_z = predict_control.normalize_batch(args, samples, ref, "A", pe)
+        t_norm = time.perf_counter() - t0
+        sm = pe.stage_ms()
+        # CBS over all chromosomes of all samples in one batched call
+        series = []
+        for i in range(b):
+            lr = np.log2(r[i]) - m_lr[i]
+            ok = np.isfinite(lr) & (nref[i] >= 150) & (lr != 0)
+            for c in range(22):
+                m = ok[offs[c]:offs[c + 1]]
+                series.append((lr[offs[c]:offs[c + 1]][m], w[offs[c]:offs[c + 1]][m]))
+        t0 = time.perf_counter()
+        ends = cbs.segment_series(series, [i % 22 for i in range(len(series))], alpha=1e-4, nperm=10000, seed=1, ctx=eng.ctx)
+        t_cbs = time.perf_counter() - t0
+        nseg = sum(len(e) for e in ends)
+        out[f"batch{b}"] = {"normalize_wall_ms": t_norm * 1e3, "normalize_kernels_ms": sm["coverage_project"] + sm["normalize_repeat"],
+                            "cbs_wall_ms": t_cbs * 1e3, "cbs_kernels_ms": _cbs_ms(eng), "segments": nseg,
+                            "cbs_stats": cbs.cbs_stats(eng.ctx)}
+    return out
+
+
+def _cbs_ms(eng):
+    import ctypes
+    from wisecondorx_b200 import _lib
+    o = np.zeros(4)
+    _lib.check(_lib.load().wcx_predict_stage_ms(eng.ctx.handle, ctypes.c_void_p(o.ctypes.data)))
+    return float(o[3])
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -300,6 +355,13 @@ def run_ours(args, rank, world, local_rank):
         return
 
     peaks = load_peaks()
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dist_topk_tc_kernel"]
+        if tj["workload"] == args.workload and tj["n_gpus"] == world:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     # dominant kernel: the tensor-core sweep.  Algorithmic flops = 2 * S * pairs;
     # TF32 dense peak taken as half the measured bf16 cuBLAS figure (nominal 1:2 ratio).
     my_pairs = n_pairs(per, rb, re)
@@ -320,12 +382,14 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "dist_topk_tc_kernel", "achieved": achieved, "peak": peak_tf32,
-                     "unit": "TFLOP/s", "frac": (achieved / peak_tf32) if achieved else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (achieved / peak_tf32) if achieved else None, "traffic": traffic,
                      "peak_src": f"{peaks['src']}: bf16_tflops_sustained / 2 (tf32)",
                      "kernel_ms": sweep_ms},
         "stages_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
         "exact_fallback_rows": st["exact_fallback_rows"],
     }
+    if world == 1 and not args.no_predict:
+        out["predict"] = predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, local_rank)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_sample(x, per, cum, args.cpu_seconds)
     print(json.dumps(out), flush=True)
@@ -341,6 +405,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict", action="store_true", help="skip the predict (configs 4 / 5) timings")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
