@@ -103,6 +103,7 @@ __global__ void cbs_prepare_kernel(const double* __restrict__ y, const double* _
   if (s >= nseg) return;
   const int64_t lo = segs[s].lo, hi = segs[s].hi;
   double tw = 0.0, twx = 0.0, mn = y[lo], mx = y[lo];
+#pragma unroll 8
   for (int64_t t = lo; t < hi; t++) {
     const double v = y[t], ww = w[t];
     twx += v * ww;
@@ -113,6 +114,7 @@ __global__ void cbs_prepare_kernel(const double* __restrict__ y, const double* _
   const double avg = twx / tw;
   const double rtw = sqrt(tw);
   double tss = 0.0, tssy = 0.0, asx = 0.0, acw = 0.0;
+#pragma unroll 8
   for (int64_t t = lo; t < hi; t++) {
     const double ww = w[t];
     const double x = y[t] - avg;
@@ -328,6 +330,80 @@ cbs_tperm_kernel(const double* __restrict__ xc, const double* __restrict__ w, TJ
   if (jb.ostat <= pstat) atomicAdd(&jobs[q].nrej, 1);
 }
 
+// ------------------------------------------------------------------------------------------
+// hybrid p-value, part 1: Siegmund's nu(x) on the integration grid of DNAcopy's `tailp`.
+// nu(x) = (2 / x^2) exp(-2 sum_{k>=1} Phi(-x sqrt(k) / 2) / k); for the small x of long segments
+// the series needs 1e4..1e6 terms per grid point (what makes this step seconds on a CPU), so it is
+// summed here: one block per (grid point, job), the doubling stages of the reference loop kept
+// (stage sums reduced in parallel), convergence test |delta / lnu| <= tol after every stage.
+// out[job][i] = nu(x_i)^2 * integral_{tl_i}^{tl_i + dincr} dt / (t (1 - t))^2
+// ------------------------------------------------------------------------------------------
+struct TailJob {
+  double b;      // sqrt of the observed statistic
+  double delta;  // (kmax + 1) / n
+  int32_t m;     // segment length
+  int32_t pad;
+};
+
+__device__ __forceinline__ double dev_pnorm(double x) { return 0.5 * erfc(-x / 1.4142135623730951); }
+
+__device__ __forceinline__ double dev_it1tsq(double x, double a) {
+  double y = x + a - 0.5;
+  double v = (8.0 * y) / (1.0 - 4.0 * y * y) + 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+  y = x - 0.5;
+  return v - (8.0 * y) / (1.0 - 4.0 * y * y) - 2.0 * log((1.0 + 2.0 * y) / (1.0 - 2.0 * y));
+}
+
+__global__ void __launch_bounds__(256)
+cbs_tailp_kernel(const TailJob* __restrict__ jobs, int ngrid, double tol, double* __restrict__ out) {
+  __shared__ double sh[8];
+  __shared__ double s_stage;
+  const TailJob jb = jobs[blockIdx.y];
+  const int gi = blockIdx.x;
+  const double dincr = (0.5 - jb.delta) / (double)ngrid;
+  const double bsqrtm = jb.b / sqrt((double)jb.m);
+  const double tl = 0.5 + (double)gi * dincr;            // tl after gi + 1 increments from 0.5 - dincr
+  const double t = 0.5 - 0.5 * dincr + (double)(gi + 1) * dincr;
+  const double x = bsqrtm / sqrt(t * (1.0 - t));
+  double lnu1;
+  if (x > 0.01) {
+    lnu1 = log(2.0) - 2.0 * log(x);
+    double lnu0 = lnu1;
+    long long k0 = 0, kn = 2;  // stage covers k in (k0, k0 + kn]; reference stages: 2, then 2, 4, 8, ...
+    bool first = true;
+    for (;;) {
+      double part = 0.0;
+      for (long long k = k0 + 1 + threadIdx.x; k <= k0 + kn; k += blockDim.x) {
+        const double dk = (double)k;
+        part += 2.0 * dev_pnorm(-x * sqrt(dk) / 2.0) / dk;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; w++) tot += sh[w];
+        s_stage = tot;
+      }
+      __syncthreads();
+      if (!first) lnu0 = lnu1;
+      lnu1 = lnu1 - s_stage;
+      k0 += kn;
+      if (!(fabs((lnu1 - lnu0) / lnu1) > tol)) break;  // `while (abs((lnu1 - lnu0) / lnu1) > tol)`
+      if (first) first = false; else kn *= 2;          // 2 more terms, then the stage size doubles
+      if (k0 > (1ll << 40)) break;
+    }
+  } else {
+    lnu1 = -0.583 * x;
+  }
+  if (threadIdx.x == 0) {
+    const double nux = exp(lnu1);
+    out[(int64_t)blockIdx.y * ngrid + gi] = (nux * nux) * dev_it1tsq(tl, dincr);
+  }
+}
+
 // ---------------- host-side scalar maths (DNAcopy tailp / nu / it1tsq) ----------------
 double pnorm_(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
 
@@ -463,6 +539,40 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
       const ArcBest& p = partial[c];
       if ((p.bss > b.bss) || (p.bss == b.bss && (p.i < b.i || (p.i == b.i && p.j < b.j)))) b = p;
     }
+    // hybrid p-value, part 1 on the device for every segment that needs it this round
+    std::vector<double> pval1_of(nseg, 2.0);
+    {
+      std::vector<TailJob> tjobs;
+      std::vector<int> tseg;
+      for (int s = 0; s < nseg; s++) {
+        const int n = (int)(work[s].hi - work[s].lo);
+        if (prep[s].flat || best[s].bss < 0.0 || n <= nmin) continue;
+        const double ostat = best[s].bss / ((prep[s].tss - best[s].bss) / ((double)n - 2.0));
+        const double ostat1 = ostat > 0 ? std::sqrt(ostat) : 0.0;
+        const int width = best[s].j - best[s].i;
+        const int l = std::min(width, n - width);
+        if (ostat1 <= 0.1 || (ostat1 >= 7.0 && l >= 10)) continue;
+        tjobs.push_back(TailJob{ostat1, ((double)kmax + 1.0) / (double)n, n, 0});
+        tseg.push_back(s);
+      }
+      if (!tjobs.empty()) {
+        const int ngrid = 100;
+        const int nj = (int)tjobs.size();
+        if (ws->tjobs.ensure(sizeof(TailJob) * nj) || ws->scratch.ensure(sizeof(double) * (size_t)nj * ngrid)) return 1;
+        WCX_CUDA_OK(cudaMemcpyAsync(ws->tjobs.p, tjobs.data(), sizeof(TailJob) * nj, cudaMemcpyHostToDevice, st));
+        cbs_tailp_kernel<<<dim3(ngrid, nj), 256, 0, st>>>(ws->tjobs.as<TailJob>(), ngrid, 1e-6, ws->scratch.as<double>());
+        std::vector<double> terms((size_t)nj * ngrid);
+        WCX_CUDA_OK(cudaMemcpyAsync(terms.data(), ws->scratch.p, sizeof(double) * terms.size(), cudaMemcpyDeviceToHost, st));
+        WCX_CUDA_OK(cudaStreamSynchronize(st));
+        if (stats) stats->launches++;
+        for (int q = 0; q < nj; q++) {
+          double acc = 0.0;
+          for (int i = 0; i < ngrid; i++) acc += terms[(size_t)q * ngrid + i];
+          const double b = tjobs[q].b;
+          pval1_of[tseg[q]] = 9.973557e-2 * (b * b * b) * std::exp(-b * b / 2.0) * acc;
+        }
+      }
+    }
     // decisions
     for (int s = 0; s < nseg; s++) {
       const Seg& sg = work[s];
@@ -488,8 +598,7 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
             bool run = true;
             int mw = -1;
             if (hybrid) {
-              const double delta = ((double)kmax + 1.0) / (double)n;
-              const double pval1 = tailp_(ostat1, delta, n, 100, 1e-6);
+              const double pval1 = pval1_of[s];
               if (pval1 > alpha) run = false;
               nrejc = (int)((alpha - pval1) * (double)nperm);
               mw = kmax;
