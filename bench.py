@@ -248,7 +248,7 @@ def run_ours(args, rank, world, local_rank):
     nr_dev = torch.empty((rows, m), dtype=torch.float64, device=dev)
 
     def step_resident():
-        eng.topk(rb, re, k, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr()))
+        eng.topk(rb, re, k, kernel=args.kernel, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr()))
         eng.null_ratios(rb, re, k, ids, device_out=nr_dev.data_ptr())
 
     def barrier():
@@ -307,7 +307,7 @@ def run_ours(args, rank, world, local_rank):
 
         def step_e2e():
             eng.load(xh, per, cum)
-            eng.topk(rb, re, k, out=(ih, dh))
+            eng.topk(rb, re, k, kernel=args.kernel, out=(ih, dh))
             eng.null_ratios(rb, re, k, ids, out=nh)
 
         h2d = x.nbytes
@@ -406,6 +406,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true", help="skip the predict (configs 4 / 5) timings")
+    ap.add_argument("--kernel", type=int, default=0, help="sweep kernel (include/wcx_b200.h WCX_KERNEL_*), 0 = default")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

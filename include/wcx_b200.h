@@ -26,10 +26,11 @@ extern "C" {
 typedef struct wcx_ctx wcx_ctx;
 
 /* kernel selector for the distance sweep */
-#define WCX_KERNEL_AUTO 0 /* tcgen05 tensor-core kernel */
-#define WCX_KERNEL_TC 1   /* tcgen05 / TMEM / TMA kernel (dist_topk_tc.cu) */
+#define WCX_KERNEL_AUTO 0 /* = WCX_KERNEL_TC2 */
+#define WCX_KERNEL_TC 1   /* tcgen05 / TMEM / TMA kernel, one CTA per SM (dist_topk_tc.cu) */
 #define WCX_KERNEL_SIMT 2 /* CUDA-core fp32 kernel (dist_topk_simt.cu), cross-check path */
 #define WCX_KERNEL_EXACT 3 /* brute-force float64 rows only (exact_rows_kernel), slow, for tests */
+#define WCX_KERNEL_TC2 4  /* tcgen05 kernel in 2-CTA pair mode (cta_group::2, halves the B-operand traffic) */
 
 int wcx_version(void);
 const char* wcx_last_error(void);

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 from oracle import c_oracle, np_oracle  # noqa: E402
 from wisecondorx_b200 import _lib, newref_tools, synth  # noqa: E402
 
-KERNELS = {"tc": _lib.KERNEL_TC, "simt": _lib.KERNEL_SIMT, "exact": _lib.KERNEL_EXACT}
+KERNELS = {"tc": _lib.KERNEL_TC, "simt": _lib.KERNEL_SIMT, "exact": _lib.KERNEL_EXACT, "tc2": _lib.KERNEL_TC2}
 
 
 @pytest.fixture(scope="module")
@@ -77,7 +77,7 @@ def test_tensor_core_tile_matches_fp64_matmul(eng):
         assert err < 1e-5 * max(1.0, np.abs(want).max()), (row0, col0, err, np.abs(want).max())
 
 
-@pytest.mark.parametrize("kernel", ["tc", "simt", "exact"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "simt", "exact"])
 @pytest.mark.parametrize("case,part,parts,k", [("A_p11", 1, 1, 30), ("A_p23", 2, 3, 30), ("G", 1, 1, 30),
                                                 ("T", 1, 1, 12), ("S", 1, 1, 20)])
 def test_golden_get_reference(gref, kernel, case, part, parts, k):
@@ -99,7 +99,7 @@ def test_random_draw_follows_python_random(gref):
     np.testing.assert_allclose(nr, gref["A_p11_nr"], rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("kernel", ["tc", "simt"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "simt"])
 def test_config1_full_vs_c_oracle(eng, kernel):
     """BASELINE config 1: 1 Mb bins (2887 autosomal), 20 samples, refsize 300 -- full parity."""
     per = synth.config_bins(1)
@@ -118,7 +118,7 @@ def test_config1_full_vs_c_oracle(eng, kernel):
     assert st["exact_fallback_rows"] <= n // 50, st
 
 
-@pytest.mark.parametrize("kernel", ["tc", "simt"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "simt"])
 def test_config2_parts_vs_c_oracle(eng, kernel):
     """BASELINE config 2: 100 kb bins (28760), 100 samples, refsize 300; parts compared in full."""
     per = synth.config_bins(2)
@@ -148,6 +148,9 @@ def test_tc_equals_simt_whole_config2(eng):
     st1 = eng.stats()
     i2, d2 = eng.topk(0, n, 300, KERNELS["simt"])
     assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    i3, d3 = eng.topk(0, n, 300, KERNELS["tc2"])
+    assert np.array_equal(i1, i3) and np.array_equal(d1, d3)
+    assert eng.stats()["exact_fallback_rows"] <= n // 100
     assert st1["exact_fallback_rows"] <= n // 100, st1
     # sortedness + index range: size-independent properties
     assert (np.diff(d1, axis=1) >= 0).all()
@@ -162,7 +165,7 @@ def test_edge_cases(eng):
     x[5, 3] = np.nan
     n = x.shape[0]
     oi, od = c_oracle.topk(x, per, cum, 64, 0, n)
-    for kernel in ("tc", "simt", "exact"):
+    for kernel in ("tc", "tc2", "simt", "exact"):
         eng.load(x, per, cum)
         idx, dist = eng.topk(0, n, 64, KERNELS[kernel])
         assert np.array_equal(idx, oi), kernel
@@ -181,3 +184,29 @@ def test_bad_arguments_raise(eng):
         eng.topk(0, 10, 0)
     with pytest.raises(_lib.WcxError):
         eng.null_ratios(0, 10, 10, [99])
+
+
+@pytest.mark.parametrize("kernel", ["tc", "tc2"])
+def test_nasty_data_vs_c_oracle(eng, kernel):
+    """Duplicated bins (exact distance ties), outlier bins with huge norms, constant bins, a few
+    NaN / inf rows, heavy-tailed noise: indexes and distances must still be bit-exact."""
+    rng = np.random.default_rng(33)
+    per = (synth.config_bins(2) // 4).astype(np.int64)
+    x, per, cum = synth.make_corrected_matrix(per, 64, seed=34)
+    n = x.shape[0]
+    x *= 1.0 + 0.02 * rng.standard_t(2.5, size=x.shape)          # heavy tails
+    dup = rng.choice(n, 400, replace=False)
+    x[dup[200:]] = x[dup[:200]]                                   # 200 exact duplicate pairs
+    x[rng.choice(n, 30, replace=False)] *= 25.0                   # outlier bins
+    x[rng.choice(n, 20, replace=False)] = 1.0                     # constant bins (mutual distance 0)
+    x[rng.choice(n, 3, replace=False), 5] = np.nan
+    x[rng.choice(n, 2, replace=False), 7] = np.inf
+    eng.load(x, per, cum)
+    rows = np.concatenate([dup[:40], rng.choice(n, 200, replace=False)])
+    idx, dist = eng.topk(0, n, 300, KERNELS[kernel])
+    st = eng.stats()
+    for r in np.sort(rows)[::7]:
+        oi, od = c_oracle.topk(x, per, cum, 300, int(r), int(r) + 1)
+        assert np.array_equal(idx[r], oi[0]), (kernel, int(r))
+        assert np.array_equal(dist[r], od[0]), (kernel, int(r))
+    assert st["exact_fallback_rows"] <= n // 20, st

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libwcx_b200.so")
 HEADER = os.path.abspath(os.path.join(HERE, "..", "include", "wcx_b200.h"))
 
-KERNEL_AUTO, KERNEL_TC, KERNEL_SIMT, KERNEL_EXACT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_TC, KERNEL_SIMT, KERNEL_EXACT, KERNEL_TC2 = 0, 1, 2, 3, 4
 
 _lib = None
 

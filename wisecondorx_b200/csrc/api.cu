@@ -17,6 +17,8 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 int launch_dist_topk_tc_debug(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                               void* tmap_storage, float* dbg_acc, cudaStream_t st);
+int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage,
+                             cudaStream_t st);
 }  // namespace wcx
 
 using namespace wcx;
@@ -261,7 +263,7 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
   std::memset(c->stats, 0, sizeof(c->stats));
   c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0.0;
   if (rows == 0) return 0;
-  if (kernel == WCX_KERNEL_AUTO) kernel = WCX_KERNEL_TC;
+  if (kernel == WCX_KERNEL_AUTO) kernel = WCX_KERNEL_TC2;
   const int gon = c->nchr > 22 ? 1 : 0;
   if (c->idx_dev.ensure(sizeof(int32_t) * (size_t)rows * k) || c->dist_dev.ensure(sizeof(double) * (size_t)rows * k))
     return 1;
@@ -301,6 +303,22 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
       items.clear();
       build_items(c, rb, re, tile_n, nsplit, lps, items);
     }
+    if (kernel == WCX_KERNEL_TC2) {
+      // pair mode: items (2p, 2p + 1) must share the candidate-column range -> group by split, pad odd groups
+      std::vector<WorkItem> paired;
+      for (int q = 0; q < nsplit; q++) {
+        int cnt = 0;
+        WorkItem last{};
+        for (const WorkItem& w : items)
+          if ((w.slot0 % (nsplit * lps)) / lps == q) { paired.push_back(w); last = w; cnt++; }
+        if (cnt & 1) {
+          WorkItem d = last;
+          d.row0 = 0; d.nrows = 0; d.slot0 = 0;
+          paired.push_back(d);
+        }
+      }
+      items.swap(paired);
+    }
     const size_t slots = (size_t)rows * nsplit * lps;
     if (c->cand_ent.ensure(sizeof(uint2) * slots * WCX_CAND_CAP) || c->cand_cnt.ensure(sizeof(int32_t) * slots) || c->cand_cut.ensure(sizeof(float) * slots))
       return 1;
@@ -314,6 +332,8 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
     if (kernel == WCX_KERNEL_SIMT) {
       if (launch_dist_topk_simt(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), st)) return 1;
+    } else if (kernel == WCX_KERNEL_TC2) {
+      if (launch_dist_topk_tc_pair(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->tmap, st)) return 1;
     } else {
       if (launch_dist_topk_tc(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), c->tmap, st)) return 1;
     }

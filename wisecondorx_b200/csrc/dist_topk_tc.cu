@@ -40,14 +40,19 @@ namespace {
 constexpr int TM = WCX_TILE_M;          // 128
 constexpr int TN = WCX_TILE_N_TC;       // 256
 constexpr int BK = WCX_KBLOCK;          // 32 tf32 = 128 bytes
-constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * BK * 4;    // 16 KB
-constexpr int B_BYTES = TN * BK * 4;    // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int B_BYTES = TN * BK * 4;    // 32 KB (1-CTA mode); a CTA of a pair stages half of it
 constexpr int TC_THREADS = 384;
 constexpr int NORM_BYTES = 8 * TN * 4;  // per-epilogue-warp copy of the tile's candidate norms
 constexpr int THR_BYTES = 2 * TM * 8;   // (item, thr) words exchanged between the two epilogue groups
-constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NORM_BYTES + THR_BYTES;
+constexpr int SPILL_BYTES = 256 * 16 * 4;  // 16 floats per epilogue thread (half a chunk), see filter_chunk
+
+template <bool PAIR> struct Cfg {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int B_STAGE = PAIR ? B_BYTES / 2 : B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NORM_BYTES + THR_BYTES + SPILL_BYTES;
+};
 constexpr int INIT_N = 512;             // entries collected before the first exact selection
 constexpr int KEEP = WCX_CAND_KEEP_TC;  // per-list guarantee; the row's two lists together hold >= 2 * KEEP
 constexpr uint32_t TMEM_COLS = 512;
@@ -55,6 +60,10 @@ constexpr uint32_t TMEM_COLS = 512;
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=TF32, K-major both,
 // N = 256 (n_dim = N >> 3 at bit 17), M = 128 (m_dim = M >> 4 at bit 24)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// cta_group::2: the instruction spans both CTAs of the pair, M = 256 (128 rows from each CTA), N = 256
+// (128 candidate columns staged by each CTA)
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -86,6 +95,51 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// pair mode: the load lands in the issuing CTA's shared memory, the bytes are credited to CTA 0's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in both CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on CTA 0's copy of a barrier from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -189,41 +243,68 @@ __device__ __forceinline__ void append(RowState& st, uint2* be, float v, int g) 
   st.c3 += (v < st.p3) ? 1 : 0;
 }
 
-// 32 accumulator columns of one row against the staged norms
+// 32 accumulator columns of one row against the staged norms.
+//
+// Appends are rare per lane (about 2 % of the elements) but almost every group of columns has SOME
+// lane of the warp that passes, so a per-element `if (v < thr) append()` makes the whole warp walk
+// the append code for nearly every element (r01b profile: ~6500 instructions per tile and warp,
+// instruction-cache misses on the unrolled copies).  Instead the hot loop is branch-free: it only
+// builds a 16-bit pass mask per half chunk; lanes with a non-zero mask park their 16 values in a
+// private shared-memory strip and drain the set bits in a compact loop in which every lane works on
+// its own entries at the same time.
 template <bool ALL_VALID>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], const float* __restrict__ snorm, int g0,
-                                             const WorkItem& w, int64_t n, RowState& st, uint2* be) {
+                                             const WorkItem& w, int64_t n, RowState& st, uint2* be,
+                                             float* __restrict__ spill) {
 #pragma unroll
-  for (int j4 = 0; j4 < 8; j4++) {
-    const float4 nb = *reinterpret_cast<const float4*>(snorm + 4 * j4);
-    const float v0 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 0]), nb.x);
-    const float v1 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 1]), nb.y);
-    const float v2 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 2]), nb.z);
-    const float v3 = fmaf(-2.f, __uint_as_float(r[4 * j4 + 3]), nb.w);
-    const float mn = fminf(fminf(v0, v1), fminf(v2, v3));
-    if (mn < st.thr) {
-      const int g = g0 + 4 * j4;
-      if (ALL_VALID) {
-        if (v0 < st.thr) append(st, be, v0, g);
-        if (v1 < st.thr) append(st, be, v1, g + 1);
-        if (v2 < st.thr) append(st, be, v2, g + 2);
-        if (v3 < st.thr) append(st, be, v3, g + 3);
-      } else {
-        const float vv[4] = {v0, v1, v2, v3};
+  for (int half = 0; half < 2; half++) {
+    float v[16];
+    uint32_t mask = 0;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int gg = g + e;
-          const bool ok = (gg < n) && !(gg >= w.chr_s && gg < w.chr_e);
-          if (ok && vv[e] < st.thr) append(st, be, vv[e], gg);
-        }
+    for (int j4 = 0; j4 < 4; j4++) {
+      const float4 nb = *reinterpret_cast<const float4*>(snorm + half * 16 + 4 * j4);
+      v[4 * j4 + 0] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 0]), nb.x);
+      v[4 * j4 + 1] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 1]), nb.y);
+      v[4 * j4 + 2] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 2]), nb.z);
+      v[4 * j4 + 3] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 3]), nb.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      bool ok = v[j] < st.thr;
+      if (!ALL_VALID) {
+        const int gg = g0 + half * 16 + j;
+        ok = ok && (gg < n) && !(gg >= w.chr_s && gg < w.chr_e);
+      }
+      mask |= ok ? (1u << j) : 0u;
+    }
+    if (mask) {
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        *reinterpret_cast<float4*>(spill + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        append(st, be, spill[j], g0 + half * 16 + j);
       }
     }
   }
 }
 
+// PAIR = false: one CTA per SM, cta_group::1, item i -> CTA (i mod grid).
+// PAIR = true : clusters of two CTAs (one SM each) cooperate through cta_group::2: items 2p and 2p + 1
+//               (same candidate-column range) form a 256-row tile; each CTA stages its own 128 target
+//               rows and HALF of the 256 candidate columns, so the L2 -> SM operand traffic per tile
+//               drops from 768 KB to 512 KB per SM; the leader CTA issues the MMAs for both.
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const WorkItem* __restrict__ items,
                     int nitems, CandView cv, float* __restrict__ dbg_acc) {
+  constexpr int STAGES = Cfg<PAIR>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work unit (item or item pair)
+  const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int nunits = PAIR ? (nitems >> 1) : nitems;
   extern __shared__ unsigned char tc_smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -236,6 +317,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
   float* s_norm = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [8 warps][TN]
   // [2 groups][TM] words (item << 32 | float bits of thr): a threshold is only adopted from the same work item
   volatile unsigned long long* s_thr = reinterpret_cast<volatile unsigned long long*>(s_norm + 8 * TN);
+  float* s_spill = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + NORM_BYTES + THR_BYTES);  // [256][16]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -246,17 +328,25 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -265,32 +355,39 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const WorkItem w = items[item];
+      for (int unit = unit0; unit < nunits; unit += unit_step) {
+        const WorkItem w = items[PAIR ? 2 * unit + (int)crank : unit];
         for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
           const int col0 = ct * TN;
           for (int kb = 0; kb < kblocks; kb++) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* sa = smem + stage * STAGE_BYTES;
             unsigned char* sb = sa + A_BYTES;
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(sa, &tmap, &full[stage], kb * BK, w.row0);
-            tma_load_2d(sb, &tmap, &full[stage], kb * BK, col0);
-            tma_load_2d(sb + B_BYTES / 2, &tmap, &full[stage], kb * BK, col0 + TN / 2);
+            if (PAIR) {
+              // CTA 0's barrier collects the bytes of both CTAs (2 x 32 KB per stage)
+              if (crank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+              tma_load_2d_pair(sa, &tmap, &full[stage], kb * BK, w.row0);
+              tma_load_2d_pair(sb, &tmap, &full[stage], kb * BK, col0 + (int)crank * (TN / 2));
+            } else {
+              mbar_expect_tx(&full[stage], STAGE_BYTES);
+              tma_load_2d(sa, &tmap, &full[stage], kb * BK, w.row0);
+              tma_load_2d(sb, &tmap, &full[stage], kb * BK, col0);
+              tma_load_2d(sb + B_BYTES / 2, &tmap, &full[stage], kb * BK, col0 + TN / 2);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (pair mode: leader CTA only) =====================
+    if (lane == 0 && crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
       uint32_t tphase = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const WorkItem w = items[item];
+      for (int unit = unit0; unit < nunits; unit += unit_step) {
+        const WorkItem w = items[PAIR ? 2 * unit : unit];
         for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
           mbar_wait(&tempty[buf], tphase ^ 1);
           tc_fence_after();
@@ -304,12 +401,15 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
 #pragma unroll
             for (int k = 0; k < BK / 8; k++) {
               // advance 8 tf32 = 32 bytes along K inside the 128B swizzle row: +2 in the >>4 address field
-              umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
+              if (PAIR) umma_tf32_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
+              else umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+            // smem slot reusable once these MMAs have read it (pair mode: in both CTAs)
+            if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull[buf]);  // accumulator complete
+          // accumulator complete (pair mode: each CTA's epilogue waits on its own copy)
+          if (PAIR) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]);
           if (++buf == 2) { buf = 0; tphase ^= 1; }
         }
       }
@@ -320,10 +420,12 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     float* snorm = s_norm + (warp - 4) * TN;
+    float* spill = s_spill + (threadIdx.x - 128) * 16;
     uint32_t tphase = 0;
     int tile_no = 0;  // running count of tiles of this CTA (parity selects the group)
     bool dbg_done = false;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    for (int unit = unit0; unit < nunits; unit += unit_step) {
+      const int item = PAIR ? 2 * unit + (int)crank : unit;
       const WorkItem w = items[item];
       const bool row_ok = row < w.nrows;
       const int64_t slot = (int64_t)w.slot0 + (int64_t)row * w.slot_stride + grp;
@@ -347,7 +449,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
           tc_fence_after();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[grp]);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[grp]); else mbar_arrive(&tempty[grp]); }
           continue;
         }
         // stage the candidate norms of this tile (issued before waiting for the accumulator)
@@ -376,22 +478,22 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
 #pragma unroll
             for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + j] = __uint_as_float(ra[j]);
           }
-          if (tile_valid) filter_chunk<true>(ra, snorm + c0, col0 + c0, w, pv.n, st, be);
-          else filter_chunk<false>(ra, snorm + c0, col0 + c0, w, pv.n, st, be);
+          if (tile_valid) filter_chunk<true>(ra, snorm + c0, col0 + c0, w, pv.n, st, be, spill);
+          else filter_chunk<false>(ra, snorm + c0, col0 + c0, w, pv.n, st, be, spill);
           tmem_ld_wait();
           if (c0 + 64 < TN) tmem_ld32(taddr + (uint32_t)(c0 + 64), ra);
           if (dbg_acc != nullptr && !dbg_done && blockIdx.x == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + 32 + j] = __uint_as_float(rb[j]);
           }
-          if (tile_valid) filter_chunk<true>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be);
-          else filter_chunk<false>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be);
+          if (tile_valid) filter_chunk<true>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be, spill);
+          else filter_chunk<false>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be, spill);
         }
         dbg_done = true;
         // accumulator buffer drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[grp]);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[grp]); else mbar_arrive(&tempty[grp]); }
         // threshold maintenance
         const float thr_before = st.thr;
         ladder_advance(st);
@@ -424,9 +526,11 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -464,7 +568,7 @@ int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitem
   if (nitems == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM));
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -473,16 +577,47 @@ int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitem
   const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
   int grid = nitems < sms ? nitems : sms;
   float* dbg = nullptr;
-  dist_topk_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(*map, pv, items, nitems, cv, dbg);
+  dist_topk_tc_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg);
   WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// pair mode: `items` holds an even number of entries, (2p, 2p + 1) sharing one candidate-column range
+int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage,
+                             cudaStream_t st) {
+  if (nitems == 0) return 0;
+  if (nitems & 1) { set_error("pair sweep: odd number of work items"); return 1; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
+  const int npairs = nitems / 2;
+  const int pairs_grid = npairs < sms / 2 ? npairs : sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs_grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg<true>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  float* dbg = nullptr;
+  WCX_CUDA_OK(cudaLaunchKernelEx(&cfg, dist_topk_tc_kernel<true>, *map, pv, items, nitems, cv, dbg));
   return 0;
 }
 
 int launch_dist_topk_tc_debug(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                               void* tmap_storage, float* dbg_acc, cudaStream_t st) {
-  WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM));
   const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
-  dist_topk_tc_kernel<<<1, TC_THREADS, TC_SMEM, st>>>(*map, pv, items, nitems, cv, dbg_acc);
+  dist_topk_tc_kernel<false><<<1, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg_acc);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
