@@ -2,6 +2,7 @@
 // management, work-item construction, stage timing; all arithmetic is in the kernels.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,15 +59,18 @@ struct wcx_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished outputs overlapped with the next stage
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev[8] = {};
   // newref state
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
   DevBuf x_buf, xc, norm, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
-  DevBuf fail, fail_rows, plan_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg, diag;
+  DevBuf fail, fail_rows, plan_dev, leaves_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg, diag;
   int64_t n = 0, n_pad = 0;
   int32_t s = 0, k_pad = 0, nchr = 0;
   std::vector<int64_t> per, cum;
   int32_t plan_len = 0;
+  int32_t plan_leaves = 0, plan_depth = 0;
   alignas(128) unsigned char tmap[128];
   bool loaded = false;
   // last topk
@@ -128,6 +132,8 @@ int wcx_create(int32_t device, wcx_ctx** out) {
   c->device = device;
   WCX_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  WCX_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  WCX_CUDA_OK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
   for (auto& e : c->ev) WCX_CUDA_OK(cudaEventCreate(&e));
   *out = c;
   return 0;
@@ -138,7 +144,7 @@ void wcx_destroy(wcx_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
-                    &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev,
+                    &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev, &c->leaves_dev,
                     &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
                     &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out})
@@ -151,6 +157,8 @@ void wcx_destroy(wcx_ctx* c) {
   if (c->cbs) cbs_workspace_destroy(c->cbs);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -212,6 +220,14 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   int pl = build_sum_plan(s, plan.data(), (int32_t)plan.size());
   if (pl < 0) { set_error("wcx_newref_load: too many samples for the summation plan"); return 1; }
   c->plan_len = pl;
+  {
+    std::vector<int32_t> leaves;
+    c->plan_leaves = plan_to_leaves(plan.data(), pl, leaves, &c->plan_depth);
+    if (c->plan_leaves < 0) { set_error("wcx_newref_load: malformed summation plan"); return 1; }
+    if (c->leaves_dev.ensure(sizeof(int32_t) * leaves.size())) return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(c->leaves_dev.p, leaves.data(), sizeof(int32_t) * leaves.size(), cudaMemcpyHostToDevice, st));
+    WCX_CUDA_OK(cudaStreamSynchronize(st));  // `leaves` goes out of scope
+  }
   if (c->plan_dev.ensure(sizeof(int32_t) * 3 * (size_t)pl)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->plan_dev.p, plan.data(), sizeof(int32_t) * 3 * (size_t)pl, cudaMemcpyHostToDevice, st));
   PrepView pv = prep_view(c);
@@ -338,7 +354,17 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
       if (launch_dist_topk_tc(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), c->tmap, st)) return 1;
     }
     WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
-    if (launch_rerank(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
+    // The bulk-copy re-rank (rerank_bulk.cu) is an opt-in experiment (WCX_RERANK_BULK=warps,stages): at config 3 it
+    // measured 82 ms against 50 ms for the LDG kernel (profiles/r01c_ncu_rerank_bulk.txt).
+    static const bool use_bulk = std::getenv("WCX_RERANK_BULK") != nullptr;
+    int rt = 1;
+    if (use_bulk)
+      rt = launch_rerank_bulk(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
+                              c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->leaves_dev.as<int32_t>(), c->plan_leaves,
+                              c->plan_depth, st);
+    if (rt < 0) return 1;
+    if (rt == 1 &&
+        launch_rerank(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
                       c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->plan_dev.as<int32_t>(), c->plan_len, st))
       return 1;
     WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
@@ -444,10 +470,20 @@ int wcx_get_reference(wcx_ctx* c, const double* x, int64_t n, int32_t s, const i
                       int32_t k, int64_t rb, int64_t re, const int32_t* sample_ids, int32_t m, int32_t kernel,
                       int32_t* idx_out, double* dist_out, double* null_out) {
   if (wcx_newref_load(c, x, n, s, per, cum, nchr, 0)) return 1;
-  if (wcx_newref_topk(c, rb, re, k, kernel, idx_out, dist_out, 0)) return 1;
-  if (null_out && m > 0)
-    if (wcx_newref_null_ratios(c, nullptr, 1, rb, re, k, sample_ids, m, null_out, 0)) return 1;
-  return 0;
+  // indexes / distances stay on the device; their D2H copy runs on the copy stream while the null-ratio
+  // kernels run on the main stream
+  if (wcx_newref_topk(c, rb, re, k, kernel, nullptr, nullptr, 1)) return 1;
+  const int64_t rows = re - rb;
+  if (rows > 0) {
+    WCX_CUDA_OK(cudaEventRecord(c->ev_copy, c->stream));
+    WCX_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+    if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out, c->idx_dev.p, sizeof(int32_t) * (size_t)rows * k, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out, c->dist_dev.p, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  int rc = 0;
+  if (null_out && m > 0) rc = wcx_newref_null_ratios(c, nullptr, 1, rb, re, k, sample_ids, m, null_out, 0);
+  WCX_CUDA_OK(cudaStreamSynchronize(c->copy_stream));
+  return rc;
 }
 
 int wcx_newref_stats(wcx_ctx* c, int64_t* out8) {

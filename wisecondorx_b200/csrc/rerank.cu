@@ -17,6 +17,7 @@
 // path whenever the prefix is not strictly below the cut or the a-posteriori check
 // (exact d_(k) + eps < bound) fails.  Flagged rows are recomputed by exact_rows_kernel, so the
 // final indexes never depend on the approximation.
+#include <cstdlib>
 #include <vector>
 
 #include "wcx_common.cuh"
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(RR_THREADS, 4)  // min 4 CTAs/SM: lets ptxas k
 rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists, int maxc, const int64_t* __restrict__ cum,
               int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
               double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
-              int plan_len) {
+              int plan_len, int pf_rounds) {
   extern __shared__ unsigned char rr_smem[];
   double* a_s = reinterpret_cast<double*>(rr_smem);
   uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((pv.s + 1) & ~1));
@@ -258,12 +259,21 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     const int64_t slot = lrow * nlists + q;
     const int c = cv.cnt[slot];
     const uint2* le = cv.ent + slot * WCX_CAND_CAP;
-    for (int i = tid; i < c; i += RR_THREADS) {
-      const uint2 e = le[i];
-      const float v = __uint_as_float(e.x);
-      if (v < cut) {
-        const int p = atomicAdd(&s_tot, 1);
-        if (p < maxc) keys[p] = ((uint64_t)f32_key_(v) << 32) | e.y;
+    // four independent loads in flight per thread (the shared-memory atomics would otherwise serialise them)
+    for (int i0 = tid; i0 < c; i0 += 4 * RR_THREADS) {
+      uint2 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * RR_THREADS;
+        e[u] = i < c ? le[i] : make_uint2(0x7f800000u, 0u);  // +inf is never below the cut
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float v = __uint_as_float(e[u].x);
+        if (v < cut) {
+          const int p = atomicAdd(&s_tot, 1);
+          if (p < maxc) keys[p] = ((uint64_t)f32_key_(v) << 32) | e[u].y;
+        }
       }
     }
   }
@@ -321,8 +331,18 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
 
   // exact distances, one quad per candidate; results overwrite keys[0..m)
+  // The candidate rows are scattered 4 KB gathers, 30 % of them from DRAM; a warp waits for the slowest of
+  // its 8 rows on every load batch.  One bulk L2 prefetch per row, issued a round ahead, takes the DRAM
+  // latency off that critical path without holding registers.
   const int quad = tid >> 2, l = tid & 3;
+  const uint32_t row_bytes = (uint32_t)pv.s * 8u;
+  auto prefetch_row = [&](int ci) {
+    if (VEC && l == 0 && ci < m)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + (int64_t)sel[ci] * pv.s), "r"(row_bytes) : "memory");
+  };
+  for (int r = 0; r < pf_rounds; r++) prefetch_row(r * (RR_THREADS / 4) + quad);
   for (int c0 = 0; c0 < m; c0 += RR_THREADS / 4) {
+    if (pf_rounds > 0) prefetch_row(c0 + pf_rounds * (RR_THREADS / 4) + quad);
     const int ci = c0 + quad;
     const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
     const int j = sel[cc];
@@ -381,13 +401,14 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
     else WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[vec] = smem;
   }
+  static const int pf_rounds = std::getenv("WCX_RERANK_PREFETCH") ? std::atoi(std::getenv("WCX_RERANK_PREFETCH")) : 1;
   WCX_CUDA_OK(cudaMemsetAsync(fail_flags, 0, sizeof(int32_t) * rows, st));
   if (vec)
     rerank_kernel<true><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
-                                                                idx_out, dist_out, fail_flags, sum_plan, plan_len);
+                                                                idx_out, dist_out, fail_flags, sum_plan, plan_len, pf_rounds);
   else
     rerank_kernel<false><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
-                                                                 idx_out, dist_out, fail_flags, sum_plan, plan_len);
+                                                                 idx_out, dist_out, fail_flags, sum_plan, plan_len, 0);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -15,10 +15,12 @@ __device__ __forceinline__ double key_d(uint64_t k) {
   return __longlong_as_double((long long)u);
 }
 
-// key of sorted rank `rank` (0-based) among the warp-distributed keys
+// key of sorted rank `rank` (0-based) among the `count` real keys distributed over the warp
+// (padding entries are ~0).  Bisection over the high 32 bits with two shortcuts: the bits shared
+// by all keys are skipped, and as soon as the bracket holds a single key that key is fetched
+// directly (about log2(count) + 2 iterations instead of 32 + 32).
 template <int R>
-__device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int rank) {
-  // the high words of all real keys share a prefix (values of similar magnitude): skip those bits
+__device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int rank, int count) {
   uint32_t hmin = 0xffffffffu, hmax = 0u;
 #pragma unroll
   for (int r = 0; r < R; r++) {
@@ -34,42 +36,44 @@ __device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int ra
   const int top = diff ? (31 - __clz(diff)) : -1;  // highest differing bit
   uint32_t hi = top >= 31 ? 0u : (hmin & ~((top >= 0 ? (2u << top) : 1u) - 1u));
   if (top < 0) hi = hmin;
+  int below = 0;      // keys with high word < hi
+  int inb = count;    // keys inside the current bracket [hi, hi + 2^(bit + 1))
+  int bit = top;
 #pragma unroll 1
-  for (int bit = top; bit >= 0; bit--) {
-    uint32_t trial = hi | (1u << bit);
+  for (; bit >= 0 && inb > 1; bit--) {
+    const uint32_t trial = hi | (1u << bit);
     int c = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) c += ((uint32_t)(key[r] >> 32) < trial) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
-    if (c <= rank) hi = trial;
+    if (c <= rank) { hi = trial; inb = below + inb - c; below = c; }
+    else { inb = c - below; }
   }
-  int below = 0, same = 0;
+  if (inb == 1) {
+    // the bracket [hi, hi + 2^(bit + 1)) holds exactly the wanted key: fetch it
+    const int sh = bit + 1;  // number of still-unknown low bits of the high word
+    uint32_t mh = 0, ml = 0;
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    uint32_t h = (uint32_t)(key[r] >> 32);
-    below += (h < hi) ? 1 : 0;
-    same += (h == hi) ? 1 : 0;
-  }
-  below = __reduce_add_sync(0xffffffffu, below);
-  same = __reduce_add_sync(0xffffffffu, same);
-  uint32_t lo = 0;
-  if (same == 1) {
-    uint32_t mine = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++)
-      if ((uint32_t)(key[r] >> 32) == hi) mine = (uint32_t)key[r];
-    lo = __reduce_or_sync(0xffffffffu, mine);
-  } else {
-    const int rank_in = rank - below;
-#pragma unroll 1
-    for (int bit = 31; bit >= 0; bit--) {
-      uint32_t trial = lo | (1u << bit);
-      int c = 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) c += ((uint32_t)(key[r] >> 32) == hi && (uint32_t)key[r] < trial) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c <= rank_in) lo = trial;
+    for (int r = 0; r < R; r++) {
+      const uint32_t h = (uint32_t)(key[r] >> 32);
+      const bool in = key[r] != ~0ull && (sh >= 32 ? true : ((h ^ hi) >> sh) == 0u);
+      if (in) { mh = h; ml = (uint32_t)key[r]; }
     }
+    mh = __reduce_or_sync(0xffffffffu, mh);
+    ml = __reduce_or_sync(0xffffffffu, ml);
+    return ((uint64_t)mh << 32) | ml;
+  }
+  // several keys share the full high word: resolve on the low word among them
+  uint32_t lo = 0;
+  const int rank_in = rank - below;
+#pragma unroll 1
+  for (int b2 = 31; b2 >= 0; b2--) {
+    const uint32_t trial = lo | (1u << b2);
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) c += ((uint32_t)(key[r] >> 32) == hi && (uint32_t)key[r] < trial) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c <= rank_in) lo = trial;
   }
   return ((uint64_t)hi << 32) | lo;
 }
@@ -78,7 +82,7 @@ __device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int ra
 template <int R>
 __device__ __forceinline__ double warp_median(const uint64_t (&key)[R], int count) {
   const int hi_rank = count >> 1;
-  const uint64_t up = warp_select<R>(key, hi_rank);
+  const uint64_t up = warp_select<R>(key, hi_rank, count);
   const double upper = key_d(up);
   if (count & 1) return upper;
   int c_lt = 0;

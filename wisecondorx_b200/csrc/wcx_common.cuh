@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #define WCX_CAND_CAP 4096   // per candidate-list capacity (entries)
 #define WCX_CAND_KEEP 512   // SIMT kernel (one list per row and split): thr is only lowered to t when >= KEEP entries are known below t
@@ -71,6 +72,10 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
                   int32_t plan_len, cudaStream_t st);
+// returns 0 = launched, 1 = shape not supported (use launch_rerank), -1 = error
+int launch_rerank_bulk(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev, int32_t nchr,
+                       int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal, int32_t* idx_out, double* dist_out,
+                       int32_t* fail_flags, const int32_t* leaves_dev, int32_t nleaves, int32_t max_depth, cudaStream_t st);
 int launch_exact_rows(const double* x, int64_t n, int32_t s, const int64_t* cum_dev, int32_t nchr,
                       int64_t row_begin, const int32_t* fail_rows, int32_t nfail, int32_t k,
                       int32_t* idx_out, double* dist_out, double* scratch, const int32_t* sum_plan,
@@ -81,5 +86,7 @@ int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t 
 
 // NumPy pairwise-summation plan for a reduction of length s (see rerank.cu)
 int build_sum_plan(int32_t s, int32_t* plan, int32_t cap);
+// (offset, length, #adds) per leaf of the plan + maximum stack depth (rerank_bulk.cu)
+int plan_to_leaves(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& leaves, int32_t* max_depth);
 
 }  // namespace wcx

@@ -81,6 +81,25 @@ class NewrefEngine:
                                             len(ids), _ptr(out), 0))
         return out
 
+    def get_reference_host(self, x, per, cum, row_begin, row_end, ref_size, sample_ids, kernel=_lib.KERNEL_AUTO, out=None):
+        """One C-ABI call (wcx_get_reference): host X in, host (indexes, distances, null ratios) out; the
+        D2H copy of indexes / distances overlaps the null-ratio kernels."""
+        L = _lib.load()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        per = np.ascontiguousarray(per, dtype=np.int64)
+        cum = np.ascontiguousarray(cum, dtype=np.int64)
+        ids = np.ascontiguousarray(sample_ids, dtype=np.int32)
+        rows = row_end - row_begin
+        if out is None:
+            out = (np.empty((rows, ref_size), dtype=np.int32), np.empty((rows, ref_size), dtype=np.float64),
+                   np.empty((rows, len(ids)), dtype=np.float64))
+        idx, dist, nr = out
+        n, s = x.shape
+        _lib.check(L.wcx_get_reference(self.ctx.handle, _ptr(x), n, s, _ptr(per), _ptr(cum), len(cum), ref_size, row_begin,
+                                       row_end, _ptr(ids), len(ids), kernel, _ptr(idx), _ptr(dist), _ptr(nr)))
+        self.n, self.s = int(n), int(s)
+        return idx, dist, nr
+
     def stats(self):
         out = np.zeros(8, dtype=np.int64)
         _lib.check(_lib.load().wcx_newref_stats(self.ctx.handle, _ptr(out)))
@@ -108,10 +127,7 @@ def get_reference(pca_corrected_data, masked_bins_per_chr, masked_bins_per_chr_c
         # same draw as the reference: one random.sample per get_reference call (:214-217)
         sample_ids = random.sample(range(n_samples), min(n_samples, 100))
     eng = NewrefEngine(device)
-    eng.load(x, masked_bins_per_chr, cum)
-    idx, dist = eng.topk(start_num, end_num, ref_size, kernel)
-    nr = eng.null_ratios(start_num, end_num, ref_size, sample_ids)
-    return idx, dist, nr
+    return eng.get_reference_host(x, masked_bins_per_chr, cum, start_num, end_num, ref_size, sample_ids, kernel)
 
 
 # ---------------------------------------------------------------------------------------------
