@@ -224,6 +224,7 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
     std::vector<int32_t> leaves;
     c->plan_leaves = plan_to_leaves(plan.data(), pl, leaves, &c->plan_depth);
     if (c->plan_leaves < 0) { set_error("wcx_newref_load: malformed summation plan"); return 1; }
+    if (c->plan_depth > 8) { set_error("wcx_newref_load: too many samples (summation tree deeper than 8)"); return 1; }
     if (c->leaves_dev.ensure(sizeof(int32_t) * leaves.size())) return 1;
     WCX_CUDA_OK(cudaMemcpyAsync(c->leaves_dev.p, leaves.data(), sizeof(int32_t) * leaves.size(), cudaMemcpyHostToDevice, st));
     WCX_CUDA_OK(cudaStreamSynchronize(st));  // `leaves` goes out of scope

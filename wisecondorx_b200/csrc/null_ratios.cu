@@ -42,6 +42,7 @@ null_ratios_kernel(const double* __restrict__ xm, int64_t n, const int32_t* __re
   }
   const int64_t b = row_begin + lrow;
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double mymed = nan;  // lane j keeps the median of column j of the chunk
   for (int mp = 0; mp < mc; mp += 2) {
     uint64_t key0[R], key1[R];
     bool nan0 = false, nan1 = false;
@@ -60,14 +61,15 @@ null_ratios_kernel(const double* __restrict__ xm, int64_t n, const int32_t* __re
     }
     nan0 = __any_sync(0xffffffffu, nan0);
     nan1 = __any_sync(0xffffffffu, nan1);
-    const double2 own = __ldg(reinterpret_cast<const double2*>(xm + b * NR_CHUNK + mp));
     const double med0 = (nan0 || k == 0) ? nan : warp_median<R>(key0, k);
-    if (lane == 0) out[lrow * m_total + m_off + mp] = log2(own.x / med0);
+    if (lane == mp) mymed = med0;
     if (mp + 1 < mc) {
       const double med1 = (nan1 || k == 0) ? nan : warp_median<R>(key1, k);
-      if (lane == 0) out[lrow * m_total + m_off + mp + 1] = log2(own.y / med1);
+      if (lane == mp + 1) mymed = med1;
     }
   }
+  // one division + log2 per column, all columns of the chunk at once (lane j = column j), coalesced store
+  if (lane < mc) out[lrow * m_total + m_off + lane] = log2(__ldg(xm + b * NR_CHUNK + lane) / mymed);
 }
 
 // XM[c][r][j] = X[r, ids[8c + j]] (zero padded past m); tile 32 rows per block, threads over (row, j)

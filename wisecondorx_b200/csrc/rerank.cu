@@ -53,7 +53,7 @@ namespace {
 
 constexpr int RR_THREADS = 256;
 constexpr int RR_MAXM = 1024;  // max candidates whose exact distance is evaluated per row
-constexpr int PLAN_STACK = 16;
+constexpr int PLAN_STACK = 8;  // depth of the register stack in exact_sqdist_quad (wcx_newref_load checks the plan)
 
 __device__ __forceinline__ uint64_t f64_key(double d) {
   uint64_t u = (uint64_t)__double_as_longlong(d);
@@ -82,11 +82,22 @@ __device__ __forceinline__ void load_pair(const double* p, double& x0, double& x
   }
 }
 
+// target row from shared memory: one 128-bit load per pair when the row is 16-byte aligned (half the wavefronts)
+template <bool VEC>
+__device__ __forceinline__ void lds_pair(const double* p, double& x0, double& x1) {
+  if (VEC) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    x0 = v.x; x1 = v.y;
+  } else {
+    x0 = p[0]; x1 = p[1];
+  }
+}
+
 template <bool VEC>
 __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a, const double* __restrict__ b,
                                                     const int32_t* __restrict__ plan, int plan_len, int l) {
-  double stack[PLAN_STACK];
-  int sp = 0;
+  // combination stack in registers (s0 = top; shifting instead of indexing keeps it out of local memory)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
   for (int op = 0; op < plan_len; op++) {
     const int code = plan[3 * op];
     if (code == 0) {
@@ -102,10 +113,11 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
         const int nblk = len >> 3;
         const double* bp = b + off + 2 * l;
         const double* ap = a + off + 2 * l;
-        double x0, x1;
+        double x0, x1, a0, a1;
         load_pair<VEC>(bp, x0, x1);
-        double t0 = __dsub_rn(x0, ap[0]);
-        double t1 = __dsub_rn(x1, ap[1]);
+        lds_pair<VEC>(ap, a0, a1);
+        double t0 = __dsub_rn(x0, a0);
+        double t1 = __dsub_rn(x1, a1);
         double r0 = __dmul_rn(t0, t0), r1 = __dmul_rn(t1, t1);
         int blk = 1;
         // batches of 5 blocks: all loads first (memory-level parallelism), then the ordered adds
@@ -115,8 +127,9 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
           for (int u = 0; u < 5; u++) load_pair<VEC>(bp + 8 * (blk + u), y0[u], y1[u]);
 #pragma unroll
           for (int u = 0; u < 5; u++) {
-            const double u0 = __dsub_rn(y0[u], ap[8 * (blk + u)]);
-            const double u1 = __dsub_rn(y1[u], ap[8 * (blk + u) + 1]);
+            lds_pair<VEC>(ap + 8 * (blk + u), a0, a1);
+            const double u0 = __dsub_rn(y0[u], a0);
+            const double u1 = __dsub_rn(y1[u], a1);
             r0 = __dadd_rn(r0, __dmul_rn(u0, u0));
             r1 = __dadd_rn(r1, __dmul_rn(u1, u1));
           }
@@ -124,8 +137,9 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
         for (; blk < nblk; blk++) {
           double y0, y1;
           load_pair<VEC>(bp + 8 * blk, y0, y1);
-          const double u0 = __dsub_rn(y0, ap[8 * blk]);
-          const double u1 = __dsub_rn(y1, ap[8 * blk + 1]);
+          lds_pair<VEC>(ap + 8 * blk, a0, a1);
+          const double u0 = __dsub_rn(y0, a0);
+          const double u1 = __dsub_rn(y1, a1);
           r0 = __dadd_rn(r0, __dmul_rn(u0, u0));
           r1 = __dadd_rn(r1, __dmul_rn(u1, u1));
         }
@@ -137,14 +151,13 @@ __device__ __forceinline__ double exact_sqdist_quad(const double* __restrict__ a
           res = __dadd_rn(res, __dmul_rn(t, t));
         }
       }
-      stack[sp++] = res;
+      s7 = s6; s6 = s5; s5 = s4; s4 = s3; s3 = s2; s2 = s1; s1 = s0; s0 = res;
     } else {
-      double r = stack[--sp];
-      double lft = stack[--sp];
-      stack[sp++] = __dadd_rn(lft, r);
+      s0 = __dadd_rn(s1, s0);  // left + right
+      s1 = s2; s2 = s3; s3 = s4; s4 = s5; s5 = s6; s6 = s7;
     }
   }
-  return stack[0];
+  return s0;
 }
 
 // sort (d, pos) pairs ascending by (d, pos); arrays in shared memory, n_pow2 entries
@@ -214,17 +227,20 @@ __global__ void __launch_bounds__(RR_THREADS, 4)  // min 4 CTAs/SM: lets ptxas k
 rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists, int maxc, const int64_t* __restrict__ cum,
               int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
               double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
-              int plan_len, int pf_rounds) {
-  extern __shared__ unsigned char rr_smem[];
+              int plan_len) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
   double* a_s = reinterpret_cast<double*>(rr_smem);
-  uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((pv.s + 1) & ~1));
-  int32_t* sel = reinterpret_cast<int32_t*>(keys + maxc);
-  int32_t* pos_s = sel + RR_MAXM;
-  int32_t* plan = pos_s + RR_MAXM;
+  uint32_t* vals = reinterpret_cast<uint32_t*>(a_s + ((pv.s + 1) & ~1));  // [maxc] orderable keys of the approximate values
+  uint32_t* jidx = vals + maxc;                                           // [maxc] candidate bins
+  int32_t* sel = reinterpret_cast<int32_t*>(jidx + maxc);                 // [RR_MAXM]
+  int32_t* plan = sel + RR_MAXM;
+  // vals / jidx are dead once `sel` is built: the exact (distance, position) pairs reuse the space
+  uint64_t* keys = reinterpret_cast<uint64_t*>(vals);  // [RR_MAXM]
+  int32_t* pos_s = reinterpret_cast<int32_t*>(keys + RR_MAXM);
   __shared__ int s_tot, s_m, s_fail, s_cnt;
   __shared__ int s_cs, s_ce;
   __shared__ float s_cut;
-  __shared__ uint32_t s_vk;
+  __shared__ uint32_t s_vk, s_mn, s_mx;
 
   const int tid = threadIdx.x;
   const int64_t lrow = blockIdx.x;
@@ -239,6 +255,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     s_ce = (int)cum[c];
     s_fail = 0;
     s_tot = 0;
+    s_mn = 0xffffffffu;
+    s_mx = 0u;
     if (gonosomal && c != 22 && c != 23) s_cs = -1;
     float cut = __int_as_float(0x7f800000);
     for (int q = 0; q < nlists; q++) cut = fminf(cut, cv.cut[lrow * nlists + q]);
@@ -254,7 +272,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   for (int i = tid; i < pv.s; i += RR_THREADS) a_s[i] = x[row * pv.s + i];
   for (int i = tid; i < 3 * plan_len; i += RR_THREADS) plan[i] = plan_g[i];
 
-  // gather the list entries below the common cut: key = (orderable(v) << 32) | j
+  // gather the list entries below the common cut
+  uint32_t mn = 0xffffffffu, mx = 0u;
   for (int q = 0; q < nlists; q++) {
     const int64_t slot = lrow * nlists + q;
     const int c = cv.cnt[slot];
@@ -272,11 +291,17 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
         const float v = __uint_as_float(e[u].x);
         if (v < cut) {
           const int p = atomicAdd(&s_tot, 1);
-          if (p < maxc) keys[p] = ((uint64_t)f32_key_(v) << 32) | e[u].y;
+          const uint32_t key = f32_key_(v);
+          mn = min(mn, key);
+          mx = max(mx, key);
+          if (p < maxc) { vals[p] = key; jidx[p] = e[u].y; }
         }
       }
     }
   }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((tid & 31) == 0) { atomicMin(&s_mn, mn); atomicMax(&s_mx, mx); }
   __syncthreads();
   const int tot = s_tot;
   if (tot > maxc) {
@@ -284,17 +309,32 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     return;
   }
 
-  // k-th smallest approximate value by bisection over the 32-bit value keys
+  // k-th smallest approximate value: bisection over the key bits below the prefix shared by all keys; stops as
+  // soon as the bracket holds a single key (about log2(tot) + 2 rounds instead of 32)
   if (tot > k) {
-    uint32_t res = 0;
-    for (int bit = 31; bit >= 0; bit--) {
+    const uint32_t diff = s_mn ^ s_mx;
+    int bit = diff ? 31 - __clz(diff) : -1;  // highest differing bit
+    uint32_t res = bit >= 31 ? 0u : (s_mn & ~((2u << (bit < 0 ? 0 : bit)) - 1u));
+    if (bit < 0) res = s_mn;
+    int below = 0, inb = tot;  // keys below res / inside the bracket [res, res + 2^(bit + 1))
+    for (; bit >= 0 && inb > 1; bit--) {
       const uint32_t trial = res | (1u << bit);
       int c = 0;
-      for (int i = tid; i < tot; i += RR_THREADS) c += ((uint32_t)(keys[i] >> 32) < trial) ? 1 : 0;
+      for (int i = tid; i < tot; i += RR_THREADS) c += (vals[i] < trial) ? 1 : 0;
       c = __syncthreads_count_sum(c);
-      if (c < k) res = trial;
+      if (c < k) { res = trial; inb = below + inb - c; below = c; }
+      else inb = c - below;
     }
-    if (tid == 0) s_vk = res;
+    if (bit >= 0) {
+      // exactly one key left in the bracket and it is the k-th smallest: fetch it
+      const uint32_t hi_excl = bit >= 31 ? 0xffffffffu : res + ((2u << bit) - 1u);  // inclusive upper end
+      for (int i = tid; i < tot; i += RR_THREADS) {
+        const uint32_t v = vals[i];
+        if (v >= res && v <= hi_excl) s_vk = v;
+      }
+    } else if (tid == 0) {
+      s_vk = res;
+    }
   }
   if (tid == 0) {
     s_m = 0;
@@ -316,10 +356,9 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   // select the candidates with v <= bound
   for (int i = tid; i < tot; i += RR_THREADS) {
-    const uint64_t kk = keys[i];
-    if ((double)key_f32_((uint32_t)(kk >> 32)) <= bound) {
+    if ((double)key_f32_(vals[i]) <= bound) {
       const int p = atomicAdd(&s_m, 1);
-      if (p < RR_MAXM) sel[p] = (int32_t)(uint32_t)(kk & 0xffffffffu);
+      if (p < RR_MAXM) sel[p] = (int32_t)jidx[i];
     }
   }
   __syncthreads();
@@ -331,18 +370,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
 
   // exact distances, one quad per candidate; results overwrite keys[0..m)
-  // The candidate rows are scattered 4 KB gathers, 30 % of them from DRAM; a warp waits for the slowest of
-  // its 8 rows on every load batch.  One bulk L2 prefetch per row, issued a round ahead, takes the DRAM
-  // latency off that critical path without holding registers.
   const int quad = tid >> 2, l = tid & 3;
-  const uint32_t row_bytes = (uint32_t)pv.s * 8u;
-  auto prefetch_row = [&](int ci) {
-    if (VEC && l == 0 && ci < m)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + (int64_t)sel[ci] * pv.s), "r"(row_bytes) : "memory");
-  };
-  for (int r = 0; r < pf_rounds; r++) prefetch_row(r * (RR_THREADS / 4) + quad);
   for (int c0 = 0; c0 < m; c0 += RR_THREADS / 4) {
-    if (pf_rounds > 0) prefetch_row(c0 + pf_rounds * (RR_THREADS / 4) + quad);
     const int ci = c0 + quad;
     const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
     const int j = sel[cc];
@@ -393,7 +422,7 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
   if (rows <= 0) return 0;
   if (nlists < 1 || nlists > 4) { set_error("rerank: bad number of candidate lists per row"); return 1; }
   const int maxc = nlists <= 2 ? 4096 : 8192;  // list entries below the common cut that fit in shared memory
-  const size_t smem = sizeof(double) * ((pv.s + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 8 + sizeof(int32_t) * 3 * plan_len;
+  const size_t smem = sizeof(double) * ((pv.s + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 4 + sizeof(int32_t) * 3 * plan_len;
   const bool vec = (pv.s % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   static size_t attr[2] = {0, 0};
   if (smem > attr[vec]) {
@@ -401,14 +430,13 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
     else WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[vec] = smem;
   }
-  static const int pf_rounds = std::getenv("WCX_RERANK_PREFETCH") ? std::atoi(std::getenv("WCX_RERANK_PREFETCH")) : 1;
   WCX_CUDA_OK(cudaMemsetAsync(fail_flags, 0, sizeof(int32_t) * rows, st));
   if (vec)
     rerank_kernel<true><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
-                                                                idx_out, dist_out, fail_flags, sum_plan, plan_len, pf_rounds);
+                                                                idx_out, dist_out, fail_flags, sum_plan, plan_len);
   else
     rerank_kernel<false><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
-                                                                 idx_out, dist_out, fail_flags, sum_plan, plan_len, 0);
+                                                                 idx_out, dist_out, fail_flags, sum_plan, plan_len);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -422,7 +450,7 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
                   int64_t row_begin, const int32_t* __restrict__ rows_list, int k, int32_t* __restrict__ idx_out,
                   double* __restrict__ dist_out, double* __restrict__ scratch, const int32_t* __restrict__ plan_g,
                   int plan_len) {
-  extern __shared__ unsigned char rr_smem[];
+  extern __shared__ __align__(16) unsigned char rr_smem[];
   double* a_s = reinterpret_cast<double*>(rr_smem);
   uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((s + 1) & ~1));  // [1024]
   int32_t* pos_s = reinterpret_cast<int32_t*>(keys + 1024);              // [1024]
