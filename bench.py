@@ -366,11 +366,14 @@ def run_ours(args, rank, world, local_rank):
     my_pairs = n_pairs(per, rb, re)
     sweep_ms = stage_acc["sweep"] / args.steps
     achieved = 2.0 * s * my_pairs / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else None
-    peak_tf32 = peaks["bf16_tflops_sustained"] / 2.0
+    # operand type of the sweep actually run: f16 (default, kernels 0 / 5 / 6) runs at the bf16/f16 tensor rate the
+    # driver measured; tf32 (kernels 1 / 4) at half of it (nominal ratio)
+    f16 = args.kernel in (0, 5, 6)
+    peak_tc = peaks["bf16_tflops_sustained"] if f16 else peaks["bf16_tflops_sustained"] / 2.0
     out = {
         "metric": "newref bin-pair distances per second", "value": value, "unit": "bin-pair dist/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32 sweep + f64 exact re-rank",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ("f16" if f16 else "tf32") + " sweep (fp32 accumulate) + f64 exact re-rank",
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][2], "refsize": k, "null_samples": m,
                    "bins": int(n), "samples": int(s), "pairs_per_step": int(pairs_total),
@@ -380,9 +383,9 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "dist_topk_tc_kernel", "achieved": achieved, "peak": peak_tf32,
-                     "unit": "TFLOP/s", "frac": (achieved / peak_tf32) if achieved else None, "traffic": traffic,
-                     "peak_src": f"{peaks['src']}: bf16_tflops_sustained / 2 (tf32)",
+        "roofline": {"bound": "tensor", "kernel": "dist_topk_tc_kernel", "achieved": achieved, "peak": peak_tc,
+                     "unit": "TFLOP/s", "frac": (achieved / peak_tc) if achieved else None, "traffic": traffic,
+                     "peak_src": f"{peaks['src']}: bf16_tflops_sustained" + ("" if f16 else " / 2 (tf32)"),
                      "kernel_ms": sweep_ms},
         "stages_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
         "exact_fallback_rows": st["exact_fallback_rows"],

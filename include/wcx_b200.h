@@ -26,11 +26,13 @@ extern "C" {
 typedef struct wcx_ctx wcx_ctx;
 
 /* kernel selector for the distance sweep */
-#define WCX_KERNEL_AUTO 0 /* = WCX_KERNEL_TC2 */
+#define WCX_KERNEL_AUTO 0 /* = WCX_KERNEL_TC2H */
 #define WCX_KERNEL_TC 1   /* tcgen05 / TMEM / TMA kernel, one CTA per SM (dist_topk_tc.cu) */
 #define WCX_KERNEL_SIMT 2 /* CUDA-core fp32 kernel (dist_topk_simt.cu), cross-check path */
 #define WCX_KERNEL_EXACT 3 /* brute-force float64 rows only (exact_rows_kernel), slow, for tests */
-#define WCX_KERNEL_TC2 4  /* tcgen05 kernel in 2-CTA pair mode (cta_group::2, halves the B-operand traffic) */
+#define WCX_KERNEL_TC2 4  /* tcgen05 kernel in 2-CTA pair mode (cta_group::2, halves the B-operand traffic), tf32 operands */
+#define WCX_KERNEL_TC2H 5 /* pair mode with scaled f16 operands (kind::f16): same 11-bit significand as tf32, twice the rate */
+#define WCX_KERNEL_TCH 6  /* one CTA per SM, f16 operands */
 
 int wcx_version(void);
 const char* wcx_last_error(void);
@@ -174,6 +176,10 @@ int wcx_cbs_stats(wcx_ctx* ctx, int64_t* out6);
 /* Test hook: raw tensor-core accumulators <Xc[row0 + i], Xc[col0 + j]> of one 128 x 256 tile,
  * written to acc_out [128 * 256] (host). */
 int wcx_debug_tc_tile(wcx_ctx* ctx, int64_t row0, int64_t col0, float* acc_out);
+/* The same for the f16 operand set (kind::f16 MMA of the scaled f16 matrix). */
+int wcx_debug_tc_tile_f16(wcx_ctx* ctx, int64_t row0, int64_t col0, float* acc_out);
+/* Test hook: f16 operands (raw half bits) [n, k_pad_h], their norms [n], k_pad_h, {scale, scale^2}. */
+int wcx_debug_prep_f16(wcx_ctx* ctx, uint16_t* xh_out, float* norm_out, int32_t* k_pad_out, double* scale_out);
 /* Test hook: final length of the first `nslots` candidate lists of the last wcx_newref_topk call
  * (lists per row = out[3] of wcx_newref_stats x 2 for the tcgen05 kernel). */
 int wcx_debug_list_counts(wcx_ctx* ctx, int32_t* cnt_out, int64_t nslots);

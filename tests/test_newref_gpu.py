@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 from oracle import c_oracle, np_oracle  # noqa: E402
 from wisecondorx_b200 import _lib, newref_tools, synth  # noqa: E402
 
-KERNELS = {"tc": _lib.KERNEL_TC, "simt": _lib.KERNEL_SIMT, "exact": _lib.KERNEL_EXACT, "tc2": _lib.KERNEL_TC2}
+KERNELS = {"tc": _lib.KERNEL_TC, "simt": _lib.KERNEL_SIMT, "exact": _lib.KERNEL_EXACT, "tc2": _lib.KERNEL_TC2,
+           "tc2h": _lib.KERNEL_TC2H, "tch": _lib.KERNEL_TCH}
 
 
 @pytest.fixture(scope="module")
@@ -77,7 +78,62 @@ def test_tensor_core_tile_matches_fp64_matmul(eng):
         assert err < 1e-5 * max(1.0, np.abs(want).max()), (row0, col0, err, np.abs(want).max())
 
 
-@pytest.mark.parametrize("kernel", ["tc", "tc2", "simt", "exact"])
+def _prep_f16(eng, n):
+    import ctypes
+    L = _lib.load()
+    kp = ctypes.c_int32()
+    _lib.check(L.wcx_debug_prep_f16(eng.ctx.handle, None, None, ctypes.byref(kp), None))
+    xh = np.empty((n, kp.value), dtype=np.float16)
+    nrm = np.empty(n, dtype=np.float32)
+    sc = np.empty(2, dtype=np.float64)
+    _lib.check(L.wcx_debug_prep_f16(eng.ctx.handle, xh.ctypes.data, nrm.ctypes.data, None, sc.ctypes.data))
+    return xh, nrm, sc
+
+
+def test_prep_f16_scales_centres_and_rounds(eng):
+    """f16 operand set: (X - mean) * 2^e rounded once to nearest-even, |values| < 2^14, norms of the rounded values."""
+    x, per, cum = synth.make_corrected_matrix([300, 200, 100] + [10] * 19, 37, seed=3)
+    eng.load(x, per, cum)
+    n, s = x.shape
+    xh, nrm, sc = _prep_f16(eng, n)
+    assert xh.shape[1] == 64
+    bound = np.abs(x).max() + np.abs(x.mean(axis=0)).max()
+    e = np.log2(sc[0])
+    assert e == int(e) and sc[1] == sc[0] ** 2
+    assert 2.0 ** 13 <= bound * sc[0] < 2.0 ** 14
+    want = ((x - x.mean(axis=0)) * sc[0]).astype(np.float16)  # NumPy rounds float64 -> float16 to nearest even
+    # the device mean (atomic accumulation order) may differ from NumPy's in the last bit: allow rare 1-ulp flips
+    got = xh[:, :s]
+    assert (got != want).mean() < 1e-3
+    assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= np.spacing(np.abs(want).max())
+    assert not xh[:, s:].any()
+    np.testing.assert_allclose(nrm, (got.astype(np.float64) ** 2).sum(1), rtol=1e-6)
+
+
+def test_tensor_core_tile_f16_matches_fp64_matmul(eng):
+    """kind::f16 accumulators vs a float64 product of the same f16 operands: products of two 11-bit significands are
+    exact in fp32, so only the accumulation may round -- the bound rerank.cu assumes is (K + 64) * 2^-23 * |a| |b|."""
+    x, per, cum = synth.make_corrected_matrix([500, 400, 300] + [20] * 19, 100, seed=4)
+    eng.load(x, per, cum)
+    L = _lib.load()
+    n, s = x.shape
+    xh, nrm, sc = _prep_f16(eng, n)
+    kp = xh.shape[1]
+    worst = 0.0
+    for row0, col0 in [(0, 0), (128, 256), (900, 1024)]:
+        acc = np.empty((128, 256), dtype=np.float32)
+        _lib.check(L.wcx_debug_tc_tile_f16(eng.ctx.handle, row0, col0, acc.ctypes.data))
+        a = np.zeros((128, kp)); b = np.zeros((256, kp))
+        ra = xh[row0:row0 + 128].astype(np.float64); rb = xh[col0:col0 + 256].astype(np.float64)
+        a[:len(ra)] = ra; b[:len(rb)] = rb
+        want = a @ b.T
+        allowed = (kp + 64) * 2.0 ** -23 * np.sqrt((a * a).sum(1))[:, None] * np.sqrt((b * b).sum(1))[None, :]
+        ratio = np.abs(acc - want) / np.maximum(allowed, 1e-300)
+        worst = max(worst, float(ratio.max()))
+    assert worst < 0.25, worst  # measured accumulation error stays far inside the assumed bound
+
+
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "tc2h", "tch", "simt", "exact"])
 @pytest.mark.parametrize("case,part,parts,k", [("A_p11", 1, 1, 30), ("A_p23", 2, 3, 30), ("G", 1, 1, 30),
                                                 ("T", 1, 1, 12), ("S", 1, 1, 20)])
 def test_golden_get_reference(gref, kernel, case, part, parts, k):
@@ -99,7 +155,7 @@ def test_random_draw_follows_python_random(gref):
     np.testing.assert_allclose(nr, gref["A_p11_nr"], rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("kernel", ["tc", "tc2", "simt"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "tc2h", "tch", "simt"])
 def test_config1_full_vs_c_oracle(eng, kernel):
     """BASELINE config 1: 1 Mb bins (2887 autosomal), 20 samples, refsize 300 -- full parity."""
     per = synth.config_bins(1)
@@ -118,7 +174,7 @@ def test_config1_full_vs_c_oracle(eng, kernel):
     assert st["exact_fallback_rows"] <= n // 50, st
 
 
-@pytest.mark.parametrize("kernel", ["tc", "tc2", "simt"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "tc2h", "simt"])
 def test_config2_parts_vs_c_oracle(eng, kernel):
     """BASELINE config 2: 100 kb bins (28760), 100 samples, refsize 300; parts compared in full."""
     per = synth.config_bins(2)
@@ -165,7 +221,7 @@ def test_edge_cases(eng):
     x[5, 3] = np.nan
     n = x.shape[0]
     oi, od = c_oracle.topk(x, per, cum, 64, 0, n)
-    for kernel in ("tc", "tc2", "simt", "exact"):
+    for kernel in ("tc", "tc2", "tc2h", "tch", "simt", "exact"):
         eng.load(x, per, cum)
         idx, dist = eng.topk(0, n, 64, KERNELS[kernel])
         assert np.array_equal(idx, oi), kernel
@@ -186,7 +242,7 @@ def test_bad_arguments_raise(eng):
         eng.null_ratios(0, 10, 10, [99])
 
 
-@pytest.mark.parametrize("kernel", ["tc", "tc2"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "tc2h"])
 def test_nasty_data_vs_c_oracle(eng, kernel):
     """Duplicated bins (exact distance ties), outlier bins with huge norms, constant bins, a few
     NaN / inf rows, heavy-tailed noise: indexes and distances must still be bit-exact."""

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libwcx_b200.so")
 HEADER = os.path.abspath(os.path.join(HERE, "..", "include", "wcx_b200.h"))
 
-KERNEL_AUTO, KERNEL_TC, KERNEL_SIMT, KERNEL_EXACT, KERNEL_TC2 = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_TC, KERNEL_SIMT, KERNEL_EXACT, KERNEL_TC2, KERNEL_TC2H, KERNEL_TCH = 0, 1, 2, 3, 4, 5, 6
 
 _lib = None
 
@@ -50,6 +50,8 @@ def load():
     L.wcx_newref_stage_ms.argtypes = [vp, vp]
     L.wcx_debug_tc_tile.argtypes = [vp, i64, i64, vp]
     L.wcx_debug_prep.argtypes = [vp, vp, vp, vp]
+    L.wcx_debug_tc_tile_f16.argtypes = [vp, i64, i64, vp]
+    L.wcx_debug_prep_f16.argtypes = [vp, vp, vp, vp, vp]
     L.wcx_debug_list_counts.argtypes = [vp, vp, i64]
     f64 = ctypes.c_double
     L.wcx_predict_load_ref.argtypes = [vp, i32, vp, vp, i64, i32, vp, vp, i32, vp, vp, i32, vp, i64]

@@ -64,14 +64,15 @@ struct wcx_ctx {
   cudaEvent_t ev[8] = {};
   // newref state
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
-  DevBuf x_buf, xc, norm, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
+  DevBuf x_buf, xc, norm, xh, norm_h, scale_dev, absmax, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
   DevBuf fail, fail_rows, plan_dev, leaves_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg, diag;
   int64_t n = 0, n_pad = 0;
-  int32_t s = 0, k_pad = 0, nchr = 0;
+  int32_t s = 0, k_pad = 0, k_pad_h = 0, nchr = 0;
   std::vector<int64_t> per, cum;
   int32_t plan_len = 0;
   int32_t plan_leaves = 0, plan_depth = 0;
   alignas(128) unsigned char tmap[128];
+  alignas(128) unsigned char tmap_h[128];  // f16 operands
   bool loaded = false;
   // last topk
   int64_t last_rb = -1, last_re = -1;
@@ -103,6 +104,23 @@ static PrepView prep_view(const wcx_ctx* c) {
   pv.n_pad = c->n_pad;
   pv.s = c->s;
   pv.k_pad = c->k_pad;
+  pv.scale = nullptr;
+  pv.abs_err = 0.f;
+  pv.f16 = 0;
+  return pv;
+}
+
+// the f16 operand set: scaled values, norms in scaled units
+static PrepView prep_view_h(const wcx_ctx* c) {
+  PrepView pv = prep_view(c);
+  pv.xc = reinterpret_cast<const float*>(c->xh.p);
+  pv.norm = c->norm_h.as<float>();
+  pv.k_pad = c->k_pad_h;
+  pv.scale = c->scale_dev.as<double>();
+  // values below the smallest normal f16 (2^-14) may be rounded to a subnormal (spacing 2^-24) or, on a path that
+  // flushes them, to zero: 2^-14 covers both
+  pv.abs_err = 6.103515625e-05f;
+  pv.f16 = 1;
   return pv;
 }
 
@@ -143,7 +161,7 @@ void wcx_destroy(wcx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
+  for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->xh, &c->norm_h, &c->scale_dev, &c->absmax, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
                     &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev, &c->leaves_dev,
                     &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
@@ -194,6 +212,7 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   c->per.assign(per, per + nchr);
   c->cum.assign(cum, cum + nchr);
   c->k_pad = (s + WCX_KBLOCK - 1) / WCX_KBLOCK * WCX_KBLOCK;
+  c->k_pad_h = (s + 2 * WCX_KBLOCK - 1) / (2 * WCX_KBLOCK) * (2 * WCX_KBLOCK);
   c->n_pad = (n + 255) / 256 * 256 + 256;
   cudaStream_t st = c->stream;
   if (x_on_device) {
@@ -205,16 +224,21 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   }
   if (c->xc.ensure(sizeof(float) * (size_t)c->n_pad * c->k_pad)) return 1;
   if (c->norm.ensure(sizeof(float) * (size_t)c->n_pad)) return 1;
+  if (c->xh.ensure(2 * (size_t)c->n_pad * c->k_pad_h) || c->norm_h.ensure(sizeof(float) * (size_t)c->n_pad)) return 1;
+  if (c->scale_dev.ensure(2 * sizeof(double)) || c->absmax.ensure(sizeof(unsigned long long))) return 1;
   if (c->colsum.ensure(sizeof(double) * s) || c->colcnt.ensure(sizeof(double) * s)) return 1;
   if (c->cum_dev.ensure(sizeof(int64_t) * nchr)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->cum_dev.p, cum, sizeof(int64_t) * nchr, cudaMemcpyHostToDevice, st));
   WCX_CUDA_OK(cudaEventRecord(c->ev[6], st));
-  if (launch_col_stats(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), st)) return 1;
+  if (launch_col_stats(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), c->absmax.as<unsigned long long>(), st)) return 1;
   if (launch_center_round(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), c->xc.as<float>(),
                           c->norm.as<float>(), c->n_pad, c->k_pad, st))
     return 1;
+  if (launch_center_round_f16(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), c->absmax.as<unsigned long long>(),
+                              c->scale_dev.as<double>(), c->xh.p, c->norm_h.as<float>(), c->n_pad, c->k_pad_h, st))
+    return 1;
   WCX_CUDA_OK(cudaEventRecord(c->ev[7], st));
-  c->launches += 2;
+  c->launches += 4;
   // NumPy pairwise-summation plan for length s
   std::vector<int32_t> plan(3 * 4096);
   int pl = build_sum_plan(s, plan.data(), (int32_t)plan.size());
@@ -233,6 +257,7 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   WCX_CUDA_OK(cudaMemcpyAsync(c->plan_dev.p, plan.data(), sizeof(int32_t) * 3 * (size_t)pl, cudaMemcpyHostToDevice, st));
   PrepView pv = prep_view(c);
   if (tc_encode_tensor_map(pv, c->tmap)) return 1;
+  if (tc_encode_tensor_map(prep_view_h(c), c->tmap_h)) return 1;
   WCX_CUDA_OK(cudaStreamSynchronize(st));  // `plan` and caller's host buffers may go away
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
@@ -280,12 +305,16 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
   std::memset(c->stats, 0, sizeof(c->stats));
   c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0.0;
   if (rows == 0) return 0;
-  if (kernel == WCX_KERNEL_AUTO) kernel = WCX_KERNEL_TC2;
+  if (kernel == WCX_KERNEL_AUTO) kernel = WCX_KERNEL_TC2H;
+  if (kernel < WCX_KERNEL_TC || kernel > WCX_KERNEL_TCH) { set_error("wcx_newref_topk: unknown kernel id"); return 1; }
+  const bool f16 = kernel == WCX_KERNEL_TC2H || kernel == WCX_KERNEL_TCH;
+  const bool pair = kernel == WCX_KERNEL_TC2 || kernel == WCX_KERNEL_TC2H;
   const int gon = c->nchr > 22 ? 1 : 0;
   if (c->idx_dev.ensure(sizeof(int32_t) * (size_t)rows * k) || c->dist_dev.ensure(sizeof(double) * (size_t)rows * k))
     return 1;
   if (c->fail.ensure(sizeof(int32_t) * (size_t)rows)) return 1;
-  PrepView pv = prep_view(c);
+  PrepView pv = f16 ? prep_view_h(c) : prep_view(c);
+  void* tmap = f16 ? c->tmap_h : c->tmap;
   std::vector<int32_t> fail_list;
 
   if (kernel == WCX_KERNEL_EXACT) {
@@ -320,7 +349,7 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
       items.clear();
       build_items(c, rb, re, tile_n, nsplit, lps, items);
     }
-    if (kernel == WCX_KERNEL_TC2) {
+    if (pair) {
       // pair mode: items (2p, 2p + 1) must share the candidate-column range -> group by split, pad odd groups
       std::vector<WorkItem> paired;
       for (int q = 0; q < nsplit; q++) {
@@ -349,10 +378,10 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
     if (kernel == WCX_KERNEL_SIMT) {
       if (launch_dist_topk_simt(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), st)) return 1;
-    } else if (kernel == WCX_KERNEL_TC2) {
-      if (launch_dist_topk_tc_pair(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->tmap, st)) return 1;
+    } else if (pair) {
+      if (launch_dist_topk_tc_pair(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, tmap, st)) return 1;
     } else {
-      if (launch_dist_topk_tc(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), c->tmap, st)) return 1;
+      if (launch_dist_topk_tc(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), tmap, st)) return 1;
     }
     WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
     // The bulk-copy re-rank (rerank_bulk.cu) is an opt-in experiment (WCX_RERANK_BULK=warps,stages): at config 3 it
@@ -501,7 +530,7 @@ int wcx_newref_stage_ms(wcx_ctx* c, double* out8) {
   return 0;
 }
 
-int wcx_debug_tc_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) {
+static int debug_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out, bool f16) {
   if (!c || !c->loaded || !acc_out) { set_error("wcx_debug_tc_tile: bad argument"); return 1; }
   if (row0 < 0 || row0 + WCX_TILE_M > c->n_pad || col0 < 0 || col0 % WCX_TILE_N_TC != 0 || col0 + WCX_TILE_N_TC > c->n_pad) {
     set_error("wcx_debug_tc_tile: tile out of range (col0 must be a multiple of 256)");
@@ -518,11 +547,25 @@ int wcx_debug_tc_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) {
     return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->items_dev.p, &w, sizeof(w), cudaMemcpyHostToDevice, st));
   CandView cv{c->cand_ent.as<uint2>(), c->cand_cnt.as<int32_t>(), c->cand_cut.as<float>(), nullptr};
-  PrepView pv = prep_view(c);
-  if (launch_dist_topk_tc_debug(pv, c->items_dev.as<WorkItem>(), 1, cv, c->tmap, c->dbg.as<float>(), st)) return 1;
+  PrepView pv = f16 ? prep_view_h(c) : prep_view(c);
+  if (launch_dist_topk_tc_debug(pv, c->items_dev.as<WorkItem>(), 1, cv, f16 ? c->tmap_h : c->tmap, c->dbg.as<float>(), st)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(acc_out, c->dbg.p, sizeof(float) * WCX_TILE_M * WCX_TILE_N_TC, cudaMemcpyDeviceToHost, st));
   WCX_CUDA_OK(cudaStreamSynchronize(st));
   c->last_rb = c->last_re = -1;
+  return 0;
+}
+
+int wcx_debug_tc_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) { return debug_tile(c, row0, col0, acc_out, false); }
+int wcx_debug_tc_tile_f16(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) { return debug_tile(c, row0, col0, acc_out, true); }
+
+int wcx_debug_prep_f16(wcx_ctx* c, uint16_t* xh_out, float* norm_out, int32_t* k_pad_out, double* scale_out) {
+  if (!c || !c->loaded) { set_error("wcx_debug_prep_f16: not loaded"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  if (k_pad_out) *k_pad_out = c->k_pad_h;
+  if (xh_out) WCX_CUDA_OK(cudaMemcpyAsync(xh_out, c->xh.p, 2 * (size_t)c->n * c->k_pad_h, cudaMemcpyDeviceToHost, c->stream));
+  if (norm_out) WCX_CUDA_OK(cudaMemcpyAsync(norm_out, c->norm_h.p, sizeof(float) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+  if (scale_out) WCX_CUDA_OK(cudaMemcpyAsync(scale_out, c->scale_dev.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  WCX_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

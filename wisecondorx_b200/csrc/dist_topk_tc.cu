@@ -39,7 +39,7 @@ namespace {
 
 constexpr int TM = WCX_TILE_M;          // 128
 constexpr int TN = WCX_TILE_N_TC;       // 256
-constexpr int BK = WCX_KBLOCK;          // 32 tf32 = 128 bytes
+constexpr int BK = WCX_KBLOCK;          // 32 tf32 = 128 bytes per row and pipeline stage (f16: 64 elements, also 128 bytes)
 constexpr int A_BYTES = TM * BK * 4;    // 16 KB
 constexpr int B_BYTES = TN * BK * 4;    // 32 KB (1-CTA mode); a CTA of a pair stages half of it
 constexpr int TC_THREADS = 384;
@@ -63,6 +63,9 @@ constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >
 // cta_group::2: the instruction spans both CTAs of the pair, M = 256 (128 rows from each CTA), N = 256
 // (128 candidate columns staged by each CTA)
 constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+// kind::f16 with F16 operands (a_format = b_format = 0): same shapes, K = 16 per instruction
+constexpr uint32_t IDESC_H = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC2_H = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,15 +108,27 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if (F16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC2_H), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
+        : "memory");
+  }
 }
 // arrive on the barrier at the same offset in both CTAs of the pair once the MMAs issued so far are done
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
@@ -155,15 +170,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma_single(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if (F16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC_H), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -295,7 +322,9 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], const floa
 //               (same candidate-column range) form a 256-row tile; each CTA stages its own 128 target
 //               rows and HALF of the 256 candidate columns, so the L2 -> SM operand traffic per tile
 //               drops from 768 KB to 512 KB per SM; the leader CTA issues the MMAs for both.
-template <bool PAIR>
+// F16: operands are the scaled f16 matrix (newref_prep.cu) and the MMA is kind::f16 -- 64 elements per 128-byte
+//       stage row, four K = 16 instructions per stage, i.e. half as many stages and MMAs per tile as TF32.
+template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const WorkItem* __restrict__ items,
                     int nitems, CandView cv, float* __restrict__ dbg_acc) {
@@ -321,7 +350,8 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kblocks = pv.k_pad / BK;
+  constexpr int BKE = F16 ? 2 * BK : BK;  // elements per stage row
+  const int kblocks = pv.k_pad / BKE;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
@@ -366,13 +396,13 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
             if (PAIR) {
               // CTA 0's barrier collects the bytes of both CTAs (2 x 32 KB per stage)
               if (crank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
-              tma_load_2d_pair(sa, &tmap, &full[stage], kb * BK, w.row0);
-              tma_load_2d_pair(sb, &tmap, &full[stage], kb * BK, col0 + (int)crank * (TN / 2));
+              tma_load_2d_pair(sa, &tmap, &full[stage], kb * BKE, w.row0);
+              tma_load_2d_pair(sb, &tmap, &full[stage], kb * BKE, col0 + (int)crank * (TN / 2));
             } else {
               mbar_expect_tx(&full[stage], STAGE_BYTES);
-              tma_load_2d(sa, &tmap, &full[stage], kb * BK, w.row0);
-              tma_load_2d(sb, &tmap, &full[stage], kb * BK, col0);
-              tma_load_2d(sb + B_BYTES / 2, &tmap, &full[stage], kb * BK, col0 + TN / 2);
+              tma_load_2d(sa, &tmap, &full[stage], kb * BKE, w.row0);
+              tma_load_2d(sb, &tmap, &full[stage], kb * BKE, col0);
+              tma_load_2d(sb + B_BYTES / 2, &tmap, &full[stage], kb * BKE, col0 + TN / 2);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -400,9 +430,9 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
             const uint64_t bdesc = make_desc(sa + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / 8; k++) {
-              // advance 8 tf32 = 32 bytes along K inside the 128B swizzle row: +2 in the >>4 address field
-              if (PAIR) umma_tf32_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
-              else umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
+              // advance 8 tf32 / 16 f16 = 32 bytes along K inside the 128B swizzle row: +2 in the >>4 address field
+              if (PAIR) umma_pair<F16>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
+              else umma_single<F16>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
             }
             // smem slot reusable once these MMAs have read it (pair mode: in both CTAs)
             if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
@@ -551,14 +581,33 @@ int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host) {
     fn = reinterpret_cast<PFN_encodeTiled>(p);
   }
   CUtensorMap* map = reinterpret_cast<CUtensorMap*>(tmap_storage_host);
+  const size_t esz = pv.f16 ? 2 : 4;
   cuuint64_t gdim[2] = {(cuuint64_t)pv.k_pad, (cuuint64_t)pv.n_pad};
-  cuuint64_t gstride[1] = {(cuuint64_t)pv.k_pad * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)TM};
+  cuuint64_t gstride[1] = {(cuuint64_t)pv.k_pad * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(pv.f16 ? 2 * BK : BK), (cuuint32_t)TM};  // 128 bytes x 128 rows
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pv.xc), gdim, gstride, box, estr,
+  CUresult r = fn(map, pv.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pv.xc), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
+  return 0;
+}
+
+template <bool F16>
+static int launch_single(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage, float* dbg,
+                         int grid_override, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<false, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
+  const int grid = grid_override > 0 ? grid_override : (nitems < sms ? nitems : sms);
+  dist_topk_tc_kernel<false, F16><<<grid, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg);
+  WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -566,30 +615,15 @@ int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitem
                         int32_t* work_counter, void* tmap_storage, cudaStream_t st) {
   (void)work_counter;
   if (nitems == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM));
-    attr_set = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
-  int grid = nitems < sms ? nitems : sms;
-  float* dbg = nullptr;
-  dist_topk_tc_kernel<false><<<grid, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg);
-  WCX_CUDA_OK(cudaGetLastError());
-  return 0;
+  return pv.f16 ? launch_single<true>(pv, items, nitems, cv, tmap_storage, nullptr, 0, st)
+                : launch_single<false>(pv, items, nitems, cv, tmap_storage, nullptr, 0, st);
 }
 
-// pair mode: `items` holds an even number of entries, (2p, 2p + 1) sharing one candidate-column range
-int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage,
-                             cudaStream_t st) {
-  if (nitems == 0) return 0;
-  if (nitems & 1) { set_error("pair sweep: odd number of work items"); return 1; }
+template <bool F16>
+static int launch_pair(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM));
+    WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<true, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM));
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -609,17 +643,22 @@ int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   float* dbg = nullptr;
-  WCX_CUDA_OK(cudaLaunchKernelEx(&cfg, dist_topk_tc_kernel<true>, *map, pv, items, nitems, cv, dbg));
+  WCX_CUDA_OK(cudaLaunchKernelEx(&cfg, dist_topk_tc_kernel<true, F16>, *map, pv, items, nitems, cv, dbg));
   return 0;
+}
+
+// pair mode: `items` holds an even number of entries, (2p, 2p + 1) sharing one candidate-column range
+int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage,
+                             cudaStream_t st) {
+  if (nitems == 0) return 0;
+  if (nitems & 1) { set_error("pair sweep: odd number of work items"); return 1; }
+  return pv.f16 ? launch_pair<true>(pv, items, nitems, cv, tmap_storage, st) : launch_pair<false>(pv, items, nitems, cv, tmap_storage, st);
 }
 
 int launch_dist_topk_tc_debug(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                               void* tmap_storage, float* dbg_acc, cudaStream_t st) {
-  WCX_CUDA_OK(cudaFuncSetAttribute(dist_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM));
-  const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
-  dist_topk_tc_kernel<false><<<1, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg_acc);
-  WCX_CUDA_OK(cudaGetLastError());
-  return 0;
+  return pv.f16 ? launch_single<true>(pv, items, nitems, cv, tmap_storage, dbg_acc, 1, st)
+                : launch_single<false>(pv, items, nitems, cv, tmap_storage, dbg_acc, 1, st);
 }
 
 }  // namespace wcx

@@ -7,25 +7,39 @@
 //  * center_round    Xc = tf32_round(float(X - mean)), zero padded to [n_pad, k_pad], plus the
 //                    row norms of the ROUNDED values (so the tensor-core dot products of the
 //                    rounded operands are exact products; only accumulation rounds).
+//  * center_round_f16  the same for the f16 sweep: Xh = half((X - mean) * 2^e), e chosen so that every finite
+//                    entry stays below 2^14; f16 and tf32 both carry 11 significant bits, so the error
+//                    bound of the sweep is unchanged while the tensor pipe runs at twice the rate on
+//                    half the operand bytes.
+#include <cuda_fp16.h>
+
 #include "wcx_common.cuh"
 
 namespace wcx {
 
 __global__ void col_stats_kernel(const double* __restrict__ x, int64_t n, int32_t s, int64_t rows_per_block,
-                                 double* __restrict__ colsum, double* __restrict__ colcnt) {
+                                 double* __restrict__ colsum, double* __restrict__ colcnt,
+                                 unsigned long long* __restrict__ absmax) {
   __shared__ double ssum[8][33];
   __shared__ double scnt[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > n) r1 = n;
-  double acc = 0.0, cnt = 0.0;
+  double acc = 0.0, cnt = 0.0, amax = 0.0;
   if (col < s) {
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
       double v = x[r * s + col];
-      if (isfinite(v)) { acc += v; cnt += 1.0; }
+      if (isfinite(v)) { acc += v; cnt += 1.0; amax = fmax(amax, fabs(v)); }
     }
   }
+  // non-negative doubles order like their bit patterns
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 16));
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+  amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+  if (threadIdx.x == 0 && amax > 0.0) atomicMax(absmax, (unsigned long long)__double_as_longlong(amax));
   ssum[threadIdx.y][threadIdx.x] = acc;
   scnt[threadIdx.y][threadIdx.x] = cnt;
   __syncthreads();
@@ -36,13 +50,15 @@ __global__ void col_stats_kernel(const double* __restrict__ x, int64_t n, int32_
   }
 }
 
-int launch_col_stats(const double* x, int64_t n, int32_t s, double* colsum, double* colcnt, cudaStream_t st) {
+int launch_col_stats(const double* x, int64_t n, int32_t s, double* colsum, double* colcnt, unsigned long long* absmax,
+                     cudaStream_t st) {
+  WCX_CUDA_OK(cudaMemsetAsync(absmax, 0, sizeof(unsigned long long), st));
   WCX_CUDA_OK(cudaMemsetAsync(colsum, 0, sizeof(double) * s, st));
   WCX_CUDA_OK(cudaMemsetAsync(colcnt, 0, sizeof(double) * s, st));
   if (n == 0 || s == 0) return 0;
   int64_t rows_per_block = 512;
   dim3 grid((s + 31) / 32, (unsigned)((n + rows_per_block - 1) / rows_per_block));
-  col_stats_kernel<<<grid, dim3(32, 8), 0, st>>>(x, n, s, rows_per_block, colsum, colcnt);
+  col_stats_kernel<<<grid, dim3(32, 8), 0, st>>>(x, n, s, rows_per_block, colsum, colcnt, absmax);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -83,6 +99,71 @@ int launch_center_round(const double* x, int64_t n, int32_t s, const double* col
   const int warps = 8;
   unsigned grid = (unsigned)((n_pad + warps - 1) / warps);
   center_round_kernel<<<grid, warps * 32, 0, st>>>(x, n, s, colsum, colcnt, xc, norm, n_pad, k_pad);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// scale[0] = 2^e with (max|x| + max|mean|) * 2^e < 2^14 (|x - mean| cannot exceed that bound), scale[1] = 4^e
+__global__ void prep_scale_kernel(const double* __restrict__ colsum, const double* __restrict__ colcnt, int32_t s,
+                                  const unsigned long long* __restrict__ absmax, double* __restrict__ scale) {
+  __shared__ double red[8];
+  double m = 0.0;
+  for (int c = threadIdx.x; c < s; c += blockDim.x) {
+    const double cnt = colcnt[c];
+    if (cnt > 0.0) m = fmax(m, fabs(colsum[c] / cnt));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, red[w]);
+    const double bound = m + __longlong_as_double((long long)*absmax);
+    int q = 0;
+    if (bound > 0.0 && isfinite(bound)) frexp(bound, &q);  // bound = f * 2^q, f in [0.5, 1)
+    int e = 14 - q;
+    e = e > 400 ? 400 : (e < -400 ? -400 : e);
+    scale[0] = ldexp(1.0, e);
+    scale[1] = ldexp(1.0, 2 * e);
+  }
+}
+
+// one warp per row
+__global__ void center_round_f16_kernel(const double* __restrict__ x, int64_t n, int32_t s,
+                                        const double* __restrict__ colsum, const double* __restrict__ colcnt,
+                                        const double* __restrict__ scale, __half* __restrict__ xh,
+                                        float* __restrict__ norm, int64_t n_pad, int32_t k_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  const double sc = scale[0];
+  __half* out = xh + row * k_pad;
+  double acc = 0.0;
+  for (int c = lane; c < k_pad; c += 32) {
+    __half h = __ushort_as_half((unsigned short)0);
+    if (row < n && c < s) {
+      const double cnt = colcnt[c];
+      const double mean = cnt > 0.0 ? colsum[c] / cnt : 0.0;
+      h = __double2half((x[row * s + c] - mean) * sc);  // one rounding, to nearest even
+    }
+    out[c] = h;
+    const double v = (double)__half2float(h);
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) norm[row] = (float)acc;
+}
+
+int launch_center_round_f16(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
+                            const unsigned long long* absmax, double* scale, void* xh, float* norm, int64_t n_pad,
+                            int32_t k_pad, cudaStream_t st) {
+  if (n_pad == 0) return 0;
+  prep_scale_kernel<<<1, 256, 0, st>>>(colsum, colcnt, s, absmax, scale);
+  const int warps = 8;
+  unsigned grid = (unsigned)((n_pad + warps - 1) / warps);
+  center_round_f16_kernel<<<grid, warps * 32, 0, st>>>(x, n, s, colsum, colcnt, scale, reinterpret_cast<__half*>(xh), norm, n_pad,
+                                                       k_pad);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -202,12 +202,12 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // rigorous bound on |d~ - d| for candidates with d <= ~D seen from a row with |a|^2 = an
-__device__ __forceinline__ double approx_eps(double an, double D, int k_pad) {
+__device__ __forceinline__ double approx_eps(double an, double D, int k_pad, double abs_err) {
   const double u = 4.8852e-4;  // 2^-11 * (1 + 2^-10): tf32 round-to-nearest of an fp32-rounded value
   double na = sqrt(an);
   double sD = sqrt(D * 1.02 + 1e-300);
   double nb = na + sD;                         // |b| <= |a| + sqrt(d)
-  double e = u * (na + nb);                    // | |a^-b^| - |a-b| | <= |da| + |db|
+  double e = u * (na + nb) + 2.0 * sqrt((double)k_pad) * abs_err;  // | |a^-b^| - |a-b| | <= |da| + |db|, |dx| <= u |x| + sqrt(K) abs_err
   double rounding = 2.0 * sD * e + e * e;
   double gamma = ((double)k_pad + 64.0) * 1.1920929e-7;  // fp32 accumulation, (k_pad + 64) * 2^-23
   double accum = 2.0 * gamma * na * nb;
@@ -346,7 +346,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     const float vk = key_f32_(s_vk);
     const double an = (double)pv.norm[row];
     const double D = fmax((double)vk + an, 0.0);
-    eps = approx_eps(an, D, pv.k_pad);
+    eps = approx_eps(an, D, pv.k_pad, (double)pv.abs_err);
     bound = (double)vk + 2.0 * eps;
   }
   // every unlisted candidate has v >= cut: the prefix {v <= bound} must lie strictly below it
@@ -390,7 +390,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   if (tid == 0 && tot > k) {
     const uint64_t kk = keys[k - 1];
     const uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
-    const double dk = __longlong_as_double((long long)u);
+    const double dk = __longlong_as_double((long long)u) * (pv.scale ? pv.scale[1] : 1.0);  // into the units of the list values
     const double an = (double)pv.norm[row];
     if (!(dk - an + eps < bound)) s_fail = 1;
   }

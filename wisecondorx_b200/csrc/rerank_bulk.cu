@@ -82,12 +82,12 @@ __device__ __forceinline__ float key_f32_(uint32_t k) {
 }
 
 // same bound as rerank.cu
-__device__ __forceinline__ double approx_eps(double an, double D, int k_pad) {
+__device__ __forceinline__ double approx_eps(double an, double D, int k_pad, double abs_err) {
   const double u = 4.8852e-4;
   double na = sqrt(an);
   double sD = sqrt(D * 1.02 + 1e-300);
   double nb = na + sD;
-  double e = u * (na + nb);
+  double e = u * (na + nb) + 2.0 * sqrt((double)k_pad) * abs_err;  // | |a^-b^| - |a-b| | <= |da| + |db|, |dx| <= u |x| + sqrt(K) abs_err
   double rounding = 2.0 * sD * e + e * e;
   double gamma = ((double)k_pad + 64.0) * 1.1920929e-7;
   double accum = 2.0 * gamma * na * nb;
@@ -265,7 +265,7 @@ rerank_bulk_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int n
     const float vk = key_f32_(res);
     const double an = (double)pv.norm[row];
     const double D = fmax((double)vk + an, 0.0);
-    eps = approx_eps(an, D, pv.k_pad);
+    eps = approx_eps(an, D, pv.k_pad, (double)pv.abs_err);
     bound = (double)vk + 2.0 * eps;
   }
   if (!((double)cut > bound)) {  // the needed prefix must lie strictly below the cut
@@ -363,7 +363,7 @@ rerank_bulk_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int n
 
   // a-posteriori completeness check: exact d_(k) + eps must stay below bound + |a|^2
   if (tid == 0 && tot > k) {
-    const double dk = key_f64(dkey[k - 1]);
+    const double dk = key_f64(dkey[k - 1]) * (pv.scale ? pv.scale[1] : 1.0);  // into the units of the list values
     const double an = (double)pv.norm[row];
     if (!(dk - an + eps < bound)) s_fail = 1;
   }

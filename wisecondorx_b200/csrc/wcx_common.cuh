@@ -47,7 +47,12 @@ struct PrepView {
   int64_t n;           // bins
   int64_t n_pad;
   int32_t s;           // samples
-  int32_t k_pad;       // S rounded up to WCX_KBLOCK
+  int32_t k_pad;       // S rounded up to the K block of the operand type (32 tf32 / 64 f16 elements = 128 bytes)
+  // f16 operands (dist_topk_tc.cu, F16 = true): xc points at __half data holding (X - mean) * scale[0]; norm and
+  // every list value are in scaled units, scale[1] = scale[0]^2 converts an exact distance.  nullptr: unscaled.
+  const double* scale;
+  float abs_err;       // per-element absolute rounding error bound of the operand conversion (scaled units)
+  int32_t f16;
 };
 
 struct CandView {
@@ -58,16 +63,23 @@ struct CandView {
 };
 
 // ---- newref kernels (host launchers; all asynchronous on `st`) ---------------------------
-int launch_col_stats(const double* x, int64_t n, int32_t s, double* colsum, double* colcnt, cudaStream_t st);
+int launch_col_stats(const double* x, int64_t n, int32_t s, double* colsum, double* colcnt, unsigned long long* absmax,
+                     cudaStream_t st);
 int launch_center_round(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
                         float* xc, float* norm, int64_t n_pad, int32_t k_pad, cudaStream_t st);
+// f16 operands: scale[0] = power of two that maps max|x| + max|mean| below 2^14, scale[1] = its square
+int launch_center_round_f16(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
+                            const unsigned long long* absmax, double* scale, void* xh, float* norm, int64_t n_pad,
+                            int32_t k_pad, cudaStream_t st);
 int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m,
                           double* xt, cudaStream_t st);
 int launch_dist_topk_simt(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                           int32_t* work_counter, cudaStream_t st);
 int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                         int32_t* work_counter, void* tmap_storage, cudaStream_t st);
-int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host);
+int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage,
+                             cudaStream_t st);
+int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host);  // element type from pv.f16
 int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
