@@ -2,6 +2,7 @@
 // management, work-item construction, stage timing; all arithmetic is in the kernels.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -404,8 +405,12 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     WCX_CUDA_OK(cudaMemcpyAsync(diag_h, c->diag.p, sizeof(diag_h), cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaMemcpyAsync(flags.data(), c->fail.p, sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaStreamSynchronize(st));
+    static const bool debug_fail = std::getenv("WCX_DEBUG_FAIL") != nullptr;
     for (int64_t i = 0; i < rows; i++)
-      if (flags[(size_t)i]) fail_list.push_back((int32_t)i);
+      if (flags[(size_t)i]) {
+        fail_list.push_back((int32_t)i);
+        if (debug_fail) fprintf(stderr, "[wcx] row %lld not certified by the fast path (reason %d) -> exact_rows\n", (long long)(rb + i), flags[(size_t)i]);
+      }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stage_ms[0] = ms;

@@ -43,12 +43,12 @@ constexpr int BK = WCX_KBLOCK;          // 32 tf32 = 128 bytes per row and pipel
 constexpr int A_BYTES = TM * BK * 4;    // 16 KB
 constexpr int B_BYTES = TN * BK * 4;    // 32 KB (1-CTA mode); a CTA of a pair stages half of it
 constexpr int TC_THREADS = 384;
-constexpr int NORM_BYTES = 8 * TN * 4;  // per-epilogue-warp copy of the tile's candidate norms
+constexpr int NORM_BYTES = 8 * (TN / 2) * 4;  // per-epilogue-warp copy of the candidate norms of its half tile
 constexpr int THR_BYTES = 2 * TM * 8;   // (item, thr) words exchanged between the two epilogue groups
-constexpr int SPILL_BYTES = 256 * 16 * 4;  // 16 floats per epilogue thread (half a chunk), see filter_chunk
+constexpr int SPILL_BYTES = 256 * 32 * 4;  // 32 floats per epilogue thread (one chunk), [8][256] float4, see filter_chunk
 
 template <bool PAIR> struct Cfg {
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int STAGES = PAIR ? 5 : 3;  // 32 KB / 48 KB stages (K = 32 tf32 or 64 f16 elements each)
   static constexpr int B_STAGE = PAIR ? B_BYTES / 2 : B_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NORM_BYTES + THR_BYTES + SPILL_BYTES;
@@ -137,13 +137,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-// arrive on CTA 0's copy of a barrier from either CTA of the pair
+// arrive on CTA 0's copy of a barrier from either CTA of the pair.  Relaxed: the barrier only hands a TMEM buffer back
+// to the MMA warp, no generic-memory data travels with it, and the TMEM reads are complete (tcgen05.wait::ld) and fenced
+// (tcgen05.fence::before_thread_sync) before the arrive.  The .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR,
+// 13 % of the epilogue's samples in the r01d profile.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar))
       : "memory");
 }
@@ -260,60 +263,87 @@ __device__ __forceinline__ void ladder_adopt(RowState& st, float t) {
   }
 }
 
-__device__ __forceinline__ void append(RowState& st, uint2* be, float v, int g) {
-  be[st.cnt] = make_uint2(__float_as_uint(v), (uint32_t)g);
-  st.cnt++;
-  st.lo = fminf(st.lo, v);
-  st.c0 += (v < st.p0) ? 1 : 0;
-  st.c1 += (v < st.p1) ? 1 : 0;
-  st.c2 += (v < st.p2) ? 1 : 0;
-  st.c3 += (v < st.p3) ? 1 : 0;
+// explicit shared-window accesses (the compiler otherwise falls back to generic LD/ST for the carved-up dynamic buffer)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
 }
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_u64_volatile(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u64_volatile(uint32_t a, unsigned long long v) {
+  asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+// bits [0, k) set (k clamped to 0..32)
+__device__ __forceinline__ uint32_t bits_below(int k) { return k <= 0 ? 0u : (k >= 32 ? 0xffffffffu : ((1u << k) - 1u)); }
 
 // 32 accumulator columns of one row against the staged norms.
 //
 // Appends are rare per lane (about 2 % of the elements) but almost every group of columns has SOME
 // lane of the warp that passes, so a per-element `if (v < thr) append()` makes the whole warp walk
-// the append code for nearly every element (r01b profile: ~6500 instructions per tile and warp,
-// instruction-cache misses on the unrolled copies).  Instead the hot loop is branch-free: it only
-// builds a 16-bit pass mask per half chunk; lanes with a non-zero mask park their 16 values in a
-// private shared-memory strip and drain the set bits in a compact loop in which every lane works on
-// its own entries at the same time.
+// the append code for nearly every element.  Instead the hot loop is branch-free: it turns the
+// accumulators into v in place and builds a 32-bit pass mask (compare + predicated OR, four
+// partial masks for ILP); lanes with a non-zero mask park their 32 values in a private
+// shared-memory strip and drain the set bits in a compact loop in which every lane works on its
+// own entries at the same time.  The loop runs max-over-lanes(popcount) times, so one drain per 32
+// columns (not two per 16) and a short body matter: the r01d profile had 31 instructions per
+// iteration and 1.6 iterations per 16 columns, as much issue time as the arithmetic itself.
 template <bool ALL_VALID>
-__device__ __forceinline__ void filter_chunk(const uint32_t (&r)[32], const float* __restrict__ snorm, int g0,
-                                             const WorkItem& w, int64_t n, RowState& st, uint2* be,
-                                             float* __restrict__ spill) {
+__device__ __forceinline__ void filter_chunk(uint32_t (&r)[32], uint32_t snorm_a, int g0, const WorkItem& w, int64_t n,
+                                             RowState& st, uint2* be, uint32_t spill_a) {
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-  for (int half = 0; half < 2; half++) {
-    float v[16];
-    uint32_t mask = 0;
+  for (int j4 = 0; j4 < 8; j4++) {
+    const float4 nb = lds_f4(snorm_a + 16 * j4);
+    r[4 * j4 + 0] = __float_as_uint(fmaf(-2.f, __uint_as_float(r[4 * j4 + 0]), nb.x));
+    r[4 * j4 + 1] = __float_as_uint(fmaf(-2.f, __uint_as_float(r[4 * j4 + 1]), nb.y));
+    r[4 * j4 + 2] = __float_as_uint(fmaf(-2.f, __uint_as_float(r[4 * j4 + 2]), nb.z));
+    r[4 * j4 + 3] = __float_as_uint(fmaf(-2.f, __uint_as_float(r[4 * j4 + 3]), nb.w));
+  }
+#define WCX_PASS(M, J) \
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(M) : "f"(__uint_as_float(r[J])), "f"(st.thr), "r"(1u << (J)))
 #pragma unroll
-    for (int j4 = 0; j4 < 4; j4++) {
-      const float4 nb = *reinterpret_cast<const float4*>(snorm + half * 16 + 4 * j4);
-      v[4 * j4 + 0] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 0]), nb.x);
-      v[4 * j4 + 1] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 1]), nb.y);
-      v[4 * j4 + 2] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 2]), nb.z);
-      v[4 * j4 + 3] = fmaf(-2.f, __uint_as_float(r[half * 16 + 4 * j4 + 3]), nb.w);
-    }
+  for (int j4 = 0; j4 < 8; j4++) {
+    WCX_PASS(m0, 4 * j4 + 0);
+    WCX_PASS(m1, 4 * j4 + 1);
+    WCX_PASS(m2, 4 * j4 + 2);
+    WCX_PASS(m3, 4 * j4 + 3);
+  }
+#undef WCX_PASS
+  uint32_t mask = (m0 | m1) | (m2 | m3);
+  if (!ALL_VALID)  // columns past the end of the matrix or inside the rows' own chromosome
+    mask &= bits_below((int)(n - g0)) & ~(bits_below(w.chr_e - g0) & ~bits_below(w.chr_s - g0));
+  if (mask) {
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      bool ok = v[j] < st.thr;
-      if (!ALL_VALID) {
-        const int gg = g0 + half * 16 + j;
-        ok = ok && (gg < n) && !(gg >= w.chr_s && gg < w.chr_e);
-      }
-      mask |= ok ? (1u << j) : 0u;
-    }
-    if (mask) {
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        *reinterpret_cast<float4*>(spill + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      while (mask) {
-        const int j = __ffs(mask) - 1;
-        mask &= mask - 1;
-        append(st, be, spill[j], g0 + half * 16 + j);
-      }
-    }
+    for (int q = 0; q < 8; q++)
+      sts_f4(spill_a + q * 4096, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+             __uint_as_float(r[4 * q + 3]));
+    uint2* wp = be + st.cnt;
+    do {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float v = lds_f(spill_a + (j >> 2) * 4096 + (j & 3) * 4);
+      *wp++ = make_uint2(__float_as_uint(v), (uint32_t)(g0 + j));
+      st.lo = fminf(st.lo, v);
+#define WCX_COUNT(C, P) asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(C) : "f"(v), "f"(P))
+      WCX_COUNT(st.c0, st.p0);
+      WCX_COUNT(st.c1, st.p1);
+      WCX_COUNT(st.c2, st.p2);
+      WCX_COUNT(st.c3, st.p3);
+#undef WCX_COUNT
+    } while (mask);
+    st.cnt = (int)(wp - be);
   }
 }
 
@@ -336,17 +366,19 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
   const int nunits = PAIR ? (nitems >> 1) : nitems;
   extern __shared__ unsigned char tc_smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the array itself: an integer round trip would demote every later access to generic LD/ST)
+  unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                     // [STAGES]
   uint64_t* empty = bars + STAGES;           // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;       // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* s_norm = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [8 warps][TN]
-  // [2 groups][TM] words (item << 32 | float bits of thr): a threshold is only adopted from the same work item
-  volatile unsigned long long* s_thr = reinterpret_cast<volatile unsigned long long*>(s_norm + 8 * TN);
-  float* s_spill = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + NORM_BYTES + THR_BYTES);  // [256][16]
+  float* s_norm = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [8 warps][TN / 2]
+  // s_thr words are (item << 32 | float bits of thr): a threshold is only adopted from the same work item
+  // [2 groups][TM] u64, then the spill strips [8][256] float4 (shared-window addresses)
+  const uint32_t s_thr_a = smem_u32(smem + STAGES * STAGE_BYTES + 256 + NORM_BYTES);
+  const uint32_t s_spill_a = s_thr_a + THR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -358,7 +390,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 8 : 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 16 : 8); }  // every epilogue warp (of both CTAs in pair mode) releases every buffer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -445,14 +477,21 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: thread owns one target row of every second tile =====================
-    const int grp = (warp - 4) >> 2;  // 0 / 1 -> TMEM buffer and tile parity
+    // ===================== epilogue: thread owns one target row and one half of the columns of every tile =====================
+    // Both groups drain every accumulator (group g: columns 128 g .. 128 g + 127) while the MMA warp fills the other
+    // TMEM buffer.  (Tile-alternating groups left each group idle for a whole MMA pass per tile: its buffer could only
+    // be refilled after it had drained it -- 30 % of the epilogue's samples sat in that wait in the r01d profile.)
+    const int grp = (warp - 4) >> 2;  // 0 / 1 -> column half
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    float* snorm = s_norm + (warp - 4) * TN;
-    float* spill = s_spill + (threadIdx.x - 128) * 16;
+    constexpr int TH = TN / 2;
+    float* snorm = s_norm + (warp - 4) * TH;
+    const uint32_t snorm_a = smem_u32(snorm);
+    const uint32_t spill_a = s_spill_a + (threadIdx.x - 128) * 16;
+    const uint32_t my_thr_a = s_thr_a + (uint32_t)(grp * TM + row) * 8;
+    const uint32_t peer_thr_a = s_thr_a + (uint32_t)((grp ^ 1) * TM + row) * 8;
     uint32_t tphase = 0;
-    int tile_no = 0;  // running count of tiles of this CTA (parity selects the group)
+    int buf = 0;
     bool dbg_done = false;
     for (int unit = unit0; unit < nunits; unit += unit_step) {
       const int item = PAIR ? 2 * unit + (int)crank : unit;
@@ -467,69 +506,71 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       st.c0 = st.c1 = st.c2 = st.c3 = 0;
       st.cnt = 0;
       st.ladder = false;
-      s_thr[grp * TM + row] = ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr);
+      sts_u64_volatile(my_thr_a, ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr));
       for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
-        const bool mine = (tile_no & 1) == grp;
-        tile_no++;
-        if (!mine) continue;
+        const int my_buf = buf;
+        const uint32_t my_phase = tphase;
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+        // this group's share of the tile: the 32-column chunks 2 i + grp (i = 0..3).  Interleaving at chunk granularity
+        // (rather than halves of 128 columns) keeps the two lists of a row balanced when its nearest candidates come in
+        // runs of adjacent bins -- a run shorter than a half tile used to land in one list only, whose threshold then
+        // certified fewer than ref_size candidates (row 149352 of config 3 fell back to the exact path for that reason).
         const int col0 = ct * TN;
         if (tile_own(w, ct)) {  // nothing to filter: just hand the accumulator back
-          mbar_wait(&tfull[grp], tphase);
-          tphase ^= 1;
+          mbar_wait(&tfull[my_buf], my_phase);
           tc_fence_after();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[grp]); else mbar_arrive(&tempty[grp]); }
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[my_buf]); else mbar_arrive(&tempty[my_buf]); }
           continue;
         }
-        // stage the candidate norms of this tile (issued before waiting for the accumulator)
-        const float4 n0 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0) + lane);
-        const float4 n1 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0) + 32 + lane);
+        // stage the candidate norms of the four chunks (issued before waiting for the accumulator): lane l holds
+        // floats 4 (l & 7) .. +3 of chunk l >> 3
+        const float4 n0 = __ldg(reinterpret_cast<const float4*>(pv.norm + col0 + 64 * (lane >> 3) + 32 * grp) + (lane & 7));
         {
-          const unsigned long long pw = s_thr[(grp ^ 1) * TM + row];
+          const unsigned long long pw = lds_u64_volatile(peer_thr_a);
           if ((uint32_t)(pw >> 32) == (uint32_t)item && row_ok) ladder_adopt(st, __uint_as_float((uint32_t)pw));
         }
         __syncwarp();
         reinterpret_cast<float4*>(snorm)[lane] = n0;
-        reinterpret_cast<float4*>(snorm)[32 + lane] = n1;
         __syncwarp();
-        mbar_wait(&tfull[grp], tphase);
-        tphase ^= 1;
+        mbar_wait(&tfull[my_buf], my_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * TN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(my_buf * TN + 32 * grp);
         const bool tile_valid = (col0 + TN <= pv.n) && (col0 + TN <= w.chr_s || col0 >= w.chr_e);
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 64) {
+        for (int i = 0; i < 4; i += 2) {  // chunk i in ra, chunk i + 1 in rb
+          const int cc = 64 * i + 32 * grp;  // first tile column of chunk i; chunk i + 1 starts 64 columns later
           tmem_ld_wait();
-          tmem_ld32(taddr + (uint32_t)(c0 + 32), rb);
+          tmem_ld32(taddr + (uint32_t)(64 * (i + 1)), rb);
           if (dbg_acc != nullptr && !dbg_done && blockIdx.x == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + j] = __uint_as_float(ra[j]);
+            for (int j = 0; j < 32; j++) dbg_acc[row * TN + cc + j] = __uint_as_float(ra[j]);
           }
-          if (tile_valid) filter_chunk<true>(ra, snorm + c0, col0 + c0, w, pv.n, st, be, spill);
-          else filter_chunk<false>(ra, snorm + c0, col0 + c0, w, pv.n, st, be, spill);
+          if (tile_valid) filter_chunk<true>(ra, snorm_a + 128 * i, col0 + cc, w, pv.n, st, be, spill_a);
+          else filter_chunk<false>(ra, snorm_a + 128 * i, col0 + cc, w, pv.n, st, be, spill_a);
           tmem_ld_wait();
-          if (c0 + 64 < TN) tmem_ld32(taddr + (uint32_t)(c0 + 64), ra);
+          if (i + 2 < 4) tmem_ld32(taddr + (uint32_t)(64 * (i + 2)), ra);
           if (dbg_acc != nullptr && !dbg_done && blockIdx.x == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) dbg_acc[row * TN + c0 + 32 + j] = __uint_as_float(rb[j]);
+            for (int j = 0; j < 32; j++) dbg_acc[row * TN + cc + 64 + j] = __uint_as_float(rb[j]);
           }
-          if (tile_valid) filter_chunk<true>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be, spill);
-          else filter_chunk<false>(rb, snorm + c0 + 32, col0 + c0 + 32, w, pv.n, st, be, spill);
+          if (tile_valid) filter_chunk<true>(rb, snorm_a + 128 * (i + 1), col0 + cc + 64, w, pv.n, st, be, spill_a);
+          else filter_chunk<false>(rb, snorm_a + 128 * (i + 1), col0 + cc + 64, w, pv.n, st, be, spill_a);
         }
         dbg_done = true;
-        // accumulator buffer drained: hand it back to the MMA warp
+        // this group's half of the accumulator is drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[grp]); else mbar_arrive(&tempty[grp]); }
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[my_buf]); else mbar_arrive(&tempty[my_buf]); }
         // threshold maintenance
         const float thr_before = st.thr;
         ladder_advance(st);
         if (cv.diag && st.thr < thr_before) atomicAdd(cv.diag + 2, 1);
         // first exact selection once INIT_N entries are in, and overflow protection afterwards
-        uint32_t need = __ballot_sync(0xffffffffu, (!st.ladder && st.cnt >= INIT_N) || st.cnt > WCX_CAND_CAP - TN);
+        uint32_t need = __ballot_sync(0xffffffffu, (!st.ladder && st.cnt >= INIT_N) || st.cnt > WCX_CAND_CAP - TH);
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
@@ -548,7 +589,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
             if (cv.diag) atomicAdd(cv.diag + (s_cnt <= 1024 ? 0 : 1), 1);
           }
         }
-        if (st.thr < thr_before) s_thr[grp * TM + row] = ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr);
+        if (st.thr < thr_before) sts_u64_volatile(my_thr_a, ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr));
       }
       if (row_ok) { cv.cnt[slot] = st.cnt; cv.cut[slot] = st.thr; }
     }

@@ -351,7 +351,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   // every unlisted candidate has v >= cut: the prefix {v <= bound} must lie strictly below it
   if (!((double)cut > bound)) {
-    if (tid == 0) fail_flags[lrow] = 1;
+    if (tid == 0) fail_flags[lrow] = 2;
     return;
   }
   // select the candidates with v <= bound
@@ -365,7 +365,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   const int m = s_m;
   if (tid == 0 && cv.diag) { atomicAdd(cv.diag + 4, m); atomicAdd(cv.diag + 5, tot >> 4); }
   if (m > RR_MAXM) {
-    if (tid == 0) fail_flags[lrow] = 1;
+    if (tid == 0) fail_flags[lrow] = 3;
     return;
   }
 
@@ -396,7 +396,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   __syncthreads();
   if (s_fail) {
-    if (tid == 0) fail_flags[lrow] = 1;
+    if (tid == 0) fail_flags[lrow] = 4;
     return;
   }
   const uint64_t key_1e10 = f64_key(1e10);
@@ -442,27 +442,23 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
 }
 
 // ------------------------------------------------------------------------------------------
-// brute-force exact rows: one CTA per listed row; all N candidate distances in float64 into
-// `scratch`, then an exact (distance, position) top-k by 64-bit key bisection.
+// brute-force exact rows (rows the fast path could not certify, WCX_KERNEL_EXACT): all N candidate
+// distances in float64 into `scratch` (exact_dist_kernel, the candidate axis split over many CTAs
+// per row so that a single failed row costs ~0.3 ms, not one CTA streaming all of X), then an
+// exact (distance, position) top-k by 64-bit key bisection (exact_rows_kernel, one CTA per row).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RR_THREADS)
-exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t* __restrict__ cum, int nchr,
-                  int64_t row_begin, const int32_t* __restrict__ rows_list, int k, int32_t* __restrict__ idx_out,
-                  double* __restrict__ dist_out, double* __restrict__ scratch, const int32_t* __restrict__ plan_g,
-                  int plan_len) {
+exact_dist_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t* __restrict__ cum, int nchr,
+                  int64_t row_begin, const int32_t* __restrict__ rows_list, double* __restrict__ scratch,
+                  const int32_t* __restrict__ plan_g, int plan_len, int cand_per_cta) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   double* a_s = reinterpret_cast<double*>(rr_smem);
-  uint64_t* keys = reinterpret_cast<uint64_t*>(a_s + ((s + 1) & ~1));  // [1024]
-  int32_t* pos_s = reinterpret_cast<int32_t*>(keys + 1024);              // [1024]
-  int32_t* plan = pos_s + 1024;
-  __shared__ int s_cs, s_ce, s_cnt;
-  __shared__ unsigned long long s_count;
-  __shared__ int s_scan[RR_THREADS];
+  int32_t* plan = reinterpret_cast<int32_t*>(a_s + ((s + 1) & ~1));
+  __shared__ int s_cs, s_ce;
   const int tid = threadIdx.x;
   const int64_t lrow = rows_list[blockIdx.x];
   const int64_t row = row_begin + lrow;
   uint64_t* dk = reinterpret_cast<uint64_t*>(scratch) + (int64_t)blockIdx.x * n;  // orderable keys of d
-
   if (tid == 0) {
     int c = 0;
     while (c < nchr && cum[c] <= row) c++;
@@ -474,20 +470,49 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
   __syncthreads();
   const int cs = s_cs, ce = s_ce;
   const int quad = tid >> 2, l = tid & 3;
-  const uint64_t key_1e10 = f64_key(1e10);
-  for (int64_t j0 = 0; j0 < n; j0 += RR_THREADS / 4) {
+  const int64_t jb = (int64_t)blockIdx.y * cand_per_cta;
+  int64_t je = jb + cand_per_cta;
+  if (je > n) je = n;
+  for (int64_t j0 = jb; j0 < je; j0 += RR_THREADS / 4) {
     int64_t j = j0 + quad;
     int64_t jj = j < n ? j : n - 1;
     double d = exact_sqdist_quad<false>(a_s, x + jj * s, plan, plan_len, l);
-    if (l == 0 && j < n) {
+    if (l == 0 && j < je) {
       bool excluded = (j >= cs && j < ce) || !(d < 1e10);  // own chromosome, NaN, >= 1e10: never inserted
       dk[j] = excluded ? ~0ull : f64_key(d);
     }
   }
+}
+
+constexpr int EX_THREADS = 1024;  // selection kernel: one CTA per row, N keys per bisection pass
+
+__global__ void __launch_bounds__(EX_THREADS)
+exact_rows_kernel(int64_t n, const int64_t* __restrict__ cum, int nchr, int64_t row_begin,
+                  const int32_t* __restrict__ rows_list, int k, int32_t* __restrict__ idx_out,
+                  double* __restrict__ dist_out, const double* __restrict__ scratch) {
+  __shared__ uint64_t keys[1024];
+  __shared__ int32_t pos_s[1024];
+  __shared__ int s_cs, s_ce, s_cnt;
+  __shared__ unsigned long long s_count;
+  __shared__ int s_scan[EX_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t lrow = rows_list[blockIdx.x];
+  const int64_t row = row_begin + lrow;
+  const uint64_t* dk = reinterpret_cast<const uint64_t*>(scratch) + (int64_t)blockIdx.x * n;  // orderable keys of d
+
+  if (tid == 0) {
+    int c = 0;
+    while (c < nchr && cum[c] <= row) c++;
+    s_cs = (int)(c == 0 ? 0 : cum[c - 1]);
+    s_ce = (int)cum[c];
+  }
   __syncthreads();
+  const int cs = s_cs, ce = s_ce;
+  const uint64_t key_1e10 = f64_key(1e10);
   // number of valid candidates
   unsigned long long loc = 0;
-  for (int64_t j = tid; j < n; j += RR_THREADS) loc += (dk[j] < key_1e10) ? 1 : 0;
+#pragma unroll 8
+  for (int64_t j = tid; j < n; j += EX_THREADS) loc += (dk[j] < key_1e10) ? 1 : 0;
   if (tid == 0) s_count = 0;
   __syncthreads();
   atomicAdd(&s_count, loc);
@@ -499,7 +524,8 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
     for (int bit = 63; bit >= 0; bit--) {
       uint64_t trial = T | (1ull << bit);
       loc = 0;
-      for (int64_t j = tid; j < n; j += RR_THREADS) loc += (dk[j] < trial) ? 1 : 0;
+#pragma unroll 8
+      for (int64_t j = tid; j < n; j += EX_THREADS) loc += (dk[j] < trial) ? 1 : 0;  // independent L2 loads, 8 in flight
       __syncthreads();
       if (tid == 0) s_count = 0;
       __syncthreads();
@@ -512,7 +538,7 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
   if (tid == 0) s_cnt = 0;
   __syncthreads();
   if (kk > 0) {
-    for (int64_t j = tid; j < n; j += RR_THREADS) {
+    for (int64_t j = tid; j < n; j += EX_THREADS) {
       if (dk[j] < T) {
         int p = atomicAdd(&s_cnt, 1);
         keys[p] = dk[j];
@@ -521,13 +547,13 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
     }
     __syncthreads();
     int have = s_cnt;
-    for (int64_t j0 = 0; j0 < n && have < kk; j0 += RR_THREADS) {
+    for (int64_t j0 = 0; j0 < n && have < kk; j0 += EX_THREADS) {
       int64_t j = j0 + tid;
       int f = (j < n && dk[j] == T) ? 1 : 0;
       s_scan[tid] = f;
       __syncthreads();
       // inclusive scan (Hillis-Steele)
-      for (int o = 1; o < RR_THREADS; o <<= 1) {
+      for (int o = 1; o < EX_THREADS; o <<= 1) {
         int v = tid >= o ? s_scan[tid - o] : 0;
         __syncthreads();
         s_scan[tid] += v;
@@ -538,18 +564,18 @@ exact_rows_kernel(const double* __restrict__ x, int64_t n, int s, const int64_t*
         keys[p] = T;
         pos_s[p] = (int)(j < cs ? j : j - (ce - cs));
       }
-      have += s_scan[RR_THREADS - 1];
+      have += s_scan[EX_THREADS - 1];
       __syncthreads();
     }
   }
   __syncthreads();
   const int p2 = next_pow2(kk < 2 ? 2 : kk);
-  for (int i = kk + tid; i < p2; i += RR_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
+  for (int i = kk + tid; i < p2; i += EX_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
   __syncthreads();
   bitonic_sort_dpos(keys, pos_s, p2);
   int32_t* oi = idx_out + lrow * k;
   double* od = dist_out + lrow * k;
-  for (int t = tid; t < k; t += RR_THREADS) {
+  for (int t = tid; t < k; t += EX_THREADS) {
     if (t < kk) {
       uint64_t q = keys[t];
       uint64_t u = (q & 0x8000000000000000ull) ? (q & 0x7fffffffffffffffull) : ~q;
@@ -568,14 +594,23 @@ int launch_exact_rows(const double* x, int64_t n, int32_t s, const int64_t* cum_
                       cudaStream_t st) {
   if (nfail <= 0) return 0;
   if (k > 1024) { set_error("exact_rows: k > 1024 unsupported"); return 1; }
-  size_t smem = sizeof(double) * ((s + 1) & ~1) + 1024 * (8 + 4) + sizeof(int32_t) * 3 * plan_len;
+  const size_t smem = sizeof(double) * ((s + 1) & ~1) + sizeof(int32_t) * 3 * plan_len;
   static size_t attr = 0;
   if (smem > attr) {
-    WCX_CUDA_OK(cudaFuncSetAttribute(exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WCX_CUDA_OK(cudaFuncSetAttribute(exact_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  exact_rows_kernel<<<nfail, RR_THREADS, smem, st>>>(x, n, s, cum_dev, nchr, row_begin, fail_rows, k, idx_out,
-                                                     dist_out, scratch, sum_plan, plan_len);
+  // about four waves of CTAs over the whole batch, 64 candidates (one per quad) per pass
+  int64_t chunks = (4 * 148 + nfail - 1) / nfail;
+  if (chunks < 1) chunks = 1;
+  int64_t per = (n + chunks - 1) / chunks;
+  per = (per + 63) / 64 * 64;
+  if (per < 64) per = 64;
+  chunks = (n + per - 1) / per;
+  if (chunks > 65535) { set_error("exact_rows: too many candidate chunks"); return 1; }
+  exact_dist_kernel<<<dim3((unsigned)nfail, (unsigned)chunks), RR_THREADS, smem, st>>>(x, n, s, cum_dev, nchr, row_begin, fail_rows,
+                                                                                  scratch, sum_plan, plan_len, (int)per);
+  exact_rows_kernel<<<nfail, EX_THREADS, 0, st>>>(n, cum_dev, nchr, row_begin, fail_rows, k, idx_out, dist_out, scratch);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
