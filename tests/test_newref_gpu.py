@@ -266,3 +266,18 @@ def test_nasty_data_vs_c_oracle(eng, kernel):
         assert np.array_equal(idx[r], oi[0]), (kernel, int(r))
         assert np.array_equal(dist[r], od[0]), (kernel, int(r))
     assert st["exact_fallback_rows"] <= n // 20, st
+
+
+@pytest.mark.parametrize("samples", [136, 777, 1100])
+def test_many_samples_both_gather_paths(eng, samples):
+    """Sample counts whose NumPy summation tree has 2 / 8 / 16 leaves: up to 8 leaves the re-rank gathers from the
+    leaf-major copy of X (rerank.cu build_leaf_layout), beyond that it falls back to the row-major LDG gather."""
+    per = [140, 120, 100, 90, 80, 70] + [25] * 16
+    x, per, cum = synth.make_corrected_matrix(per, samples, seed=40 + samples)
+    n = x.shape[0]
+    eng.load(x, per, cum)
+    idx, dist = eng.topk(0, n, 300)
+    oi, od = c_oracle.topk(x, per, cum, 300, 0, n)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)
+    assert eng.stats()["exact_fallback_rows"] <= n // 20

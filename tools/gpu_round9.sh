@@ -1,0 +1,11 @@
+#!/bin/bash
+# round-9: leaf-major re-rank gather vs the LDG gather
+mkdir -p gpurun_out
+TAG=r01e
+SUM='import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ["value","ms_per_step","stages_ms","exact_fallback_rows"]}, d["e2e"]["ms_per_step"], d["roofline"]["frac"])'
+echo "=== newref gpu tests"; timeout 600 python -m pytest tests/test_newref_gpu.py -q -x --tb=short 2>&1 | tail -15
+echo "=== bench config3 (leaf-major)"; timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-predict 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_leaf.json | python -c "$SUM"
+echo "=== bench config3 (LDG)"; WCX_RERANK_LDG=1 timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-predict 2>&1 | tail -1 | python -c "$SUM"
+echo "=== bench config2 (leaf-major)"; timeout 200 python bench.py --workload config2 --no-cpu-baseline --no-predict 2>&1 | tail -1 | python -c "$SUM"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:rerank_kernel -c 1 -o gpurun_out/prof_${TAG}_rerank_leaf python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-predict > gpurun_out/prof_${TAG}_rerank.log 2>&1
+ls -la gpurun_out | tail -5

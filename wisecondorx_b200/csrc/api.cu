@@ -67,6 +67,8 @@ struct wcx_ctx {
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
   DevBuf x_buf, xc, norm, xh, norm_h, scale_dev, absmax, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
   DevBuf fail, fail_rows, plan_dev, leaves_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg, diag;
+  DevBuf xp, perm_dev, leafdesc_dev;  // leaf-major copy of X for the re-rank gather (rerank.cu)
+  int32_t sp = 0, leaf_n = 0;
   int64_t n = 0, n_pad = 0;
   int32_t s = 0, k_pad = 0, k_pad_h = 0, nchr = 0;
   std::vector<int64_t> per, cum;
@@ -164,7 +166,7 @@ void wcx_destroy(wcx_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->xh, &c->norm_h, &c->scale_dev, &c->absmax, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
                     &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev, &c->leaves_dev,
-                    &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->p_partial,
+                    &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->xp, &c->perm_dev, &c->leafdesc_dev, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
                     &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out})
     b->release();
@@ -238,7 +240,6 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   if (launch_center_round_f16(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), c->absmax.as<unsigned long long>(),
                               c->scale_dev.as<double>(), c->xh.p, c->norm_h.as<float>(), c->n_pad, c->k_pad_h, st))
     return 1;
-  WCX_CUDA_OK(cudaEventRecord(c->ev[7], st));
   c->launches += 4;
   // NumPy pairwise-summation plan for length s
   std::vector<int32_t> plan(3 * 4096);
@@ -256,6 +257,22 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   }
   if (c->plan_dev.ensure(sizeof(int32_t) * 3 * (size_t)pl)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->plan_dev.p, plan.data(), sizeof(int32_t) * 3 * (size_t)pl, cudaMemcpyHostToDevice, st));
+  // leaf-major copy of X for the re-rank gather
+  std::vector<int32_t> perm, leafdesc;
+  c->sp = build_leaf_layout(plan.data(), pl, perm, leafdesc);
+  c->leaf_n = c->sp > 0 ? (int32_t)(leafdesc.size() / 4) : 0;
+  if (c->leaf_n >= 1 && c->leaf_n <= 8) {
+    if (c->xp.ensure(sizeof(double) * (size_t)n * c->sp) || c->perm_dev.ensure(sizeof(int32_t) * perm.size()) ||
+        c->leafdesc_dev.ensure(sizeof(int32_t) * leafdesc.size()))
+      return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(c->perm_dev.p, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice, st));
+    WCX_CUDA_OK(cudaMemcpyAsync(c->leafdesc_dev.p, leafdesc.data(), sizeof(int32_t) * leafdesc.size(), cudaMemcpyHostToDevice, st));
+    if (launch_permute_rows(c->d_x, n, s, c->perm_dev.as<int32_t>(), c->sp, c->xp.as<double>(), st)) return 1;
+    c->launches += 1;
+  } else {
+    c->leaf_n = 0;
+  }
+  WCX_CUDA_OK(cudaEventRecord(c->ev[7], st));
   PrepView pv = prep_view(c);
   if (tc_encode_tensor_map(pv, c->tmap)) return 1;
   if (tc_encode_tensor_map(prep_view_h(c), c->tmap_h)) return 1;
@@ -396,7 +413,8 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     if (rt < 0) return 1;
     if (rt == 1 &&
         launch_rerank(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
-                      c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->plan_dev.as<int32_t>(), c->plan_len, st))
+                      c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->plan_dev.as<int32_t>(), c->plan_len,
+                      c->leaf_n ? c->xp.as<double>() : nullptr, c->sp, c->leafdesc_dev.as<int32_t>(), c->leaf_n, st))
       return 1;
     WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
     c->launches += 2;

@@ -140,43 +140,87 @@ __global__ void cbs_prepare_kernel(const double* __restrict__ y, const double* _
 // all-arcs maximum.  arcs 0 <= i < j <= n with al0 <= j - i <= n - al0.
 // prefix arrays are stored shifted: P(t) = t == 0 ? 0 : arr[lo + t - 1]
 // ------------------------------------------------------------------------------------------
+// Register-tiled: a thread keeps MA_J end positions j (sx_j, cw_j) in registers and walks the chunk's start positions
+// i staged in shared memory (one broadcast LDS.128 per i for MA_J arcs).  The division of the statistic is only
+// executed for arcs that can still matter: with thr = best * (1 - 2^-50) an arc whose rounded quotient num / den
+// reaches `best` always satisfies num >= fl(thr * den) (three roundings of 2^-53 each are covered by the 2^-50
+// margin), so skipping the others cannot change the maximum or its tie rule; the survivors go through the exact
+// division and the (largest bss, smallest i, smallest j) comparison.  7 FP64 operations per arc instead of a
+// division, 0.5 shared-memory loads instead of 2 global ones.
+constexpr int MA_J = 4;
+constexpr int MA_ISTAGE = 512;
+
 __global__ void __launch_bounds__(256)
 cbs_maxarc_kernel(const double* __restrict__ sx, const double* __restrict__ cw, const Seg* __restrict__ segs,
                   const Chunk* __restrict__ chunks, int al0, ArcBest* __restrict__ partial) {
+  __shared__ double2 s_iv[MA_ISTAGE];
   __shared__ double s_b[256];
   __shared__ int s_i[256], s_j[256];
+  const int tid = threadIdx.x;
   const Chunk ch = chunks[blockIdx.x];
   const int64_t lo = segs[ch.seg].lo;
   const int n = (int)(segs[ch.seg].hi - lo);
   const double* psx = sx + lo - 1;  // psx[t] valid for t >= 1
   const double* pcw = cw + lo - 1;
   const double cwn = pcw[n];
-  double best = -1.0;
+  const unsigned span = (unsigned)(n - 2 * al0);  // arc widths d = j - i with al0 <= d <= n - al0
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double best = -1.0, thr = -1.0;
   int bi = 0, bj = 0;
-  for (int i = ch.i0; i < ch.i1; i++) {
-    const double sxi = i == 0 ? 0.0 : psx[i];
-    const double cwi = i == 0 ? 0.0 : pcw[i];
-    const int jlo = i + al0;
-    const int jhi = min(n, i + n - al0);
-    for (int j = jlo + (int)threadIdx.x; j <= jhi; j += 256) {
-      const double s = psx[j] - sxi;
-      const double dw = pcw[j] - cwi;
-      const double bss = (s * s) / (dw * (cwn - dw));
-      if (bss > best) { best = bss; bi = i; bj = j; }  // i, j ascend per thread: strict > keeps the smallest
+  for (int ib = ch.i0; ib < ch.i1; ib += MA_ISTAGE) {
+    const int ie = min(ch.i1, ib + MA_ISTAGE);
+    __syncthreads();
+    for (int t = tid; t < ie - ib; t += 256) {
+      const int i = ib + t;
+      s_iv[t] = make_double2(i == 0 ? 0.0 : psx[i], i == 0 ? 0.0 : pcw[i]);
+    }
+    __syncthreads();
+    const int jend = min(n, ie - 1 + n - al0);
+    for (int jt = ib + al0; jt <= jend; jt += 256 * MA_J) {
+      double sxj[MA_J], cwj[MA_J];
+#pragma unroll
+      for (int u = 0; u < MA_J; u++) {
+        const int j = jt + tid + 256 * u;
+        const bool in = j <= jend;
+        sxj[u] = in ? psx[j] : nan;  // NaN numerator: never passes the filter
+        cwj[u] = in ? pcw[j] : 0.0;
+      }
+      // start positions that can pair with this tile: j - (n - al0) <= i <= j - al0
+      const int i_lo = max(ib, jt - (n - al0));
+      const int i_hi = min(ie, jt + 256 * MA_J - al0);
+      int dbase = jt + tid - i_lo - al0;  // (j - i) - al0 of slot 0
+      for (int i = i_lo; i < i_hi; i++, dbase--) {
+        const double2 v = s_iv[i - ib];
+#pragma unroll
+        for (int u = 0; u < MA_J; u++) {
+          const double sd = sxj[u] - v.x;
+          const double dw = cwj[u] - v.y;
+          const double num = sd * sd;
+          const double den = dw * (cwn - dw);
+          if ((unsigned)(dbase + 256 * u) <= span && num >= thr * den) {
+            const double bss = num / den;
+            const int j = jt + tid + 256 * u;
+            if (arc_better(bss, i, j, best, bi, bj)) {
+              best = bss; bi = i; bj = j;
+              thr = best * (1.0 - 0x1p-50);
+            }
+          }
+        }
+      }
     }
   }
-  s_b[threadIdx.x] = best; s_i[threadIdx.x] = bi; s_j[threadIdx.x] = bj;
+  s_b[tid] = best; s_i[tid] = bi; s_j[tid] = bj;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      const int t = threadIdx.x + o;
-      if (arc_better(s_b[t], s_i[t], s_j[t], s_b[threadIdx.x], s_i[threadIdx.x], s_j[threadIdx.x])) {
-        s_b[threadIdx.x] = s_b[t]; s_i[threadIdx.x] = s_i[t]; s_j[threadIdx.x] = s_j[t];
+    if (tid < o) {
+      const int t = tid + o;
+      if (arc_better(s_b[t], s_i[t], s_j[t], s_b[tid], s_i[tid], s_j[tid])) {
+        s_b[tid] = s_b[t]; s_i[tid] = s_i[t]; s_j[tid] = s_j[t];
       }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { partial[blockIdx.x].bss = s_b[0]; partial[blockIdx.x].i = s_i[0]; partial[blockIdx.x].j = s_j[0]; }
+  if (tid == 0) { partial[blockIdx.x].bss = s_b[0]; partial[blockIdx.x].i = s_i[0]; partial[blockIdx.x].j = s_j[0]; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,23 +230,45 @@ cbs_maxarc_kernel(const double* __restrict__ sx, const double* __restrict__ cw, 
 // ------------------------------------------------------------------------------------------
 struct PermJob {
   int64_t lo;
+  int64_t scratch_off;  // first double of this job's scratch: two planes of n * nperm doubles
   int32_t n, max_width;
   uint32_t seed, lo_id, hi_id;
   int32_t perm0;      // first permutation index of this batch
+  int32_t nperm;      // permutations of this batch (= scratch stride)
+  int32_t pad;
   double ostat, rtw, tot_w, tss_y;
 };
 
+// max over the arcs (i, j), j in [j0, j1], of the statistic; the division only runs for arcs that can raise `best`
+// (same filter and margin as cbs_maxarc_kernel: the result equals the maximum of the rounded quotients)
+__device__ __forceinline__ void perm_arcs(const double* __restrict__ sxp, int64_t stride, const double* __restrict__ pcw,
+                                          double sxi, double cwi, double cwn, int j0, int j1, double& best, double& thr) {
+  for (int j = j0; j <= j1; j++) {
+    const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
+    const double dw = pcw[j] - cwi;
+    const double num = s * s;
+    const double den = dw * (cwn - dw);
+    if (num >= thr * den) {
+      const double bss = num / den;
+      if (bss > best) { best = bss; thr = best * (1.0 - 0x1p-50); }
+    }
+  }
+}
+
+// grid (ceil(max nperm / 128), jobs): all permutation tests of a round run in one launch
 __global__ void __launch_bounds__(128)
-cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, const double* __restrict__ cw, PermJob job,
-                int nperm_batch, int al0, double* __restrict__ scratch, int stride, int* __restrict__ nrej) {
+cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, const double* __restrict__ cw,
+                const PermJob* __restrict__ jobs, int al0, double* __restrict__ scratch_all, int* __restrict__ nrej) {
+  const PermJob job = jobs[blockIdx.y];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nperm_batch) return;
+  if (p >= job.nperm) return;
   const int n = job.n;
+  const int64_t stride = job.nperm;
   const double* y = yy + job.lo;
   const double* ws = w + job.lo;
   const double* pcw = cw + job.lo - 1;
-  double* py = scratch + p;                    // py[i * stride]
-  double* sxp = scratch + (int64_t)n * stride + p;  // second plane: re-centred prefix sums, index t = 1..n at (t-1)
+  double* py = scratch_all + job.scratch_off + p;   // py[i * stride]
+  double* sxp = py + (int64_t)n * stride;           // second plane: re-centred prefix sums, index t = 1..n at (t-1)
   for (int i = 0; i < n; i++) py[(int64_t)i * stride] = y[i];
   PermStream st(job.seed, 0u, job.lo_id, job.hi_id, (uint32_t)(job.perm0 + p));
   // wxperm: Fisher-Yates from the top; px[i] = py[i] / rw[i]; accumulate sum(ws * px) on the fly is
@@ -224,39 +290,24 @@ cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, con
   const double tss = job.tss_y - job.tot_w * xbar * xbar;
   for (int t = 1; t <= n; t++) sxp[(int64_t)(t - 1) * stride] = sxp[(int64_t)(t - 1) * stride] - xbar * (pcw[t] * job.rtw);
   const double cwn = pcw[n];
-  double best = -1.0;
+  double best = -1.0, thr = -1.0;
   const int mw = job.max_width;
   for (int i = 0; i < n; i++) {
     const double sxi = i == 0 ? 0.0 : sxp[(int64_t)(i - 1) * stride];
     const double cwi = i == 0 ? 0.0 : pcw[i];
     const int jlo = i + al0, jhi = min(n, i + n - al0);
     if (mw < 0) {
-      for (int j = jlo; j <= jhi; j++) {
-        const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
-        const double dw = pcw[j] - cwi;
-        const double bss = (s * s) / (dw * (cwn - dw));
-        best = bss > best ? bss : best;
-      }
+      perm_arcs(sxp, stride, pcw, sxi, cwi, cwn, jlo, jhi, best, thr);
     } else {
       // short arcs and, through the complement, long ones: width <= mw or width >= n - mw
       const int j1 = min(jhi, i + mw);
-      for (int j = jlo; j <= j1; j++) {
-        const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
-        const double dw = pcw[j] - cwi;
-        const double bss = (s * s) / (dw * (cwn - dw));
-        best = bss > best ? bss : best;
-      }
+      perm_arcs(sxp, stride, pcw, sxi, cwi, cwn, jlo, j1, best, thr);
       const int j2 = max(max(jlo, i + n - mw), j1 + 1);
-      for (int j = j2; j <= jhi; j++) {
-        const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
-        const double dw = pcw[j] - cwi;
-        const double bss = (s * s) / (dw * (cwn - dw));
-        best = bss > best ? bss : best;
-      }
+      perm_arcs(sxp, stride, pcw, sxi, cwi, cwn, j2, jhi, best, thr);
     }
   }
   const double pstat = best / ((tss - best) / ((double)n - 2.0));
-  if (job.ostat <= pstat) atomicAdd(nrej, 1);
+  if (job.ostat <= pstat) atomicAdd(nrej + blockIdx.y, 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -465,7 +516,7 @@ struct DBuf {
 }  // namespace
 
 struct CbsWorkspace {
-  DBuf y, w, xc, sx, cw, yy, segs, prep, chunks, partial, scratch, nrej, tjobs;
+  DBuf y, w, xc, sx, cw, yy, segs, prep, chunks, partial, scratch, nrej, tjobs, pjobs;
 };
 
 CbsWorkspace* cbs_workspace_create() { return new CbsWorkspace(); }
@@ -487,7 +538,7 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
   for (int s = 0; s < nseries; s++)
     if (off[s + 1] > off[s]) pending.push_back(Seg{off[s], off[s + 1], s, 0});
   const int al0 = min_width;
-  const int64_t CHUNK_ARCS = 1 << 21;
+  const int64_t CHUNK_ARCS = 1 << 20;
   if (stats) std::memset(stats, 0, sizeof(*stats));
   while (!pending.empty()) {
     // segments too short to split are final
@@ -573,7 +624,96 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
         }
       }
     }
-    // decisions
+    // decisions, part 1: gates and the hybrid p-value decide most segments; the rest need a permutation test
+    std::vector<char> split_of(nseg, 0);
+    std::vector<double> ostat_of(nseg, 0.0);
+    struct PermTest { int seg, nrejc, mw, nrej, done; };
+    std::vector<PermTest> tests;
+    for (int s = 0; s < nseg; s++) {
+      const int n = (int)(work[s].hi - work[s].lo);
+      const SegPrep& pr = prep[s];
+      if (pr.flat || best[s].bss < 0.0) continue;
+      double ostat = best[s].bss / ((pr.tss - best[s].bss) / ((double)n - 2.0));
+      const double ostat1 = ostat > 0 ? std::sqrt(ostat) : 0.0;
+      ostat *= 0.99999;
+      ostat_of[s] = ostat;
+      if (!(ostat1 > 0.1)) continue;
+      const int width = best[s].j - best[s].i;
+      const int l = std::min(width, n - width);
+      if (ostat1 >= 7.0 && l >= 10) { split_of[s] = 1; continue; }
+      if (n > nmin) {
+        const double pval1 = pval1_of[s];
+        if (pval1 > alpha) continue;
+        tests.push_back(PermTest{s, (int)((alpha - pval1) * (double)nperm), kmax, 0, 0});
+      } else {
+        tests.push_back(PermTest{s, (int)(alpha * (double)nperm), -1, 0, 0});
+      }
+    }
+    // permutation tests of the whole round in escalating batches (256, 1024, then 2048 at a time): all undecided
+    // tests share one launch per stage; a test stops as soon as its rejection count exceeds the threshold, which
+    // is the decision the full count would give (the permutation index is the Philox counter, not the batch)
+    if (!tests.empty()) {
+      if (stats) stats->perm_tests += (int)tests.size();
+      std::vector<int> active(tests.size());
+      for (size_t q = 0; q < tests.size(); q++) active[q] = (int)q;
+      int stage = 0;
+      while (!active.empty()) {
+        const int want = stage == 0 ? 256 : (stage == 1 ? 1024 : 2048);
+        stage++;
+        // groups of tests whose scratch fits the budget
+        size_t g0 = 0;
+        std::vector<int> still;
+        while (g0 < active.size()) {
+          std::vector<PermJob> jobs;
+          std::vector<int> jq;
+          size_t doubles = 0;
+          int maxnb = 0;
+          size_t g1 = g0;
+          for (; g1 < active.size(); g1++) {
+            PermTest& t = tests[active[g1]];
+            const Seg& sg = work[t.seg];
+            const int n = (int)(sg.hi - sg.lo);
+            const int nb = std::min(want, nperm - t.done);
+            const size_t need = 2 * (size_t)n * nb;
+            if (!jobs.empty() && (doubles + need) * sizeof(double) > ((size_t)3 << 30)) break;
+            const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
+            PermJob job;
+            job.lo = sg.lo; job.scratch_off = (int64_t)doubles; job.n = n; job.max_width = t.mw;
+            job.seed = (uint32_t)((uint64_t)seed * 1000003ull + (uint64_t)(uint32_t)sid);
+            job.lo_id = (uint32_t)(sg.lo - off[sg.series]); job.hi_id = (uint32_t)(sg.hi - off[sg.series]);
+            job.perm0 = t.done; job.nperm = nb; job.pad = 0;
+            job.ostat = ostat_of[t.seg]; job.rtw = prep[t.seg].rtw; job.tot_w = prep[t.seg].tot_w; job.tss_y = prep[t.seg].tss_y;
+            jobs.push_back(job);
+            jq.push_back(active[g1]);
+            doubles += need;
+            maxnb = std::max(maxnb, nb);
+          }
+          const int nj = (int)jobs.size();
+          if (ws->scratch.ensure(sizeof(double) * doubles) || ws->pjobs.ensure(sizeof(PermJob) * nj) || ws->nrej.ensure(sizeof(int) * nj)) return 1;
+          WCX_CUDA_OK(cudaMemcpyAsync(ws->pjobs.p, jobs.data(), sizeof(PermJob) * nj, cudaMemcpyHostToDevice, st));
+          WCX_CUDA_OK(cudaMemsetAsync(ws->nrej.p, 0, sizeof(int) * nj, st));
+          cbs_perm_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(),
+                                                                       ws->pjobs.as<PermJob>(), al0, ws->scratch.as<double>(), ws->nrej.as<int>());
+          WCX_CUDA_OK(cudaGetLastError());
+          std::vector<int> h(nj);
+          WCX_CUDA_OK(cudaMemcpyAsync(h.data(), ws->nrej.p, sizeof(int) * nj, cudaMemcpyDeviceToHost, st));
+          WCX_CUDA_OK(cudaStreamSynchronize(st));
+          if (stats) stats->launches++;
+          for (int q = 0; q < nj; q++) {
+            PermTest& t = tests[jq[q]];
+            t.nrej += h[q];
+            t.done += jobs[q].nperm;
+            if (stats) stats->permutations += jobs[q].nperm;
+            if (t.nrej > t.nrejc) continue;                           // not significant: decided, no split
+            if (t.done >= nperm) { split_of[t.seg] = 1; continue; }   // significant
+            still.push_back(jq[q]);
+          }
+          g0 = g1;
+        }
+        active.swap(still);
+      }
+    }
+    // decisions, part 2: change-points of the segments that split
     for (int s = 0; s < nseg; s++) {
       const Seg& sg = work[s];
       const int n = (int)(sg.hi - sg.lo);
@@ -581,56 +721,8 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
       const uint32_t sseed = (uint32_t)((uint64_t)seed * 1000003ull + (uint64_t)(uint32_t)sid);
       const uint32_t lo_id = (uint32_t)(sg.lo - off[sg.series]), hi_id = (uint32_t)(sg.hi - off[sg.series]);
       std::vector<int> cpts;
-      bool split = false;
-      const SegPrep& pr = prep[s];
+      const bool split = split_of[s] != 0;
       const int i1 = best[s].i, i2 = best[s].j;
-      if (!pr.flat && best[s].bss >= 0.0) {
-        double ostat = best[s].bss / ((pr.tss - best[s].bss) / ((double)n - 2.0));
-        const double ostat1 = ostat > 0 ? std::sqrt(ostat) : 0.0;
-        ostat *= 0.99999;
-        if (ostat1 > 0.1) {
-          const int width = i2 - i1;
-          const int l = std::min(width, n - width);
-          split = (ostat1 >= 7.0 && l >= 10);
-          if (!split) {
-            const bool hybrid = n > nmin;
-            int nrejc;
-            bool run = true;
-            int mw = -1;
-            if (hybrid) {
-              const double pval1 = pval1_of[s];
-              if (pval1 > alpha) run = false;
-              nrejc = (int)((alpha - pval1) * (double)nperm);
-              mw = kmax;
-            } else {
-              nrejc = (int)(alpha * (double)nperm);
-            }
-            if (run) {
-              if (stats) stats->perm_tests++;
-              const int PB = 2048;
-              const size_t need = sizeof(double) * 2 * (size_t)n * PB;
-              if (ws->scratch.ensure(need)) return 1;
-              int nrej = 0;
-              split = true;
-              for (int p0 = 0; p0 < nperm; p0 += PB) {
-                const int nb = std::min(PB, nperm - p0);
-                WCX_CUDA_OK(cudaMemsetAsync(ws->nrej.p, 0, sizeof(int), st));
-                PermJob job;
-                job.lo = sg.lo; job.n = n; job.max_width = mw; job.seed = sseed; job.lo_id = lo_id; job.hi_id = hi_id;
-                job.perm0 = p0; job.ostat = ostat; job.rtw = pr.rtw; job.tot_w = pr.tot_w; job.tss_y = pr.tss_y;
-                cbs_perm_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(), job,
-                                                                  nb, al0, ws->scratch.as<double>(), PB, ws->nrej.as<int>());
-                int h = 0;
-                WCX_CUDA_OK(cudaMemcpyAsync(&h, ws->nrej.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-                WCX_CUDA_OK(cudaStreamSynchronize(st));
-                if (stats) { stats->launches++; stats->permutations += nb; }
-                nrej += h;
-                if (nrej > nrejc) { split = false; break; }
-              }
-            }
-          }
-        }
-      }
       if (split) {
         if (i2 == n) cpts.push_back(i1);
         else if (i1 == 0) cpts.push_back(i2);

@@ -17,6 +17,7 @@
 // path whenever the prefix is not strictly below the cut or the a-posteriori check
 // (exact d_(k) + eps < bound) fails.  Flagged rows are recomputed by exact_rows_kernel, so the
 // final indexes never depend on the approximation.
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -47,6 +48,70 @@ int build_sum_plan(int32_t s, int32_t* plan, int32_t cap) {
   if ((int32_t)p.size() > cap) return -1;
   for (size_t i = 0; i < p.size(); i++) plan[i] = p[i];
   return (int32_t)(p.size() / 3);
+}
+
+// ------------------------------------------------------------------------------------------
+// Leaf-major ("chain-interleaved") copy of X for the re-rank gather.
+//
+// The r01d profile of the LDG re-rank shows the L1 data pipe at 88 % (one warp-level LDG.128 of 8 quads touches 8
+// cache lines = 8-10 wavefronts per 512 bytes, plus 4 wavefronts per LDS.128 of the target row) with L2 at 37 %.
+// Here every row of X is stored once more in the order the summation consumes it: a leaf of NumPy's pairwise tree
+// (<= 128 terms, accumulator chain c = element index mod 8) becomes `steps` units of 128 bytes; unit t holds, for
+// chain c = 0..7, the chain's elements 2t and 2t+1 (16 bytes per chain).  Eight lanes (one per chain) then read one
+// full 128-byte line per step (4 lines = 4 wavefronts per warp-level LDG.128), every lane adds its own chain in
+// NumPy's order, and the target row's chain values of the leaf sit in registers while the lane group walks its
+// candidates, so the target row costs 8 LDS.128 per leaf instead of one per candidate block.
+// Padding (odd block count, tail padded to even) is 0.0 in every row: (0 - 0)^2 = +0 added to a non-negative
+// accumulator leaves it bit-identical.  The < 8 tail terms of a leaf follow its units and are added in sequence.
+// desc: 4 int32 per leaf = (offset in doubles, steps, tail terms, 0).  Returns the permuted row length.
+// ------------------------------------------------------------------------------------------
+int build_leaf_layout(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& perm, std::vector<int32_t>& desc) {
+  perm.clear();
+  desc.clear();
+  for (int op = 0; op < plan_len; op++) {
+    if (plan[3 * op] != 0) continue;
+    const int off = plan[3 * op + 1], len = plan[3 * op + 2];
+    const int nblk = len >> 3, steps = (nblk + 1) >> 1, tail = len - (nblk << 3);
+    if (steps > 8) return -1;
+    desc.push_back((int32_t)perm.size());
+    desc.push_back(steps);
+    desc.push_back(tail);
+    desc.push_back(0);
+    for (int t = 0; t < steps; t++)
+      for (int c = 0; c < 8; c++) {
+        perm.push_back(off + 8 * (2 * t) + c);
+        perm.push_back(2 * t + 1 < nblk ? off + 8 * (2 * t + 1) + c : -1);
+      }
+    for (int i = 0; i < tail; i++) perm.push_back(off + 8 * nblk + i);
+    while (perm.size() % 16) perm.push_back(-1);  // every leaf starts on a 128-byte line
+  }
+  return (int)perm.size();
+}
+
+namespace {
+
+// xp[r][p] = perm[p] >= 0 ? x[r][perm[p]] : 0.0
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const double* __restrict__ x, int64_t n, int32_t s, const int32_t* __restrict__ perm, int32_t sp,
+                    double* __restrict__ xp) {
+  for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+    const double* xr = x + r * s;
+    double* o = xp + r * sp;
+    for (int p = threadIdx.x; p < sp; p += 256) {
+      const int q = perm[p];
+      o[p] = q >= 0 ? xr[q] : 0.0;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_permute_rows(const double* x, int64_t n, int32_t s, const int32_t* perm_dev, int32_t sp, double* xp, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)std::min<int64_t>(n, 148 * 16);
+  permute_rows_kernel<<<grid, 256, 0, st>>>(x, n, s, perm_dev, sp, xp);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 namespace {
@@ -179,6 +244,84 @@ __device__ void bitonic_sort_dpos(uint64_t* dkey, int32_t* pos, int n_pow2) {
   }
 }
 
+// Same sort with the elements in registers: element i = e * RR_THREADS + tid lives in slot e of thread tid.  A
+// compare-exchange distance j < 32 is a warp shuffle, j >= RR_THREADS pairs two slots of one thread, only
+// j = 32, 64, 128 go through shared memory (9 of the 45 steps at 512 entries) -- the r01d profile shows the
+// barrier-per-step shared-memory version costing ~9k L1 wavefronts and 45 barriers per row.
+__device__ __forceinline__ bool dpos_less(uint64_t ka, int32_t pa, uint64_t kb, int32_t pb) {
+  return (ka < kb) || (ka == kb && pa < pb);
+}
+__device__ __forceinline__ void dpos_cswap(uint64_t& ka, int32_t& pa, uint64_t& kb, int32_t& pb, bool up) {
+  const bool gt = dpos_less(kb, pb, ka, pa);
+  if (gt == up) {
+    const uint64_t tk = ka; ka = kb; kb = tk;
+    const int32_t tp = pa; pa = pb; pb = tp;
+  }
+}
+__device__ void bitonic_sort_dpos_regs(uint64_t* dkey, int32_t* pos, int n_pow2) {
+  const int tid = threadIdx.x;
+  const int E = n_pow2 > RR_THREADS ? n_pow2 / RR_THREADS : 1;  // 1, 2 or 4 (RR_MAXM = 4 * RR_THREADS)
+  uint64_t kk[4];
+  int32_t pp[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int i = e * RR_THREADS + tid;
+    const bool valid = e < E && i < n_pow2;
+    kk[e] = valid ? dkey[i] : ~0ull;
+    pp[e] = valid ? pos[i] : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= RR_THREADS) {
+        // both elements in this thread; the lower one (slot without bit j / RR_THREADS) decides the direction
+        if (j == RR_THREADS) {
+          dpos_cswap(kk[0], pp[0], kk[1], pp[1], ((tid) & k) == 0);
+          if (E > 2) dpos_cswap(kk[2], pp[2], kk[3], pp[3], ((2 * RR_THREADS + tid) & k) == 0);
+        } else {
+          dpos_cswap(kk[0], pp[0], kk[2], pp[2], ((tid) & k) == 0);
+          dpos_cswap(kk[1], pp[1], kk[3], pp[3], ((RR_THREADS + tid) & k) == 0);
+        }
+      } else {
+        if (j >= 32) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int i = e * RR_THREADS + tid;
+            if (e < E && i < n_pow2) { dkey[i] = kk[e]; pos[i] = pp[e]; }
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (e < E) {
+            const int i = e * RR_THREADS + tid;
+            uint64_t ok;
+            int32_t op;
+            if (j >= 32) {
+              const bool valid = i < n_pow2;
+              ok = valid ? dkey[i ^ j] : ~0ull;
+              op = valid ? pos[i ^ j] : 0x7fffffff;
+            } else {
+              ok = __shfl_xor_sync(0xffffffffu, kk[e], j);
+              op = __shfl_xor_sync(0xffffffffu, pp[e], j);
+            }
+            const bool keep_min = (((i & j) == 0) == ((i & k) == 0));
+            const bool less_o = dpos_less(ok, op, kk[e], pp[e]);
+            if (keep_min == less_o) { kk[e] = ok; pp[e] = op; }  // equal pairs are identical: either choice is the same
+          }
+        }
+        if (j >= 32) __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int i = e * RR_THREADS + tid;
+    if (e < E && i < n_pow2) { dkey[i] = kk[e]; pos[i] = pp[e]; }
+  }
+  __syncthreads();
+}
+
 // block-wide sum of a per-thread count; result valid in every thread (two barriers)
 __device__ __forceinline__ int __syncthreads_count_sum(int c) {
   __shared__ int s_red[RR_THREADS / 32];
@@ -215,6 +358,107 @@ __device__ __forceinline__ double approx_eps(double an, double D, int k_pad, dou
   return 1.5 * (rounding + accum + misc) + 1e-300;
 }
 
+
+// ---- leaf-major evaluation (see build_leaf_layout) ------------------------------------------------------------
+
+// volatile: the 2 x STEPS loads of a candidate pair are issued back to back, before the first dependent add
+__device__ __forceinline__ double2 ldg_nc_d2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// One leaf (STEPS units of 128 bytes + `tail` sequential terms at row offset `off`) of the candidates
+// sel[0..cn): 8 lanes (one per accumulator chain, c8 = lane & 7) per candidate, 32 candidates per pass; PAIR: two
+// passes (A, B) in flight and the target row's unit (one LDS.128) shared by the pair.  Leaf sums go to
+// leafres[candidate * nleaves + lf].
+template <int STEPS, bool PAIR>
+__device__ __forceinline__ void leaf_pass(const double* __restrict__ x, int sp, const double* __restrict__ a_s,
+                                          const int32_t* __restrict__ sel, int cn, int off, int tail, int nleaves, int lf,
+                                          double* __restrict__ leafres, int tid) {
+  constexpr int NV = STEPS > 0 ? STEPS : 1;
+  constexpr int G = RR_THREADS / 8;
+  const int lane = tid & 31, c8 = tid & 7, grp = tid >> 3;
+  const double2* ap = reinterpret_cast<const double2*>(a_s + off) + c8;  // unit t: ap[8 * t]
+  const int toff = off + STEPS * 16 + c8;                                // this lane's tail term (c8 < tail)
+  const double a_tail = c8 < tail ? a_s[toff] : 0.0;
+  const int base = lane & ~7;
+  for (int c0 = 0; c0 < cn; c0 += (PAIR ? 2 : 1) * G) {
+    const int ciA = c0 + grp, ciB = ciA + G;
+    // clamped: idle groups redo the last candidate, which keeps the warp converged for the shuffles
+    const double* rowA = x + (int64_t)sel[ciA < cn ? ciA : cn - 1] * sp;
+    const double* rowB = PAIR ? x + (int64_t)sel[ciB < cn ? ciB : cn - 1] * sp : rowA;
+    const double2* pa = reinterpret_cast<const double2*>(rowA + off) + c8;
+    const double2* pb = reinterpret_cast<const double2*>(rowB + off) + c8;
+    double2 va[NV], vb[NV];
+#pragma unroll
+    for (int t = 0; t < STEPS; t++) va[t] = ldg_nc_d2(pa + 8 * t);
+    if (PAIR) {
+#pragma unroll
+      for (int t = 0; t < STEPS; t++) vb[t] = ldg_nc_d2(pb + 8 * t);
+    }
+    double ta = 0.0, tb = 0.0;
+    if (c8 < tail) {
+      ta = __ldg(rowA + toff);
+      if (PAIR) tb = __ldg(rowB + toff);
+    }
+    double rA = 0.0, rB = 0.0;
+#pragma unroll
+    for (int t = 0; t < STEPS; t++) {
+      const double2 av = ap[8 * t];
+      const double uA0 = __dsub_rn(va[t].x, av.x);
+      rA = __dadd_rn(rA, __dmul_rn(uA0, uA0));
+      if (PAIR) {
+        const double uB0 = __dsub_rn(vb[t].x, av.x);
+        rB = __dadd_rn(rB, __dmul_rn(uB0, uB0));
+      }
+      const double uA1 = __dsub_rn(va[t].y, av.y);
+      rA = __dadd_rn(rA, __dmul_rn(uA1, uA1));
+      if (PAIR) {
+        const double uB1 = __dsub_rn(vb[t].y, av.y);
+        rB = __dadd_rn(rB, __dmul_rn(uB1, uB1));
+      }
+    }
+    // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), identical in all 8 lanes
+    double sA = __dadd_rn(rA, __shfl_xor_sync(0xffffffffu, rA, 1));
+    sA = __dadd_rn(sA, __shfl_xor_sync(0xffffffffu, sA, 2));
+    sA = __dadd_rn(sA, __shfl_xor_sync(0xffffffffu, sA, 4));
+    double sB = 0.0;
+    if (PAIR) {
+      sB = __dadd_rn(rB, __shfl_xor_sync(0xffffffffu, rB, 1));
+      sB = __dadd_rn(sB, __shfl_xor_sync(0xffffffffu, sB, 2));
+      sB = __dadd_rn(sB, __shfl_xor_sync(0xffffffffu, sB, 4));
+    }
+    if (tail > 0) {
+      ta = __dsub_rn(ta, a_tail);
+      tb = __dsub_rn(tb, a_tail);
+      const double qa = __dmul_rn(ta, ta), qb = __dmul_rn(tb, tb);
+      for (int i = 0; i < tail; i++) {
+        sA = __dadd_rn(sA, __shfl_sync(0xffffffffu, qa, base + i));
+        if (PAIR) sB = __dadd_rn(sB, __shfl_sync(0xffffffffu, qb, base + i));
+      }
+    }
+    if (c8 == 0) {
+      if (ciA < cn) leafres[ciA * nleaves + lf] = sA;
+      if (PAIR && ciB < cn) leafres[ciB * nleaves + lf] = sB;
+    }
+  }
+}
+
+// combination of the leaf sums of one candidate in NumPy's order (register stack, as exact_sqdist_quad)
+__device__ __forceinline__ double combine_leaves(const double* __restrict__ lr, const int32_t* __restrict__ plan, int plan_len) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
+  int li = 0;
+  for (int op = 0; op < plan_len; op++) {
+    if (plan[3 * op] == 0) {
+      s7 = s6; s6 = s5; s5 = s4; s4 = s3; s3 = s2; s2 = s1; s1 = s0; s0 = lr[li++];
+    } else {
+      s0 = __dadd_rn(s1, s0);
+      s1 = s2; s2 = s3; s3 = s4; s4 = s5; s5 = s6; s6 = s7;
+    }
+  }
+  return s0;
+}
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -222,21 +466,28 @@ __device__ __forceinline__ double approx_eps(double an, double D, int k_pad, dou
 // ------------------------------------------------------------------------------------------
 // shared memory: a[S] doubles | keys[maxc] u64 (later: exact distance keys) | sel[RR_MAXM] i32 |
 //                pos[RR_MAXM] i32 | plan
-template <bool VEC>
-__global__ void __launch_bounds__(RR_THREADS, 4)  // min 4 CTAs/SM: lets ptxas keep the batched loads in flight (64 regs)
+// LEAF: `x` is the leaf-major copy (row stride `sp` doubles, build_leaf_layout), `leaf_g` its descriptors.
+template <bool VEC, bool LEAF, bool PAIR>
+__global__ void __launch_bounds__(RR_THREADS, (LEAF && PAIR) ? 3 : 4)  // LDG version: min 4 CTAs/SM keeps the batched loads in flight (64 regs)
 rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists, int maxc, const int64_t* __restrict__ cum,
               int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
               double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
-              int plan_len) {
+              int plan_len, int sp, const int32_t* __restrict__ leaf_g, int nleaves) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
+  const int row_len = LEAF ? sp : pv.s;  // doubles per row of `x`
   double* a_s = reinterpret_cast<double*>(rr_smem);
-  uint32_t* vals = reinterpret_cast<uint32_t*>(a_s + ((pv.s + 1) & ~1));  // [maxc] orderable keys of the approximate values
+  uint32_t* vals = reinterpret_cast<uint32_t*>(a_s + ((row_len + 1) & ~1));  // [maxc] orderable keys of the approximate values
   uint32_t* jidx = vals + maxc;                                           // [maxc] candidate bins
   int32_t* sel = reinterpret_cast<int32_t*>(jidx + maxc);                 // [RR_MAXM]
   int32_t* plan = sel + RR_MAXM;
+  // LEAF: leaf descriptors and the per-candidate leaf sums [RR_MAXM][nleaves] follow the plan
+  int32_t* leaf_s = plan + ((3 * plan_len + 3) & ~3);
   // vals / jidx are dead once `sel` is built: the exact (distance, position) pairs reuse the space
   uint64_t* keys = reinterpret_cast<uint64_t*>(vals);  // [RR_MAXM]
   int32_t* pos_s = reinterpret_cast<int32_t*>(keys + RR_MAXM);
+  // LEAF: per-candidate leaf sums of a batch of candidates, in the rest of the dead list region
+  double* leafres = reinterpret_cast<double*>(pos_s + RR_MAXM);
+  const int leafres_bytes = maxc * 8 - RR_MAXM * 12;
   __shared__ int s_tot, s_m, s_fail, s_cnt;
   __shared__ int s_cs, s_ce;
   __shared__ float s_cut;
@@ -269,8 +520,10 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   const int cs = s_cs, ce = s_ce;
   const float cut = s_cut;
-  for (int i = tid; i < pv.s; i += RR_THREADS) a_s[i] = x[row * pv.s + i];
+  for (int i = tid; i < row_len; i += RR_THREADS) a_s[i] = x[row * row_len + i];
   for (int i = tid; i < 3 * plan_len; i += RR_THREADS) plan[i] = plan_g[i];
+  if (LEAF)
+    for (int i = tid; i < 4 * nleaves; i += RR_THREADS) leaf_s[i] = leaf_g[i];
 
   // gather the list entries below the common cut
   uint32_t mn = 0xffffffffu, mx = 0u;
@@ -369,22 +622,52 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     return;
   }
 
-  // exact distances, one quad per candidate; results overwrite keys[0..m)
-  const int quad = tid >> 2, l = tid & 3;
-  for (int c0 = 0; c0 < m; c0 += RR_THREADS / 4) {
-    const int ci = c0 + quad;
-    const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
-    const int j = sel[cc];
-    const double d = exact_sqdist_quad<VEC>(a_s, x + (int64_t)j * pv.s, plan, plan_len, l);
-    if (l == 0 && ci < m) {
-      keys[ci] = f64_key(d);
-      pos_s[ci] = j < cs ? j : j - (ce - cs);  // position in the chromosome-excluded array
+  if (LEAF) {
+    // exact distances, leaf-major (leaf_pass); candidates in batches whose leaf sums fit leafres
+    const int cap = min(RR_MAXM, leafres_bytes / (8 * nleaves));
+    for (int cb = 0; cb < m; cb += cap) {
+      const int cn = min(cap, m - cb);
+      for (int lf = 0; lf < nleaves; lf++) {
+        const int off = leaf_s[4 * lf], steps = leaf_s[4 * lf + 1], tail = leaf_s[4 * lf + 2];
+        switch (steps) {
+          case 8: leaf_pass<8, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 7: leaf_pass<7, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 6: leaf_pass<6, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 5: leaf_pass<5, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 4: leaf_pass<4, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 3: leaf_pass<3, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 2: leaf_pass<2, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 1: leaf_pass<1, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          default: leaf_pass<0, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+        }
+      }
+      __syncthreads();
+      for (int ci = tid; ci < cn; ci += RR_THREADS) {
+        const int j = sel[cb + ci];
+        keys[cb + ci] = f64_key(combine_leaves(leafres + ci * nleaves, plan, plan_len));
+        pos_s[cb + ci] = j < cs ? j : j - (ce - cs);  // position in the chromosome-excluded array
+      }
+      __syncthreads();
+    }
+  } else {
+    // exact distances, one quad per candidate; results overwrite keys[0..m)
+    const int quad = tid >> 2, l = tid & 3;
+    for (int c0 = 0; c0 < m; c0 += RR_THREADS / 4) {
+      const int ci = c0 + quad;
+      const int cc = ci < m ? ci : (m - 1);  // keep the warp converged for the shuffles
+      const int j = sel[cc];
+      const double d = exact_sqdist_quad<VEC>(a_s, x + (int64_t)j * pv.s, plan, plan_len, l);
+      if (l == 0 && ci < m) {
+        keys[ci] = f64_key(d);
+        pos_s[ci] = j < cs ? j : j - (ce - cs);  // position in the chromosome-excluded array
+      }
     }
   }
   const int p2m = next_pow2(m < 2 ? 2 : m);
   for (int i = m + tid; i < p2m; i += RR_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
   __syncthreads();
-  bitonic_sort_dpos(keys, pos_s, p2m);
+  if (LEAF) bitonic_sort_dpos_regs(keys, pos_s, p2m);
+  else bitonic_sort_dpos(keys, pos_s, p2m);
 
   // a-posteriori completeness check: exact d_(k) + eps must stay below bound + |a|^2
   if (tid == 0 && tot > k) {
@@ -417,26 +700,33 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
 int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
-                  int32_t plan_len, cudaStream_t st) {
+                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves, cudaStream_t st) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0) return 0;
   if (nlists < 1 || nlists > 4) { set_error("rerank: bad number of candidate lists per row"); return 1; }
   const int maxc = nlists <= 2 ? 4096 : 8192;  // list entries below the common cut that fit in shared memory
-  const size_t smem = sizeof(double) * ((pv.s + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 4 + sizeof(int32_t) * 3 * plan_len;
+  // leaf-major gather (default) needs the permuted copy; WCX_RERANK_LDG=1 forces the row-major LDG gather,
+  // WCX_RERANK_PAIR=0 the one-candidate-per-lane-group variant (4 CTAs per SM instead of 3)
+  static const bool force_ldg = std::getenv("WCX_RERANK_LDG") != nullptr;
+  static const char* pair_env = std::getenv("WCX_RERANK_PAIR");
+  static const bool pair = !(pair_env && pair_env[0] == '0');
+  const bool leaf = xp != nullptr && !force_ldg && nleaves >= 1 && nleaves <= 8;
+  const int row_len = leaf ? sp : pv.s;
+  size_t smem = sizeof(double) * ((row_len + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 4 + sizeof(int32_t) * ((3 * plan_len + 3) & ~3);
+  if (leaf) smem += sizeof(int32_t) * 4 * nleaves;
   const bool vec = (pv.s % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  static size_t attr[2] = {0, 0};
-  if (smem > attr[vec]) {
-    if (vec) WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else WCX_CUDA_OK(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[vec] = smem;
+  static size_t attr[4] = {0, 0, 0, 0};
+  const int which = leaf ? (pair ? 3 : 2) : (vec ? 1 : 0);
+  auto kern = which == 3 ? rerank_kernel<true, true, true> : which == 2 ? rerank_kernel<true, true, false>
+              : which == 1 ? rerank_kernel<true, false, false> : rerank_kernel<false, false, false>;
+  if (smem > attr[which]) {
+    WCX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[which] = smem;
   }
   WCX_CUDA_OK(cudaMemsetAsync(fail_flags, 0, sizeof(int32_t) * rows, st));
-  if (vec)
-    rerank_kernel<true><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
-                                                                idx_out, dist_out, fail_flags, sum_plan, plan_len);
-  else
-    rerank_kernel<false><<<(unsigned)rows, RR_THREADS, smem, st>>>(x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal,
-                                                                 idx_out, dist_out, fail_flags, sum_plan, plan_len);
+  kern<<<(unsigned)rows, RR_THREADS, smem, st>>>(leaf ? xp : x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal, idx_out,
+                                               dist_out, fail_flags, sum_plan, plan_len, leaf ? sp : 0, leaf ? leaf_dev : nullptr,
+                                               leaf ? nleaves : 0);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
