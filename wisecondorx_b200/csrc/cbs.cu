@@ -16,12 +16,13 @@
 //   cbs_prepare_kernel   one thread per segment: weighted mean, centring, tss and the sequential
 //                        prefix sums sx / cw (sequential on purpose: every rounding is specified)
 //   cbs_maxarc_kernel    the O(n^2) all-arcs maximum, brute force, split into balanced chunks of
-//                        start positions over the whole grid; block reduce with the tie rule
+//                        start positions over the whole grid, register-tiled over end positions, division only
+//                        for arcs that can still be the maximum; block reduce with the tie rule
 //                        (largest bss, then smallest start, then smallest end)
-//   cbs_perm_kernel      one thread per permutation (Fisher-Yates in a private scratch column,
-//                        re-centred prefix sums, short-arc or all-arc maximum) -- only for the rare
-//                        segments whose statistic falls between the tail-probability and |t| >= 7 gates
-//   cbs_tperm_kernel     one thread per permutation of the edge t-tests
+//   cbs_tailp_kernel     Siegmund tail approximation (hybrid p-value, part 1) for every segment that needs it
+//   cbs_perm_prep / _arcs / _count   permutation tests of ALL undecided segments of the round in one staged
+//                        launch (256 permutations first, the remainder only for tests still undecided)
+//   cbs_tprep / cbs_tperm  edge t-tests of two-change-point arcs (preparation batched per round)
 // The scalar decisions (tail probability, thresholds) run on the host between the kernels.
 // This file is compiled with -fmad=false: no FMA contraction, IEEE division.
 #include <algorithm>
@@ -239,26 +240,21 @@ struct PermJob {
   double ostat, rtw, tot_w, tss_y;
 };
 
-// max over the arcs (i, j), j in [j0, j1], of the statistic; the division only runs for arcs that can raise `best`
-// (same filter and margin as cbs_maxarc_kernel: the result equals the maximum of the rounded quotients)
-__device__ __forceinline__ void perm_arcs(const double* __restrict__ sxp, int64_t stride, const double* __restrict__ pcw,
-                                          double sxi, double cwi, double cwn, int j0, int j1, double& best, double& thr) {
-  for (int j = j0; j <= j1; j++) {
-    const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
-    const double dw = pcw[j] - cwi;
-    const double num = s * s;
-    const double den = dw * (cwn - dw);
-    if (num >= thr * den) {
-      const double bss = num / den;
-      if (bss > best) { best = bss; thr = best * (1.0 - 0x1p-50); }
-    }
-  }
-}
+// The permutation statistic in three kernels (the one-thread-per-permutation version spent ~70 ms per launch in its
+// sequential arc scan whatever the number of permutations, profiles/r01g_launches_config3_with_predict.csv):
+//   cbs_perm_prep_kernel   one thread per permutation: Fisher-Yates, prefix sums, re-centring (sequential by
+//                          definition: every rounding and the Philox stream order are specified)
+//   cbs_perm_arcs_kernel   the arc scan, parallel over (permutation, block of start positions); per-permutation
+//                          maximum through atomicMax on the bit pattern (non-negative doubles order like integers,
+//                          the initial -1.0 is below all of them) -- a maximum does not depend on the order
+//   cbs_perm_count_kernel  statistic of each permutation against the observed one
+// Per job the scratch holds two planes [n][nperm] (values, prefix sums; permutation index fastest so that the
+// threads of a warp touch consecutive doubles) followed by best[nperm] and tss[nperm].
+constexpr int PA_ICHUNK = 64;
 
-// grid (ceil(max nperm / 128), jobs): all permutation tests of a round run in one launch
 __global__ void __launch_bounds__(128)
-cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, const double* __restrict__ cw,
-                const PermJob* __restrict__ jobs, int al0, double* __restrict__ scratch_all, int* __restrict__ nrej) {
+cbs_perm_prep_kernel(const double* __restrict__ yy, const double* __restrict__ w, const double* __restrict__ cw,
+                     const PermJob* __restrict__ jobs, double* __restrict__ scratch_all) {
   const PermJob job = jobs[blockIdx.y];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= job.nperm) return;
@@ -269,6 +265,7 @@ cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, con
   const double* pcw = cw + job.lo - 1;
   double* py = scratch_all + job.scratch_off + p;   // py[i * stride]
   double* sxp = py + (int64_t)n * stride;           // second plane: re-centred prefix sums, index t = 1..n at (t-1)
+  double* bestp = scratch_all + job.scratch_off + 2 * (int64_t)n * stride;
   for (int i = 0; i < n; i++) py[(int64_t)i * stride] = y[i];
   PermStream st(job.seed, 0u, job.lo_id, job.hi_id, (uint32_t)(job.perm0 + p));
   // wxperm: Fisher-Yates from the top; px[i] = py[i] / rw[i]; accumulate sum(ws * px) on the fly is
@@ -289,10 +286,43 @@ cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, con
   const double xbar = acc / job.tot_w;
   const double tss = job.tss_y - job.tot_w * xbar * xbar;
   for (int t = 1; t <= n; t++) sxp[(int64_t)(t - 1) * stride] = sxp[(int64_t)(t - 1) * stride] - xbar * (pcw[t] * job.rtw);
+  bestp[p] = -1.0;
+  bestp[stride + p] = tss;
+}
+
+// max over the arcs (i, j), j in [j0, j1], of the statistic; the division only runs for arcs that can raise `best`
+// (same filter and margin as cbs_maxarc_kernel: the result equals the maximum of the rounded quotients)
+__device__ __forceinline__ void perm_arcs(const double* __restrict__ sxp, int64_t stride, const double* __restrict__ pcw,
+                                          double sxi, double cwi, double cwn, int j0, int j1, double& best, double& thr) {
+  for (int j = j0; j <= j1; j++) {
+    const double s = sxp[(int64_t)(j - 1) * stride] - sxi;
+    const double dw = pcw[j] - cwi;
+    const double num = s * s;
+    const double den = dw * (cwn - dw);
+    if (num >= thr * den) {
+      const double bss = num / den;
+      if (bss > best) { best = bss; thr = best * (1.0 - 0x1p-50); }
+    }
+  }
+}
+
+// grid (ceil(max nperm / 128), ceil(max n / PA_ICHUNK), jobs)
+__global__ void __launch_bounds__(128)
+cbs_perm_arcs_kernel(const double* __restrict__ cw, const PermJob* __restrict__ jobs, int al0, double* __restrict__ scratch_all) {
+  const PermJob job = jobs[blockIdx.z];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = job.n;
+  const int ia = blockIdx.y * PA_ICHUNK;
+  if (p >= job.nperm || ia >= n) return;
+  const int ib = min(n, ia + PA_ICHUNK);
+  const int64_t stride = job.nperm;
+  const double* pcw = cw + job.lo - 1;
+  const double* sxp = scratch_all + job.scratch_off + (int64_t)n * stride + p;
+  double* bestp = scratch_all + job.scratch_off + 2 * (int64_t)n * stride;
   const double cwn = pcw[n];
   double best = -1.0, thr = -1.0;
   const int mw = job.max_width;
-  for (int i = 0; i < n; i++) {
+  for (int i = ia; i < ib; i++) {
     const double sxi = i == 0 ? 0.0 : sxp[(int64_t)(i - 1) * stride];
     const double cwi = i == 0 ? 0.0 : pcw[i];
     const int jlo = i + al0, jhi = min(n, i + n - al0);
@@ -306,7 +336,17 @@ cbs_perm_kernel(const double* __restrict__ yy, const double* __restrict__ w, con
       perm_arcs(sxp, stride, pcw, sxi, cwi, cwn, j2, jhi, best, thr);
     }
   }
-  const double pstat = best / ((tss - best) / ((double)n - 2.0));
+  if (best >= 0.0) atomicMax(reinterpret_cast<long long*>(bestp + p), __double_as_longlong(best));
+}
+
+__global__ void __launch_bounds__(128)
+cbs_perm_count_kernel(const PermJob* __restrict__ jobs, const double* __restrict__ scratch_all, int* __restrict__ nrej) {
+  const PermJob job = jobs[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= job.nperm) return;
+  const double* bestp = scratch_all + job.scratch_off + 2 * (int64_t)job.n * job.nperm;
+  const double best = bestp[p], tss = bestp[job.nperm + p];
+  const double pstat = best / ((tss - best) / ((double)job.n - 2.0));
   if (job.ostat <= pstat) atomicAdd(nrej + blockIdx.y, 1);
 }
 
@@ -658,7 +698,7 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
       for (size_t q = 0; q < tests.size(); q++) active[q] = (int)q;
       int stage = 0;
       while (!active.empty()) {
-        const int want = stage == 0 ? 256 : (stage == 1 ? 1024 : 2048);
+        const int want = stage == 0 ? 256 : nperm;  // a first look decides most tests; the rest run to the end
         stage++;
         // groups of tests whose scratch fits the budget
         size_t g0 = 0;
@@ -667,14 +707,14 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
           std::vector<PermJob> jobs;
           std::vector<int> jq;
           size_t doubles = 0;
-          int maxnb = 0;
+          int maxnb = 0, maxn = 0;
           size_t g1 = g0;
           for (; g1 < active.size(); g1++) {
             PermTest& t = tests[active[g1]];
             const Seg& sg = work[t.seg];
             const int n = (int)(sg.hi - sg.lo);
             const int nb = std::min(want, nperm - t.done);
-            const size_t need = 2 * (size_t)n * nb;
+            const size_t need = 2 * (size_t)n * nb + 2 * (size_t)nb;
             if (!jobs.empty() && (doubles + need) * sizeof(double) > ((size_t)3 << 30)) break;
             const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
             PermJob job;
@@ -687,18 +727,22 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
             jq.push_back(active[g1]);
             doubles += need;
             maxnb = std::max(maxnb, nb);
+            maxn = std::max(maxn, n);
           }
           const int nj = (int)jobs.size();
           if (ws->scratch.ensure(sizeof(double) * doubles) || ws->pjobs.ensure(sizeof(PermJob) * nj) || ws->nrej.ensure(sizeof(int) * nj)) return 1;
           WCX_CUDA_OK(cudaMemcpyAsync(ws->pjobs.p, jobs.data(), sizeof(PermJob) * nj, cudaMemcpyHostToDevice, st));
           WCX_CUDA_OK(cudaMemsetAsync(ws->nrej.p, 0, sizeof(int) * nj, st));
-          cbs_perm_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(),
-                                                                       ws->pjobs.as<PermJob>(), al0, ws->scratch.as<double>(), ws->nrej.as<int>());
+          cbs_perm_prep_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(),
+                                                                            ws->pjobs.as<PermJob>(), ws->scratch.as<double>());
+          cbs_perm_arcs_kernel<<<dim3((maxnb + 127) / 128, (maxn + PA_ICHUNK - 1) / PA_ICHUNK, nj), 128, 0, st>>>(
+              ws->cw.as<double>(), ws->pjobs.as<PermJob>(), al0, ws->scratch.as<double>());
+          cbs_perm_count_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->pjobs.as<PermJob>(), ws->scratch.as<double>(), ws->nrej.as<int>());
           WCX_CUDA_OK(cudaGetLastError());
           std::vector<int> h(nj);
           WCX_CUDA_OK(cudaMemcpyAsync(h.data(), ws->nrej.p, sizeof(int) * nj, cudaMemcpyDeviceToHost, st));
           WCX_CUDA_OK(cudaStreamSynchronize(st));
-          if (stats) stats->launches++;
+          if (stats) stats->launches += 3;
           for (int q = 0; q < nj; q++) {
             PermTest& t = tests[jq[q]];
             t.nrej += h[q];
@@ -713,13 +757,42 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
         active.swap(still);
       }
     }
-    // decisions, part 2: change-points of the segments that split
+    // decisions, part 2: change-points of the segments that split.  Arcs strictly inside a segment get two edge
+    // t-tests; their preparation (sequential sums, one thread per test) runs once for the whole round
+    std::vector<TJob> tj;
+    std::vector<int> tj_of(nseg, -1);
+    for (int s = 0; s < nseg; s++) {
+      if (!split_of[s]) continue;
+      const Seg& sg = work[s];
+      const int n = (int)(sg.hi - sg.lo);
+      const int i1 = best[s].i, i2 = best[s].j;
+      if (i2 == n || i1 == 0) continue;
+      const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
+      TJob jobs[2];
+      std::memset(jobs, 0, sizeof(jobs));
+      jobs[0].lo = sg.lo; jobs[0].n1 = i1; jobs[0].n2 = i2 - i1; jobs[0].test = 1;
+      jobs[1].lo = sg.lo + i1; jobs[1].n1 = i2 - i1; jobs[1].n2 = n - i2; jobs[1].test = 2;
+      for (auto& jb : jobs) {
+        jb.seed = (uint32_t)((uint64_t)seed * 1000003ull + (uint64_t)(uint32_t)sid);
+        jb.lo_id = (uint32_t)(sg.lo - off[sg.series]);
+        jb.hi_id = (uint32_t)(sg.hi - off[sg.series]);
+      }
+      tj_of[s] = (int)tj.size();
+      tj.push_back(jobs[0]);
+      tj.push_back(jobs[1]);
+    }
+    if (!tj.empty()) {
+      const int ntj = (int)tj.size();
+      if (ws->tjobs.ensure(sizeof(TJob) * ntj)) return 1;
+      WCX_CUDA_OK(cudaMemcpyAsync(ws->tjobs.p, tj.data(), sizeof(TJob) * ntj, cudaMemcpyHostToDevice, st));
+      cbs_tprep_kernel<<<(ntj + 31) / 32, 32, 0, st>>>(ws->xc.as<double>(), ws->w.as<double>(), ws->tjobs.as<TJob>(), ntj);
+      WCX_CUDA_OK(cudaMemcpyAsync(tj.data(), ws->tjobs.p, sizeof(TJob) * ntj, cudaMemcpyDeviceToHost, st));
+      WCX_CUDA_OK(cudaStreamSynchronize(st));
+      if (stats) stats->launches++;
+    }
     for (int s = 0; s < nseg; s++) {
       const Seg& sg = work[s];
       const int n = (int)(sg.hi - sg.lo);
-      const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
-      const uint32_t sseed = (uint32_t)((uint64_t)seed * 1000003ull + (uint64_t)(uint32_t)sid);
-      const uint32_t lo_id = (uint32_t)(sg.lo - off[sg.series]), hi_id = (uint32_t)(sg.hi - off[sg.series]);
       std::vector<int> cpts;
       const bool split = split_of[s] != 0;
       const int i1 = best[s].i, i2 = best[s].j;
@@ -727,29 +800,19 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
         if (i2 == n) cpts.push_back(i1);
         else if (i1 == 0) cpts.push_back(i2);
         else {
-          // two edge t-tests on the centred data of this segment
-          TJob jobs[2];
-          std::memset(jobs, 0, sizeof(jobs));
-          jobs[0].lo = sg.lo; jobs[0].n1 = i1; jobs[0].n2 = i2 - i1; jobs[0].test = 1;
-          jobs[1].lo = sg.lo + i1; jobs[1].n1 = i2 - i1; jobs[1].n2 = n - i2; jobs[1].test = 2;
-          for (auto& jb : jobs) { jb.seed = sseed; jb.lo_id = lo_id; jb.hi_id = hi_id; }
-          if (ws->tjobs.ensure(sizeof(jobs))) return 1;
-          WCX_CUDA_OK(cudaMemcpyAsync(ws->tjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, st));
-          cbs_tprep_kernel<<<1, 32, 0, st>>>(ws->xc.as<double>(), ws->w.as<double>(), ws->tjobs.as<TJob>(), 2);
-          WCX_CUDA_OK(cudaMemcpyAsync(jobs, ws->tjobs.p, sizeof(jobs), cudaMemcpyDeviceToHost, st));
-          WCX_CUDA_OK(cudaStreamSynchronize(st));
-          if (stats) stats->launches++;
           for (int q = 0; q < 2; q++) {
+            const int gq = tj_of[s] + q;
+            const TJob& jb = tj[gq];
             double pval;
-            if (jobs[q].skip == 1) pval = 1.0;
-            else if (jobs[q].skip == 2) pval = 0.0;
+            if (jb.skip == 1) pval = 1.0;
+            else if (jb.skip == 2) pval = 0.0;
             else {
-              const int nn = jobs[q].n1 + jobs[q].n2;
+              const int nn = jb.n1 + jb.n2;
               if (ws->scratch.ensure(sizeof(double) * (size_t)nn * nperm)) return 1;
-              cbs_tperm_kernel<<<(nperm + 127) / 128, 128, 0, st>>>(ws->xc.as<double>(), ws->w.as<double>(), ws->tjobs.as<TJob>(), q,
+              cbs_tperm_kernel<<<(nperm + 127) / 128, 128, 0, st>>>(ws->xc.as<double>(), ws->w.as<double>(), ws->tjobs.as<TJob>(), gq,
                                                                     nperm, ws->scratch.as<double>(), nperm);
               TJob back;
-              WCX_CUDA_OK(cudaMemcpyAsync(&back, ws->tjobs.as<TJob>() + q, sizeof(TJob), cudaMemcpyDeviceToHost, st));
+              WCX_CUDA_OK(cudaMemcpyAsync(&back, ws->tjobs.as<TJob>() + gq, sizeof(TJob), cudaMemcpyDeviceToHost, st));
               WCX_CUDA_OK(cudaStreamSynchronize(st));
               if (stats) { stats->launches++; stats->permutations += nperm; stats->t_tests++; }
               pval = (double)back.nrej / (double)nperm;
