@@ -248,8 +248,11 @@ def run_ours(args, rank, world, local_rank):
     nr_dev = torch.empty((rows, m), dtype=torch.float64, device=dev)
 
     def step_resident():
-        eng.topk(rb, re, k, kernel=args.kernel, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr()))
-        eng.null_ratios(rb, re, k, ids, device_out=nr_dev.data_ptr())
+        if args.unfused:
+            eng.topk(rb, re, k, kernel=args.kernel, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr()))
+            eng.null_ratios(rb, re, k, ids, device_out=nr_dev.data_ptr())
+        else:  # one C-ABI call: sweep, then re-rank with the null ratios fused into it
+            eng.reference(rb, re, k, ids, kernel=args.kernel, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr(), nr_dev.data_ptr()))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -333,8 +336,7 @@ def run_ours(args, rank, world, local_rank):
                 xd.copy_(x_pin, non_blocking=True)
             dist.broadcast(xd, 0)
             eng.load(None, per, cum, on_device_ptr=xd.data_ptr(), shape=(n, s))
-            eng.topk(rb, re, k, device_out=(pads[0].data_ptr(), pads[1].data_ptr()))
-            eng.null_ratios(rb, re, k, ids, device_out=pads[2].data_ptr())
+            eng.reference(rb, re, k, ids, device_out=(pads[0].data_ptr(), pads[1].data_ptr(), pads[2].data_ptr()))
             for i, p in enumerate(pads):
                 dist.gather(p, bufs[i] if rank == 0 else None, 0)
             if rank == 0:
@@ -378,7 +380,10 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOADS[args.workload][2], "refsize": k, "null_samples": m,
                    "bins": int(n), "samples": int(s), "pairs_per_step": int(pairs_total),
                    "l2": "inputs (X fp64 %.0f MB + operands) larger than the 126 MB L2" % (x.nbytes / 1e6),
-                   "parallelism": f"target-bin parts x{world}"},
+                   "parallelism": f"target-bin parts x{world}",
+                   "null_ratios": "separate call after the top-k" if args.unfused else
+                                  "row blocks on a side stream next to the re-rank of the following block "
+                                  "(stages_ms.null_ratios = what they add after the last re-rank block)"},
         "e2e": {"value": e2e_value, "unit": "bin-pair dist/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
@@ -410,6 +415,7 @@ def main():
     ap.add_argument("--no-predict", action="store_true", help="skip the predict (configs 4 / 5) timings")
     ap.add_argument("--kernel", type=int, default=0, help="sweep kernel (include/wcx_b200.h WCX_KERNEL_*), 0 = default")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--unfused", action="store_true", help="separate topk and null-ratio calls (stage timings of the null kernel)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -72,7 +72,16 @@ int wcx_newref_null_ratios(wcx_ctx* ctx, const int32_t* idx, int32_t idx_on_devi
                            int64_t row_end, int32_t k, const int32_t* sample_ids, int32_t m,
                            double* out, int32_t out_on_device);
 
-/* One-call host-to-host form of get_reference: load + topk + null ratios. */
+/* Top-k and null ratios of rows [row_begin, row_end) in one pass over the loaded matrix -- the body of
+ * get_reference (newref_tools.py:176-224) after the matrix is resident.  The null ratios of a row are computed by
+ * the same CTA that finalises its indexes (fused into the re-rank kernel) when ref_size <= 320; with host outputs
+ * the rows are processed in blocks and the D2H copy of a finished block overlaps the next one.  m == 0 skips the
+ * null ratios.  Outputs as wcx_newref_topk / wcx_newref_null_ratios. */
+int wcx_newref_reference(wcx_ctx* ctx, int64_t row_begin, int64_t row_end, int32_t k, int32_t kernel,
+                         const int32_t* sample_ids, int32_t m, int32_t* idx_out, double* dist_out,
+                         double* null_out, int32_t out_on_device);
+
+/* One-call host-to-host form of get_reference: wcx_newref_load + wcx_newref_reference. */
 int wcx_get_reference(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, const int64_t* per,
                       const int64_t* cum, int32_t c, int32_t k, int64_t row_begin, int64_t row_end,
                       const int32_t* sample_ids, int32_t m, int32_t kernel, int32_t* idx_out,

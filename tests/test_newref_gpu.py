@@ -281,3 +281,56 @@ def test_many_samples_both_gather_paths(eng, samples):
     assert np.array_equal(idx, oi)
     assert np.array_equal(dist, od)
     assert eng.stats()["exact_fallback_rows"] <= n // 20
+
+
+def test_fused_reference_equals_separate_calls(eng):
+    """wcx_newref_reference (null ratios fused into the re-rank kernel, rows in blocks) against topk + null_ratios
+    and the C oracle; host and device-resident outputs; part ranges crossing chromosome borders."""
+    import torch
+    per = synth.config_bins(2)
+    x, per, cum = synth.make_corrected_matrix(per, 100, seed=51)
+    n = x.shape[0]
+    eng.load(x, per, cum)
+    ids = list(range(3, 100, 2)) + [0, 98]                    # 51 columns: a ragged last chunk of 3
+    for s, e in ((0, 9000), (int(cum[2]) - 700, int(cum[2]) + 8000), (n - 300, n)):
+        idx, dist, nr = eng.reference(s, e, 300, ids)
+        oi, od = c_oracle.topk(x, per, cum, 300, s, e)
+        onr = c_oracle.null_ratios(x, oi, s, e, ids)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+        np.testing.assert_allclose(nr, onr, rtol=1e-12, atol=1e-14)
+        i2, d2 = eng.topk(s, e, 300)
+        n2 = eng.null_ratios(s, e, 300, ids)
+        assert np.array_equal(idx, i2) and np.array_equal(dist, d2) and np.array_equal(nr, n2, equal_nan=True)
+    # device-resident outputs
+    s, e = 100, 4100
+    ti = torch.empty((e - s, 300), dtype=torch.int32, device="cuda:0")
+    td = torch.empty((e - s, 300), dtype=torch.float64, device="cuda:0")
+    tn = torch.empty((e - s, len(ids)), dtype=torch.float64, device="cuda:0")
+    eng.reference(s, e, 300, ids, device_out=(ti.data_ptr(), td.data_ptr(), tn.data_ptr()))
+    eng.ctx.sync()
+    idx, dist, nr = eng.reference(s, e, 300, ids)
+    assert np.array_equal(ti.cpu().numpy(), idx) and np.array_equal(td.cpu().numpy(), dist)
+    assert np.array_equal(tn.cpu().numpy(), nr, equal_nan=True)
+
+
+def test_fused_reference_edge_cases(eng, gref):
+    """Fewer candidates than ref_size (-1 fillers wrap to the last bin), NaN rows, gonosomal placeholder rows,
+    large ref_size (unfused fall-back) -- against the oracle / golden vectors of the live reference."""
+    per = np.array([40, 30, 20, 10] + [0] * 18)
+    x, per, cum = synth.make_corrected_matrix(per, 9, seed=21)
+    x[5, 3] = np.nan
+    n = x.shape[0]
+    ids = [0, 3, 8, 5]
+    eng.load(x, per, cum)
+    for k in (64, 350):
+        idx, dist, nr = eng.reference(0, n, k, ids)
+        oi, od = c_oracle.topk(x, per, cum, k, 0, n)
+        onr = c_oracle.null_ratios(x, oi, 0, n, ids)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), k
+        np.testing.assert_allclose(nr, onr, rtol=1e-12, atol=1e-14, equal_nan=True)
+    # gonosomal reference of the golden file: autosomal rows are placeholders (idx 0, dist 1.0)
+    gx, gper, gcum = gref["G_x"], gref["G_per"], gref["G_cum"]
+    eng.load(gx, gper, gcum)
+    idx, dist, nr = eng.reference(0, gx.shape[0], 30, gref["G_ids"].tolist())
+    assert np.array_equal(idx, gref["G_idx"]) and np.array_equal(dist, gref["G_dist"])
+    np.testing.assert_allclose(nr, gref["G_nr"], rtol=1e-12, atol=1e-14, equal_nan=True)

@@ -45,6 +45,7 @@ def load():
     L.wcx_newref_load.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32]
     L.wcx_newref_topk.argtypes = [vp, i64, i64, i32, i32, vp, vp, i32]
     L.wcx_newref_null_ratios.argtypes = [vp, vp, i32, i64, i64, i32, vp, i32, vp, i32]
+    L.wcx_newref_reference.argtypes = [vp, i64, i64, i32, i32, vp, i32, vp, vp, vp, i32]
     L.wcx_get_reference.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32, i64, i64, vp, i32, i32, vp, vp, vp]
     L.wcx_newref_stats.argtypes = [vp, vp]
     L.wcx_newref_stage_ms.argtypes = [vp, vp]

@@ -61,7 +61,11 @@ struct wcx_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished outputs overlapped with the next stage
+  cudaStream_t null_stream = nullptr;  // high priority: null ratios of finished row blocks next to the re-rank of the next
   cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_blk[16] = {};         // per row block: re-rank done / null ratios done
+  cudaEvent_t ev_null[16] = {};
+  cudaEvent_t ev_tail[2] = {};         // timing of the exposed null-ratio tail
   cudaEvent_t ev[8] = {};
   // newref state
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
@@ -155,6 +159,14 @@ int wcx_create(int32_t device, wcx_ctx** out) {
   c->stream = c->own_stream;
   WCX_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   WCX_CUDA_OK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0;
+    WCX_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    WCX_CUDA_OK(cudaStreamCreateWithPriority(&c->null_stream, cudaStreamNonBlocking, hi));
+  }
+  for (auto& e : c->ev_blk) WCX_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : c->ev_null) WCX_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : c->ev_tail) WCX_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : c->ev) WCX_CUDA_OK(cudaEventCreate(&e));
   *out = c;
   return 0;
@@ -178,6 +190,10 @@ void wcx_destroy(wcx_ctx* c) {
   if (c->cbs) cbs_workspace_destroy(c->cbs);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_blk) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_null) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_tail) if (e) cudaEventDestroy(e);
+  if (c->null_stream) cudaStreamDestroy(c->null_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -312,8 +328,18 @@ static void build_items(const wcx_ctx* c, int64_t rb, int64_t re, int tile_n, in
   }
 }
 
-int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kernel, int32_t* idx_out,
-                    double* dist_out, int32_t out_on_device) {
+}  // extern "C"
+
+// null ratios requested together with the top-k (wcx_newref_reference): computed inside the re-rank kernel when
+// the shape allows it, otherwise by the stand-alone kernels after it
+struct NullPlan {
+  const int32_t* sample_ids;
+  int32_t m;
+  double* out;
+};
+
+static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kernel, int32_t* idx_out, double* dist_out,
+                     int32_t out_on_device, const NullPlan* np) {
   if (!c || !c->loaded) { set_error("wcx_newref_topk: call wcx_newref_load first"); return 1; }
   if (rb < 0 || re > c->n || rb > re) { set_error("wcx_newref_topk: bad row range"); return 1; }
   if (k <= 0 || k > 400) { set_error("wcx_newref_topk: ref_size must be in [1, 400]"); return 1; }
@@ -334,6 +360,24 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
   PrepView pv = f16 ? prep_view_h(c) : prep_view(c);
   void* tmap = f16 ? c->tmap_h : c->tmap;
   std::vector<int32_t> fail_list;
+  // null plan: gather the chosen sample columns first (needs only X), decide whether the re-rank kernel can fuse
+  double* d_null = nullptr;
+  bool fused = false;
+  c->stage_ms[3] = 0.0;
+  if (np && np->m > 0) {
+    for (int i = 0; i < np->m; i++)
+      if (np->sample_ids[i] < 0 || np->sample_ids[i] >= c->s) { set_error("wcx_newref_reference: sample id out of range"); return 1; }
+    if (c->xt.ensure(sizeof(double) * (size_t)null_ratio_staging_doubles(c->n, np->m)) || c->ids_dev.ensure(sizeof(int32_t) * np->m)) return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(c->ids_dev.p, np->sample_ids, sizeof(int32_t) * np->m, cudaMemcpyHostToDevice, st));
+    if (launch_transpose_cols(c->d_x, c->n, c->s, c->ids_dev.as<int32_t>(), np->m, c->xt.as<double>(), st)) return 1;
+    c->launches += 1;
+    d_null = np->out;
+    if (!out_on_device) {
+      if (c->nr_dev.ensure(sizeof(double) * (size_t)rows * np->m)) return 1;
+      d_null = c->nr_dev.as<double>();
+    }
+    fused = kernel != WCX_KERNEL_EXACT && rerank_can_fuse_nulls(c->leaf_n, k);
+  }
 
   if (kernel == WCX_KERNEL_EXACT) {
     // every real row through the brute-force path; placeholder rows via the rerank kernel's early exit
@@ -402,20 +446,50 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
       if (launch_dist_topk_tc(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), tmap, st)) return 1;
     }
     WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
-    // The bulk-copy re-rank (rerank_bulk.cu) is an opt-in experiment (WCX_RERANK_BULK=warps,stages): at config 3 it
-    // measured 82 ms against 50 ms for the LDG kernel (profiles/r01c_ncu_rerank_bulk.txt).
-    static const bool use_bulk = std::getenv("WCX_RERANK_BULK") != nullptr;
-    int rt = 1;
-    if (use_bulk)
-      rt = launch_rerank_bulk(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
-                              c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->leaves_dev.as<int32_t>(), c->plan_leaves,
-                              c->plan_depth, st);
-    if (rt < 0) return 1;
-    if (rt == 1 &&
-        launch_rerank(c->d_x, pv, cv, nsplit * lps, c->cum_dev.as<int64_t>(), c->nchr, rb, re, k, gon, c->idx_dev.as<int32_t>(),
-                      c->dist_dev.as<double>(), c->fail.as<int32_t>(), c->plan_dev.as<int32_t>(), c->plan_len,
-                      c->leaf_n ? c->xp.as<double>() : nullptr, c->sp, c->leafdesc_dev.as<int32_t>(), c->leaf_n, st))
-      return 1;
+    {
+      // The rows go through the re-rank in a few blocks.  The null ratios of a finished block run on a second,
+      // high-priority stream next to the re-rank of the following block (the re-rank waits on gathers at ~50 %
+      // issue utilisation, the median selection is issue bound), and with host outputs the D2H copy of a finished
+      // block (copy stream) overlaps the kernels of the next one.
+      const int nlists = nsplit * lps;
+      static const bool serial_nulls = std::getenv("WCX_SERIAL_NULLS") != nullptr;
+      const bool side = d_null && !fused && !serial_nulls;   // null ratios on the side stream
+      const int nblk = rows >= 8192 ? 8 : 1;
+      for (int bq = 0; bq < nblk; bq++) {
+        const int64_t r0 = rows * bq / nblk, r1 = rows * (bq + 1) / nblk;
+        if (r1 <= r0) continue;
+        CandView cvb{cv.ent + (size_t)r0 * nlists * WCX_CAND_CAP, cv.cnt + r0 * nlists, cv.cut + r0 * nlists, cv.diag};
+        if (launch_rerank(c->d_x, pv, cvb, nlists, c->cum_dev.as<int64_t>(), c->nchr, rb + r0, rb + r1, k, gon,
+                          c->idx_dev.as<int32_t>() + r0 * k, c->dist_dev.as<double>() + r0 * k, c->fail.as<int32_t>() + r0,
+                          c->plan_dev.as<int32_t>(), c->plan_len, c->leaf_n ? c->xp.as<double>() : nullptr, c->sp,
+                          c->leafdesc_dev.as<int32_t>(), c->leaf_n, fused ? c->xt.as<double>() : nullptr, fused ? np->m : 0,
+                          fused ? d_null + r0 * np->m : nullptr, st))
+          return 1;
+        c->launches += bq ? 1 : 0;
+        WCX_CUDA_OK(cudaEventRecord(c->ev_blk[bq], st));
+        cudaEvent_t ready = c->ev_blk[bq];
+        if (d_null && !fused) {
+          cudaStream_t ns = side ? c->null_stream : st;
+          if (side) WCX_CUDA_OK(cudaStreamWaitEvent(ns, c->ev_blk[bq], 0));
+          if (launch_null_ratios(c->xt.as<double>(), c->n, c->idx_dev.as<int32_t>() + r0 * k, rb + r0, rb + r1, k, np->m,
+                                 d_null + r0 * np->m, ns))
+            return 1;
+          c->launches += (np->m + 7) / 8;
+          WCX_CUDA_OK(cudaEventRecord(c->ev_null[bq], ns));
+          ready = c->ev_null[bq];
+        }
+        if (!out_on_device) {
+          WCX_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+          if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out + r0 * k, c->idx_dev.as<int32_t>() + r0 * k, sizeof(int32_t) * (size_t)(r1 - r0) * k, cudaMemcpyDeviceToHost, c->copy_stream));
+          if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out + r0 * k, c->dist_dev.as<double>() + r0 * k, sizeof(double) * (size_t)(r1 - r0) * k, cudaMemcpyDeviceToHost, c->copy_stream));
+          if (d_null) WCX_CUDA_OK(cudaMemcpyAsync(np->out + r0 * np->m, d_null + r0 * np->m, sizeof(double) * (size_t)(r1 - r0) * np->m, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+      }
+      // the caller's stream owns the results again once the side stream has drained
+      WCX_CUDA_OK(cudaEventRecord(c->ev_tail[0], st));
+      if (side) WCX_CUDA_OK(cudaStreamWaitEvent(st, c->ev_null[nblk - 1], 0));
+      WCX_CUDA_OK(cudaEventRecord(c->ev_tail[1], st));
+    }
     WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
     c->launches += 2;
     std::vector<int32_t> flags((size_t)rows);
@@ -432,7 +506,7 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stage_ms[0] = ms;
-    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev_tail[0]);
     c->stage_ms[1] = ms;
     c->stats[0] = (int64_t)items.size();
     c->stats[3] = nsplit;
@@ -463,15 +537,74 @@ int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kerne
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
     c->stage_ms[2] = ms;
   }
+  if (d_null) {
+    WCX_CUDA_OK(cudaEventRecord(c->ev[5], st));
+    if (kernel != WCX_KERNEL_EXACT) {
+      // rows the fast path did not certify got their indexes from exact_rows: their null ratios follow here
+      for (int32_t i : fail_list) {
+        if (launch_null_ratios(c->xt.as<double>(), c->n, c->idx_dev.as<int32_t>() + (size_t)i * k, rb + i, rb + i + 1, k, np->m,
+                               d_null + (size_t)i * np->m, st))
+          return 1;
+        c->launches += (np->m + 7) / 8;
+      }
+    } else {
+      if (launch_null_ratios(c->xt.as<double>(), c->n, c->idx_dev.as<int32_t>(), rb, re, k, np->m, d_null, st)) return 1;
+      c->launches += (np->m + 7) / 8;
+    }
+    WCX_CUDA_OK(cudaEventRecord(c->ev[6], st));
+  }
   c->stats[2] = c->launches;
   c->last_rb = rb;
   c->last_re = re;
   c->last_k = k;
-  const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out, c->idx_dev.p, sizeof(int32_t) * (size_t)rows * k, kind, st));
-  if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out, c->dist_dev.p, sizeof(double) * (size_t)rows * k, kind, st));
-  if (!out_on_device) WCX_CUDA_OK(cudaStreamSynchronize(st));
+  if (out_on_device) {
+    if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out, c->idx_dev.p, sizeof(int32_t) * (size_t)rows * k, cudaMemcpyDeviceToDevice, st));
+    if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out, c->dist_dev.p, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToDevice, st));
+  } else {
+    const bool chunked = kernel != WCX_KERNEL_EXACT;  // the re-rank loop above already copied the certified rows
+    if (!chunked) {
+      if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out, c->idx_dev.p, sizeof(int32_t) * (size_t)rows * k, cudaMemcpyDeviceToHost, st));
+      if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out, c->dist_dev.p, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, st));
+    } else {
+      WCX_CUDA_OK(cudaStreamSynchronize(c->copy_stream));  // the block copies must land before the patches below
+      for (int32_t i : fail_list) {
+        if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out + (size_t)i * k, c->idx_dev.as<int32_t>() + (size_t)i * k, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, st));
+        if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out + (size_t)i * k, c->dist_dev.as<double>() + (size_t)i * k, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    if (d_null) {
+      if (chunked) {
+        for (int32_t i : fail_list)
+          WCX_CUDA_OK(cudaMemcpyAsync(np->out + (size_t)i * np->m, d_null + (size_t)i * np->m, sizeof(double) * np->m, cudaMemcpyDeviceToHost, st));
+      } else {
+        WCX_CUDA_OK(cudaMemcpyAsync(np->out, d_null, sizeof(double) * (size_t)rows * np->m, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    WCX_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  if (d_null) {
+    if (out_on_device) WCX_CUDA_OK(cudaStreamSynchronize(st));
+    // what the null ratios add after the last re-rank block (they overlap the re-rank otherwise) + the failed rows
+    float ms = 0.f, ms2 = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]);
+    if (kernel != WCX_KERNEL_EXACT) cudaEventElapsedTime(&ms2, c->ev_tail[0], c->ev_tail[1]);
+    c->stage_ms[3] = ms + ms2;
+  }
   return 0;
+}
+
+extern "C" {
+
+int wcx_newref_topk(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kernel, int32_t* idx_out,
+                    double* dist_out, int32_t out_on_device) {
+  return topk_impl(c, rb, re, k, kernel, idx_out, dist_out, out_on_device, nullptr);
+}
+
+int wcx_newref_reference(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kernel, const int32_t* sample_ids, int32_t m,
+                         int32_t* idx_out, double* dist_out, double* null_out, int32_t out_on_device) {
+  if (m < 0 || (m > 0 && (!sample_ids || !null_out))) { set_error("wcx_newref_reference: bad argument"); return 1; }
+  NullPlan np{sample_ids, m, null_out};
+  return topk_impl(c, rb, re, k, kernel, idx_out, dist_out, out_on_device, m > 0 ? &np : nullptr);
 }
 
 int wcx_newref_null_ratios(wcx_ctx* c, const int32_t* idx, int32_t idx_on_device, int64_t rb, int64_t re, int32_t k,
@@ -523,20 +656,8 @@ int wcx_get_reference(wcx_ctx* c, const double* x, int64_t n, int32_t s, const i
                       int32_t k, int64_t rb, int64_t re, const int32_t* sample_ids, int32_t m, int32_t kernel,
                       int32_t* idx_out, double* dist_out, double* null_out) {
   if (wcx_newref_load(c, x, n, s, per, cum, nchr, 0)) return 1;
-  // indexes / distances stay on the device; their D2H copy runs on the copy stream while the null-ratio
-  // kernels run on the main stream
-  if (wcx_newref_topk(c, rb, re, k, kernel, nullptr, nullptr, 1)) return 1;
-  const int64_t rows = re - rb;
-  if (rows > 0) {
-    WCX_CUDA_OK(cudaEventRecord(c->ev_copy, c->stream));
-    WCX_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
-    if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out, c->idx_dev.p, sizeof(int32_t) * (size_t)rows * k, cudaMemcpyDeviceToHost, c->copy_stream));
-    if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out, c->dist_dev.p, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, c->copy_stream));
-  }
-  int rc = 0;
-  if (null_out && m > 0) rc = wcx_newref_null_ratios(c, nullptr, 1, rb, re, k, sample_ids, m, null_out, 0);
-  WCX_CUDA_OK(cudaStreamSynchronize(c->copy_stream));
-  return rc;
+  // one pass: sweep, then re-rank + null ratios block by block with the D2H copies of finished blocks overlapped
+  return wcx_newref_reference(c, rb, re, k, kernel, sample_ids, null_out ? m : 0, idx_out, dist_out, null_out, 0);
 }
 
 int wcx_newref_stats(wcx_ctx* c, int64_t* out8) {

@@ -290,6 +290,77 @@ cbs_perm_prep_kernel(const double* __restrict__ yy, const double* __restrict__ w
   bestp[stride + p] = tss;
 }
 
+// Same result as cbs_perm_prep_kernel with the Fisher-Yates shuffle in shared memory: one warp per permutation, the
+// shuffle runs on a uint16 index array (n <= 65535) -- the lanes draw the 32 Philox numbers of a batch in parallel
+// (the stream position of step i is n - 1 - i whatever the order they are computed in), lane 0 applies the 32
+// swaps in order -- then px[i] = y[a[i]] / sqrt(w[i]) and the prefix sums in sequence (a warp-wide chain of
+// additions, every lane keeping the sum of its own position).  The global-memory version above spends ~3 us per
+// element in dependent random accesses (36-61 ms per launch at n = 12 k, profiles/r01h_launches_*).
+__global__ void __launch_bounds__(256)
+cbs_perm_fy_kernel(const double* __restrict__ yy, const double* __restrict__ w, const double* __restrict__ cw,
+                   const PermJob* __restrict__ jobs, double* __restrict__ scratch_all, int warps, int n_stride) {
+  extern __shared__ uint16_t fy_smem[];
+  const PermJob job = jobs[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * warps + warp;
+  if (warp >= warps || p >= job.nperm) return;  // warps are independent: no block-wide barrier below
+  const int n = job.n;
+  const int64_t stride = job.nperm;
+  const double* y = yy + job.lo;
+  const double* ws = w + job.lo;
+  const double* pcw = cw + job.lo - 1;
+  double* sxp = scratch_all + job.scratch_off + (int64_t)n * stride + p;  // prefix-sum plane, index t = 1..n at (t-1)
+  double* bestp = scratch_all + job.scratch_off + 2 * (int64_t)n * stride;
+  uint16_t* a = fy_smem + (size_t)warp * n_stride;
+  for (int i = lane; i < n; i += 32) a[i] = (uint16_t)i;
+  __syncwarp();
+  for (int ib = n - 1; ib >= 0; ib -= 32) {
+    const int i = ib - lane;
+    uint32_t j = 0;
+    if (i >= 0) {
+      const uint32_t t = (uint32_t)(n - 1 - i);
+      uint32_t buf[4];
+      philox4x32(t >> 2, (uint32_t)(job.perm0 + p), job.lo_id, job.hi_id, job.seed, 0u, buf);
+      j = (uint32_t)(((uint64_t)buf[t & 3] * (uint32_t)(i + 1)) >> 32);
+    }
+    const int cnt = min(32, ib + 1);
+    for (int q = 0; q < cnt; q++) {
+      const uint32_t jq = __shfl_sync(0xffffffffu, j, q);
+      if (lane == 0) {
+        const int iq = ib - q;
+        const uint16_t ti = a[iq], tj = a[jq];
+        a[jq] = ti;
+        a[iq] = tj;
+      }
+    }
+    __syncwarp();
+  }
+  double acc = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    double wpx = 0.0;
+    if (i < n) {
+      const double wsi = ws[i];
+      const double px = y[a[i]] / sqrt(wsi);
+      wpx = wsi * px;
+    }
+    double mine = 0.0;
+    const int cnt = min(32, n - i0);
+    for (int q = 0; q < cnt; q++) {
+      acc = acc + __shfl_sync(0xffffffffu, wpx, q);
+      if (lane == q) mine = acc;
+    }
+    if (i < n) sxp[(int64_t)i * stride] = mine;
+  }
+  const double xbar = acc / job.tot_w;
+  const double tss = job.tss_y - job.tot_w * xbar * xbar;
+  for (int t = 1 + lane; t <= n; t += 32) sxp[(int64_t)(t - 1) * stride] = sxp[(int64_t)(t - 1) * stride] - xbar * (pcw[t] * job.rtw);
+  if (lane == 0) {
+    bestp[p] = -1.0;
+    bestp[stride + p] = tss;
+  }
+}
+
 // max over the arcs (i, j), j in [j0, j1], of the statistic; the division only runs for arcs that can raise `best`
 // (same filter and margin as cbs_maxarc_kernel: the result equals the maximum of the rounded quotients)
 __device__ __forceinline__ void perm_arcs(const double* __restrict__ sxp, int64_t stride, const double* __restrict__ pcw,
@@ -596,20 +667,16 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
     cbs_prepare_kernel<<<(nseg + 63) / 64, 64, 0, st>>>(ws->y.as<double>(), ws->w.as<double>(), ws->segs.as<Seg>(), nseg,
                                                        ws->xc.as<double>(), ws->sx.as<double>(), ws->cw.as<double>(),
                                                        ws->yy.as<double>(), ws->prep.as<SegPrep>());
-    // balanced chunks of start positions
+    // balanced chunks of start positions: start i owns arcs(i) = min(n, i + n - al0) - (i + al0) + 1 end positions,
+    // non-increasing in i, so a chunk of width CHUNK_ARCS / arcs(i0) never exceeds the budget
     std::vector<Chunk> chunks;
     for (int s = 0; s < nseg; s++) {
       const int n = (int)(work[s].hi - work[s].lo);
-      int i0 = 0;
-      int64_t acc = 0;
-      for (int i = 0; i < n; i++) {
-        const int jlo = i + al0, jhi = std::min(n, i + n - al0);
-        acc += jhi >= jlo ? (jhi - jlo + 1) : 0;
-        if (acc >= CHUNK_ARCS || i == n - 1) {
-          chunks.push_back(Chunk{s, i0, i + 1, 0});
-          i0 = i + 1;
-          acc = 0;
-        }
+      for (int i0 = 0; i0 < n;) {
+        const int64_t a0 = std::max<int64_t>(1, (int64_t)std::min(n, i0 + n - al0) - (i0 + al0) + 1);
+        const int wdt = (int)std::max<int64_t>(1, std::min<int64_t>(n - i0, CHUNK_ARCS / a0));
+        chunks.push_back(Chunk{s, i0, i0 + wdt, 0});
+        i0 += wdt;
       }
     }
     const int nchunks = (int)chunks.size();
@@ -733,8 +800,22 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
           if (ws->scratch.ensure(sizeof(double) * doubles) || ws->pjobs.ensure(sizeof(PermJob) * nj) || ws->nrej.ensure(sizeof(int) * nj)) return 1;
           WCX_CUDA_OK(cudaMemcpyAsync(ws->pjobs.p, jobs.data(), sizeof(PermJob) * nj, cudaMemcpyHostToDevice, st));
           WCX_CUDA_OK(cudaMemsetAsync(ws->nrej.p, 0, sizeof(int) * nj, st));
-          cbs_perm_prep_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(),
-                                                                            ws->pjobs.as<PermJob>(), ws->scratch.as<double>());
+          // shuffle in shared memory (one warp per permutation) when the index array fits, else in global memory
+          const int n_stride = (maxn + 7) & ~7;
+          const int fy_warps = maxn <= 65535 ? std::min(8, (200 * 1024) / (2 * n_stride)) : 0;
+          if (fy_warps >= 1) {
+            const int fy_smem = fy_warps * n_stride * 2;
+            static int fy_attr = 0;
+            if (fy_smem > fy_attr) {
+              WCX_CUDA_OK(cudaFuncSetAttribute(cbs_perm_fy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+              fy_attr = 200 * 1024;
+            }
+            cbs_perm_fy_kernel<<<dim3((maxnb + fy_warps - 1) / fy_warps, nj), 256, fy_smem, st>>>(
+                ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(), ws->pjobs.as<PermJob>(), ws->scratch.as<double>(), fy_warps, n_stride);
+          } else {
+            cbs_perm_prep_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->yy.as<double>(), ws->w.as<double>(), ws->cw.as<double>(),
+                                                                              ws->pjobs.as<PermJob>(), ws->scratch.as<double>());
+          }
           cbs_perm_arcs_kernel<<<dim3((maxnb + 127) / 128, (maxn + PA_ICHUNK - 1) / PA_ICHUNK, nj), 128, 0, st>>>(
               ws->cw.as<double>(), ws->pjobs.as<PermJob>(), al0, ws->scratch.as<double>());
           cbs_perm_count_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->pjobs.as<PermJob>(), ws->scratch.as<double>(), ws->nrej.as<int>());

@@ -13,13 +13,12 @@
 // pair of samples the warp gathers k double2 values and selects the two middle order statistics
 // of each with a bisection over order-preserving 64-bit keys (select.cuh) -- no sort.
 // np.median returns NaN when any value is NaN.
-#include "select.cuh"
+#include "null_ratios.cuh"
 #include "wcx_common.cuh"
 
 namespace wcx {
 
 namespace {
-constexpr int NR_CHUNK = 8;
 
 // xm: [n][8] sample values of this chunk; idx: [rows, k]; out: [rows, m_total] at columns m_off..
 template <int R>
@@ -40,36 +39,7 @@ null_ratios_kernel(const double* __restrict__ xm, int64_t n, const int32_t* __re
     }
     g[r] = (int32_t)v;
   }
-  const int64_t b = row_begin + lrow;
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  double mymed = nan;  // lane j keeps the median of column j of the chunk
-  for (int mp = 0; mp < mc; mp += 2) {
-    uint64_t key0[R], key1[R];
-    bool nan0 = false, nan1 = false;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      if (g[r] >= 0) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(xm + (int64_t)g[r] * NR_CHUNK + mp));
-        nan0 |= (v.x != v.x);
-        nan1 |= (v.y != v.y);
-        key0[r] = dkey(v.x);
-        key1[r] = dkey(v.y);
-      } else {
-        key0[r] = ~0ull;
-        key1[r] = ~0ull;
-      }
-    }
-    nan0 = __any_sync(0xffffffffu, nan0);
-    nan1 = __any_sync(0xffffffffu, nan1);
-    const double med0 = (nan0 || k == 0) ? nan : warp_median<R>(key0, k);
-    if (lane == mp) mymed = med0;
-    if (mp + 1 < mc) {
-      const double med1 = (nan1 || k == 0) ? nan : warp_median<R>(key1, k);
-      if (lane == mp + 1) mymed = med1;
-    }
-  }
-  // one division + log2 per column, all columns of the chunk at once (lane j = column j), coalesced store
-  if (lane < mc) out[lrow * m_total + m_off + lane] = log2(__ldg(xm + b * NR_CHUNK + lane) / mymed);
+  null_row_chunk<R>(xm, g, k, mc, row_begin + lrow, lane, out + lrow * m_total + m_off);
 }
 
 // XM[c][r][j] = X[r, ids[8c + j]] (zero padded past m); tile 32 rows per block, threads over (row, j)

@@ -83,14 +83,13 @@ int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host);  // eleme
 int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
-                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves, cudaStream_t st);
+                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves,
+                  const double* null_xm, int32_t null_m, double* null_out, cudaStream_t st);
+// true when launch_rerank can compute the null ratios in the same kernel for this shape (leaf-major gather, k <= 320)
+bool rerank_can_fuse_nulls(int32_t nleaves, int32_t k);
 // leaf-major copy of X for the re-rank gather (rerank.cu): layout from the summation plan, then the copy itself
 int build_leaf_layout(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& perm, std::vector<int32_t>& desc);
 int launch_permute_rows(const double* x, int64_t n, int32_t s, const int32_t* perm_dev, int32_t sp, double* xp, cudaStream_t st);
-// returns 0 = launched, 1 = shape not supported (use launch_rerank), -1 = error
-int launch_rerank_bulk(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev, int32_t nchr,
-                       int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal, int32_t* idx_out, double* dist_out,
-                       int32_t* fail_flags, const int32_t* leaves_dev, int32_t nleaves, int32_t max_depth, cudaStream_t st);
 int launch_exact_rows(const double* x, int64_t n, int32_t s, const int64_t* cum_dev, int32_t nchr,
                       int64_t row_begin, const int32_t* fail_rows, int32_t nfail, int32_t k,
                       int32_t* idx_out, double* dist_out, double* scratch, const int32_t* sum_plan,
@@ -101,7 +100,7 @@ int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t 
 
 // NumPy pairwise-summation plan for a reduction of length s (see rerank.cu)
 int build_sum_plan(int32_t s, int32_t* plan, int32_t cap);
-// (offset, length, #adds) per leaf of the plan + maximum stack depth (rerank_bulk.cu)
+// (offset, length, #adds) per leaf of the plan + maximum stack depth (rerank.cu)
 int plan_to_leaves(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& leaves, int32_t* max_depth);
 
 }  // namespace wcx

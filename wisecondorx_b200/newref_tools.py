@@ -81,6 +81,25 @@ class NewrefEngine:
                                             len(ids), _ptr(out), 0))
         return out
 
+    def reference(self, row_begin, row_end, ref_size, sample_ids, kernel=_lib.KERNEL_AUTO, out=None, device_out=None):
+        """Top-k and null ratios of the loaded matrix in one pass (wcx_newref_reference; the null ratios are fused
+        into the re-rank kernel).  device_out = (idx_ptr, dist_ptr, null_ptr) leaves the results in HBM."""
+        L = _lib.load()
+        ids = np.ascontiguousarray(sample_ids, dtype=np.int32)
+        rows = row_end - row_begin
+        if device_out is not None:
+            ip, dp, npt = device_out
+            _lib.check(L.wcx_newref_reference(self.ctx.handle, row_begin, row_end, ref_size, kernel, _ptr(ids), len(ids),
+                                              ctypes.c_void_p(ip), ctypes.c_void_p(dp), ctypes.c_void_p(npt), 1))
+            return None
+        if out is None:
+            out = (np.empty((rows, ref_size), dtype=np.int32), np.empty((rows, ref_size), dtype=np.float64),
+                   np.empty((rows, len(ids)), dtype=np.float64))
+        idx, dist, nr = out
+        _lib.check(L.wcx_newref_reference(self.ctx.handle, row_begin, row_end, ref_size, kernel, _ptr(ids), len(ids),
+                                          _ptr(idx), _ptr(dist), _ptr(nr), 0))
+        return idx, dist, nr
+
     def get_reference_host(self, x, per, cum, row_begin, row_end, ref_size, sample_ids, kernel=_lib.KERNEL_AUTO, out=None):
         """One C-ABI call (wcx_get_reference): host X in, host (indexes, distances, null ratios) out; the
         D2H copy of indexes / distances overlaps the null-ratio kernels."""
