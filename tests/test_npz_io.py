@@ -1,0 +1,46 @@
+"""The parallel .npz writer / loader (wisecondorx_b200/npz_io.py) against NumPy's own reader and writer:
+same keys, dtypes, shapes and values; a valid zip archive; multi-block deflate streams; chained CRC-32."""
+import zipfile
+import zlib
+
+import numpy as np
+
+from wisecondorx_b200 import npz_io
+
+
+def test_crc32_combine_matches_zlib():
+    rng = np.random.default_rng(0)
+    for la, lb in [(0, 5), (7, 0), (1, 1), (1000, 12345), (65536, 3)]:
+        a, b = rng.bytes(la), rng.bytes(lb)
+        assert npz_io._crc32_combine(zlib.crc32(a), zlib.crc32(b), lb) == zlib.crc32(a + b)
+
+
+def test_savez_compressed_roundtrip(tmp_path, monkeypatch):
+    monkeypatch.setattr(npz_io, "BLOCK", 1 << 16)  # force many blocks per member
+    rng = np.random.default_rng(1)
+    d = {"indexes": rng.integers(0, 1000, (3000, 300), dtype=np.int32), "distances": rng.random((3000, 300)),
+         "null_ratios.F": rng.standard_normal((3000, 100)), "mask": rng.random(5000) > 0.03, "binsize": 15000,
+         "has_female": True, "trained_cutoff": np.float64(0.0023), "empty": np.zeros((0, 3)),
+         "sample": np.array({"1": np.arange(5, dtype=np.int32)}, dtype=object)}
+    ours, ref = tmp_path / "ours.npz", tmp_path / "ref.npz"
+    npz_io.savez_compressed(str(ours), threads=4, **d)
+    np.savez_compressed(str(ref), **d)
+    assert zipfile.ZipFile(ours).testzip() is None
+    a, b = np.load(ours, allow_pickle=True), np.load(ref, allow_pickle=True)
+    assert sorted(a.files) == sorted(b.files)
+    for k in b.files:
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
+        if a[k].dtype == object:
+            assert np.array_equal(a[k].item()["1"], b[k].item()["1"])
+        else:
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_load_samples(tmp_path):
+    paths = []
+    for i in range(5):
+        p = tmp_path / f"s{i}.npz"
+        np.savez_compressed(str(p), binsize=5000, sample={"1": np.full(4, i, dtype=np.int32)}, quality={})
+        paths.append(str(p))
+    out = npz_io.load_samples(paths, threads=3)
+    assert [int(s["1"][0]) for s, _ in out] == list(range(5)) and all(b == 5000 for _, b in out)

@@ -64,3 +64,33 @@ def test_shard_bounds_are_the_reference_parts():
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert b == [newref_tools._get_part(r, w, n) for r in range(w)]
+
+
+def _worker_shm(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    per = [23, 19, 17, 13, 11] + [3] * 17
+    x, per, cum = synth.make_corrected_matrix(per, 9, seed=4)
+    ids = [3, 1, 8, 0]
+    sr = parallel.ShardedReference(x.shape[0], x.shape[1], 12, len(ids), torch.device("cpu"), compute_fn=_oracle_compute)
+    for _ in range(2):  # buffers are reused across runs
+        out = sr.run(sr.slice_of(x), per, cum, ids)
+    if rank == 0:
+        np.savez(tmp, idx=out[0], dist=out[1], nr=out[2])
+    sr.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_reference_shared_segment(world, tmp_path):
+    """ShardedReference: sliced upload + all-gather of X, per-rank parts, row blocks written by every rank into one
+    shared host segment -- equals the single-process result."""
+    tmp = str(tmp_path / "out.npz")
+    mp.spawn(_worker_shm, args=(world, _free_port(), tmp), nprocs=world, join=True)
+    got = np.load(tmp)
+    per = [23, 19, 17, 13, 11] + [3] * 17
+    x, per, cum = synth.make_corrected_matrix(per, 9, seed=4)
+    idx, dst, nr = np_oracle.get_reference(x, per, cum, 12, 1, 1, [3, 1, 8, 0])
+    assert np.array_equal(got["idx"], idx) and np.array_equal(got["dist"], dst)
+    assert np.array_equal(got["nr"], nr, equal_nan=True)

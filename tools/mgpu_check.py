@@ -25,5 +25,13 @@ if rank == 0:
     nr = eng.null_ratios(0, n, 300, ids)
     ok = np.array_equal(out[0], idx) and np.array_equal(out[1], dst) and np.allclose(out[2], nr, rtol=1e-13, equal_nan=True)
     print("MGPU_CHECK", "OK" if ok else "MISMATCH", out[0].shape, "world", world, flush=True)
+# the shared-segment variant (sliced upload + all-gather, every rank writes its block to one host array)
+sr = parallel.ShardedReference(x.shape[0], x.shape[1], 300, len(ids), dev)
+for _ in range(2):
+    res = sr.run(sr.slice_of(x), per, cum, ids)
+if rank == 0:
+    ok2 = np.array_equal(res[0], idx) and np.array_equal(res[1], dst) and np.allclose(res[2], nr, rtol=1e-13, equal_nan=True)
+    print("MGPU_SHM_CHECK", "OK" if ok2 else "MISMATCH", flush=True)
+sr.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -454,7 +454,7 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       const int nlists = nsplit * lps;
       static const bool serial_nulls = std::getenv("WCX_SERIAL_NULLS") != nullptr;
       const bool side = d_null && !fused && !serial_nulls;   // null ratios on the side stream
-      const int nblk = rows >= 8192 ? 8 : 1;
+      const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(8, rows / 12000));  // >= 12 k rows per block: two full waves of the null kernel
       for (int bq = 0; bq < nblk; bq++) {
         const int64_t r0 = rows * bq / nblk, r1 = rows * (bq + 1) / nblk;
         if (r1 <= r0) continue;

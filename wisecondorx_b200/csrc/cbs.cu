@@ -782,7 +782,7 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
             const int n = (int)(sg.hi - sg.lo);
             const int nb = std::min(want, nperm - t.done);
             const size_t need = 2 * (size_t)n * nb + 2 * (size_t)nb;
-            if (!jobs.empty() && (doubles + need) * sizeof(double) > ((size_t)3 << 30)) break;
+            if (!jobs.empty() && (doubles + need) * sizeof(double) > ((size_t)8 << 30)) break;  // scratch budget per launch: 8 GB of the 180
             const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
             PermJob job;
             job.lo = sg.lo; job.scratch_off = (int64_t)doubles; job.n = n; job.max_width = t.mw;

@@ -15,7 +15,9 @@ import warnings
 
 import numpy as np
 
-from . import cbs, newref_control, predict_control, predict_output, predict_tools
+import time
+
+from . import cbs, newref_control, npz_io, predict_control, predict_output, predict_tools
 from .overall_tools import gender_correct, scale_sample
 
 
@@ -77,12 +79,15 @@ def tool_newref(args):
         logging.critical("Parameter --yfrac should be a positive number lower than or equal to 1")
         sys.exit()
     samples = []
+    timings = {}
+    t0 = time.perf_counter()
     logging.info("Importing data ...")
-    for infile in args.infiles:
+    for infile, (sample, binsize) in zip(args.infiles, npz_io.load_samples(args.infiles)):  # inflated concurrently
         logging.info("Loading: {}".format(infile))
-        npz = np.load(infile, encoding="latin1", allow_pickle=True)
-        samples.append(scale_sample(npz["sample"].item(), int(npz["binsize"]), args.binsize))
+        samples.append(scale_sample(sample, binsize, args.binsize))
     samples = np.array(samples)
+    timings["load_samples"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     genders, trained_cutoff = train_gender_model(args, samples)
     if genders.count("F") < 5 and args.nipt:
         logging.warning("A NIPT reference should have at least 5 female feti samples. Removing --nipt flag.")
@@ -99,29 +104,40 @@ def tool_newref(args):
     device = getattr(args, "device", 0)
     parts = max(1, int(args.cpus))
     results = []
+    timings["gender_model_and_masks"] = time.perf_counter() - t0
+
+    def one_pass(sample_list, gender, nparts):
+        t1 = time.perf_counter()
+        prep = newref_control.tool_newref_prep(sample_list, gender, total_mask, bins_per_chr, device)
+        t2 = time.perf_counter()
+        results.append(newref_control.tool_newref_main(prep, args.refsize, nparts, device))
+        timings["prep." + gender] = t2 - t1
+        timings["get_reference." + gender] = time.perf_counter() - t2
+
     if len(genders) > 9:
         logging.info("Starting autosomal reference creation ...")
-        prep = newref_control.tool_newref_prep(list(samples), "A", total_mask, bins_per_chr, device)
         logging.info("This might take a while ...")
-        results.append(newref_control.tool_newref_main(prep, args.refsize, parts, device))
+        one_pass(list(samples), "A", parts)
     else:
         logging.critical("Provide at least 10 samples to enable the generation of a reference.")
         sys.exit()
     if genders.count("F") > 4:
         logging.info("Starting female gonosomal reference creation ...")
-        prep = newref_control.tool_newref_prep(list(samples[g == "F"]), "F", total_mask, bins_per_chr, device)
-        results.append(newref_control.tool_newref_main(prep, args.refsize, 1, device))
+        one_pass(list(samples[g == "F"]), "F", 1)
     else:
         logging.warning("Provide at least 5 female samples to enable normalization of female gonosomes.")
     if not args.nipt:
         if genders.count("M") > 4:
             logging.info("Starting male gonosomal reference creation ...")
-            prep = newref_control.tool_newref_prep(list(samples[g == "M"]), "M", total_mask, bins_per_chr, device)
-            results.append(newref_control.tool_newref_main(prep, args.refsize, 1, device))
+            one_pass(list(samples[g == "M"]), "M", 1)
         else:
             logging.warning("Provide at least 5 male samples to enable normalization of male gonosomes.")
+    t0 = time.perf_counter()
     newref_control.tool_newref_merge(args.outfile, results, args.binsize, args.nipt, trained_cutoff)
+    timings["write_reference"] = time.perf_counter() - t0
+    logging.info("Stage wall-clock [s]: " + ", ".join("{} {:.2f}".format(k, v) for k, v in timings.items()))
     logging.info("Finished creating reference")
+    return timings
 
 
 # ---------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ import random
 
 import numpy as np
 
-from . import newref_tools
+from . import newref_tools, npz_io
 
 
 def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
@@ -61,8 +61,7 @@ def tool_newref_main(prep, refsize, parts: int = 1, device: int = 0):
     for part in range(1, parts + 1):
         start, end = newref_tools._get_part(part - 1, parts, n)
         sample_ids = random.sample(range(s), min(s, 100))  # newref_tools.py:214-217
-        idx, dist = eng.topk(start, end, refsize)
-        nr = eng.null_ratios(start, end, refsize, sample_ids)
+        idx, dist, nr = eng.reference(start, end, refsize, sample_ids)
         idx_parts.append(idx); dist_parts.append(dist); nr_parts.append(nr)
     out = {k: v for k, v in prep.items() if k != "pca_corrected_data"}
     out["indexes"] = np.concatenate(idx_parts)
@@ -88,5 +87,5 @@ def tool_newref_merge(outfile, results, binsize, is_nipt, trained_cutoff):
             final_ref[key + sfx] = res[key]
     final_ref["is_nipt"] = is_nipt
     final_ref["trained_cutoff"] = trained_cutoff
-    np.savez_compressed(outfile, **final_ref)
+    npz_io.savez_compressed(outfile, **final_ref)  # same format as np.savez_compressed (newref_control.py:237), deflated on all cores
     return final_ref

@@ -1,0 +1,159 @@
+"""Reference `.npz` I/O on all host cores.
+
+The reference writes its files with np.savez_compressed (main.py:33, newref_control.py:145,176,237): a zip archive
+with one deflate stream per array, produced by a single thread -- at 15 kb / 500 samples the final reference holds
+3 x (indexes 0.23 GB, distances 0.46 GB, null_ratios 0.15 GB) and zlib alone takes longer than every GPU stage
+together.  `savez_compressed` here writes the SAME format (np.load reads it back, the reference reads it) but
+
+  * compresses the arrays concurrently, and
+  * splits a large array into blocks that are deflated independently and concatenated into one valid raw deflate
+    stream (every block but the last ends on a full-flush boundary, the last one finishes the stream; the CRC-32 of
+    the member is the chained crc32 of the blocks) -- the pigz construction, zlib releases the GIL while it works.
+
+`load_samples` reads many sample files concurrently (inflate also releases the GIL)."""
+from __future__ import annotations
+
+import io
+import os
+import struct
+import zlib
+import zipfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+BLOCK = 8 << 20  # bytes deflated per task
+
+
+def _npy_bytes(arr) -> memoryview:
+    """The .npy serialisation of one array (header + data), exactly what np.savez stores in a member."""
+    bio = io.BytesIO()
+    np.lib.format.write_array(bio, np.asanyarray(arr), allow_pickle=True)
+    return bio.getbuffer()
+
+
+def _deflate_block(args):
+    buf, last, level = args
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    out = c.compress(buf)
+    out += c.flush(zlib.Z_FINISH if last else zlib.Z_FULL_FLUSH)
+    return out, zlib.crc32(buf), len(buf)
+
+
+def savez_compressed(file, threads: int | None = None, level: int = 6, **arrays):
+    """Drop-in for np.savez_compressed(file, **arrays) with parallel deflate; same on-disk format."""
+    if isinstance(file, (str, os.PathLike)):
+        file = os.fspath(file)
+        if not file.endswith(".npz"):
+            file += ".npz"
+    threads = threads or min(32, len(os.sched_getaffinity(0)))
+    members = [(name + ".npy", _npy_bytes(a)) for name, a in arrays.items()]
+    tasks = []
+    for mi, (_, raw) in enumerate(members):
+        nblk = max(1, -(-len(raw) // BLOCK))
+        for b in range(nblk):
+            tasks.append((mi, (raw[b * BLOCK:(b + 1) * BLOCK], b == nblk - 1, level)))
+    with ThreadPoolExecutor(threads) as pool:
+        results = list(pool.map(_deflate_block, [t[1] for t in tasks]))
+    per_member = [[] for _ in members]
+    for (mi, _), res in zip(tasks, results):
+        per_member[mi].append(res)
+    with open(file, "wb") as fh:
+        central = []
+        for (name, raw), blocks in zip(members, per_member):
+            crc = 0
+            for _, c, ln in blocks:
+                crc = _crc32_combine(crc, c, ln)
+            csize = sum(len(b[0]) for b in blocks)
+            usize = len(raw)
+            central.append(_write_member(fh, name, blocks, crc, csize, usize))
+        _write_central_directory(fh, central)
+
+
+def _write_member(fh, name, blocks, crc, csize, usize):
+    offset = fh.tell()
+    fname = name.encode("utf-8")
+    zip64 = csize >= 0xFFFFFFFF or usize >= 0xFFFFFFFF
+    extra = struct.pack("<HHQQ", 1, 16, usize, csize) if zip64 else b""
+    ver = 45 if zip64 else 20
+    fh.write(struct.pack("<4sHHHHHLLLHH", b"PK\x03\x04", ver, 0, 8, 0, 0x21, crc,
+                         0xFFFFFFFF if zip64 else csize, 0xFFFFFFFF if zip64 else usize, len(fname), len(extra)))
+    fh.write(fname)
+    fh.write(extra)
+    for data, _, _ in blocks:
+        fh.write(data)
+    return (fname, crc, csize, usize, offset)
+
+
+def _write_central_directory(fh, central):
+    start = fh.tell()
+    for fname, crc, csize, usize, offset in central:
+        zip64 = csize >= 0xFFFFFFFF or usize >= 0xFFFFFFFF or offset >= 0xFFFFFFFF
+        extra = b""
+        if zip64:
+            extra = struct.pack("<HHQQQ", 1, 24, usize, csize, offset)
+        ver = 45 if zip64 else 20
+        fh.write(struct.pack("<4sHHHHHHLLLHHHHHLL", b"PK\x01\x02", ver, ver, 0, 8, 0, 0x21, crc,
+                             0xFFFFFFFF if zip64 else csize, 0xFFFFFFFF if zip64 else usize, len(fname), len(extra), 0, 0, 0,
+                             0o600 << 16, 0xFFFFFFFF if zip64 else offset))
+        fh.write(fname)
+        fh.write(extra)
+    size = fh.tell() - start
+    n = len(central)
+    if start >= 0xFFFFFFFF or n >= 0xFFFF:
+        z64 = fh.tell()
+        fh.write(struct.pack("<4sQHHLLQQQQ", b"PK\x06\x06", 44, 45, 45, 0, 0, n, n, size, start))
+        fh.write(struct.pack("<4sLQL", b"PK\x06\x07", 0, z64, 1))
+        fh.write(struct.pack("<4sHHHHLLH", b"PK\x05\x06", 0, 0, min(n, 0xFFFF), min(n, 0xFFFF), min(size, 0xFFFFFFFF), 0xFFFFFFFF, 0))
+    else:
+        fh.write(struct.pack("<4sHHHHLLH", b"PK\x05\x06", 0, 0, n, n, size, start, 0))
+
+
+# ---- crc32(A || B) from crc32(A), crc32(B), len(B): zlib's crc32_combine (GF(2) matrix squaring) ----
+def _gf2_times(mat, vec):
+    s = 0
+    i = 0
+    while vec:
+        if vec & 1:
+            s ^= mat[i]
+        vec >>= 1
+        i += 1
+    return s
+
+
+def _gf2_square(mat):
+    return [_gf2_times(mat, mat[i]) for i in range(32)]
+
+
+def _crc32_combine(crc1, crc2, len2):
+    if len2 <= 0:
+        return crc1
+    odd = [0xEDB88320] + [1 << i for i in range(31)]  # operator for one zero bit
+    even = _gf2_square(odd)   # two zero bits
+    odd = _gf2_square(even)   # four zero bits
+    while True:
+        even = _gf2_square(odd)
+        if len2 & 1:
+            crc1 = _gf2_times(even, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+        odd = _gf2_square(even)
+        if len2 & 1:
+            crc1 = _gf2_times(odd, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+    return crc1 ^ crc2
+
+
+def load_samples(paths, threads: int | None = None):
+    """[(sample dict, binsize)] of the sample .npz files `paths` (reference main.py:62-64), read concurrently."""
+    threads = threads or min(32, len(os.sched_getaffinity(0)))
+
+    def one(pth):
+        with np.load(pth, encoding="latin1", allow_pickle=True) as npz:
+            return npz["sample"].item(), int(npz["binsize"])
+
+    with ThreadPoolExecutor(threads) as pool:
+        return list(pool.map(one, paths))

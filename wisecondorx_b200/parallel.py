@@ -31,8 +31,7 @@ def _gpu_compute(x_dev, per, cum, ref_size, start, end, sample_ids, engine):
     idx = torch.empty((rows, ref_size), dtype=torch.int32, device=x_dev.device)
     dst = torch.empty((rows, ref_size), dtype=torch.float64, device=x_dev.device)
     nr = torch.empty((rows, m), dtype=torch.float64, device=x_dev.device)
-    engine.topk(start, end, ref_size, device_out=(idx.data_ptr(), dst.data_ptr()))
-    engine.null_ratios(start, end, ref_size, sample_ids, device_out=nr.data_ptr())
+    engine.reference(start, end, ref_size, sample_ids, device_out=(idx.data_ptr(), dst.data_ptr(), nr.data_ptr()))
     return idx, dst, nr
 
 
@@ -90,3 +89,108 @@ def gather_row_blocks(tensors, bounds, rank, device, group=None):
         else:
             dist.gather(pad, None, 0, group=group)
     return tuple(outs) if rank == 0 else None
+
+
+class ShardedReference:
+    """Host-to-host get_reference over the ranks of one box with every PCIe link and NVLink used once:
+
+      1. every rank copies ITS slice of X (ceil(N / W) rows) from its host memory to its GPU  -> H2D time / W
+      2. one NCCL all-gather of the slices over NVLink / NVSwitch gives every GPU the whole matrix (the only
+         exchange of the data path: each target bin needs all of X but no other bin's result)
+      3. every rank runs its part (the reference's part r + 1 of W, newref_tools.py:244-247)
+      4. every rank copies its row block straight into ONE host result array that lives in a POSIX
+         shared-memory segment mapped (and page-locked) by all ranks                       -> D2H time / W
+      5. barrier: rank 0 holds the complete (indexes, distances, null_ratios) in part order
+
+    The segment, the registrations and the device buffers are created once and reused by every run() (what a
+    pinned staging buffer is at N = 1).  `compute_fn` as in get_reference_sharded (CPU / gloo tests)."""
+
+    def __init__(self, n, s, ref_size, m, device, group=None, compute_fn=None, engine=None):
+        import os
+        from multiprocessing import shared_memory
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n, self.s, self.k, self.m = int(n), int(s), int(ref_size), int(m)
+        self.device = torch.device(device)
+        self.compute_fn = compute_fn
+        self.bounds = shard_bounds(self.n, self.world)
+        self.slice_rows = -(-self.n // self.world)
+        self.x_full = torch.empty((self.slice_rows * self.world, self.s), dtype=torch.float64, device=self.device)
+        self.x_slice = torch.empty((self.slice_rows, self.s), dtype=torch.float64, device=self.device)
+        start, end = self.bounds[self.rank]
+        rows = end - start
+        self.dev_out = (torch.empty((rows, self.k), dtype=torch.int32, device=self.device),
+                        torch.empty((rows, self.k), dtype=torch.float64, device=self.device),
+                        torch.empty((rows, self.m), dtype=torch.float64, device=self.device))
+        sizes = [self.n * self.k * 4, self.n * self.k * 8, self.n * self.m * 8]
+        offs = [0, sizes[0], sizes[0] + sizes[1]]
+        total = max(1, sum(sizes))
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=total)
+            name[0] = self._shm.name
+        dist.broadcast_object_list(name, 0, group=group)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+        buf = self._shm.buf
+        self.host_out = (np.ndarray((self.n, self.k), dtype=np.int32, buffer=buf, offset=offs[0]),
+                         np.ndarray((self.n, self.k), dtype=np.float64, buffer=buf, offset=offs[1]),
+                         np.ndarray((self.n, self.m), dtype=np.float64, buffer=buf, offset=offs[2]))
+        self._registered = False
+        if self.device.type == "cuda":
+            ptr = self.host_out[0].ctypes.data
+            rc = torch.cuda.cudart().cudaHostRegister(ptr, total, 0)
+            self._registered = int(rc) == 0
+            self._reg_ptr = ptr
+            if compute_fn is None:
+                self.engine = engine or newref_tools.NewrefEngine(self.device.index or 0)
+                self.engine.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._host_t = tuple(torch.from_numpy(a) for a in self.host_out)
+        dist.barrier(group=group)
+
+    def slice_of(self, x):
+        """This rank's slice of the host matrix (rows [rank * slice_rows, ...)), e.g. to pin it once."""
+        a = self.rank * self.slice_rows
+        return x[a: min(self.n, a + self.slice_rows)]
+
+    def run(self, x_slice_host, per, cum, sample_ids):
+        """x_slice_host: this rank's slice of X (torch CPU tensor, ideally pinned, or NumPy).  Returns the three host
+        arrays (views of the shared segment; complete on every rank after the closing barrier)."""
+        if not torch.is_tensor(x_slice_host):
+            x_slice_host = torch.from_numpy(np.ascontiguousarray(x_slice_host, dtype=np.float64))
+        r = x_slice_host.shape[0]
+        self.x_slice[:r].copy_(x_slice_host, non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.x_full, self.x_slice, group=self.group)
+        else:
+            self.x_full.copy_(self.x_slice)
+        xd = self.x_full[: self.n]
+        start, end = self.bounds[self.rank]
+        ids = list(sample_ids)
+        if self.compute_fn is None:
+            self.engine.load(None, per, cum, on_device_ptr=xd.data_ptr(), shape=(self.n, self.s))
+            self.engine.reference(start, end, self.k, ids, device_out=tuple(t.data_ptr() for t in self.dev_out))
+            outs = self.dev_out
+        else:
+            outs = self.compute_fn(xd, np.asarray(per, dtype=np.int64), np.asarray(cum, dtype=np.int64), self.k, start, end, ids)
+        for host, dev in zip(self._host_t, outs):
+            host[start:end].copy_(dev, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(group=self.group)
+        return self.host_out
+
+    def close(self):
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self._reg_ptr)
+            self._registered = False
+        self._host_t = None
+        self.host_out = None
+        dist.barrier(group=self.group)
+        try:
+            self._shm.close()
+            if self.rank == 0:
+                self._shm.unlink()
+        except Exception:
+            pass
