@@ -316,6 +316,9 @@ def run_ours(args, rank, world, local_rank):
         d2h = ih.nbytes + dh.nbytes + nh.nbytes
         e2e_ms, _, _ = timed(step_e2e, max(1, args.steps // 2), max(1, args.warmup))
         e2e_ms /= max(1, args.steps // 2)
+        # self-check: the host-to-host call and the device-resident call return the same arrays
+        e2e_same = bool(np.array_equal(ih, idx_dev.cpu().numpy()) and np.array_equal(dh, dist_dev.cpu().numpy())
+                        and np.array_equal(nh, nr_dev.cpu().numpy(), equal_nan=True))
     else:
         # every rank uploads its slice of X, one NCCL all-gather over NVLink gives every GPU the matrix, sharded
         # compute, every rank writes its row block into one shared page-locked host segment (parallel.ShardedReference)
@@ -330,6 +333,13 @@ def run_ours(args, rank, world, local_rank):
         d2h = n * k * 12 + n * m * 8
         e2e_ms, _, _ = timed(step_e2e, max(1, args.steps // 2), max(1, args.warmup))
         e2e_ms /= max(1, args.steps // 2)
+        ho = sr.host_out
+        e2e_same = bool(np.array_equal(ho[0][rb:re], idx_dev.cpu().numpy()) and np.array_equal(ho[1][rb:re], dist_dev.cpu().numpy())
+                        and np.array_equal(ho[2][rb:re], nr_dev.cpu().numpy(), equal_nan=True))
+        flag = torch.tensor([1 if e2e_same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank checks its own block of the shared host arrays
+        e2e_same = bool(flag.item())
+        del ho
         sr.close()
     e2e_value = pairs_total / (e2e_ms * 1e-3)
 
@@ -371,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
                                   "row blocks on a side stream next to the re-rank of the following block "
                                   "(stages_ms.null_ratios = what they add after the last re-rank block)"},
         "e2e": {"value": e2e_value, "unit": "bin-pair dist/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "equals_resident_result": e2e_same},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "dist_topk_tc_kernel", "achieved": achieved, "peak": peak_tc,

@@ -28,6 +28,13 @@ def test_savez_compressed_roundtrip(tmp_path, monkeypatch):
     assert zipfile.ZipFile(ours).testzip() is None
     a, b = np.load(ours, allow_pickle=True), np.load(ref, allow_pickle=True)
     assert sorted(a.files) == sorted(b.files)
+    for src in (ours, ref):  # the concurrent reader on both writers' files
+        c = npz_io.load_npz(str(src), threads=3)
+        assert sorted(c) == sorted(b.files)
+        for k in b.files:
+            assert c[k].dtype == b[k].dtype and c[k].shape == b[k].shape, k
+            if c[k].dtype != object:
+                assert np.array_equal(c[k], b[k]), k
     for k in b.files:
         assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
         if a[k].dtype == object:
@@ -44,3 +51,27 @@ def test_load_samples(tmp_path):
         paths.append(str(p))
     out = npz_io.load_samples(paths, threads=3)
     assert [int(s["1"][0]) for s, _ in out] == list(range(5)) and all(b == 5000 for _, b in out)
+
+
+def test_post_processed_result_matches_reference_inflate_loop():
+    """main.get_post_processed_result against a restatement of the reference's loops (predict_control.py:49-63,
+    predict_tools.py:163-170), including more results than kept bins (surplus ignored)."""
+    from wisecondorx_b200 import main as wmain
+    rng = np.random.default_rng(5)
+    bins_per_chr = [7, 5, 4]
+    mask = rng.random(16) > 0.3
+    cnt = int(mask.sum())
+    for extra in (0, 3):
+        res = rng.random(cnt + extra)
+        sizes = rng.integers(0, 300, cnt + extra)
+        want_flat = [0.0] * len(mask)
+        r = res.copy()
+        r[sizes < 150] = 0
+        j = 0
+        for i, v in enumerate(mask):
+            if v:
+                want_flat[i] = r[j]
+                j += 1
+        want = [want_flat[sum(bins_per_chr[:c]):sum(bins_per_chr[:c + 1])] for c in range(3)]
+        got = wmain.get_post_processed_result(150, res, sizes, mask, bins_per_chr)
+        assert all(np.array_equal(g, np.array(w)) for g, w in zip(got, want))

@@ -43,8 +43,10 @@ def run():
     if a.predict:
         t0 = time.perf_counter()
         pargs = wmain.build_parser().parse_args(["predict", paths[-1], ref, os.path.join(d, "out"), "--bed"])
-        pargs.func(pargs)
+        res = pargs.func(pargs)
         out["predict_wall_s"] = round(time.perf_counter() - t0, 2)
+        out["predict_stages_s"] = {k: round(v, 3) for k, v in res.get("timings", {}).items()}
+        out["predict_segments"] = len(res["results_c"])
     print(json.dumps(out), flush=True)
 
 

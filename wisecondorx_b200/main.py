@@ -149,7 +149,14 @@ def get_post_processed_result(minrefbins, result, ref_sizes, mask, bins_per_chr)
     result = np.array(result, dtype=float)
     result[ref_sizes < minrefbins] = 0
     full = np.zeros(len(mask), dtype=float)
-    full[np.asarray(mask, dtype=bool)] = result
+    mask_b = np.asarray(mask, dtype=bool)
+    cnt = int(np.sum(mask_b))
+    # the reference's inflate loop hands out results[j] to the j-th kept bin (predict_tools.py:163-170): surplus
+    # results are ignored, missing ones raise.  The counts differ when the gonosomal pass of newref removed
+    # autosomal bins after the autosomal snapshot -- preserved, not fixed.
+    if len(result) < cnt:
+        raise IndexError("list index out of range")
+    full[mask_b] = result[:cnt]
     offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
     return [full[offs[c]:offs[c + 1]] for c in range(len(bins_per_chr))]
 
@@ -199,10 +206,14 @@ def tool_test(args):
         sys.exit()
     logging.info("Importing data ...")
     # inflate the reference once (the reference re-inflates on every access)
-    ref_file = dict(np.load(args.reference, encoding="latin1", allow_pickle=True))
+    timings = {}
+    t0 = time.perf_counter()
+    ref_file = npz_io.load_npz(args.reference)  # all members inflated once, concurrently
+    timings["load_reference"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     sample_file = np.load(args.infile, encoding="latin1", allow_pickle=True)
     sample = sample_file["sample"].item()
-    n_reads = sum([sum(sample[x]) for x in sample.keys()])
+    n_reads = int(sum(int(np.sum(sample[x], dtype=np.int64)) for x in sample.keys()))
     sample = scale_sample(sample, int(sample_file["binsize"].item()), int(ref_file["binsize"]))
     gender = predict_gender(sample, ref_file["trained_cutoff"])
     if not ref_file["is_nipt"]:
@@ -259,7 +270,7 @@ def tool_test(args):
                for key, val in (("results_r", results_r), ("results_z", results_z), ("results_w", results_w))}
     mask_b = np.asarray(mask, dtype=bool)
     pos = np.arange(int(np.sum(mask_b)), dtype=np.int32)
-    pos[ref_sizes < args.minrefbins] = -1  # rows blanked by get_post_processed_result (reference predict_control.py:50-51)
+    pos[ref_sizes[:len(pos)] < args.minrefbins] = -1  # rows blanked by get_post_processed_result (reference predict_control.py:50-51)
     inflate = np.full(len(mask_b), -1, dtype=np.int32)
     inflate[mask_b] = pos
     results["results_nr"] = {"dense": nr, "inflate": inflate}
@@ -267,11 +278,18 @@ def tool_test(args):
     if args.blacklist:
         logging.info("Applying blacklist ...")
         apply_blacklist(args.blacklist, rem_input["binsize"], results)
+    timings["normalize_and_assemble"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     logging.info("Executing circular binary segmentation ...")
     results["results_c"] = cbs.exec_cbs(rem_input, results, engine)
+    timings["cbs_and_segment_z"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     if args.bed:
         logging.info("Writing tables ...")
         predict_output.generate_output_tables(rem_input, results, engine)
+    timings["write_tables"] = time.perf_counter() - t0
+    logging.info("Stage wall-clock [s]: " + ", ".join("{} {:.2f}".format(k, v) for k, v in timings.items()))
+    results["timings"] = timings
     if args.plot:
         logging.warning("--plot needs the reference's R plotter and is not part of the accelerated path; skipped")
     logging.info("Finished prediction")

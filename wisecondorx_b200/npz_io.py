@@ -157,3 +157,51 @@ def load_samples(paths, threads: int | None = None):
 
     with ThreadPoolExecutor(threads) as pool:
         return list(pool.map(one, paths))
+
+
+def load_npz(path, threads: int | None = None):
+    """dict(np.load(path, allow_pickle=True)) with the members inflated concurrently (the reference re-inflates a
+    member on every `ref_file[key]` access, predict_tools.py:75,117-118,153; a 15 kb reference holds 2.5 GB)."""
+    threads = threads or min(32, len(os.sched_getaffinity(0)))
+    with zipfile.ZipFile(path) as zf:
+        infos = zf.infolist()
+    with open(path, "rb") as fh:
+        fd = fh.fileno()
+
+        def one(info):
+            # local header: 30 bytes + name + extra, then the raw deflate stream
+            hdr = os.pread(fd, 30, info.header_offset)
+            nlen, elen = struct.unpack("<HH", hdr[26:30])
+            raw = os.pread(fd, info.compress_size, info.header_offset + 30 + nlen + elen)
+            if info.compress_type == zipfile.ZIP_DEFLATED:
+                data = zlib.decompress(raw, -15, info.file_size)
+            elif info.compress_type == zipfile.ZIP_STORED:
+                data = raw
+            else:
+                raise ValueError("unsupported zip compression in " + info.filename)
+            bio = io.BytesIO(data)
+            version = np.lib.format.read_magic(bio)
+            if version == (1, 0):
+                shape, fortran, dtype = np.lib.format.read_array_header_1_0(bio)
+            else:
+                shape, fortran, dtype = np.lib.format.read_array_header_2_0(bio)
+            name = info.filename[:-4] if info.filename.endswith(".npy") else info.filename
+            if dtype.hasobject:
+                bio.seek(0)
+                return name, np.lib.format.read_array(bio, allow_pickle=True)
+            arr = np.frombuffer(data, dtype=dtype, offset=bio.tell(), count=int(np.prod(shape, dtype=np.int64)))
+            arr = arr.reshape(shape, order="F" if fortran else "C")
+            return name, arr.copy() if arr.size < 4096 else _writable(arr)
+
+        with ThreadPoolExecutor(threads) as pool:
+            return dict(pool.map(one, infos))
+
+
+def _writable(arr):
+    """np.load returns writable arrays; frombuffer views of bytes are read-only.  One copy of a large member would cost
+    as much as its inflation, so the view is kept and only flagged -- callers that write get a copy."""
+    try:
+        arr.flags.writeable = False
+    except ValueError:
+        pass
+    return arr

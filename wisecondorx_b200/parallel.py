@@ -190,7 +190,10 @@ class ShardedReference:
         dist.barrier(group=self.group)
         try:
             self._shm.close()
-            if self.rank == 0:
-                self._shm.unlink()
-        except Exception:
+        except BufferError:  # a caller still holds a view of the result arrays: the mapping goes with its last reference
             pass
+        if self.rank == 0:
+            try:
+                self._shm.unlink()
+            except FileNotFoundError:
+                pass
