@@ -75,6 +75,7 @@ def _write_member(fh, name, blocks, crc, csize, usize):
     fname = name.encode("utf-8")
     zip64 = csize >= 0xFFFFFFFF or usize >= 0xFFFFFFFF
     extra = struct.pack("<HHQQ", 1, 16, usize, csize) if zip64 else b""
+    extra += _block_index_extra(blocks)
     ver = 45 if zip64 else 20
     fh.write(struct.pack("<4sHHHHHLLLHH", b"PK\x03\x04", ver, 0, 8, 0, 0x21, crc,
                          0xFFFFFFFF if zip64 else csize, 0xFFFFFFFF if zip64 else usize, len(fname), len(extra)))
@@ -82,16 +83,28 @@ def _write_member(fh, name, blocks, crc, csize, usize):
     fh.write(extra)
     for data, _, _ in blocks:
         fh.write(data)
-    return (fname, crc, csize, usize, offset)
+    return (fname, crc, csize, usize, offset, _block_index_extra(blocks))
+
+
+BLOCK_INDEX_ID = 0x6377  # private zip extra field ("wc"): compressed / uncompressed size of every independently
+                         # deflated block of the member -- other readers skip unknown extra fields
+
+
+def _block_index_extra(blocks):
+    if len(blocks) < 2 or len(blocks) > 4000:
+        return b""
+    body = b"".join(struct.pack("<LL", len(data), ulen) for data, _, ulen in blocks)
+    return struct.pack("<HH", BLOCK_INDEX_ID, len(body)) + body
 
 
 def _write_central_directory(fh, central):
     start = fh.tell()
-    for fname, crc, csize, usize, offset in central:
+    for fname, crc, csize, usize, offset, bidx in central:
         zip64 = csize >= 0xFFFFFFFF or usize >= 0xFFFFFFFF or offset >= 0xFFFFFFFF
         extra = b""
         if zip64:
             extra = struct.pack("<HHQQQ", 1, 24, usize, csize, offset)
+        extra += bidx
         ver = 45 if zip64 else 20
         fh.write(struct.pack("<4sHHHHHHLLLHHHHHLL", b"PK\x01\x02", ver, ver, 0, 8, 0, 0x21, crc,
                              0xFFFFFFFF if zip64 else csize, 0xFFFFFFFF if zip64 else usize, len(fname), len(extra), 0, 0, 0,
@@ -173,7 +186,28 @@ def load_npz(path, threads: int | None = None):
             hdr = os.pread(fd, 30, info.header_offset)
             nlen, elen = struct.unpack("<HH", hdr[26:30])
             raw = os.pread(fd, info.compress_size, info.header_offset + 30 + nlen + elen)
-            if info.compress_type == zipfile.ZIP_DEFLATED:
+            bidx = _find_block_index(info.extra)
+            if info.compress_type == zipfile.ZIP_DEFLATED and bidx:
+                # written by savez_compressed above: the blocks are independent raw deflate segments
+                data = bytearray(info.file_size)
+                view, rawv = memoryview(data), memoryview(raw)
+                jobs, co, uo = [], 0, 0
+                for clen, ulen in bidx:
+                    jobs.append((co, clen, uo, ulen))
+                    co += clen
+                    uo += ulen
+                if co != info.compress_size or uo != info.file_size:
+                    raise ValueError("corrupt block index in " + info.filename)
+
+                def blk(j):
+                    c0, cl, u0, ul = j
+                    out = zlib.decompressobj(-15).decompress(rawv[c0:c0 + cl])
+                    if len(out) != ul:
+                        raise ValueError("corrupt block in " + info.filename)
+                    view[u0:u0 + ul] = out
+
+                list(blk_pool.map(blk, jobs))
+            elif info.compress_type == zipfile.ZIP_DEFLATED:
                 data = zlib.decompress(raw, -15, info.file_size)
             elif info.compress_type == zipfile.ZIP_STORED:
                 data = raw
@@ -193,8 +227,19 @@ def load_npz(path, threads: int | None = None):
             arr = arr.reshape(shape, order="F" if fortran else "C")
             return name, arr.copy() if arr.size < 4096 else _writable(arr)
 
-        with ThreadPoolExecutor(threads) as pool:
+        with ThreadPoolExecutor(threads) as pool, ThreadPoolExecutor(threads) as blk_pool:
             return dict(pool.map(one, infos))
+
+
+def _find_block_index(extra: bytes):
+    i = 0
+    while i + 4 <= len(extra):
+        hid, ln = struct.unpack("<HH", extra[i:i + 4])
+        if hid == BLOCK_INDEX_ID:
+            body = extra[i + 4:i + 4 + ln]
+            return [struct.unpack("<LL", body[q:q + 8]) for q in range(0, len(body), 8)]
+        i += 4 + ln
+    return None
 
 
 def _writable(arr):

@@ -128,9 +128,16 @@ class ShardedReference:
         total = max(1, sum(sizes))
         name = [None]
         if self.rank == 0:
-            self._shm = shared_memory.SharedMemory(create=True, size=total)
-            name[0] = self._shm.name
+            try:
+                self._shm = shared_memory.SharedMemory(create=True, size=total)
+                os.posix_fallocate(self._shm._fd, 0, total)  # a too small /dev/shm fails here, not with SIGBUS later
+                name[0] = self._shm.name
+            except OSError as e:
+                name[0] = None
+                self._err = str(e)
         dist.broadcast_object_list(name, 0, group=group)
+        if name[0] is None:  # every rank raises: callers fall back to get_reference_sharded (gather through rank 0)
+            raise RuntimeError("ShardedReference: cannot create the shared result segment ({} bytes)".format(total))
         if self.rank != 0:
             self._shm = shared_memory.SharedMemory(name=name[0])
         buf = self._shm.buf
