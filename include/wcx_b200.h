@@ -125,6 +125,13 @@ int wcx_pca_apply(wcx_ctx* ctx, const double* u, const double* sigma, int32_t nc
  * d_out [n] = sum_s (corrected[b, s] - med[s])^2.  The MAD cutoff (:42-46) is a host scalar step. */
 int wcx_pca_distance(wcx_ctx* ctx, const double* corrected, int64_t n, int32_t s, int32_t on_device,
                      double* med_out, double* d_out);
+/* Device-resident chain (no [n, S] matrix crosses PCIe between the steps of tool_newref_prep and get_reference):
+ *   wcx_newref_normalize_and_mask(out = NULL, out_on_device = 1)  keeps the matrix in the context,
+ *   wcx_pca_gram(x = NULL, x_on_device = 1)                       reads it,
+ *   wcx_pca_apply(corrected_out = NULL) / wcx_pca_distance(corrected = NULL)  keep / read the corrected matrix,
+ *   wcx_newref_load(x = NULL, x_on_device = 2)                    loads the corrected matrix for get_reference.
+ * wcx_prep_fetch copies a resident matrix to the host (which = 0: normalised + masked, 1: corrected). */
+int wcx_prep_fetch(wcx_ctx* ctx, int32_t which, int64_t n, int32_t s, double* out);
 /* Device milliseconds: out[0] = mean + Gram, out[1] = components + correction, out[2] = medians + distances. */
 int wcx_newref_prep_stage_ms(wcx_ctx* ctx, double* out4);
 

@@ -38,3 +38,36 @@ def test_train_pca_matches_exact_pca(n, s):
     bad, cutoff, want_d = np_oracle.pca_distance_filter(want_c)
     np.testing.assert_allclose(med, np.median(corrected, axis=0), rtol=0, atol=0)
     np.testing.assert_allclose(d, want_d, rtol=1e-7)
+
+
+def test_device_resident_prep_equals_host_functions():
+    """newref_tools.DevicePrep (matrices kept in HBM between the steps) returns what the three drop-in functions
+    return through host memory: same kernels, same bits."""
+    samples, _ = synth.make_samples(14, 1_000_000, seed=9, depth=3e6)
+    chrs = range(1, 23)
+    counts = newref_tools.stack_counts(samples, chrs)
+    rng = np.random.default_rng(2)
+    mask = (rng.random(counts.shape[0]) > 0.05) & (counts.sum(axis=1) > 0)  # dead bins would give 0 / 0 rows
+    masked = newref_tools.normalize_and_mask(samples, chrs, mask)
+    corrected, pca = newref_tools.train_pca(masked)
+    d, med = newref_tools.pca_distance(corrected)
+    dp = newref_tools.DevicePrep(0)
+    assert tuple(dp.normalize_and_mask(counts, mask)) == masked.shape
+    assert np.array_equal(dp.fetch("masked"), masked)
+    pca2 = dp.train_pca()
+    assert np.array_equal(pca2.components_, pca.components_) and np.array_equal(pca2.mean_, pca.mean_)
+    assert np.array_equal(dp.fetch("corrected"), corrected, equal_nan=True)  # dead bins give 0 / 0
+    d2, med2 = dp.pca_distance()
+    assert np.array_equal(d2, d, equal_nan=True) and np.array_equal(med2, med, equal_nan=True)
+    # get_reference from the resident corrected matrix == from the host copy
+    per = [int(x) for x in np.diff(np.concatenate([[0], np.cumsum([len(samples[0][str(c)]) for c in chrs])]))]
+    offs = np.concatenate([[0], np.cumsum(per)])
+    mper = np.array([int(mask[offs[i]:offs[i + 1]].sum()) for i in range(22)])
+    good = ~np.isnan(corrected).any(axis=1)
+    if good.all():
+        eng = newref_tools.NewrefEngine(0)
+        dp.load_into(eng, mper, np.cumsum(mper))
+        i1, d1 = eng.topk(0, masked.shape[0], 50)
+        eng.load(corrected, mper, np.cumsum(mper))
+        i2, d2 = eng.topk(0, masked.shape[0], 50)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2)

@@ -215,6 +215,11 @@ int wcx_sync(wcx_ctx* c) {
 
 int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int64_t* per, const int64_t* cum,
                     int32_t nchr, int32_t x_on_device) {
+  if (x_on_device == 2) {
+    // the corrected matrix left in the context by wcx_pca_apply(corrected_out = NULL)
+    if (!c || !c->q_corr.p || c->q_n != n || c->q_s != s) { set_error("wcx_newref_load: no device-resident corrected matrix of that shape"); return 1; }
+    x = c->q_corr.as<double>();
+  }
   if (!c || !x || !per || !cum) { set_error("wcx_newref_load: null argument"); return 1; }
   if (n <= 0 || s <= 0 || nchr <= 0) { set_error("wcx_newref_load: empty matrix"); return 1; }
   if (n > 0x7fffff00ll) { set_error("wcx_newref_load: too many bins"); return 1; }
@@ -930,7 +935,7 @@ int wcx_cbs_stats(wcx_ctx* c, int64_t* out6) {
 // ================================================================================================
 int wcx_newref_normalize_and_mask(wcx_ctx* c, const int32_t* counts, int64_t bins_total, int32_t s, const int32_t* mask_pos,
                                   int64_t n, double* out, int32_t out_on_device) {
-  if (!c || !counts || !mask_pos || !out || bins_total <= 0 || s <= 0 || n < 0) { set_error("wcx_newref_normalize_and_mask: bad argument"); return 1; }
+  if (!c || !counts || !mask_pos || (!out && !out_on_device) || bins_total <= 0 || s <= 0 || n < 0) { set_error("wcx_newref_normalize_and_mask: bad argument"); return 1; }
   for (int64_t i = 0; i < n; i++)
     if (mask_pos[i] < 0 || mask_pos[i] >= bins_total) { set_error("wcx_newref_normalize_and_mask: mask position out of range"); return 1; }
   WCX_CUDA_OK(cudaSetDevice(c->device));
@@ -939,9 +944,13 @@ int wcx_newref_normalize_and_mask(wcx_ctx* c, const int32_t* counts, int64_t bin
       c->q_colsum.ensure(sizeof(unsigned long long) * s))
     return 1;
   double* d_out = out;
-  if (!out_on_device) {
+  if (!out_on_device || !out) {
+    // out == NULL with out_on_device: the matrix stays in the context (input of wcx_pca_gram(x = NULL))
     if (c->q_x.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1) * s)) return 1;
     d_out = c->q_x.as<double>();
+    c->q_xptr = d_out;
+    c->q_n = n;
+    c->q_s = s;
   }
   if (launch_normalize_and_mask(c->q_counts.as<int32_t>(), bins_total, s, c->q_pos.as<int32_t>(), n,
                                 c->q_colsum.as<unsigned long long>(), d_out, st))
@@ -953,10 +962,13 @@ int wcx_newref_normalize_and_mask(wcx_ctx* c, const int32_t* counts, int64_t bin
 }
 
 int wcx_pca_gram(wcx_ctx* c, const double* x, int64_t n, int32_t s, int32_t x_on_device, double* mean_out, double* gram_out) {
-  if (!c || !x || !mean_out || !gram_out || n <= 0 || s <= 0) { set_error("wcx_pca_gram: bad argument"); return 1; }
+  if (!c || (!x && !x_on_device) || !mean_out || !gram_out || n <= 0 || s <= 0) { set_error("wcx_pca_gram: bad argument"); return 1; }
   WCX_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  if (x_on_device) {
+  if (x_on_device && !x) {
+    // the matrix left in the context by wcx_newref_normalize_and_mask(out = NULL)
+    if (c->q_xptr != c->q_x.as<double>() || !c->q_x.p || c->q_n != n || c->q_s != s) { set_error("wcx_pca_gram: no device-resident matrix of that shape"); return 1; }
+  } else if (x_on_device) {
     c->q_xptr = x;
   } else {
     if (h2d(c->q_x, x, sizeof(double) * (size_t)n * s, st)) return 1;
@@ -1041,6 +1053,16 @@ int wcx_pca_distance(wcx_ctx* c, const double* corrected, int64_t n, int32_t s, 
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->prep_ms[2] = ms;
   c->launches += 132;
+  return 0;
+}
+
+int wcx_prep_fetch(wcx_ctx* c, int32_t which, int64_t n, int32_t s, double* out) {
+  if (!c || !out || n <= 0 || s <= 0 || c->q_n != n || c->q_s != s) { set_error("wcx_prep_fetch: bad argument or shape"); return 1; }
+  const DevBuf& b = which == 0 ? c->q_x : c->q_corr;
+  if (!b.p || b.cap < sizeof(double) * (size_t)n * s) { set_error("wcx_prep_fetch: that matrix is not resident"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  WCX_CUDA_OK(cudaMemcpyAsync(out, b.p, sizeof(double) * (size_t)n * s, cudaMemcpyDeviceToHost, c->stream));
+  WCX_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -23,9 +23,12 @@ def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
     bins_per_chr = list(bins_per_chr[:last_chr])
     mask = mask[: int(np.sum(bins_per_chr))]  # a view of the caller's total mask
     chrs = range(1, last_chr + 1)
-    masked = newref_tools.normalize_and_mask(samples, chrs, mask, device)
-    corrected, pca = newref_tools.train_pca(masked, device=device)
-    d, _ = newref_tools.pca_distance(corrected, device=device)
+    # the [N, S] matrices stay in HBM from here to get_reference (newref_tools.DevicePrep)
+    dp = newref_tools.DevicePrep(device)
+    counts = newref_tools.stack_counts(samples, chrs)
+    dp.normalize_and_mask(counts, mask)
+    pca = dp.train_pca()
+    d, _ = dp.pca_distance()
     mad = np.median(np.abs(d - np.median(d)))
     cutoff = max(np.median(d) + 10 * mad, 5.0)  # newref_control.py:45
     bad = d > cutoff
@@ -33,8 +36,9 @@ def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
         logging.info("Removing {} anomalous bins based on PCA distance (cutoff={:.4f})".format(int(np.sum(bad)), cutoff))
         masked_indices = np.where(mask)[0]
         mask[masked_indices[bad]] = False
-        masked = newref_tools.normalize_and_mask(samples, chrs, mask, device)
-        corrected, pca = newref_tools.train_pca(masked, device=device)
+        dp.normalize_and_mask(counts, mask)
+        pca = dp.train_pca()
+    corrected = dp  # device-resident: tool_newref_main loads it without a copy
     offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
     masked_bins_per_chr = [int(np.sum(mask[offs[i]:offs[i + 1]])) for i in range(len(bins_per_chr))]
     return {
@@ -56,7 +60,10 @@ def tool_newref_main(prep, refsize, parts: int = 1, device: int = 0):
     per, cum = prep["masked_bins_per_chr"], prep["masked_bins_per_chr_cum"]
     n, s = x.shape
     eng = newref_tools.NewrefEngine(device)
-    eng.load(x, per, cum)
+    if isinstance(x, np.ndarray):
+        eng.load(x, per, cum)
+    else:  # newref_tools.DevicePrep: the corrected matrix is already in the context
+        x.load_into(eng, per, cum)
     idx_parts, dist_parts, nr_parts = [], [], []
     for part in range(1, parts + 1):
         start, end = newref_tools._get_part(part - 1, parts, n)

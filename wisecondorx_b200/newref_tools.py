@@ -232,3 +232,63 @@ def pca_distance(corrected=None, shape=None, device: int = 0):
         med = np.empty(s); d = np.empty(n)
         _lib.check(L.wcx_pca_distance(ctx.handle, _ptr(x), n, s, 0, _ptr(med), _ptr(d)))
     return d, med
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident form of the preparation chain (no [N, S] matrix crosses PCIe between the steps)
+# ---------------------------------------------------------------------------------------------
+class DevicePrep:
+    """normalize_and_mask -> train_pca -> PCA-distance -> get_reference with the [N, S] matrices kept in the
+    context's device buffers: the same C-ABI calls as the drop-in functions above with NULL host pointers
+    (`out = NULL`, `x = NULL`, `corrected = NULL`, `wcx_newref_load(x_on_device = 2)`)."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+        self.ctx = _lib.default_context(device)
+        self.shape = None
+
+    def normalize_and_mask(self, counts, mask):
+        """counts: int32 [bins_total, S] (stack_counts); mask: bool [bins_total].  Leaves the [N, S] matrix on the device."""
+        counts = np.ascontiguousarray(counts)
+        pos = np.ascontiguousarray(np.flatnonzero(np.asarray(mask, dtype=bool)[: counts.shape[0]]), dtype=np.int32)
+        _lib.check(_lib.load().wcx_newref_normalize_and_mask(self.ctx.handle, _ptr(counts), counts.shape[0], counts.shape[1], _ptr(pos),
+                                                             len(pos), None, 1))
+        self.shape = (len(pos), counts.shape[1])
+        return self.shape
+
+    def train_pca(self, pcacomp=5):
+        """PCA of the resident matrix; returns the model (components_, mean_), keeps `corrected` on the device."""
+        n, s = self.shape
+        L = _lib.load()
+        mean = np.empty(n, dtype=np.float64)
+        gram = np.empty((s, s), dtype=np.float64)
+        _lib.check(L.wcx_pca_gram(self.ctx.handle, None, n, s, 1, _ptr(mean), _ptr(gram)))
+        w, u = np.linalg.eigh(gram)
+        order = np.argsort(w)[::-1][:pcacomp]
+        lam = np.clip(w[order], 1e-300, None)
+        u = np.ascontiguousarray(u[:, order])
+        sigma = np.ascontiguousarray(np.sqrt(lam))
+        comps = np.empty((pcacomp, n), dtype=np.float64)
+        _lib.check(L.wcx_pca_apply(self.ctx.handle, _ptr(u), _ptr(sigma), pcacomp, _ptr(comps), None, 0))
+        piv = np.argmax(np.abs(comps), axis=1)
+        comps *= np.sign(comps[np.arange(pcacomp), piv])[:, None]
+        return _PCAModel(comps, mean, lam / max(s - 1, 1))
+
+    def pca_distance(self):
+        return pca_distance(None, shape=self.shape, device=self.device)
+
+    def load_into(self, engine, per, cum):
+        """wcx_newref_load on the resident corrected matrix (no copy)."""
+        n, s = self.shape
+        per = np.ascontiguousarray(per, dtype=np.int64)
+        cum = np.ascontiguousarray(cum, dtype=np.int64)
+        _lib.check(_lib.load().wcx_newref_load(engine.ctx.handle, None, n, s, _ptr(per), _ptr(cum), len(cum), 2))
+        engine.n, engine.s = int(n), int(s)
+
+    def fetch(self, which: str):
+        """Host copy of a resident matrix ("masked" or "corrected"): tests, or callers that want the reference's
+        prepdatafile (newref_control.py:68)."""
+        n, s = self.shape
+        out = np.empty((n, s), dtype=np.float64)
+        _lib.check(_lib.load().wcx_prep_fetch(self.ctx.handle, 0 if which == "masked" else 1, n, s, _ptr(out)))
+        return out
