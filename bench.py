@@ -168,21 +168,47 @@ def predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, device):
         t_norm = time.perf_counter() - t0
         sm = pe.stage_ms()
         # CBS over all chromosomes of all samples in one batched call
-        series = []
-        for i in range(b):
-            lr = np.log2(r[i]) - m_lr[i]
-            ok = np.isfinite(lr) & (nref[i] >= 150) & (lr != 0)
-            for c in range(22):
-                m = ok[offs[c]:offs[c + 1]]
-                series.append((lr[offs[c]:offs[c + 1]][m], w[offs[c]:offs[c + 1]][m]))
         t0 = time.perf_counter()
-        ends = cbs.segment_series(series, [i % 22 for i in range(len(series))], alpha=1e-4, nperm=10000, seed=1, ctx=eng.ctx)
+        ends = predict_control.segment_batch(r, w, nref, m_lr, offs, 150, 1e-4, 10000, 1, eng.ctx)
         t_cbs = time.perf_counter() - t0
         nseg = sum(len(e) for e in ends)
         out[f"batch{b}"] = {"normalize_wall_ms": t_norm * 1e3, "normalize_kernels_ms": sm["coverage_project"] + sm["normalize_repeat"],
                             "cbs_wall_ms": t_cbs * 1e3, "cbs_kernels_ms": _cbs_ms(eng), "segments": nseg,
                             "cbs_stats": cbs.cbs_stats(eng.ctx)}
     return out
+
+
+def predict_sharded_extras(eng, x, per, cum, idx_full, dist_full, device, rank, world):
+    """BASELINE config 5 on N GPUs: 96 test samples sharded over the ranks (reference arrays replicated, no
+    collective on the data path); wall-clock = max over ranks of normalize + CBS for the rank's samples."""
+    import types
+    import torch
+    import torch.distributed as dist
+    from wisecondorx_b200 import parallel, predict_tools
+    n, s = x.shape
+    rng = np.random.default_rng(99)
+    comps = np.linalg.qr(rng.standard_normal((n, 5)))[0].T.copy()
+    ref = {"indexes": idx_full, "distances": dist_full, "masked_bins_per_chr": per, "masked_bins_per_chr_cum": cum,
+           "pca_components": comps, "pca_mean": np.full(n, 1.0 / n), "mask": np.ones(n, dtype=bool), "bins_per_chr": per}
+    offs = np.concatenate([[0], cum]).astype(int)
+    a, b = parallel.shard_samples(96, world)[rank]
+    samples = [None] * 96
+    for i in range(96):  # same stream on every rank; only the rank's own samples are kept
+        lam = 60.0 * np.clip(x[:, i % s], 0, None)
+        lam[offs[4] + 2000: offs[4] + 2400] *= 1.5
+        c = rng.poisson(lam).astype(np.int32)
+        if a <= i < b:
+            samples[i] = {str(k + 1): c[offs[k]:offs[k + 1]] for k in range(22)}
+    args = types.SimpleNamespace(maskrepeats=5, minrefbins=150, alpha=1e-4, seed=1)
+    pe = predict_tools.PredictEngine(device, eng.ctx)
+    parallel.predict_batch_sharded(args, samples[a:a + 1] * world, ref, "A", pe)  # warm-up: reference arrays to the device
+    dist.barrier()
+    t0 = time.perf_counter()
+    (_, _), _, summary = parallel.predict_batch_sharded(args, samples, ref, "A", pe)
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", device))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"samples": 96, "samples_per_rank": b - a, "wall_ms_max_over_ranks": float(t.item()) * 1e3,
+            "segments": int(sum(summary)) if summary is not None else None}
 
 
 def _cbs_ms(eng):
@@ -340,6 +366,9 @@ def run_ours(args, rank, world, local_rank):
             ho = sr.host_out
             e2e_same = bool(np.array_equal(ho[0][rb:re], idx_dev.cpu().numpy()) and np.array_equal(ho[1][rb:re], dist_dev.cpu().numpy())
                             and np.array_equal(ho[2][rb:re], nr_dev.cpu().numpy(), equal_nan=True))
+            predict_sharded = None
+            if not args.no_predict:
+                predict_sharded = predict_sharded_extras(eng, x, per, cum, np.array(ho[0]), np.array(ho[1]), local_rank, rank, world)
             del ho
             sr.close()
             e2e_path = "sliced H2D + NCCL all-gather of X, row blocks written by every rank into one shared pinned host segment"
@@ -355,6 +384,7 @@ def run_ours(args, rank, world, local_rank):
                 o = holder["out"]
                 e2e_same = bool(np.array_equal(o[0][rb:re], idx_dev.cpu().numpy()) and np.array_equal(o[1][rb:re], dist_dev.cpu().numpy()))
             e2e_path = "H2D on rank 0 + NCCL broadcast of X, gather of the row blocks to rank 0, D2H on rank 0"
+            predict_sharded = None
         e2e_ms /= max(1, args.steps // 2)
         flag = torch.tensor([1 if e2e_same else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank checks its own block of the host arrays
@@ -411,6 +441,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_predict:
         out["predict"] = predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, local_rank)
+    if world > 1 and predict_sharded is not None:
+        out["predict"] = {"batch96_sharded": predict_sharded}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_sample(x, per, cum, args.cpu_seconds)
     print(json.dumps(out), flush=True)

@@ -334,3 +334,35 @@ def test_fused_reference_edge_cases(eng, gref):
     idx, dist, nr = eng.reference(0, gx.shape[0], 30, gref["G_ids"].tolist())
     assert np.array_equal(idx, gref["G_idx"]) and np.array_equal(dist, gref["G_dist"])
     np.testing.assert_allclose(nr, gref["G_nr"], rtol=1e-12, atol=1e-14, equal_nan=True)
+
+
+def test_fused_null_kernel_experiment_subprocess():
+    """The opt-in fused re-rank + null-ratio kernel (WCX_FUSED_NULLS=1, read once per process) stays bit-identical
+    to the default path: run in a child process and compare with this process's result."""
+    import subprocess
+    import sys
+    import tempfile
+    per = (synth.config_bins(2) // 3).astype(np.int64)
+    x, per, cum = synth.make_corrected_matrix(per, 64, seed=77)
+    n = x.shape[0]
+    ids = list(range(0, 64, 3))
+    eng = newref_tools.NewrefEngine(0)
+    eng.load(x, per, cum)
+    idx, dist, nr = eng.reference(0, n, 300, ids)
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from wisecondorx_b200 import newref_tools, synth\n"
+        "per = (synth.config_bins(2) // 3).astype(np.int64)\n"
+        "x, per, cum = synth.make_corrected_matrix(per, 64, seed=77)\n"
+        "eng = newref_tools.NewrefEngine(0); eng.load(x, per, cum)\n"
+        "idx, dist, nr = eng.reference(0, x.shape[0], 300, list(range(0, 64, 3)))\n"
+        "np.savez(sys.argv[1], idx=idx, dist=dist, nr=nr)\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "fused.npz")
+        env = dict(os.environ, WCX_FUSED_NULLS="1")
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=240)
+        got = np.load(out)
+        assert np.array_equal(got["idx"], idx) and np.array_equal(got["dist"], dist)
+        assert np.array_equal(got["nr"], nr, equal_nan=True)

@@ -94,3 +94,31 @@ def test_sharded_reference_shared_segment(world, tmp_path):
     idx, dst, nr = np_oracle.get_reference(x, per, cum, 12, 1, 1, [3, 1, 8, 0])
     assert np.array_equal(got["idx"], idx) and np.array_equal(got["dist"], dst)
     assert np.array_equal(got["nr"], nr, equal_nan=True)
+
+
+def _worker_predict(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    samples = list(range(100, 111))  # 11 "samples": uneven blocks
+
+    def fake(args, my, ref, gender, eng):
+        return {"ids": list(my)}, [s % 7 for s in my]
+
+    (a, b), res, summary = parallel.predict_batch_sharded(None, samples, None, "A", None, process_fn=fake)
+    assert res["ids"] == samples[a:b]
+    if rank == 0:
+        np.save(tmp, np.array(summary))
+    else:
+        assert summary is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_predict_batch_sharded_over_samples(world, tmp_path):
+    tmp = str(tmp_path / "sum.npy")
+    mp.spawn(_worker_predict, args=(world, _free_port(), tmp), nprocs=world, join=True)
+    assert np.load(tmp).tolist() == [s % 7 for s in range(100, 111)]
+    blocks = parallel.shard_samples(11, world)
+    assert blocks[0][0] == 0 and blocks[-1][1] == 11 and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))

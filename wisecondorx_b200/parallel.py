@@ -204,3 +204,50 @@ class ShardedReference:
                 self._shm.unlink()
             except FileNotFoundError:
                 pass
+
+
+# ---------------------------------------------------------------------------------------------
+# predict, batch of samples (BASELINE config 5): samples sharded over the ranks, reference replicated
+# ---------------------------------------------------------------------------------------------
+def shard_samples(n_samples: int, world: int):
+    """Contiguous blocks of samples per rank (same arithmetic as the target-bin parts)."""
+    return [newref_tools._get_part(r, world, n_samples) for r in range(world)]
+
+
+def predict_batch_sharded(args, samples, ref_file, ref_gender="A", engine=None, process_fn=None, group=None):
+    """`normalize` + CBS for a batch of samples with the SAMPLES sharded over the ranks.  Every rank holds the
+    whole reference (0.7 GB at 15 kb) and processes its block of samples independently -- no collective on the data
+    path, exactly like the reference's one-process-per-sample shell loop (docs/include/pipeline/predict.sh:15-23);
+    each rank keeps (and would write out) the results of its own samples.  Rank 0 additionally receives a small
+    summary (segments per sample) through gather_object.
+
+    process_fn(args, my_samples, ref_file, ref_gender, engine) -> (results, segments_per_sample); defaults to
+    normalize_batch + segment_batch on the GPU (the gloo tests inject a CPU function)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    a, b = shard_samples(len(samples), world)[rank]
+    mine = samples[a:b]
+    if process_fn is None:
+        from . import predict_control
+
+        def process_fn(args_, my, ref, gender, eng):
+            if not my:
+                return None, []
+            r, z, w, nref, m_lr, m_z = predict_control.normalize_batch(args_, my, ref, gender, eng)
+            offs = np.concatenate([[0], np.asarray(ref["masked_bins_per_chr_cum"], dtype=np.int64)])
+            ends = predict_control.segment_batch(r, w, nref, m_lr, offs, getattr(args_, "minrefbins", 150), getattr(args_, "alpha", 1e-4),
+                                                 10000, getattr(args_, "seed", None) or 0, eng.ctx if eng else None)
+            nchr = len(offs) - 1
+            per_sample = [int(sum(len(e) for e in ends[i * nchr:(i + 1) * nchr])) for i in range(len(my))]
+            return {"r": r, "z": z, "w": w, "ref_sizes": nref, "m_lr": m_lr, "m_z": m_z, "segment_ends": ends}, per_sample
+
+    results, per_sample = process_fn(args, mine, ref_file, ref_gender, engine)
+    summary = None
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((a, b, per_sample), gathered, dst=0, group=group)
+        if rank == 0:
+            summary = [n for (_, _, lst) in sorted(gathered, key=lambda t: t[0]) for n in lst]
+    else:
+        summary = list(per_sample)
+    return (a, b), results, summary

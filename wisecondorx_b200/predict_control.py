@@ -36,3 +36,21 @@ def inflate_results(results, mask):
     out = np.zeros(len(mask), dtype=np.asarray(results).dtype)
     out[mask] = results
     return out
+
+
+def segment_batch(r, w, nref, m_lr, chr_offsets, minrefbins=150, alpha=1e-4, nperm=10000, seed=0, ctx=None):
+    """CBS of a normalised batch in one call: the log2 ratios of every (sample, chromosome) as one series each
+    (bins without enough reference bins or without signal are dropped like NA bins in CBS.R:41).  Returns the list
+    of segment-end arrays in (sample, chromosome) order."""
+    from . import cbs
+    offs = np.asarray(chr_offsets, dtype=np.int64)
+    nchr = len(offs) - 1
+    series = []
+    for i in range(r.shape[0]):
+        with np.errstate(all="ignore"):
+            lr = np.log2(r[i]) - m_lr[i]
+        ok = np.isfinite(lr) & (nref[i] >= minrefbins) & (lr != 0)
+        for c in range(nchr):
+            m = ok[offs[c]:offs[c + 1]]
+            series.append((lr[offs[c]:offs[c + 1]][m], w[offs[c]:offs[c + 1]][m]))
+    return cbs.segment_series(series, [i % nchr for i in range(len(series))], alpha=alpha, nperm=nperm, seed=seed, ctx=ctx)
