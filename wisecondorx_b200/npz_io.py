@@ -25,11 +25,30 @@ import numpy as np
 BLOCK = 8 << 20  # bytes deflated per task
 
 
-def _npy_bytes(arr) -> memoryview:
-    """The .npy serialisation of one array (header + data), exactly what np.savez stores in a member."""
+def _npy_parts(arr):
+    """The .npy serialisation of one array, exactly what np.savez stores in a member, as (header bytes, data
+    buffer): C-contiguous numeric arrays are not copied, everything else goes through np.lib.format.write_array."""
+    arr = np.asanyarray(arr)
+    if arr.dtype.hasobject or not arr.flags.c_contiguous or arr.ndim == 0 or arr.size == 0:
+        bio = io.BytesIO()
+        np.lib.format.write_array(bio, arr, allow_pickle=True)
+        return b"", bio.getbuffer()
     bio = io.BytesIO()
-    np.lib.format.write_array(bio, np.asanyarray(arr), allow_pickle=True)
-    return bio.getbuffer()
+    np.lib.format.write_array_header_1_0(bio, np.lib.format.header_data_from_array_1_0(arr))
+    return bio.getvalue(), memoryview(arr).cast("B")
+
+
+def _member_blocks(header: bytes, data):
+    """BLOCK-sized pieces of header + data; only the first piece (which carries the header) is a copy."""
+    total = len(header) + len(data)
+    if total <= BLOCK or not header:
+        whole = (header + bytes(data)) if header else data
+        return [whole[b * BLOCK:(b + 1) * BLOCK] for b in range(max(1, -(-len(whole) // BLOCK)))], total
+    first = BLOCK - len(header)
+    blocks = [header + bytes(data[:first])]
+    for o in range(first, len(data), BLOCK):
+        blocks.append(data[o:o + BLOCK])
+    return blocks, total
 
 
 def _deflate_block(args):
@@ -47,12 +66,13 @@ def savez_compressed(file, threads: int | None = None, level: int = 6, **arrays)
         if not file.endswith(".npz"):
             file += ".npz"
     threads = threads or min(32, len(os.sched_getaffinity(0)))
-    members = [(name + ".npy", _npy_bytes(a)) for name, a in arrays.items()]
+    members = []
     tasks = []
-    for mi, (_, raw) in enumerate(members):
-        nblk = max(1, -(-len(raw) // BLOCK))
-        for b in range(nblk):
-            tasks.append((mi, (raw[b * BLOCK:(b + 1) * BLOCK], b == nblk - 1, level)))
+    for mi, (name, a) in enumerate(arrays.items()):
+        blocks, total = _member_blocks(*_npy_parts(a))
+        members.append((name + ".npy", total))
+        for b, blk in enumerate(blocks):
+            tasks.append((mi, (blk, b == len(blocks) - 1, level)))
     with ThreadPoolExecutor(threads) as pool:
         results = list(pool.map(_deflate_block, [t[1] for t in tasks]))
     per_member = [[] for _ in members]
@@ -60,12 +80,11 @@ def savez_compressed(file, threads: int | None = None, level: int = 6, **arrays)
         per_member[mi].append(res)
     with open(file, "wb") as fh:
         central = []
-        for (name, raw), blocks in zip(members, per_member):
+        for (name, usize), blocks in zip(members, per_member):
             crc = 0
             for _, c, ln in blocks:
                 crc = _crc32_combine(crc, c, ln)
             csize = sum(len(b[0]) for b in blocks)
-            usize = len(raw)
             central.append(_write_member(fh, name, blocks, crc, csize, usize))
         _write_central_directory(fh, central)
 
