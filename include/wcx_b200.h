@@ -201,6 +201,12 @@ int wcx_debug_prep_f16(wcx_ctx* ctx, uint16_t* xh_out, float* norm_out, int32_t*
 int wcx_debug_list_counts(wcx_ctx* ctx, int32_t* cnt_out, int64_t nslots);
 /* Test hook: prepared operands.  xc_out [n, k_pad] (host, may be NULL), norm_out [n] (host). */
 int wcx_debug_prep(wcx_ctx* ctx, float* xc_out, float* norm_out, int32_t* k_pad_out);
+/* Test hook, host only (no GPU needed): for S samples the NumPy pairwise-summation plan (int32 triples), the
+ * leaf-major permutation of a row used by the re-rank gather (perm[p] = source column or -1 for zero padding) and
+ * the leaf descriptors (offset, steps, tail terms, 0).  sizes3 = {permuted row length, leaves, plan triples}.
+ * Output pointers may be NULL to query the sizes. */
+int wcx_debug_leaf_layout(int32_t s, int32_t* perm_out, int32_t perm_cap, int32_t* desc_out, int32_t desc_cap,
+                          int32_t* plan_out, int32_t plan_cap, int32_t* sizes3);
 
 #ifdef __cplusplus
 }

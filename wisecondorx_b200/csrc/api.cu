@@ -727,6 +727,23 @@ int wcx_debug_list_counts(wcx_ctx* c, int32_t* cnt_out, int64_t nslots) {
   return 0;
 }
 
+// host only (no device needed): the leaf-major layout of a row of S samples (rerank.cu build_leaf_layout)
+int wcx_debug_leaf_layout(int32_t s, int32_t* perm_out, int32_t perm_cap, int32_t* desc_out, int32_t desc_cap, int32_t* plan_out,
+                          int32_t plan_cap, int32_t* sizes3) {
+  if (s <= 0 || !sizes3) { set_error("wcx_debug_leaf_layout: bad argument"); return 1; }
+  std::vector<int32_t> plan(3 * 4096);
+  const int pl = build_sum_plan(s, plan.data(), (int32_t)plan.size());
+  if (pl < 0) { set_error("wcx_debug_leaf_layout: too many samples"); return 1; }
+  std::vector<int32_t> perm, desc;
+  const int sp = build_leaf_layout(plan.data(), pl, perm, desc);
+  if (sp < 0) { set_error("wcx_debug_leaf_layout: leaf too long"); return 1; }
+  sizes3[0] = sp; sizes3[1] = (int32_t)desc.size() / 4; sizes3[2] = pl;
+  if (perm_out) { if (perm_cap < sp) { set_error("perm_cap too small"); return 1; } std::memcpy(perm_out, perm.data(), sizeof(int32_t) * sp); }
+  if (desc_out) { if (desc_cap < (int32_t)desc.size()) { set_error("desc_cap too small"); return 1; } std::memcpy(desc_out, desc.data(), sizeof(int32_t) * desc.size()); }
+  if (plan_out) { if (plan_cap < 3 * pl) { set_error("plan_cap too small"); return 1; } std::memcpy(plan_out, plan.data(), sizeof(int32_t) * 3 * pl); }
+  return 0;
+}
+
 int wcx_debug_prep(wcx_ctx* c, float* xc_out, float* norm_out, int32_t* k_pad_out) {
   if (!c || !c->loaded) { set_error("wcx_debug_prep: not loaded"); return 1; }
   WCX_CUDA_OK(cudaSetDevice(c->device));
