@@ -10,7 +10,7 @@
 // 8 sample values per bin), so one chunk (n * 64 bytes) stays L2-resident while the whole grid
 // works on it and a gather of two adjacent samples is a single 16-byte load.
 // One warp per target bin: the bin's k indexes live in registers (R = ceil(k / 32) per lane); per
-// pair of samples the warp gathers k double2 values and selects the two middle order statistics
+// pair of samples the warp gathers k pairs of pre-computed keys (null_ratios.cuh) and selects the two middle order statistics
 // of each with a bisection over order-preserving 64-bit keys (select.cuh) -- no sort.
 // np.median returns NaN when any value is NaN.
 #include "null_ratios.cuh"
@@ -22,8 +22,8 @@ namespace {
 
 // xm: [n][8] sample values of this chunk; idx: [rows, k]; out: [rows, m_total] at columns m_off..
 template <int R>
-__global__ void __launch_bounds__(256)
-null_ratios_kernel(const double* __restrict__ xm, int64_t n, const int32_t* __restrict__ idx, int64_t row_begin,
+__global__ void __launch_bounds__(256, R <= 10 ? 4 : 2)
+null_ratios_kernel(const uint64_t* __restrict__ xm, int64_t n, const int32_t* __restrict__ idx, int64_t row_begin,
                    int64_t rows, int k, int mc, int m_off, int m_total, double* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t lrow = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -50,7 +50,7 @@ __global__ void gather_cols_kernel(const double* __restrict__ x, int64_t n, int3
   const int c = blockIdx.y;
   if (r >= n) return;
   const int mm = c * NR_CHUNK + j;
-  xm[((int64_t)c * n + r) * NR_CHUNK + j] = mm < m ? x[r * s + ids[mm]] : 0.0;
+  reinterpret_cast<uint64_t*>(xm)[((int64_t)c * n + r) * NR_CHUNK + j] = null_key(mm < m ? x[r * s + ids[mm]] : 0.0);
 }
 }  // namespace
 
@@ -74,7 +74,7 @@ int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t 
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   for (int m0 = 0; m0 < m; m0 += NR_CHUNK) {
     const int mc = m - m0 < NR_CHUNK ? m - m0 : NR_CHUNK;
-    const double* xm = xt + (int64_t)(m0 / NR_CHUNK) * n * NR_CHUNK;
+    const uint64_t* xm = reinterpret_cast<const uint64_t*>(xt) + (int64_t)(m0 / NR_CHUNK) * n * NR_CHUNK;
     if (k <= 320)
       null_ratios_kernel<10><<<grid, warps * 32, 0, st>>>(xm, n, idx, row_begin, rows, k, mc, m0, m, out);
     else

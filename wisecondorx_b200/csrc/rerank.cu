@@ -551,8 +551,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     if (NULLS) {
       // all k indexes are 0: the median of k copies of col[0] is col[0] ((v + v) / 2 is exact)
       for (int c = tid; c < na.m_total; c += RR_THREADS) {
-        const double* xm = na.xm + (int64_t)(c / NR_CHUNK) * pv.n * NR_CHUNK + (c % NR_CHUNK);
-        na.out[lrow * na.m_total + c] = log2(__ldg(xm + row * NR_CHUNK) / __ldg(xm));
+        const uint64_t* xm = reinterpret_cast<const uint64_t*>(na.xm) + (int64_t)(c / NR_CHUNK) * pv.n * NR_CHUNK + (c % NR_CHUNK);
+        na.out[lrow * na.m_total + c] = log2(key_d(__ldg(xm + row * NR_CHUNK)) / key_d(__ldg(xm)));
       }
     }
     return;
@@ -757,7 +757,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     const int nchunks = (na.m_total + NR_CHUNK - 1) / NR_CHUNK;
     for (int c = warp; c < nchunks; c += RR_THREADS / 32) {
       const int mc = min(NR_CHUNK, na.m_total - c * NR_CHUNK);
-      null_row_chunk<R>(na.xm + (int64_t)c * pv.n * NR_CHUNK, g, k, mc, row, lane, na.out + lrow * na.m_total + c * NR_CHUNK);
+      null_row_chunk<R>(reinterpret_cast<const uint64_t*>(na.xm) + (int64_t)c * pv.n * NR_CHUNK, g, k, mc, row, lane,
+                        na.out + lrow * na.m_total + c * NR_CHUNK);
     }
   }
 }

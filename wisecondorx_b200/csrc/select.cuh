@@ -19,8 +19,10 @@ __device__ __forceinline__ double key_d(uint64_t k) {
 // (padding entries are ~0).  Bisection over the high 32 bits with two shortcuts: the bits shared
 // by all keys are skipped, and as soon as the bracket holds a single key that key is fetched
 // directly (about log2(count) + 2 iterations instead of 32 + 32).
+// hmax_out (optional): largest high word among the real keys -- lets a caller that maps NaN to a key with high
+// word 0xffffffff detect it without a pass of its own.
 template <int R>
-__device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int rank, int count) {
+__device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int rank, int count, uint32_t* hmax_out = nullptr) {
   uint32_t hmin = 0xffffffffu, hmax = 0u;
 #pragma unroll
   for (int r = 0; r < R; r++) {
@@ -32,6 +34,7 @@ __device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int ra
   }
   hmin = __reduce_min_sync(0xffffffffu, hmin);
   hmax = __reduce_max_sync(0xffffffffu, hmax);
+  if (hmax_out) *hmax_out = hmax;
   const uint32_t diff = hmin ^ hmax;
   const int top = diff ? (31 - __clz(diff)) : -1;  // highest differing bit
   uint32_t hi = top >= 31 ? 0u : (hmin & ~((top >= 0 ? (2u << top) : 1u) - 1u));
@@ -83,9 +86,9 @@ __device__ __forceinline__ uint64_t warp_select(const uint64_t (&key)[R], int ra
 
 // np.median of the `count` real keys (count >= 1, no NaN among them)
 template <int R>
-__device__ __forceinline__ double warp_median(const uint64_t (&key)[R], int count) {
+__device__ __forceinline__ double warp_median(const uint64_t (&key)[R], int count, uint32_t* hmax_out = nullptr) {
   const int hi_rank = count >> 1;
-  const uint64_t up = warp_select<R>(key, hi_rank, count);
+  const uint64_t up = warp_select<R>(key, hi_rank, count, hmax_out);
   const double upper = key_d(up);
   if (count & 1) return upper;
   int c_lt = 0;
