@@ -208,8 +208,8 @@ def load_npz(path, threads: int | None = None):
             bidx = _find_block_index(info.extra)
             if info.compress_type == zipfile.ZIP_DEFLATED and bidx:
                 # written by savez_compressed above: the blocks are independent raw deflate segments
-                data = bytearray(info.file_size)
-                view, rawv = memoryview(data), memoryview(raw)
+                data = np.empty(info.file_size, dtype=np.uint8)  # no zero fill; np.copyto releases the GIL for the block copies
+                view, rawv = data, memoryview(raw)
                 jobs, co, uo = [], 0, 0
                 for clen, ulen in bidx:
                     jobs.append((co, clen, uo, ulen))
@@ -223,7 +223,7 @@ def load_npz(path, threads: int | None = None):
                     out = zlib.decompressobj(-15).decompress(rawv[c0:c0 + cl])
                     if len(out) != ul:
                         raise ValueError("corrupt block in " + info.filename)
-                    view[u0:u0 + ul] = out
+                    np.copyto(view[u0:u0 + ul], np.frombuffer(out, dtype=np.uint8))
 
                 list(blk_pool.map(blk, jobs))
             elif info.compress_type == zipfile.ZIP_DEFLATED:
@@ -232,7 +232,7 @@ def load_npz(path, threads: int | None = None):
                 data = raw
             else:
                 raise ValueError("unsupported zip compression in " + info.filename)
-            bio = io.BytesIO(data)
+            bio = io.BytesIO(memoryview(data)[:4096].tobytes() if isinstance(data, np.ndarray) else data[:4096])  # header only
             version = np.lib.format.read_magic(bio)
             if version == (1, 0):
                 shape, fortran, dtype = np.lib.format.read_array_header_1_0(bio)
@@ -240,8 +240,7 @@ def load_npz(path, threads: int | None = None):
                 shape, fortran, dtype = np.lib.format.read_array_header_2_0(bio)
             name = info.filename[:-4] if info.filename.endswith(".npy") else info.filename
             if dtype.hasobject:
-                bio.seek(0)
-                return name, np.lib.format.read_array(bio, allow_pickle=True)
+                return name, np.lib.format.read_array(io.BytesIO(bytes(data)), allow_pickle=True)
             arr = np.frombuffer(data, dtype=dtype, offset=bio.tell(), count=int(np.prod(shape, dtype=np.int64)))
             arr = arr.reshape(shape, order="F" if fortran else "C")
             return name, arr.copy() if arr.size < 4096 else _writable(arr)
