@@ -12,6 +12,8 @@ from wisecondorx_b200 import _lib
 
 
 def _layout(s):
+    from wisecondorx_b200 import build
+    build.build()  # no-op when the in-tree library is up to date (nvcc cross-compiles without a GPU)
     L = _lib.load()
     sizes = np.zeros(3, dtype=np.int32)
     _lib.check(L.wcx_debug_leaf_layout(s, None, 0, None, 0, None, 0, ctypes.c_void_p(sizes.ctypes.data)))
