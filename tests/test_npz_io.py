@@ -75,3 +75,32 @@ def test_post_processed_result_matches_reference_inflate_loop():
         want = [want_flat[sum(bins_per_chr[:c]):sum(bins_per_chr[:c + 1])] for c in range(3)]
         got = wmain.get_post_processed_result(150, res, sizes, mask, bins_per_chr)
         assert all(np.array_equal(g, np.array(w)) for g, w in zip(got, want))
+
+
+def test_async_writer_and_newref_merge(tmp_path):
+    """AsyncNpzWriter (arrays deflated while the caller goes on) through tool_newref_merge: key layout of the
+    reference's final .npz (newref_control.py:220-237), passes queued early or at merge time."""
+    from wisecondorx_b200 import newref_control
+    rng = np.random.default_rng(3)
+
+    def fake_pass(gender, n):
+        return {"gender": gender, "mask": rng.random(50) > 0.1, "bins_per_chr": np.arange(3), "masked_bins_per_chr": np.arange(3),
+                "masked_bins_per_chr_cum": np.cumsum(np.arange(3)), "pca_components": rng.random((5, n)), "pca_mean": rng.random(n),
+                "indexes": rng.integers(0, n, (n, 7), dtype=np.int32), "distances": rng.random((n, 7)), "null_ratios": rng.random((n, 4))}
+
+    for early in (False, True):
+        out = str(tmp_path / f"ref{int(early)}.npz")
+        results = [fake_pass("A", 40), fake_pass("F", 45), fake_pass("M", 47)]
+        writer = npz_io.AsyncNpzWriter(out) if early else None
+        if early:
+            for r in results[:2]:
+                newref_control.writer_add_pass(writer, r, 15000)
+        newref_control.tool_newref_merge(out, results, 15000, False, 0.0023, writer)
+        z = np.load(out, allow_pickle=True)
+        for res, sfx in zip(results, ("", ".F", ".M")):
+            assert int(z["binsize" + sfx]) == 15000
+            for key in newref_control.RESULT_KEYS:
+                assert np.array_equal(z[key + sfx], res[key]) and z[key + sfx].dtype == np.asarray(res[key]).dtype
+        assert bool(z["has_female"]) and bool(z["has_male"]) and not bool(z["is_nipt"]) and float(z["trained_cutoff"]) == 0.0023
+        assert "_queued" not in z.files and "gender" not in z.files
+        assert len(z.files) == 3 * 10 + 4

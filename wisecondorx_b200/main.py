@@ -106,11 +106,14 @@ def tool_newref(args):
     results = []
     timings["gender_model_and_masks"] = time.perf_counter() - t0
 
+    writer = npz_io.AsyncNpzWriter(args.outfile)  # deflates the arrays of a finished pass while the next one runs
+
     def one_pass(sample_list, gender, nparts):
         t1 = time.perf_counter()
         prep = newref_control.tool_newref_prep(sample_list, gender, total_mask, bins_per_chr, device)
         t2 = time.perf_counter()
         results.append(newref_control.tool_newref_main(prep, args.refsize, nparts, device))
+        newref_control.writer_add_pass(writer, results[-1], args.binsize)
         timings["prep." + gender] = t2 - t1
         timings["get_reference." + gender] = time.perf_counter() - t2
 
@@ -133,7 +136,7 @@ def tool_newref(args):
         else:
             logging.warning("Provide at least 5 male samples to enable normalization of male gonosomes.")
     t0 = time.perf_counter()
-    newref_control.tool_newref_merge(args.outfile, results, args.binsize, args.nipt, trained_cutoff)
+    newref_control.tool_newref_merge(args.outfile, results, args.binsize, args.nipt, trained_cutoff, writer)
     timings["write_reference"] = time.perf_counter() - t0
     logging.info("Stage wall-clock [s]: " + ", ".join("{} {:.2f}".format(k, v) for k, v in timings.items()))
     logging.info("Finished creating reference")

@@ -77,9 +77,18 @@ def tool_newref_main(prep, refsize, parts: int = 1, device: int = 0):
     return out
 
 
-def tool_newref_merge(outfile, results, binsize, is_nipt, trained_cutoff):
+RESULT_KEYS = ("mask", "bins_per_chr", "masked_bins_per_chr", "masked_bins_per_chr_cum", "pca_components", "pca_mean",
+               "indexes", "distances", "null_ratios")
+
+
+def tool_newref_merge(outfile, results, binsize, is_nipt, trained_cutoff, writer=None):
     """Final reference .npz with the reference's key layout (newref_control.py:220-237): autosomal keys
-    plain, gonosomal keys suffixed .F / .M, plus has_female / has_male / is_nipt / trained_cutoff."""
+    plain, gonosomal keys suffixed .F / .M, plus has_female / has_male / is_nipt / trained_cutoff.
+    Same format as np.savez_compressed (:237), deflated on all cores; with `writer` (npz_io.AsyncNpzWriter) the
+    arrays of the passes already handed to writer_add_pass are being deflated since their pass finished."""
+    own = writer is None
+    if own:
+        writer = npz_io.AsyncNpzWriter(outfile)
     final_ref = {"has_female": False, "has_male": False}
     for res in results:
         gender = res["gender"]
@@ -89,10 +98,24 @@ def tool_newref_merge(outfile, results, binsize, is_nipt, trained_cutoff):
         if gender == "M":
             final_ref["has_male"] = True
         final_ref["binsize" + sfx] = binsize
-        for key in ("mask", "bins_per_chr", "masked_bins_per_chr", "masked_bins_per_chr_cum", "pca_components", "pca_mean",
-                    "indexes", "distances", "null_ratios"):
+        for key in RESULT_KEYS:
             final_ref[key + sfx] = res[key]
+        if not res.get("_queued"):
+            writer_add_pass(writer, res, binsize)
+    for key in ("has_female", "has_male"):
+        writer.add(key, final_ref[key])
     final_ref["is_nipt"] = is_nipt
     final_ref["trained_cutoff"] = trained_cutoff
-    npz_io.savez_compressed(outfile, **final_ref)  # same format as np.savez_compressed (newref_control.py:237), deflated on all cores
+    writer.add("is_nipt", is_nipt)
+    writer.add("trained_cutoff", trained_cutoff)
+    writer.close()
     return final_ref
+
+
+def writer_add_pass(writer, res, binsize):
+    """Starts deflating the arrays of one finished pass (A / F / M) while the next pass runs on the GPU."""
+    sfx = "" if res["gender"] == "A" else ".{}".format(res["gender"])
+    writer.add("binsize" + sfx, binsize)
+    for key in RESULT_KEYS:
+        writer.add(key + sfx, res[key])
+    res["_queued"] = True

@@ -89,6 +89,45 @@ def savez_compressed(file, threads: int | None = None, level: int = 6, **arrays)
         _write_central_directory(fh, central)
 
 
+class AsyncNpzWriter:
+    """savez_compressed in two halves: add(name, array) starts deflating the array on the pool right away (the caller
+    goes on computing -- zlib and the CUDA library both release the GIL), close() waits and writes the archive.
+    The arrays must not be modified between add() and close().  Same on-disk format as savez_compressed."""
+
+    def __init__(self, file, threads: int | None = None, level: int = 6):
+        if isinstance(file, (str, os.PathLike)):
+            file = os.fspath(file)
+            if not file.endswith(".npz"):
+                file += ".npz"
+        self.file = file
+        self.level = level
+        # two cores stay free for the caller, whose host work (NumPy, LAPACK) runs while the pool deflates
+        self.pool = ThreadPoolExecutor(threads or max(1, min(32, len(os.sched_getaffinity(0)) - 2)))
+        self.members = []  # (name, usize, [futures], keep-alive)
+
+    def add(self, name, array):
+        header, data = _npy_parts(array)
+        blocks, total = _member_blocks(header, data)
+        futs = [self.pool.submit(_deflate_block, (blk, b == len(blocks) - 1, self.level)) for b, blk in enumerate(blocks)]
+        self.members.append((name + ".npy", total, futs, (array, data)))
+
+    def close(self):
+        try:
+            with open(self.file, "wb") as fh:
+                central = []
+                for name, usize, futs, _ in self.members:
+                    blocks = [f.result() for f in futs]
+                    crc = 0
+                    for _, c, ln in blocks:
+                        crc = _crc32_combine(crc, c, ln)
+                    csize = sum(len(b[0]) for b in blocks)
+                    central.append(_write_member(fh, name, blocks, crc, csize, usize))
+                _write_central_directory(fh, central)
+        finally:
+            self.pool.shutdown(wait=True)
+            self.members = []
+
+
 def _write_member(fh, name, blocks, crc, csize, usize):
     offset = fh.tell()
     fname = name.encode("utf-8")
