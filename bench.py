@@ -107,9 +107,12 @@ def make_workload(name: str):
     return x, per, cum
 
 
-def cpu_reference_sample(x, per, cum, target_seconds=20.0):
+def cpu_reference_sample(x, per, cum, target_seconds=20.0, check=None, max_windows=64):
     """Times the CPU restatement of the reference path (oracle/wcx_oracle.c, OpenMP over all host
-    cores) on a bounded sample of target bins spread over the genome; returns pairs/s."""
+    cores) on a bounded sample of target bins spread over the genome; returns pairs/s.
+    check = (row_begin, idx, dist, null_ratios): host arrays of the GPU result for rows row_begin.. -- every timed
+    window that lies inside them is compared with the oracle's output (indexes and distances bit-exact, null ratios
+    1e-12) and the verdict is returned under "parity"."""
     from oracle import c_oracle
     c_oracle.build()
     n = x.shape[0]
@@ -119,26 +122,43 @@ def cpu_reference_sample(x, per, cum, target_seconds=20.0):
     # calibrate with one row per thread, then size the sample
     rows_done, pairs_done, t_total = 0, 0, 0.0
     batch = threads
-    starts = rng.permutation(max(1, n - batch))[:64]
+    lo_s, hi_s = (0, n - batch) if check is None else (check[0], check[0] + check[1].shape[0] - batch)
+    starts = lo_s + rng.permutation(max(1, hi_s - lo_s))[:max_windows]
     si = 0
+    parity = {"rows": 0, "ok": True, "windows": 0, "checks": "indexes == , distances == (bit-exact), null ratios rtol 1e-12"}
     while t_total < target_seconds and si < len(starts):
         s0 = int(starts[si]); si += 1
         e0 = min(n, s0 + batch)
         t0 = time.perf_counter()
-        idx, _ = c_oracle.topk(x, per, cum, REFSIZE, s0, e0, threads)
-        c_oracle.null_ratios(x, idx, s0, e0, ids, threads)
+        idx, dist = c_oracle.topk(x, per, cum, REFSIZE, s0, e0, threads)
+        nr = c_oracle.null_ratios(x, idx, s0, e0, ids, threads)
         t_total += time.perf_counter() - t0
         rows_done += e0 - s0
         pairs_done += n_pairs(per, s0, e0)
+        if check is not None:
+            rb, gi, gd, gn = check
+            lo, hi = max(s0, rb), min(e0, rb + gi.shape[0])
+            if hi > lo:
+                a, b = lo - rb, hi - rb
+                same = (np.array_equal(gi[a:b], idx[lo - s0:hi - s0]) and np.array_equal(gd[a:b], dist[lo - s0:hi - s0]) and
+                        np.allclose(gn[a:b], nr[lo - s0:hi - s0], rtol=1e-12, atol=1e-14, equal_nan=True))
+                parity["rows"] += hi - lo
+                parity["windows"] += 1
+                if not same:
+                    parity["ok"] = False
+                    parity.setdefault("first_mismatch_row", lo)
         if si == 1 and t_total > 0:
             est = target_seconds / t_total
             batch = int(max(threads, min(4096, batch * max(1.0, est / 8))))
-    return {"value": pairs_done / t_total, "unit": "bin-pair dist/s", "cores": threads, "kind": "port",
-            "sample": f"{rows_done} target bins in {si} windows spread over the genome (all {n} candidates each), "
-                      f"C restatement of get_reference with OpenMP, {t_total:.1f} s"}
+    out = {"value": pairs_done / t_total, "unit": "bin-pair dist/s", "cores": threads, "kind": "port",
+           "sample": f"{rows_done} target bins in {si} windows spread over the genome (all {n} candidates each), "
+                     f"C restatement of get_reference with OpenMP, {t_total:.1f} s"}
+    if check is not None:
+        out["parity"] = parity
+    return out
 
 
-def predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, device):
+def predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, device, batches=(1, 96)):
     """BASELINE configs 4 / 5 (reported beside the headline metric): `normalize` (coverage + PCA projection +
     3 within-sample passes) and the CUDA CBS for 1 and 96 test samples against the reference just built."""
     import types
@@ -160,7 +180,7 @@ def predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, device):
     args = types.SimpleNamespace(maskrepeats=5)
     pe = predict_tools.PredictEngine(device, eng.ctx)
     out = {}
-    for b in (1, 96):
+    for b in batches:
         samples = [sample(i) for i in range(b)]
         predict_control.normalize_batch(args, samples[:1], ref, "A", pe)  # load the reference arrays once, warm up
         t0 = time.perf_counter()
@@ -443,11 +463,22 @@ def run_ours(args, rank, world, local_rank):
         out["predict"] = predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, local_rank)
     if world > 1 and predict_sharded is not None:
         out["predict"] = {"batch96_sharded": predict_sharded}
+    # parity of THIS run's result at THIS configuration: the oracle's rows against the GPU arrays (the CPU baseline's
+    # timed windows double as the parity sample; without the baseline leg a short sample is still checked)
+    check = (rb, idx_dev.cpu().numpy(), dist_dev.cpu().numpy(), nr_dev.cpu().numpy())
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference_sample(x, per, cum, args.cpu_seconds)
+        cb = cpu_reference_sample(x, per, cum, args.cpu_seconds, check=check)
+    else:
+        cb = cpu_reference_sample(x[:, :], per, cum, 2.0, check=check, max_windows=3)
+    out["parity"] = cb.pop("parity")
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cb
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not out["parity"]["ok"] or out["parity"]["rows"] == 0:
+        sys.stderr.write("bench.py: GPU result differs from the oracle (or nothing was compared): %r\n" % (out["parity"],))
+        sys.exit(1)
 
 
 def main():

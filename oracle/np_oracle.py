@@ -309,3 +309,106 @@ def get_z_score(results_c, results_nr, results_r, results_w):
             z = "nan"
         zs.append(z)
     return zs
+
+
+# --------------------------------------------------------------------------------------
+# newref: tool_newref_prep (newref_control.py:24-80) and get_mask (newref_tools.py:77-102)
+# --------------------------------------------------------------------------------------
+
+
+def get_mask(samples):
+    """newref_tools.py:77-102: bins whose summed depth-normalised coverage exceeds 5 % of the median
+    over the non-empty bins.  Returns (mask over the concatenated 24 chromosomes, bins_per_chr)."""
+    lens = [max(len(s[str(c)]) for s in samples) for c in range(1, 25)]
+    all_data = normalize_and_mask(samples, range(1, 25), np.ones(int(sum(lens)), dtype=bool))
+    sum_per_bin = np.sum(all_data, 1)
+    median_cov = np.median(sum_per_bin[sum_per_bin > 0])
+    return sum_per_bin > (0.05 * median_cov), lens
+
+
+def tool_newref_prep(samples, gender, mask, bins_per_chr, pcacomp=5):
+    """newref_control.py:24-80 with the exact PCA in place of sklearn's randomized solver.  `mask` is edited IN
+    PLACE through a view exactly like the reference (:33, :51-54), so a caller that passes its
+    total mask sees the removed bins in the later passes.  Returns the dict the reference saves (:68-80)."""
+    last_chr = {"A": 22, "F": 23}.get(gender, 24)
+    bins_per_chr = list(bins_per_chr[:last_chr])
+    mask = mask[: int(np.sum(bins_per_chr))]
+    chrs = range(1, last_chr + 1)
+    masked = normalize_and_mask(samples, chrs, mask)
+    corrected, comps, mean = train_pca(masked, pcacomp)
+    bad, cutoff, _ = pca_distance_filter(corrected)
+    if np.any(bad):
+        mask[np.where(mask)[0][bad]] = False
+        masked = normalize_and_mask(samples, chrs, mask)
+        corrected, comps, mean = train_pca(masked, pcacomp)
+    offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
+    mbpc = [int(np.sum(mask[offs[i]:offs[i + 1]])) for i in range(len(bins_per_chr))]
+    return {"mask": mask.copy(), "bins_per_chr": np.array(bins_per_chr), "masked_bins_per_chr": np.array(mbpc),
+            "masked_bins_per_chr_cum": np.cumsum(mbpc), "pca_components": comps, "pca_mean": mean,
+            "pca_corrected_data": corrected, "n_removed": int(np.sum(bad)), "cutoff": float(cutoff)}
+
+
+# --------------------------------------------------------------------------------------
+# predict: result assembly and post-processing (main.py:242-271, predict_control.py:49-63,
+# predict_tools.py:163-233)
+# --------------------------------------------------------------------------------------
+
+
+def assemble_results(aut, gon, nr_aut, nr_gon, minrefbins, mask, bins_per_chr):
+    """main.py:242-271 + get_post_processed_result (predict_control.py:49-63).  aut / gon are the tuples
+    (results_r, results_z, results_w, ref_sizes, m_lr, m_z) of the two `normalize` calls.  Returns per-chromosome
+    lists of float arrays for r / z / w (0 = no data) and the ref_sizes vector."""
+    r = np.append(aut[0], gon[0])
+    z = np.append(aut[1], gon[1]) - aut[5]
+    with np.errstate(all="ignore"):
+        w = np.append(aut[2] * np.nanmean(gon[2]), gon[2] * np.nanmean(aut[2]))
+        w = w / np.nanmean(w)
+    if np.isnan(w).any() or np.isinf(w).any():
+        w = np.ones(len(w))
+    ref_sizes = np.append(aut[3], gon[3])
+    mask = np.asarray(mask, dtype=bool)
+    offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
+    out = {}
+    for key, val in (("results_r", r), ("results_z", z), ("results_w", w)):
+        val = np.array(val, dtype=float)
+        val[ref_sizes < minrefbins] = 0  # predict_control.py:50-51
+        full = np.zeros(len(mask))
+        full[mask] = val[: int(mask.sum())]  # inflate_results, predict_tools.py:163-170
+        out[key] = [full[offs[c]:offs[c + 1]] for c in range(len(bins_per_chr))]
+    return out, ref_sizes
+
+
+def log_trans(results, log_r_median):
+    """predict_tools.py:180-193."""
+    for c in range(len(results["results_r"])):
+        with np.errstate(all="ignore"):
+            r = np.log2(results["results_r"][c])
+        bad = ~np.isfinite(r)
+        r[bad] = 0
+        results["results_z"][c][bad] = 0
+        results["results_w"][c][bad] = 0
+        r[r != 0] -= log_r_median
+        results["results_r"][c] = r
+
+
+def per_bin_stats(indexes, distances):
+    """ref_qc.py:22-38: mean and max distance and number of reference bins of every target bin."""
+    d = np.asarray(distances, dtype=float)
+    return np.mean(d, axis=1), np.max(d, axis=1), np.full(len(d), np.asarray(indexes).shape[1], dtype=int)
+
+
+def apply_blacklist(results, bed_text, binsize):
+    """predict_tools.py:202-233: bins [int(s / binsize), int(e / binsize) + 1) of every BED line are blanked in
+    r / z / w; chrY lines are skipped when the results hold 23 chromosomes; out-of-range positions are ignored."""
+    for line in bed_text.splitlines():
+        if not line.strip():
+            continue
+        name, s, e = line.strip().split("\t")
+        name = name[3:] if name[:3] == "chr" else name
+        c = int({"X": "23", "Y": "24"}.get(name, name)) - 1
+        if len(results["results_r"]) < 24 and c == 23:
+            continue
+        lo = max(0, int(int(s) / binsize))
+        hi = min(len(results["results_r"][c]), int(int(e) / binsize) + 1)
+        for key in ("results_r", "results_z", "results_w"):
+            results[key][c][lo:hi] = 0

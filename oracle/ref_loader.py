@@ -27,7 +27,7 @@ _loaded = None
 
 def load():
     """Returns a namespace with the reference modules (newref_tools, newref_control,
-    predict_tools, predict_control, overall_tools)."""
+    predict_tools, predict_control, overall_tools, main, predict_output, ref_qc)."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -48,8 +48,10 @@ def load():
         explained_variance_ = np.ones(1)
 
     predict_tools.PCA = _ShimPCA
+    from wisecondorx import main, predict_output, ref_qc
+    main.qc_reference = ref_qc.qc_reference  # main.py:135 calls it without importing it (NameError)
     ns = types.SimpleNamespace(newref_tools=newref_tools, newref_control=newref_control,
                                predict_tools=predict_tools, predict_control=predict_control,
-                               overall_tools=overall_tools)
+                               overall_tools=overall_tools, main=main, predict_output=predict_output, ref_qc=ref_qc)
     _loaded = ns
     return ns

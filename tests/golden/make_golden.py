@@ -76,8 +76,7 @@ def golden_newref_predict(R):
     """Runs the reference's whole `newref` (main.tool_newref) on 24 synthetic samples at 5 Mb
     bins, then `normalize` (predict_control.py:21) for A / F / M on a test sample with a planted
     gain, and `get_z_score` (overall_tools.py:88) on hand-made segments."""
-    from wisecondorx import main as ref_main, ref_qc
-    ref_main.qc_reference = ref_qc.qc_reference  # main.py:135 NameError (SURVEY section 0)
+    ref_main = R.main  # ref_loader injects qc_reference (main.py:135 NameError, SURVEY section 0)
     binsize = 5_000_000
     samples, genders = synth.make_samples(24, binsize, seed=21, depth=4e6)
     tmp = tempfile.mkdtemp()
@@ -149,6 +148,100 @@ def golden_newref_predict(R):
     out["zs_nr"], out["zs_has_nr"], out["zs_bpc"] = dense, has, np.array(bpc)
     np.savez_compressed(os.path.join(HERE, "newref_predict.npz"), **out)
     print("newref_predict.npz written", {k: v.shape for k, v in ref.items() if hasattr(v, "shape")})
+    golden_tool_test(R, ref_main, args.outfile, test_samples, tmp, binsize)
+
+
+def golden_tool_test(R, ref_main, ref_path, test_samples, tmp, binsize):
+    """The reference's whole `tool_test` (main.py:145-300) on the two test samples against the reference .npz it
+    built itself, with the R bridge replaced by tests/golden/stub_cbs.py (R / DNAcopy are absent):
+    golden for the result assembly (main.py:242-271), get_post_processed_result, log_trans, apply_blacklist,
+    get_z_score as called from exec_cbs, and the four output tables."""
+    import copy
+    from stub_cbs import stub_segments
+    out = {}
+    bl = os.path.join(tmp, "blacklist.bed")
+    with open(bl, "w") as fh:
+        fh.write("chr3\t{}\t{}\n".format(2 * binsize + 5, 4 * binsize - 1))
+        fh.write("X\t{}\t{}\n".format(10 * binsize, 12 * binsize))
+        fh.write("chr7\t0\t100\n")
+    out["blacklist_text"] = np.array(open(bl).read())
+
+    def fake_exec_R(json_dict):
+        if "results_c" in json_dict:
+            return None
+        nchr = 24 if json_dict["ref_gender"] == "M" else 23  # CBS.R:30-34
+        return [{"chr": c + 1, "s": s_, "e": e_, "r": r_} for c, s_, e_, r_ in
+                stub_segments(json_dict["results_r"], json_dict["results_w"], nchr)]
+
+    captured = {}
+    orig_tables = ref_main.generate_output_tables
+
+    def capture(rem_input, results):
+        captured["rem_input"] = {k: v for k, v in rem_input.items() if k != "args"}
+        captured["results"] = copy.deepcopy({k: v for k, v in results.items() if k != "results_nr"})
+        orig_tables(rem_input, results)
+
+    R.predict_tools.exec_R = fake_exec_R
+    ref_main.generate_output_tables = capture
+    try:
+        for si, ts in enumerate(test_samples):
+            f = os.path.join(tmp, f"test{si}.npz")
+            np.savez_compressed(f, binsize=binsize, sample=ts, quality={})
+            outid = os.path.join(tmp, f"out{si}")
+            targs = types.SimpleNamespace(infile=f, reference=ref_path, outid=outid, minrefbins=10, maskrepeats=5, alpha=1e-4,
+                                          zscore=5, beta=None, blacklist=bl if si == 0 else None, gender=None, ylim="def",
+                                          bed=True, plot=False, cairo=False, add_plot_title=False, seed=1, regions=None)
+            ref_main.tool_test(targs)
+            res, rem = captured["results"], captured["rem_input"]
+            for key in ("results_r", "results_z", "results_w"):
+                out[f"t{si}_{key}"] = np.concatenate([np.asarray(x, dtype=float) for x in res[key]])
+            out[f"t{si}_results_c"] = np.array([[c[0], c[1], c[2], np.nan if isinstance(c[3], str) else c[3], c[4]]
+                                                for c in res["results_c"]], dtype=float)
+            out[f"t{si}_meta"] = np.array([rem["ref_gender"], rem["gender"], str(rem["n_reads"]), str(rem["binsize"])])
+            for sfx in ("_bins.bed", "_segments.bed", "_aberrations.bed", "_statistics.txt"):
+                out[f"t{si}{sfx}"] = np.array(open(outid + sfx).read())
+    finally:
+        ref_main.generate_output_tables = orig_tables
+    np.savez_compressed(os.path.join(HERE, "tool_test.npz"), **out)
+    print("tool_test.npz written", sorted(out))
+
+
+def golden_prep(R):
+    """tool_newref_prep (newref_control.py:24-80) for the A, F and M passes of one sample set, the mask leaking from
+    pass to pass as in main.py:98-137: normalize_and_mask, train_pca (np.random.seed pinned; sklearn's randomized
+    solver where `auto` picks it), the PCA-distance filter with the in-place mask edit and the redo.
+    Six bins carry sample-specific noise the five components cannot explain, so the filter fires."""
+    binsize = 2_000_000
+    S = 60
+    samples, genders = synth.make_samples(S, binsize, seed=41, depth=8e6)
+    rng = np.random.default_rng(42)
+    lens = [len(samples[0][str(c)]) for c in range(1, 25)]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    for b in rng.choice(int(offs[22]), 6, replace=False):
+        c = int(np.searchsorted(offs, b, side="right")) - 1
+        for s in samples:
+            s[str(c + 1)][b - offs[c]] = int(s[str(c + 1)][b - offs[c]] * rng.lognormal(0, 1.2))
+    out = {"counts": np.stack([np.concatenate([s[str(c)] for c in range(1, 25)]) for s in samples], axis=1).astype(np.int32),
+           "lens": np.array(lens), "genders": np.array(genders), "binsize": np.array(binsize)}
+    samples = np.array(samples)
+    for i, s in enumerate(samples):
+        samples[i] = R.overall_tools.gender_correct(s, genders[i])
+    total_mask, bpc = R.newref_tools.get_mask(samples)
+    g = np.array(genders)
+    total_mask = total_mask & R.newref_tools.get_mask(samples[g == "F"])[0] & R.newref_tools.get_mask(samples[g == "M"])[0]
+    out["total_mask"], out["bins_per_chr"] = total_mask.copy(), np.array(bpc)
+    tmp = tempfile.mkdtemp()
+    for gender, sub in (("A", samples), ("F", samples[g == "F"]), ("M", samples[g == "M"])):
+        a = types.SimpleNamespace(prepdatafile=os.path.join(tmp, "d.npy"), prepfile=os.path.join(tmp, "p.npz"), binsize=binsize)
+        np.random.seed(3)
+        R.newref_control.tool_newref_prep(a, sub, gender, total_mask, bpc)  # edits total_mask in place
+        p = np.load(a.prepfile)
+        for key in ("mask", "masked_bins_per_chr", "masked_bins_per_chr_cum", "pca_components", "pca_mean"):
+            out[f"{gender}_{key}"] = p[key]
+        out[f"{gender}_corrected_rows"] = np.load(a.prepdatafile)[::5]  # every 5th bin keeps the fixture small
+        out[f"{gender}_total_mask_after"] = total_mask.copy()
+    np.savez_compressed(os.path.join(HERE, "prep.npz"), **out)
+    print("prep.npz written", {k: v.shape for k, v in out.items()})
 
 
 def golden_example_bed():
@@ -183,3 +276,5 @@ if __name__ == "__main__":
         golden_newref_predict(R)
     if a.only in (None, "example_bed"):
         golden_example_bed()
+    if a.only in (None, "prep"):
+        golden_prep(R)

@@ -1,0 +1,215 @@
+"""f2 / f3: the vectorised host functions of the drop-in package against the LIVE reference functions they mirror
+(scale_sample, gender model, get_mask, get_post_processed_result / inflate_results, log_trans, apply_blacklist, the
+bins / segments / aberrations writers, segment statistics, ref QC).  Pure host code: runs where /root/reference exists
+(the build container); on the GPU box the committed goldens (tests/test_assembly_gpu.py) cover the same functions."""
+import copy
+import logging
+import os
+import types
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+from wisecondorx_b200 import main as wcx_main, overall_tools, predict_control, predict_output, predict_tools, ref_qc, synth
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="live reference not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def R():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("frm,to", [(5000, 15000), (5000, 100000), (100000, 100000), (50000, 1000000)])
+def test_scale_sample(R, frm, to):
+    rng = np.random.default_rng(frm + to)
+    sample = {str(c): rng.poisson(30, int(rng.integers(1, 700))).astype(np.int32) for c in range(1, 25)}
+    sample["7"] = np.zeros(0, dtype=np.int32) if frm != to else sample["7"]
+    want = R.overall_tools.scale_sample(copy.deepcopy(sample), frm, to)
+    got = overall_tools.scale_sample(copy.deepcopy(sample), frm, to)
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+        assert np.asarray(got[k]).dtype == np.asarray(want[k]).dtype, k
+
+
+def test_scale_sample_rejects_like_reference(R):
+    sample = {"1": np.arange(10, dtype=np.int32)}
+    for fn in (R.overall_tools.scale_sample, overall_tools.scale_sample):
+        with pytest.raises(SystemExit):
+            fn(sample, 5000, 7000)
+
+
+def test_get_mask_and_gender_model(R):
+    samples, genders = synth.make_samples(16, 2_000_000, seed=12, depth=5e6)
+    arr = np.array(samples)
+    want_mask, want_bpc = R.newref_tools.get_mask(arr)
+    got_mask, got_bpc = wcx_main.get_mask(arr)
+    assert np.array_equal(got_mask, want_mask) and list(got_bpc) == list(want_bpc)
+    args = types.SimpleNamespace(yfrac=0.006, plotyfrac=None)
+    want_g, want_cut = R.newref_tools.train_gender_model(args, arr)
+    got_g, got_cut = wcx_main.train_gender_model(args, arr)
+    assert got_g == want_g and got_cut == want_cut
+    for s in samples[:4]:
+        assert wcx_main.predict_gender(s, 0.006) == R.predict_tools.predict_gender(s, 0.006)
+
+
+def test_gender_model_gmm(R):
+    """Without --yfrac: GaussianMixture + first local minimum (newref_tools.py:21-68).  Needs a bimodal Y fraction."""
+    samples, genders = synth.make_samples(40, 5_000_000, seed=8, depth=5e6)
+    arr = np.array(samples)
+    args = types.SimpleNamespace(yfrac=None, plotyfrac=None)
+    np.random.seed(1)
+    try:
+        want_g, want_cut = R.newref_tools.train_gender_model(args, arr)
+    except IndexError:
+        pytest.skip("the reference finds no local minimum on this synthetic Y-fraction distribution (SURVEY.md 8c)")
+    np.random.seed(1)
+    got_g, got_cut = wcx_main.train_gender_model(args, arr)
+    assert got_g == want_g and np.isclose(got_cut, want_cut, rtol=1e-12)
+
+
+def _fake_results(rng, bpc, zero_frac=0.1):
+    res = {"results_r": [], "results_z": [], "results_w": []}
+    for nb in bpc:
+        r = np.exp2(rng.normal(0, 0.1, nb))
+        r[rng.random(nb) < zero_frac] = 0
+        r[rng.random(nb) < 0.02] = -1.0  # log2 of a negative ratio -> nan -> blanked
+        res["results_r"].append(r)
+        res["results_z"].append(rng.normal(0, 1, nb))
+        res["results_w"].append(rng.uniform(0.5, 2, nb))
+    return res
+
+
+def test_post_processing_chain(R, tmp_path):
+    rng = np.random.default_rng(2)
+    bpc = [int(x) for x in rng.integers(5, 60, 24)]
+    total = sum(bpc)
+    mask = rng.random(total) > 0.15
+    nm = int(mask.sum())
+    ref_sizes = rng.integers(0, 300, nm)
+    vals = rng.normal(1, 0.1, nm)
+    rem = {"mask": mask, "bins_per_chr": bpc, "binsize": 100000}
+    args = types.SimpleNamespace(minrefbins=150)
+    want = R.predict_control.get_post_processed_result(args, vals.copy(), ref_sizes, rem)
+    got = wcx_main.get_post_processed_result(150, vals.copy(), ref_sizes, mask, bpc)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+    assert np.array_equal(predict_control.inflate_results(vals, mask), np.array(R.predict_tools.inflate_results(vals, rem), dtype=float))
+    # log_trans
+    res_w = _fake_results(rng, bpc)
+    res_g = copy.deepcopy(res_w)
+    want_res = {k: [x.copy() for x in v] for k, v in res_w.items()}
+    with np.errstate(all="ignore"):
+        R.predict_tools.log_trans(want_res, 0.0123)
+    wcx_main.log_trans(res_g, 0.0123)
+    for key in ("results_r", "results_z", "results_w"):
+        for c in range(24):
+            np.testing.assert_array_equal(np.asarray(res_g[key][c], dtype=float), np.asarray(want_res[key][c], dtype=float), err_msg=key)
+    # apply_blacklist (chr prefix, X / Y names, out-of-range and clipped intervals, chrY skipped with 23 chromosomes)
+    bl = tmp_path / "bl.bed"
+    bl.write_text("chr1\t150000\t420000\n2\t0\t99999\nX\t200000\t100000000\nY\t0\t300000\nchr5\t-5\t10\n")
+    for nchr in (24, 23):
+        a = {k: [np.array(x, dtype=float) for x in v[:nchr]] for k, v in res_g.items()}
+        b = {k: [np.array(x, dtype=float).tolist() for x in v[:nchr]] for k, v in res_g.items()}
+        rem2 = {"args": types.SimpleNamespace(blacklist=str(bl)), "binsize": 100000}
+        R.predict_tools.apply_blacklist(rem2, b)
+        wcx_main.apply_blacklist(str(bl), 100000, a)
+        for key in a:
+            for c in range(nchr):
+                np.testing.assert_array_equal(a[key][c], np.asarray(b[key][c], dtype=float))
+
+
+def test_raw_vector_equals_reference_coverage_normalisation(R):
+    """host half of coverage_normalize_and_mask (predict_tools.py:35-44): pad / truncate per chromosome."""
+    rng = np.random.default_rng(4)
+    bpc = [int(x) for x in rng.integers(5, 40, 24)]
+    sample = {str(c + 1): rng.poisson(20, bpc[c] + int(rng.integers(-3, 4))).astype(np.int32) for c in range(24)}
+    mask = rng.random(sum(bpc)) > 0.2
+    rem = {"bins_per_chr": bpc, "mask": mask}
+    ref_file = {"bins_per_chr": bpc, "mask": mask}
+    want = R.predict_tools.coverage_normalize_and_mask(sample, ref_file, "")
+    raw = predict_tools.raw_vector(sample, bpc)
+    np.testing.assert_allclose((raw / raw.sum())[mask], want, rtol=1e-15)
+
+
+def test_table_writers(R, tmp_path):
+    rng = np.random.default_rng(6)
+    bpc = [int(x) for x in rng.integers(4, 30, 24)]
+    res = _fake_results(rng, bpc, 0.2)
+    for c in range(24):
+        res["results_r"][c] = np.where(res["results_r"][c] > 0, np.log2(np.abs(res["results_r"][c]) + 1e-9), 0.0)
+    segs = []
+    for c in range(24):
+        h = bpc[c] // 2
+        segs.append([c, 0, h, float(rng.normal(0, 4)), float(rng.normal(0, 0.2))])
+        segs.append([c, h, bpc[c], "nan" if c % 5 == 0 else float(rng.normal(0, 8)), float(rng.normal(0, 0.2))])
+    res["results_c"] = segs
+    for beta, gender in ((None, "F"), (0.4, "M")):
+        outs = []
+        for tag, mod in (("ref", R.predict_output), ("got", predict_output)):
+            outid = str(tmp_path / f"{tag}{gender}")
+            rem = {"args": types.SimpleNamespace(outid=outid, beta=beta, zscore=5, regions=None), "binsize": 100000,
+                   "ref_gender": gender, "gender": gender, "n_reads": 123, "bins_per_chr": bpc}
+            r2 = {k: ([np.asarray(x).tolist() for x in v] if tag == "ref" and k != "results_c" else copy.deepcopy(v)) for k, v in res.items()}
+            mod._generate_bins_bed(rem, r2)
+            mod._generate_segments_and_aberrations_bed(rem, r2)
+            outs.append(outid)
+        for sfx in ("_bins.bed", "_segments.bed", "_aberrations.bed"):
+            assert open(outs[0] + sfx).read() == open(outs[1] + sfx).read(), sfx
+    # segment statistics helpers
+    lists = [np.asarray(x).tolist() for x in res["results_r"]]
+    assert overall_tools.get_median_segment_variance(segs, res["results_r"]) == R.overall_tools.get_median_segment_variance(segs, lists)
+    num = [sg for sg in segs if not isinstance(sg[3], str)]  # both raise TypeError on a "nan" z-score
+    assert overall_tools.get_cpa(num, 100000) == R.overall_tools.get_cpa(num, 100000)
+
+
+def test_regions_bed_autosomes(R, tmp_path):
+    """_generate_regions_bed (predict_output.py:86-137) on autosomal regions (the reference raises on X / Y, A.8)."""
+    rng = np.random.default_rng(9)
+    bpc = [int(x) for x in rng.integers(10, 30, 24)]
+    res = _fake_results(rng, bpc, 0.1)
+    reg = tmp_path / "regions.bed"
+    reg.write_text("chr1\t0\t450000\tA\n2\t300000\t99999999\tB\n\nchr3\t500000\t100000\tbad\n")
+    outs = []
+    for tag, mod in (("ref", R.predict_output), ("got", predict_output)):
+        outid = str(tmp_path / tag)
+        rem = {"args": types.SimpleNamespace(outid=outid, regions=str(reg)), "binsize": 100000, "bins_per_chr": bpc}
+        mod._generate_regions_bed(rem, {k: [np.asarray(x) for x in v] for k, v in res.items()})
+        outs.append(outid + "_regions.bed")
+    assert open(outs[0]).read() == open(outs[1]).read()
+
+
+def test_ref_qc_matches_reference(R, tmp_path, caplog):
+    rng = np.random.default_rng(11)
+    ref = {"binsize": 100000, "is_nipt": False, "trained_cutoff": 0.005, "has_female": True, "has_male": True}
+    for sfx, nchr in ((".F", 23), (".M", 24), ("", 22)):
+        per = rng.integers(20, 60, nchr)
+        n = int(per.sum())
+        ref["bins_per_chr" + sfx] = per
+        ref["masked_bins_per_chr" + sfx] = per
+        ref["masked_bins_per_chr_cum" + sfx] = np.cumsum(per)
+        ref["indexes" + sfx] = rng.integers(0, n, (n, 160 if sfx != ".F" else 100)).astype(np.int32)
+        d = np.sort(rng.random((n, ref["indexes" + sfx].shape[1])) * (3 if sfx == ".M" else 1), axis=1)
+        if sfx == ".M":
+            d[int(np.cumsum(per)[22]):] *= 9  # poor chrY
+        ref["distances" + sfx] = d
+    path = str(tmp_path / "ref.npz")
+    np.savez_compressed(path, **ref)
+    with caplog.at_level(logging.INFO):
+        caplog.clear()
+        want = R.ref_qc.qc_reference(path)
+        want_msgs = [r.getMessage() for r in caplog.records]
+        caplog.clear()
+        got = ref_qc.qc_reference(path)
+        got_msgs = [r.getMessage() for r in caplog.records]
+        caplog.clear()
+        got2 = ref_qc.qc_reference(path, ref)
+    assert got == want == got2
+    assert got_msgs == want_msgs
+    for sfx in (".F", ".M"):
+        a = ref_qc.compute_metrics(ref, sfx)
+        b = R.ref_qc._compute_metrics(ref, sfx)
+        assert a == b

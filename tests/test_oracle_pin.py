@@ -67,3 +67,58 @@ def test_predict_pieces_live(R):
         np.testing.assert_allclose(got[1], want[1], rtol=1e-12, equal_nan=True)   # r
         assert np.array_equal(got[2], want[2])                                    # ref sizes
         assert np.isclose(got[3], want[3], rtol=1e-12) and np.isclose(got[4], want[4], rtol=1e-10)
+
+
+def _planted_samples(S, binsize, seed):
+    samples, genders = synth.make_samples(S, binsize, seed=seed, depth=8e6)
+    rng = np.random.default_rng(seed + 1)
+    offs = np.concatenate([[0], np.cumsum([len(samples[0][str(c)]) for c in range(1, 25)])])
+    for b in rng.choice(int(offs[22]), 6, replace=False):  # bins the five components cannot explain
+        c = int(np.searchsorted(offs, b, side="right")) - 1
+        for s in samples:
+            s[str(c + 1)][b - offs[c]] = int(s[str(c + 1)][b - offs[c]] * rng.lognormal(0, 1.2))
+    return samples, genders
+
+
+@pytest.mark.parametrize("S,binsize,seed", [(100, 1_000_000, 41), (24, 5_000_000, 7)])
+def test_prep_chain_live(R, tmp_path, S, binsize, seed):
+    """a1-a3: normalize_and_mask (bit-exact), get_mask, train_pca (np.random.seed pinned, 1e-5 per SURVEY A.3) and
+    the PCA-distance filter INCLUDING the in-place mask edit and the redo (newref_control.py:38-58) against the
+    live reference, A -> F -> M with the mask leaking from pass to pass (main.py:98-137)."""
+    samples, genders = _planted_samples(S, binsize, seed)
+    samples = np.array(samples)
+    for i, s in enumerate(samples):
+        samples[i] = R.overall_tools.gender_correct(s, genders[i])
+    mask_ref, bpc = R.newref_tools.get_mask(samples)
+    mask_o, bpc_o = np_oracle.get_mask(samples)
+    assert np.array_equal(mask_ref, mask_o) and list(bpc) == list(bpc_o)
+    want_nm = R.newref_tools.normalize_and_mask(samples, range(1, 23), mask_ref[: sum(bpc[:22])])
+    assert np.array_equal(np_oracle.normalize_and_mask(samples, range(1, 23), mask_ref[: sum(bpc[:22])]), want_nm)
+    m1, m2 = mask_ref.copy(), mask_ref.copy()
+    g = np.array(genders)
+    removed = 0
+    for gender, sub in (("A", samples), ("F", samples[g == "F"]), ("M", samples[g == "M"])):
+        a = types.SimpleNamespace(prepdatafile=str(tmp_path / "d.npy"), prepfile=str(tmp_path / "p.npz"), binsize=binsize)
+        np.random.seed(3)
+        R.newref_control.tool_newref_prep(a, sub, gender, m1, bpc)
+        want, wc = np.load(a.prepfile), np.load(a.prepdatafile)
+        got = np_oracle.tool_newref_prep(sub, gender, m2, bpc)
+        removed += got["n_removed"]
+        assert np.array_equal(m1, m2)  # the leak into the caller's mask
+        assert np.array_equal(want["mask"], got["mask"])
+        assert np.array_equal(want["masked_bins_per_chr"], got["masked_bins_per_chr"])
+        assert np.array_equal(want["masked_bins_per_chr_cum"], got["masked_bins_per_chr_cum"])
+        np.testing.assert_allclose(got["pca_mean"], want["pca_mean"], rtol=1e-12)
+        np.testing.assert_allclose(got["pca_components"], want["pca_components"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(got["pca_corrected_data"], wc, rtol=1e-5)
+    assert removed > 0  # the filter and the redo were exercised
+
+
+def test_qc_per_bin_stats_live(R):
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, 1000, (500, 40)).astype(np.int32)
+    dist = np.sort(rng.random((500, 40)) * 4, axis=1)
+    want = R.ref_qc._compute_per_bin_stats(idx, dist)
+    got = np_oracle.per_bin_stats(idx, dist)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a, b, rtol=1e-15)

@@ -1,13 +1,16 @@
-"""GPU parity tests of the newref preparation kernels (normalize_and_mask, train_pca, PCA-distance
-filter) against the NumPy oracle; train_pca additionally against the live reference's golden
-where the problem is well conditioned."""
+"""GPU parity tests of the newref preparation chain (normalize_and_mask, train_pca, PCA-distance filter with the
+in-place mask edit and the redo): the kernels against the NumPy oracle (which tests/test_oracle_pin.py pins to the
+live reference) and `newref_control.tool_newref_prep` against the golden written by the live reference's own
+tool_newref_prep (tests/golden/prep.npz, A -> F -> M with the leaking mask)."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 from oracle import np_oracle  # noqa: E402
-from wisecondorx_b200 import newref_tools, synth  # noqa: E402
+from wisecondorx_b200 import newref_control, newref_tools, synth  # noqa: E402
 
 
 def test_normalize_and_mask_bit_exact():
@@ -71,3 +74,57 @@ def test_device_resident_prep_equals_host_functions():
         eng.load(corrected, mper, np.cumsum(mper))
         i2, d2 = eng.topk(0, masked.shape[0], 50)
         assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+
+
+def test_tool_newref_prep_matches_reference_golden(golden_dir):
+    """a1-a3 through the product path: masks / bin counts exact, PCA model and corrected matrix within 1e-5 of the
+    reference's sklearn fit (np.random.seed pinned when the golden was made)."""
+    g = np.load(os.path.join(golden_dir, "prep.npz"))
+    offs = np.concatenate([[0], np.cumsum(g["lens"])])
+    genders = [str(x) for x in g["genders"]]
+    samples = []
+    for i in range(g["counts"].shape[1]):
+        s = {str(c + 1): g["counts"][offs[c]:offs[c + 1], i].copy() for c in range(24)}
+        if genders[i] == "M":  # gender_correct, main.py:95-97
+            s["23"], s["24"] = s["23"] * 2, s["24"] * 2
+        samples.append(s)
+    bpc = [int(x) for x in g["bins_per_chr"]]
+    total_mask = g["total_mask"].copy()
+    for gender in ("A", "F", "M"):
+        sub = [s for s, gg in zip(samples, genders) if gender == "A" or gg == gender]
+        prep = newref_control.tool_newref_prep(sub, gender, total_mask, bpc)
+        assert np.array_equal(prep["mask"], g[gender + "_mask"])
+        assert np.array_equal(total_mask, g[gender + "_total_mask_after"])  # the edit leaked into the caller's mask
+        assert np.array_equal(prep["masked_bins_per_chr"], g[gender + "_masked_bins_per_chr"])
+        assert np.array_equal(prep["masked_bins_per_chr_cum"], g[gender + "_masked_bins_per_chr_cum"])
+        np.testing.assert_allclose(prep["pca_mean"], g[gender + "_pca_mean"], rtol=1e-12)
+        np.testing.assert_allclose(prep["pca_components"], g[gender + "_pca_components"], rtol=0, atol=1e-5)
+        corrected = prep["pca_corrected_data"].fetch("corrected")
+        np.testing.assert_allclose(corrected[::5], g[gender + "_corrected_rows"], rtol=1e-5)
+
+
+def test_train_pca_rank_deficient_pass():
+    """A gonosomal pass may run with exactly 5 samples (main.py:104,119): the centred matrix has rank 4, so the
+    fifth component must not be divided by a round-off singular value (it used to reach ~1e130 and turn every
+    predicted ratio into ~1e-257).  Rows are unit norm and mutually orthogonal, the correction equals the rank-4
+    exact PCA and a projection of a new sample stays finite."""
+    rng = np.random.default_rng(5)
+    n, s = 4000, 5
+    prof = rng.gamma(20.0, 1 / 20.0, n) / n
+    x = np.stack([prof * (1 + 0.05 * rng.standard_normal(n)) for _ in range(s)], axis=1)
+    corrected, pca = newref_tools.train_pca(x)
+    assert pca.components_.shape == (5, n) and np.isfinite(pca.components_).all()
+    gram = pca.components_ @ pca.components_.T
+    np.testing.assert_allclose(gram, np.eye(5), atol=1e-9)
+    want_c, comps4, mean = np_oracle.train_pca(x, 4)
+    np.testing.assert_allclose(corrected, want_c, rtol=1e-9)
+    np.testing.assert_allclose(pca.components_[:4], comps4, rtol=0, atol=1e-8)
+    new = prof * (1 + 0.05 * rng.standard_normal(n))
+    rec = (new - pca.mean_) @ pca.components_.T @ pca.components_ + pca.mean_
+    assert np.isfinite(new / rec).all() and np.abs(new / rec).max() < 10
+    dp = newref_tools.DevicePrep(0)
+    # the device-resident chain takes the same path
+    counts = np.round(x * 4e9).astype(np.int32)
+    dp.normalize_and_mask(counts, np.ones(n, dtype=bool))
+    pca2 = dp.train_pca()
+    assert np.isfinite(pca2.components_).all() and np.allclose(np.linalg.norm(pca2.components_, axis=1), 1.0)

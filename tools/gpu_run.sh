@@ -1,0 +1,28 @@
+#!/bin/bash
+# One GPU-box session: tests, smoke, bench, launch list, optional full captures.  Usage: tools/gpu_run.sh TAG [steps...]
+# steps: tests smoke bench launches ncu_newref ncu_predict bench2 (default: tests smoke bench)
+mkdir -p gpurun_out
+TAG=${1:-r02a}; shift
+STEPS=${@:-tests smoke bench}
+for S in $STEPS; do
+  case $S in
+    tests) echo "=== pytest -m gpu"; timeout 1200 python -m pytest tests -m gpu -q -x --tb=short 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.txt ;;
+    smoke) echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1 | cut -c1-300 ;;
+    bench) echo "=== bench"; timeout 900 python bench.py 2>gpurun_out/${TAG}_bench.err | tail -1 | tee gpurun_out/${TAG}_bench.json | cut -c1-1500 ;;
+    benchref) echo "=== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>>gpurun_out/${TAG}_bench.err | tail -1 | tee gpurun_out/${TAG}_bench_reference.json | cut -c1-600 ;;
+    launches) echo "=== ncu launch list"
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1
+      tail -1 gpurun_out/${TAG}_launches.log | cut -c1-300 ;;
+    ncu_newref)
+      for K in dist_topk_tc rerank null_ratios; do
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -f -o gpurun_out/${TAG}_prof_$K python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-predict > gpurun_out/${TAG}_prof_$K.log 2>&1
+        python tools/ncu_summary.py gpurun_out/${TAG}_prof_$K.ncu-rep > gpurun_out/${TAG}_ncu_$K.txt 2>&1
+      done ;;
+    ncu_predict)
+      timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:normalize_pass|nanmedian|select_|weights_kernel|cutoff_partial|segment_z|cbs_prepare|cbs_tailp|cbs_maxarc|coverage|project_' -c 70 -f -o gpurun_out/${TAG}_prof_predict python tools/predict_profile.py > gpurun_out/${TAG}_prof_predict.log 2>&1
+      python tools/ncu_summary.py gpurun_out/${TAG}_prof_predict.ncu-rep > gpurun_out/${TAG}_ncu_predict.txt 2>&1
+      tail -3 gpurun_out/${TAG}_prof_predict.log | cut -c1-300 ;;
+    *) echo "=== custom: $S"; timeout 1200 bash -c "$S" 2>&1 | tail -30 ;;
+  esac
+done
+ls -la gpurun_out | tail -20

@@ -17,7 +17,7 @@ import numpy as np
 
 import time
 
-from . import cbs, newref_control, npz_io, predict_control, predict_output, predict_tools
+from . import cbs, newref_control, npz_io, predict_control, predict_output, predict_tools, ref_qc
 from .overall_tools import gender_correct, scale_sample
 
 
@@ -78,6 +78,11 @@ def tool_newref(args):
     if args.yfrac is not None and (args.yfrac < 0 or args.yfrac > 1):
         logging.critical("Parameter --yfrac should be a positive number lower than or equal to 1")
         sys.exit()
+    if getattr(args, "plotyfrac", None) is not None:
+        # the reference draws the Y-fraction histogram with matplotlib and exits (newref_tools.py:44-58)
+        logging.critical("--plotyfrac needs the reference's matplotlib plot and is not part of the accelerated path; "
+                         "run the reference's `WisecondorX newref --plotyfrac` for the histogram")
+        sys.exit()
     samples = []
     timings = {}
     t0 = time.perf_counter()
@@ -136,8 +141,12 @@ def tool_newref(args):
         else:
             logging.warning("Provide at least 5 male samples to enable normalization of male gonosomes.")
     t0 = time.perf_counter()
-    newref_control.tool_newref_merge(args.outfile, results, args.binsize, args.nipt, trained_cutoff, writer)
+    final_ref = newref_control.tool_newref_merge(args.outfile, results, args.binsize, args.nipt, trained_cutoff, writer)
     timings["write_reference"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    logging.info("Running QC on the newly created reference...")
+    ref_qc.qc_reference(args.outfile, final_ref)  # reference main.py:134-135 (ref_qc.py:140); arrays still in memory
+    timings["qc_reference"] = time.perf_counter() - t0
     logging.info("Stage wall-clock [s]: " + ", ".join("{} {:.2f}".format(k, v) for k, v in timings.items()))
     logging.info("Finished creating reference")
     return timings
@@ -206,6 +215,10 @@ def tool_test(args):
         sys.exit()
     if args.alpha <= 0 or args.alpha > 1:
         logging.critical("Parameter --alpha should be a strictly positive number lower than or equal to 1")
+        sys.exit()
+    if args.plot and not args.bed:
+        logging.critical("--plot needs the reference's R plotter and is not part of the accelerated path; add --bed "
+                         "(the tables are written here) or run the reference's `WisecondorX predict --plot`")
         sys.exit()
     logging.info("Importing data ...")
     # inflate the reference once (the reference re-inflates on every access)

@@ -163,6 +163,48 @@ class _PCAModel:
         self.n_components_ = components.shape[0]
 
 
+def _pca_spectrum(gram, pcacomp):
+    """Top eigenpairs of the S x S Gram matrix of the centred data -> (u [S, n_eff], sigma [n_eff], lam [pcacomp],
+    n_eff).  The centred matrix has rank <= S - 1: with S <= pcacomp samples (the reference allows gonosomal passes
+    with exactly 5, main.py:104,119) the trailing eigenvalues are round-off, and dividing by their square root would
+    blow the stored components up to ~1e130.  Only the numerically non-zero part of the spectrum (relative 1e-12) is
+    sent to the device; _finish_components pads the rest."""
+    w, u = np.linalg.eigh(gram)
+    order = np.argsort(w)[::-1][:pcacomp]
+    lam = np.clip(w[order], 0.0, None)
+    lam_full = np.zeros(pcacomp)
+    lam_full[: len(lam)] = lam
+    n_eff = int(np.sum(lam > 1e-12 * max(lam[0], 1e-300))) if len(lam) else 0
+    n_eff = max(1, min(n_eff, gram.shape[0] - 1 if gram.shape[0] > 1 else 1))
+    lam_full[n_eff:] = 0.0
+    return (np.ascontiguousarray(u[:, order[:n_eff]]), np.ascontiguousarray(np.sqrt(np.clip(lam[:n_eff], 1e-300, None))),
+            lam_full, n_eff)
+
+
+def _finish_components(comps, pcacomp):
+    """sklearn's sign convention (svd_flip, u_based_decision=False: largest |entry| of each row positive) and, for a
+    rank-deficient fit, unit-norm rows orthogonal to the fitted ones in place of the null-space vectors LAPACK would
+    return (they reconstruct nothing of the training data; sklearn's are equally arbitrary but also unit norm)."""
+    n_eff, n = comps.shape
+    piv = np.argmax(np.abs(comps), axis=1)
+    sgn = np.sign(comps[np.arange(n_eff), piv])
+    comps = comps * np.where(sgn == 0, 1.0, sgn)[:, None]
+    if n_eff < pcacomp:
+        rng = np.random.default_rng(0)
+        rows = [comps]
+        basis = comps
+        for _ in range(pcacomp - n_eff):
+            v = rng.standard_normal(n)
+            for _ in range(2):  # two Gram-Schmidt sweeps
+                v -= basis.T @ (basis @ v)
+            v /= np.linalg.norm(v)
+            v *= np.sign(v[np.argmax(np.abs(v))])
+            rows.append(v[None, :])
+            basis = np.concatenate([basis, v[None, :]])
+        comps = np.concatenate(rows)
+    return np.ascontiguousarray(comps)
+
+
 def stack_counts(samples, chrs):
     """int32 [bins_total, S]: per-chromosome read counts of every sample, zero padded to the longest
     sample (host half of normalize_and_mask, newref_tools.py:114-122)."""
@@ -202,19 +244,12 @@ def train_pca(ref_data, pcacomp=5, device: int = 0, keep_on_device: bool = False
     mean = np.empty(n, dtype=np.float64)
     gram = np.empty((s, s), dtype=np.float64)
     _lib.check(L.wcx_pca_gram(ctx.handle, _ptr(x), n, s, 0, _ptr(mean), _ptr(gram)))
-    w, u = np.linalg.eigh(gram)
-    order = np.argsort(w)[::-1][:pcacomp]
-    lam = np.clip(w[order], 1e-300, None)
-    u = np.ascontiguousarray(u[:, order])
-    sigma = np.ascontiguousarray(np.sqrt(lam))
-    comps = np.empty((pcacomp, n), dtype=np.float64)
+    u, sigma, lam, n_eff = _pca_spectrum(gram, pcacomp)
+    comps = np.empty((n_eff, n), dtype=np.float64)
     corrected = None if keep_on_device else np.empty((n, s), dtype=np.float64)
-    _lib.check(L.wcx_pca_apply(ctx.handle, _ptr(u), _ptr(sigma), pcacomp, _ptr(comps),
+    _lib.check(L.wcx_pca_apply(ctx.handle, _ptr(u), _ptr(sigma), n_eff, _ptr(comps),
                                None if keep_on_device else _ptr(corrected), 0))
-    # sklearn's sign convention (svd_flip, u_based_decision=False): largest |entry| of each row positive
-    piv = np.argmax(np.abs(comps), axis=1)
-    comps *= np.sign(comps[np.arange(pcacomp), piv])[:, None]
-    return corrected, _PCAModel(comps, mean, lam / max(s - 1, 1))
+    return corrected, _PCAModel(_finish_components(comps, pcacomp), mean, lam / max(s - 1, 1))
 
 
 def pca_distance(corrected=None, shape=None, device: int = 0):
@@ -263,16 +298,10 @@ class DevicePrep:
         mean = np.empty(n, dtype=np.float64)
         gram = np.empty((s, s), dtype=np.float64)
         _lib.check(L.wcx_pca_gram(self.ctx.handle, None, n, s, 1, _ptr(mean), _ptr(gram)))
-        w, u = np.linalg.eigh(gram)
-        order = np.argsort(w)[::-1][:pcacomp]
-        lam = np.clip(w[order], 1e-300, None)
-        u = np.ascontiguousarray(u[:, order])
-        sigma = np.ascontiguousarray(np.sqrt(lam))
-        comps = np.empty((pcacomp, n), dtype=np.float64)
-        _lib.check(L.wcx_pca_apply(self.ctx.handle, _ptr(u), _ptr(sigma), pcacomp, _ptr(comps), None, 0))
-        piv = np.argmax(np.abs(comps), axis=1)
-        comps *= np.sign(comps[np.arange(pcacomp), piv])[:, None]
-        return _PCAModel(comps, mean, lam / max(s - 1, 1))
+        u, sigma, lam, n_eff = _pca_spectrum(gram, pcacomp)
+        comps = np.empty((n_eff, n), dtype=np.float64)
+        _lib.check(L.wcx_pca_apply(self.ctx.handle, _ptr(u), _ptr(sigma), n_eff, _ptr(comps), None, 0))
+        return _PCAModel(_finish_components(comps, pcacomp), mean, lam / max(s - 1, 1))
 
     def pca_distance(self):
         return pca_distance(None, shape=self.shape, device=self.device)

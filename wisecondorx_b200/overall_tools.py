@@ -22,8 +22,7 @@ def scale_sample(sample, from_size, to_size):
         data = np.asarray(data)
         new_len = int(np.ceil(len(data) / float(scale)))
         if new_len == 0:
-            out[name] = np.zeros(0, dtype=np.int32)
-            continue
+            continue  # the reference assigns inside its per-bin loop (:38-39): an empty chromosome leaves no key
         out[name] = np.add.reduceat(data, np.arange(0, len(data), scale)).astype(np.int32)
     return out
 

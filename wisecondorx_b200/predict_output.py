@@ -19,6 +19,40 @@ def generate_output_tables(rem_input, results, engine=None):
     _generate_bins_bed(rem_input, results)
     _generate_segments_and_aberrations_bed(rem_input, results)
     _generate_chr_statistics_file(rem_input, results, engine)
+    if getattr(rem_input["args"], "regions", None) is not None:
+        _generate_regions_bed(rem_input, results)
+
+
+def _generate_regions_bed(rem_input, results):
+    """Weighted mean ratio / z-score of user-given regions (reference predict_output.py:86-137).  The reference maps
+    chrX / chrY to indexes 21 / 22 and then overrides the result with int(name) (a ValueError for X / Y, SURVEY.md
+    A.8); here X / Y address chromosomes 23 / 24 of the results, everything else is as in the reference."""
+    import re
+    binsize = rem_input["binsize"]
+    with open("{}_regions.bed".format(rem_input["args"].outid), "w") as fh, open(rem_input["args"].regions) as rh:
+        fh.write("chr\tstart\tend\tname\tratio\tzscore\n")
+        for region in (line.strip().split("\t") for line in rh if line.strip() != ""):
+            assert len(region) >= 4, "Regions file must have at least 4 columns: chr, start, end, name"
+            chr_name, start, end, name = region[:4]
+            short = re.sub("chr", "", chr_name)
+            c = {"X": 22, "Y": 23}.get(short)
+            c = int(short) - 1 if c is None else c
+            start_bin, end_bin = int(start) // binsize, int(end) // binsize
+            if c >= len(results["results_r"]):
+                fh.write("Skipping invalid region: {}\n".format("\t".join(region)))
+                continue
+            end_bin = min(end_bin, int(rem_input["bins_per_chr"][c]) - 1)
+            if start_bin < 0 or end_bin < 0 or start_bin > end_bin:
+                fh.write("Skipping invalid region: {}\n".format("\t".join(region)))
+                continue
+            r = np.asarray(results["results_r"][c][start_bin:end_bin + 1], dtype=float)
+            w = np.asarray(results["results_w"][c][start_bin:end_bin + 1], dtype=float)
+            z = np.asarray(results["results_z"][c][start_bin:end_bin + 1], dtype=float)
+            if len(r) == 0:
+                fh.write("Skipping region with no bins: {}\n".format("\t".join(region)))
+                continue
+            fh.write("\t".join(str(x) for x in [chr_name, start, end, name, _fmt(np.ma.average(r, weights=w)),
+                                                _fmt(np.ma.average(z, weights=w))]) + "\n")
 
 
 def _generate_bins_bed(rem_input, results):
