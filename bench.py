@@ -158,44 +158,117 @@ def cpu_reference_sample(x, per, cum, target_seconds=20.0, check=None, max_windo
     return out
 
 
-def predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, device, batches=(1, 96)):
-    """BASELINE configs 4 / 5 (reported beside the headline metric): `normalize` (coverage + PCA projection +
-    3 within-sample passes) and the CUDA CBS for 1 and 96 test samples against the reference just built."""
+def cli_and_predict_extras(device, n_train=500, binsize=15000, batch=96, cpu_baseline=True, batches=None):
+    """The rest of the BASELINE metric, measured in the same run on the same box:
+
+    * `cli`: wall-clock of the drop-in command line at config 3 -- `WisecondorX newref` (A + F + M passes, .npz in,
+      reference .npz out) on 500 synthetic sample files at 15 kb, then `WisecondorX predict --bed` of one more sample
+      against the reference it wrote.  The sample files are generated and written outside the timed regions.
+    * `predict` (configs 4 / 5): the whole numeric flow of predict (predict_control.predict_batch: gender, both
+      `normalize` calls, assembly, log transform, CBS through exec_cbs, segment z-scores) for 1 and 96 samples against
+      that reference, with the device time of every kernel family, a roofline entry for the normalisation passes and
+      the CPU baseline: the NumPy restatement of `normalize` x2 + `get_z_score` (oracle/np_oracle.py, kind "port",
+      pinned to the live reference by tests/test_oracle_pin.py) on one sample, one core, at the same size."""
+    import shutil
+    import tempfile
     import types
-    from wisecondorx_b200 import cbs, predict_control, predict_tools
-    n, s = x.shape
-    rng = np.random.default_rng(99)
-    comps = np.linalg.qr(rng.standard_normal((n, 5)))[0].T.copy()
-    ref = {"indexes": idx_dev.cpu().numpy(), "distances": dist_dev.cpu().numpy(), "masked_bins_per_chr": per,
-           "masked_bins_per_chr_cum": cum, "pca_components": comps, "pca_mean": np.full(n, 1.0 / n),
-           "mask": np.ones(n, dtype=bool), "bins_per_chr": per}
-    offs = np.concatenate([[0], cum]).astype(int)
-
-    def sample(i):
-        lam = 60.0 * np.clip(x[:, i % s], 0, None)
-        lam[offs[4] + 2000: offs[4] + 2400] *= 1.5  # planted 6 Mb gain on chr5
-        c = rng.poisson(lam).astype(np.int32)
-        return {str(k + 1): c[offs[k]:offs[k + 1]] for k in range(22)}
-
-    args = types.SimpleNamespace(maskrepeats=5)
-    pe = predict_tools.PredictEngine(device, eng.ctx)
+    from concurrent.futures import ThreadPoolExecutor
+    from wisecondorx_b200 import _lib, main as wmain, npz_io, predict_control, predict_tools, synth
+    batches = batches or (1, batch)
+    d = tempfile.mkdtemp(prefix="wcx_bench_")
     out = {}
-    for b in batches:
-        samples = [sample(i) for i in range(b)]
-        predict_control.normalize_batch(args, samples[:1], ref, "A", pe)  # load the reference arrays once, warm up
+    try:
         t0 = time.perf_counter()
-        r, z, w, nref, m_lr, m_z = predict_control.normalize_batch(args, samples, ref, "A", pe)
-        t_norm = time.perf_counter() - t0
-        sm = pe.stage_ms()
-        # CBS over all chromosomes of all samples in one batched call
+        samples, genders = synth.make_samples(n_train + batch, binsize, seed=3, cnv=[(n_train, 5, 2000, 2400, 1.5)])
+        paths = [os.path.join(d, "s%04d.npz" % i) for i in range(n_train + 1)]
+        with ThreadPoolExecutor(min(32, len(os.sched_getaffinity(0)))) as pool:
+            list(pool.map(lambda i: np.savez_compressed(paths[i], binsize=binsize, sample=samples[i], quality={}), range(n_train + 1)))
+        t_gen = time.perf_counter() - t0
+        ref = os.path.join(d, "reference.npz")
+        parser = wmain.build_parser()
         t0 = time.perf_counter()
-        ends = predict_control.segment_batch(r, w, nref, m_lr, offs, 150, 1e-4, 10000, 1, eng.ctx)
-        t_cbs = time.perf_counter() - t0
-        nseg = sum(len(e) for e in ends)
-        out[f"batch{b}"] = {"normalize_wall_ms": t_norm * 1e3, "normalize_kernels_ms": sm["coverage_project"] + sm["normalize_repeat"],
-                            "cbs_wall_ms": t_cbs * 1e3, "cbs_kernels_ms": _cbs_ms(eng), "segments": nseg,
-                            "cbs_stats": cbs.cbs_stats(eng.ctx)}
+        a = parser.parse_args(["newref"] + paths[:n_train] + [ref, "--binsize", str(binsize), "--yfrac", "0.006", "--device", str(device)])
+        st_new = a.func(a)
+        t_newref = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        a = parser.parse_args(["predict", paths[n_train], ref, os.path.join(d, "out"), "--bed", "--seed", "1", "--device", str(device)])
+        res = a.func(a)
+        t_predict = time.perf_counter() - t0
+        ab = [l.split("\t") for l in open(os.path.join(d, "out_aberrations.bed")).read().splitlines()[1:]]
+        out["cli"] = {"config": "500 samples @ 15 kb (A + F + M passes), refsize 300; predict of 1 sample with a planted chr5 gain",
+                      "generate_and_write_inputs_s": round(t_gen, 2), "newref_wall_s": round(t_newref, 2),
+                      "newref_stages_s": {k: round(v, 3) for k, v in (st_new or {}).items()},
+                      "reference_npz_mb": os.path.getsize(ref) >> 20, "predict_wall_s": round(t_predict, 2),
+                      "predict_stages_s": {k: round(v, 3) for k, v in res.get("timings", {}).items()},
+                      "predict_segments": len(res["results_c"]),
+                      "planted_gain_found": any(x[0] == "5" and x[5] == "gain" for x in ab)}
+        # ---- predict batches through the library flow
+        ref_file = npz_io.load_npz(ref)
+        eng = predict_tools.PredictEngine(device)
+        args = types.SimpleNamespace(maskrepeats=5, minrefbins=150, alpha=1e-4, seed=1, gender=None, blacklist=None, zscore=5, beta=None)
+        tests = samples[n_train:]
+        predict_control.predict_batch(args, tests[:1], [binsize], ref_file, eng)  # reference arrays to the device, warm-up
+        n_a = int(ref_file["masked_bins_per_chr_cum"][-1])
+        k = int(ref_file["indexes"].shape[1])
+        pred = {}
+        for b in batches:
+            eng.ctx.__dict__["kernel_ms_acc"] = {}
+            tim = {}
+            t0 = time.perf_counter()
+            outs = predict_control.predict_batch(args, tests[:b], [binsize] * b, ref_file, eng, tim)
+            wall = time.perf_counter() - t0
+            acc = dict(eng.ctx.__dict__["kernel_ms_acc"])
+            nk = acc.get("coverage_project", 0) + acc.get("gather_list", 0) + acc.get("passes", 0) + acc.get("medians", 0)
+            pred[f"batch{b}"] = {"wall_ms": wall * 1e3, "normalize_and_assemble_wall_ms": tim["normalize_and_assemble"] * 1e3,
+                                 "cbs_and_segment_z_wall_ms": tim["cbs_and_segment_z"] * 1e3, "normalize_kernels_ms": nk,
+                                 "cbs_kernels_ms": acc.get("cbs", 0.0), "segment_z_kernels_ms": acc.get("segment_z", 0.0),
+                                 "kernels_ms": {kk: round(v, 3) for kk, v in acc.items()},
+                                 "segments": int(sum(len(o[1]["results_c"]) for o in outs)), "cbs_stats": cbs_stats(eng)}
+        # roofline of the dominant predict kernel family: the three passes of the AUTOSOMAL normalize of one sample,
+        # algorithmic bytes per SURVEY.md 8(d): 3 * N * k * (4 + 8) + 3 * 4 * N * 8
+        eng.ctx.__dict__["kernel_ms_acc"] = {}
+        predict_control.normalize_batch(args, [predict_control.resolve_genders(args, dict(tests[0]), ref_file)[0]], ref_file, "A", eng)
+        pm = eng.ctx.__dict__["kernel_ms_acc"]
+        bytes_k9 = 3.0 * n_a * k * 12 + 3.0 * 4 * n_a * 8
+        peaks = load_peaks()
+        ach = bytes_k9 / (pm["passes"] * 1e-3) / 1e9
+        pred["roofline"] = {"bound": "hbm", "kernel": "normalize_pass_kernel x3 (autosomal normalize, batch 1)", "achieved": ach,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "kernel_ms": pm["passes"],
+                            "algorithmic_bytes": bytes_k9, "medians_ms": pm["medians"], "coverage_project_ms": pm["coverage_project"],
+                            "note": "bytes_K9 of SURVEY.md 8(d); the kernels read a third of it (4-byte gather lists resolved once per "
+                                    "(reference, cutoff) instead of idx + dist rows in every pass)",
+                            "peak_src": peaks["src"] + ": hbm_gbs"}
+        if cpu_baseline:
+            pred["cpu_baseline"] = predict_cpu_baseline(tests[0], ref_file, outs[0] if batches[-1] == 1 else None, args)
+        out["predict"] = pred
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
     return out
+
+
+def cbs_stats(eng):
+    from wisecondorx_b200 import cbs
+    return cbs.cbs_stats(eng.ctx)
+
+
+def predict_cpu_baseline(sample, ref_file, gpu_out, args):
+    """The reference's predict numeric path on the host: normalize (predict_control.py:21-39) for the autosomes and the
+    gonosomes + get_z_score (overall_tools.py:88-119) over whole-chromosome segments, restated in NumPy
+    (oracle/np_oracle.py), one sample, one core, at 15 kb against the reference the GPU just built.  CBS is excluded on
+    the CPU side (R / DNAcopy are not installed)."""
+    from oracle import np_oracle
+    from wisecondorx_b200 import predict_control
+    s2, gender, rg = predict_control.resolve_genders(args, dict(sample), ref_file)
+    t0 = time.perf_counter()
+    aut = np_oracle.normalize(s2, ref_file, "A", args.maskrepeats)
+    t_a = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    gon = np_oracle.normalize(s2, ref_file, rg, args.maskrepeats)
+    t_g = time.perf_counter() - t0
+    return {"value": t_a + t_g, "unit": "s per sample (normalize x2)", "cores": 1, "kind": "port",
+            "normalize_autosomes_s": t_a, "normalize_gonosomes_s": t_g,
+            "sample": "np_oracle.normalize for the autosomal and the gonosomal reference of one 15 kb sample (all bins), "
+                      "NumPy single process; CBS excluded (no R)"}
 
 
 def predict_sharded_extras(eng, x, per, cum, idx_full, dist_full, device, rank, world):
@@ -297,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
         if args.unfused:
             eng.topk(rb, re, k, kernel=args.kernel, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr()))
             eng.null_ratios(rb, re, k, ids, device_out=nr_dev.data_ptr())
-        else:  # one C-ABI call: sweep, then re-rank with the null ratios fused into it
+        else:  # one C-ABI call: sweep, then re-rank blocks with the null-ratio kernels of finished blocks on a side stream
             eng.reference(rb, re, k, ids, kernel=args.kernel, device_out=(idx_dev.data_ptr(), dist_dev.data_ptr(), nr_dev.data_ptr()))
 
     def barrier():
@@ -330,6 +403,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item()), clocks, extra
 
     launches0 = eng.stats()["launches"]
+
     stage_acc = {"sweep": 0.0, "rerank": 0.0, "exact_rows": 0.0, "null_ratios": 0.0}
 
     def step_resident_timed():
@@ -416,6 +490,7 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    idx_host, dist_host, nr_host = idx_dev.cpu().numpy(), dist_dev.cpu().numpy(), nr_dev.cpu().numpy()
     peaks = load_peaks()
     traffic = None
     try:
@@ -460,12 +535,12 @@ def run_ours(args, rank, world, local_rank):
         "exact_fallback_rows": st["exact_fallback_rows"],
     }
     if world == 1 and not args.no_predict:
-        out["predict"] = predict_extras(eng, x, per, cum, idx_dev, dist_dev, nr_dev, local_rank)
+        out.update(cli_and_predict_extras(local_rank, cpu_baseline=not args.no_cpu_baseline))
     if world > 1 and predict_sharded is not None:
         out["predict"] = {"batch96_sharded": predict_sharded}
     # parity of THIS run's result at THIS configuration: the oracle's rows against the GPU arrays (the CPU baseline's
     # timed windows double as the parity sample; without the baseline leg a short sample is still checked)
-    check = (rb, idx_dev.cpu().numpy(), dist_dev.cpu().numpy(), nr_dev.cpu().numpy())
+    check = (rb, idx_host, dist_host, nr_host)
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_sample(x, per, cum, args.cpu_seconds, check=check)
     else:

@@ -43,6 +43,11 @@ void wcx_destroy(wcx_ctx* ctx);
 /* Issue subsequent work on `cuda_stream` (a cudaStream_t); NULL restores the context's own stream. */
 int wcx_set_stream(wcx_ctx* ctx, void* cuda_stream);
 int wcx_sync(wcx_ctx* ctx);
+/* Page-locked host memory (cudaHostAlloc) for buffers that cross PCIe in every call: every entry point accepts
+ * ordinary host pointers too, but copies from / to pageable memory are staged by the driver at a fraction of the
+ * link rate.  The host mirror (wisecondorx_b200/_lib.py PinnedPool) hands these out as NumPy arrays. */
+int wcx_host_alloc(uint64_t bytes, void** out);
+int wcx_host_free(void* p);
 
 /* ---- newref ------------------------------------------------------------------------------
  * Replaces get_reference (newref_tools.py:155-224): get_ref_for_bins (:255-278) and the
@@ -72,11 +77,13 @@ int wcx_newref_null_ratios(wcx_ctx* ctx, const int32_t* idx, int32_t idx_on_devi
                            int64_t row_end, int32_t k, const int32_t* sample_ids, int32_t m,
                            double* out, int32_t out_on_device);
 
-/* Top-k and null ratios of rows [row_begin, row_end) in one pass over the loaded matrix -- the body of
- * get_reference (newref_tools.py:176-224) after the matrix is resident.  The null ratios of a row are computed by
- * the same CTA that finalises its indexes (fused into the re-rank kernel) when ref_size <= 320; with host outputs
- * the rows are processed in blocks and the D2H copy of a finished block overlaps the next one.  m == 0 skips the
- * null ratios.  Outputs as wcx_newref_topk / wcx_newref_null_ratios. */
+/* Top-k and null ratios of rows [row_begin, row_end) in one call -- the body of get_reference
+ * (newref_tools.py:176-224) after the matrix is resident.  One sweep over the candidate axis nominates candidates for
+ * every row; the rows then go through the exact re-rank in blocks, the null-ratio kernels of a finished block run on
+ * a second stream next to the re-rank of the following block, and with host outputs the D2H copy of a finished block
+ * overlaps the kernels of the next one.  m == 0 skips the null ratios.  Outputs as wcx_newref_topk /
+ * wcx_newref_null_ratios.  ref_size: 1..400 on the tensor-core path; 401..512 is served by the brute-force float64
+ * row kernel (WCX_KERNEL_EXACT) -- same results, much slower. */
 int wcx_newref_reference(wcx_ctx* ctx, int64_t row_begin, int64_t row_end, int32_t k, int32_t kernel,
                          const int32_t* sample_ids, int32_t m, int32_t* idx_out, double* dist_out,
                          double* null_out, int32_t out_on_device);
@@ -164,13 +171,16 @@ int wcx_predict_normalize(wcx_ctx* ctx, int32_t set_id, const double* raw, int32
 /* get_z_score: nr = null ratios float64 [n_masked, m]; inflate_pos int32 [bins_total] = row of nr
  * for each unmasked bin or -1; r, w float64 [bins_total] = post-processed log2 ratios (0 = no
  * data) and weights; segments as [start, end) offsets into the concatenated bin axis with their
- * ratio seg_r.  z_out float64 [nseg]; NaN where the reference returns the string "nan". */
+ * ratio seg_r.  z_out float64 [nseg]; NaN where the reference returns the string "nan".  nr == NULL reuses the null
+ * ratios uploaded by the previous call (same n_masked and m): they belong to the reference, not to the sample. */
 int wcx_segment_zscore(wcx_ctx* ctx, const double* nr, int64_t n_masked, int32_t m,
                        const int32_t* inflate_pos, const double* r, const double* w, int64_t bins_total,
                        const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out);
-/* Device milliseconds of the last predict calls: out[0] = coverage + projection, out[1] = the
- * three normalisation passes + medians, out[2] = segment z-score, out[3] = last wcx_cbs_segment. */
-int wcx_predict_stage_ms(wcx_ctx* ctx, double* out4);
+/* Device milliseconds of the last predict calls: out[0] = coverage + projection, out[1] = gather lists + the
+ * three normalisation passes + medians, out[2] = segment z-score, out[3] = last wcx_cbs_segment, out[4] = gather-list
+ * build (only when the (reference set, cutoff) changed), out[5] = the three passes, out[6] = the two medians,
+ * out[7] reserved. */
+int wcx_predict_stage_ms(wcx_ctx* ctx, double* out8);
 
 /* ---- CBS -----------------------------------------------------------------------------------
  * Replaces the R bridge: exec_cbs (predict_tools.py:242-263) -> exec_R (overall_tools.py:65-80) ->

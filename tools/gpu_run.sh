@@ -19,10 +19,11 @@ for S in $STEPS; do
         python tools/ncu_summary.py gpurun_out/${TAG}_prof_$K.ncu-rep > gpurun_out/${TAG}_ncu_$K.txt 2>&1
       done ;;
     ncu_predict)
-      timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:normalize_pass|nanmedian|select_|weights_kernel|cutoff_partial|segment_z|cbs_prepare|cbs_tailp|cbs_maxarc|coverage|project_' -c 70 -f -o gpurun_out/${TAG}_prof_predict python tools/predict_profile.py > gpurun_out/${TAG}_prof_predict.log 2>&1
+      timeout 900 ncu --set full --clock-control none -k 'regex:normalize_pass|nanmedian|radix_|weights_kernel|cutoff_partial|segment_z|cbs_prepare|cbs_tailp|cbs_maxarc|coverage_gather|project_apply' -c 48 -f -o gpurun_out/${TAG}_prof_predict python tools/predict_profile.py > gpurun_out/${TAG}_prof_predict.log 2>&1
       python tools/ncu_summary.py gpurun_out/${TAG}_prof_predict.ncu-rep > gpurun_out/${TAG}_ncu_predict.txt 2>&1
+      [ $(stat -c %s gpurun_out/${TAG}_prof_predict.ncu-rep) -gt 30000000 ] && rm -f gpurun_out/${TAG}_prof_predict.ncu-rep  # gpurun_out is capped at 64 MiB
       tail -3 gpurun_out/${TAG}_prof_predict.log | cut -c1-300 ;;
     *) echo "=== custom: $S"; timeout 1200 bash -c "$S" 2>&1 | tail -30 ;;
   esac
 done
-ls -la gpurun_out | tail -20
+du -sh gpurun_out; ls -la gpurun_out | tail -20

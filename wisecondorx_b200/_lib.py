@@ -42,6 +42,8 @@ def load():
     L.wcx_destroy.restype = None
     L.wcx_set_stream.argtypes = [vp, vp]
     L.wcx_sync.argtypes = [vp]
+    L.wcx_host_alloc.argtypes = [ctypes.c_uint64, ctypes.POINTER(vp)]
+    L.wcx_host_free.argtypes = [vp]
     L.wcx_newref_load.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32]
     L.wcx_newref_topk.argtypes = [vp, i64, i64, i32, i32, vp, vp, i32]
     L.wcx_newref_null_ratios.argtypes = [vp, vp, i32, i64, i64, i32, vp, i32, vp, i32]
@@ -120,3 +122,41 @@ def default_context(device: int = 0) -> Context:
     if device not in _default_ctx:
         _default_ctx[device] = Context(device)
     return _default_ctx[device]
+
+
+class PinnedPool:
+    """NumPy arrays over page-locked host memory (wcx_host_alloc).  A buffer goes back to the pool when the last
+    array that views it is garbage collected, so steady-state callers (a loop of predict batches) allocate nothing;
+    cudaHostAlloc itself costs ~0.1-0.3 ms per MB, more than the copy it speeds up."""
+
+    GRAIN = 1 << 20
+
+    def __init__(self):
+        self._free = {}
+
+    def empty(self, shape, dtype=None):
+        import weakref
+        import numpy as np
+        dtype = np.dtype(dtype or np.float64)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        size = max(self.GRAIN, (nbytes + self.GRAIN - 1) // self.GRAIN * self.GRAIN)
+        lst = self._free.setdefault(size, [])
+        if lst:
+            ptr = lst.pop()
+        else:
+            p = ctypes.c_void_p()
+            check(load().wcx_host_alloc(size, ctypes.byref(p)))
+            ptr = p.value
+        buf = (ctypes.c_char * size).from_address(ptr)
+        weakref.finalize(buf, lst.append, ptr)
+        return np.frombuffer(buf, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
+
+    def trim(self):
+        """Frees the buffers that are not in use."""
+        L = load()
+        for lst in self._free.values():
+            while lst:
+                L.wcx_host_free(ctypes.c_void_p(lst.pop()))
+
+
+pinned = PinnedPool()

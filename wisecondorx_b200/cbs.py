@@ -32,6 +32,7 @@ def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx
     nseg = np.zeros(max(ns, 1), dtype=np.int32)
     _lib.check(L.wcx_cbs_segment(ctx.handle, _ptr(y), _ptr(w), _ptr(off), ns, _ptr(ids), float(alpha), int(nperm),
                                  int(seed) & 0xFFFFFFFF, _ptr(ends), _ptr(nseg)))
+    predict_tools.accumulate_ms(ctx, ("cbs",))
     out, o = [], 0
     for s in range(ns):
         out.append(ends[o:o + nseg[s]].copy())
@@ -46,11 +47,9 @@ def cbs_stats(ctx: _lib.Context | None = None):
     return dict(zip(["rounds", "segments_tested", "perm_tests", "t_tests", "permutations", "launches"], out.tolist()))
 
 
-def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, nperm=10000, ctx=None):
-    """CBS.R as a function: [[chr (0-based), s, e (exclusive), r], ...]."""
+def _cbs_prepare(results_r, results_w, ref_gender):
+    """CBS.R:30-63 for one sample: per chromosome the ratio / weight vectors, the NA mask and the NA-free series."""
     nchr = 24 if ref_gender == "M" else 23  # CBS.R:30-34
-    seed_i = 0 if seed is None else int(seed)
-    na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
     prepared, series, ids = [], [], []
     for c in range(nchr):
         ratio = np.asarray(results_r[c], dtype=np.float64)
@@ -63,7 +62,12 @@ def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, np
         prepared.append((c, ratio, wts, na, keep))
         series.append((ratio[keep], wts[keep]))
         ids.append(c)
-    all_ends = segment_series(series, ids, alpha, nperm, seed_i, ctx)
+    return prepared, series, ids
+
+
+def _cbs_finish(prepared, all_ends, binsize):
+    """CBS.R:80-129: split the segments over long NA runs, weighted segment means, 0-based half-open coordinates."""
+    na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
     out = []
     for (c, ratio, wts, na, keep), ends in zip(prepared, all_ends):
         starts = np.concatenate([[0], ends[:-1]]).astype(np.int64)
@@ -86,6 +90,28 @@ def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, np
     return out
 
 
+def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, nperm=10000, ctx=None):
+    """CBS.R as a function: [[chr (0-based), s, e (exclusive), r], ...]."""
+    return cbs_segments_batch([(results_r, results_w, ref_gender)], alpha, binsize, seed, nperm, ctx)[0]
+
+
+def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None):
+    """CBS.R for a batch of samples [(results_r, results_w, ref_gender), ...] with ONE device call over all
+    (sample, chromosome) series.  The permutation streams are keyed by (seed, chromosome), not by the position of a
+    series in the batch, so every sample gets the segments it would get alone."""
+    seed_i = 0 if seed is None else int(seed)
+    preps, series, ids, counts = [], [], [], []
+    for results_r, results_w, ref_gender in samples:
+        p, s, i = _cbs_prepare(results_r, results_w, ref_gender)
+        preps.append(p); series += s; ids += i; counts.append(len(s))
+    all_ends = segment_series(series, ids, alpha, nperm, seed_i, ctx)
+    out, o = [], 0
+    for p, n in zip(preps, counts):
+        out.append(_cbs_finish(p, all_ends[o:o + n], binsize))
+        o += n
+    return out
+
+
 def exec_cbs(rem_input, results, engine: predict_tools.PredictEngine | None = None, nperm=10000):
     """Drop-in for predict_tools.exec_cbs (reference predict_tools.py:242-263): segments
     results["results_r"] with weights results["results_w"], then attaches the between-sample
@@ -96,3 +122,19 @@ def exec_cbs(rem_input, results, engine: predict_tools.PredictEngine | None = No
                              engine.ctx if engine else None)
     segment_z = predict_tools.get_z_score(results_c, results, engine)
     return [results_c[i][:3] + [segment_z[i]] + [results_c[i][3]] for i in range(len(results_c))]
+
+
+def exec_cbs_batch(rem_inputs, results_list, engine: predict_tools.PredictEngine | None = None, nperm=10000):
+    """exec_cbs for a batch of samples that share args (alpha, seed) and the reference: one CBS call, then the
+    segment z-scores per sample."""
+    if not rem_inputs:
+        return []
+    args = rem_inputs[0]["args"]
+    segs = cbs_segments_batch([(res["results_r"], res["results_w"], str(rem["ref_gender"])) for rem, res in zip(rem_inputs, results_list)],
+                              float(args.alpha), float(rem_inputs[0]["binsize"]), getattr(args, "seed", None), nperm,
+                              engine.ctx if engine else None)
+    out = []
+    for results_c, res in zip(segs, results_list):
+        z = predict_tools.get_z_score(results_c, res, engine)
+        out.append([results_c[i][:3] + [z[i]] + [results_c[i][3]] for i in range(len(results_c))])
+    return out

@@ -50,6 +50,10 @@ struct DevBuf {
 
 struct RefSet {
   DevBuf idx, dist, cum, comps, mean, mask_pos;
+  DevBuf gl;                 // gather lists of the last (cutoff, ct): predict.cu gather_list_kernel
+  double gl_cutoff = 0.0;
+  int64_t gl_ct = -1;
+  bool gl_valid = false;
   int64_t n = 0, bins_total = 0;
   int32_t k = 0, nchr = 0, ncomp = 0;
   std::vector<int64_t> cum_h;
@@ -92,8 +96,10 @@ struct wcx_ctx {
   // predict state
   RefSet ref[3];
   DevBuf p_partial, p_totals, p_tdots, p_state, p_raw, p_x, p_copy_a, p_copy_b, p_z, p_r, p_n, p_mlr, p_mz, p_w;
-  DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out;
-  double predict_ms[4] = {};
+  DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out, p_radix;
+  double predict_ms[8] = {};
+  int64_t z_nr_rows = -1;  // null ratios resident for wcx_segment_zscore(nr = NULL)
+  int32_t z_nr_m = 0;
   CbsWorkspace* cbs = nullptr;
   // newref prep state
   DevBuf q_counts, q_pos, q_colsum, q_x, q_mean, q_partial, q_gram, q_u, q_sigma, q_comps, q_corr, q_med, q_d, q_work;
@@ -181,13 +187,13 @@ void wcx_destroy(wcx_ctx* c) {
                     &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev, &c->leaves_dev,
                     &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->xp, &c->perm_dev, &c->leafdesc_dev, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
-                    &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out})
+                    &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out, &c->p_radix})
     b->release();
   for (DevBuf* b : {&c->q_counts, &c->q_pos, &c->q_colsum, &c->q_x, &c->q_mean, &c->q_partial, &c->q_gram, &c->q_u, &c->q_sigma,
                     &c->q_comps, &c->q_corr, &c->q_med, &c->q_d, &c->q_work})
     b->release();
   for (auto& r : c->ref)
-    for (DevBuf* b : {&r.idx, &r.dist, &r.cum, &r.comps, &r.mean, &r.mask_pos}) b->release();
+    for (DevBuf* b : {&r.idx, &r.dist, &r.cum, &r.comps, &r.mean, &r.mask_pos, &r.gl}) b->release();
   if (c->cbs) cbs_workspace_destroy(c->cbs);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -204,6 +210,18 @@ void wcx_destroy(wcx_ctx* c) {
 int wcx_set_stream(wcx_ctx* c, void* cuda_stream) {
   if (!c) { set_error("null context"); return 1; }
   c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return 0;
+}
+
+int wcx_host_alloc(uint64_t bytes, void** out) {
+  if (!out) { set_error("wcx_host_alloc: out is NULL"); return 1; }
+  *out = nullptr;
+  WCX_CUDA_OK(cudaHostAlloc(out, bytes ? (size_t)bytes : 1, cudaHostAllocPortable));
+  return 0;
+}
+
+int wcx_host_free(void* p) {
+  if (p) WCX_CUDA_OK(cudaFreeHost(p));
   return 0;
 }
 
@@ -356,7 +374,8 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
                      int32_t out_on_device, const NullPlan* np) {
   if (!c || !c->loaded) { set_error("wcx_newref_topk: call wcx_newref_load first"); return 1; }
   if (rb < 0 || re > c->n || rb > re) { set_error("wcx_newref_topk: bad row range"); return 1; }
-  if (k <= 0 || k > 400) { set_error("wcx_newref_topk: ref_size must be in [1, 400]"); return 1; }
+  if (k <= 0 || k > 512) { set_error("wcx_newref_topk: ref_size must be in [1, 512]"); return 1; }
+  if (k > 400) kernel = WCX_KERNEL_EXACT;  // beyond the candidate-list guarantee of the sweep (2 x WCX_CAND_KEEP_TC per row)
   WCX_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const int64_t rows = re - rb;
@@ -639,6 +658,9 @@ int wcx_newref_null_ratios(wcx_ctx* c, const int32_t* idx, int32_t idx_on_device
   } else if (idx_on_device) {
     d_idx = idx;
   } else {
+    // caller-supplied positions: Python semantics, -n <= v < n (negative wraps); anything else would gather out of bounds
+    for (size_t i = 0; i < (size_t)rows * k; i++)
+      if (idx[i] < -c->n || idx[i] >= c->n) { set_error("wcx_newref_null_ratios: index out of range [-n, n)"); return 1; }
     if (c->idx_dev.ensure(sizeof(int32_t) * (size_t)rows * k)) return 1;
     WCX_CUDA_OK(cudaMemcpyAsync(c->idx_dev.p, idx, sizeof(int32_t) * (size_t)rows * k, cudaMemcpyHostToDevice, st));
     d_idx = c->idx_dev.as<int32_t>();
@@ -794,6 +816,7 @@ int wcx_predict_load_ref(wcx_ctx* c, int32_t set_id, const int32_t* idx, const d
   cudaStream_t st = c->stream;
   RefSet& r = c->ref[set_id];
   r.loaded = false;
+  r.gl_valid = false;
   if (h2d(r.idx, idx, sizeof(int32_t) * (size_t)n * k, st) || h2d(r.dist, dist, sizeof(double) * (size_t)n * k, st) ||
       h2d(r.cum, cum, sizeof(int64_t) * nchr, st) || h2d(r.comps, comps, sizeof(double) * (size_t)ncomp * n, st) ||
       h2d(r.mean, mean, sizeof(double) * (size_t)n, st) || h2d(r.mask_pos, mask_pos, sizeof(int32_t) * (size_t)n, st))
@@ -855,7 +878,8 @@ int wcx_predict_normalize(wcx_ctx* c, int32_t set_id, const double* raw, int32_t
   if (c->p_raw.ensure(sizeof(double) * (size_t)B * r->bins_total) || c->p_x.ensure(bn) || c->p_copy_a.ensure(bn) || c->p_copy_b.ensure(bn) ||
       c->p_z.ensure(bo) || c->p_r.ensure(bo) || c->p_n.ensure(bo) || c->p_mlr.ensure(sizeof(double) * B) || c->p_mz.ensure(sizeof(double) * B) ||
       c->p_state.ensure(sizeof(double) * 4) || c->p_partial.ensure(sizeof(double) * (size_t)predict_red_blocks() * 8 * 128) ||
-      c->p_totals.ensure(sizeof(double) * 128) || c->p_tdots.ensure(sizeof(double) * 128 * 8))
+      c->p_totals.ensure(sizeof(double) * 128) || c->p_tdots.ensure(sizeof(double) * 128 * 8) ||
+      c->p_radix.ensure(radix_scratch_bytes(B, nout > 0 ? nout : 1)))
     return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->p_raw.p, raw, sizeof(double) * (size_t)B * r->bins_total, cudaMemcpyHostToDevice, st));
   // the cutoff travels through device memory (state[3]) so the kernels read one source of truth
@@ -866,12 +890,24 @@ int wcx_predict_normalize(wcx_ctx* c, int32_t set_id, const double* raw, int32_t
                               c->p_totals.as<double>(), c->p_tdots.as<double>(), st))
     return 1;
   WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
-  if (launch_normalize_repeat(c->p_x.as<double>(), c->p_copy_a.as<double>(), c->p_copy_b.as<double>(), B, n, r->idx.as<int32_t>(),
-                              r->dist.as<double>(), r->k, c->p_state.as<double>() + 3, r->cum.as<int64_t>(), r->nchr, ct,
-                              c->p_z.as<double>(), c->p_r.as<double>(), c->p_n.as<double>(), c->p_mlr.as<double>(),
-                              c->p_mz.as<double>(), st))
-    return 1;
+  if (nout > 0 && !(r->gl_valid && r->gl_cutoff == cutoff && r->gl_ct == ct)) {
+    r->gl_valid = false;
+    if (r->gl.ensure(sizeof(int32_t) * (size_t)nout * r->k)) return 1;
+    if (launch_gather_list(r->idx.as<int32_t>(), r->dist.as<double>(), n, r->k, c->p_state.as<double>() + 3, r->cum.as<int64_t>(),
+                           r->nchr, ct, r->gl.as<int32_t>(), st))
+      return 1;
+    r->gl_cutoff = cutoff; r->gl_ct = ct; r->gl_valid = true;
+    c->launches += 1;
+  }
   WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
+  if (launch_normalize_repeat(c->p_x.as<double>(), c->p_copy_a.as<double>(), c->p_copy_b.as<double>(), B, n, r->gl.as<int32_t>(),
+                              r->k, ct, c->p_z.as<double>(), c->p_r.as<double>(), c->p_n.as<double>(), st))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[3], st));
+  if (nout > 0 && launch_nanmedians(c->p_r.as<double>(), c->p_z.as<double>(), B, nout, c->p_radix.p, c->p_mlr.as<double>(),
+                                    c->p_mz.as<double>(), st))
+    return 1;
+  WCX_CUDA_OK(cudaEventRecord(c->ev[4], st));
   if (nout > 0) {
     WCX_CUDA_OK(cudaMemcpyAsync(z, c->p_z.p, sizeof(double) * (size_t)B * nout, cudaMemcpyDeviceToHost, st));
     WCX_CUDA_OK(cudaMemcpyAsync(rr, c->p_r.p, sizeof(double) * (size_t)B * nout, cudaMemcpyDeviceToHost, st));
@@ -883,24 +919,43 @@ int wcx_predict_normalize(wcx_ctx* c, int32_t set_id, const double* raw, int32_t
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->predict_ms[0] = ms;
-  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[4]);
   c->predict_ms[1] = ms;
-  c->launches += 13;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+  c->predict_ms[4] = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->predict_ms[5] = ms;
+  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
+  c->predict_ms[6] = ms;
+  c->launches += 6 + 3 + 1 + 6;  // coverage + projection, three passes, key pass + six radix passes
   return 0;
 }
 
 int wcx_segment_zscore(wcx_ctx* c, const double* nr, int64_t n_masked, int32_t m, const int32_t* inflate_pos, const double* r,
                        const double* w, int64_t bins_total, const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out) {
-  if (!c || !nr || !inflate_pos || !r || !w || !seg_se || !seg_r || !z_out || m <= 0 || m > 128 || nseg < 0) {
+  if (!c || !inflate_pos || !r || !w || !seg_se || !seg_r || !z_out || m <= 0 || m > 128 || nseg < 0) {
     set_error("wcx_segment_zscore: bad argument (1 <= null samples <= 128)");
+    return 1;
+  }
+  if (!nr && (c->z_nr_rows != n_masked || c->z_nr_m != m || !c->z_nr.p)) {
+    set_error("wcx_segment_zscore: nr == NULL but no null ratios of that shape are resident");
     return 1;
   }
   for (int i = 0; i < nseg; i++)
     if (seg_se[2 * i] < 0 || seg_se[2 * i + 1] > bins_total || seg_se[2 * i] > seg_se[2 * i + 1]) { set_error("wcx_segment_zscore: segment out of range"); return 1; }
+  for (int64_t i = 0; i < bins_total; i++)
+    if (inflate_pos[i] >= n_masked) { set_error("wcx_segment_zscore: inflate position out of range"); return 1; }
   if (nseg == 0) return 0;
   WCX_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  if (h2d(c->z_nr, nr, sizeof(double) * (size_t)n_masked * m, st) || h2d(c->z_pos, inflate_pos, sizeof(int32_t) * (size_t)bins_total, st) ||
+  if (nr) {
+    // 0.16 GB at 15 kb: uploaded once per reference, later calls pass NULL
+    c->z_nr_rows = -1;
+    if (h2d(c->z_nr, nr, sizeof(double) * (size_t)n_masked * m, st)) return 1;
+    c->z_nr_rows = n_masked;
+    c->z_nr_m = m;
+  }
+  if (h2d(c->z_pos, inflate_pos, sizeof(int32_t) * (size_t)bins_total, st) ||
       h2d(c->z_r, r, sizeof(double) * (size_t)bins_total, st) || h2d(c->z_w, w, sizeof(double) * (size_t)bins_total, st) ||
       h2d(c->z_se, seg_se, sizeof(int64_t) * 2 * (size_t)nseg, st) || h2d(c->z_segr, seg_r, sizeof(double) * (size_t)nseg, st) ||
       c->z_out.ensure(sizeof(double) * (size_t)nseg))
@@ -919,9 +974,9 @@ int wcx_segment_zscore(wcx_ctx* c, const double* nr, int64_t n_masked, int32_t m
   return 0;
 }
 
-int wcx_predict_stage_ms(wcx_ctx* c, double* out4) {
-  if (!c || !out4) { set_error("null argument"); return 1; }
-  std::memcpy(out4, c->predict_ms, sizeof(c->predict_ms));
+int wcx_predict_stage_ms(wcx_ctx* c, double* out8) {
+  if (!c || !out8) { set_error("null argument"); return 1; }
+  std::memcpy(out8, c->predict_ms, sizeof(c->predict_ms));
   return 0;
 }
 

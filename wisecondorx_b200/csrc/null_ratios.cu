@@ -36,6 +36,7 @@ null_ratios_kernel(const uint64_t* __restrict__ xm, int64_t n, const int32_t* __
     if (t < k) {
       v = idx[lrow * k + t];
       if (v < 0) v += n;  // Python negative index
+      v = v < 0 ? 0 : (v >= n ? n - 1 : v);  // device-resident lists are not validated by the host: never gather out of bounds
     }
     g[r] = (int32_t)v;
   }

@@ -9,6 +9,8 @@
 //   get_optimal_cutoff           predict_tools.py:74-82
 //   normalize_repeat / _normalize_once   predict_tools.py:94-142
 //   get_z_score                  overall_tools.py:88-119
+#include <algorithm>
+
 #include "select.cuh"
 #include "wcx_common.cuh"
 #include "predict.cuh"
@@ -145,12 +147,14 @@ __global__ void project_apply_kernel(double* __restrict__ x, int64_t n, const do
 }
 
 // ---- _normalize_once ------------------------------------------------------------------------------
-// one warp per target bin i in [ct, n); loops over the B samples so idx/dist rows are read once.
+// Which reference bins a target bin uses depends only on the reference set and the cutoff (predict_tools.py:117-131:
+// distances below the cutoff, chromosome-excluded position -> bin of the full vector), not on the sample or the pass:
+// gather_list_kernel resolves it ONCE per (reference set, cutoff) into gl[i - ct][t] = global bin or -1, and the three
+// passes of every sample read 4 bytes per reference bin instead of 12 (+ the position arithmetic per pass).
 __global__ void __launch_bounds__(256)
-normalize_pass_kernel(const double* __restrict__ test_data, const double* __restrict__ copy_in, double* __restrict__ copy_out,
-                      int B, int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ dist, int k,
-                      const double* __restrict__ cutoff_p, const int64_t* __restrict__ cum, int nchr, int64_t ct,
-                      double* __restrict__ z_out, double* __restrict__ r_out, double* __restrict__ n_out) {
+gather_list_kernel(const int32_t* __restrict__ idx, const double* __restrict__ dist, int64_t n, int k,
+                   const double* __restrict__ cutoff_p, const int64_t* __restrict__ cum, int nchr, int64_t ct,
+                   int32_t* __restrict__ gl) {
   const int lane = threadIdx.x & 31;
   const int64_t i = ct + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
@@ -159,51 +163,78 @@ normalize_pass_kernel(const double* __restrict__ test_data, const double* __rest
   while (c < nchr && cum[c] <= i) c++;
   const int64_t cs = c == 0 ? 0 : cum[c - 1], ce = cum[c];
   const int64_t nc = ce - cs, nex = n - nc;
-  int32_t g[PR_R];
-#pragma unroll
-  for (int r = 0; r < PR_R; r++) {
-    const int t = r * 32 + lane;
+  for (int t = lane; t < k; t += 32) {
     int32_t gg = -1;
-    if (t < k && dist[i * k + t] < cutoff) {
+    if (dist[i * k + t] < cutoff) {
       int64_t p = idx[i * k + t];
       if (p < 0) p += nex;                 // Python negative index into the chr-excluded array
       if (p >= 0 && p < nex) gg = (int32_t)(p < cs ? p : p + nc);
     }
-    g[r] = gg;
+    gl[(i - ct) * k + t] = gg;
+  }
+}
+
+// one warp per target bin i in [ct, n); loops over the B samples so the gather list is read once per batch.
+// R = register slots per lane (R / 4 quads of 4 consecutive list entries, 16-byte loads when k % 4 == 0).
+// The kept values are >= 0, so their order-preserving key is the bit pattern with the sign bit set: the value is
+// recovered from the key and needs no registers of its own.
+template <int R>
+__global__ void __launch_bounds__(256)
+normalize_pass_kernel(const double* __restrict__ test_data, const double* __restrict__ copy_in, double* __restrict__ copy_out,
+                      int B, int64_t n, const int32_t* __restrict__ gl, int k, int64_t ct,
+                      double* __restrict__ z_out, double* __restrict__ r_out, double* __restrict__ n_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ct + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  int32_t g[R];
+  const int32_t* grow = gl + (i - ct) * k;
+  if ((k & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < R / 4; j++) {
+      const int q = j * 32 + lane;
+      int4 v = make_int4(-1, -1, -1, -1);
+      if (4 * q < k) v = __ldg(reinterpret_cast<const int4*>(grow) + q);
+      g[4 * j] = v.x; g[4 * j + 1] = v.y; g[4 * j + 2] = v.z; g[4 * j + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int t = r * 32 + lane;
+      g[r] = t < k ? __ldg(grow + t) : -1;
+    }
   }
   const int64_t nout = n - ct;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
   for (int b = 0; b < B; b++) {
     const double* cp = copy_in + (int64_t)b * n;
-    uint64_t key[PR_R];
-    double v[PR_R];
+    uint64_t key[R];
     int cnt = 0;
     double sum = 0.0;
 #pragma unroll
-    for (int r = 0; r < PR_R; r++) {
+    for (int r = 0; r < R; r++) {
       double val = -1.0;
-      if (g[r] >= 0) val = cp[g[r]];
-      const bool keep = g[r] >= 0 && val >= 0.0;  // NaN and negatives (masked bins) dropped
-      v[r] = keep ? val : 0.0;
-      key[r] = keep ? dkey(val) : ~0ull;
+      if (g[r] >= 0) val = __ldg(cp + g[r]);
+      const bool keep = val >= 0.0;  // NaN and negatives (masked bins) dropped
+      key[r] = keep ? ((uint64_t)__double_as_longlong(val) | 0x8000000000000000ull) : ~0ull;
       cnt += keep ? 1 : 0;
       sum += keep ? val : 0.0;
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
     double mean = nan, sd = nan, med = nan;
     if (cnt > 0) {
       mean = sum / (double)cnt;
       double ss = 0.0;
 #pragma unroll
-      for (int r = 0; r < PR_R; r++) {
-        if (key[r] != ~0ull) { const double t = v[r] - mean; ss += t * t; }
+      for (int r = 0; r < R; r++) {
+        const double t = __longlong_as_double((long long)(key[r] & 0x7fffffffffffffffull)) - mean;
+        ss += key[r] != ~0ull ? t * t : 0.0;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       sd = sqrt(ss / (double)cnt);
-      med = warp_median<PR_R>(key, cnt);
+      med = warp_median<R>(key, cnt);
     }
     if (lane == 0) {
       const double x = test_data[(int64_t)b * n + i];
@@ -216,64 +247,148 @@ normalize_pass_kernel(const double* __restrict__ test_data, const double* __rest
   }
 }
 
-// ---- np.nanmedian over a row (optionally of log2) ---------------------------------------------------
-// one block per row; bisection over order-preserving 64-bit keys, NaN excluded
-__global__ void __launch_bounds__(1024)
-nanmedian_kernel(const double* __restrict__ vals, int64_t len, int take_log2, double* __restrict__ out) {
+// ---- np.nanmedian over rows (optionally of log2): multi-CTA radix select -----------------------------------
+// The two medians of normalize_repeat (predict_tools.py:106-107: nanmedian(log2(r)), nanmedian(z)) are order
+// statistics of ~1.9e5 doubles per sample.  (The first version ran one CTA per sample with 64 bisection passes and
+// log2 recomputed in each: 14.7 ms of the 18.3 ms of a batch-1 normalize, on 1 of 148 SMs.)  Here: the values become
+// order-preserving 64-bit keys ONCE (log2 applied once, NaN counted out), then six passes of an 11-bit radix select
+// (digits at bit 53, 42, 31, 20, 9, 0) over all SMs.  Pass p histograms digit p of the keys that match the prefix
+// found so far; the next launch starts by scanning that histogram (every CTA does the same 2048-bin scan, CTA 0 of the
+// row records the state).  Both middle order statistics ((cnt - 1) / 2 and cnt / 2) are tracked, so an even count
+// needs no extra pass.  blockIdx.z selects the array (0: log2(r), 1: z): seven launches do both medians of a batch.
+constexpr int RS_BINS = 2048;
+constexpr int RS_PASSES = 6;
+__constant__ int RS_SHIFT[RS_PASSES] = {53, 42, 31, 20, 9, 0};
+
+struct RadixState {           // per (array, row, pass): state BEFORE pass p
+  unsigned long long prefix[2];  // high bits fixed so far for the lower / upper middle rank
+  long long rank[2];             // rank of the wanted key among the keys that match the prefix
+};
+
+__device__ __forceinline__ int rs_digit(unsigned long long key, int pass) {
+  return (int)((key >> RS_SHIFT[pass]) & (pass == RS_PASSES - 1 ? 511ull : 2047ull));
+}
+// mask of the bits above digit `pass`
+__device__ __forceinline__ unsigned long long rs_himask(int pass) {
+  return pass == 0 ? 0ull : ~((1ull << (RS_SHIFT[pass - 1])) - 1ull);
+}
+
+// keys[a][row][i], cnt[a][row] = number of non-NaN values, hist of pass 0
+__global__ void __launch_bounds__(256)
+radix_keys_kernel(const double* __restrict__ r, const double* __restrict__ z, int64_t len, unsigned long long* __restrict__ keys,
+                  unsigned long long* __restrict__ cnt, unsigned int* __restrict__ hist, int B) {
+  __shared__ unsigned int sh[RS_BINS];
   __shared__ unsigned long long s_cnt;
-  __shared__ unsigned long long s_best;
-  const double* p = vals + (int64_t)blockIdx.x * len;
-  auto load = [&](int64_t i) -> double { double v = p[i]; return take_log2 ? log2(v) : v; };
-  unsigned long long loc = 0;
-  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) { double v = load(i); loc += (v == v) ? 1 : 0; }
+  const int a = blockIdx.z, row = blockIdx.y;
+  const double* src = (a == 0 ? r : z) + (int64_t)row * len;
+  unsigned long long* kd = keys + ((int64_t)a * B + row) * len;
+  for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) sh[i] = 0;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
-  atomicAdd(&s_cnt, loc);
+  unsigned long long loc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = src[i];
+    if (a == 0) v = log2(v);
+    unsigned long long k = ~0ull;  // NaN: above every number, never counted
+    if (v == v) { k = dkey(v); loc++; atomicAdd(&sh[(int)(k >> 53)], 1u); }
+    kd[i] = k;
+  }
+  loc = __reduce_add_sync(0xffffffffu, (unsigned)loc);
+  if ((threadIdx.x & 31) == 0 && loc) atomicAdd(&s_cnt, loc);
   __syncthreads();
-  const long long valid = (long long)s_cnt;
-  if (valid == 0) {
-    if (threadIdx.x == 0) out[blockIdx.x] = __longlong_as_double(0x7ff8000000000000ll);
+  unsigned int* h = hist + (((int64_t)a * B + row) * RS_PASSES + 0) * 2 * RS_BINS;
+  for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&h[i], sh[i]);
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(&cnt[(int64_t)a * B + row], s_cnt);
+}
+
+// scan of the histogram(s) of pass `pass - 1` -> state before `pass`; valid in every thread after the call
+__device__ __forceinline__ RadixState rs_advance(const RadixState& prev, const unsigned int* __restrict__ h, int pass_done,
+                                                 unsigned int* sh_scan /*[RS_BINS]*/) {
+  RadixState out = prev;
+  const bool same = prev.prefix[0] == prev.prefix[1] && prev.rank[0] == prev.rank[1];
+  for (int sidx = 0; sidx < 2; sidx++) {
+    if (sidx == 1 && same) { out.prefix[1] = out.prefix[0]; out.rank[1] = out.rank[0]; break; }
+    // the two ranks share one histogram while their prefixes agree
+    const unsigned int* hh = h + ((sidx == 1 && prev.prefix[0] != prev.prefix[1]) ? RS_BINS : 0);
+    // block-wide inclusive scan of 2048 bins: 8 bins per thread (256 threads)
+    unsigned int v[8], run = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = hh[threadIdx.x * 8 + j]; run += v[j]; }
+    __syncthreads();
+    sh_scan[threadIdx.x] = run;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const unsigned int t = threadIdx.x >= o ? sh_scan[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sh_scan[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const long long want = prev.rank[sidx];
+    long long before = threadIdx.x ? (long long)sh_scan[threadIdx.x - 1] : 0ll;
+    __syncthreads();
+    // the owning thread publishes (digit, rank inside the bucket)
+    if (want >= before && want < before + (long long)run) {
+      int j = 0;
+      while (want >= before + (long long)v[j]) { before += v[j]; j++; }
+      sh_scan[256] = (unsigned)(threadIdx.x * 8 + j);
+      sh_scan[257] = (unsigned)(want - before);
+    }
+    __syncthreads();
+    out.prefix[sidx] = prev.prefix[sidx] | ((unsigned long long)sh_scan[256] << RS_SHIFT[pass_done]);
+    out.rank[sidx] = (long long)sh_scan[257];
+    __syncthreads();
+  }
+  return out;
+}
+
+// pass p in 1..RS_PASSES: advance the state from the histogram of pass p - 1, then histogram digit p of the matching
+// keys.  p == RS_PASSES (launched with one CTA per row) only advances -- the prefixes are then the two keys -- and
+// writes the median.  states: [2][B][RS_PASSES + 1].
+__global__ void __launch_bounds__(256)
+radix_pass_kernel(const unsigned long long* __restrict__ keys, int64_t len, const unsigned long long* __restrict__ cnt,
+                  unsigned int* __restrict__ hist, RadixState* __restrict__ states, int pass, int B,
+                  double* __restrict__ m_lr, double* __restrict__ m_z) {
+  __shared__ unsigned int sh[2 * RS_BINS];
+  __shared__ unsigned int sh_scan[258];
+  const int a = blockIdx.z, row = blockIdx.y;
+  const int64_t ar = (int64_t)a * B + row;
+  const long long n = (long long)cnt[ar];
+  if (n == 0) {
+    if (pass == RS_PASSES && threadIdx.x == 0) (a == 0 ? m_lr : m_z)[row] = __longlong_as_double(0x7ff8000000000000ll);
     return;
   }
-  const long long hi_rank = valid >> 1;
-  uint64_t T = 0;
-  for (int bit = 63; bit >= 0; bit--) {
-    const uint64_t trial = T | (1ull << bit);
-    loc = 0;
-    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
-      double v = load(i);
-      if (v == v) loc += (dkey(v) < trial) ? 1 : 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    atomicAdd(&s_cnt, loc);
-    __syncthreads();
-    if ((long long)s_cnt <= hi_rank) T = trial;
+  RadixState prev;
+  if (pass == 1) {
+    prev.prefix[0] = prev.prefix[1] = 0ull;
+    prev.rank[0] = (n - 1) >> 1;
+    prev.rank[1] = n >> 1;
+  } else {
+    prev = states[ar * (RS_PASSES + 1) + (pass - 1)];
   }
-  double upper = key_d(T);
-  double med = upper;
-  if ((valid & 1) == 0) {
-    // lower middle
-    unsigned long long best = 0;
-    loc = 0;
-    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
-      double v = load(i);
-      if (v == v) {
-        uint64_t kk = dkey(v);
-        if (kk < T) { loc++; best = kk > best ? kk : best; }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { s_cnt = 0; s_best = 0; }
-    __syncthreads();
-    atomicAdd(&s_cnt, loc);
-    atomicMax(&s_best, best);
-    __syncthreads();
-    double lower = ((long long)s_cnt == hi_rank) ? key_d((uint64_t)s_best) : upper;
-    med = (lower + upper) / 2.0;
+  const RadixState st = rs_advance(prev, hist + (ar * RS_PASSES + (pass - 1)) * 2 * RS_BINS, pass - 1, sh_scan);
+  if (pass == RS_PASSES) {
+    // np.median / np.nanmedian: mean of the two middle order statistics (the same key twice for an odd count)
+    if (threadIdx.x == 0) (a == 0 ? m_lr : m_z)[row] = (key_d(st.prefix[0]) + key_d(st.prefix[1])) / 2.0;
+    return;
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = med;
+  if (blockIdx.x == 0 && threadIdx.x == 0) states[ar * (RS_PASSES + 1) + pass] = st;
+  for (int i = threadIdx.x; i < 2 * RS_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const unsigned long long hm = rs_himask(pass);
+  const bool split = st.prefix[0] != st.prefix[1];
+  const unsigned long long* kd = keys + ar * len;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = kd[i];
+    if (k == ~0ull) continue;
+    const unsigned long long kh = k & hm;
+    if (kh == st.prefix[0]) atomicAdd(&sh[rs_digit(k, pass)], 1u);
+    else if (split && kh == st.prefix[1]) atomicAdd(&sh[RS_BINS + rs_digit(k, pass)], 1u);
+  }
+  __syncthreads();
+  unsigned int* h = hist + (ar * RS_PASSES + pass) * 2 * RS_BINS;
+  for (int i = threadIdx.x; i < 2 * RS_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
 // ---- get_z_score ---------------------------------------------------------------------------------------
@@ -377,27 +492,70 @@ int launch_coverage_project(const double* raw, int32_t B, int64_t bins_total, co
   return 0;
 }
 
-// three passes of _normalize_once with the -1 masking in between (normalize_repeat), then the two
-// nanmedians.  copy_a / copy_b: [B, n] ping-pong buffers.
-int launch_normalize_repeat(const double* x, double* copy_a, double* copy_b, int32_t B, int64_t n, const int32_t* idx,
-                            const double* dist, int32_t k, const double* cutoff_dev, const int64_t* cum_dev,
-                            int32_t nchr, int64_t ct, double* z, double* r, double* nref, double* m_lr, double* m_z,
-                            cudaStream_t st) {
+// gl [n - ct, k] for one (reference set, cutoff): see gather_list_kernel
+int launch_gather_list(const int32_t* idx, const double* dist, int64_t n, int32_t k, const double* cutoff_dev,
+                       const int64_t* cum_dev, int32_t nchr, int64_t ct, int32_t* gl, cudaStream_t st) {
+  const int64_t nout = n - ct;
+  if (nout <= 0) return 0;
+  gather_list_kernel<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(idx, dist, n, k, cutoff_dev, cum_dev, nchr, ct, gl);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+size_t radix_scratch_bytes(int32_t B, int64_t len) {
+  return sizeof(unsigned long long) * 2 * (size_t)B * (size_t)len       // keys
+         + sizeof(unsigned long long) * 2 * (size_t)B                   // valid counts
+         + sizeof(unsigned int) * 2 * (size_t)B * RS_PASSES * 2 * RS_BINS  // histograms
+         + sizeof(RadixState) * 2 * (size_t)B * (RS_PASSES + 1);
+}
+
+// m_lr[b] = nanmedian(log2(r[b, :])), m_z[b] = nanmedian(z[b, :]) (predict_tools.py:106-107)
+int launch_nanmedians(const double* r, const double* z, int32_t B, int64_t len, void* scratch, double* m_lr, double* m_z,
+                      cudaStream_t st) {
+  if (B <= 0) return 0;
+  unsigned char* p = reinterpret_cast<unsigned char*>(scratch);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(p);
+  p += sizeof(unsigned long long) * 2 * (size_t)B * (size_t)len;
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(p);
+  p += sizeof(unsigned long long) * 2 * (size_t)B;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(p);
+  const size_t hist_bytes = sizeof(unsigned int) * 2 * (size_t)B * RS_PASSES * 2 * RS_BINS;
+  p += hist_bytes;
+  RadixState* states = reinterpret_cast<RadixState*>(p);
+  WCX_CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 2 * (size_t)B + hist_bytes, st));
+  // about four CTAs per SM over the whole batch, at least 1024 keys per CTA
+  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((len + 1023) / 1024, (592 + 2 * B - 1) / (2 * B)));
+  const dim3 grid(chunks, B, 2);
+  radix_keys_kernel<<<grid, 256, 0, st>>>(r, z, len, keys, cnt, hist, B);
+  for (int pass = 1; pass < RS_PASSES; pass++)
+    radix_pass_kernel<<<grid, 256, 0, st>>>(keys, len, cnt, hist, states, pass, B, m_lr, m_z);
+  radix_pass_kernel<<<dim3(1, B, 2), 256, 0, st>>>(keys, len, cnt, hist, states, RS_PASSES, B, m_lr, m_z);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// three passes of _normalize_once with the -1 masking in between (normalize_repeat; the two nanmedians that follow are
+// launch_nanmedians).  copy_a / copy_b: [B, n] ping-pong buffers; gl: launch_gather_list.
+int launch_normalize_repeat(const double* x, double* copy_a, double* copy_b, int32_t B, int64_t n, const int32_t* gl,
+                            int32_t k, int64_t ct, double* z, double* r, double* nref, cudaStream_t st) {
   if (k > PR_MAXK) { set_error("normalize: ref_size > 512 unsupported"); return 1; }
   const int64_t nout = n - ct;
   if (nout <= 0 || B <= 0) return 0;
   WCX_CUDA_OK(cudaMemcpyAsync(copy_a, x, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToDevice, st));
-  WCX_CUDA_OK(cudaMemcpyAsync(copy_b, x, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToDevice, st));
+  // the passes rewrite the target bins [ct, n) only: the second buffer needs the prefix [0, ct) of every sample once
+  if (ct > 0)
+    WCX_CUDA_OK(cudaMemcpy2DAsync(copy_b, sizeof(double) * (size_t)n, x, sizeof(double) * (size_t)n, sizeof(double) * (size_t)ct,
+                                  (size_t)B, cudaMemcpyDeviceToDevice, st));
   const unsigned grid = (unsigned)((nout + 7) / 8);
   double* in = copy_a;
   double* out = copy_b;
   for (int pass = 0; pass < 3; pass++) {
-    normalize_pass_kernel<<<grid, 256, 0, st>>>(x, in, pass < 2 ? out : nullptr, B, n, idx, dist, k, cutoff_dev, cum_dev,
-                                                nchr, ct, z, r, nref);
+    if (k <= 384)
+      normalize_pass_kernel<12><<<grid, 256, 0, st>>>(x, in, pass < 2 ? out : nullptr, B, n, gl, k, ct, z, r, nref);
+    else
+      normalize_pass_kernel<16><<<grid, 256, 0, st>>>(x, in, pass < 2 ? out : nullptr, B, n, gl, k, ct, z, r, nref);
     double* t = in; in = out; out = t;
   }
-  nanmedian_kernel<<<B, 1024, 0, st>>>(r, nout, 1, m_lr);
-  nanmedian_kernel<<<B, 1024, 0, st>>>(z, nout, 0, m_z);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

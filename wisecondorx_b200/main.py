@@ -66,8 +66,7 @@ def get_mask(samples):
     return sum_per_bin > (0.05 * median_cov), bins_per_chr
 
 
-def predict_gender(sample, trained_cutoff):
-    return "M" if _y_fraction(sample) > trained_cutoff else "F"  # reference predict_tools.py:17-24
+predict_gender = predict_control.predict_gender
 
 
 # ---------------------------------------------------------------------------------------------
@@ -155,51 +154,9 @@ def tool_newref(args):
 # ---------------------------------------------------------------------------------------------
 # predict
 # ---------------------------------------------------------------------------------------------
-def get_post_processed_result(minrefbins, result, ref_sizes, mask, bins_per_chr):
-    """Zeroes bins with fewer than minrefbins reference bins, unmasks and splits per chromosome
-    (reference predict_control.py:49-63 + predict_tools.py:163-170), vectorised."""
-    result = np.array(result, dtype=float)
-    result[ref_sizes < minrefbins] = 0
-    full = np.zeros(len(mask), dtype=float)
-    mask_b = np.asarray(mask, dtype=bool)
-    cnt = int(np.sum(mask_b))
-    # the reference's inflate loop hands out results[j] to the j-th kept bin (predict_tools.py:163-170): surplus
-    # results are ignored, missing ones raise.  The counts differ when the gonosomal pass of newref removed
-    # autosomal bins after the autosomal snapshot (SURVEY.md A.4) -- preserved, not fixed.
-    if len(result) < cnt:
-        raise IndexError("list index out of range")
-    full[mask_b] = result[:cnt]
-    offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
-    return [full[offs[c]:offs[c + 1]] for c in range(len(bins_per_chr))]
-
-
-def log_trans(results, log_r_median):
-    """log2 of the ratios; non-finite entries blank r, z and w; the median log-ratio is subtracted
-    from every non-zero entry (reference predict_tools.py:180-193)."""
-    for c in range(len(results["results_r"])):
-        with np.errstate(all="ignore"):
-            r = np.log2(results["results_r"][c])
-        bad = ~np.isfinite(r)
-        r[bad] = 0
-        results["results_z"][c][bad] = 0
-        results["results_w"][c][bad] = 0
-        nz = r != 0
-        r[nz] = r[nz] - log_r_median
-        results["results_r"][c] = r
-
-
-def apply_blacklist(path, binsize, results):
-    """Blanks the bins overlapping the BED intervals of --blacklist (reference :202-233)."""
-    for line in open(path):
-        chr_name, s, e = line.strip().split("\t")[:3]
-        chr_name = chr_name[3:] if chr_name[:3] == "chr" else chr_name
-        c = {"X": 23, "Y": 24}.get(chr_name, None) or int(chr_name)
-        c -= 1
-        if len(results["results_r"]) < 24 and c == 23:
-            continue
-        lo, hi = max(0, int(int(s) / binsize)), min(len(results["results_r"][c]), int(int(e) / binsize) + 1)
-        for key in ("results_r", "results_z", "results_w"):
-            results[key][c][lo:hi] = 0
+get_post_processed_result = predict_control.get_post_processed_result
+log_trans = predict_control.log_trans
+apply_blacklist = predict_control.apply_blacklist
 
 
 def tool_test(args):
@@ -228,77 +185,10 @@ def tool_test(args):
     timings["load_reference"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     sample_file = np.load(args.infile, encoding="latin1", allow_pickle=True)
-    sample = sample_file["sample"].item()
-    n_reads = int(sum(int(np.sum(sample[x], dtype=np.int64)) for x in sample.keys()))
-    sample = scale_sample(sample, int(sample_file["binsize"].item()), int(ref_file["binsize"]))
-    gender = predict_gender(sample, ref_file["trained_cutoff"])
-    if not ref_file["is_nipt"]:
-        if args.gender:
-            gender = args.gender
-        sample = gender_correct(sample, gender)
-        ref_gender = gender
-    else:
-        if args.gender:
-            gender = args.gender
-        ref_gender = "F"
     engine = predict_tools.PredictEngine(getattr(args, "device", 0))
-    logging.info("Normalizing autosomes ...")
-    results_r, results_z, results_w, ref_sizes, m_lr, m_z = predict_control.normalize(args, sample, ref_file, "A", engine)
-    if not ref_file["is_nipt"]:
-        if not ref_file["has_male"] and gender == "M":
-            logging.warning("This sample is male, whilst the reference is created with fewer than 5 males. "
-                            "The female gonosomal reference will be used for X predictions.")
-            ref_gender = "F"
-        elif not ref_file["has_female"] and gender == "F":
-            logging.warning("This sample is female, whilst the reference is created with fewer than 5 females. "
-                            "The male gonosomal reference will be used for XY predictions.")
-            ref_gender = "M"
-    logging.info("Normalizing gonosomes ...")
-    nr_aut = ref_file["null_ratios"]
-    nr_gon = ref_file["null_ratios.{}".format(ref_gender)][len(nr_aut):]
-    r2, z2, w2, n2, _, _ = predict_control.normalize(args, sample, ref_file, ref_gender, engine)
-    sfx = ".{}".format(ref_gender)
-    rem_input = {
-        "args": args, "binsize": int(ref_file["binsize"]), "n_reads": n_reads, "ref_gender": ref_gender, "gender": gender,
-        "mask": ref_file["mask" + sfx], "bins_per_chr": ref_file["bins_per_chr" + sfx],
-        "masked_bins_per_chr": ref_file["masked_bins_per_chr" + sfx],
-        "masked_bins_per_chr_cum": ref_file["masked_bins_per_chr_cum" + sfx],
-    }
-    # assembly (reference main.py:242-257)
-    results_r = np.append(results_r, r2)
-    results_z = np.append(results_z, z2) - m_z
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        results_w = np.append(results_w * np.nanmean(w2), w2 * np.nanmean(results_w))
-        results_w = results_w / np.nanmean(results_w)
-    if np.isnan(results_w).any() or np.isinf(results_w).any():
-        logging.warning("Non-numeric values found in weights -- reference too small. Circular binary segmentation and "
-                        "z-scoring will be unweighted")
-        results_w = np.ones(len(results_w))
-    ref_sizes = np.append(ref_sizes, n2)
-    m = max(nr_aut.shape[1], nr_gon.shape[1] if len(nr_gon) else 0)
-    nr = np.full((len(nr_aut) + len(nr_gon), m), np.nan)
-    nr[:len(nr_aut), :nr_aut.shape[1]] = nr_aut
-    if len(nr_gon):
-        nr[len(nr_aut):, :nr_gon.shape[1]] = nr_gon
-    mask, bpc = rem_input["mask"], rem_input["bins_per_chr"]
-    results = {key: get_post_processed_result(args.minrefbins, val, ref_sizes, mask, bpc)
-               for key, val in (("results_r", results_r), ("results_z", results_z), ("results_w", results_w))}
-    mask_b = np.asarray(mask, dtype=bool)
-    pos = np.arange(int(np.sum(mask_b)), dtype=np.int32)
-    pos[ref_sizes[:len(pos)] < args.minrefbins] = -1  # rows blanked by get_post_processed_result (reference predict_control.py:50-51)
-    inflate = np.full(len(mask_b), -1, dtype=np.int32)
-    inflate[mask_b] = pos
-    results["results_nr"] = {"dense": nr, "inflate": inflate}
-    log_trans(results, m_lr)
-    if args.blacklist:
-        logging.info("Applying blacklist ...")
-        apply_blacklist(args.blacklist, rem_input["binsize"], results)
-    timings["normalize_and_assemble"] = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    logging.info("Executing circular binary segmentation ...")
-    results["results_c"] = cbs.exec_cbs(rem_input, results, engine)
-    timings["cbs_and_segment_z"] = time.perf_counter() - t0
+    # gender, both normalisations, assembly (reference main.py:242-271), log transform, blacklist, CBS + segment z-scores
+    rem_input, results = predict_control.predict_batch(args, [sample_file["sample"].item()], [int(sample_file["binsize"].item())],
+                                                       ref_file, engine, timings)[0]
     t0 = time.perf_counter()
     if args.bed:
         logging.info("Writing tables ...")

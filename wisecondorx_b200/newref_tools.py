@@ -82,8 +82,9 @@ class NewrefEngine:
         return out
 
     def reference(self, row_begin, row_end, ref_size, sample_ids, kernel=_lib.KERNEL_AUTO, out=None, device_out=None):
-        """Top-k and null ratios of the loaded matrix in one pass (wcx_newref_reference; the null ratios are fused
-        into the re-rank kernel).  device_out = (idx_ptr, dist_ptr, null_ptr) leaves the results in HBM."""
+        """Top-k and null ratios of the loaded matrix in one call (wcx_newref_reference: one sweep, then re-rank and
+        null-ratio kernels block by block on two streams).  device_out = (idx_ptr, dist_ptr, null_ptr) leaves the
+        results in HBM."""
         L = _lib.load()
         ids = np.ascontiguousarray(sample_ids, dtype=np.int32)
         rows = row_end - row_begin

@@ -1,9 +1,13 @@
 """Host-side mirror of the reference's predict controller (predict_control.py)."""
 from __future__ import annotations
 
+import logging
+import warnings
+
 import numpy as np
 
 from . import predict_tools
+from .overall_tools import gender_correct, scale_sample
 
 
 def normalize(args, sample, ref_file, ref_gender, engine: predict_tools.PredictEngine | None = None):
@@ -54,3 +58,180 @@ def segment_batch(r, w, nref, m_lr, chr_offsets, minrefbins=150, alpha=1e-4, npe
             m = ok[offs[c]:offs[c + 1]]
             series.append((lr[offs[c]:offs[c + 1]][m], w[offs[c]:offs[c + 1]][m]))
     return cbs.segment_series(series, [i % nchr for i in range(len(series))], alpha=alpha, nperm=nperm, seed=seed, ctx=ctx)
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole numeric flow of `predict` (reference main.py:168-290 up to the output writers) for a batch of samples
+# ---------------------------------------------------------------------------------------------
+def _y_fraction(sample):
+    return float(np.sum(sample["24"])) / float(np.sum([np.sum(sample[x]) for x in sample.keys()]))
+
+
+def predict_gender(sample, trained_cutoff):
+    return "M" if _y_fraction(sample) > trained_cutoff else "F"  # reference predict_tools.py:17-24
+
+
+def get_post_processed_result(minrefbins, result, ref_sizes, mask, bins_per_chr):
+    """Zeroes bins with fewer than minrefbins reference bins, unmasks and splits per chromosome
+    (reference predict_control.py:49-63 + predict_tools.py:163-170), vectorised."""
+    result = np.array(result, dtype=float)
+    result[ref_sizes < minrefbins] = 0
+    full = np.zeros(len(mask), dtype=float)
+    mask_b = np.asarray(mask, dtype=bool)
+    cnt = int(np.sum(mask_b))
+    # the reference's inflate loop hands out results[j] to the j-th kept bin (predict_tools.py:163-170): surplus
+    # results are ignored, missing ones raise.  The counts differ when the gonosomal pass of newref removed
+    # autosomal bins after the autosomal snapshot (SURVEY.md A.4) -- preserved, not fixed.
+    if len(result) < cnt:
+        raise IndexError("list index out of range")
+    full[mask_b] = result[:cnt]
+    offs = np.concatenate([[0], np.cumsum(bins_per_chr)]).astype(int)
+    return [full[offs[c]:offs[c + 1]] for c in range(len(bins_per_chr))]
+
+
+def log_trans(results, log_r_median):
+    """log2 of the ratios; non-finite entries blank r, z and w; the median log-ratio is subtracted
+    from every non-zero entry (reference predict_tools.py:180-193)."""
+    for c in range(len(results["results_r"])):
+        with np.errstate(all="ignore"):
+            r = np.log2(results["results_r"][c])
+        bad = ~np.isfinite(r)
+        r[bad] = 0
+        results["results_z"][c][bad] = 0
+        results["results_w"][c][bad] = 0
+        nz = r != 0
+        r[nz] = r[nz] - log_r_median
+        results["results_r"][c] = r
+
+
+def apply_blacklist(path, binsize, results):
+    """Blanks the bins overlapping the BED intervals of --blacklist (reference predict_tools.py:202-233)."""
+    for line in open(path):
+        chr_name, s, e = line.strip().split("\t")[:3]
+        chr_name = chr_name[3:] if chr_name[:3] == "chr" else chr_name
+        c = {"X": 23, "Y": 24}.get(chr_name, None) or int(chr_name)
+        c -= 1
+        if len(results["results_r"]) < 24 and c == 23:
+            continue
+        lo, hi = max(0, int(int(s) / binsize)), min(len(results["results_r"][c]), int(int(e) / binsize) + 1)
+        for key in ("results_r", "results_z", "results_w"):
+            results[key][c][lo:hi] = 0
+
+
+def resolve_genders(args, sample, ref_file):
+    """(sample after gender_correct, gender, ref_gender) as reference main.py:188-230."""
+    gender = predict_gender(sample, ref_file["trained_cutoff"])
+    if not ref_file["is_nipt"]:
+        if args.gender:
+            gender = args.gender
+        sample = gender_correct(sample, gender)
+        ref_gender = gender
+        if not ref_file["has_male"] and gender == "M":
+            logging.warning("This sample is male, whilst the reference is created with fewer than 5 males. "
+                            "The female gonosomal reference will be used for X predictions.")
+            ref_gender = "F"
+        elif not ref_file["has_female"] and gender == "F":
+            logging.warning("This sample is female, whilst the reference is created with fewer than 5 females. "
+                            "The male gonosomal reference will be used for XY predictions.")
+            ref_gender = "M"
+    else:
+        if args.gender:
+            gender = args.gender
+        ref_gender = "F"
+    return sample, gender, ref_gender
+
+
+def assemble(args, aut, gon, nr, ref_file, ref_gender, gender, n_reads):
+    """Result assembly of one sample (reference main.py:232-271): aut / gon = (r, z, w, ref_sizes, m_lr, m_z) of the
+    two `normalize` calls, nr = the stacked autosomal + gonosomal null ratios of ref_gender (shared by the batch)."""
+    sfx = ".{}".format(ref_gender)
+    rem_input = {
+        "args": args, "binsize": int(ref_file["binsize"]), "n_reads": n_reads, "ref_gender": ref_gender, "gender": gender,
+        "mask": ref_file["mask" + sfx], "bins_per_chr": ref_file["bins_per_chr" + sfx],
+        "masked_bins_per_chr": ref_file["masked_bins_per_chr" + sfx],
+        "masked_bins_per_chr_cum": ref_file["masked_bins_per_chr_cum" + sfx],
+    }
+    results_r, results_z, results_w, ref_sizes, m_lr, m_z = aut
+    r2, z2, w2, n2 = gon[:4]
+    results_r = np.append(results_r, r2)
+    results_z = np.append(results_z, z2) - m_z
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        results_w = np.append(results_w * np.nanmean(w2), w2 * np.nanmean(results_w))
+        results_w = results_w / np.nanmean(results_w)
+    if np.isnan(results_w).any() or np.isinf(results_w).any():
+        logging.warning("Non-numeric values found in weights -- reference too small. Circular binary segmentation and "
+                        "z-scoring will be unweighted")
+        results_w = np.ones(len(results_w))
+    ref_sizes = np.append(ref_sizes, n2)
+    mask, bpc = rem_input["mask"], rem_input["bins_per_chr"]
+    results = {key: get_post_processed_result(args.minrefbins, val, ref_sizes, mask, bpc)
+               for key, val in (("results_r", results_r), ("results_z", results_z), ("results_w", results_w))}
+    mask_b = np.asarray(mask, dtype=bool)
+    pos = np.arange(int(np.sum(mask_b)), dtype=np.int32)
+    pos[ref_sizes[:len(pos)] < args.minrefbins] = -1  # rows blanked by get_post_processed_result (reference predict_control.py:50-51)
+    inflate = np.full(len(mask_b), -1, dtype=np.int32)
+    inflate[mask_b] = pos
+    results["results_nr"] = {"dense": nr, "inflate": inflate}
+    log_trans(results, m_lr)
+    if getattr(args, "blacklist", None):
+        apply_blacklist(args.blacklist, rem_input["binsize"], results)
+    return rem_input, results
+
+
+def stacked_null_ratios(ref_file, ref_gender):
+    """Autosomal null ratios followed by the gonosomal rows of ref_gender (reference main.py:216-219, :252), one
+    dense [rows, M] array (NaN padded when the two sets were built with different numbers of null samples)."""
+    nr_aut = ref_file["null_ratios"]
+    nr_gon = ref_file["null_ratios.{}".format(ref_gender)][len(nr_aut):]
+    m = max(nr_aut.shape[1], nr_gon.shape[1] if len(nr_gon) else 0)
+    nr = np.full((len(nr_aut) + len(nr_gon), m), np.nan)
+    nr[:len(nr_aut), :nr_aut.shape[1]] = nr_aut
+    if len(nr_gon):
+        nr[len(nr_aut):, :nr_gon.shape[1]] = nr_gon
+    return nr
+
+
+def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.PredictEngine | None = None, timings=None):
+    """Everything `predict` computes before the output writers, for a batch of raw samples against one reference:
+    re-binning, gender, both `normalize` calls (the autosomal one for the whole batch at once, the gonosomal one per
+    reference gender), the result assembly, log transform, blacklist, CBS (one device call for every chromosome of
+    every sample) and the segment z-scores.  Returns [(rem_input, results), ...] in sample order; results carry
+    results_c like the reference's dict after exec_cbs (main.py:283)."""
+    import time
+    from . import cbs
+    eng = engine or predict_tools.default_engine()
+    t0 = time.perf_counter()
+    prepared, genders, ref_genders, n_reads = [], [], [], []
+    for sample, bs in zip(samples, binsizes):
+        n_reads.append(int(sum(int(np.sum(sample[x], dtype=np.int64)) for x in sample.keys())))
+        sample = scale_sample(dict(sample), int(bs), int(ref_file["binsize"]))
+        sample, g, rg = resolve_genders(args, sample, ref_file)
+        prepared.append(sample); genders.append(g); ref_genders.append(rg)
+    logging.info("Normalizing autosomes ...")
+    r, z, w, n, m_lr, m_z = normalize_batch(args, prepared, ref_file, "A", eng)
+    logging.info("Normalizing gonosomes ...")
+    gon = {}
+    nrs = {}
+    for rg in sorted(set(ref_genders)):
+        ids = [i for i, x in enumerate(ref_genders) if x == rg]
+        r2, z2, w2, n2, _, _ = normalize_batch(args, [prepared[i] for i in ids], ref_file, rg, eng)
+        for j, i in enumerate(ids):
+            gon[i] = (r2[j], z2[j], w2, n2[j])
+        nrs[rg] = stacked_null_ratios(ref_file, rg)
+    out = []
+    for i in range(len(prepared)):
+        aut = (r[i], z[i], w, n[i], float(m_lr[i]), float(m_z[i]))
+        out.append(assemble(args, aut, gon[i], nrs[ref_genders[i]], ref_file, ref_genders[i], genders[i], n_reads[i]))
+    if timings is not None:
+        timings["normalize_and_assemble"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    logging.info("Executing circular binary segmentation ...")
+    if len(out) == 1:
+        out[0][1]["results_c"] = cbs.exec_cbs(out[0][0], out[0][1], eng)
+    else:
+        for (rem, res), rc in zip(out, cbs.exec_cbs_batch([o[0] for o in out], [o[1] for o in out], eng)):
+            res["results_c"] = rc
+    if timings is not None:
+        timings["cbs_and_segment_z"] = time.perf_counter() - t0
+    return out

@@ -22,11 +22,14 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
-def raw_vector(sample, bins_per_chr):
+def raw_vector(sample, bins_per_chr, out=None):
     """Per-chromosome read counts padded / truncated to the reference's bins_per_chr and
     concatenated (the host half of coverage_normalize_and_mask, predict_tools.py:35-44); the
-    division by the total and the masking happen on the device."""
-    out = np.zeros(int(np.sum(bins_per_chr)), dtype=np.float64)
+    division by the total and the masking happen on the device.  `out`: row of a preallocated batch matrix."""
+    if out is None:
+        out = np.zeros(int(np.sum(bins_per_chr)), dtype=np.float64)
+    else:
+        out[:] = 0.0
     off = 0
     for c, nb in enumerate(bins_per_chr):
         nb = int(nb)
@@ -43,17 +46,20 @@ class PredictEngine:
 
     def __init__(self, device: int = 0, ctx: _lib.Context | None = None):
         self.ctx = ctx or _lib.default_context(device)
-        self._loaded = {}
-        self._ref_token = None
-        self.meta = {}
+        # which reference object fills which device slot is a property of the CONTEXT (engines may share one), and the
+        # cache holds a strong reference to the dict: an id() can be reused once the old dict is collected
+        if not hasattr(self.ctx, "predict_sets"):
+            self.ctx.predict_sets = {}
+
+    @property
+    def meta(self):
+        return {ap: m for ap, (_, m) in self.ctx.predict_sets.items()}
 
     def _ensure_ref(self, ref_file, ap: str):
-        token = id(ref_file)
-        if self._ref_token != token:
-            self._loaded = {}
-            self.meta = {}
-            self._ref_token = token
-        if ap in self._loaded:
+        sets = self.ctx.predict_sets
+        if any(obj is not ref_file for obj, _ in sets.values()):
+            sets.clear()  # another reference: every slot is stale
+        if ap in sets:
             return
         L = _lib.load()
         idx = np.ascontiguousarray(ref_file["indexes" + ap], dtype=np.int32)
@@ -68,8 +74,7 @@ class PredictEngine:
         n, k = idx.shape
         _lib.check(L.wcx_predict_load_ref(self.ctx.handle, SET_ID[ap], _ptr(idx), _ptr(dist), n, k, _ptr(per), _ptr(cum),
                                           len(cum), _ptr(comps), _ptr(mean), comps.shape[0], _ptr(mask_pos), int(len(mask))))
-        self._loaded[ap] = True
-        self.meta[ap] = {"n": n, "k": k, "cum": cum, "bins_per_chr": bpc, "bins_total": int(len(mask))}
+        sets[ap] = (ref_file, {"n": n, "k": k, "cum": cum, "bins_per_chr": bpc, "bins_total": int(len(mask))})
 
     def get_weights(self, ref_file, ap):
         self._ensure_ref(ref_file, ap)
@@ -87,19 +92,22 @@ class PredictEngine:
         """Batch form: samples = list of sample dicts -> (z, r, nref [B, n - ct], m_lr [B], m_z [B])."""
         self._ensure_ref(ref_file, ap)
         meta = self.meta[ap]
-        raw = np.stack([raw_vector(s, meta["bins_per_chr"]) for s in samples])
-        b = raw.shape[0]
+        # page-locked staging for everything that crosses PCIe (0.6 GB at batch 96); _lib.pinned recycles the buffers
+        b = len(samples)
+        raw = _lib.pinned.empty((b, meta["bins_total"]))
+        for i, s in enumerate(samples):
+            raw_vector(s, meta["bins_per_chr"], out=raw[i])
         nout = meta["n"] - ct
-        z = np.empty((b, nout)); r = np.empty((b, nout)); nref = np.empty((b, nout))
+        z = _lib.pinned.empty((b, nout)); r = _lib.pinned.empty((b, nout)); nref = _lib.pinned.empty((b, nout))
         m_lr = np.empty(b); m_z = np.empty(b)
         _lib.check(_lib.load().wcx_predict_normalize(self.ctx.handle, SET_ID[ap], _ptr(raw), b, float(cutoff), int(cp), int(ct),
                                                      _ptr(z), _ptr(r), _ptr(nref), _ptr(m_lr), _ptr(m_z)))
+        accumulate_ms(self.ctx, ("coverage_project", "gather_list", "passes", "medians"))
         return z, r, nref, m_lr, m_z
 
     def stage_ms(self):
-        out = np.zeros(4)
-        _lib.check(_lib.load().wcx_predict_stage_ms(self.ctx.handle, _ptr(out)))
-        return {"coverage_project": out[0], "normalize_repeat": out[1], "segment_z": out[2]}
+        """Device milliseconds of the last calls (wcx_predict_stage_ms)."""
+        return stage_ms(self.ctx)
 
     def segment_zscore(self, nr, inflate_pos, r, w, seg_se, seg_r):
         nr = np.ascontiguousarray(nr, dtype=np.float64)
@@ -109,9 +117,32 @@ class PredictEngine:
         seg_se = np.ascontiguousarray(seg_se, dtype=np.int64).reshape(-1, 2)
         seg_r = np.ascontiguousarray(seg_r, dtype=np.float64)
         out = np.empty(len(seg_r), dtype=np.float64)
-        _lib.check(_lib.load().wcx_segment_zscore(self.ctx.handle, _ptr(nr), nr.shape[0], nr.shape[1], _ptr(inflate_pos), _ptr(r),
-                                                  _ptr(w), len(r), _ptr(seg_se), _ptr(seg_r), len(seg_r), _ptr(out)))
+        # the null ratios belong to the reference: upload them once per array object (strong reference kept on the
+        # context), later calls pass NULL
+        resident = getattr(self.ctx, "z_nr_obj", None) is nr
+        self.ctx.z_nr_obj = None
+        _lib.check(_lib.load().wcx_segment_zscore(self.ctx.handle, None if resident else _ptr(nr), nr.shape[0], nr.shape[1],
+                                                  _ptr(inflate_pos), _ptr(r), _ptr(w), len(r), _ptr(seg_se), _ptr(seg_r),
+                                                  len(seg_r), _ptr(out)))
+        if len(seg_r):
+            self.ctx.z_nr_obj = nr
+            accumulate_ms(self.ctx, ("segment_z",))
         return out
+
+
+def stage_ms(ctx):
+    out = np.zeros(8)
+    _lib.check(_lib.load().wcx_predict_stage_ms(ctx.handle, _ptr(out)))
+    return {"coverage_project": out[0], "normalize_repeat": out[1], "segment_z": out[2], "cbs": out[3],
+            "gather_list": out[4], "passes": out[5], "medians": out[6]}
+
+
+def accumulate_ms(ctx, keys):
+    """Adds the device times of the call that just returned to the context's running totals (bench / CLI timings)."""
+    acc = ctx.__dict__.setdefault("kernel_ms_acc", {})
+    sm = stage_ms(ctx)
+    for k in keys:
+        acc[k] = acc.get(k, 0.0) + float(sm[k])
 
 
 _engines = {}
