@@ -57,6 +57,9 @@ int wcx_host_free(void* p);
  *   per/cum = masked_bins_per_chr(_cum) (C entries; C > 22 selects the gonosomal behaviour of
  *   newref_tools.py:186-191).  Copies (or borrows, if x_on_device) X and prepares the
  *   tensor-core operands.  A borrowed device X must stay alive until the next load/destroy.
+ *   x_on_device: 0 host pointer, 1 device pointer on the context's device (borrowed), 2 the corrected matrix left in
+ *   this context by wcx_pca_apply (x ignored), 3 device pointer on ANY device of the box (copied once, e.g. the
+ *   matrix prepared on GPU 0 when the target-bin parts are spread over several GPUs).
  */
 int wcx_newref_load(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, const int64_t* per,
                     const int64_t* cum, int32_t c, int32_t x_on_device);
@@ -139,6 +142,9 @@ int wcx_pca_distance(wcx_ctx* ctx, const double* corrected, int64_t n, int32_t s
  *   wcx_newref_load(x = NULL, x_on_device = 2)                    loads the corrected matrix for get_reference.
  * wcx_prep_fetch copies a resident matrix to the host (which = 0: normalised + masked, 1: corrected). */
 int wcx_prep_fetch(wcx_ctx* ctx, int32_t which, int64_t n, int32_t s, double* out);
+/* Device pointer of a resident matrix (which as above) after the context's stream has drained: input of
+ * wcx_newref_load(x_on_device = 3) on another context / GPU.  Valid until the next preparation call on `ctx`. */
+int wcx_prep_device_ptr(wcx_ctx* ctx, int32_t which, int64_t n, int32_t s, const double** out);
 /* Device milliseconds: out[0] = mean + Gram, out[1] = components + correction, out[2] = medians + distances. */
 int wcx_newref_prep_stage_ms(wcx_ctx* ctx, double* out4);
 

@@ -60,3 +60,26 @@ def test_newref_then_predict(workdir):
     assert 0.4 < float(gains[0][3]) < 0.7  # log2(1.5) = 0.585
     bins = open(outid + "_bins.bed").read().splitlines()
     assert bins[0] == "chr\tstart\tend\tid\tratio\tzscore" and len(bins) == 1 + int(np.sum(r["bins_per_chr.F"]))
+
+
+def test_newref_multi_device_equals_single(workdir):
+    """`newref --gpus N`: the target bins of every part are cut into one row range per device, every device context gets
+    its own copy of the prepared matrix (wcx_newref_load x_on_device = 3) and writes its rows into the shared result
+    arrays from its own host thread.  Three contexts on the one GPU of the test box exercise exactly that path; the result
+    must equal the single-context run bit for bit (same null-sample draws: random is seeded)."""
+    import random
+    from wisecondorx_b200 import main as wmain, newref_control
+    samples, genders = synth.make_samples(24, 2_000_000, seed=77, depth=6e6)
+    arr = np.array(samples)
+    mask, bpc = wmain.get_mask(arr)
+    outs = []
+    for devices, parts in (([0], 1), ([0, 0, 0], 1), ([0, 0], 3)):
+        prep = newref_control.tool_newref_prep(list(arr), "A", mask.copy(), bpc, 0)
+        random.seed(11)
+        outs.append(newref_control.tool_newref_main(prep, 80, parts, 0, devices))
+    a, b, c = outs
+    assert np.array_equal(a["indexes"], b["indexes"]) and np.array_equal(a["distances"], b["distances"])
+    assert np.array_equal(a["null_ratios"], b["null_ratios"], equal_nan=True)
+    # three parts draw three sets of null samples: indexes / distances are unaffected
+    assert np.array_equal(a["indexes"], c["indexes"]) and np.array_equal(a["distances"], c["distances"])
+    assert c["null_ratios"].shape == a["null_ratios"].shape

@@ -366,3 +366,38 @@ def test_fused_null_kernel_experiment_subprocess():
         got = np.load(out)
         assert np.array_equal(got["idx"], idx) and np.array_equal(got["dist"], dist)
         assert np.array_equal(got["nr"], nr, equal_nan=True)
+
+
+@pytest.mark.parametrize("k", [300, 101, 64, 25, 200, 333])
+def test_null_ratio_fast_path_equals_exact_selection(eng, k):
+    """The thread-per-median kernel (15-bit order-preserving codes, packed fp16 bisection) against the exact
+    warp-cooperative 64-bit selection (WCX_NULL_WARP=1) and the oracle on data built to break it: heavy ties
+    (quantised values -> many reference bins inside one code cell), a constant column, a column with NaN and one with
+    inf, -1 fillers, rows whose indexes are all the same bin, odd / even / unaligned k."""
+    rng = np.random.default_rng(k)
+    n, s = 6000, 24
+    per = np.array([1500, 1200, 900, 700, 500, 400] + [50] * 16)
+    x = 1.0 + 0.05 * rng.standard_normal((n, s))
+    x[:, 3] = np.round(x[:, 3] * 64) / 64          # ~20 distinct values: every median sits in a tie
+    x[:, 5] = 0.75                                   # no spread
+    x[rng.integers(0, n, 40), 7] = np.nan
+    x[rng.integers(0, n, 5), 9] = np.inf
+    x[:, 11] = np.round(x[:, 11] * 4096) / 4096     # mild ties
+    cum = np.cumsum(per)
+    rows = 700
+    idx = rng.integers(0, n - 1500, size=(rows, k)).astype(np.int32)
+    idx[5, :] = 17                                   # placeholder-like row
+    idx[6, k // 2:] = -1                             # fillers wrap to the last bin
+    idx[7, :] = np.arange(k)                         # consecutive bins
+    ids = list(range(s))
+    eng.load(x, per, cum)
+    want = np_oracle.null_ratios(x, idx, 100, 100 + rows, ids)
+    got = eng.null_ratios(100, 100 + rows, k, ids, idx=idx)
+    os.environ["WCX_NULL_WARP"] = "1"
+    try:
+        legacy = eng.null_ratios(100, 100 + rows, k, ids, idx=idx)
+    finally:
+        del os.environ["WCX_NULL_WARP"]
+    assert np.array_equal(got, legacy, equal_nan=True)  # same medians, same final division / log2
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14, equal_nan=True)
+    assert np.isnan(got[:, 7]).any() and not np.isnan(got[:, 0]).any()

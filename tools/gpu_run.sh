@@ -21,8 +21,24 @@ for S in $STEPS; do
     ncu_predict)
       timeout 900 ncu --set full --clock-control none -k 'regex:normalize_pass|nanmedian|radix_|weights_kernel|cutoff_partial|segment_z|cbs_prepare|cbs_tailp|cbs_maxarc|coverage_gather|project_apply' -c 48 -f -o gpurun_out/${TAG}_prof_predict python tools/predict_profile.py > gpurun_out/${TAG}_prof_predict.log 2>&1
       python tools/ncu_summary.py gpurun_out/${TAG}_prof_predict.ncu-rep > gpurun_out/${TAG}_ncu_predict.txt 2>&1
-      [ $(stat -c %s gpurun_out/${TAG}_prof_predict.ncu-rep) -gt 30000000 ] && rm -f gpurun_out/${TAG}_prof_predict.ncu-rep  # gpurun_out is capped at 64 MiB
+      [ -f gpurun_out/${TAG}_prof_predict.ncu-rep ] && [ $(stat -c %s gpurun_out/${TAG}_prof_predict.ncu-rep) -gt 30000000 ] && rm -f gpurun_out/${TAG}_prof_predict.ncu-rep  # gpurun_out is capped at 64 MiB
       tail -3 gpurun_out/${TAG}_prof_predict.log | cut -c1-300 ;;
+    prof_batch) echo "=== predict batch 96: host profile + CBS launch list"
+      timeout 600 python tools/predict_profile.py --batch 96 --cprofile > gpurun_out/${TAG}_batch96_cprofile.txt 2>&1
+      head -c 3000 gpurun_out/${TAG}_batch96_cprofile.txt | tail -c 1500
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:cbs_|segment_z' --csv --log-file gpurun_out/${TAG}_batch96_cbs_launches.csv python tools/predict_profile.py --batch 96 > gpurun_out/${TAG}_batch96_cbs_launches.log 2>&1
+      python - <<PYEOF
+import csv, collections
+rows = list(csv.reader(open("gpurun_out/${TAG}_batch96_cbs_launches.csv")))
+hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+ki, vi = rows[hdr].index("Kernel Name"), rows[hdr].index("Metric Value")
+acc = collections.Counter(); cnt = collections.Counter()
+for r in rows[hdr + 2:]:
+    if len(r) > vi:
+        n = r[ki].split("(")[0][:60]; acc[n] += float(r[vi].replace(",", "")); cnt[n] += 1
+for n, v in acc.most_common(): print("%-60s %6d launches %10.3f ms" % (n, cnt[n], v / 1e6))
+PYEOF
+      ;;
     *) echo "=== custom: $S"; timeout 1200 bash -c "$S" 2>&1 | tail -30 ;;
   esac
 done

@@ -1,33 +1,49 @@
 #!/usr/bin/env python
-"""One predict pass (normalize for 1 sample, CBS, segment z-scores) against a config-3-size reference built on the
-GPU -- the workload the ncu captures of the predict / CBS kernels are taken on (tools/gpu_run.sh ncu_predict)."""
-import os
-import sys
+"""The predict workload the ncu captures / host profiles are taken on: `WisecondorX newref` on 500 synthetic samples at
+15 kb (so the reference is the real thing: A / F / M sets, PCA model, masks, null ratios), then the library's predict flow
+(predict_control.predict_batch: both normalize calls, assembly, CBS, segment z-scores) for a batch of samples.
 
-import numpy as np
-import torch
+    python tools/predict_profile.py [--batch 1] [--cprofile]      (tools/gpu_run.sh ncu_predict / prof_batch)
+"""
+import argparse
+import cProfile
+import io
+import json
+import os
+import pstats
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from wisecondorx_b200 import _lib, newref_tools  # noqa: E402
 
 
 def main():
-    workload = sys.argv[1] if len(sys.argv) > 1 else "config3"
-    x, per, cum = bench.make_workload(workload)
-    n, s = x.shape
-    dev = torch.device("cuda", 0)
-    eng = newref_tools.NewrefEngine(0, _lib.Context(0))
-    k, m = bench.REFSIZE, min(s, bench.NULL_M)
-    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
-    dist = torch.empty((n, k), dtype=torch.float64, device=dev)
-    nr = torch.empty((n, m), dtype=torch.float64, device=dev)
-    eng.load(x, per, cum)
-    eng.reference(0, n, k, np.arange(m, dtype=np.int32), device_out=(idx.data_ptr(), dist.data_ptr(), nr.data_ptr()))
-    torch.cuda.synchronize()
-    out = bench.predict_extras(eng, x, per, cum, idx, dist, nr, 0, batches=(1,))
-    print(out)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--train", type=int, default=500)
+    ap.add_argument("--cprofile", action="store_true")
+    a = ap.parse_args()
+    if a.cprofile:
+        pr = cProfile.Profile()
+        orig = bench.predict_batch_timed
+
+        def wrapped(*args, **kw):
+            if args[2] >= a.batch and a.batch > 1:
+                pr.enable()
+                try:
+                    return orig(*args, **kw)
+                finally:
+                    pr.disable()
+            return orig(*args, **kw)
+
+        bench.predict_batch_timed = wrapped
+    out = bench.cli_and_predict_extras(0, n_train=a.train, batch=max(a.batch, 1), cpu_baseline=False, batches=(1, a.batch) if a.batch > 1 else (1,))
+    print(json.dumps(out["predict"]))
+    if a.cprofile:
+        sio = io.StringIO()
+        pstats.Stats(pr, stream=sio).sort_stats("cumulative").print_stats(45)
+        print(sio.getvalue())
 
 
 if __name__ == "__main__":

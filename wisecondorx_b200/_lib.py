@@ -68,6 +68,7 @@ def load():
     L.wcx_newref_normalize_and_mask.argtypes = [vp, vp, i64, i32, vp, i64, vp, i32]
     L.wcx_pca_gram.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.wcx_prep_fetch.argtypes = [vp, i32, i64, i32, vp]
+    L.wcx_prep_device_ptr.argtypes = [vp, i32, i64, i32, ctypes.POINTER(vp)]
     L.wcx_debug_leaf_layout.argtypes = [i32, vp, i32, vp, i32, vp, i32, vp]
     L.wcx_pca_apply.argtypes = [vp, vp, vp, i32, vp, vp, i32]
     L.wcx_pca_distance.argtypes = [vp, vp, i64, i32, i32, vp, vp]

@@ -99,17 +99,14 @@ def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None
     """CBS.R for a batch of samples [(results_r, results_w, ref_gender), ...] with ONE device call over all
     (sample, chromosome) series.  The permutation streams are keyed by (seed, chromosome), not by the position of a
     series in the batch, so every sample gets the segments it would get alone."""
+    from .predict_control import _map_threads
     seed_i = 0 if seed is None else int(seed)
     preps, series, ids, counts = [], [], [], []
-    for results_r, results_w, ref_gender in samples:
-        p, s, i = _cbs_prepare(results_r, results_w, ref_gender)
+    for p, s, i in _map_threads(lambda t: _cbs_prepare(*t), samples):
         preps.append(p); series += s; ids += i; counts.append(len(s))
     all_ends = segment_series(series, ids, alpha, nperm, seed_i, ctx)
-    out, o = [], 0
-    for p, n in zip(preps, counts):
-        out.append(_cbs_finish(p, all_ends[o:o + n], binsize))
-        o += n
-    return out
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(int)
+    return _map_threads(lambda j: _cbs_finish(preps[j], all_ends[offs[j]:offs[j + 1]], binsize), range(len(preps)))
 
 
 def exec_cbs(rem_input, results, engine: predict_tools.PredictEngine | None = None, nperm=10000):

@@ -96,7 +96,7 @@ struct wcx_ctx {
   // predict state
   RefSet ref[3];
   DevBuf p_partial, p_totals, p_tdots, p_state, p_raw, p_x, p_copy_a, p_copy_b, p_z, p_r, p_n, p_mlr, p_mz, p_w;
-  DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out, p_radix;
+  DevBuf z_nr, z_pos, z_r, z_w, z_se, z_segr, z_out, z_partial, p_radix;
   double predict_ms[8] = {};
   int64_t z_nr_rows = -1;  // null ratios resident for wcx_segment_zscore(nr = NULL)
   int32_t z_nr_m = 0;
@@ -187,7 +187,7 @@ void wcx_destroy(wcx_ctx* c) {
                     &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev, &c->leaves_dev,
                     &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->xp, &c->perm_dev, &c->leafdesc_dev, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
-                    &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out, &c->p_radix})
+                    &c->p_n, &c->p_mlr, &c->p_mz, &c->p_w, &c->z_nr, &c->z_pos, &c->z_r, &c->z_w, &c->z_se, &c->z_segr, &c->z_out, &c->z_partial, &c->p_radix})
     b->release();
   for (DevBuf* b : {&c->q_counts, &c->q_pos, &c->q_colsum, &c->q_x, &c->q_mean, &c->q_partial, &c->q_gram, &c->q_u, &c->q_sigma,
                     &c->q_comps, &c->q_corr, &c->q_med, &c->q_d, &c->q_work})
@@ -258,7 +258,13 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   c->k_pad_h = (s + 2 * WCX_KBLOCK - 1) / (2 * WCX_KBLOCK) * (2 * WCX_KBLOCK);
   c->n_pad = (n + 255) / 256 * 256 + 256;
   cudaStream_t st = c->stream;
-  if (x_on_device) {
+  if (x_on_device == 3) {
+    // a device pointer that may live on ANOTHER GPU of the box (multi-GPU newref: the corrected matrix is prepared on
+    // one device): one copy over NVLink / PCIe into this context's own buffer (unified addressing resolves the source)
+    if (c->x_buf.ensure(sizeof(double) * (size_t)n * s)) return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(c->x_buf.p, x, sizeof(double) * (size_t)n * s, cudaMemcpyDefault, st));
+    c->d_x = c->x_buf.as<double>();
+  } else if (x_on_device) {
     c->d_x = x;
   } else {
     if (c->x_buf.ensure(sizeof(double) * (size_t)n * s)) return 1;
@@ -364,6 +370,14 @@ static void build_items(const wcx_ctx* c, int64_t rb, int64_t re, int tile_n, in
 
 // null ratios requested together with the top-k (wcx_newref_reference): computed inside the re-rank kernel when
 // the shape allows it, otherwise by the stand-alone kernels after it
+// rows [r0, r1) of a call (relative to row_begin) whose candidate lists share one layout: nsplit column ranges x lists
+// per range, the first list of the region at slot_base
+struct Region {
+  int64_t r0, r1;
+  int nsplit;
+  size_t slot_base;
+};
+
 struct NullPlan {
   const int32_t* sample_ids;
   int32_t m;
@@ -433,35 +447,77 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     const int tile_n = kernel == WCX_KERNEL_SIMT ? WCX_TILE_N_SIMT : WCX_TILE_N_TC;
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device);
-    // column splits: enough work items to balance a persistent grid when the part has few row tiles
+    // Work items.  Every item is one tile of 128 target rows against a range of candidate column tiles; a persistent
+    // grid takes them round-robin, so the sweep lasts ceil(units / CTAs) unit times.  Two regions of rows:
+    //   A  the units that fill whole rounds of the grid: one item per row tile over ALL columns (2 lists per row);
+    //   B  the units of the last, partial round: split into sB column ranges each (2 sB lists per row), so the tail
+    //      costs ceil(L sB / CTAs) / sB of a unit time instead of a whole one.  At config 3 the last of 11 rounds
+    //      held 9 of 74 CTA pairs busy; on 1/8 of the rows (8 GPUs) it was 2.53 rounds of work in 3.
     std::vector<WorkItem> items;
     const int lps = kernel == WCX_KERNEL_SIMT ? 1 : 2;  // the tcgen05 kernel keeps one list per epilogue group
     build_items(c, rb, re, tile_n, 1, lps, items);
-    const int64_t row_tiles = (int64_t)items.size();
-    int nsplit = 1;
     const int nct = (int)((c->n + tile_n - 1) / tile_n);
-    while (nsplit < 2 && row_tiles * nsplit < 4 * dev_sms && nct / (nsplit * 2) >= 8) nsplit *= 2;
-    if (nsplit > 1) {
-      items.clear();
-      build_items(c, rb, re, tile_n, nsplit, lps, items);
-    }
+    Region regA{0, rows, 1, 0}, regB{rows, rows, 1, 0};
     if (pair) {
-      // pair mode: items (2p, 2p + 1) must share the candidate-column range -> group by split, pad odd groups
-      std::vector<WorkItem> paired;
-      for (int q = 0; q < nsplit; q++) {
+      const int n_units = ((int)items.size() + 1) / 2;
+      const int P = std::max(1, dev_sms / 2);  // CTA pairs of the persistent grid
+      static const char* split_env = std::getenv("WCX_TAIL_SPLIT");  // tests: force a split factor (1 = off)
+      const int full_units = (n_units / P) * P;
+      const int L = n_units - full_units;
+      int sB = 1;
+      if (L > 0) {
+        double best = 1.0;  // duration of the tail in unit times
+        for (int sc = 2; sc <= 8 && nct / sc >= 8; sc *= 2) {
+          const double t = (double)((L * sc + P - 1) / P) / sc;
+          if (t < best - 1e-9) { best = t; sB = sc; }
+        }
+        if (split_env) { const int f = std::atoi(split_env); if (f >= 1 && f <= 8 && (f & (f - 1)) == 0 && nct / f >= 1) sB = f; }
+      }
+      std::vector<WorkItem> base;
+      base.swap(items);
+      const size_t nA = std::min(base.size(), (size_t)2 * full_units);
+      const int64_t rowsA = nA < base.size() ? (int64_t)base[nA].row0 - rb : rows;
+      regA = Region{0, rowsA, 1, 0};
+      regB = Region{rowsA, rows, sB, (size_t)rowsA * lps};
+      for (size_t i = 0; i < nA; i++) items.push_back(base[i]);  // slot0 / stride of build_items(nsplit = 1) are region A's
+      // region B: pair mode wants items (2p, 2p + 1) on the same column range -> split-major order, odd groups padded
+      for (int q = 0; q < sB; q++) {
         int cnt = 0;
         WorkItem last{};
-        for (const WorkItem& w : items)
-          if ((w.slot0 % (nsplit * lps)) / lps == q) { paired.push_back(w); last = w; cnt++; }
+        for (size_t i = nA; i < base.size(); i++) {
+          WorkItem w = base[i];
+          w.ct_begin = (int)((int64_t)nct * q / sB);
+          w.ct_end = (int)((int64_t)nct * (q + 1) / sB);
+          w.slot0 = (int32_t)(regB.slot_base + ((int64_t)w.row0 - rb - rowsA) * sB * lps + q * lps);
+          w.slot_stride = sB * lps;
+          items.push_back(w);
+          last = w;
+          cnt++;
+        }
         if (cnt & 1) {
           WorkItem d = last;
           d.row0 = 0; d.nrows = 0; d.slot0 = 0;
-          paired.push_back(d);
+          items.push_back(d);
         }
       }
-      items.swap(paired);
+      if (regB.r1 == regB.r0 && (items.size() & 1)) {  // no region B: pad region A's odd item count
+        WorkItem d = items.back();
+        d.row0 = 0; d.nrows = 0; d.slot0 = 0;
+        items.push_back(d);
+      }
+    } else {
+      // one CTA per SM / CUDA-core kernels (cross-check paths): one uniform column split as before
+      const int64_t row_tiles = (int64_t)items.size();
+      int nsplit = 1;
+      while (nsplit < 2 && row_tiles * nsplit < 4 * dev_sms && nct / (nsplit * 2) >= 8) nsplit *= 2;
+      if (nsplit > 1) {
+        items.clear();
+        build_items(c, rb, re, tile_n, nsplit, lps, items);
+      }
+      regA = Region{0, rows, nsplit, 0};
     }
-    const size_t slots = (size_t)rows * nsplit * lps;
+    const size_t slots = (size_t)(regA.r1 - regA.r0) * regA.nsplit * lps + (size_t)(regB.r1 - regB.r0) * regB.nsplit * lps;
+    if (slots > 0x7fffffffull) { set_error("wcx_newref_topk: too many candidate lists for one call (split the row range)"); return 1; }
     if (c->cand_ent.ensure(sizeof(uint2) * slots * WCX_CAND_CAP) || c->cand_cnt.ensure(sizeof(int32_t) * slots) || c->cand_cut.ensure(sizeof(float) * slots))
       return 1;
     if (c->items_dev.ensure(sizeof(WorkItem) * std::max<size_t>(items.size(), 1)) || c->counter.ensure(sizeof(int32_t))) return 1;
@@ -485,47 +541,55 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       // high-priority stream next to the re-rank of the following block (the re-rank waits on gathers at ~50 %
       // issue utilisation, the median selection is issue bound), and with host outputs the D2H copy of a finished
       // block (copy stream) overlaps the kernels of the next one.
-      const int nlists = nsplit * lps;
       static const bool serial_nulls = std::getenv("WCX_SERIAL_NULLS") != nullptr;
       const bool side = d_null && !fused && !serial_nulls;   // null ratios on the side stream
-      const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(8, rows / 12000));  // >= 12 k rows per block: two full waves of the null kernel
-      for (int bq = 0; bq < nblk; bq++) {
-        const int64_t r0 = rows * bq / nblk, r1 = rows * (bq + 1) / nblk;
-        if (r1 <= r0) continue;
-        CandView cvb{cv.ent + (size_t)r0 * nlists * WCX_CAND_CAP, cv.cnt + r0 * nlists, cv.cut + r0 * nlists, cv.diag};
-        if (launch_rerank(c->d_x, pv, cvb, nlists, c->cum_dev.as<int64_t>(), c->nchr, rb + r0, rb + r1, k, gon,
-                          c->idx_dev.as<int32_t>() + r0 * k, c->dist_dev.as<double>() + r0 * k, c->fail.as<int32_t>() + r0,
-                          c->plan_dev.as<int32_t>(), c->plan_len, c->leaf_n ? c->xp.as<double>() : nullptr, c->sp,
-                          c->leafdesc_dev.as<int32_t>(), c->leaf_n, fused ? c->xt.as<double>() : nullptr, fused ? np->m : 0,
-                          fused ? d_null + r0 * np->m : nullptr, st))
-          return 1;
-        c->launches += bq ? 1 : 0;
-        WCX_CUDA_OK(cudaEventRecord(c->ev_blk[bq], st));
-        cudaEvent_t ready = c->ev_blk[bq];
-        if (d_null && !fused) {
-          cudaStream_t ns = side ? c->null_stream : st;
-          if (side) WCX_CUDA_OK(cudaStreamWaitEvent(ns, c->ev_blk[bq], 0));
-          if (launch_null_ratios(c->xt.as<double>(), c->n, c->idx_dev.as<int32_t>() + r0 * k, rb + r0, rb + r1, k, np->m,
-                                 d_null + r0 * np->m, ns))
+      int bq = 0;       // block counter over both regions (events)
+      int last_blk = -1;
+      for (const Region& rg : {regA, regB}) {
+        const int64_t rrows = rg.r1 - rg.r0;
+        if (rrows <= 0) continue;
+        const int nlists = rg.nsplit * lps;
+        const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(rg.nsplit > 1 && pair ? 2 : 8, rrows / 12000));  // >= 12 k rows per block: two full waves of the null kernel
+        for (int bi = 0; bi < nblk; bi++, bq++) {
+          const int64_t r0 = rg.r0 + rrows * bi / nblk, r1 = rg.r0 + rrows * (bi + 1) / nblk;
+          if (r1 <= r0) continue;
+          const size_t s0 = rg.slot_base + (size_t)(r0 - rg.r0) * nlists;
+          CandView cvb{cv.ent + s0 * WCX_CAND_CAP, cv.cnt + s0, cv.cut + s0, cv.diag};
+          if (launch_rerank(c->d_x, pv, cvb, nlists, c->cum_dev.as<int64_t>(), c->nchr, rb + r0, rb + r1, k, gon,
+                            c->idx_dev.as<int32_t>() + r0 * k, c->dist_dev.as<double>() + r0 * k, c->fail.as<int32_t>() + r0,
+                            c->plan_dev.as<int32_t>(), c->plan_len, c->leaf_n ? c->xp.as<double>() : nullptr, c->sp,
+                            c->leafdesc_dev.as<int32_t>(), c->leaf_n, fused ? c->xt.as<double>() : nullptr, fused ? np->m : 0,
+                            fused ? d_null + r0 * np->m : nullptr, st))
             return 1;
-          c->launches += (np->m + 7) / 8;
-          WCX_CUDA_OK(cudaEventRecord(c->ev_null[bq], ns));
-          ready = c->ev_null[bq];
-        }
-        if (!out_on_device) {
-          WCX_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
-          if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out + r0 * k, c->idx_dev.as<int32_t>() + r0 * k, sizeof(int32_t) * (size_t)(r1 - r0) * k, cudaMemcpyDeviceToHost, c->copy_stream));
-          if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out + r0 * k, c->dist_dev.as<double>() + r0 * k, sizeof(double) * (size_t)(r1 - r0) * k, cudaMemcpyDeviceToHost, c->copy_stream));
-          if (d_null) WCX_CUDA_OK(cudaMemcpyAsync(np->out + r0 * np->m, d_null + r0 * np->m, sizeof(double) * (size_t)(r1 - r0) * np->m, cudaMemcpyDeviceToHost, c->copy_stream));
+          c->launches += 1;
+          WCX_CUDA_OK(cudaEventRecord(c->ev_blk[bq], st));
+          cudaEvent_t ready = c->ev_blk[bq];
+          if (d_null && !fused) {
+            cudaStream_t ns = side ? c->null_stream : st;
+            if (side) WCX_CUDA_OK(cudaStreamWaitEvent(ns, c->ev_blk[bq], 0));
+            if (launch_null_ratios(c->xt.as<double>(), c->n, c->idx_dev.as<int32_t>() + r0 * k, rb + r0, rb + r1, k, np->m,
+                                   d_null + r0 * np->m, ns))
+              return 1;
+            c->launches += (np->m + 7) / 8;
+            WCX_CUDA_OK(cudaEventRecord(c->ev_null[bq], ns));
+            ready = c->ev_null[bq];
+            last_blk = bq;
+          }
+          if (!out_on_device) {
+            WCX_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+            if (idx_out) WCX_CUDA_OK(cudaMemcpyAsync(idx_out + r0 * k, c->idx_dev.as<int32_t>() + r0 * k, sizeof(int32_t) * (size_t)(r1 - r0) * k, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (dist_out) WCX_CUDA_OK(cudaMemcpyAsync(dist_out + r0 * k, c->dist_dev.as<double>() + r0 * k, sizeof(double) * (size_t)(r1 - r0) * k, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (d_null) WCX_CUDA_OK(cudaMemcpyAsync(np->out + r0 * np->m, d_null + r0 * np->m, sizeof(double) * (size_t)(r1 - r0) * np->m, cudaMemcpyDeviceToHost, c->copy_stream));
+          }
         }
       }
       // the caller's stream owns the results again once the side stream has drained
       WCX_CUDA_OK(cudaEventRecord(c->ev_tail[0], st));
-      if (side) WCX_CUDA_OK(cudaStreamWaitEvent(st, c->ev_null[nblk - 1], 0));
+      if (side && last_blk >= 0) WCX_CUDA_OK(cudaStreamWaitEvent(st, c->ev_null[last_blk], 0));
       WCX_CUDA_OK(cudaEventRecord(c->ev_tail[1], st));
     }
     WCX_CUDA_OK(cudaEventRecord(c->ev[2], st));
-    c->launches += 2;
+    c->launches += 1;
     std::vector<int32_t> flags((size_t)rows);
     uint32_t diag_h[8] = {};
     WCX_CUDA_OK(cudaMemcpyAsync(diag_h, c->diag.p, sizeof(diag_h), cudaMemcpyDeviceToHost, st));
@@ -543,7 +607,7 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     cudaEventElapsedTime(&ms, c->ev[1], c->ev_tail[0]);
     c->stage_ms[1] = ms;
     c->stats[0] = (int64_t)items.size();
-    c->stats[3] = nsplit;
+    c->stats[3] = regB.r1 > regB.r0 ? regB.nsplit : regA.nsplit;
     c->stats[5] = diag_h[0];
     c->stats[6] = diag_h[1];
     c->stats[7] = diag_h[2];
@@ -958,11 +1022,11 @@ int wcx_segment_zscore(wcx_ctx* c, const double* nr, int64_t n_masked, int32_t m
   if (h2d(c->z_pos, inflate_pos, sizeof(int32_t) * (size_t)bins_total, st) ||
       h2d(c->z_r, r, sizeof(double) * (size_t)bins_total, st) || h2d(c->z_w, w, sizeof(double) * (size_t)bins_total, st) ||
       h2d(c->z_se, seg_se, sizeof(int64_t) * 2 * (size_t)nseg, st) || h2d(c->z_segr, seg_r, sizeof(double) * (size_t)nseg, st) ||
-      c->z_out.ensure(sizeof(double) * (size_t)nseg))
+      c->z_out.ensure(sizeof(double) * (size_t)nseg) || c->z_partial.ensure(segment_z_scratch_bytes(nseg)))
     return 1;
   WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
   if (launch_segment_z(c->z_nr.as<double>(), m, c->z_pos.as<int32_t>(), c->z_r.as<double>(), c->z_w.as<double>(),
-                       c->z_se.as<int64_t>(), c->z_segr.as<double>(), nseg, c->z_out.as<double>(), st))
+                       c->z_se.as<int64_t>(), c->z_segr.as<double>(), nseg, c->z_out.as<double>(), c->z_partial.as<double>(), st))
     return 1;
   WCX_CUDA_OK(cudaEventRecord(c->ev[1], st));
   WCX_CUDA_OK(cudaMemcpyAsync(z_out, c->z_out.p, sizeof(double) * (size_t)nseg, cudaMemcpyDeviceToHost, st));
@@ -970,7 +1034,7 @@ int wcx_segment_zscore(wcx_ctx* c, const double* nr, int64_t n_masked, int32_t m
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->predict_ms[2] = ms;
-  c->launches += 1;
+  c->launches += 2;
   return 0;
 }
 
@@ -1147,6 +1211,16 @@ int wcx_prep_fetch(wcx_ctx* c, int32_t which, int64_t n, int32_t s, double* out)
   WCX_CUDA_OK(cudaSetDevice(c->device));
   WCX_CUDA_OK(cudaMemcpyAsync(out, b.p, sizeof(double) * (size_t)n * s, cudaMemcpyDeviceToHost, c->stream));
   WCX_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int wcx_prep_device_ptr(wcx_ctx* c, int32_t which, int64_t n, int32_t s, const double** out) {
+  if (!c || !out || c->q_n != n || c->q_s != s) { set_error("wcx_prep_device_ptr: bad argument or shape"); return 1; }
+  const DevBuf& b = which == 0 ? c->q_x : c->q_corr;
+  if (!b.p || b.cap < sizeof(double) * (size_t)n * s) { set_error("wcx_prep_device_ptr: that matrix is not resident"); return 1; }
+  WCX_CUDA_OK(cudaSetDevice(c->device));
+  WCX_CUDA_OK(cudaStreamSynchronize(c->stream));  // the caller may hand the pointer to another context / device
+  *out = b.as<double>();
   return 0;
 }
 

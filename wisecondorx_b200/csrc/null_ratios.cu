@@ -13,10 +13,27 @@
 // pair of samples the warp gathers k pairs of pre-computed keys (null_ratios.cuh) and selects the two middle order statistics
 // of each with a bisection over order-preserving 64-bit keys (select.cuh) -- no sort.
 // np.median returns NaN when any value is NaN.
+#include <algorithm>
+#include <cstdlib>
+
+#include <cuda_fp16.h>
+
 #include "null_ratios.cuh"
 #include "wcx_common.cuh"
 
 namespace wcx {
+
+namespace {
+struct NqCol;
+}
+// layout of the null-ratio staging buffer (`xt`): XM keys | codes of the fast path | column maps | histograms
+struct NullStaging {
+  uint16_t* xq;
+  NqCol* cols;
+  unsigned int* hist;
+  size_t bytes;
+};
+NullStaging null_staging(double* xt, int64_t n, int32_t m);
 
 namespace {
 
@@ -53,6 +70,318 @@ __global__ void gather_cols_kernel(const double* __restrict__ x, int64_t n, int3
   const int mm = c * NR_CHUNK + j;
   reinterpret_cast<uint64_t*>(xm)[((int64_t)c * n + r) * NR_CHUNK + j] = null_key(mm < m ? x[r * s + ids[mm]] : 0.0);
 }
+
+// =================================================================================================================
+// Fast path: one THREAD per (target bin, sample column).
+//
+// The warp-per-bin kernel above spends ~650 warp instructions per median of 300 (a 64-bit key bisection whose fixed
+// cost per step -- warp reduction, bracket bookkeeping -- is paid per column): 18 ms for the 1.9e7 medians of config 3,
+// issue bound at 0.5 % of its HBM traffic bound.  Here every sample value gets a 15-bit order-preserving CODE once per
+// call (nq_* kernels: an equal-frequency map through a 65 536-bin histogram of the column, so the ~N values of a column
+// share a code with ~N / 30 000 others), stored as the bit pattern of a positive normal fp16.  A thread keeps the codes
+// of its bin's k reference bins packed two per register (150 registers for k = 300) and selects the upper-median code by
+// a 15-step bisection in which one HSET2 + one HADD2 handle two keys: ~2 k instructions per step and thread, no
+// shuffles, no shared memory, no divergence.  The two middle VALUES are then fetched in float64 through the positions of
+// the selected codes.  A selected code that is not unique among the k keys (two reference bins inside one code cell,
+// ~1 % of the medians; columns with NaN / inf / no spread; placeholder rows) is resolved by the exact warp-cooperative
+// selection of select.cuh, one flagged median at a time -- results are identical to the kernel above in every case.
+// =================================================================================================================
+constexpr int NQ_STRIDE = 128;         // code row stride in columns (uint16)
+constexpr int NQ_HBINS = 65536;        // histogram cells per column
+constexpr uint32_t NQ_LO = 0x0400u;    // smallest code: smallest positive normal fp16
+constexpr uint32_t NQ_HI = 0x7BFEu;    // largest code (0x7BFF = largest finite fp16 is the padding key)
+constexpr uint32_t NQ_PAD = 0x7BFFu;
+
+struct NqCol {
+  double lo, scale;   // histogram cell of v: (v - lo) * scale
+  double sum, sumsq;  // accumulators of nq_stats_kernel
+  unsigned long long cnt, bad;
+  int32_t exact;      // 1: every median of this column takes the exact path (NaN / inf present or zero spread)
+  int32_t pad_;
+};
+
+__device__ __forceinline__ double nq_value(const uint64_t* __restrict__ xm, int64_t n, int64_t bin, int col) {
+  return key_d(__ldg(xm + ((int64_t)(col >> 3) * n + bin) * NR_CHUNK + (col & 7)));
+}
+__device__ __forceinline__ uint64_t nq_key(const uint64_t* __restrict__ xm, int64_t n, int64_t bin, int col) {
+  return __ldg(xm + ((int64_t)(col >> 3) * n + bin) * NR_CHUNK + (col & 7));
+}
+
+__global__ void __launch_bounds__(256)
+nq_stats_kernel(const uint64_t* __restrict__ xm, int64_t n, int m, NqCol* __restrict__ cols) {
+  __shared__ double sh[3][8];
+  const int col = blockIdx.y;
+  double s1 = 0.0, s2 = 0.0, bad = 0.0;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (int64_t)gridDim.x * blockDim.x) {
+    const double v = nq_value(xm, n, b, col);
+    if (isfinite(v)) { s1 += v; s2 += v * v; } else bad += 1.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; sh[2][threadIdx.x >> 5] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b2 = 0.0, c = 0.0;
+    for (int w = 0; w < 8; w++) { a += sh[0][w]; b2 += sh[1][w]; c += sh[2][w]; }
+    atomicAdd(&cols[col].sum, a);
+    atomicAdd(&cols[col].sumsq, b2);
+    if (c > 0.0) atomicAdd(&cols[col].bad, (unsigned long long)c);
+  }
+}
+
+__global__ void nq_map_kernel(int64_t n, int m, NqCol* __restrict__ cols) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m) return;
+  NqCol c = cols[col];
+  const double good = (double)n - (double)c.bad;
+  const double mean = good > 0.0 ? c.sum / good : 0.0;
+  double var = good > 0.0 ? c.sumsq / good - mean * mean : 0.0;
+  if (!(var > 0.0)) var = 0.0;
+  const double sd = sqrt(var);
+  c.lo = mean - 8.0 * sd;
+  c.scale = (double)NQ_HBINS / (16.0 * sd);
+  c.exact = (c.bad != 0 || !(sd > 0.0) || !isfinite(c.scale) || !isfinite(c.lo)) ? 1 : 0;
+  cols[col] = c;
+}
+
+__device__ __forceinline__ double nq_cell(double v, const NqCol& c) {
+  double t = (v - c.lo) * c.scale;
+  t = t < 0.0 ? 0.0 : t;
+  const double top = (double)NQ_HBINS - 1.0 / 1024.0;
+  return t > top ? top : t;  // NaN (exact columns only) falls through the comparisons: harmless
+}
+
+// hist[col][cell] += 1
+__global__ void __launch_bounds__(256)
+nq_hist_kernel(const uint64_t* __restrict__ xm, int64_t n, int m, const NqCol* __restrict__ cols, unsigned int* __restrict__ hist) {
+  const int col = blockIdx.y;
+  const NqCol c = cols[col];
+  if (c.exact) return;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += (int64_t)gridDim.x * blockDim.x) {
+    const double t = nq_cell(nq_value(xm, n, b, col), c);
+    atomicAdd(&hist[(int64_t)col * (NQ_HBINS + 1) + (int)t], 1u);
+  }
+}
+
+// in place: hist[col][0 .. HBINS] becomes the exclusive prefix sum (entry HBINS = total); one CTA per column
+__global__ void __launch_bounds__(1024)
+nq_prefix_kernel(unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[1024];
+  unsigned int* h = hist + (int64_t)blockIdx.x * (NQ_HBINS + 1);
+  constexpr int PER = NQ_HBINS / 1024;
+  unsigned int v[PER], run = 0;
+#pragma unroll
+  for (int j = 0; j < PER; j++) { v[j] = h[threadIdx.x * PER + j]; run += v[j]; }
+  sh[threadIdx.x] = run;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  unsigned int before = threadIdx.x ? sh[threadIdx.x - 1] : 0u;
+#pragma unroll
+  for (int j = 0; j < PER; j++) { h[threadIdx.x * PER + j] = before; before += v[j]; }
+  if (threadIdx.x == 1023) h[NQ_HBINS] = before;
+}
+
+// xq[bin][col] = code: LO + floor((prefix[cell] + frac * count[cell]) * (HI - LO + 1) / total), monotone in the value
+__global__ void __launch_bounds__(256)
+nq_code_kernel(const uint64_t* __restrict__ xm, int64_t n, int m, const NqCol* __restrict__ cols, const unsigned int* __restrict__ hist,
+               uint16_t* __restrict__ xq) {
+  const int col = threadIdx.x & (NQ_STRIDE - 1);
+  const int64_t b = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
+  if (b >= n || col >= m) return;
+  const NqCol c = cols[col];
+  uint32_t code = NQ_LO;
+  if (!c.exact) {
+    const double t = nq_cell(nq_value(xm, n, b, col), c);
+    const int cell = (int)t;
+    const unsigned int* h = hist + (int64_t)col * (NQ_HBINS + 1);
+    const double c0 = (double)h[cell], c1 = (double)h[cell + 1], tot = (double)h[NQ_HBINS];
+    const double pos = c0 + (t - (double)cell) * (c1 - c0);
+    const double q = pos * ((double)(NQ_HI - NQ_LO + 1) / tot);
+    code = NQ_LO + (uint32_t)q;
+    code = code > NQ_HI ? NQ_HI : code;
+  }
+  xq[b * NQ_STRIDE + col] = (uint16_t)code;
+}
+
+// ---- packed fp16 helpers: the codes are bit patterns of positive normal halves, so fp16 compares order them ----
+__device__ __forceinline__ uint32_t h2_lt(uint32_t a, uint32_t b) {  // 1.0h per half where a < b
+  uint32_t d;
+  asm("set.lt.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ int h2_total(uint32_t acc) {  // sum of the two (small, integral) halves
+  return (int)(__half2float(__ushort_as_half((unsigned short)(acc & 0xffffu))) +
+               __half2float(__ushort_as_half((unsigned short)(acc >> 16))));
+}
+template <int NP>
+__device__ __forceinline__ int nq_count_lt(const uint32_t (&k2)[NP], uint32_t trial) {
+  const uint32_t t2 = trial | (trial << 16);
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // four chains; each half counts at most NP / 4 + 1: exact in fp16
+#pragma unroll
+  for (int j = 0; j < NP; j += 4) {
+    a0 = h2_add(a0, h2_lt(k2[j], t2));
+    if (j + 1 < NP) a1 = h2_add(a1, h2_lt(k2[j + 1], t2));
+    if (j + 2 < NP) a2 = h2_add(a2, h2_lt(k2[j + 2], t2));
+    if (j + 3 < NP) a3 = h2_add(a3, h2_lt(k2[j + 3], t2));
+  }
+  return h2_total(a0) + h2_total(a1) + h2_total(a2) + h2_total(a3);
+}
+// largest key below `lim` (0 if none) and the position (0-based) of the LAST key equal to `code`
+template <int NP>
+__device__ __forceinline__ uint32_t nq_max_below(const uint32_t (&k2)[NP], uint32_t lim) {
+  uint32_t best = 0;
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    const uint32_t lo = k2[j] & 0xffffu, hi = k2[j] >> 16;
+    best = (lo < lim && lo > best) ? lo : best;
+    best = (hi < lim && hi > best) ? hi : best;
+  }
+  return best;
+}
+template <int NP>
+__device__ __forceinline__ int nq_find(const uint32_t (&k2)[NP], uint32_t code) {
+  int pos = -1;
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    const uint32_t x = k2[j] ^ (code | (code << 16));
+    pos = (x & 0xffffu) == 0u ? 2 * j : pos;
+    pos = (x >> 16) == 0u ? 2 * j + 1 : pos;
+  }
+  return pos;
+}
+
+// reference position -> bin of the full column: -1 (missing entries) wraps to the last bin like a Python index.  The
+// positions come from this library's own re-rank or were validated by the host (wcx_newref_null_ratios), so they lie
+// in [-n, n): no clamp on the hot path.
+__device__ __forceinline__ int32_t nq_wrap(int32_t v, int32_t n) { return v + ((v >> 31) & n); }
+
+// NP packed registers (2 NP >= k keys; FULL: k == 2 NP exactly, no bounds checks in the gather), R = slots per lane of
+// the exact warp-cooperative path (32 R >= k)
+template <int NP, int R, bool FULL>
+__global__ void __launch_bounds__(128, NP > 128 ? 2 : (NP > 64 ? 3 : 4))
+null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ xm, const NqCol* __restrict__ cols, int64_t n,
+                 const int32_t* __restrict__ idx, int64_t row_begin, int64_t rows, int k, int m, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = rows * m;
+  const int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p0 < total;
+  const int64_t p = active ? p0 : total - 1;  // whole warps stay alive for the cooperative exact path
+  const int64_t lrow = p / m;
+  const int col = (int)(p - lrow * m);
+  const int32_t* __restrict__ irow = idx + lrow * k;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double med = nan;
+  bool need_exact = cols[col].exact != 0;
+  bool done = false;
+  // rows whose k indexes are all the same bin (placeholder rows of gonosomal references, newref_tools.py:186-191):
+  // the median of k copies of a value is the value ((v + v) / 2 is exact)
+  const int32_t n32 = (int32_t)n;
+  if (irow[0] == irow[k - 1] && irow[0] == irow[k >> 1]) {
+    bool same = true;
+    for (int t = 1; t < k; t++) same &= irow[t] == irow[0];
+    if (same) {
+      med = nq_value(xm, n, nq_wrap(irow[0], n32), col);
+      done = true;
+    }
+  }
+  if (!done && !need_exact) {
+    uint32_t k2[NP];
+    const uint16_t* __restrict__ xqc = xq + col;
+    if (FULL) {
+      // k == 2 NP, rows 16-byte aligned (k % 4 == 0): four positions per 128-bit load, in groups of 8 loads so that the
+      // compiler keeps a bounded number of gathers in flight instead of hoisting all 2 NP of them
+      const int4* __restrict__ iv = reinterpret_cast<const int4*>(irow);
+#pragma unroll
+      for (int j = 0; j < NP / 2; j++) {
+        const int4 q = __ldg(iv + j);
+        const uint32_t c0 = xqc[(int64_t)nq_wrap(q.x, n32) * NQ_STRIDE];
+        const uint32_t c1 = xqc[(int64_t)nq_wrap(q.y, n32) * NQ_STRIDE];
+        const uint32_t c2 = xqc[(int64_t)nq_wrap(q.z, n32) * NQ_STRIDE];
+        const uint32_t c3 = xqc[(int64_t)nq_wrap(q.w, n32) * NQ_STRIDE];
+        k2[2 * j] = c0 | (c1 << 16);
+        k2[2 * j + 1] = c2 | (c3 << 16);
+        if ((j & 7) == 7) asm volatile("" ::: "memory");
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        uint32_t c0 = NQ_PAD, c1 = NQ_PAD;
+        if (2 * j < k) c0 = xqc[(int64_t)nq_wrap(irow[2 * j], n32) * NQ_STRIDE];
+        if (2 * j + 1 < k) c1 = xqc[(int64_t)nq_wrap(irow[2 * j + 1], n32) * NQ_STRIDE];
+        k2[j] = c0 | (c1 << 16);
+        if ((j & 15) == 15) asm volatile("" ::: "memory");
+      }
+    }
+    const int t = k >> 1;  // rank of the upper middle key (the median itself for odd k)
+    uint32_t T = 0;
+    int below = 0;
+#pragma unroll 1
+    for (int bit = 14; bit >= 0; bit--) {
+      const uint32_t trial = T | (1u << bit);
+      const int c = nq_count_lt<NP>(k2, trial);
+      if (c <= t) { T = trial; below = c; }
+    }
+    // T is the code of the rank-t key: count(< T) <= t < count(< T + 1)
+    const int eq_hi = nq_count_lt<NP>(k2, T + 1u) - below;
+    bool ok = eq_hi == 1;
+    uint32_t T_lo = T;
+    if (ok && !(k & 1)) {
+      // even k: the lower middle key (rank t - 1) is the largest key below T -- if rank t is the first key with code T
+      ok = below == t;
+      if (ok) {
+        T_lo = nq_max_below<NP>(k2, T);
+        ok = (t - nq_count_lt<NP>(k2, T_lo)) == 1;
+      }
+    }
+    if (ok) {
+      const int j_hi = nq_find<NP>(k2, T);
+      const double v_hi = nq_value(xm, n, nq_wrap(irow[j_hi], n32), col);
+      if (k & 1) {
+        med = v_hi;
+      } else {
+        const int j_lo = nq_find<NP>(k2, T_lo);
+        const double v_lo = nq_value(xm, n, nq_wrap(irow[j_lo], n32), col);
+        med = (v_lo + v_hi) / 2.0;  // np.median: mean of the two middle values
+      }
+      done = true;
+    } else {
+      need_exact = true;
+    }
+  }
+  // exact path, one flagged (bin, column) at a time by the whole warp
+  uint32_t pending = __ballot_sync(0xffffffffu, need_exact && !done);
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const int64_t srow = __shfl_sync(0xffffffffu, lrow, src);
+    const int scol = __shfl_sync(0xffffffffu, col, src);
+    const int32_t* __restrict__ ir = idx + srow * k;
+    uint64_t key[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int t = r * 32 + lane;
+      key[r] = t < k ? nq_key(xm, n, nq_wrap(ir[t], n32), scol) : ~0ull;
+    }
+    uint32_t hmax = 0;
+    const double mm = warp_median<R>(key, k, &hmax);
+    if (lane == src) med = hmax == 0xffffffffu ? nan : mm;  // np.median is NaN when any value is NaN
+  }
+  if (active) out[lrow * m + col] = log2(nq_value(xm, n, row_begin + lrow, col) / med);
+}
 }  // namespace
 
 int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m, double* xt,
@@ -61,16 +390,61 @@ int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* 
   dim3 grid((unsigned)((n + 31) / 32), (m + NR_CHUNK - 1) / NR_CHUNK);
   gather_cols_kernel<<<grid, 256, 0, st>>>(x, n, s, ids, m, xt);
   WCX_CUDA_OK(cudaGetLastError());
+  if (m <= NQ_STRIDE) {
+    // codes of the fast path (see above): column statistics, histogram, prefix, codes
+    NullStaging ns = null_staging(xt, n, m);
+    WCX_CUDA_OK(cudaMemsetAsync(ns.cols, 0, sizeof(NqCol) * NQ_STRIDE + sizeof(unsigned int) * (size_t)m * (NQ_HBINS + 1), st));
+    const uint64_t* xm = reinterpret_cast<const uint64_t*>(xt);
+    const unsigned gb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 592 / m + 1));
+    nq_stats_kernel<<<dim3(gb, m), 256, 0, st>>>(xm, n, m, ns.cols);
+    nq_map_kernel<<<1, NQ_STRIDE, 0, st>>>(n, m, ns.cols);
+    nq_hist_kernel<<<dim3(gb, m), 256, 0, st>>>(xm, n, m, ns.cols, ns.hist);
+    nq_prefix_kernel<<<m, 1024, 0, st>>>(ns.hist);
+    nq_code_kernel<<<(unsigned)((n + 1) / 2), 256, 0, st>>>(xm, n, m, ns.cols, ns.hist, ns.xq);
+    WCX_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 
-int64_t null_ratio_staging_doubles(int64_t n, int32_t m) { return (int64_t)((m + NR_CHUNK - 1) / NR_CHUNK) * n * NR_CHUNK; }
+NullStaging null_staging(double* xt, int64_t n, int32_t m) {
+  NullStaging ns;
+  unsigned char* p = reinterpret_cast<unsigned char*>(xt);
+  p += sizeof(double) * (size_t)((m + NR_CHUNK - 1) / NR_CHUNK) * n * NR_CHUNK;  // XM keys
+  ns.xq = reinterpret_cast<uint16_t*>(p);
+  p += ((sizeof(uint16_t) * (size_t)n * NQ_STRIDE + 255) / 256) * 256;
+  ns.cols = reinterpret_cast<NqCol*>(p);
+  p += sizeof(NqCol) * NQ_STRIDE;
+  ns.hist = reinterpret_cast<unsigned int*>(p);
+  p += sizeof(unsigned int) * (size_t)NQ_STRIDE * (NQ_HBINS + 1);
+  ns.bytes = (size_t)(p - reinterpret_cast<unsigned char*>(xt));
+  return ns;
+}
+
+int64_t null_ratio_staging_doubles(int64_t n, int32_t m) { return (int64_t)((null_staging(nullptr, n, m).bytes + 7) / 8); }
 
 int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t row_begin, int64_t row_end,
                        int32_t k, int32_t m, double* out, cudaStream_t st) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0 || m <= 0) return 0;
   if (k > 512) { set_error("null_ratios: ref_size > 512 unsupported"); return 1; }
+  const bool legacy = std::getenv("WCX_NULL_WARP") != nullptr;  // cross-check (tests): the warp-per-bin kernel
+  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2) {
+    NullStaging ns = null_staging(const_cast<double*>(xt), n, m);
+    const uint64_t* xm = reinterpret_cast<const uint64_t*>(xt);
+    const int64_t total = rows * m;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+#define WCX_NQ_LAUNCH(NP, R, FULL) null_fast_kernel<NP, R, FULL><<<grid, 128, 0, st>>>(ns.xq, xm, ns.cols, n, idx, row_begin, rows, k, m, out)
+    const bool aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    if (k == 300 && aligned) WCX_NQ_LAUNCH(150, 10, true);
+    else if (k <= 64) WCX_NQ_LAUNCH(32, 2, false);
+    else if (k <= 128) WCX_NQ_LAUNCH(64, 4, false);
+    else if (k <= 200) WCX_NQ_LAUNCH(100, 7, false);
+    else if (k <= 300) WCX_NQ_LAUNCH(150, 10, false);
+    else WCX_NQ_LAUNCH(200, 13, false);
+#undef WCX_NQ_LAUNCH
+    WCX_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   for (int m0 = 0; m0 < m; m0 += NR_CHUNK) {

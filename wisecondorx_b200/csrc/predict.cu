@@ -392,56 +392,71 @@ radix_pass_kernel(const unsigned long long* __restrict__ keys, int64_t len, cons
 }
 
 // ---- get_z_score ---------------------------------------------------------------------------------------
-// one block per segment: 128 null columns x 2 bin lanes.  M <= 128 (the reference uses
-// min(S, 100) null samples, newref_tools.py:211).
+// Per segment and null column: weighted mean of the column over the segment's bins with data, then
+// z = (segment ratio - mean over columns) / population sd over columns (overall_tools.py:88-119).
+// Two stages so that a whole-chromosome segment (16 598 bins at 15 kb) is not one CTA's serial loop: stage 1 cuts
+// every segment into SZ_CHUNKS bin ranges (grid = chunks x segments), 128 null columns x 2 bin lanes per CTA, and
+// writes per-chunk partial sums; stage 2 adds the chunks in a fixed order (deterministic) and finishes the segment.
+// M <= 128 (the reference uses min(S, 100) null samples, newref_tools.py:211).
+constexpr int SZ_CHUNKS = 32;
+
 __global__ void __launch_bounds__(256)
-segment_z_kernel(const double* __restrict__ nr, int m, const int32_t* __restrict__ inflate_pos, const double* __restrict__ r,
-                 const double* __restrict__ w, const int64_t* __restrict__ seg_se, const double* __restrict__ seg_r,
-                 double* __restrict__ z_out) {
-  __shared__ double s_num[2][128];
-  __shared__ double s_den[2][128];
-  __shared__ int s_any[2][128];
-  __shared__ double s_val[128];
-  __shared__ double sh[32];
-  __shared__ double s_mean, s_count;
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+segment_z_partial_kernel(const double* __restrict__ nr, int m, const int32_t* __restrict__ inflate_pos, const double* __restrict__ r,
+                         const double* __restrict__ w, const int64_t* __restrict__ seg_se, double* __restrict__ partial) {
+  __shared__ double s_num[128], s_den[128], s_any[128];
   const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
-  const int64_t s = seg_se[2 * blockIdx.x], e = seg_se[2 * blockIdx.x + 1];
-  double num = 0.0, den = 0.0;
-  int any = 0;
+  const int seg = blockIdx.y, ch = blockIdx.x;
+  const int64_t s = seg_se[2 * seg], e = seg_se[2 * seg + 1], len = e - s;
+  const int64_t cs = s + len * ch / SZ_CHUNKS, ce = s + len * (ch + 1) / SZ_CHUNKS;
+  double num = 0.0, den = 0.0, any = 0.0;
   if (tx < m) {
-    for (int64_t b = s + ty; b < e; b += 2) {
+    for (int64_t b = cs + ty; b < ce; b += 2) {
       if (r[b] == 0.0) continue;  // bins without data are dropped (overall_tools.py:98-100,106)
       const int32_t p = inflate_pos[b];
       if (p < 0) continue;
       const double v = nr[(int64_t)p * m + tx];
-      if (isfinite(v)) { num += w[b] * v; den += w[b]; any = 1; }  // non-finite entries are masked (:101-108)
+      if (isfinite(v)) { num += w[b] * v; den += w[b]; any = 1.0; }  // non-finite entries are masked (:101-108)
     }
   }
-  s_num[ty][tx] = num; s_den[ty][tx] = den; s_any[ty][tx] = any;
+  if (ty == 1) { s_num[tx] = num; s_den[tx] = den; s_any[tx] = any; }
   __syncthreads();
   if (ty == 0) {
-    double val = nan;
-    if (tx < m && (s_any[0][tx] | s_any[1][tx])) val = (s_num[0][tx] + s_num[1][tx]) / (s_den[0][tx] + s_den[1][tx]);
-    s_val[tx] = val;
+    double* o = partial + ((int64_t)seg * SZ_CHUNKS + ch) * 3 * 128;
+    o[tx] = num + s_num[tx];
+    o[128 + tx] = den + s_den[tx];
+    o[256 + tx] = any + s_any[tx];
   }
-  __syncthreads();
-  const bool ok = (ty == 0 && tx < m && isfinite(s_val[tx]));
-  const double sum_v = block_sum(ok ? s_val[tx] : 0.0, sh);
+}
+
+__global__ void __launch_bounds__(128)
+segment_z_final_kernel(const double* __restrict__ partial, int m, const double* __restrict__ seg_r, double* __restrict__ z_out) {
+  __shared__ double sh[32];
+  __shared__ double s_mean, s_count;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  const int tx = threadIdx.x, seg = blockIdx.x;
+  double num = 0.0, den = 0.0, any = 0.0;
+  for (int ch = 0; ch < SZ_CHUNKS; ch++) {
+    const double* o = partial + ((int64_t)seg * SZ_CHUNKS + ch) * 3 * 128;
+    num += o[tx]; den += o[128 + tx]; any += o[256 + tx];
+  }
+  double val = nan;
+  if (tx < m && any > 0.0) val = num / den;
+  const bool ok = tx < m && isfinite(val);
+  const double sum_v = block_sum(ok ? val : 0.0, sh);
   const double sum_c = block_sum(ok ? 1.0 : 0.0, sh);
   if (threadIdx.x == 0) { s_mean = sum_v / sum_c; s_count = sum_c; }
   __syncthreads();
   const double mean = s_mean, cnt = s_count;
-  const double dv = ok ? (s_val[tx] - mean) : 0.0;
+  const double dv = ok ? (val - mean) : 0.0;
   const double ss = block_sum(dv * dv, sh);
   if (threadIdx.x == 0) {
     double z = nan;
     if (cnt > 0.0) {
       const double sd = sqrt(ss / cnt);
-      z = (seg_r[blockIdx.x] - mean) / sd;
+      z = (seg_r[seg] - mean) / sd;
       if (z == z) { z = z > 1000.0 ? 1000.0 : z; z = z < -1000.0 ? -1000.0 : z; }  // min/max clip (:114-115)
     }
-    z_out[blockIdx.x] = z;
+    z_out[seg] = z;
   }
 }
 
@@ -560,11 +575,15 @@ int launch_normalize_repeat(const double* x, double* copy_a, double* copy_b, int
   return 0;
 }
 
+size_t segment_z_scratch_bytes(int32_t nseg) { return sizeof(double) * (size_t)(nseg > 0 ? nseg : 1) * SZ_CHUNKS * 3 * 128; }
+
 int launch_segment_z(const double* nr, int32_t m, const int32_t* inflate_pos, const double* r, const double* w,
-                     const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out, cudaStream_t st) {
+                     const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out, double* partial, cudaStream_t st) {
   if (nseg <= 0) return 0;
   if (m > 128) { set_error("get_z_score: more than 128 null samples unsupported"); return 1; }
-  segment_z_kernel<<<nseg, 256, 0, st>>>(nr, m, inflate_pos, r, w, seg_se, seg_r, z_out);
+  if (nseg > 65535) { set_error("get_z_score: more than 65535 segments in one call unsupported"); return 1; }
+  segment_z_partial_kernel<<<dim3(SZ_CHUNKS, nseg), 256, 0, st>>>(nr, m, inflate_pos, r, w, seg_se, partial);
+  segment_z_final_kernel<<<nseg, 128, 0, st>>>(partial, m, seg_r, z_out);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -17,6 +17,7 @@ int launch_nanmedians(const double* r, const double* z, int32_t B, int64_t len, 
                       cudaStream_t st);
 int launch_normalize_repeat(const double* x, double* copy_a, double* copy_b, int32_t B, int64_t n, const int32_t* gl,
                             int32_t k, int64_t ct, double* z, double* r, double* nref, cudaStream_t st);
+size_t segment_z_scratch_bytes(int32_t nseg);
 int launch_segment_z(const double* nr, int32_t m, const int32_t* inflate_pos, const double* r, const double* w,
-                     const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out, cudaStream_t st);
+                     const int64_t* seg_se, const double* seg_r, int32_t nseg, double* z_out, double* partial, cudaStream_t st);
 }  // namespace wcx

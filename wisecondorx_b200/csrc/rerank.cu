@@ -780,7 +780,7 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
                   const double* null_xm, int32_t null_m, double* null_out, cudaStream_t st) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0) return 0;
-  if (nlists < 1 || nlists > 4) { set_error("rerank: bad number of candidate lists per row"); return 1; }
+  if (nlists < 1 || nlists > 16) { set_error("rerank: bad number of candidate lists per row"); return 1; }
   const int maxc = nlists <= 2 ? 4096 : 8192;  // list entries below the common cut that fit in shared memory
   // leaf-major gather (default) needs the permuted copy; WCX_RERANK_LDG=1 forces the row-major LDG gather,
   // WCX_RERANK_PAIR=1 the two-candidates-per-lane-group variant (3 CTAs per SM instead of 4; measured 37.1 ms

@@ -106,6 +106,8 @@ def tool_newref(args):
     if genders.count("M") > 4 and not args.nipt:
         total_mask = total_mask & get_mask(samples[g == "M"])[0]
     device = getattr(args, "device", 0)
+    gpus = max(1, int(getattr(args, "gpus", 1) or 1))
+    devices = [device + g for g in range(gpus)]
     parts = max(1, int(args.cpus))
     results = []
     timings["gender_model_and_masks"] = time.perf_counter() - t0
@@ -116,7 +118,7 @@ def tool_newref(args):
         t1 = time.perf_counter()
         prep = newref_control.tool_newref_prep(sample_list, gender, total_mask, bins_per_chr, device)
         t2 = time.perf_counter()
-        results.append(newref_control.tool_newref_main(prep, args.refsize, nparts, device))
+        results.append(newref_control.tool_newref_main(prep, args.refsize, nparts, device, devices))
         newref_control.writer_add_pass(writer, results[-1], args.binsize)
         timings["prep." + gender] = t2 - t1
         timings["get_reference." + gender] = time.perf_counter() - t2
@@ -230,6 +232,8 @@ def build_parser():
     p.add_argument("--plotyfrac", type=str, default=None); p.add_argument("--refsize", type=int, default=300)
     p.add_argument("--binsize", type=int, default=1e5); p.add_argument("--cpus", type=int, default=1)
     p.add_argument("--device", type=int, default=0, help="CUDA device (new)")
+    p.add_argument("--gpus", type=int, default=1, help="number of GPUs (devices --device .. --device + N - 1) the target bins "
+                                                        "are spread over (new; the reference spreads them over --cpus threads)")
     p.set_defaults(func=tool_newref)
     p = sub.add_parser("gender", description="Returns the gender of a .npz resulting from convert")
     p.add_argument("infile", type=str); p.add_argument("reference", type=str)

@@ -11,7 +11,7 @@ import random
 
 import numpy as np
 
-from . import newref_tools, npz_io
+from . import _lib, newref_tools, npz_io
 
 
 def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
@@ -53,27 +53,61 @@ def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
     }
 
 
-def tool_newref_main(prep, refsize, parts: int = 1, device: int = 0):
+def tool_newref_main(prep, refsize, parts: int = 1, device: int = 0, devices=None):
     """get_reference over `parts` parts, concatenated in part order (reference tool_newref_main +
-    tool_newref_post, newref_control.py:90-189).  One null-sample draw per part, like the reference."""
+    tool_newref_post, newref_control.py:90-189).  One null-sample draw per part, like the reference.
+
+    devices: CUDA devices to spread the target bins over (`newref --gpus N`).  The reference's own fan-out is over
+    parts of the target-bin axis (newref_control.py:90-104, newref_tools.py:244-247) -- rows are independent given the
+    matrix -- so every part is cut into one row range per device; each device gets the matrix once (a copy of the
+    matrix prepared on `device`, over NVLink) and writes its rows straight into the result arrays.  One host thread
+    drives each device through its own context (the C-ABI calls release the GIL); no collective is needed."""
     x = prep["pca_corrected_data"]
     per, cum = prep["masked_bins_per_chr"], prep["masked_bins_per_chr_cum"]
     n, s = x.shape
-    eng = newref_tools.NewrefEngine(device)
-    if isinstance(x, np.ndarray):
-        eng.load(x, per, cum)
-    else:  # newref_tools.DevicePrep: the corrected matrix is already in the context
-        x.load_into(eng, per, cum)
-    idx_parts, dist_parts, nr_parts = [], [], []
+    m = min(s, 100)
+    draws = []
     for part in range(1, parts + 1):
         start, end = newref_tools._get_part(part - 1, parts, n)
-        sample_ids = random.sample(range(s), min(s, 100))  # newref_tools.py:214-217
-        idx, dist, nr = eng.reference(start, end, refsize, sample_ids)
-        idx_parts.append(idx); dist_parts.append(dist); nr_parts.append(nr)
+        draws.append((start, end, random.sample(range(s), m)))  # newref_tools.py:214-217, in part order
+    idx = _lib.pinned.empty((n, refsize), np.int32)
+    dist = _lib.pinned.empty((n, refsize), np.float64)
+    nr = _lib.pinned.empty((n, m), np.float64)
+    devices = list(devices) if devices else [device]
+
+    def load(eng, first):
+        if isinstance(x, np.ndarray):
+            eng.load(x, per, cum)
+        elif first:  # newref_tools.DevicePrep: the corrected matrix is already in this context
+            x.load_into(eng, per, cum)
+        else:
+            eng.load(None, per, cum, on_device_ptr=x.device_ptr("corrected"), shape=(n, s), copy_from_any_device=True)
+
+    def run(eng, g, ngpu):
+        for start, end, ids in draws:
+            a, b = start + (end - start) * g // ngpu, start + (end - start) * (g + 1) // ngpu
+            if b > a:
+                eng.reference(a, b, refsize, ids, out=(idx[a:b], dist[a:b], nr[a:b]))
+
+    if len(devices) == 1:
+        eng = newref_tools.NewrefEngine(devices[0])
+        load(eng, True)
+        run(eng, 0, 1)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        engines = [newref_tools.NewrefEngine(d, newref_tools._lib.default_context(d) if i == 0 and d == device else _lib.Context(d))
+                   for i, d in enumerate(devices)]
+
+        def worker(g):
+            load(engines[g], g == 0 and devices[0] == device)
+            run(engines[g], g, len(devices))
+
+        with ThreadPoolExecutor(len(devices)) as pool:
+            list(pool.map(worker, range(len(devices))))
+        for e in engines[1:]:
+            e.ctx.close()
     out = {k: v for k, v in prep.items() if k != "pca_corrected_data"}
-    out["indexes"] = np.concatenate(idx_parts)
-    out["distances"] = np.concatenate(dist_parts)
-    out["null_ratios"] = np.concatenate(nr_parts)
+    out["indexes"], out["distances"], out["null_ratios"] = idx, dist, nr
     return out
 
 

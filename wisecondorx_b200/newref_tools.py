@@ -36,14 +36,16 @@ class NewrefEngine:
         self.ctx = ctx or _lib.default_context(device)
         self.n = self.s = 0
 
-    def load(self, x, per, cum, on_device_ptr: int | None = None, shape=None):
+    def load(self, x, per, cum, on_device_ptr: int | None = None, shape=None, copy_from_any_device: bool = False):
+        """copy_from_any_device: on_device_ptr may live on another GPU of the box; it is copied into this context once
+        (wcx_newref_load x_on_device = 3) instead of being borrowed."""
         L = _lib.load()
         per = np.ascontiguousarray(per, dtype=np.int64)
         cum = np.ascontiguousarray(cum, dtype=np.int64)
         if on_device_ptr is not None:
             n, s = shape
             _lib.check(L.wcx_newref_load(self.ctx.handle, ctypes.c_void_p(on_device_ptr), n, s, _ptr(per),
-                                         _ptr(cum), len(cum), 1))
+                                         _ptr(cum), len(cum), 3 if copy_from_any_device else 1))
         else:
             x = np.ascontiguousarray(x, dtype=np.float64)
             n, s = x.shape
@@ -314,6 +316,13 @@ class DevicePrep:
         cum = np.ascontiguousarray(cum, dtype=np.int64)
         _lib.check(_lib.load().wcx_newref_load(engine.ctx.handle, None, n, s, _ptr(per), _ptr(cum), len(cum), 2))
         engine.n, engine.s = int(n), int(s)
+
+    def device_ptr(self, which: str = "corrected") -> int:
+        """Device address of a resident matrix (for NewrefEngine.load(..., copy_from_any_device=True) on other GPUs)."""
+        n, s = self.shape
+        out = ctypes.c_void_p()
+        _lib.check(_lib.load().wcx_prep_device_ptr(self.ctx.handle, 0 if which == "masked" else 1, n, s, ctypes.byref(out)))
+        return int(out.value)
 
     def fetch(self, which: str):
         """Host copy of a resident matrix ("masked" or "corrected"): tests, or callers that want the reference's

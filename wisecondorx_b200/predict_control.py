@@ -192,6 +192,17 @@ def stacked_null_ratios(ref_file, ref_gender):
     return nr
 
 
+def _map_threads(fn, items, min_items=4):
+    """fn over items on a thread pool (host post-processing of a batch: NumPy releases the GIL in its loops)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    items = list(items)
+    if len(items) < min_items:
+        return [fn(i) for i in items]
+    with ThreadPoolExecutor(min(16, len(items), max(1, len(os.sched_getaffinity(0)) - 1))) as pool:
+        return list(pool.map(fn, items))
+
+
 def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.PredictEngine | None = None, timings=None):
     """Everything `predict` computes before the output writers, for a batch of raw samples against one reference:
     re-binning, gender, both `normalize` calls (the autosomal one for the whole batch at once, the gonosomal one per
@@ -219,10 +230,11 @@ def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.Predi
         for j, i in enumerate(ids):
             gon[i] = (r2[j], z2[j], w2, n2[j])
         nrs[rg] = stacked_null_ratios(ref_file, rg)
-    out = []
-    for i in range(len(prepared)):
+    def one(i):
         aut = (r[i], z[i], w, n[i], float(m_lr[i]), float(m_z[i]))
-        out.append(assemble(args, aut, gon[i], nrs[ref_genders[i]], ref_file, ref_genders[i], genders[i], n_reads[i]))
+        return assemble(args, aut, gon[i], nrs[ref_genders[i]], ref_file, ref_genders[i], genders[i], n_reads[i])
+
+    out = _map_threads(one, range(len(prepared)))  # ~30 NumPy passes over 2e5 bins per sample: the GIL is released in them
     if timings is not None:
         timings["normalize_and_assemble"] = time.perf_counter() - t0
     t0 = time.perf_counter()
