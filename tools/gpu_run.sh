@@ -23,6 +23,24 @@ for S in $STEPS; do
       python tools/ncu_summary.py gpurun_out/${TAG}_prof_predict.ncu-rep > gpurun_out/${TAG}_ncu_predict.txt 2>&1
       [ -f gpurun_out/${TAG}_prof_predict.ncu-rep ] && [ $(stat -c %s gpurun_out/${TAG}_prof_predict.ncu-rep) -gt 30000000 ] && rm -f gpurun_out/${TAG}_prof_predict.ncu-rep  # gpurun_out is capped at 64 MiB
       tail -3 gpurun_out/${TAG}_prof_predict.log | cut -c1-300 ;;
+    ncu_null) echo "=== ncu: null-ratio kernels (stand-alone call)"
+      timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:null_fast|null_ratios_kernel|nq_|gather_cols' -c 8 -f -o gpurun_out/${TAG}_prof_null python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-predict --unfused > gpurun_out/${TAG}_prof_null.log 2>&1
+      python tools/ncu_summary.py gpurun_out/${TAG}_prof_null.ncu-rep > gpurun_out/${TAG}_ncu_null.txt 2>&1
+      python tools/ncu_table.py gpurun_out/${TAG}_ncu_null.txt
+      ncu -i gpurun_out/${TAG}_prof_null.ncu-rep --page details --csv 2>/dev/null | grep -i -E "null_fast" | grep -i -E "Issue Slots Busy|Executed Ipc|No Eligible|Stall|Theoretical Occupancy|Achieved Occupancy|L1/TEX Hit|Local" | cut -d, -f5,13- | head -40
+      ;;
+    nullcmp) echo "=== null ratios: side stream vs serial vs stand-alone"
+      for MODE in side serial unfused; do
+        EXTRA=""; ENV=""
+        [ $MODE == serial ] && ENV="WCX_SERIAL_NULLS=1"
+        [ $MODE == unfused ] && EXTRA="--unfused"
+        env $ENV timeout 300 python bench.py --steps 10 --warmup 3 --no-predict --no-cpu-baseline $EXTRA 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_$MODE.json
+        python - <<PYEOF
+import json
+d = json.load(open("gpurun_out/${TAG}_bench_$MODE.json"))
+print("$MODE", "ms/step %.2f" % d["ms_per_step"], "e2e %.2f" % d["e2e"]["ms_per_step"], {k: round(v, 2) for k, v in d["stages_ms"].items()}, d["parity"]["ok"])
+PYEOF
+      done ;;
     prof_batch) echo "=== predict batch 96: host profile + CBS launch list"
       timeout 600 python tools/predict_profile.py --batch 96 --cprofile > gpurun_out/${TAG}_batch96_cprofile.txt 2>&1
       head -c 3000 gpurun_out/${TAG}_batch96_cprofile.txt | tail -c 1500

@@ -130,8 +130,11 @@ def exec_cbs_batch(rem_inputs, results_list, engine: predict_tools.PredictEngine
     segs = cbs_segments_batch([(res["results_r"], res["results_w"], str(rem["ref_gender"])) for rem, res in zip(rem_inputs, results_list)],
                               float(args.alpha), float(rem_inputs[0]["binsize"]), getattr(args, "seed", None), nperm,
                               engine.ctx if engine else None)
-    out = []
-    for results_c, res in zip(segs, results_list):
-        z = predict_tools.get_z_score(results_c, res, engine)
-        out.append([results_c[i][:3] + [z[i]] + [results_c[i][3]] for i in range(len(results_c))])
+    out = [None] * len(segs)
+    # samples of one reference gender share their null-ratio array, which stays on the device between calls: walk the
+    # batch gender by gender so that it is uploaded once per gender, not once per sample
+    for j in sorted(range(len(segs)), key=lambda i: str(rem_inputs[i]["ref_gender"])):
+        results_c = segs[j]
+        z = predict_tools.get_z_score(results_c, results_list[j], engine)
+        out[j] = [results_c[i][:3] + [z[i]] + [results_c[i][3]] for i in range(len(results_c))]
     return out

@@ -240,28 +240,67 @@ __device__ __forceinline__ int nq_count_lt(const uint32_t (&k2)[NP], uint32_t tr
   }
   return h2_total(a0) + h2_total(a1) + h2_total(a2) + h2_total(a3);
 }
-// largest key below `lim` (0 if none) and the position (0-based) of the LAST key equal to `code`
+__device__ __forceinline__ uint32_t h2_eq(uint32_t a, uint32_t b) {  // 1.0h per half where a == b
+  uint32_t d;
+  asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// bit pattern of the fp16 pair (float(lo), float(hi)) for small non-negative integers (exact below 2048)
+__host__ __device__ constexpr uint32_t h_bits(int v) {
+  if (v == 0) return 0u;
+  int e = 0;
+  while ((v >> e) > 1) e++;
+  return (uint32_t)(((e + 15) << 10) | (((v << (10 - e)) & 0x3ff)));
+}
+__host__ __device__ constexpr uint32_t h2_const(int lo, int hi) { return h_bits(lo) | (h_bits(hi) << 16); }
+
+// largest key below `lim` as a code (0 if none): key * [key < lim] keeps the key or +0, fp16 max orders the patterns
 template <int NP>
 __device__ __forceinline__ uint32_t nq_max_below(const uint32_t (&k2)[NP], uint32_t lim) {
-  uint32_t best = 0;
+  const uint32_t l2 = lim | (lim << 16);
+  uint32_t b0 = 0, b1 = 0;
 #pragma unroll
-  for (int j = 0; j < NP; j++) {
-    const uint32_t lo = k2[j] & 0xffffu, hi = k2[j] >> 16;
-    best = (lo < lim && lo > best) ? lo : best;
-    best = (hi < lim && hi > best) ? hi : best;
+  for (int j = 0; j < NP; j += 2) {
+    b0 = h2_max(b0, h2_mul(k2[j], h2_lt(k2[j], l2)));
+    if (j + 1 < NP) b1 = h2_max(b1, h2_mul(k2[j + 1], h2_lt(k2[j + 1], l2)));
   }
-  return best;
+  const uint32_t b = h2_max(b0, b1);
+  const uint32_t lo = b & 0xffffu, hi = b >> 16;
+  return lo > hi ? lo : hi;
 }
+// number of keys equal to `code` and the sum of (position + 1) over them -- the position itself when there is one
 template <int NP>
-__device__ __forceinline__ int nq_find(const uint32_t (&k2)[NP], uint32_t code) {
-  int pos = -1;
+__device__ __forceinline__ void nq_find(const uint32_t (&k2)[NP], uint32_t code, int& count, int& pos) {
+  const uint32_t c2 = code | (code << 16);
+  uint32_t n0 = 0, n1 = 0, p0 = 0, p1 = 0;
 #pragma unroll
-  for (int j = 0; j < NP; j++) {
-    const uint32_t x = k2[j] ^ (code | (code << 16));
-    pos = (x & 0xffffu) == 0u ? 2 * j : pos;
-    pos = (x >> 16) == 0u ? 2 * j + 1 : pos;
+  for (int j = 0; j < NP; j += 2) {
+    const uint32_t e0 = h2_eq(k2[j], c2);
+    n0 = h2_add(n0, e0);
+    p0 = h2_fma(e0, h2_const(2 * j + 1, 2 * j + 2), p0);
+    if (j + 1 < NP) {
+      const uint32_t e1 = h2_eq(k2[j + 1], c2);
+      n1 = h2_add(n1, e1);
+      p1 = h2_fma(e1, h2_const(2 * j + 3, 2 * j + 4), p1);
+    }
   }
-  return pos;
+  count = h2_total(n0) + h2_total(n1);
+  pos = h2_total(p0) + h2_total(p1) - 1;  // meaningful only when count == 1 (sums of several positions may round)
 }
 
 // reference position -> bin of the full column: -1 (missing entries) wraps to the last bin like a Python index.  The
@@ -275,26 +314,35 @@ template <int NP, int R, bool FULL>
 __global__ void __launch_bounds__(128, NP > 128 ? 2 : (NP > 64 ? 3 : 4))
 null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ xm, const NqCol* __restrict__ cols, int64_t n,
                  const int32_t* __restrict__ idx, int64_t row_begin, int64_t rows, int k, int m, double* __restrict__ out) {
+  // A block covers 128 consecutive (bin, column) pairs = at most 128 / m + 2 bins.  Their reference positions are turned
+  // into element offsets of the code table once per block (wrap + multiply), shared by all columns of the bin.
+  extern __shared__ int32_t s_off[];  // [bins of the block][k]
   const int lane = threadIdx.x & 31;
   const int64_t total = rows * m;
-  const int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t blk0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t row_first = blk0 / m;
+  const int64_t blk_last = blk0 + blockDim.x - 1 < total - 1 ? blk0 + blockDim.x - 1 : total - 1;
+  const int nrows_blk = (int)(blk_last / m - row_first) + 1;
+  const int32_t n32 = (int32_t)n;
+  for (int e = threadIdx.x; e < nrows_blk * k; e += blockDim.x) s_off[e] = nq_wrap(idx[row_first * k + e], n32) * NQ_STRIDE;
+  __syncthreads();
+  const int64_t p0 = blk0 + threadIdx.x;
   const bool active = p0 < total;
   const int64_t p = active ? p0 : total - 1;  // whole warps stay alive for the cooperative exact path
   const int64_t lrow = p / m;
   const int col = (int)(p - lrow * m);
-  const int32_t* __restrict__ irow = idx + lrow * k;
+  const int32_t* __restrict__ orow = s_off + (lrow - row_first) * k;
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   double med = nan;
   bool need_exact = cols[col].exact != 0;
   bool done = false;
-  // rows whose k indexes are all the same bin (placeholder rows of gonosomal references, newref_tools.py:186-191):
+  // rows whose k positions are all the same bin (placeholder rows of gonosomal references, newref_tools.py:186-191):
   // the median of k copies of a value is the value ((v + v) / 2 is exact)
-  const int32_t n32 = (int32_t)n;
-  if (irow[0] == irow[k - 1] && irow[0] == irow[k >> 1]) {
+  if (orow[0] == orow[k - 1] && orow[0] == orow[k >> 1]) {
     bool same = true;
-    for (int t = 1; t < k; t++) same &= irow[t] == irow[0];
+    for (int t = 1; t < k; t++) same &= orow[t] == orow[0];
     if (same) {
-      med = nq_value(xm, n, nq_wrap(irow[0], n32), col);
+      med = nq_value(xm, n, orow[0] / NQ_STRIDE, col);
       done = true;
     }
   }
@@ -302,26 +350,22 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
     uint32_t k2[NP];
     const uint16_t* __restrict__ xqc = xq + col;
     if (FULL) {
-      // k == 2 NP, rows 16-byte aligned (k % 4 == 0): four positions per 128-bit load, in groups of 8 loads so that the
-      // compiler keeps a bounded number of gathers in flight instead of hoisting all 2 NP of them
-      const int4* __restrict__ iv = reinterpret_cast<const int4*>(irow);
+      // k == 2 NP: four offsets per 128-bit shared-memory load (a broadcast: the threads of a bin read the same words)
+      const int4* __restrict__ ov = reinterpret_cast<const int4*>(orow);
 #pragma unroll
       for (int j = 0; j < NP / 2; j++) {
-        const int4 q = __ldg(iv + j);
-        const uint32_t c0 = xqc[(int64_t)nq_wrap(q.x, n32) * NQ_STRIDE];
-        const uint32_t c1 = xqc[(int64_t)nq_wrap(q.y, n32) * NQ_STRIDE];
-        const uint32_t c2 = xqc[(int64_t)nq_wrap(q.z, n32) * NQ_STRIDE];
-        const uint32_t c3 = xqc[(int64_t)nq_wrap(q.w, n32) * NQ_STRIDE];
+        const int4 q = ov[j];
+        const uint32_t c0 = xqc[q.x], c1 = xqc[q.y], c2 = xqc[q.z], c3 = xqc[q.w];
         k2[2 * j] = c0 | (c1 << 16);
         k2[2 * j + 1] = c2 | (c3 << 16);
-        if ((j & 7) == 7) asm volatile("" ::: "memory");
+        if ((j & 7) == 7) asm volatile("" ::: "memory");  // bounded number of gathers in flight: no spills
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NP; j++) {
         uint32_t c0 = NQ_PAD, c1 = NQ_PAD;
-        if (2 * j < k) c0 = xqc[(int64_t)nq_wrap(irow[2 * j], n32) * NQ_STRIDE];
-        if (2 * j + 1 < k) c1 = xqc[(int64_t)nq_wrap(irow[2 * j + 1], n32) * NQ_STRIDE];
+        if (2 * j < k) c0 = xqc[orow[2 * j]];
+        if (2 * j + 1 < k) c1 = xqc[orow[2 * j + 1]];
         k2[j] = c0 | (c1 << 16);
         if ((j & 15) == 15) asm volatile("" ::: "memory");
       }
@@ -335,26 +379,25 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
       const int c = nq_count_lt<NP>(k2, trial);
       if (c <= t) { T = trial; below = c; }
     }
-    // T is the code of the rank-t key: count(< T) <= t < count(< T + 1)
-    const int eq_hi = nq_count_lt<NP>(k2, T + 1u) - below;
+    // T is the code of the rank-t key: count(< T) <= t < count(< T + 1).  It can stand for its VALUE only if no
+    // other key shares the code; an even k also needs the rank t - 1 key: the largest key below T, provided rank t is
+    // the first key with code T.
+    int eq_hi, j_hi, eq_lo = 1, j_lo = 0;
+    nq_find<NP>(k2, T, eq_hi, j_hi);
     bool ok = eq_hi == 1;
-    uint32_t T_lo = T;
     if (ok && !(k & 1)) {
-      // even k: the lower middle key (rank t - 1) is the largest key below T -- if rank t is the first key with code T
       ok = below == t;
       if (ok) {
-        T_lo = nq_max_below<NP>(k2, T);
-        ok = (t - nq_count_lt<NP>(k2, T_lo)) == 1;
+        nq_find<NP>(k2, nq_max_below<NP>(k2, T), eq_lo, j_lo);
+        ok = eq_lo == 1;
       }
     }
     if (ok) {
-      const int j_hi = nq_find<NP>(k2, T);
-      const double v_hi = nq_value(xm, n, nq_wrap(irow[j_hi], n32), col);
+      const double v_hi = nq_value(xm, n, orow[j_hi] / NQ_STRIDE, col);
       if (k & 1) {
         med = v_hi;
       } else {
-        const int j_lo = nq_find<NP>(k2, T_lo);
-        const double v_lo = nq_value(xm, n, nq_wrap(irow[j_lo], n32), col);
+        const double v_lo = nq_value(xm, n, orow[j_lo] / NQ_STRIDE, col);
         med = (v_lo + v_hi) / 2.0;  // np.median: mean of the two middle values
       }
       done = true;
@@ -428,13 +471,15 @@ int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t 
   if (rows <= 0 || m <= 0) return 0;
   if (k > 512) { set_error("null_ratios: ref_size > 512 unsupported"); return 1; }
   const bool legacy = std::getenv("WCX_NULL_WARP") != nullptr;  // cross-check (tests): the warp-per-bin kernel
-  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2) {
+  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2 && sizeof(int32_t) * (size_t)(128 / m + 2) * k <= 40 * 1024) {
     NullStaging ns = null_staging(const_cast<double*>(xt), n, m);
     const uint64_t* xm = reinterpret_cast<const uint64_t*>(xt);
     const int64_t total = rows * m;
     const unsigned grid = (unsigned)((total + 127) / 128);
-#define WCX_NQ_LAUNCH(NP, R, FULL) null_fast_kernel<NP, R, FULL><<<grid, 128, 0, st>>>(ns.xq, xm, ns.cols, n, idx, row_begin, rows, k, m, out)
-    const bool aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    // shared memory: reference offsets of the bins a block covers (128 / m + 2 of them, k each; rows 16-byte aligned)
+    const size_t smem = sizeof(int32_t) * (size_t)(128 / m + 2) * k;
+    const bool aligned = (k & 3) == 0;
+#define WCX_NQ_LAUNCH(NP, R, FULL) null_fast_kernel<NP, R, FULL><<<grid, 128, smem, st>>>(ns.xq, xm, ns.cols, n, idx, row_begin, rows, k, m, out)
     if (k == 300 && aligned) WCX_NQ_LAUNCH(150, 10, true);
     else if (k <= 64) WCX_NQ_LAUNCH(32, 2, false);
     else if (k <= 128) WCX_NQ_LAUNCH(64, 4, false);

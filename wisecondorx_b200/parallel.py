@@ -177,14 +177,15 @@ class ShardedReference:
         ids = list(sample_ids)
         if self.compute_fn is None:
             self.engine.load(None, per, cum, on_device_ptr=xd.data_ptr(), shape=(self.n, self.s))
-            self.engine.reference(start, end, self.k, ids, device_out=tuple(t.data_ptr() for t in self.dev_out))
-            outs = self.dev_out
+            # host outputs: the library copies every finished row block to the (page-locked) shared segment while the
+            # next block is still in the re-rank, instead of one D2H of the whole part at the end
+            self.engine.reference(start, end, self.k, ids, out=tuple(a[start:end] for a in self.host_out))
         else:
             outs = self.compute_fn(xd, np.asarray(per, dtype=np.int64), np.asarray(cum, dtype=np.int64), self.k, start, end, ids)
-        for host, dev in zip(self._host_t, outs):
-            host[start:end].copy_(dev, non_blocking=True)
-        if self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).synchronize()
+            for host, dev in zip(self._host_t, outs):
+                host[start:end].copy_(dev, non_blocking=True)
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
         dist.barrier(group=self.group)
         return self.host_out
 

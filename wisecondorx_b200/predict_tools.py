@@ -77,16 +77,25 @@ class PredictEngine:
         sets[ap] = (ref_file, {"n": n, "k": k, "cum": cum, "bins_per_chr": bpc, "bins_total": int(len(mask))})
 
     def get_weights(self, ref_file, ap):
+        """get_weights (predict_tools.py:152-155); a function of the reference only: computed once per resident set."""
         self._ensure_ref(ref_file, ap)
-        out = np.empty(self.meta[ap]["n"], dtype=np.float64)
-        _lib.check(_lib.load().wcx_predict_weights(self.ctx.handle, SET_ID[ap], _ptr(out)))
-        return out
+        meta = self.ctx.predict_sets[ap][1]
+        if "weights" not in meta:
+            out = np.empty(meta["n"], dtype=np.float64)
+            _lib.check(_lib.load().wcx_predict_weights(self.ctx.handle, SET_ID[ap], _ptr(out)))
+            meta["weights"] = out
+        return meta["weights"].copy()
 
     def get_optimal_cutoff(self, ref_file, repeats):
-        self._ensure_ref(ref_file, "")  # always the autosomal distances (predict_tools.py:75)
-        out = ctypes.c_double()
-        _lib.check(_lib.load().wcx_predict_optimal_cutoff(self.ctx.handle, 0, int(repeats), ctypes.byref(out)))
-        return float(out.value)
+        """get_optimal_cutoff (predict_tools.py:74-82), always on the autosomal distances (:75); ten streaming passes
+        over 0.46 GB at 15 kb, cached per (resident reference, repeats)."""
+        self._ensure_ref(ref_file, "")
+        cache = self.ctx.predict_sets[""][1].setdefault("cutoff", {})
+        if int(repeats) not in cache:
+            out = ctypes.c_double()
+            _lib.check(_lib.load().wcx_predict_optimal_cutoff(self.ctx.handle, 0, int(repeats), ctypes.byref(out)))
+            cache[int(repeats)] = float(out.value)
+        return cache[int(repeats)]
 
     def normalize_set(self, samples, ref_file, ap, cutoff, cp, ct):
         """Batch form: samples = list of sample dicts -> (z, r, nref [B, n - ct], m_lr [B], m_z [B])."""
@@ -94,11 +103,13 @@ class PredictEngine:
         meta = self.meta[ap]
         # page-locked staging for everything that crosses PCIe (0.6 GB at batch 96); _lib.pinned recycles the buffers
         b = len(samples)
-        raw = _lib.pinned.empty((b, meta["bins_total"]))
+        # (a handful of samples: ordinary arrays -- cudaHostAlloc costs more than the pageable copy of a few MB)
+        alloc = _lib.pinned.empty if b >= 8 else (lambda shape: np.empty(shape, dtype=np.float64))
+        raw = alloc((b, meta["bins_total"]))
         for i, s in enumerate(samples):
             raw_vector(s, meta["bins_per_chr"], out=raw[i])
         nout = meta["n"] - ct
-        z = _lib.pinned.empty((b, nout)); r = _lib.pinned.empty((b, nout)); nref = _lib.pinned.empty((b, nout))
+        z = alloc((b, nout)); r = alloc((b, nout)); nref = alloc((b, nout))
         m_lr = np.empty(b); m_z = np.empty(b)
         _lib.check(_lib.load().wcx_predict_normalize(self.ctx.handle, SET_ID[ap], _ptr(raw), b, float(cutoff), int(cp), int(ct),
                                                      _ptr(z), _ptr(r), _ptr(nref), _ptr(m_lr), _ptr(m_z)))
