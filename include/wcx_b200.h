@@ -27,12 +27,12 @@ typedef struct wcx_ctx wcx_ctx;
 
 /* kernel selector for the distance sweep */
 #define WCX_KERNEL_AUTO 0 /* = WCX_KERNEL_TC2H */
-#define WCX_KERNEL_TC 1   /* tcgen05 / TMEM / TMA kernel, one CTA per SM (dist_topk_tc.cu) */
+#define WCX_KERNEL_TC 1   /* (round 1: tf32, one CTA per SM; removed) now an alias of WCX_KERNEL_TCH */
 #define WCX_KERNEL_SIMT 2 /* CUDA-core fp32 kernel (dist_topk_simt.cu), cross-check path */
-#define WCX_KERNEL_EXACT 3 /* brute-force float64 rows only (exact_rows_kernel), slow, for tests */
-#define WCX_KERNEL_TC2 4  /* tcgen05 kernel in 2-CTA pair mode (cta_group::2, halves the B-operand traffic), tf32 operands */
-#define WCX_KERNEL_TC2H 5 /* pair mode with scaled f16 operands (kind::f16): same 11-bit significand as tf32, twice the rate */
-#define WCX_KERNEL_TCH 6  /* one CTA per SM, f16 operands */
+#define WCX_KERNEL_EXACT 3 /* brute-force float64 rows only (exact_rows_kernel), slow; tests and ref_size > 400 */
+#define WCX_KERNEL_TC2 4  /* (round 1: tf32, CTA pairs; removed) now an alias of WCX_KERNEL_TC2H */
+#define WCX_KERNEL_TC2H 5 /* tcgen05 / TMEM / TMA kernel, 2-CTA pairs (cta_group::2), scaled f16 operands: the product path */
+#define WCX_KERNEL_TCH 6  /* the same kernel with one CTA per SM (cta_group::1), cross-check path */
 
 int wcx_version(void);
 const char* wcx_last_error(void);
@@ -205,17 +205,15 @@ int wcx_cbs_segment(wcx_ctx* ctx, const double* y, const double* w, const int64_
  * with permutations, permutations evaluated, kernel launches. */
 int wcx_cbs_stats(wcx_ctx* ctx, int64_t* out6);
 
-/* Test hook: raw tensor-core accumulators <Xc[row0 + i], Xc[col0 + j]> of one 128 x 256 tile,
+/* Test hook: raw tensor-core accumulators of one 128 x 256 tile of the kind::f16 MMA over the scaled f16 operands,
  * written to acc_out [128 * 256] (host). */
-int wcx_debug_tc_tile(wcx_ctx* ctx, int64_t row0, int64_t col0, float* acc_out);
-/* The same for the f16 operand set (kind::f16 MMA of the scaled f16 matrix). */
 int wcx_debug_tc_tile_f16(wcx_ctx* ctx, int64_t row0, int64_t col0, float* acc_out);
 /* Test hook: f16 operands (raw half bits) [n, k_pad_h], their norms [n], k_pad_h, {scale, scale^2}. */
 int wcx_debug_prep_f16(wcx_ctx* ctx, uint16_t* xh_out, float* norm_out, int32_t* k_pad_out, double* scale_out);
 /* Test hook: final length of the first `nslots` candidate lists of the last wcx_newref_topk call
  * (lists per row = out[3] of wcx_newref_stats x 2 for the tcgen05 kernel). */
 int wcx_debug_list_counts(wcx_ctx* ctx, int32_t* cnt_out, int64_t nslots);
-/* Test hook: prepared operands.  xc_out [n, k_pad] (host, may be NULL), norm_out [n] (host). */
+/* Test hook: fp32 operands of the CUDA-core cross-check kernel.  xc_out [n, k_pad] (host, may be NULL), norm_out [n] (host). */
 int wcx_debug_prep(wcx_ctx* ctx, float* xc_out, float* norm_out, int32_t* k_pad_out);
 /* Test hook, host only (no GPU needed): for S samples the NumPy pairwise-summation plan (int32 triples), the
  * leaf-major permutation of a row used by the re-rank gather (perm[p] = source column or -1 for zero padding) and

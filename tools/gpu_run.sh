@@ -23,6 +23,17 @@ for S in $STEPS; do
       python tools/ncu_summary.py gpurun_out/${TAG}_prof_predict.ncu-rep > gpurun_out/${TAG}_ncu_predict.txt 2>&1
       [ -f gpurun_out/${TAG}_prof_predict.ncu-rep ] && [ $(stat -c %s gpurun_out/${TAG}_prof_predict.ncu-rep) -gt 30000000 ] && rm -f gpurun_out/${TAG}_prof_predict.ncu-rep  # gpurun_out is capped at 64 MiB
       tail -3 gpurun_out/${TAG}_prof_predict.log | cut -c1-300 ;;
+    bench2|bench4|bench8) N=${S#bench}; echo "=== bench on $N GPUs"
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 2>gpurun_out/${TAG}_bench_${N}gpu.err | tail -1 | tee gpurun_out/${TAG}_bench_${N}gpu.json | cut -c1-300
+      python - <<PYEOF
+import json
+try:
+    d = json.load(open("gpurun_out/${TAG}_bench_${N}gpu.json"))
+    print("N=$N ms/step %.2f e2e %.2f frac %.3f" % (d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["frac"]), {k: round(v, 2) for k, v in d["stages_ms"].items()}, d["parity"], d.get("predict"))
+except Exception as e:
+    print("bench $N failed:", e); print(open("gpurun_out/${TAG}_bench_${N}gpu.err").read()[-1500:])
+PYEOF
+      ;;
     ncu_null) echo "=== ncu: null-ratio kernels (stand-alone call)"
       timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:null_fast|null_ratios_kernel|nq_|gather_cols' -c 8 -f -o gpurun_out/${TAG}_prof_null python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-predict --unfused > gpurun_out/${TAG}_prof_null.log 2>&1
       python tools/ncu_summary.py gpurun_out/${TAG}_prof_null.ncu-rep > gpurun_out/${TAG}_ncu_null.txt 2>&1

@@ -51,7 +51,6 @@ def load():
     L.wcx_get_reference.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32, i64, i64, vp, i32, i32, vp, vp, vp]
     L.wcx_newref_stats.argtypes = [vp, vp]
     L.wcx_newref_stage_ms.argtypes = [vp, vp]
-    L.wcx_debug_tc_tile.argtypes = [vp, i64, i64, vp]
     L.wcx_debug_prep.argtypes = [vp, vp, vp, vp]
     L.wcx_debug_tc_tile_f16.argtypes = [vp, i64, i64, vp]
     L.wcx_debug_prep_f16.argtypes = [vp, vp, vp, vp, vp]

@@ -333,7 +333,6 @@ static int ensure_tf32(wcx_ctx* c) {
   if (launch_center_round(c->d_x, c->n, c->s, c->colsum.as<double>(), c->colcnt.as<double>(), c->xc.as<float>(),
                           c->norm.as<float>(), c->n_pad, c->k_pad, c->stream))
     return 1;
-  if (tc_encode_tensor_map(prep_view(c), c->tmap)) return 1;
   c->launches += 1;
   c->tf32_ready = true;
   return 0;
@@ -396,7 +395,8 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
   std::memset(c->stats, 0, sizeof(c->stats));
   c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0.0;
   if (rows == 0) return 0;
-  if (kernel == WCX_KERNEL_AUTO) kernel = WCX_KERNEL_TC2H;
+  if (kernel == WCX_KERNEL_AUTO || kernel == WCX_KERNEL_TC2) kernel = WCX_KERNEL_TC2H;  // (ids of the removed tf32 variants
+  if (kernel == WCX_KERNEL_TC) kernel = WCX_KERNEL_TCH;                                  //  select the f16 kernel of the same layout)
   if (kernel < WCX_KERNEL_TC || kernel > WCX_KERNEL_TCH) { set_error("wcx_newref_topk: unknown kernel id"); return 1; }
   const bool f16 = kernel == WCX_KERNEL_TC2H || kernel == WCX_KERNEL_TCH;
   const bool pair = kernel == WCX_KERNEL_TC2 || kernel == WCX_KERNEL_TC2H;
@@ -404,13 +404,12 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
   if (c->idx_dev.ensure(sizeof(int32_t) * (size_t)rows * k) || c->dist_dev.ensure(sizeof(double) * (size_t)rows * k))
     return 1;
   if (c->fail.ensure(sizeof(int32_t) * (size_t)rows)) return 1;
-  if (!f16 && kernel != WCX_KERNEL_EXACT && ensure_tf32(c)) return 1;
+  if (kernel == WCX_KERNEL_SIMT && ensure_tf32(c)) return 1;  // the CUDA-core cross-check kernel reads fp32 operands
   PrepView pv = f16 ? prep_view_h(c) : prep_view(c);
   void* tmap = f16 ? c->tmap_h : c->tmap;
   std::vector<int32_t> fail_list;
   // null plan: gather the chosen sample columns first (needs only X), decide whether the re-rank kernel can fuse
   double* d_null = nullptr;
-  bool fused = false;
   c->stage_ms[3] = 0.0;
   if (np && np->m > 0) {
     for (int i = 0; i < np->m; i++)
@@ -424,7 +423,6 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       if (c->nr_dev.ensure(sizeof(double) * (size_t)rows * np->m)) return 1;
       d_null = c->nr_dev.as<double>();
     }
-    fused = kernel != WCX_KERNEL_EXACT && rerank_can_fuse_nulls(c->leaf_n, k);
   }
 
   if (kernel == WCX_KERNEL_EXACT) {
@@ -542,7 +540,7 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       // issue utilisation, the median selection is issue bound), and with host outputs the D2H copy of a finished
       // block (copy stream) overlaps the kernels of the next one.
       static const bool serial_nulls = std::getenv("WCX_SERIAL_NULLS") != nullptr;
-      const bool side = d_null && !fused && !serial_nulls;   // null ratios on the side stream
+      const bool side = d_null && !serial_nulls;   // null ratios on the side stream
       int bq = 0;       // block counter over both regions (events)
       int last_blk = -1;
       for (const Region& rg : {regA, regB}) {
@@ -558,13 +556,12 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
           if (launch_rerank(c->d_x, pv, cvb, nlists, c->cum_dev.as<int64_t>(), c->nchr, rb + r0, rb + r1, k, gon,
                             c->idx_dev.as<int32_t>() + r0 * k, c->dist_dev.as<double>() + r0 * k, c->fail.as<int32_t>() + r0,
                             c->plan_dev.as<int32_t>(), c->plan_len, c->leaf_n ? c->xp.as<double>() : nullptr, c->sp,
-                            c->leafdesc_dev.as<int32_t>(), c->leaf_n, fused ? c->xt.as<double>() : nullptr, fused ? np->m : 0,
-                            fused ? d_null + r0 * np->m : nullptr, st))
+                            c->leafdesc_dev.as<int32_t>(), c->leaf_n, st))
             return 1;
           c->launches += 1;
           WCX_CUDA_OK(cudaEventRecord(c->ev_blk[bq], st));
           cudaEvent_t ready = c->ev_blk[bq];
-          if (d_null && !fused) {
+          if (d_null) {
             cudaStream_t ns = side ? c->null_stream : st;
             if (side) WCX_CUDA_OK(cudaStreamWaitEvent(ns, c->ev_blk[bq], 0));
             if (launch_null_ratios(c->xt.as<double>(), c->n, c->idx_dev.as<int32_t>() + r0 * k, rb + r0, rb + r1, k, np->m,
@@ -792,7 +789,7 @@ static int debug_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out, bo
     return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(c->items_dev.p, &w, sizeof(w), cudaMemcpyHostToDevice, st));
   CandView cv{c->cand_ent.as<uint2>(), c->cand_cnt.as<int32_t>(), c->cand_cut.as<float>(), nullptr};
-  if (!f16 && ensure_tf32(c)) return 1;
+  if (!f16) { set_error("wcx_debug_tc_tile: only the f16 operand set is supported"); return 1; }
   PrepView pv = f16 ? prep_view_h(c) : prep_view(c);
   if (launch_dist_topk_tc_debug(pv, c->items_dev.as<WorkItem>(), 1, cv, f16 ? c->tmap_h : c->tmap, c->dbg.as<float>(), st)) return 1;
   WCX_CUDA_OK(cudaMemcpyAsync(acc_out, c->dbg.p, sizeof(float) * WCX_TILE_M * WCX_TILE_N_TC, cudaMemcpyDeviceToHost, st));
@@ -801,7 +798,6 @@ static int debug_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out, bo
   return 0;
 }
 
-int wcx_debug_tc_tile(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) { return debug_tile(c, row0, col0, acc_out, false); }
 int wcx_debug_tc_tile_f16(wcx_ctx* c, int64_t row0, int64_t col0, float* acc_out) { return debug_tile(c, row0, col0, acc_out, true); }
 
 int wcx_debug_prep_f16(wcx_ctx* c, uint16_t* xh_out, float* norm_out, int32_t* k_pad_out, double* scale_out) {

@@ -1,33 +1,39 @@
-// tcgen05 / TMEM / TMA version of the fused distance + approximate top-k sweep (sm_100a).
+// The distance sweep: fused bins x bins contraction + approximate top-k nomination on tcgen05 / TMEM / TMA (sm_100a).
 //
-// Reference loop replaced: get_ref_for_bins, newref_tools.py:255-278.  The bins x bins squared
-// distance is the one dense contraction of WisecondorX:
+// Reference loop replaced: get_ref_for_bins, newref_tools.py:255-278.  The bins x bins squared distance is the one
+// dense contraction of WisecondorX:
 //     d(i,j) = |a_i|^2 + |b_j|^2 - 2 <a_i, b_j>
-// The <a_i, b_j> tile (128 target bins x 256 candidate bins, K = samples) runs on the 5th-gen
-// tensor cores as a TF32 UMMA with fp32 accumulation in TMEM.  Operands are the centred,
-// tf32-rounded matrix Xc (newref_prep.cu), K-major, staged by TMA into 128B-swizzled shared
-// memory tiles.  The epilogue never writes the distance tile anywhere: each epilogue thread
-// owns one target row (= one TMEM lane), pulls 32 accumulator columns at a time with
-// tcgen05.ld, forms v = |b_j|^2 - 2 acc and appends (v, j) to the row's candidate list only if
-// v is below the row's running threshold (1-2 % of the elements).
+// <a_i, b_j> runs on the 5th-generation tensor cores as a kind::f16 UMMA with fp32 accumulation in TMEM.  Operands are
+// the centred matrix scaled by a power of two and rounded to f16 (newref_prep.cu: same 11-bit significand as tf32 at
+// twice the tensor rate and half the bytes), K-major, staged by TMA into 128-byte-swizzled shared-memory tiles.  The
+// sweep only NOMINATES candidates: rerank.cu recomputes the nominated distances exactly (float64, NumPy's summation
+// order) and proves per row that no candidate was missed, so the f16 rounding never reaches the result.
 //
-// Threshold maintenance (candidates.cuh states the invariant).  After the first 768 entries an
-// exact warp-cooperative selection fixes thr and a ladder of four probe values below it; every
-// append counts itself against the probes (4 compares), and when the first probe has seen
-// WCX_CAND_KEEP entries below it thr drops to that probe -- no list traffic at all.  Entries that
-// end up above thr stay in the list (lazy deletion, filtered by rerank.cu); a physical compaction
-// happens only if a list is about to overflow its 2048 slots (rare).
+// Shipping configuration (PAIR = true): clusters of two CTAs (one per SM) drive one cta_group::2 MMA of M = 256 target
+// rows x N = 256 candidate columns per tile; each CTA stages its own 128 target rows and HALF of the candidate
+// columns (the pair halves the L2 -> SM operand traffic of B).  The epilogue never writes the distance tile: each
+// epilogue thread owns one target row (= one TMEM lane), pulls 32 accumulator columns at a time with tcgen05.ld, forms
+// v = |b_j|^2 - 2 acc and appends (v, j) to the row's candidate list only if v is below the row's running threshold
+// (1-2 % of the elements).
+//
+// Threshold maintenance (candidates.cuh states the invariant).  After the first 512 entries an exact warp-cooperative
+// selection fixes thr and a ladder of four probe values below it; every append counts itself against the probes, and
+// when the first probe has seen WCX_CAND_KEEP_TC entries below it thr drops to that probe -- no list traffic at all.
+// Entries that end up above thr stay in the list (lazy deletion, filtered by rerank.cu); a physical compaction happens
+// only if a list is about to overflow its 4096 slots (rare).
 //
 // Warp roles (384 threads, one CTA per SM, persistent over work items):
 //   warp 0        TMA producer (one elected lane)
-//   warp 1        MMA issuer   (one elected lane, tcgen05.mma cta_group::1 kind::tf32, M128 N256 K8)
-//   warp 2        TMEM allocator (512 columns = two 128x256 fp32 accumulators)
-//   warps 4..7    epilogue group 0: tiles 0,2,4,.. of the CTA (TMEM buffer 0)
-//   warps 8..11   epilogue group 1: tiles 1,3,5,.. of the CTA (TMEM buffer 1)
-//                 warp w owns TMEM lanes 32*(w%4)..+31; each group keeps its own list per row and
-//                 the two groups exchange thresholds through shared memory.
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA, 4 stages of 48 KB) and TMEM full/empty
-// mbarriers (MMA <-> epilogue group).
+//   warp 1        MMA issuer   (one elected lane of the pair's leader CTA: tcgen05.mma cta_group::2 kind::f16, K = 16)
+//   warp 2        TMEM allocator (512 columns = two 256-column fp32 accumulators)
+//   warps 4..11   epilogue: BOTH warp groups drain every accumulator (group g takes the 32-column chunks 2 i + g), so a
+//                 TMEM buffer is handed back after half a drain while the MMA warp fills the other one; each group keeps
+//                 its own list per row and the two groups exchange thresholds through shared memory.
+// Pipelines: smem full / empty mbarriers (TMA <-> MMA, 5 stages of 32 KB per CTA) and TMEM full / empty mbarriers
+// (MMA <-> epilogue).  All CTA pairs walk the candidate axis in lock-step (tiles inside the rows' own chromosome are
+// still multiplied), so every B tile is fetched from HBM once and served from L2 to the other pairs.
+// The one-CTA-per-SM variant (PAIR = false) is kept as a cross-check path and for the single-tile test hook; the tf32
+// operand variants of round 1 are gone.
 #include <cuda.h>
 
 #include "candidates.cuh"
@@ -656,8 +662,8 @@ int launch_dist_topk_tc(const PrepView& pv, const WorkItem* items, int32_t nitem
                         int32_t* work_counter, void* tmap_storage, cudaStream_t st) {
   (void)work_counter;
   if (nitems == 0) return 0;
-  return pv.f16 ? launch_single<true>(pv, items, nitems, cv, tmap_storage, nullptr, 0, st)
-                : launch_single<false>(pv, items, nitems, cv, tmap_storage, nullptr, 0, st);
+  if (!pv.f16) { set_error("dist_topk_tc: only the f16 operand set is supported"); return 1; }
+  return launch_single<true>(pv, items, nitems, cv, tmap_storage, nullptr, 0, st);
 }
 
 template <bool F16>
@@ -693,13 +699,14 @@ int launch_dist_topk_tc_pair(const PrepView& pv, const WorkItem* items, int32_t 
                              cudaStream_t st) {
   if (nitems == 0) return 0;
   if (nitems & 1) { set_error("pair sweep: odd number of work items"); return 1; }
-  return pv.f16 ? launch_pair<true>(pv, items, nitems, cv, tmap_storage, st) : launch_pair<false>(pv, items, nitems, cv, tmap_storage, st);
+  if (!pv.f16) { set_error("dist_topk_tc: only the f16 operand set is supported"); return 1; }
+  return launch_pair<true>(pv, items, nitems, cv, tmap_storage, st);
 }
 
 int launch_dist_topk_tc_debug(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
                               void* tmap_storage, float* dbg_acc, cudaStream_t st) {
-  return pv.f16 ? launch_single<true>(pv, items, nitems, cv, tmap_storage, dbg_acc, 1, st)
-                : launch_single<false>(pv, items, nitems, cv, tmap_storage, dbg_acc, 1, st);
+  if (!pv.f16) { set_error("dist_topk_tc: only the f16 operand set is supported"); return 1; }
+  return launch_single<true>(pv, items, nitems, cv, tmap_storage, dbg_acc, 1, st);
 }
 
 }  // namespace wcx

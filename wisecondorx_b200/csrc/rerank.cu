@@ -21,7 +21,6 @@
 #include <cstdlib>
 #include <vector>
 
-#include "null_ratios.cuh"
 #include "wcx_common.cuh"
 
 namespace wcx {
@@ -493,18 +492,12 @@ __device__ __forceinline__ double combine_leaves(const double* __restrict__ lr, 
 // are final -- the gather-latency-bound re-rank and the issue-bound median selection of different CTAs of an SM
 // then overlap (stand-alone they ran back to back at ~50 % and ~75 % issue utilisation).  xm / m_total / null_out as
 // in null_ratios.cu; rows that are not certified leave their null ratios to the caller.
-struct NullArgs {
-  const double* xm;   // [chunks][n][NR_CHUNK] gathered sample columns
-  double* out;        // [rows][m_total]
-  int32_t m_total;
-};
-
-template <bool VEC, bool LEAF, bool PAIR, bool NULLS>
-__global__ void __launch_bounds__(RR_THREADS, (LEAF && PAIR) ? 3 : 4)  // LDG version: min 4 CTAs/SM keeps the batched loads in flight (64 regs)
+template <bool VEC, bool LEAF>
+__global__ void __launch_bounds__(RR_THREADS, 4)  // min 4 CTAs/SM keeps the batched loads in flight (64 regs)
 rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists, int maxc, const int64_t* __restrict__ cum,
               int nchr, int64_t row_begin, int k, int gonosomal, int32_t* __restrict__ idx_out,
               double* __restrict__ dist_out, int32_t* __restrict__ fail_flags, const int32_t* __restrict__ plan_g,
-              int plan_len, int sp, const int32_t* __restrict__ leaf_g, int nleaves, NullArgs na) {
+              int plan_len, int sp, const int32_t* __restrict__ leaf_g, int nleaves) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int row_len = LEAF ? sp : pv.s;  // doubles per row of `x`
   double* a_s = reinterpret_cast<double*>(rr_smem);
@@ -548,13 +541,6 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   __syncthreads();
   if (s_cs < 0) {  // placeholder rows of gonosomal references (newref_tools.py:186-191)
     for (int t = tid; t < k; t += RR_THREADS) { oi[t] = 0; od[t] = 1.0; }
-    if (NULLS) {
-      // all k indexes are 0: the median of k copies of col[0] is col[0] ((v + v) / 2 is exact)
-      for (int c = tid; c < na.m_total; c += RR_THREADS) {
-        const uint64_t* xm = reinterpret_cast<const uint64_t*>(na.xm) + (int64_t)(c / NR_CHUNK) * pv.n * NR_CHUNK + (c % NR_CHUNK);
-        na.out[lrow * na.m_total + c] = log2(key_d(__ldg(xm + row * NR_CHUNK)) / key_d(__ldg(xm)));
-      }
-    }
     return;
   }
   const int cs = s_cs, ce = s_ce;
@@ -672,15 +658,15 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
       for (int lf = 0; lf < nleaves; lf++) {
         const int off = leaf_s[4 * lf], steps = leaf_s[4 * lf + 1], tail = leaf_s[4 * lf + 2];
         switch (steps) {
-          case 8: leaf_pass<8, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 7: leaf_pass<7, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 6: leaf_pass<6, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 5: leaf_pass<5, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 4: leaf_pass<4, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 3: leaf_pass<3, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 2: leaf_pass<2, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          case 1: leaf_pass<1, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
-          default: leaf_pass<0, PAIR>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 8: leaf_pass<8, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 7: leaf_pass<7, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 6: leaf_pass<6, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 5: leaf_pass<5, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 4: leaf_pass<4, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 3: leaf_pass<3, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 2: leaf_pass<2, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 1: leaf_pass<1, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          default: leaf_pass<0, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
         }
       }
       __syncthreads();
@@ -738,69 +724,26 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
       oi[t] = -1;
     }
   }
-  if (NULLS) {
-    // the row's indexes as the null-ratio gather uses them: positions applied to the FULL column, -1 wraps
-    int32_t* gs = sel;  // dead since the distance phase
-    for (int t = tid; t < k; t += RR_THREADS) {
-      const bool have = t < m && keys[t] < key_1e10;
-      gs[t] = have ? pos_s[t] : (int32_t)(pv.n - 1);
-    }
-    __syncthreads();
-    constexpr int R = 10;  // k <= 320 (checked by the launcher)
-    const int lane = tid & 31, warp = tid >> 5;
-    int32_t g[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int t = r * 32 + lane;
-      g[r] = t < k ? gs[t] : -1;
-    }
-    const int nchunks = (na.m_total + NR_CHUNK - 1) / NR_CHUNK;
-    for (int c = warp; c < nchunks; c += RR_THREADS / 32) {
-      const int mc = min(NR_CHUNK, na.m_total - c * NR_CHUNK);
-      null_row_chunk<R>(reinterpret_cast<const uint64_t*>(na.xm) + (int64_t)c * pv.n * NR_CHUNK, g, k, mc, row, lane,
-                        na.out + lrow * na.m_total + c * NR_CHUNK);
-    }
-  }
-}
-
-bool rerank_can_fuse_nulls(int32_t nleaves, int32_t k) {
-  static const bool force_ldg = std::getenv("WCX_RERANK_LDG") != nullptr;
-  static const char* pair_env = std::getenv("WCX_RERANK_PAIR");
-  // opt-in experiment: at config 3 the fused kernel measured 69.8 ms against 36.4 + 23.3 ms for the separate kernels
-  // -- with all 13 column chunks live at once the 153 MB of gathered columns no longer stay in L2 next to the
-  // re-rank's own gather stream (DRAM reads 158 GB instead of 71 GB, profiles/r01i_ncu_rerank_fused.txt)
-  static const bool no_fuse = std::getenv("WCX_FUSED_NULLS") == nullptr;
-  return !force_ldg && !no_fuse && !(pair_env && pair_env[0] == '1') && nleaves >= 1 && nleaves <= 8 && k <= 320;
 }
 
 int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
-                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves,
-                  const double* null_xm, int32_t null_m, double* null_out, cudaStream_t st) {
+                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves, cudaStream_t st) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0) return 0;
   if (nlists < 1 || nlists > 16) { set_error("rerank: bad number of candidate lists per row"); return 1; }
   const int maxc = nlists <= 2 ? 4096 : 8192;  // list entries below the common cut that fit in shared memory
-  // leaf-major gather (default) needs the permuted copy; WCX_RERANK_LDG=1 forces the row-major LDG gather,
-  // WCX_RERANK_PAIR=1 the two-candidates-per-lane-group variant (3 CTAs per SM instead of 4; measured 37.1 ms
-  // against 35.9 ms at config 3, profiles/r01g_*)
-  static const bool force_ldg = std::getenv("WCX_RERANK_LDG") != nullptr;
-  static const char* pair_env = std::getenv("WCX_RERANK_PAIR");
-  static const bool pair = pair_env && pair_env[0] == '1';
-  const bool leaf = xp != nullptr && !force_ldg && nleaves >= 1 && nleaves <= 8;
+  // the leaf-major gather needs the permuted copy (summation trees of up to 8 leaves, S <= 1024); otherwise the
+  // row-major gather of quads
+  const bool leaf = xp != nullptr && nleaves >= 1 && nleaves <= 8;
   const int row_len = leaf ? sp : pv.s;
   size_t smem = sizeof(double) * ((row_len + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 4 + sizeof(int32_t) * ((3 * plan_len + 3) & ~3);
   if (leaf) smem += sizeof(int32_t) * 4 * nleaves;
   const bool vec = (pv.s % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  static size_t attr[5] = {0, 0, 0, 0, 0};
-  const bool nulls = null_xm != nullptr && null_out != nullptr && null_m > 0;
-  if (nulls && !(leaf && !pair && k <= 320)) { set_error("rerank: fused null ratios need the leaf-major gather and ref_size <= 320"); return 1; }
-  const int which = nulls ? 4 : leaf ? (pair ? 3 : 2) : (vec ? 1 : 0);
-  auto kern = which == 4 ? rerank_kernel<true, true, false, true>
-              : which == 3 ? rerank_kernel<true, true, true, false> : which == 2 ? rerank_kernel<true, true, false, false>
-              : which == 1 ? rerank_kernel<true, false, false, false> : rerank_kernel<false, false, false, false>;
-  NullArgs na{null_xm, null_out, null_m};
+  static size_t attr[3] = {0, 0, 0};
+  const int which = leaf ? 2 : (vec ? 1 : 0);
+  auto kern = which == 2 ? rerank_kernel<true, true> : which == 1 ? rerank_kernel<true, false> : rerank_kernel<false, false>;
   if (smem > attr[which]) {
     WCX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[which] = smem;
@@ -808,7 +751,7 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
   WCX_CUDA_OK(cudaMemsetAsync(fail_flags, 0, sizeof(int32_t) * rows, st));
   kern<<<(unsigned)rows, RR_THREADS, smem, st>>>(leaf ? xp : x, pv, cv, nlists, maxc, cum_dev, nchr, row_begin, k, gonosomal, idx_out,
                                                dist_out, fail_flags, sum_plan, plan_len, leaf ? sp : 0, leaf ? leaf_dev : nullptr,
-                                               leaf ? nleaves : 0, na);
+                                               leaf ? nleaves : 0);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

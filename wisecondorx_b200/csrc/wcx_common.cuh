@@ -83,10 +83,7 @@ int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host);  // eleme
 int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlists, const int64_t* cum_dev,
                   int32_t nchr, int64_t row_begin, int64_t row_end, int32_t k, int32_t gonosomal,
                   int32_t* idx_out, double* dist_out, int32_t* fail_flags, const int32_t* sum_plan,
-                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves,
-                  const double* null_xm, int32_t null_m, double* null_out, cudaStream_t st);
-// true when launch_rerank can compute the null ratios in the same kernel for this shape (leaf-major gather, k <= 320)
-bool rerank_can_fuse_nulls(int32_t nleaves, int32_t k);
+                  int32_t plan_len, const double* xp, int32_t sp, const int32_t* leaf_dev, int32_t nleaves, cudaStream_t st);
 // leaf-major copy of X for the re-rank gather (rerank.cu): layout from the summation plan, then the copy itself
 int build_leaf_layout(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& perm, std::vector<int32_t>& desc);
 int launch_permute_rows(const double* x, int64_t n, int32_t s, const int32_t* perm_dev, int32_t sp, double* xp, cudaStream_t st);
