@@ -469,6 +469,8 @@ def run_ours(args, rank, world, local_rank):
                 sr.run(x_slice_pin, per, cum, ids)
 
             e2e_ms, _, _ = timed(step_e2e, max(1, args.steps // 2), max(1, args.warmup))
+            e2e_phases = {}
+            sr.run(x_slice_pin, per, cum, ids, phases=e2e_phases)  # one more pass with a synchronisation after every phase
             ho = sr.host_out
             e2e_same = bool(np.array_equal(ho[0][rb:re], idx_dev.cpu().numpy()) and np.array_equal(ho[1][rb:re], dist_dev.cpu().numpy())
                             and np.array_equal(ho[2][rb:re], nr_dev.cpu().numpy(), equal_nan=True))
@@ -496,6 +498,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank checks its own block of the host arrays
         e2e_same = bool(flag.item())
     e2e_value = pairs_total / (e2e_ms * 1e-3)
+    e2e_phases = locals().get("e2e_phases")
 
     if rank != 0:
         if world > 1:
@@ -536,7 +539,8 @@ def run_ours(args, rank, world, local_rank):
                                   "row blocks on a side stream next to the re-rank of the following block "
                                   "(stages_ms.null_ratios = what they add after the last re-rank block)"},
         "e2e": {"value": e2e_value, "unit": "bin-pair dist/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "equals_resident_result": e2e_same, "path": e2e_path},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "equals_resident_result": e2e_same, "path": e2e_path,
+                "phases_ms_cumulative_rank0": {k: round(v, 2) for k, v in e2e_phases.items()} if e2e_phases else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "dist_topk_tc_kernel", "achieved": achieved, "peak": peak_tc,

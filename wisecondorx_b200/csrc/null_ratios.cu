@@ -358,7 +358,6 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
         const uint32_t c0 = xqc[q.x], c1 = xqc[q.y], c2 = xqc[q.z], c3 = xqc[q.w];
         k2[2 * j] = c0 | (c1 << 16);
         k2[2 * j + 1] = c2 | (c3 << 16);
-        if ((j & 7) == 7) asm volatile("" ::: "memory");  // bounded number of gathers in flight: no spills
       }
     } else {
 #pragma unroll
@@ -367,7 +366,6 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
         if (2 * j < k) c0 = xqc[orow[2 * j]];
         if (2 * j + 1 < k) c1 = xqc[orow[2 * j + 1]];
         k2[j] = c0 | (c1 << 16);
-        if ((j & 15) == 15) asm volatile("" ::: "memory");
       }
     }
     const int t = k >> 1;  // rank of the upper middle key (the median itself for odd k)

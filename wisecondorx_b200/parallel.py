@@ -154,6 +154,10 @@ class ShardedReference:
                 self.engine = engine or newref_tools.NewrefEngine(self.device.index or 0)
                 self.engine.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._host_t = tuple(torch.from_numpy(a) for a in self.host_out)
+        self.chunks = 4 if self.device.type == "cuda" and self.world > 1 else 1
+        if self.chunks > 1:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._copy_ev = [torch.cuda.Event() for _ in range(self.chunks)]
         dist.barrier(group=group)
 
     def slice_of(self, x):
@@ -161,22 +165,50 @@ class ShardedReference:
         a = self.rank * self.slice_rows
         return x[a: min(self.n, a + self.slice_rows)]
 
-    def run(self, x_slice_host, per, cum, sample_ids):
+    def run(self, x_slice_host, per, cum, sample_ids, phases=None):
         """x_slice_host: this rank's slice of X (torch CPU tensor, ideally pinned, or NumPy).  Returns the three host
-        arrays (views of the shared segment; complete on every rank after the closing barrier)."""
+        arrays (views of the shared segment; complete on every rank after the closing barrier).
+        phases: optional dict that receives the wall-clock of the phases in ms (adds stream synchronisations)."""
+        import time
+        t_start = time.perf_counter()
+
+        def mark(name):
+            if phases is not None:
+                if self.device.type == "cuda":
+                    torch.cuda.synchronize(self.device)
+                phases[name] = (time.perf_counter() - t_start) * 1e3
         if not torch.is_tensor(x_slice_host):
             x_slice_host = torch.from_numpy(np.ascontiguousarray(x_slice_host, dtype=np.float64))
         r = x_slice_host.shape[0]
-        self.x_slice[:r].copy_(x_slice_host, non_blocking=True)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.x_full, self.x_slice, group=self.group)
+        if self.world > 1 and self.device.type == "cuda" and self.chunks > 1:
+            # upload and exchange in row chunks: the NCCL all-gather of chunk c runs (on NCCL's stream) while chunk
+            # c + 1 is still crossing PCIe; every chunk lands at its final place in the gathered matrix
+            cur = torch.cuda.current_stream(self.device)
+            step = -(-self.slice_rows // self.chunks)
+            for c in range(self.chunks):
+                a, b = c * step, min(self.slice_rows, (c + 1) * step)
+                if b <= a:
+                    break
+                with torch.cuda.stream(self._copy_stream):
+                    if a < r:
+                        self.x_slice[a:min(b, r)].copy_(x_slice_host[a:min(b, r)], non_blocking=True)
+                    self._copy_ev[c].record(self._copy_stream)
+                cur.wait_event(self._copy_ev[c])
+                outs = [self.x_full[w * self.slice_rows + a: w * self.slice_rows + b] for w in range(self.world)]
+                dist.all_gather(outs, self.x_slice[a:b], group=self.group)
         else:
-            self.x_full.copy_(self.x_slice)
+            self.x_slice[:r].copy_(x_slice_host, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.x_full, self.x_slice, group=self.group)
+            else:
+                self.x_full.copy_(self.x_slice)
+        mark("upload_and_all_gather")
         xd = self.x_full[: self.n]
         start, end = self.bounds[self.rank]
         ids = list(sample_ids)
         if self.compute_fn is None:
             self.engine.load(None, per, cum, on_device_ptr=xd.data_ptr(), shape=(self.n, self.s))
+            mark("prepare_operands")
             # host outputs: the library copies every finished row block to the (page-locked) shared segment while the
             # next block is still in the re-rank, instead of one D2H of the whole part at the end
             self.engine.reference(start, end, self.k, ids, out=tuple(a[start:end] for a in self.host_out))
@@ -186,7 +218,9 @@ class ShardedReference:
                 host[start:end].copy_(dev, non_blocking=True)
             if self.device.type == "cuda":
                 torch.cuda.current_stream(self.device).synchronize()
+        mark("compute_and_download")
         dist.barrier(group=self.group)
+        mark("barrier")
         return self.host_out
 
     def close(self):
