@@ -107,7 +107,8 @@ int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
  * events on the context's stream: out[0] = sweep (distance + approximate top-k), out[1] = exact
  * re-rank, out[2] = brute-force rows, out[3] = last wcx_newref_null_ratios, out[4] = last
  * wcx_newref_load preparation kernels; out[5] = exact float64 distances evaluated by the re-rank,
- * out[6] = list entries below the cut gathered by the re-rank (counters, not times), out[7] reserved. */
+ * out[6] = list entries below the cut gathered by the re-rank (counters, not times), out[7] = how long the sweep's
+ * partial last round (launched beside the re-rank) runs past the main sweep launch; out[0] includes it. */
 int wcx_newref_stage_ms(wcx_ctx* ctx, double* out8);
 
 /* ---- newref preparation ---------------------------------------------------------------------

@@ -6,6 +6,7 @@ segment means, 0-based half-open coordinates) is restated here line by line."""
 from __future__ import annotations
 
 import ctypes
+import logging
 
 import numpy as np
 
@@ -95,11 +96,24 @@ def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, np
     return cbs_segments_batch([(results_r, results_w, ref_gender)], alpha, binsize, seed, nperm, ctx)[0]
 
 
+_noted = [False]
+
+
+def _note_not_bit_compatible():
+    """Once per process: the segmentation follows DNAcopy's algorithm but not R's random stream."""
+    if not _noted[0]:
+        logging.info("Segmentation runs on the GPU (circular binary segmentation as in DNAcopy::segment; permutations come "
+                     "from a Philox stream, not R's Mersenne Twister, and the full permutation count replaces DNAcopy's "
+                     "sequential stopping rule): breakpoints of borderline segments can differ from the reference's R run")
+        _noted[0] = True
+
+
 def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None):
     """CBS.R for a batch of samples [(results_r, results_w, ref_gender), ...] with ONE device call over all
     (sample, chromosome) series.  The permutation streams are keyed by (seed, chromosome), not by the position of a
     series in the batch, so every sample gets the segments it would get alone."""
     from .predict_control import _map_threads
+    _note_not_bit_compatible()
     seed_i = 0 if seed is None else int(seed)
     preps, series, ids, counts = [], [], [], []
     for p, s, i in _map_threads(lambda t: _cbs_prepare(*t), samples):

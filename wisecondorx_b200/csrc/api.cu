@@ -66,10 +66,12 @@ struct wcx_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished outputs overlapped with the next stage
   cudaStream_t null_stream = nullptr;  // high priority: null ratios of finished row blocks next to the re-rank of the next
+  cudaStream_t tail_stream = nullptr;  // high priority: the sweep's partial last round (region B) next to the re-rank of region A
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev_blk[16] = {};         // per row block: re-rank done / null ratios done
   cudaEvent_t ev_null[16] = {};
   cudaEvent_t ev_tail[2] = {};         // timing of the exposed null-ratio tail
+  cudaEvent_t ev_tailsweep[2] = {};    // the sweep's partial last round (region B) on the side stream
   cudaEvent_t ev[8] = {};
   // newref state
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
@@ -170,10 +172,12 @@ int wcx_create(int32_t device, wcx_ctx** out) {
     int lo = 0, hi = 0;
     WCX_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     WCX_CUDA_OK(cudaStreamCreateWithPriority(&c->null_stream, cudaStreamNonBlocking, hi));
+    WCX_CUDA_OK(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, hi));
   }
   for (auto& e : c->ev_blk) WCX_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : c->ev_null) WCX_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : c->ev_tail) WCX_CUDA_OK(cudaEventCreate(&e));
+  for (auto& e : c->ev_tailsweep) WCX_CUDA_OK(cudaEventCreate(&e));
   for (auto& e : c->ev) WCX_CUDA_OK(cudaEventCreate(&e));
   *out = c;
   return 0;
@@ -200,7 +204,9 @@ void wcx_destroy(wcx_ctx* c) {
   for (auto& e : c->ev_blk) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_null) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_tail) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_tailsweep) if (e) cudaEventDestroy(e);
   if (c->null_stream) cudaStreamDestroy(c->null_stream);
+  if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -445,39 +451,45 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     const int tile_n = kernel == WCX_KERNEL_SIMT ? WCX_TILE_N_SIMT : WCX_TILE_N_TC;
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, c->device);
-    // Work items.  Every item is one tile of 128 target rows against a range of candidate column tiles; a persistent
-    // grid takes them round-robin, so the sweep lasts ceil(units / CTAs) unit times.  Two regions of rows:
-    //   A  the units that fill whole rounds of the grid: one item per row tile over ALL columns (2 lists per row);
-    //   B  the units of the last, partial round: split into sB column ranges each (2 sB lists per row), so the tail
-    //      costs ceil(L sB / CTAs) / sB of a unit time instead of a whole one.  At config 3 the last of 11 rounds
-    //      held 9 of 74 CTA pairs busy; on 1/8 of the rows (8 GPUs) it was 2.53 rounds of work in 3.
+    // Work items.  Every item is one tile of 128 target rows against the candidate column tiles; a persistent grid of
+    // CTA pairs takes the units (two items = 256 rows) round-robin, so the sweep lasts ceil(units / pairs) unit times:
+    // 10.12 rounds of work in 11 at config 3, 1.27 in 2 on 1/8 of the rows (8 GPUs).  Two regions of rows:
+    //   A  the units that fill whole rounds of the grid -- the main launch;
+    //   B  the units of the last, partial round -- a second launch on a high-priority stream that needs only 2 L of the
+    //      SMs and runs WHILE region A is already in the re-rank (tensor-bound next to a gather-latency-bound kernel).
+    // (Splitting region B into candidate-column ranges instead -- WCX_TAIL_SPLIT=s, 2 s lists per row -- was measured and
+    // does not pay: on 1/s of the columns a list's threshold stays s times looser, the epilogue appends s times more
+    // entries and the first tiles of every sub-unit append everything; the tail got no shorter on 8 GPUs.)
     std::vector<WorkItem> items;
     const int lps = kernel == WCX_KERNEL_SIMT ? 1 : 2;  // the tcgen05 kernel keeps one list per epilogue group
     build_items(c, rb, re, tile_n, 1, lps, items);
     const int nct = (int)((c->n + tile_n - 1) / tile_n);
     Region regA{0, rows, 1, 0}, regB{rows, rows, 1, 0};
+    bool tail_overlap = false;
+    size_t n_items_a = 0;
     if (pair) {
       const int n_units = ((int)items.size() + 1) / 2;
       const int P = std::max(1, dev_sms / 2);  // CTA pairs of the persistent grid
-      static const char* split_env = std::getenv("WCX_TAIL_SPLIT");  // tests: force a split factor (1 = off)
+      const char* split_env = std::getenv("WCX_TAIL_SPLIT");  // experiment / tests: column split factor of region B
+      static const bool no_overlap = std::getenv("WCX_TAIL_SERIAL") != nullptr;
       const int full_units = (n_units / P) * P;
-      const int L = n_units - full_units;
+      const int L = full_units > 0 ? n_units - full_units : 0;  // fewer units than CTA pairs: one launch, nothing to overlap
       int sB = 1;
-      if (L > 0) {
-        double best = 1.0;  // duration of the tail in unit times
-        for (int sc = 2; sc <= 8 && nct / sc >= 8; sc *= 2) {
-          const double t = (double)((L * sc + P - 1) / P) / sc;
-          if (t < best - 1e-9) { best = t; sB = sc; }
-        }
-        if (split_env) { const int f = std::atoi(split_env); if (f >= 1 && f <= 8 && (f & (f - 1)) == 0 && nct / f >= 1) sB = f; }
-      }
+      if (L > 0 && split_env) { const int f = std::atoi(split_env); if (f >= 1 && f <= 8 && (f & (f - 1)) == 0 && nct / f >= 1) sB = f; }
+      tail_overlap = L > 0 && sB == 1 && !no_overlap;
       std::vector<WorkItem> base;
       base.swap(items);
-      const size_t nA = std::min(base.size(), (size_t)2 * full_units);
+      const size_t nA = L > 0 ? std::min(base.size(), (size_t)2 * full_units) : base.size();
       const int64_t rowsA = nA < base.size() ? (int64_t)base[nA].row0 - rb : rows;
       regA = Region{0, rowsA, 1, 0};
       regB = Region{rowsA, rows, sB, (size_t)rowsA * lps};
       for (size_t i = 0; i < nA; i++) items.push_back(base[i]);  // slot0 / stride of build_items(nsplit = 1) are region A's
+      if (items.size() & 1) {  // (only when there is no region B) pad the odd item count
+        WorkItem d = items.back();
+        d.row0 = 0; d.nrows = 0; d.slot0 = 0;
+        items.push_back(d);
+      }
+      n_items_a = items.size();
       // region B: pair mode wants items (2p, 2p + 1) on the same column range -> split-major order, odd groups padded
       for (int q = 0; q < sB; q++) {
         int cnt = 0;
@@ -497,11 +509,6 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
           d.row0 = 0; d.nrows = 0; d.slot0 = 0;
           items.push_back(d);
         }
-      }
-      if (regB.r1 == regB.r0 && (items.size() & 1)) {  // no region B: pad region A's odd item count
-        WorkItem d = items.back();
-        d.row0 = 0; d.nrows = 0; d.slot0 = 0;
-        items.push_back(d);
       }
     } else {
       // one CTA per SM / CUDA-core kernels (cross-check paths): one uniform column split as before
@@ -528,6 +535,15 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     WCX_CUDA_OK(cudaEventRecord(c->ev[0], st));
     if (kernel == WCX_KERNEL_SIMT) {
       if (launch_dist_topk_simt(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, c->counter.as<int32_t>(), st)) return 1;
+    } else if (pair && tail_overlap) {
+      // region B on the tail stream (ready as soon as the lists are zeroed: its CTA pairs take the first SMs the main
+      // launch frees), region A on the caller's stream; the re-rank of region A follows region A only
+      WCX_CUDA_OK(cudaStreamWaitEvent(c->tail_stream, c->ev[0], 0));
+      if (launch_dist_topk_tc_pair(pv, c->items_dev.as<WorkItem>(), (int)n_items_a, cv, tmap, st)) return 1;
+      WCX_CUDA_OK(cudaEventRecord(c->ev_tailsweep[0], c->tail_stream));
+      if (launch_dist_topk_tc_pair(pv, c->items_dev.as<WorkItem>() + n_items_a, (int)(items.size() - n_items_a), cv, tmap, c->tail_stream)) return 1;
+      WCX_CUDA_OK(cudaEventRecord(c->ev_tailsweep[1], c->tail_stream));
+      c->launches += 1;
     } else if (pair) {
       if (launch_dist_topk_tc_pair(pv, c->items_dev.as<WorkItem>(), (int)items.size(), cv, tmap, st)) return 1;
     } else {
@@ -546,8 +562,11 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       for (const Region& rg : {regA, regB}) {
         const int64_t rrows = rg.r1 - rg.r0;
         if (rrows <= 0) continue;
+        if (tail_overlap && rg.r0 == regB.r0 && rg.r1 == regB.r1) WCX_CUDA_OK(cudaStreamWaitEvent(st, c->ev_tailsweep[1], 0));
         const int nlists = rg.nsplit * lps;
-        const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(rg.nsplit > 1 && pair ? 2 : 8, rrows / 12000));  // >= 12 k rows per block: two full waves of the null kernel
+        // >= 4 k rows per block (7 waves of re-rank CTAs); with host outputs the copy of a block hides behind the kernels of
+        // the next one, so a part of 24 k rows (8 GPUs) wants more than two blocks
+        const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(rg.nsplit > 1 && pair ? 3 : 8, rrows / 4000));
         for (int bi = 0; bi < nblk; bi++, bq++) {
           const int64_t r0 = rg.r0 + rrows * bi / nblk, r1 = rg.r0 + rrows * (bi + 1) / nblk;
           if (r1 <= r0) continue;
@@ -601,6 +620,16 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stage_ms[0] = ms;
+    if (tail_overlap) {
+      // + the time the partial last round needs on top of the main launch (it starts on the first freed SMs and ends
+      // inside the re-rank of region A): sweep = first list write to last list write
+      float ms_b = 0.f;
+      cudaEventElapsedTime(&ms_b, c->ev[0], c->ev_tailsweep[1]);
+      c->stage_ms[7] = ms_b > ms ? ms_b - ms : 0.f;
+      c->stage_ms[0] = ms_b > ms ? ms_b : ms;
+    } else {
+      c->stage_ms[7] = 0.0;
+    }
     cudaEventElapsedTime(&ms, c->ev[1], c->ev_tail[0]);
     c->stage_ms[1] = ms;
     c->stats[0] = (int64_t)items.size();

@@ -133,7 +133,7 @@ class NewrefEngine:
         out = np.zeros(8, dtype=np.float64)
         _lib.check(_lib.load().wcx_newref_stage_ms(self.ctx.handle, _ptr(out)))
         return {"sweep": out[0], "rerank": out[1], "exact_rows": out[2], "null_ratios": out[3], "prep": out[4],
-                "exact_evals": out[5], "gathered_entries": out[6]}
+                "exact_evals": out[5], "gathered_entries": out[6], "sweep_tail_past_main": out[7]}
 
 
 def get_reference(pca_corrected_data, masked_bins_per_chr, masked_bins_per_chr_cum, ref_size, part,
