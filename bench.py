@@ -416,7 +416,7 @@ def run_ours(args, rank, world, local_rank):
 
     launches0 = eng.stats()["launches"]
 
-    stage_acc = {"sweep": 0.0, "rerank": 0.0, "exact_rows": 0.0, "null_ratios": 0.0}
+    stage_acc = {"sweep": 0.0, "rerank": 0.0, "exact_rows": 0.0, "null_ratios": 0.0, "sweep_tail_past_main": 0.0}
 
     def step_resident_timed():
         step_resident()
@@ -516,8 +516,12 @@ def run_ours(args, rank, world, local_rank):
         pass
     # dominant kernel: the tensor-core sweep.  Algorithmic flops = 2 * S * pairs;
     # TF32 dense peak taken as half the measured bf16 cuBLAS figure (nominal 1:2 ratio).
-    my_pairs = n_pairs(per, rb, re)
-    sweep_ms = stage_acc["sweep"] / args.steps
+    # The sweep is two launches of the same kernel: the main one (whole rounds of the persistent grid, all SMs) and the
+    # partial last round (its own launch beside the re-rank).  The roofline entry is the MAIN launch: its flops (the rows
+    # it sweeps) over its own duration (stages_ms.sweep minus what the partial round runs past it).
+    rows_main = st.get("rows_main_sweep", rows) or rows
+    my_pairs = n_pairs(per, rb, rb + rows_main)
+    sweep_ms = (stage_acc["sweep"] - stage_acc["sweep_tail_past_main"]) / args.steps
     achieved = 2.0 * s * my_pairs / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else None
     # operand type of the sweep actually run: f16 (default, kernels 0 / 5 / 6) runs at the bf16/f16 tensor rate the
     # driver measured; tf32 (kernels 1 / 4) at half of it (nominal ratio)
@@ -546,7 +550,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "dist_topk_tc_kernel", "achieved": achieved, "peak": peak_tc,
                      "unit": "TFLOP/s", "frac": (achieved / peak_tc) if achieved else None, "traffic": traffic,
                      "peak_src": f"{peaks['src']}: bf16_tflops_sustained" + ("" if f16 else " / 2 (tf32)"),
-                     "kernel_ms": sweep_ms},
+                     "kernel_ms": sweep_ms, "rows_of_launch": int(rows_main), "rows_total": int(rows)},
         "stages_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
         "exact_fallback_rows": st["exact_fallback_rows"],
     }

@@ -98,8 +98,8 @@ int wcx_get_reference(wcx_ctx* ctx, const double* x, int64_t n, int32_t s, const
                       double* dist_out, double* null_out);
 
 /* Counters of the last wcx_newref_topk call: out[0] = work items, out[1] = rows recomputed by the
- * exact brute-force path, out[2] = kernel launches issued since wcx_create, out[3] = column
- * splits per row, out[4] = sweep kernel used, out[5] = exact list compactions, out[6] = streamed
+ * exact brute-force path, out[2] = kernel launches issued since wcx_create, out[3] = rows swept by the main
+ * sweep launch (the remaining rows: the partial last round, launched beside the re-rank), out[4] = sweep kernel used, out[5] = exact list compactions, out[6] = streamed
  * (overflow) compactions, out[7] = ladder threshold steps. */
 int wcx_newref_stats(wcx_ctx* ctx, int64_t* out8);
 

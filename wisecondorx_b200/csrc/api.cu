@@ -633,7 +633,7 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     cudaEventElapsedTime(&ms, c->ev[1], c->ev_tail[0]);
     c->stage_ms[1] = ms;
     c->stats[0] = (int64_t)items.size();
-    c->stats[3] = regB.r1 > regB.r0 ? regB.nsplit : regA.nsplit;
+    c->stats[3] = regA.r1 - regA.r0;  // rows swept by the main launch (the rest: the overlapped partial round)
     c->stats[5] = diag_h[0];
     c->stats[6] = diag_h[1];
     c->stats[7] = diag_h[2];

@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include "null_ratios.cuh"
+#include "packed_select.cuh"
 #include "wcx_common.cuh"
 
 namespace wcx {
@@ -88,9 +89,7 @@ __global__ void gather_cols_kernel(const double* __restrict__ x, int64_t n, int3
 // =================================================================================================================
 constexpr int NQ_STRIDE = 128;         // code row stride in columns (uint16)
 constexpr int NQ_HBINS = 65536;        // histogram cells per column
-constexpr uint32_t NQ_LO = 0x0400u;    // smallest code: smallest positive normal fp16
-constexpr uint32_t NQ_HI = 0x7BFEu;    // largest code (0x7BFF = largest finite fp16 is the padding key)
-constexpr uint32_t NQ_PAD = 0x7BFFu;
+constexpr uint32_t NQ_LO = PS_CODE_LO, NQ_HI = PS_CODE_HI, NQ_PAD = PS_CODE_PAD;
 
 struct NqCol {
   double lo, scale;   // histogram cell of v: (v - lo) * scale
@@ -212,97 +211,6 @@ nq_code_kernel(const uint64_t* __restrict__ xm, int64_t n, int m, const NqCol* _
   xq[b * NQ_STRIDE + col] = (uint16_t)code;
 }
 
-// ---- packed fp16 helpers: the codes are bit patterns of positive normal halves, so fp16 compares order them ----
-__device__ __forceinline__ uint32_t h2_lt(uint32_t a, uint32_t b) {  // 1.0h per half where a < b
-  uint32_t d;
-  asm("set.lt.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ int h2_total(uint32_t acc) {  // sum of the two (small, integral) halves
-  return (int)(__half2float(__ushort_as_half((unsigned short)(acc & 0xffffu))) +
-               __half2float(__ushort_as_half((unsigned short)(acc >> 16))));
-}
-template <int NP>
-__device__ __forceinline__ int nq_count_lt(const uint32_t (&k2)[NP], uint32_t trial) {
-  const uint32_t t2 = trial | (trial << 16);
-  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // four chains; each half counts at most NP / 4 + 1: exact in fp16
-#pragma unroll
-  for (int j = 0; j < NP; j += 4) {
-    a0 = h2_add(a0, h2_lt(k2[j], t2));
-    if (j + 1 < NP) a1 = h2_add(a1, h2_lt(k2[j + 1], t2));
-    if (j + 2 < NP) a2 = h2_add(a2, h2_lt(k2[j + 2], t2));
-    if (j + 3 < NP) a3 = h2_add(a3, h2_lt(k2[j + 3], t2));
-  }
-  return h2_total(a0) + h2_total(a1) + h2_total(a2) + h2_total(a3);
-}
-__device__ __forceinline__ uint32_t h2_eq(uint32_t a, uint32_t b) {  // 1.0h per half where a == b
-  uint32_t d;
-  asm("set.eq.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("mul.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-// bit pattern of the fp16 pair (float(lo), float(hi)) for small non-negative integers (exact below 2048)
-__host__ __device__ constexpr uint32_t h_bits(int v) {
-  if (v == 0) return 0u;
-  int e = 0;
-  while ((v >> e) > 1) e++;
-  return (uint32_t)(((e + 15) << 10) | (((v << (10 - e)) & 0x3ff)));
-}
-__host__ __device__ constexpr uint32_t h2_const(int lo, int hi) { return h_bits(lo) | (h_bits(hi) << 16); }
-
-// largest key below `lim` as a code (0 if none): key * [key < lim] keeps the key or +0, fp16 max orders the patterns
-template <int NP>
-__device__ __forceinline__ uint32_t nq_max_below(const uint32_t (&k2)[NP], uint32_t lim) {
-  const uint32_t l2 = lim | (lim << 16);
-  uint32_t b0 = 0, b1 = 0;
-#pragma unroll
-  for (int j = 0; j < NP; j += 2) {
-    b0 = h2_max(b0, h2_mul(k2[j], h2_lt(k2[j], l2)));
-    if (j + 1 < NP) b1 = h2_max(b1, h2_mul(k2[j + 1], h2_lt(k2[j + 1], l2)));
-  }
-  const uint32_t b = h2_max(b0, b1);
-  const uint32_t lo = b & 0xffffu, hi = b >> 16;
-  return lo > hi ? lo : hi;
-}
-// number of keys equal to `code` and the sum of (position + 1) over them -- the position itself when there is one
-template <int NP>
-__device__ __forceinline__ void nq_find(const uint32_t (&k2)[NP], uint32_t code, int& count, int& pos) {
-  const uint32_t c2 = code | (code << 16);
-  uint32_t n0 = 0, n1 = 0, p0 = 0, p1 = 0;
-#pragma unroll
-  for (int j = 0; j < NP; j += 2) {
-    const uint32_t e0 = h2_eq(k2[j], c2);
-    n0 = h2_add(n0, e0);
-    p0 = h2_fma(e0, h2_const(2 * j + 1, 2 * j + 2), p0);
-    if (j + 1 < NP) {
-      const uint32_t e1 = h2_eq(k2[j + 1], c2);
-      n1 = h2_add(n1, e1);
-      p1 = h2_fma(e1, h2_const(2 * j + 3, 2 * j + 4), p1);
-    }
-  }
-  count = h2_total(n0) + h2_total(n1);
-  pos = h2_total(p0) + h2_total(p1) - 1;  // meaningful only when count == 1 (sums of several positions may round)
-}
-
 // reference position -> bin of the full column: -1 (missing entries) wraps to the last bin like a Python index.  The
 // positions come from this library's own re-rank or were validated by the host (wcx_newref_null_ratios), so they lie
 // in [-n, n): no clamp on the hot path.
@@ -369,24 +277,18 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
       }
     }
     const int t = k >> 1;  // rank of the upper middle key (the median itself for odd k)
-    uint32_t T = 0;
     int below = 0;
-#pragma unroll 1
-    for (int bit = 14; bit >= 0; bit--) {
-      const uint32_t trial = T | (1u << bit);
-      const int c = nq_count_lt<NP>(k2, trial);
-      if (c <= t) { T = trial; below = c; }
-    }
+    const uint32_t T = ps_select<NP>(k2, t, below);
     // T is the code of the rank-t key: count(< T) <= t < count(< T + 1).  It can stand for its VALUE only if no
     // other key shares the code; an even k also needs the rank t - 1 key: the largest key below T, provided rank t is
     // the first key with code T.
     int eq_hi, j_hi, eq_lo = 1, j_lo = 0;
-    nq_find<NP>(k2, T, eq_hi, j_hi);
+    ps_find<NP>(k2, T, eq_hi, j_hi);
     bool ok = eq_hi == 1;
     if (ok && !(k & 1)) {
       ok = below == t;
       if (ok) {
-        nq_find<NP>(k2, nq_max_below<NP>(k2, T), eq_lo, j_lo);
+        ps_find<NP>(k2, ps_max_below<NP>(k2, T), eq_lo, j_lo);
         ok = eq_lo == 1;
       }
     }

@@ -126,7 +126,7 @@ class NewrefEngine:
         out = np.zeros(8, dtype=np.int64)
         _lib.check(_lib.load().wcx_newref_stats(self.ctx.handle, _ptr(out)))
         return {"work_items": int(out[0]), "exact_fallback_rows": int(out[1]), "launches": int(out[2]),
-                "column_splits": int(out[3]), "kernel": int(out[4]), "exact_compactions": int(out[5]),
+                "rows_main_sweep": int(out[3]), "kernel": int(out[4]), "exact_compactions": int(out[5]),
                 "stream_compactions": int(out[6]), "ladder_steps": int(out[7])}
 
     def stage_ms(self):
