@@ -120,55 +120,3 @@ def test_normalize_midsize_vs_oracle():
             assert np.array_equal(nb[b], nn)
             np.testing.assert_allclose([mlb[b], mzb[b]], [m_lr, m_z], rtol=1e-7, atol=1e-9)
         np.testing.assert_allclose(wb, w, rtol=1e-12)
-
-
-@pytest.mark.parametrize("batch,k", [(1, 300), (3, 300), (40, 60), (2, 101)])
-def test_normalize_thread_per_bin_equals_warp_selection(batch, k):
-    """The thread-per-(bin, sample) kernel (15-bit codes, packed fp16 bisection, exact fallback) against the
-    warp-per-bin kernel with the exact 64-bit selection (WCX_NORM_WARP=1) on data with heavy ties (quantised counts),
-    bins without coverage, and reference lists with out-of-cutoff entries: medians (r) and reference counts must be
-    identical, z within the rounding of the differently ordered sums."""
-    rng = np.random.default_rng(100 + batch + k)
-    per = np.array([700, 600, 500, 400] + [100] * 18 + [150, 60])
-    cum = np.cumsum(per)
-    n = int(cum[-1])
-    idx = np.empty((n, k), dtype=np.int32)
-    for c in range(len(per)):
-        s0, e0 = int(cum[c] - per[c]), int(cum[c])
-        idx[s0:e0] = rng.integers(0, n - per[c], size=(e0 - s0, k))
-    idx[10, 5:] = -1
-    dist = np.sort(rng.random((n, k)) * 2.0, axis=1)
-    bpc = per + 3
-    mask = np.ones(int(bpc.sum()), dtype=bool)
-    o = 0
-    for nb in bpc:
-        mask[o + rng.choice(int(nb), 3, replace=False)] = False
-        o += int(nb)
-    comps = np.linalg.qr(rng.standard_normal((n, 5)))[0].T.copy()
-    for sfx in ("", ".F"):
-        pass
-    ref = {"indexes": idx, "distances": dist, "masked_bins_per_chr": per, "masked_bins_per_chr_cum": cum,
-           "pca_components": comps, "pca_mean": np.full(n, 1.0 / n), "mask": mask, "bins_per_chr": bpc,
-           "indexes.F": idx, "distances.F": dist, "masked_bins_per_chr.F": per, "masked_bins_per_chr_cum.F": cum,
-           "pca_components.F": comps, "pca_mean.F": np.full(n, 1.0 / n), "mask.F": mask, "bins_per_chr.F": bpc}
-    offs = np.concatenate([[0], np.cumsum(bpc)]).astype(int)
-    samples = []
-    for b in range(batch):
-        c = rng.poisson(4.0 if b % 2 else 40.0, int(bpc.sum())).astype(np.int32)  # low depth: many equal values
-        c[rng.integers(0, len(c), 50)] = 0
-        samples.append({str(i + 1): c[offs[i]:offs[i + 1]] for i in range(24)})
-    args = types.SimpleNamespace(maskrepeats=3)
-    eng = predict_tools.PredictEngine(0, predict_tools._lib.Context(0))
-    for gender in ("A", "F"):
-        fast = predict_control.normalize_batch(args, samples, ref, gender, eng)
-        os.environ["WCX_NORM_WARP"] = "1"
-        try:
-            slow = predict_control.normalize_batch(args, samples, ref, gender, eng)
-        finally:
-            del os.environ["WCX_NORM_WARP"]
-        assert np.array_equal(fast[0], slow[0], equal_nan=True)          # r = x / median
-        assert np.array_equal(fast[3], slow[3])                          # reference counts
-        np.testing.assert_allclose(fast[1], slow[1], rtol=1e-11, atol=1e-13, equal_nan=True)  # z
-        np.testing.assert_allclose(fast[4], slow[4], rtol=1e-12, equal_nan=True)
-        np.testing.assert_allclose(fast[5], slow[5], rtol=1e-9, atol=1e-12, equal_nan=True)
-    eng.ctx.close()

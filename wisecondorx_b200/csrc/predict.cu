@@ -13,7 +13,6 @@
 #include <cstdlib>
 
 #include "select.cuh"
-#include "packed_select.cuh"
 #include "wcx_common.cuh"
 #include "predict.cuh"
 
@@ -177,6 +176,9 @@ gather_list_kernel(const int32_t* __restrict__ idx, const double* __restrict__ d
 }
 
 // one warp per target bin i in [ct, n); loops over the B samples so the gather list is read once per batch.
+// (A thread-per-(bin, sample) variant on packed 15-bit codes -- the design of the null-ratio kernel -- was built and
+// measured in round 2: 3.0 ms for the three passes of one sample against 1.1 ms here, 158 ms against 111 ms at batch 96;
+// with one thread per bin the gather lists and the two value passes are uncoalesced.  Not kept.)
 // R = register slots per lane (R / 4 quads of 4 consecutive list entries, 16-byte loads when k % 4 == 0).
 // The kept values are >= 0, so their order-preserving key is the bit pattern with the sign bit set: the value is
 // recovered from the key and needs no registers of its own.
@@ -246,160 +248,6 @@ normalize_pass_kernel(const double* __restrict__ test_data, const double* __rest
       n_out[(int64_t)b * nout + (i - ct)] = (double)cnt;
       if (copy_out) copy_out[(int64_t)b * n + i] = (fabs(z) >= Z_MASK) ? -1.0 : cp[i];
     }
-  }
-}
-
-// ---- _normalize_once, one THREAD per (target bin, sample) ---------------------------------------------------------
-// The warp-per-bin kernel above is bound by the instruction count of the exact 64-bit selection (~1 270 warp
-// instructions per bin and sample: 0.37 ms per pass at 15 kb, and no gain from batching).  Here a thread owns one
-// (bin, sample): it walks the bin's gather list twice --
-//   pass A: count, sum, minimum and maximum of the kept reference values;
-//   pass B: sum of squared deviations from the mean, and a 15-bit CODE per value (linear map of [min, max], monotone),
-//           packed two per register (packed_select.cuh)
-// -- selects the middle code(s) by a 15-step bisection with packed-half compares, and fetches the one or two middle
-// VALUES in float64 through the positions of the selected codes.  If a selected code is shared by two values (a few
-// per cent of the medians) the whole warp resolves that (bin, sample) with the exact selection of select.cuh, so the
-// median is the exact one in every case; mean and sd are per-thread sequential sums (the same for every batch size).
-// The sample vectors are kept BIN-major ([n][B]): the 32 lanes of a warp are consecutive samples of one bin (B >= 32)
-// and gather 256 contiguous bytes per reference bin, or consecutive bins of one sample (B = 1).
-__global__ void __launch_bounds__(256)
-transpose_copy_kernel(const double* __restrict__ x, int B, int64_t n, double* __restrict__ a, double* __restrict__ b) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n * B) return;
-  const int64_t i = p / B;
-  const int s = (int)(p - i * B);
-  const double v = x[(int64_t)s * n + i];
-  a[p] = v;
-  b[p] = v;
-}
-
-template <int NP, int R>
-__global__ void __launch_bounds__(128, NP > 160 ? 2 : (NP > 64 ? 3 : 4))
-normalize_fast_kernel(const double* __restrict__ test_data, const double* __restrict__ cin, double* __restrict__ cout, int B,
-                      int64_t n, const int32_t* __restrict__ gl, int k, int64_t ct, int write_results,
-                      double* __restrict__ z_out, double* __restrict__ r_out, double* __restrict__ n_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nout = n - ct;
-  const int64_t total = nout * B;
-  const int64_t p0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = p0 < total;
-  const int64_t p = active ? p0 : total - 1;  // whole warps stay alive for the cooperative exact path
-  const int64_t il = p / B;                   // bin - ct
-  const int b = (int)(p - il * B);
-  const int64_t i = ct + il;
-  const int32_t* __restrict__ grow = gl + il * k;
-  const double* __restrict__ cb = cin + b;    // value of bin g for this sample: cb[g * B]
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  // ---- pass A
-  int cnt = 0;
-  double sum = 0.0;
-  float fmin = __int_as_float(0x7f800000), fmax = __int_as_float(0xff800000);
-#pragma unroll 4
-  for (int j = 0; j < k; j++) {
-    const int32_t g = __ldg(grow + j);
-    if (g >= 0) {
-      const double v = __ldg(cb + (int64_t)g * B);
-      if (v >= 0.0) {  // NaN and negatives (masked bins) dropped
-        cnt++;
-        sum += v;
-        const float f = (float)v;
-        fmin = fminf(fmin, f);
-        fmax = fmaxf(fmax, f);
-      }
-    }
-  }
-  double mean = nan, sd = nan, med = nan;
-  bool need_exact = false;
-  if (cnt > 0) {
-    mean = sum / (double)cnt;
-    // ---- pass B: squared deviations + codes.  code = LO + trunc((f - fmin) * scale), f = (float)v: monotone in v
-    const float scale = fmax > fmin ? (float)(PS_CODE_HI - PS_CODE_LO) / (fmax - fmin) : 0.f;
-    double ss = 0.0;
-    uint32_t k2[NP];
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-      uint32_t c0 = PS_CODE_PAD, c1 = PS_CODE_PAD;
-      if (2 * j < k) {
-        const int32_t g = __ldg(grow + 2 * j);
-        if (g >= 0) {
-          const double v = __ldg(cb + (int64_t)g * B);
-          if (v >= 0.0) {
-            const double t = v - mean;
-            ss += t * t;
-            c0 = PS_CODE_LO + min((uint32_t)(((float)v - fmin) * scale), PS_CODE_HI - PS_CODE_LO);
-          }
-        }
-      }
-      if (2 * j + 1 < k) {
-        const int32_t g = __ldg(grow + 2 * j + 1);
-        if (g >= 0) {
-          const double v = __ldg(cb + (int64_t)g * B);
-          if (v >= 0.0) {
-            const double t = v - mean;
-            ss += t * t;
-            c1 = PS_CODE_LO + min((uint32_t)(((float)v - fmin) * scale), PS_CODE_HI - PS_CODE_LO);
-          }
-        }
-      }
-      k2[j] = c0 | (c1 << 16);
-    }
-    sd = sqrt(ss / (double)cnt);
-    // ---- the middle code(s) of the cnt kept values (padding sorts last)
-    const int t = cnt >> 1;
-    int below = 0;
-    const uint32_t T = ps_select<NP>(k2, t, below);
-    int eq_hi, j_hi, eq_lo = 1, j_lo = 0;
-    ps_find<NP>(k2, T, eq_hi, j_hi);
-    bool ok = eq_hi == 1;
-    if (ok && !(cnt & 1)) {
-      ok = below == t;
-      if (ok) {
-        ps_find<NP>(k2, ps_max_below<NP>(k2, T), eq_lo, j_lo);
-        ok = eq_lo == 1;
-      }
-    }
-    if (ok) {
-      const double v_hi = __ldg(cb + (int64_t)__ldg(grow + j_hi) * B);
-      med = (cnt & 1) ? v_hi : (__ldg(cb + (int64_t)__ldg(grow + j_lo) * B) + v_hi) / 2.0;
-    } else {
-      need_exact = true;
-    }
-  }
-  // ---- exact selection for the flagged (bin, sample)s, one at a time by the whole warp
-  uint32_t pending = __ballot_sync(0xffffffffu, need_exact);
-  while (pending) {
-    const int src = __ffs(pending) - 1;
-    pending &= pending - 1;
-    const int64_t sil = __shfl_sync(0xffffffffu, il, src);
-    const int sb = __shfl_sync(0xffffffffu, b, src);
-    const int32_t* __restrict__ gr = gl + sil * k;
-    uint64_t key[R];
-    int c = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int t = r * 32 + lane;
-      double v = -1.0;
-      if (t < k) {
-        const int32_t g = __ldg(gr + t);
-        if (g >= 0) v = __ldg(cin + (int64_t)g * B + sb);
-      }
-      const bool keep = v >= 0.0;
-      key[r] = keep ? ((uint64_t)__double_as_longlong(v) | 0x8000000000000000ull) : ~0ull;
-      c += keep ? 1 : 0;
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    const double mm = warp_median<R>(key, c);
-    if (lane == src) med = mm;
-  }
-  if (active) {
-    const double x = test_data[(int64_t)b * n + i];
-    const double z = (x - mean) / sd;
-    if (write_results) {
-      z_out[(int64_t)b * nout + il] = z;
-      r_out[(int64_t)b * nout + il] = x / med;
-      n_out[(int64_t)b * nout + il] = (double)cnt;
-    }
-    if (cout) cout[i * B + b] = (fabs(z) >= Z_MASK) ? -1.0 : cin[i * B + b];
   }
 }
 
@@ -712,29 +560,6 @@ int launch_normalize_repeat(const double* x, double* copy_a, double* copy_b, int
   if (k > PR_MAXK) { set_error("normalize: ref_size > 512 unsupported"); return 1; }
   const int64_t nout = n - ct;
   if (nout <= 0 || B <= 0) return 0;
-  const bool warp_per_bin = std::getenv("WCX_NORM_WARP") != nullptr || k > 400 || k < 2;  // cross-check (tests) / large ref_size
-  if (!warp_per_bin) {
-    // thread per (bin, sample); sample vectors bin-major
-    const int64_t tot = n * (int64_t)B;
-    transpose_copy_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, B, n, copy_a, copy_b);
-    const unsigned grid = (unsigned)((nout * B + 127) / 128);
-    double* in = copy_a;
-    double* out = copy_b;
-    for (int pass = 0; pass < 3; pass++) {
-      double* o = pass < 2 ? out : nullptr;
-      const int wr = pass == 2 ? 1 : 0;  // the reference returns the results of the third pass (predict_tools.py:99-108)
-#define WCX_NF_LAUNCH(NP, R) normalize_fast_kernel<NP, R><<<grid, 128, 0, st>>>(x, in, o, B, n, gl, k, ct, wr, z, r, nref)
-      if (k <= 64) WCX_NF_LAUNCH(32, 2);
-      else if (k <= 128) WCX_NF_LAUNCH(64, 4);
-      else if (k <= 200) WCX_NF_LAUNCH(100, 7);
-      else if (k <= 300) WCX_NF_LAUNCH(150, 10);
-      else WCX_NF_LAUNCH(200, 13);
-#undef WCX_NF_LAUNCH
-      double* t = in; in = out; out = t;
-    }
-    WCX_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
   WCX_CUDA_OK(cudaMemcpyAsync(copy_a, x, sizeof(double) * (size_t)B * n, cudaMemcpyDeviceToDevice, st));
   // the passes rewrite the target bins [ct, n) only: the second buffer needs the prefix [0, ct) of every sample once
   if (ct > 0)
