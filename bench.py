@@ -49,6 +49,13 @@ def n_pairs(per, row_begin=0, row_end=None):
     return total
 
 
+def workload_config(name, n, s, pairs_total):
+    """The `config` object: the workload only, identical in both arms (implementation notes go under `notes`)."""
+    return {"workload": WORKLOADS[name][2], "refsize": REFSIZE, "null_samples": min(int(s), NULL_M), "bins": int(n),
+            "samples": int(s), "pairs_per_step": int(pairs_total), "l2": "inputs larger than L2, no flush" if n * s * 8 > 200e6
+            else "inputs fit in L2 (parity-size workload)"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -341,7 +348,8 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_pairs / v * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][2], "note": "ms_per_step extrapolated from the bounded sample"},
+        "config": workload_config(args.workload, x.shape[0], x.shape[1], total_pairs),
+        "notes": {"ms_per_step": "extrapolated from the bounded sample"},
         "cpu_baseline": {"value": v, "unit": "bin-pair dist/s", "cores": vals[-1]["cores"], "kind": "port",
                          "sample": vals[-1]["sample"]},
         "e2e": {"value": v, "unit": "bin-pair dist/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -532,16 +540,15 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][2], "refsize": k, "null_samples": m,
-                   "bins": int(n), "samples": int(s), "pairs_per_step": int(pairs_total),
-                   "arithmetic": "results are float64, bit-exact with the reference's NumPy order (exact re-rank); the sweep that "
-                                 "nominates candidates runs on " + ("f16" if f16 else "tf32") + " tensor-core operands with fp32 accumulation",
-                   "l2": ("inputs (X fp64 %.0f MB + operands) larger than the 126 MB L2, no flush needed" % (x.nbytes / 1e6)) if x.nbytes > 200e6
-                         else "inputs fit in L2 and are not flushed: parity-size workload, not the bench line",
-                   "parallelism": f"target-bin parts x{world}",
-                   "null_ratios": "separate call after the top-k" if args.unfused else
-                                  "row blocks on a side stream next to the re-rank of the following block "
-                                  "(stages_ms.null_ratios = what they add after the last re-rank block)"},
+        "config": workload_config(args.workload, n, s, pairs_total),
+        "notes": {"arithmetic": "results are float64, bit-exact with the reference's NumPy order (exact re-rank); the sweep that "
+                                "nominates candidates runs on " + ("f16" if f16 else "tf32") + " tensor-core operands with fp32 accumulation",
+                  "l2": ("inputs (X fp64 %.0f MB + operands) larger than the 126 MB L2, no flush needed" % (x.nbytes / 1e6)) if x.nbytes > 200e6
+                        else "inputs fit in L2 and are not flushed: parity-size workload, not the bench line",
+                  "parallelism": f"target-bin parts x{world}",
+                  "null_ratios": "separate call after the top-k" if args.unfused else
+                                 "row blocks on a side stream next to the re-rank of the following block "
+                                 "(stages_ms.null_ratios = what they add after the last re-rank block)"},
         "e2e": {"value": e2e_value, "unit": "bin-pair dist/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "equals_resident_result": e2e_same, "path": e2e_path,
                 "phases_ms_cumulative_rank0": {k: round(v, 2) for k, v in e2e_phases.items()} if e2e_phases else None},
