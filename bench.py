@@ -313,7 +313,7 @@ def predict_sharded_extras(eng, x, per, cum, idx_full, dist_full, device, rank, 
             samples[i] = {str(k + 1): c[offs[k]:offs[k + 1]] for k in range(22)}
     args = types.SimpleNamespace(maskrepeats=5, minrefbins=150, alpha=1e-4, seed=1)
     pe = predict_tools.PredictEngine(device, eng.ctx)
-    parallel.predict_batch_sharded(args, samples[a:a + 1] * world, ref, "A", pe)  # warm-up: reference arrays to the device
+    parallel.predict_batch_sharded(args, samples, ref, "A", pe)  # warm-up: reference arrays to the device, staging buffers allocated
     dist.barrier()
     t0 = time.perf_counter()
     (_, _), _, summary = parallel.predict_batch_sharded(args, samples, ref, "A", pe)

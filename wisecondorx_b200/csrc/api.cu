@@ -457,9 +457,10 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     //   A  the units that fill whole rounds of the grid -- the main launch;
     //   B  the units of the last, partial round -- a second launch on a high-priority stream that needs only 2 L of the
     //      SMs and runs WHILE region A is already in the re-rank (tensor-bound next to a gather-latency-bound kernel).
-    // (Splitting region B into candidate-column ranges instead -- WCX_TAIL_SPLIT=s, 2 s lists per row -- was measured and
-    // does not pay: on 1/s of the columns a list's threshold stays s times looser, the epilogue appends s times more
-    // entries and the first tiles of every sub-unit append everything; the tail got no shorter on 8 GPUs.)
+    // (Splitting region B into s candidate-column ranges instead, 2 s lists per row, was measured and does not pay: on 1/s of
+    // the columns a list's threshold stays s times looser, the epilogue appends s times more entries and the first tiles of
+    // every sub-unit append everything; the tail got no shorter on 8 GPUs.  The Region / nlists machinery below still
+    // supports it.)
     std::vector<WorkItem> items;
     const int lps = kernel == WCX_KERNEL_SIMT ? 1 : 2;  // the tcgen05 kernel keeps one list per epilogue group
     build_items(c, rb, re, tile_n, 1, lps, items);
@@ -470,13 +471,11 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
     if (pair) {
       const int n_units = ((int)items.size() + 1) / 2;
       const int P = std::max(1, dev_sms / 2);  // CTA pairs of the persistent grid
-      const char* split_env = std::getenv("WCX_TAIL_SPLIT");  // experiment / tests: column split factor of region B
-      static const bool no_overlap = std::getenv("WCX_TAIL_SERIAL") != nullptr;
+      static const bool no_overlap = std::getenv("WCX_TAIL_SERIAL") != nullptr;  // measurement switch: one launch, no overlap
       const int full_units = (n_units / P) * P;
       const int L = full_units > 0 ? n_units - full_units : 0;  // fewer units than CTA pairs: one launch, nothing to overlap
-      int sB = 1;
-      if (L > 0 && split_env) { const int f = std::atoi(split_env); if (f >= 1 && f <= 8 && (f & (f - 1)) == 0 && nct / f >= 1) sB = f; }
-      tail_overlap = L > 0 && sB == 1 && !no_overlap;
+      const int sB = 1;
+      tail_overlap = L > 0 && !no_overlap;
       std::vector<WorkItem> base;
       base.swap(items);
       const size_t nA = L > 0 ? std::min(base.size(), (size_t)2 * full_units) : base.size();
