@@ -86,3 +86,28 @@ def test_tool_test_matches_reference(gold, tmp_path, monkeypatch, si):
     _cmp_table(open(outid + "_aberrations.bed").read(), str(gtool[f"t{si}_aberrations.bed"]), 1e-6)
     _cmp_table(open(outid + "_statistics.txt").read(), str(gtool[f"t{si}_statistics.txt"]), 1e-5, atol=2e-5)
     assert str(meta[0]) in ("F", "M")
+
+
+def test_predict_batch_equals_single_samples(gold):
+    """predict_control.predict_batch (one normalize call per reference set, ONE CBS call and one z-score call per
+    gender for the whole batch) returns for every sample exactly what it returns for that sample alone: segments,
+    segment z-scores and the per-bin results."""
+    import types
+    from wisecondorx_b200 import predict_control, predict_tools
+    gpred, _ = gold
+    ref = {k[5:]: gpred[k] for k in gpred.files if k.startswith("ref__")}
+    ref = {k: (v.item() if v.shape == () else v) for k, v in ref.items()}
+    binsize = int(ref["binsize"])
+    samples = [{str(c): gpred[f"t{si}_sample_{c}"] for c in range(1, 25)} for si in (0, 1, 0, 1, 1)]
+    args = types.SimpleNamespace(maskrepeats=5, minrefbins=10, alpha=1e-4, seed=3, gender=None, blacklist=None, zscore=5, beta=None)
+    eng = predict_tools.PredictEngine(0)
+    batch = predict_control.predict_batch(args, samples, [binsize] * len(samples), ref, eng)
+    assert len(batch) == len(samples)
+    for s, (rem, res) in zip(samples, batch):
+        rem1, res1 = predict_control.predict_batch(args, [s], [binsize], ref, eng)[0]
+        assert rem1["ref_gender"] == rem["ref_gender"] and rem1["gender"] == rem["gender"]
+        assert res1["results_c"] == res["results_c"]
+        for key in ("results_r", "results_z", "results_w"):
+            for a, b in zip(res1[key], res[key]):
+                assert np.array_equal(a, b)
+    assert {rem["ref_gender"] for rem, _ in batch} == {"F", "M"}

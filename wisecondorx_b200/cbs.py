@@ -145,10 +145,19 @@ def exec_cbs_batch(rem_inputs, results_list, engine: predict_tools.PredictEngine
                               float(args.alpha), float(rem_inputs[0]["binsize"]), getattr(args, "seed", None), nperm,
                               engine.ctx if engine else None)
     out = [None] * len(segs)
-    # samples of one reference gender share their null-ratio array, which stays on the device between calls: walk the
-    # batch gender by gender so that it is uploaded once per gender, not once per sample
-    for j in sorted(range(len(segs)), key=lambda i: str(rem_inputs[i]["ref_gender"])):
-        results_c = segs[j]
-        z = predict_tools.get_z_score(results_c, results_list[j], engine)
-        out[j] = [results_c[i][:3] + [z[i]] + [results_c[i][3]] for i in range(len(results_c))]
+    # samples of one reference gender share their null-ratio array (resident on the device): one z-score call per gender,
+    # in chunks that stay below the kernel's segment limit
+    groups = {}
+    for j in range(len(segs)):
+        groups.setdefault(id(results_list[j]["results_nr"]["dense"]), []).append(j)
+    for js in groups.values():
+        chunk, nseg = [], 0
+        for j in js + [None]:
+            if j is None or nseg + len(segs[j]) > 60000:
+                for jj, z in zip(chunk, predict_tools.get_z_score_batch([(segs[i], results_list[i]) for i in chunk], engine)):
+                    out[jj] = [segs[jj][i][:3] + [z[i]] + [segs[jj][i][3]] for i in range(len(segs[jj]))]
+                chunk, nseg = [], 0
+            if j is not None:
+                chunk.append(j)
+                nseg += len(segs[j])
     return out

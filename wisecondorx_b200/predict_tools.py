@@ -175,6 +175,36 @@ def get_optimal_cutoff(ref_file, repeats, engine: PredictEngine | None = None):
     return (engine or default_engine()).get_optimal_cutoff(ref_file, repeats)
 
 
+def get_z_score_batch(items, engine: PredictEngine | None = None):
+    """get_z_score for several samples that share ONE null-ratio array (same reference gender): items =
+    [(results_c, results), ...] with results["results_nr"] = {"dense": nr, "inflate": ...} (the array form).  The bin
+    axes of the samples are concatenated and the segment offsets shifted, so one device call serves the batch.
+    Returns a list of per-sample lists like get_z_score."""
+    if not items:
+        return []
+    nr = items[0][1]["results_nr"]["dense"]
+    rs, ws, infl, segs, segr, counts = [], [], [], [], [], []
+    base = 0
+    for results_c, results in items:
+        assert results["results_nr"]["dense"] is nr
+        r = np.concatenate([np.asarray(x, dtype=np.float64) for x in results["results_r"]])
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in results["results_r"]])]).astype(np.int64)
+        rs.append(r)
+        ws.append(np.concatenate([np.asarray(x, dtype=np.float64) for x in results["results_w"]]))
+        infl.append(results["results_nr"]["inflate"])
+        segs.append(np.array([[base + offs[sg[0]] + sg[1], base + offs[sg[0]] + sg[2]] for sg in results_c], dtype=np.int64).reshape(-1, 2))
+        segr.append(np.array([sg[3] for sg in results_c], dtype=np.float64))
+        counts.append(len(results_c))
+        base += len(r)
+    z = (engine or default_engine()).segment_zscore(nr, np.concatenate(infl), np.concatenate(rs), np.concatenate(ws),
+                                                     np.concatenate(segs), np.concatenate(segr))
+    out, o = [], 0
+    for c in counts:
+        out.append([("nan" if np.isnan(v) else float(v)) for v in z[o:o + c]])
+        o += c
+    return out
+
+
 def get_z_score(results_c, results, engine: PredictEngine | None = None):
     """Drop-in for overall_tools.get_z_score (reference overall_tools.py:88-119): takes the
     reference's per-chromosome list structures and returns a list of floats / the string "nan"."""
