@@ -416,20 +416,14 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
   std::vector<int32_t> fail_list;
   // null plan: gather the chosen sample columns first (needs only X), decide whether the re-rank kernel can fuse
   double* d_null = nullptr;
-  bool codes_deferred = false;
   c->stage_ms[3] = 0.0;
   if (np && np->m > 0) {
     for (int i = 0; i < np->m; i++)
       if (np->sample_ids[i] < 0 || np->sample_ids[i] >= c->s) { set_error("wcx_newref_reference: sample id out of range"); return 1; }
     if (c->xt.ensure(sizeof(double) * (size_t)null_ratio_staging_doubles(c->n, np->m)) || c->ids_dev.ensure(sizeof(int32_t) * np->m)) return 1;
     WCX_CUDA_OK(cudaMemcpyAsync(c->ids_dev.p, np->sample_ids, sizeof(int32_t) * np->m, cudaMemcpyHostToDevice, st));
-    // the column keys / codes of the null-ratio path need only X: with the tensor-core sweep they are built on the side
-    // stream while the re-rank runs (below); the other paths build them here
-    codes_deferred = kernel != WCX_KERNEL_EXACT && kernel != WCX_KERNEL_SIMT;
-    if (!codes_deferred) {
-      if (launch_transpose_cols(c->d_x, c->n, c->s, c->ids_dev.as<int32_t>(), np->m, c->xt.as<double>(), st)) return 1;
-      c->launches += 6;
-    }
+    if (launch_transpose_cols(c->d_x, c->n, c->s, c->ids_dev.as<int32_t>(), np->m, c->xt.as<double>(), st)) return 1;
+    c->launches += 1;
     d_null = np->out;
     if (!out_on_device) {
       if (c->nr_dev.ensure(sizeof(double) * (size_t)rows * np->m)) return 1;
@@ -562,13 +556,6 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       // block (copy stream) overlaps the kernels of the next one.
       static const bool serial_nulls = std::getenv("WCX_SERIAL_NULLS") != nullptr;
       const bool side = d_null && !serial_nulls;   // null ratios on the side stream
-      if (d_null && codes_deferred) {
-        // (ids_dev was uploaded on st before ev[0]; the side stream starts once the main sweep launch is done)
-        cudaStream_t cs = side ? c->null_stream : st;
-        if (side) WCX_CUDA_OK(cudaStreamWaitEvent(cs, c->ev[1], 0));
-        if (launch_transpose_cols(c->d_x, c->n, c->s, c->ids_dev.as<int32_t>(), np->m, c->xt.as<double>(), cs)) return 1;
-        c->launches += 6;
-      }
       int bq = 0;       // block counter over both regions (events)
       int last_blk = -1;
       for (const Region& rg : {regA, regB}) {
