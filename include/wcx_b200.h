@@ -116,7 +116,8 @@ int wcx_newref_stage_ms(wcx_ctx* ctx, double* out8);
  *
  * normalize_and_mask (newref_tools.py:110-129): counts int32 [bins_total, S] = per-sample read counts
  * stacked per chromosome (zero padded), mask_pos int32 [n] = np.flatnonzero(mask); out float64 [n, S] =
- * counts[mask_pos] / column totals.  Bit-exact (integer totals). */
+ * counts[mask_pos] / column totals.  Bit-exact (integer totals).  counts == NULL reuses the count matrix uploaded by the
+ * previous call (same bins_total and S): the redo after the PCA-distance filter changes only the mask. */
 int wcx_newref_normalize_and_mask(wcx_ctx* ctx, const int32_t* counts, int64_t bins_total, int32_t s,
                                   const int32_t* mask_pos, int64_t n, double* out, int32_t out_on_device);
 /* train_pca (newref_tools.py:138-147), exact-PCA formulation in three steps:

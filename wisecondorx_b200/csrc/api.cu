@@ -107,6 +107,8 @@ struct wcx_ctx {
   DevBuf q_counts, q_pos, q_colsum, q_x, q_mean, q_partial, q_gram, q_u, q_sigma, q_comps, q_corr, q_med, q_d, q_work;
   int64_t q_n = 0;
   int32_t q_s = 0;
+  int64_t q_counts_rows = -1;  // count matrix resident for wcx_newref_normalize_and_mask(counts = NULL)
+  int32_t q_counts_s = 0;
   const double* q_xptr = nullptr;
   double prep_ms[4] = {};
   CbsStats cbs_stats = {};
@@ -1107,14 +1109,22 @@ int wcx_cbs_stats(wcx_ctx* c, int64_t* out6) {
 // ================================================================================================
 int wcx_newref_normalize_and_mask(wcx_ctx* c, const int32_t* counts, int64_t bins_total, int32_t s, const int32_t* mask_pos,
                                   int64_t n, double* out, int32_t out_on_device) {
-  if (!c || !counts || !mask_pos || (!out && !out_on_device) || bins_total <= 0 || s <= 0 || n < 0) { set_error("wcx_newref_normalize_and_mask: bad argument"); return 1; }
+  if (!c || !mask_pos || (!out && !out_on_device) || bins_total <= 0 || s <= 0 || n < 0) { set_error("wcx_newref_normalize_and_mask: bad argument"); return 1; }
+  if (!counts && (c->q_counts_rows != bins_total || c->q_counts_s != s || !c->q_counts.p)) {
+    set_error("wcx_newref_normalize_and_mask: counts == NULL but no count matrix of that shape is resident");
+    return 1;
+  }
   for (int64_t i = 0; i < n; i++)
     if (mask_pos[i] < 0 || mask_pos[i] >= bins_total) { set_error("wcx_newref_normalize_and_mask: mask position out of range"); return 1; }
   WCX_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  if (h2d(c->q_counts, counts, sizeof(int32_t) * (size_t)bins_total * s, st) || h2d(c->q_pos, mask_pos, sizeof(int32_t) * (size_t)n, st) ||
-      c->q_colsum.ensure(sizeof(unsigned long long) * s))
-    return 1;
+  if (counts) {
+    c->q_counts_rows = -1;
+    if (h2d(c->q_counts, counts, sizeof(int32_t) * (size_t)bins_total * s, st)) return 1;
+    c->q_counts_rows = bins_total;
+    c->q_counts_s = s;
+  }
+  if (h2d(c->q_pos, mask_pos, sizeof(int32_t) * (size_t)n, st) || c->q_colsum.ensure(sizeof(unsigned long long) * s)) return 1;
   double* d_out = out;
   if (!out_on_device || !out) {
     // out == NULL with out_on_device: the matrix stays in the context (input of wcx_pca_gram(x = NULL))

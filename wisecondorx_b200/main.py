@@ -17,7 +17,7 @@ import numpy as np
 
 import time
 
-from . import cbs, newref_control, npz_io, predict_control, predict_output, predict_tools, ref_qc
+from . import cbs, newref_control, newref_tools, npz_io, predict_control, predict_output, predict_tools, ref_qc
 from .overall_tools import gender_correct, scale_sample
 
 
@@ -49,19 +49,30 @@ def train_gender_model(args, samples):
     return genders.tolist(), cut_off
 
 
+def _row_chunks(total, nthreads):
+    step = max(4096, -(-total // (4 * nthreads)))
+    return [(a, min(total, a + step)) for a in range(0, total, step)]
+
+
 def get_mask(samples):
-    """Bins with more than 5 % of the median (non-zero) summed normalised coverage (reference :77-102)."""
+    """Bins with more than 5 % of the median (non-zero) summed normalised coverage (reference newref_tools.py:77-102).
+    Same arithmetic as the reference, element for element -- exact column totals (integers), one division per element,
+    NumPy's pairwise sum along each contiguous row -- but the [bins, samples] float matrix (0.8 GB at 15 kb / 500
+    samples) is never materialised: row chunks go through a thread pool (NumPy releases the GIL in these loops)."""
+    from concurrent.futures import ThreadPoolExecutor
     bins_per_chr = [max(len(s[str(c)]) for s in samples) for c in range(1, 25)]
     total = int(sum(bins_per_chr))
-    all_data = np.zeros((total, len(samples)), dtype=float)
-    off = 0
-    for c, nb in zip(range(1, 25), bins_per_chr):
-        for i, s in enumerate(samples):
-            a = np.asarray(s[str(c)])
-            all_data[off:off + len(a), i] = a
-        off += nb
-    all_data = all_data / np.sum(all_data, 0)
-    sum_per_bin = np.sum(all_data, 1)
+    ns = len(samples)
+    nthreads = max(1, min(16, len(os.sched_getaffinity(0))))
+    counts = newref_tools.stack_counts(samples, range(1, 25))  # int32 [total, S], zero padded
+    col_sum = np.sum(counts, 0, dtype=np.int64).astype(float)   # exact, like the float sum of integer counts
+
+    def rows(ab):
+        a, b = ab
+        return np.sum(counts[a:b].astype(float) / col_sum, 1)
+
+    with ThreadPoolExecutor(nthreads) as pool:
+        sum_per_bin = np.concatenate(list(pool.map(rows, _row_chunks(total, nthreads)))) if total else np.zeros(0)
     median_cov = np.median(sum_per_bin[sum_per_bin > 0])
     return sum_per_bin > (0.05 * median_cov), bins_per_chr
 

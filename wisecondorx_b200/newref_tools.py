@@ -210,16 +210,37 @@ def _finish_components(comps, pcacomp):
 
 def stack_counts(samples, chrs):
     """int32 [bins_total, S]: per-chromosome read counts of every sample, zero padded to the longest
-    sample (host half of normalize_and_mask, newref_tools.py:114-122)."""
+    sample (host half of normalize_and_mask, newref_tools.py:114-122).  Samples are written by a few threads (every
+    sample is one strided column of the result)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    chrs = list(chrs)
     lens = [max(len(s[str(c)]) for s in samples) for c in chrs]
-    total = int(sum(lens))
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    total = int(offs[-1])
     out = np.zeros((total, len(samples)), dtype=np.int32)
-    off = 0
-    for c, ln in zip(chrs, lens):
-        for i, s in enumerate(samples):
-            a = np.asarray(s[str(c)])
-            out[off:off + len(a), i] = a
-        off += ln
+
+    def fill(block):
+        # a block of adjacent samples: contiguous row pieces of the result (better than one strided column at a time)
+        a, b = block
+        tmp = np.zeros((total, b - a), dtype=np.int32)
+        for i in range(a, b):
+            s = samples[i]
+            for c, o in zip(chrs, offs[:-1]):
+                v = np.asarray(s[str(c)])
+                tmp[o:o + len(v), i - a] = v
+        out[:, a:b] = tmp
+
+    ns = len(samples)
+    nthreads = max(1, min(8, len(os.sched_getaffinity(0)), ns // 16 or 1))
+    step = max(8, -(-ns // (2 * nthreads)))
+    blocks = [(a, min(ns, a + step)) for a in range(0, ns, step)]
+    if nthreads == 1:
+        for blk in blocks:
+            fill(blk)
+    else:
+        with ThreadPoolExecutor(nthreads) as pool:
+            list(pool.map(fill, blocks))
     return out
 
 
@@ -230,6 +251,7 @@ def normalize_and_mask(samples, chrs, mask, device: int = 0):
     pos = np.ascontiguousarray(np.flatnonzero(np.asarray(mask, dtype=bool)[: counts.shape[0]]), dtype=np.int32)
     out = np.empty((len(pos), counts.shape[1]), dtype=np.float64)
     ctx = _lib.default_context(device)
+    ctx.__dict__["_counts_obj"] = None  # this call replaces whatever count matrix DevicePrep left on the device
     _lib.check(_lib.load().wcx_newref_normalize_and_mask(ctx.handle, _ptr(counts), counts.shape[0], counts.shape[1], _ptr(pos),
                                                          len(pos), _ptr(out), 0))
     return out
@@ -289,8 +311,12 @@ class DevicePrep:
         """counts: int32 [bins_total, S] (stack_counts); mask: bool [bins_total].  Leaves the [N, S] matrix on the device."""
         counts = np.ascontiguousarray(counts)
         pos = np.ascontiguousarray(np.flatnonzero(np.asarray(mask, dtype=bool)[: counts.shape[0]]), dtype=np.int32)
-        _lib.check(_lib.load().wcx_newref_normalize_and_mask(self.ctx.handle, _ptr(counts), counts.shape[0], counts.shape[1], _ptr(pos),
-                                                             len(pos), None, 1))
+        # the same matrix again (the redo after the PCA-distance filter): it is still on the device
+        resident = self.ctx.__dict__.get("_counts_obj") is counts  # residency is a property of the context
+        self.ctx.__dict__["_counts_obj"] = None
+        _lib.check(_lib.load().wcx_newref_normalize_and_mask(self.ctx.handle, None if resident else _ptr(counts), counts.shape[0],
+                                                             counts.shape[1], _ptr(pos), len(pos), None, 1))
+        self.ctx.__dict__["_counts_obj"] = counts
         self.shape = (len(pos), counts.shape[1])
         return self.shape
 
