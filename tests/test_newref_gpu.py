@@ -218,6 +218,14 @@ def test_bad_arguments_raise(eng):
         eng.topk(0, 10, 0)
     with pytest.raises(_lib.WcxError):
         eng.null_ratios(0, 10, 10, [99])
+    n = x.shape[0]
+    for bad in (n, n + 7, -n - 1):  # caller-supplied positions follow Python index semantics: [-n, n)
+        idx = np.zeros((10, 10), dtype=np.int32)
+        idx[3, 4] = bad
+        with pytest.raises(_lib.WcxError):
+            eng.null_ratios(0, 10, 10, [0, 1], idx=idx)
+    idx = np.full((10, 10), -n, dtype=np.int32)  # -n is the first bin
+    assert np.isfinite(eng.null_ratios(0, 10, 10, [0, 1], idx=idx)).all()
 
 
 @pytest.mark.parametrize("kernel", ["tc2h", "tch"])

@@ -747,6 +747,14 @@ int wcx_newref_null_ratios(wcx_ctx* c, const int32_t* idx, int32_t idx_on_device
     if (c->last_rb != rb || c->last_re != re || c->last_k != k) { set_error("wcx_newref_null_ratios: no matching device-resident indexes"); return 1; }
     d_idx = c->idx_dev.as<int32_t>();
   } else if (idx_on_device) {
+    // caller-supplied device positions are checked on the device before anything gathers through them
+    int32_t bad = 0;
+    if (c->diag.ensure(sizeof(int32_t) * 8)) return 1;
+    WCX_CUDA_OK(cudaMemsetAsync(c->diag.p, 0, sizeof(int32_t), st));
+    if (launch_validate_positions(idx, rows * (int64_t)k, c->n, c->diag.as<int32_t>(), st)) return 1;
+    WCX_CUDA_OK(cudaMemcpyAsync(&bad, c->diag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    WCX_CUDA_OK(cudaStreamSynchronize(st));
+    if (bad) { set_error("wcx_newref_null_ratios: index out of range [-n, n)"); return 1; }
     d_idx = idx;
   } else {
     // caller-supplied positions: Python semantics, -n <= v < n (negative wraps); anything else would gather out of bounds

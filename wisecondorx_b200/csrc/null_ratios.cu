@@ -327,6 +327,26 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
 }
 }  // namespace
 
+namespace {
+__global__ void validate_positions_kernel(const int32_t* __restrict__ idx, int64_t count, int32_t n, int32_t* __restrict__ bad) {
+  int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = idx[i];
+    local |= (v < -n || v >= n) ? 1 : 0;
+  }
+  if (__any_sync(0xffffffffu, local) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+}  // namespace
+
+// bad[0] |= 1 if any position of a caller-supplied DEVICE index array lies outside [-n, n) (Python index semantics)
+int launch_validate_positions(const int32_t* idx, int64_t count, int64_t n, int32_t* bad, cudaStream_t st) {
+  if (count <= 0) return 0;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((count + 255) / 256, 1184));
+  validate_positions_kernel<<<grid, 256, 0, st>>>(idx, count, (int32_t)n, bad);
+  WCX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m, double* xt,
                           cudaStream_t st) {
   if (n == 0 || m == 0) return 0;

@@ -92,6 +92,7 @@ int launch_exact_rows(const double* x, int64_t n, int32_t s, const int64_t* cum_
                       int32_t* idx_out, double* dist_out, double* scratch, const int32_t* sum_plan,
                       int32_t plan_len, cudaStream_t st);
 int64_t null_ratio_staging_doubles(int64_t n, int32_t m);
+int launch_validate_positions(const int32_t* idx, int64_t count, int64_t n, int32_t* bad, cudaStream_t st);
 int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t row_begin, int64_t row_end,
                        int32_t k, int32_t m, double* out, cudaStream_t st);
 

@@ -89,6 +89,15 @@ def savez_compressed(file, threads: int | None = None, level: int = 6, **arrays)
         _write_central_directory(fh, central)
 
 
+def _be_nice():
+    """Lowers the priority of the calling THREAD (Linux: per-thread nice through its native id)."""
+    try:
+        import threading
+        os.setpriority(os.PRIO_PROCESS, threading.get_native_id(), 10)
+    except (AttributeError, OSError, PermissionError):
+        pass
+
+
 class AsyncNpzWriter:
     """savez_compressed in two halves: add(name, array) starts deflating the array on the pool right away (the caller
     goes on computing -- zlib and the CUDA library both release the GIL), close() waits and writes the archive.
@@ -102,7 +111,9 @@ class AsyncNpzWriter:
         self.file = file
         self.level = level
         # two cores stay free for the caller, whose host work (NumPy, LAPACK) runs while the pool deflates
-        self.pool = ThreadPoolExecutor(threads or max(1, min(32, len(os.sched_getaffinity(0)) - 2)))
+        # background work: the deflate threads run at a lower scheduling priority than the caller, whose host work
+        # (NumPy, LAPACK, the next pass's preparation) shares the cores with them
+        self.pool = ThreadPoolExecutor(threads or max(1, min(32, len(os.sched_getaffinity(0)) - 2)), initializer=_be_nice)
         self.members = []  # (name, usize, [futures], keep-alive)
 
     def add(self, name, array):
