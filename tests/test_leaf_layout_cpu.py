@@ -28,22 +28,18 @@ def _kernel_order_distance(a, b, perm, desc, plan):
     ap = np.where(perm >= 0, a[np.maximum(perm, 0)], 0.0)
     bp = np.where(perm >= 0, b[np.maximum(perm, 0)], 0.0)
     leaf_sums = []
-    for off, steps, tail, half in desc:
+    for off, steps, tail, _ in desc:
         r = np.zeros(8)
         for t in range(steps):
             for c in range(8):
                 for e in range(2):
                     u = bp[off + t * 16 + c * 2 + e] - ap[off + t * 16 + c * 2 + e]
                     r[c] = r[c] + u * u
-        if half:  # one more block of 8: 8 bytes per chain
-            for c in range(8):
-                u = bp[off + steps * 16 + c] - ap[off + steps * 16 + c]
-                r[c] = r[c] + u * u
         s1 = [r[c] + r[c ^ 1] for c in range(8)]
         s2 = [s1[c] + s1[c ^ 2] for c in range(8)]
         res = s2[0] + s2[4]
         for i in range(tail):
-            u = bp[off + steps * 16 + half * 8 + i] - ap[off + steps * 16 + half * 8 + i]
+            u = bp[off + steps * 16 + i] - ap[off + steps * 16 + i]
             res = res + u * u
         leaf_sums.append(res)
     stack, li = [], 0
@@ -60,9 +56,8 @@ def _kernel_order_distance(a, b, perm, desc, plan):
 def test_leaf_layout_reproduces_numpy_sum(s):
     perm, desc, plan = _layout(s)
     assert sorted(int(q) for q in perm if q >= 0) == list(range(s))          # a permutation of the columns + padding
-    assert len(perm) == s + (s & 1)                                          # a pure permutation: rows padded to an even length only
-    assert all(int(d[0]) % 8 == 0 for d in desc)                             # every leaf starts on a 64-byte boundary
-    assert all(0 <= int(d[1]) <= 8 and 0 <= int(d[2]) < 8 and int(d[3]) in (0, 1) for d in desc)
+    assert len(perm) % 16 == 0 and all(int(d[0]) % 16 == 0 for d in desc)    # every leaf starts on a 128-byte line
+    assert all(0 <= int(d[1]) <= 8 and 0 <= int(d[2]) < 8 for d in desc)
     rng = np.random.default_rng(s)
     for _ in range(10):
         a = 1.0 + 0.05 * rng.standard_normal(s)

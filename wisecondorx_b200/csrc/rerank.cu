@@ -77,16 +77,17 @@ int plan_to_leaves(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& 
 // The r01d profile of the LDG re-rank shows the L1 data pipe at 88 % (one warp-level LDG.128 of 8 quads touches 8
 // cache lines = 8-10 wavefronts per 512 bytes, plus 4 wavefronts per LDS.128 of the target row) with L2 at 37 %.
 // Here every row of X is stored once more in the order the summation consumes it: a leaf of NumPy's pairwise tree
-// (<= 128 terms = up to 16 blocks of 8, accumulator chain c = element index mod 8) becomes `steps` units of 128
-// bytes -- unit t holds, for chain c = 0..7, the chain's elements of blocks 2t and 2t+1 (16 bytes per chain) -- then,
-// for an odd block count, one HALF unit of 64 bytes (block 2 steps: 8 bytes per chain), then the < 8 tail terms in
-// sequence.  Eight lanes (one per chain) read one full 128-byte unit per step, every lane adds its own chain in
-// NumPy's order, and the target row's chain values of the leaf sit in shared memory in the same layout.
-// The layout is a pure permutation of the row (round 1 padded odd block counts and tails with zeros: 528 doubles per
-// row at S = 500; the gather is bound by the L2 -> SM bytes, so the 28 padding doubles were 5 % of its time).  Only
-// the last leaf of a tree can have a length that is not a multiple of 8, so every leaf starts on a 64-byte boundary;
-// rows are padded to an even length (16-byte aligned rows for the 128-bit loads).
-// desc: 4 int32 per leaf = (offset in doubles, steps, tail terms, half unit 0 / 1).  Returns the permuted row length.
+// (<= 128 terms, accumulator chain c = element index mod 8) becomes `steps` units of 128 bytes; unit t holds, for
+// chain c = 0..7, the chain's elements 2t and 2t+1 (16 bytes per chain).  Eight lanes (one per chain) then read one
+// full 128-byte line per step (4 lines = 4 wavefronts per warp-level LDG.128), every lane adds its own chain in
+// NumPy's order, and the target row's chain values of the leaf sit in registers while the lane group walks its
+// candidates, so the target row costs 8 LDS.128 per leaf instead of one per candidate block.
+// Padding (odd block count, tail padded to even) is 0.0 in every row: (0 - 0)^2 = +0 added to a non-negative
+// accumulator leaves it bit-identical.  The < 8 tail terms of a leaf follow its units and are added in sequence.
+// (A padding-free layout -- a pure permutation of the row, half units for odd block counts, 500 instead of 528 doubles
+// at S = 500 -- was measured in round 2: 5 % fewer bytes but 41.8 instead of 38.2 ms, because units and rows no longer
+// start on 128-byte lines and every 128-byte unit read touches two lines.  The alignment is worth more than the bytes.)
+// desc: 4 int32 per leaf = (offset in doubles, steps, tail terms, 0).  Returns the permuted row length.
 // ------------------------------------------------------------------------------------------
 int build_leaf_layout(const int32_t* plan, int32_t plan_len, std::vector<int32_t>& perm, std::vector<int32_t>& desc) {
   perm.clear();
@@ -94,23 +95,20 @@ int build_leaf_layout(const int32_t* plan, int32_t plan_len, std::vector<int32_t
   for (int op = 0; op < plan_len; op++) {
     if (plan[3 * op] != 0) continue;
     const int off = plan[3 * op + 1], len = plan[3 * op + 2];
-    const int nblk = len >> 3, steps = nblk >> 1, half = nblk & 1, tail = len - (nblk << 3);
+    const int nblk = len >> 3, steps = (nblk + 1) >> 1, tail = len - (nblk << 3);
     if (steps > 8) return -1;
-    if (perm.size() % 8) return -1;  // only the last leaf may have a partial block
     desc.push_back((int32_t)perm.size());
     desc.push_back(steps);
     desc.push_back(tail);
-    desc.push_back(half);
+    desc.push_back(0);
     for (int t = 0; t < steps; t++)
       for (int c = 0; c < 8; c++) {
         perm.push_back(off + 8 * (2 * t) + c);
-        perm.push_back(off + 8 * (2 * t + 1) + c);
+        perm.push_back(2 * t + 1 < nblk ? off + 8 * (2 * t + 1) + c : -1);
       }
-    if (half)
-      for (int c = 0; c < 8; c++) perm.push_back(off + 8 * (2 * steps) + c);
     for (int i = 0; i < tail; i++) perm.push_back(off + 8 * nblk + i);
+    while (perm.size() % 16) perm.push_back(-1);  // every leaf starts on a 128-byte line
   }
-  if (perm.size() % 2) perm.push_back(-1);  // rows stay 16-byte aligned
   return (int)perm.size();
 }
 
@@ -394,56 +392,80 @@ __device__ __forceinline__ double2 ldg_nc_d2(const double2* p) {
   return v;
 }
 
-// One leaf (STEPS units of 128 bytes, `half` more unit of 64 bytes, `tail` sequential terms, at row offset `off`) of the
-// candidates sel[0..cn): 8 lanes (one per accumulator chain, c8 = lane & 7) per candidate, 32 candidates per pass.
-// Leaf sums go to leafres[candidate * nleaves + lf].
-template <int STEPS>
+// One leaf (STEPS units of 128 bytes + `tail` sequential terms at row offset `off`) of the candidates
+// sel[0..cn): 8 lanes (one per accumulator chain, c8 = lane & 7) per candidate, 32 candidates per pass; PAIR: two
+// passes (A, B) in flight and the target row's unit (one LDS.128) shared by the pair.  Leaf sums go to
+// leafres[candidate * nleaves + lf].
+template <int STEPS, bool PAIR>
 __device__ __forceinline__ void leaf_pass(const double* __restrict__ x, int sp, const double* __restrict__ a_s,
-                                          const int32_t* __restrict__ sel, int cn, int off, int tail, int half, int nleaves, int lf,
+                                          const int32_t* __restrict__ sel, int cn, int off, int tail, int nleaves, int lf,
                                           double* __restrict__ leafres, int tid) {
   constexpr int NV = STEPS > 0 ? STEPS : 1;
   constexpr int G = RR_THREADS / 8;
   const int lane = tid & 31, c8 = tid & 7, grp = tid >> 3;
   const double2* ap = reinterpret_cast<const double2*>(a_s + off) + c8;  // unit t: ap[8 * t]
-  const int hoff = off + STEPS * 16 + c8;                                // this lane's element of the half unit
-  const int toff = off + STEPS * 16 + half * 8 + c8;                     // this lane's tail term (c8 < tail)
-  const double a_half = half ? a_s[hoff] : 0.0;
+  const int toff = off + STEPS * 16 + c8;                                // this lane's tail term (c8 < tail)
   const double a_tail = c8 < tail ? a_s[toff] : 0.0;
   const int base = lane & ~7;
-  for (int c0 = 0; c0 < cn; c0 += G) {
-    const int ciA = c0 + grp;
+  for (int c0 = 0; c0 < cn; c0 += (PAIR ? 2 : 1) * G) {
+    const int ciA = c0 + grp, ciB = ciA + G;
     // clamped: idle groups redo the last candidate, which keeps the warp converged for the shuffles
     const double* rowA = x + (int64_t)sel[ciA < cn ? ciA : cn - 1] * sp;
+    const double* rowB = PAIR ? x + (int64_t)sel[ciB < cn ? ciB : cn - 1] * sp : rowA;
     const double2* pa = reinterpret_cast<const double2*>(rowA + off) + c8;
-    double2 va[NV];
+    const double2* pb = reinterpret_cast<const double2*>(rowB + off) + c8;
+    double2 va[NV], vb[NV];
 #pragma unroll
     for (int t = 0; t < STEPS; t++) va[t] = ldg_nc_d2(pa + 8 * t);
-    double vh = 0.0, ta = 0.0;
-    if (half) vh = __ldg(rowA + hoff);
-    if (c8 < tail) ta = __ldg(rowA + toff);
-    double rA = 0.0;
+    if (PAIR) {
+#pragma unroll
+      for (int t = 0; t < STEPS; t++) vb[t] = ldg_nc_d2(pb + 8 * t);
+    }
+    double ta = 0.0, tb = 0.0;
+    if (c8 < tail) {
+      ta = __ldg(rowA + toff);
+      if (PAIR) tb = __ldg(rowB + toff);
+    }
+    double rA = 0.0, rB = 0.0;
 #pragma unroll
     for (int t = 0; t < STEPS; t++) {
       const double2 av = ap[8 * t];
       const double uA0 = __dsub_rn(va[t].x, av.x);
       rA = __dadd_rn(rA, __dmul_rn(uA0, uA0));
+      if (PAIR) {
+        const double uB0 = __dsub_rn(vb[t].x, av.x);
+        rB = __dadd_rn(rB, __dmul_rn(uB0, uB0));
+      }
       const double uA1 = __dsub_rn(va[t].y, av.y);
       rA = __dadd_rn(rA, __dmul_rn(uA1, uA1));
-    }
-    if (half) {
-      const double uh = __dsub_rn(vh, a_half);
-      rA = __dadd_rn(rA, __dmul_rn(uh, uh));
+      if (PAIR) {
+        const double uB1 = __dsub_rn(vb[t].y, av.y);
+        rB = __dadd_rn(rB, __dmul_rn(uB1, uB1));
+      }
     }
     // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), identical in all 8 lanes
     double sA = __dadd_rn(rA, __shfl_xor_sync(0xffffffffu, rA, 1));
     sA = __dadd_rn(sA, __shfl_xor_sync(0xffffffffu, sA, 2));
     sA = __dadd_rn(sA, __shfl_xor_sync(0xffffffffu, sA, 4));
+    double sB = 0.0;
+    if (PAIR) {
+      sB = __dadd_rn(rB, __shfl_xor_sync(0xffffffffu, rB, 1));
+      sB = __dadd_rn(sB, __shfl_xor_sync(0xffffffffu, sB, 2));
+      sB = __dadd_rn(sB, __shfl_xor_sync(0xffffffffu, sB, 4));
+    }
     if (tail > 0) {
       ta = __dsub_rn(ta, a_tail);
-      const double qa = __dmul_rn(ta, ta);
-      for (int i = 0; i < tail; i++) sA = __dadd_rn(sA, __shfl_sync(0xffffffffu, qa, base + i));
+      tb = __dsub_rn(tb, a_tail);
+      const double qa = __dmul_rn(ta, ta), qb = __dmul_rn(tb, tb);
+      for (int i = 0; i < tail; i++) {
+        sA = __dadd_rn(sA, __shfl_sync(0xffffffffu, qa, base + i));
+        if (PAIR) sB = __dadd_rn(sB, __shfl_sync(0xffffffffu, qb, base + i));
+      }
     }
-    if (c8 == 0 && ciA < cn) leafres[ciA * nleaves + lf] = sA;
+    if (c8 == 0) {
+      if (ciA < cn) leafres[ciA * nleaves + lf] = sA;
+      if (PAIR && ciB < cn) leafres[ciB * nleaves + lf] = sB;
+    }
   }
 }
 
@@ -637,17 +659,17 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     for (int cb = 0; cb < m; cb += cap) {
       const int cn = min(cap, m - cb);
       for (int lf = 0; lf < nleaves; lf++) {
-        const int off = leaf_s[4 * lf], steps = leaf_s[4 * lf + 1], tail = leaf_s[4 * lf + 2], half = leaf_s[4 * lf + 3];
+        const int off = leaf_s[4 * lf], steps = leaf_s[4 * lf + 1], tail = leaf_s[4 * lf + 2];
         switch (steps) {
-          case 8: leaf_pass<8>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 7: leaf_pass<7>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 6: leaf_pass<6>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 5: leaf_pass<5>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 4: leaf_pass<4>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 3: leaf_pass<3>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 2: leaf_pass<2>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          case 1: leaf_pass<1>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
-          default: leaf_pass<0>(x, sp, a_s, sel + cb, cn, off, tail, half, nleaves, lf, leafres, tid); break;
+          case 8: leaf_pass<8, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 7: leaf_pass<7, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 6: leaf_pass<6, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 5: leaf_pass<5, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 4: leaf_pass<4, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 3: leaf_pass<3, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 2: leaf_pass<2, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          case 1: leaf_pass<1, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
+          default: leaf_pass<0, false>(x, sp, a_s, sel + cb, cn, off, tail, nleaves, lf, leafres, tid); break;
         }
       }
       __syncthreads();
