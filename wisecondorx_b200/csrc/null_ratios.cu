@@ -216,76 +216,30 @@ nq_code_kernel(const uint64_t* __restrict__ xm, int64_t n, int m, const NqCol* _
 // in [-n, n): no clamp on the hot path.
 __device__ __forceinline__ int32_t nq_wrap(int32_t v, int32_t n) { return v + ((v >> 31) & n); }
 
-// TWO threads (adjacent lanes) per median: each holds half of the bin's k codes -- NPT packed registers, the quads
-// (4 consecutive reference positions) 2 j + h for h = lane & 1 -- and the two exchange their counts with one shuffle per
-// bisection step.  One thread per median needed 150 key registers for k = 300: 8-12 warps per SM and a single
-// accumulator chain (the compiler had no registers left for independent ones), 40 % issue utilisation.  Half the keys
-// per thread leave room for four chains and 16 warps per SM.
-// R = slots per lane of the exact warp-cooperative path (32 R >= k); 4 NPT >= k + 3.
-template <int NPT>
-__device__ __forceinline__ int pair_count_lt(const uint32_t (&k2)[NPT], uint32_t trial) {
-  const int own = ps_count_lt<NPT>(k2, trial);
-  return own + __shfl_xor_sync(0xffffffffu, own, 1);
-}
-// count of keys equal to `code` over the pair and the position (0-based, in the bin's reference list) of that key when
-// there is exactly one.  Register r of thread h holds the keys 4 q + 2 (r & 1) + {0, 1} of quad q = 2 (r >> 1) + h.
-template <int NPT>
-__device__ __forceinline__ void pair_find(const uint32_t (&k2)[NPT], uint32_t code, int h, int& count, int& pos) {
-  const uint32_t c2 = code | (code << 16);
-  uint32_t n0 = 0, n1 = 0, p0 = 0, p1 = 0;
-#pragma unroll
-  for (int r = 0; r < NPT; r += 2) {
-    const uint32_t e0 = h2_eq(k2[r], c2);
-    n0 = h2_add(n0, e0);
-    p0 = h2_fma(e0, h2_const(8 * (r >> 1) + 1, 8 * (r >> 1) + 2), p0);   // positions + 1 for h = 0
-    if (r + 1 < NPT) {
-      const uint32_t e1 = h2_eq(k2[r + 1], c2);
-      n1 = h2_add(n1, e1);
-      p1 = h2_fma(e1, h2_const(8 * (r >> 1) + 3, 8 * (r >> 1) + 4), p1);
-    }
-  }
-  const int cown = h2_total(n0) + h2_total(n1);
-  const int pown = h2_total(p0) + h2_total(p1) - 1 + 4 * h * cown;  // quads of thread 1 are shifted by 4 positions
-  const int coth = __shfl_xor_sync(0xffffffffu, cown, 1);
-  const int poth = __shfl_xor_sync(0xffffffffu, pown, 1);
-  count = cown + coth;
-  pos = cown ? pown : poth;  // meaningful only when count == 1
-}
-template <int NPT>
-__device__ __forceinline__ uint32_t pair_max_below(const uint32_t (&k2)[NPT], uint32_t lim) {
-  const uint32_t own = ps_max_below<NPT>(k2, lim);
-  const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
-  return own > oth ? own : oth;
-}
-
-template <int NPT, int R>
-__global__ void __launch_bounds__(128, NPT > 80 ? 3 : 4)
+// NP packed registers (2 NP >= k keys; FULL: k == 2 NP exactly, no bounds checks in the gather), R = slots per lane of
+// the exact warp-cooperative path (32 R >= k)
+template <int NP, int R, bool FULL>
+__global__ void __launch_bounds__(128, NP > 160 ? 2 : (NP > 64 ? 3 : 4))
 null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ xm, const NqCol* __restrict__ cols, int64_t n,
                  const int32_t* __restrict__ idx, int64_t row_begin, int64_t rows, int k, int m, double* __restrict__ out) {
-  // A block covers 64 consecutive (bin, column) pairs = at most 64 / m + 2 bins.  Their reference positions are turned
-  // into element offsets of the code table once per block (wrap + multiply), shared by all columns of the bin; the list
-  // is padded to a multiple of 8 with -1 (no key).
-  extern __shared__ int32_t s_off[];  // [bins of the block][kp], kp = k rounded up to 8
+  // A block covers 128 consecutive (bin, column) pairs = at most 128 / m + 2 bins.  Their reference positions are turned
+  // into element offsets of the code table once per block (wrap + multiply), shared by all columns of the bin.
+  extern __shared__ int32_t s_off[];  // [bins of the block][k]
   const int lane = threadIdx.x & 31;
-  const int h = threadIdx.x & 1;
-  const int kp = (k + 7) & ~7;
   const int64_t total = rows * m;
-  const int64_t blk0 = (int64_t)blockIdx.x * (blockDim.x >> 1);
+  const int64_t blk0 = (int64_t)blockIdx.x * blockDim.x;
   const int64_t row_first = blk0 / m;
-  const int64_t blk_last = blk0 + (blockDim.x >> 1) - 1 < total - 1 ? blk0 + (blockDim.x >> 1) - 1 : total - 1;
+  const int64_t blk_last = blk0 + blockDim.x - 1 < total - 1 ? blk0 + blockDim.x - 1 : total - 1;
   const int nrows_blk = (int)(blk_last / m - row_first) + 1;
   const int32_t n32 = (int32_t)n;
-  for (int e = threadIdx.x; e < nrows_blk * kp; e += blockDim.x) {
-    const int rr = e / kp, t = e - rr * kp;
-    s_off[e] = t < k ? nq_wrap(idx[(row_first + rr) * k + t], n32) * NQ_STRIDE : -1;
-  }
+  for (int e = threadIdx.x; e < nrows_blk * k; e += blockDim.x) s_off[e] = nq_wrap(idx[row_first * k + e], n32) * NQ_STRIDE;
   __syncthreads();
-  const int64_t p0 = blk0 + (threadIdx.x >> 1);
+  const int64_t p0 = blk0 + threadIdx.x;
   const bool active = p0 < total;
-  const int64_t p = active ? p0 : total - 1;  // whole warps stay alive for the shuffles and the cooperative exact path
+  const int64_t p = active ? p0 : total - 1;  // whole warps stay alive for the cooperative exact path
   const int64_t lrow = p / m;
   const int col = (int)(p - lrow * m);
-  const int32_t* __restrict__ orow = s_off + (lrow - row_first) * kp;
+  const int32_t* __restrict__ orow = s_off + (lrow - row_first) * k;
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   double med = nan;
   bool need_exact = cols[col].exact != 0;
@@ -300,67 +254,59 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
       done = true;
     }
   }
-  // (`done` and `need_exact` are the same in both threads of a pair: same bin, same column)
-  const bool fast = !done && !need_exact;
-  const uint32_t warp_fast = __ballot_sync(0xffffffffu, fast);
-  if (warp_fast) {  // the shuffles below need the whole warp; lanes that are not `fast` compute on padding keys
-    uint32_t k2[NPT];
+  if (!done && !need_exact) {
+    uint32_t k2[NP];
     const uint16_t* __restrict__ xqc = xq + col;
-    const int4* __restrict__ ov = reinterpret_cast<const int4*>(orow);
-    const int nquads = kp >> 2;
+    if (FULL) {
+      // k == 2 NP: four offsets per 128-bit shared-memory load (a broadcast: the threads of a bin read the same words)
+      const int4* __restrict__ ov = reinterpret_cast<const int4*>(orow);
 #pragma unroll
-    for (int j = 0; j < (NPT + 1) / 2; j++) {
-      const int q = 2 * j + h;
-      uint32_t c0 = NQ_PAD, c1 = NQ_PAD, c2 = NQ_PAD, c3 = NQ_PAD;
-      if (fast && q < nquads) {
-        const int4 o = ov[q];
-        if (o.x >= 0) c0 = xqc[o.x];
-        if (o.y >= 0) c1 = xqc[o.y];
-        if (o.z >= 0) c2 = xqc[o.z];
-        if (o.w >= 0) c3 = xqc[o.w];
+      for (int j = 0; j < NP / 2; j++) {
+        const int4 q = ov[j];
+        const uint32_t c0 = xqc[q.x], c1 = xqc[q.y], c2 = xqc[q.z], c3 = xqc[q.w];
+        k2[2 * j] = c0 | (c1 << 16);
+        k2[2 * j + 1] = c2 | (c3 << 16);
       }
-      k2[2 * j] = c0 | (c1 << 16);
-      if (2 * j + 1 < NPT) k2[2 * j + 1] = c2 | (c3 << 16);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        uint32_t c0 = NQ_PAD, c1 = NQ_PAD;
+        if (2 * j < k) c0 = xqc[orow[2 * j]];
+        if (2 * j + 1 < k) c1 = xqc[orow[2 * j + 1]];
+        k2[j] = c0 | (c1 << 16);
+      }
     }
     const int t = k >> 1;  // rank of the upper middle key (the median itself for odd k)
-    uint32_t T = 0;
     int below = 0;
-#pragma unroll 1
-    for (int bit = 14; bit >= 0; bit--) {
-      const uint32_t trial = T | (1u << bit);
-      const int c = pair_count_lt<NPT>(k2, trial);
-      if (c <= t) { T = trial; below = c; }
-    }
+    const uint32_t T = ps_select<NP>(k2, t, below);
     // T is the code of the rank-t key: count(< T) <= t < count(< T + 1).  It can stand for its VALUE only if no
     // other key shares the code; an even k also needs the rank t - 1 key: the largest key below T, provided rank t is
     // the first key with code T.
     int eq_hi, j_hi, eq_lo = 1, j_lo = 0;
-    pair_find<NPT>(k2, T, h, eq_hi, j_hi);
+    ps_find<NP>(k2, T, eq_hi, j_hi);
     bool ok = eq_hi == 1;
-    const bool want_lo = ok && !(k & 1) && below == t;
-    if (ok && !(k & 1)) ok = below == t;
-    if (__ballot_sync(0xffffffffu, want_lo)) {  // warp-uniform: the pair functions shuffle
-      const uint32_t T_lo = pair_max_below<NPT>(k2, T);
-      pair_find<NPT>(k2, T_lo, h, eq_lo, j_lo);
-      if (want_lo) ok = eq_lo == 1;
-    }
-    if (fast) {
+    if (ok && !(k & 1)) {
+      ok = below == t;
       if (ok) {
-        const double v_hi = nq_value(xm, n, orow[j_hi] / NQ_STRIDE, col);
-        if (k & 1) {
-          med = v_hi;
-        } else {
-          const double v_lo = nq_value(xm, n, orow[j_lo] / NQ_STRIDE, col);
-          med = (v_lo + v_hi) / 2.0;  // np.median: mean of the two middle values
-        }
-        done = true;
-      } else {
-        need_exact = true;
+        ps_find<NP>(k2, ps_max_below<NP>(k2, T), eq_lo, j_lo);
+        ok = eq_lo == 1;
       }
     }
+    if (ok) {
+      const double v_hi = nq_value(xm, n, orow[j_hi] / NQ_STRIDE, col);
+      if (k & 1) {
+        med = v_hi;
+      } else {
+        const double v_lo = nq_value(xm, n, orow[j_lo] / NQ_STRIDE, col);
+        med = (v_lo + v_hi) / 2.0;  // np.median: mean of the two middle values
+      }
+      done = true;
+    } else {
+      need_exact = true;
+    }
   }
-  // exact path, one flagged (bin, column) at a time by the whole warp (flagged by the even lane of its pair)
-  uint32_t pending = __ballot_sync(0xffffffffu, need_exact && !done && h == 0);
+  // exact path, one flagged (bin, column) at a time by the whole warp
+  uint32_t pending = __ballot_sync(0xffffffffu, need_exact && !done);
   while (pending) {
     const int src = __ffs(pending) - 1;
     pending &= pending - 1;
@@ -377,7 +323,7 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
     const double mm = warp_median<R>(key, k, &hmax);
     if (lane == src) med = hmax == 0xffffffffu ? nan : mm;  // np.median is NaN when any value is NaN
   }
-  if (active && h == 0) out[lrow * m + col] = log2(nq_value(xm, n, row_begin + lrow, col) / med);
+  if (active) out[lrow * m + col] = log2(nq_value(xm, n, row_begin + lrow, col) / med);
 }
 }  // namespace
 
@@ -445,21 +391,21 @@ int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t 
   if (rows <= 0 || m <= 0) return 0;
   if (k > 512) { set_error("null_ratios: ref_size > 512 unsupported"); return 1; }
   const bool legacy = std::getenv("WCX_NULL_WARP") != nullptr;  // cross-check (tests): the warp-per-bin kernel
-  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2 && sizeof(int32_t) * (size_t)(64 / m + 2) * ((k + 7) & ~7) <= 40 * 1024) {
+  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2 && sizeof(int32_t) * (size_t)(128 / m + 2) * k <= 40 * 1024) {
     NullStaging ns = null_staging(const_cast<double*>(xt), n, m);
     const uint64_t* xm = reinterpret_cast<const uint64_t*>(xt);
     const int64_t total = rows * m;
-    // two threads per median, 64 medians per block; shared memory: reference offsets of the bins a block covers
-    // (64 / m + 2 of them, k rounded up to 8 each)
-    const int kp = (k + 7) & ~7;
-    const size_t smem = sizeof(int32_t) * (size_t)(64 / m + 2) * kp;
-    const unsigned grid2 = (unsigned)((total + 63) / 64);
-#define WCX_NQ_LAUNCH(NPT, R) null_fast_kernel<NPT, R><<<grid2, 128, smem, st>>>(ns.xq, xm, ns.cols, n, idx, row_begin, rows, k, m, out)
-    if (k <= 64) WCX_NQ_LAUNCH(16, 2);
-    else if (k <= 128) WCX_NQ_LAUNCH(32, 4);
-    else if (k <= 200) WCX_NQ_LAUNCH(50, 7);
-    else if (k <= 304) WCX_NQ_LAUNCH(76, 10);
-    else WCX_NQ_LAUNCH(100, 13);
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    // shared memory: reference offsets of the bins a block covers (128 / m + 2 of them, k each; rows 16-byte aligned)
+    const size_t smem = sizeof(int32_t) * (size_t)(128 / m + 2) * k;
+    const bool aligned = (k & 3) == 0;
+#define WCX_NQ_LAUNCH(NP, R, FULL) null_fast_kernel<NP, R, FULL><<<grid, 128, smem, st>>>(ns.xq, xm, ns.cols, n, idx, row_begin, rows, k, m, out)
+    if (k == 300 && aligned) WCX_NQ_LAUNCH(150, 10, true);
+    else if (k <= 64) WCX_NQ_LAUNCH(32, 2, false);
+    else if (k <= 128) WCX_NQ_LAUNCH(64, 4, false);
+    else if (k <= 200) WCX_NQ_LAUNCH(100, 7, false);
+    else if (k <= 300) WCX_NQ_LAUNCH(150, 10, false);
+    else WCX_NQ_LAUNCH(200, 13, false);
 #undef WCX_NQ_LAUNCH
     WCX_CUDA_OK(cudaGetLastError());
     return 0;
