@@ -217,9 +217,13 @@ nq_code_kernel(const uint64_t* __restrict__ xm, int64_t n, int m, const NqCol* _
 __device__ __forceinline__ int32_t nq_wrap(int32_t v, int32_t n) { return v + ((v >> 31) & n); }
 
 // NP packed registers (2 NP >= k keys; FULL: k == 2 NP exactly, no bounds checks in the gather), R = slots per lane of
-// the exact warp-cooperative path (32 R >= k)
+// the exact warp-cooperative path (32 R >= k).
+// Measured variants of this kernel at config 3 (stand-alone call incl. 0.6 ms of code building): 255 registers / 8 warps
+// per SM 11.6 ms (this one); capped at 168 registers / 12 warps per SM 12.4 ms (the compiler then serialises the count
+// into one accumulator chain); two threads per median with half the keys each (126 registers, four chains, 16 warps
+// per SM, one shuffle per step) 14.0 ms.  More warps did not buy throughput here.
 template <int NP, int R, bool FULL>
-__global__ void __launch_bounds__(128, NP > 160 ? 2 : (NP > 64 ? 3 : 4))
+__global__ void __launch_bounds__(128, NP > 128 ? 2 : (NP > 64 ? 3 : 4))
 null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ xm, const NqCol* __restrict__ cols, int64_t n,
                  const int32_t* __restrict__ idx, int64_t row_begin, int64_t rows, int k, int m, double* __restrict__ out) {
   // A block covers 128 consecutive (bin, column) pairs = at most 128 / m + 2 bins.  Their reference positions are turned
