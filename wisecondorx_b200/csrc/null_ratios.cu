@@ -17,7 +17,6 @@
 #include <cstdlib>
 
 #include <cuda_fp16.h>
-#include <cuda_pipeline.h>
 
 #include "null_ratios.cuh"
 #include "packed_select.cuh"
@@ -227,52 +226,25 @@ template <int NP, int R, bool FULL>
 __global__ void __launch_bounds__(128, NP > 128 ? 2 : (NP > 64 ? 3 : 4))
 null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ xm, const NqCol* __restrict__ cols, int64_t n,
                  const int32_t* __restrict__ idx, int64_t row_begin, int64_t rows, int k, int m, double* __restrict__ out) {
-  // Persistent blocks over chunks of 128 consecutive (bin, column) pairs (= at most 128 / m + 2 bins).  The reference
-  // positions of a chunk's bins are staged in shared memory -- double buffered: the cp.async of the NEXT chunk's positions
-  // is in flight while this chunk is bisected (the r02t profile had 23 % of the stall samples on this load when every
-  // block fetched its own positions and waited) -- and turned into element offsets of the code table once per chunk
-  // (wrap + multiply), shared by all columns of a bin.
-  extern __shared__ int32_t s_buf[];  // 2 x [bins of a chunk][k]
+  // A block covers 128 consecutive (bin, column) pairs = at most 128 / m + 2 bins.  Their reference positions are turned
+  // into element offsets of the code table once per block (wrap + multiply), shared by all columns of the bin.
+  extern __shared__ int32_t s_off[];  // [bins of the block][k]
   const int lane = threadIdx.x & 31;
   const int64_t total = rows * m;
-  const int64_t nchunks = (total + blockDim.x - 1) / blockDim.x;
+  const int64_t blk0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t row_first = blk0 / m;
+  const int64_t blk_last = blk0 + blockDim.x - 1 < total - 1 ? blk0 + blockDim.x - 1 : total - 1;
+  const int nrows_blk = (int)(blk_last / m - row_first) + 1;
   const int32_t n32 = (int32_t)n;
-  const int buf_ints = (128 / m + 2) * k;
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  auto chunk_rows = [&](int64_t c, int64_t& row_first) -> int {
-    const int64_t blk0 = c * blockDim.x;
-    row_first = blk0 / m;
-    const int64_t blk_last = blk0 + blockDim.x - 1 < total - 1 ? blk0 + blockDim.x - 1 : total - 1;
-    return (int)(blk_last / m - row_first) + 1;
-  };
-  auto stage = [&](int64_t c, int32_t* dst) {
-    int64_t rf;
-    const int nr = chunk_rows(c, rf);
-    const int32_t* src = idx + rf * k;  // the bins of a chunk are consecutive rows: one contiguous range
-    for (int e = threadIdx.x; e < nr * k; e += blockDim.x) __pipeline_memcpy_async(dst + e, src + e, 4);
-    __pipeline_commit();
-  };
-  int cur = 0;
-  if ((int64_t)blockIdx.x < nchunks) stage(blockIdx.x, s_buf);
-  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, cur ^= 1) {
-  int32_t* s_off = s_buf + cur * buf_ints;
-  const int64_t next = chunk + gridDim.x;
-  if (next < nchunks) stage(next, s_buf + (cur ^ 1) * buf_ints);
-  else __pipeline_commit();
-  __pipeline_wait_prior(1);  // everything but the newest group: this chunk's positions have landed
+  for (int e = threadIdx.x; e < nrows_blk * k; e += blockDim.x) s_off[e] = nq_wrap(idx[row_first * k + e], n32) * NQ_STRIDE;
   __syncthreads();
-  int64_t row_first;
-  const int nrows_blk = chunk_rows(chunk, row_first);
-  for (int e = threadIdx.x; e < nrows_blk * k; e += blockDim.x) s_off[e] = nq_wrap(s_off[e], n32) * NQ_STRIDE;
-  __syncthreads();
-  const int64_t blk0 = chunk * blockDim.x;
   const int64_t p0 = blk0 + threadIdx.x;
   const bool active = p0 < total;
   const int64_t p = active ? p0 : total - 1;  // whole warps stay alive for the cooperative exact path
   const int64_t lrow = p / m;
   const int col = (int)(p - lrow * m);
   const int32_t* __restrict__ orow = s_off + (lrow - row_first) * k;
-  const double x_own = nq_value(xm, n, row_begin + lrow, col);  // issued early: only needed for the final ratio
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
   double med = nan;
   bool need_exact = cols[col].exact != 0;
   bool done = false;
@@ -355,9 +327,7 @@ null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ x
     const double mm = warp_median<R>(key, k, &hmax);
     if (lane == src) med = hmax == 0xffffffffu ? nan : mm;  // np.median is NaN when any value is NaN
   }
-  if (active) out[lrow * m + col] = log2(x_own / med);
-  __syncthreads();  // the buffer of this chunk is the target of the next iteration's cp.async
-  }
+  if (active) out[lrow * m + col] = log2(nq_value(xm, n, row_begin + lrow, col) / med);
 }
 }  // namespace
 
@@ -425,17 +395,14 @@ int launch_null_ratios(const double* xt, int64_t n, const int32_t* idx, int64_t 
   if (rows <= 0 || m <= 0) return 0;
   if (k > 512) { set_error("null_ratios: ref_size > 512 unsupported"); return 1; }
   const bool legacy = std::getenv("WCX_NULL_WARP") != nullptr;  // cross-check (tests): the warp-per-bin kernel
-  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2 && 2 * sizeof(int32_t) * (size_t)(128 / m + 2) * k <= 48 * 1024) {
+  if (!legacy && m <= NQ_STRIDE && k <= 400 && k >= 2 && sizeof(int32_t) * (size_t)(128 / m + 2) * k <= 40 * 1024) {
     NullStaging ns = null_staging(const_cast<double*>(xt), n, m);
     const uint64_t* xm = reinterpret_cast<const uint64_t*>(xt);
     const int64_t total = rows * m;
-    // shared memory: two buffers of reference offsets for the bins of a chunk (128 / m + 2 of them, k each)
-    const size_t smem = 2 * sizeof(int32_t) * (size_t)(128 / m + 2) * k;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    // shared memory: reference offsets of the bins a block covers (128 / m + 2 of them, k each; rows 16-byte aligned)
+    const size_t smem = sizeof(int32_t) * (size_t)(128 / m + 2) * k;
     const bool aligned = (k & 3) == 0;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)std::min<int64_t>((total + 127) / 128, (int64_t)sms * (k > 256 ? 2 : 4));
 #define WCX_NQ_LAUNCH(NP, R, FULL) null_fast_kernel<NP, R, FULL><<<grid, 128, smem, st>>>(ns.xq, xm, ns.cols, n, idx, row_begin, rows, k, m, out)
     if (k == 300 && aligned) WCX_NQ_LAUNCH(150, 10, true);
     else if (k <= 64) WCX_NQ_LAUNCH(32, 2, false);
