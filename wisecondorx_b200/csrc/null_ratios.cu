@@ -221,7 +221,8 @@ __device__ __forceinline__ int32_t nq_wrap(int32_t v, int32_t n) { return v + ((
 // Measured variants of this kernel at config 3 (stand-alone call incl. 0.6 ms of code building): 255 registers / 8 warps
 // per SM 11.6 ms (this one); capped at 168 registers / 12 warps per SM 12.4 ms (the compiler then serialises the count
 // into one accumulator chain); two threads per median with half the keys each (126 registers, four chains, 16 warps
-// per SM, one shuffle per step) 14.0 ms.  More warps did not buy throughput here.
+// per SM, one shuffle per step) 14.0 ms; persistent blocks with the next chunk's positions prefetched by cp.async 14.0 ms.
+// Neither more warps nor prefetching the positions bought throughput here.
 template <int NP, int R, bool FULL>
 __global__ void __launch_bounds__(128, NP > 128 ? 2 : (NP > 64 ? 3 : 4))
 null_fast_kernel(const uint16_t* __restrict__ xq, const uint64_t* __restrict__ xm, const NqCol* __restrict__ cols, int64_t n,
