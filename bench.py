@@ -560,6 +560,8 @@ def run_ours(args, rank, world, local_rank):
                      "kernel_ms": sweep_ms, "rows_of_launch": int(rows_main), "rows_total": int(rows)},
         "stages_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
         "exact_fallback_rows": st["exact_fallback_rows"],
+        "counters": {"rerank_exact_distances_per_row": eng.stage_ms()["exact_evals"] / max(1, rows),
+                     "listed_candidates_per_row": eng.stage_ms()["gathered_entries"] / max(1, rows)},
     }
     if world == 1 and not args.no_predict:
         out.update(cli_and_predict_extras(local_rank, cpu_baseline=not args.no_cpu_baseline))

@@ -9,6 +9,21 @@ for S in $STEPS; do
     tests) echo "=== pytest -m gpu"; timeout 1200 python -m pytest tests -m gpu -q -x --tb=short 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.txt ;;
     smoke) echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1 | cut -c1-300 ;;
     bench) echo "=== bench"; timeout 900 python bench.py 2>gpurun_out/${TAG}_bench.err | tail -1 | tee gpurun_out/${TAG}_bench.json | cut -c1-1500 ;;
+    sweeptest) echo "=== sweep variants (short, guarded by a 150 s limit)"
+      timeout 150 python -m pytest tests/test_newref_gpu.py -m gpu -x -q -k "streaming or config2 or edge" </dev/null 2>&1 | tail -5
+      [ ${PIPESTATUS[0]} -ne 0 ] && { echo "sweeptest failed: stopping"; exit 1; } ;;
+    benchq|benchq_own) echo "=== quick bench ($S): 10 steps, no predict / CLI / CPU baseline"
+      ENV=""; [ $S == benchq_own ] && ENV="WCX_SWEEP_MULTIPLY_OWN=1"
+      env $ENV timeout 300 python bench.py --steps 10 --warmup 3 --no-predict --no-cpu-baseline </dev/null 2>gpurun_out/${TAG}_${S}.err | tail -1 > gpurun_out/${TAG}_${S}.json
+      python - <<PYEOF
+import json
+try:
+    d = json.load(open("gpurun_out/${TAG}_${S}.json"))
+    print("$S ms/step %.2f e2e %.2f frac %.3f sweep kernel %.2f ms" % (d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["frac"], d["roofline"]["kernel_ms"]), {k: round(v, 2) for k, v in d["stages_ms"].items()}, d.get("parity"), d.get("counters"))
+except Exception as e:
+    print("$S failed:", e); print(open("gpurun_out/${TAG}_${S}.err").read()[-1500:])
+PYEOF
+      ;;
     benchref) echo "=== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>>gpurun_out/${TAG}_bench.err | tail -1 | tee gpurun_out/${TAG}_bench_reference.json | cut -c1-600 ;;
     launches) echo "=== ncu launch list"
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1
@@ -68,7 +83,7 @@ for r in rows[hdr + 2:]:
 for n, v in acc.most_common(): print("%-60s %6d launches %10.3f ms" % (n, cnt[n], v / 1e6))
 PYEOF
       ;;
-    *) echo "=== custom: $S"; timeout 1200 bash -c "$S" 2>&1 | tail -30 ;;
+    *) echo "=== custom: $S"; timeout 300 bash -c "$S" </dev/null 2>&1 | tail -30 ;;
   esac
 done
 du -sh gpurun_out; ls -la gpurun_out | tail -20

@@ -75,7 +75,7 @@ struct wcx_ctx {
   cudaEvent_t ev[8] = {};
   // newref state
   const double* d_x = nullptr;  // owned (x_buf) or borrowed
-  DevBuf x_buf, xc, norm, xh, norm_h, scale_dev, absmax, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
+  DevBuf x_buf, xc, norm, xh, norm_h, normres_h, rho_dev, scale_dev, absmax, colsum, colcnt, cum_dev, items_dev, counter, cand_ent, cand_cnt, cand_cut;
   DevBuf fail, fail_rows, plan_dev, leaves_dev, scratch, idx_dev, dist_dev, xt, ids_dev, nr_dev, dbg, diag;
   DevBuf xp, perm_dev, leafdesc_dev;  // leaf-major copy of X for the re-rank gather (rerank.cu)
   int32_t sp = 0, leaf_n = 0;
@@ -114,6 +114,8 @@ struct wcx_ctx {
   CbsStats cbs_stats = {};
 };
 
+static constexpr float WCX_F16_ABS_ERR = 6.103515625e-05f;  // 2^-14, see prep_view_h
+
 static PrepView prep_view(const wcx_ctx* c) {
   PrepView pv;
   pv.xc = c->xc.as<float>();
@@ -125,6 +127,8 @@ static PrepView prep_view(const wcx_ctx* c) {
   pv.scale = nullptr;
   pv.abs_err = 0.f;
   pv.f16 = 0;
+  pv.normres = nullptr;
+  pv.rho_max = nullptr;
   return pv;
 }
 
@@ -137,8 +141,10 @@ static PrepView prep_view_h(const wcx_ctx* c) {
   pv.scale = c->scale_dev.as<double>();
   // values below the smallest normal f16 (2^-14) may be rounded to a subnormal (spacing 2^-24) or, on a path that
   // flushes them, to zero: 2^-14 covers both
-  pv.abs_err = 6.103515625e-05f;
+  pv.abs_err = WCX_F16_ABS_ERR;
   pv.f16 = 1;
+  pv.normres = c->normres_h.as<float2>();
+  pv.rho_max = c->rho_dev.as<float>();
   return pv;
 }
 
@@ -189,7 +195,7 @@ void wcx_destroy(wcx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->xh, &c->norm_h, &c->scale_dev, &c->absmax, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
+  for (DevBuf* b : {&c->x_buf, &c->xc, &c->norm, &c->xh, &c->norm_h, &c->normres_h, &c->rho_dev, &c->scale_dev, &c->absmax, &c->colsum, &c->colcnt, &c->cum_dev, &c->items_dev, &c->counter,
                     &c->cand_ent, &c->cand_cnt, &c->cand_cut, &c->fail, &c->fail_rows, &c->plan_dev, &c->leaves_dev,
                     &c->scratch, &c->idx_dev, &c->dist_dev, &c->xt, &c->ids_dev, &c->nr_dev, &c->dbg, &c->diag, &c->xp, &c->perm_dev, &c->leafdesc_dev, &c->p_partial,
                     &c->p_totals, &c->p_tdots, &c->p_state, &c->p_raw, &c->p_x, &c->p_copy_a, &c->p_copy_b, &c->p_z, &c->p_r,
@@ -280,6 +286,7 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
     c->d_x = c->x_buf.as<double>();
   }
   if (c->xh.ensure(2 * (size_t)c->n_pad * c->k_pad_h) || c->norm_h.ensure(sizeof(float) * (size_t)c->n_pad)) return 1;
+  if (c->normres_h.ensure(sizeof(float2) * (size_t)c->n_pad) || c->rho_dev.ensure(sizeof(float))) return 1;
   if (c->scale_dev.ensure(2 * sizeof(double)) || c->absmax.ensure(sizeof(unsigned long long))) return 1;
   if (c->colsum.ensure(sizeof(double) * s) || c->colcnt.ensure(sizeof(double) * s)) return 1;
   if (c->cum_dev.ensure(sizeof(int64_t) * nchr)) return 1;
@@ -288,7 +295,8 @@ int wcx_newref_load(wcx_ctx* c, const double* x, int64_t n, int32_t s, const int
   if (launch_col_stats(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), c->absmax.as<unsigned long long>(), st)) return 1;
   c->tf32_ready = false;  // the fp32 / tf32 operand set is only built when a tf32 or CUDA-core sweep asks for it (ensure_tf32)
   if (launch_center_round_f16(c->d_x, n, s, c->colsum.as<double>(), c->colcnt.as<double>(), c->absmax.as<unsigned long long>(),
-                              c->scale_dev.as<double>(), c->xh.p, c->norm_h.as<float>(), c->n_pad, c->k_pad_h, st))
+                              c->scale_dev.as<double>(), c->xh.p, c->norm_h.as<float>(), c->normres_h.as<float2>(),
+                              c->rho_dev.as<float>(), 2.0 * sqrt((double)c->k_pad_h) * (double)WCX_F16_ABS_ERR, c->n_pad, c->k_pad_h, st))
     return 1;
   c->launches += 3;
   // NumPy pairwise-summation plan for length s

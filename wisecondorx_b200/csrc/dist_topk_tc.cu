@@ -36,6 +36,8 @@
 // operand variants of round 1 are gone.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "candidates.cuh"
 #include "wcx_common.cuh"
 
@@ -363,7 +365,7 @@ __device__ __forceinline__ void filter_chunk(uint32_t (&r)[32], uint32_t snorm_a
 template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const WorkItem* __restrict__ items,
-                    int nitems, CandView cv, float* __restrict__ dbg_acc) {
+                    int nitems, CandView cv, float* __restrict__ dbg_acc, int skip_own) {
   constexpr int STAGES = Cfg<PAIR>::STAGES;
   constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
@@ -425,7 +427,9 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       uint32_t phase = 0;
       for (int unit = unit0; unit < nunits; unit += unit_step) {
         const WorkItem w = items[PAIR ? 2 * unit + (int)crank : unit];
+        const WorkItem wo = items[PAIR ? 2 * unit + (int)(crank ^ 1u) : unit];  // the other half of the 256-row tile
         for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
+          if (skip_own && tile_own(w, ct) && tile_own(wo, ct)) continue;  // all three roles skip the same tiles
           const int col0 = ct * TN;
           for (int kb = 0; kb < kblocks; kb++) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -456,7 +460,9 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       uint32_t tphase = 0;
       for (int unit = unit0; unit < nunits; unit += unit_step) {
         const WorkItem w = items[PAIR ? 2 * unit : unit];
+        const WorkItem wo = items[PAIR ? 2 * unit + 1 : unit];
         for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
+          if (skip_own && tile_own(w, ct) && tile_own(wo, ct)) continue;
           mbar_wait(&tempty[buf], tphase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TN);
@@ -502,6 +508,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
     for (int unit = unit0; unit < nunits; unit += unit_step) {
       const int item = PAIR ? 2 * unit + (int)crank : unit;
       const WorkItem w = items[item];
+      const WorkItem wo = items[PAIR ? (item ^ 1) : item];
       const bool row_ok = row < w.nrows;
       const int64_t slot = (int64_t)w.slot0 + (int64_t)row * w.slot_stride + grp;
       uint2* be = cv.ent + (row_ok ? slot : 0) * WCX_CAND_CAP;
@@ -514,6 +521,7 @@ dist_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap, PrepView pv, const
       st.ladder = false;
       sts_u64_volatile(my_thr_a, ((unsigned long long)(uint32_t)item << 32) | __float_as_uint(st.thr));
       for (int ct = w.ct_begin; ct < w.ct_end; ct++) {
+        if (skip_own && tile_own(w, ct) && tile_own(wo, ct)) continue;  // never multiplied
         const int my_buf = buf;
         const uint32_t my_phase = tphase;
         if (++buf == 2) { buf = 0; tphase ^= 1; }
@@ -640,6 +648,10 @@ int tc_encode_tensor_map(const PrepView& pv, void* tmap_storage_host) {
   return 0;
 }
 
+// Candidate tiles that lie inside the own chromosome of all 256 rows of a unit produce no candidates and are not
+// multiplied (5.7 % of the tiles on a whole genome).  WCX_SWEEP_MULTIPLY_OWN=1 multiplies them anyway (measurement).
+static int sweep_skip_own() { return getenv("WCX_SWEEP_MULTIPLY_OWN") == nullptr ? 1 : 0; }
+
 template <bool F16>
 static int launch_single(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv, void* tmap_storage, float* dbg,
                          int grid_override, cudaStream_t st) {
@@ -653,7 +665,7 @@ static int launch_single(const PrepView& pv, const WorkItem* items, int32_t nite
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const CUtensorMap* map = reinterpret_cast<const CUtensorMap*>(tmap_storage);
   const int grid = grid_override > 0 ? grid_override : (nitems < sms ? nitems : sms);
-  dist_topk_tc_kernel<false, F16><<<grid, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg);
+  dist_topk_tc_kernel<false, F16><<<grid, TC_THREADS, Cfg<false>::SMEM, st>>>(*map, pv, items, nitems, cv, dbg, sweep_skip_own());
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -690,7 +702,7 @@ static int launch_pair(const PrepView& pv, const WorkItem* items, int32_t nitems
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   float* dbg = nullptr;
-  WCX_CUDA_OK(cudaLaunchKernelEx(&cfg, dist_topk_tc_kernel<true, F16>, *map, pv, items, nitems, cv, dbg));
+  WCX_CUDA_OK(cudaLaunchKernelEx(&cfg, dist_topk_tc_kernel<true, F16>, *map, pv, items, nitems, cv, dbg, sweep_skip_own()));
   return 0;
 }
 

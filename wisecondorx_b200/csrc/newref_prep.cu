@@ -132,38 +132,57 @@ __global__ void prep_scale_kernel(const double* __restrict__ colsum, const doubl
 __global__ void center_round_f16_kernel(const double* __restrict__ x, int64_t n, int32_t s,
                                         const double* __restrict__ colsum, const double* __restrict__ colcnt,
                                         const double* __restrict__ scale, __half* __restrict__ xh,
-                                        float* __restrict__ norm, int64_t n_pad, int32_t k_pad) {
+                                        float* __restrict__ norm, float2* __restrict__ normres,
+                                        unsigned int* __restrict__ rho_bits, double tau, int64_t n_pad, int32_t k_pad) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_pad) return;
   const double sc = scale[0];
   __half* out = xh + row * k_pad;
-  double acc = 0.0;
+  double acc = 0.0, racc = 0.0;
   for (int c = lane; c < k_pad; c += 32) {
     __half h = __ushort_as_half((unsigned short)0);
+    double t = 0.0;
     if (row < n && c < s) {
       const double cnt = colcnt[c];
       const double mean = cnt > 0.0 ? colsum[c] / cnt : 0.0;
-      h = __double2half((x[row * s + c] - mean) * sc);  // one rounding, to nearest even
+      t = (x[row * s + c] - mean) * sc;
+      h = __double2half(t);  // one rounding, to nearest even
     }
     out[c] = h;
     const double v = (double)__half2float(h);
     acc += v * v;
+    racc += (t - v) * (t - v);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) norm[row] = (float)acc;
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    racc += __shfl_xor_sync(0xffffffffu, racc, o);
+  }
+  if (lane == 0) {
+    norm[row] = (float)acc;
+    // measured rounding residual |x - x^| of the row (rerank.cu: approx_eps_meas), rounded up; the largest ratio
+    // (|x - x^| - tau) / |x^| over the finite rows bounds the residual of a candidate known only by its norm
+    const double r = sqrt(racc) * (1.0 + 1e-9);
+    const float rf = __double2float_ru(r);
+    normres[row] = make_float2((float)acc, rf);
+    if (row < n && acc > 0.0 && isfinite(acc) && isfinite(r)) {
+      const double rho = fmax(r - tau, 0.0) / sqrt(acc) * (1.0 + 1e-6);
+      atomicMax(rho_bits, __float_as_uint(__double2float_ru(rho)));  // non-negative floats order like their bit patterns
+    }
+  }
 }
 
 int launch_center_round_f16(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
-                            const unsigned long long* absmax, double* scale, void* xh, float* norm, int64_t n_pad,
-                            int32_t k_pad, cudaStream_t st) {
+                            const unsigned long long* absmax, double* scale, void* xh, float* norm, float2* normres,
+                            float* rho_max, double tau, int64_t n_pad, int32_t k_pad, cudaStream_t st) {
   if (n_pad == 0) return 0;
+  WCX_CUDA_OK(cudaMemsetAsync(rho_max, 0, sizeof(float), st));
   prep_scale_kernel<<<1, 256, 0, st>>>(colsum, colcnt, s, absmax, scale);
   const int warps = 8;
   unsigned grid = (unsigned)((n_pad + warps - 1) / warps);
-  center_round_f16_kernel<<<grid, warps * 32, 0, st>>>(x, n, s, colsum, colcnt, scale, reinterpret_cast<__half*>(xh), norm, n_pad,
-                                                       k_pad);
+  center_round_f16_kernel<<<grid, warps * 32, 0, st>>>(x, n, s, colsum, colcnt, scale, reinterpret_cast<__half*>(xh), norm, normres,
+                                                       reinterpret_cast<unsigned int*>(rho_max), tau, n_pad, k_pad);
   WCX_CUDA_OK(cudaGetLastError());
   return 0;
 }

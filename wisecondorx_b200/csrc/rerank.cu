@@ -368,20 +368,43 @@ __device__ __forceinline__ int next_pow2(int v) {
   return p;
 }
 
-// rigorous bound on |d~ - d| for candidates with d <= ~D seen from a row with |a|^2 = an
-__device__ __forceinline__ double approx_eps(double an, double D, int k_pad, double abs_err) {
-  const double u = 4.8852e-4;  // 2^-11 * (1 + 2^-10): tf32 round-to-nearest of an fp32-rounded value
-  double na = sqrt(an);
-  double sD = sqrt(D * 1.02 + 1e-300);
-  double nb = na + sD;                         // |b| <= |a| + sqrt(d)
-  double e = u * (na + nb) + 2.0 * sqrt((double)k_pad) * abs_err;  // | |a^-b^| - |a-b| | <= |da| + |db|, |dx| <= u |x| + sqrt(K) abs_err
-  double rounding = 2.0 * sD * e + e * e;
-  double gamma = ((double)k_pad + 64.0) * 1.1920929e-7;  // fp32 accumulation, (k_pad + 64) * 2^-23
-  double accum = 2.0 * gamma * na * nb;
-  double misc = 4.77e-7 * (an + nb * nb + 2.0 * na * nb);  // fp32 norm + final fma roundings
+// Rigorous bound on |d~ - d| (d~ = |a^|^2 + v~, the value the sweep formed; d the squared distance of the unrounded
+// rows), all in the units of the list values.
+//   an = |a^|^2, nb >= |b^|, e >= |a - a^| + |b - b^|, sD >= min(|a - b|, |a^ - b^|)
+// | |a^-b^| - |a-b| | <= e gives | |a^-b^|^2 - |a-b|^2 | <= 2 sD e + e^2 whichever of the two distances sD bounds;
+// the rest is arithmetic: fp32 accumulation of the K products (exact products of the rounded operands), the fp32
+// roundings of the two norms and of v = |b^|^2 - 2 acc.  The factor 1.5 is slack on top of the worst case.
+__device__ __forceinline__ double eps_from(double an, double nb, double e, double sD, int k_pad) {
+  const double na = sqrt(an);
+  const double rounding = 2.0 * sD * e + e * e;
+  const double gamma = ((double)k_pad + 64.0) * 1.1920929e-7;  // fp32 accumulation, (k_pad + 64) * 2^-23
+  const double accum = 2.0 * gamma * na * nb;
+  const double misc = 4.77e-7 * (an + nb * nb + 2.0 * na * nb);  // fp32 norms + final fma rounding
   return 1.5 * (rounding + accum + misc) + 1e-300;
 }
 
+// One bound for every candidate whose squared distance (exact or approximate) is at most Dq, seen from a row with
+// |a^|^2 = an: |b^| <= |a^| + sqrt(Dq).  Conversion residuals: worst case u |x| per row (ra < 0), or -- f16 operands --
+// the row's own measured residual ra and rho |b^| + tau for the candidate (PrepView::rho_max: the largest measured
+// ratio of the matrix; typically 0.4-0.5 u, which is what shrinks the evaluated prefix from ~1.29 k to ~1.15 k).
+__device__ __forceinline__ double approx_eps(double an, double Dq, int k_pad, double abs_err, double ra, double rho) {
+  const double u = 4.8852e-4;  // 2^-11 * (1 + 2^-10): f16 / tf32 round-to-nearest of an fp32-rounded value
+  const double na = sqrt(an);
+  const double sD = sqrt(Dq);
+  const double nb = na + sD;
+  const double tau = 2.0 * sqrt((double)k_pad) * abs_err;  // subnormal / flush-to-zero floor of both operands
+  const double e = (ra >= 0.0 ? ra + fmin(rho, u) * nb + tau : u * (na + nb)) + tau;
+  return eps_from(an, nb, e, sD, k_pad);
+}
+
+// Bound for ONE listed candidate from its own norm and measured residual (normres) and its approximate value v.
+__device__ __forceinline__ double cand_eps(double an, double ra, float2 nr, double v, int k_pad, double abs_err) {
+  const double tau = 2.0 * sqrt((double)k_pad) * abs_err;
+  const double nb = sqrt((double)nr.x);
+  const double e = ra + (double)nr.y + tau;
+  const double sD = sqrt(fmax(v + an, 0.0) * 1.02 + 1e-300);  // |a^ - b^|^2 = v + an up to the arithmetic terms (2 % covers them: checked by `bound`)
+  return eps_from(an, nb, e, sD, k_pad);
+}
 
 // ---- leaf-major evaluation (see build_leaf_layout) ------------------------------------------------------------
 
@@ -488,7 +511,7 @@ __device__ __forceinline__ double combine_leaves(const double* __restrict__ lr, 
 // ------------------------------------------------------------------------------------------
 // rerank kernel: one CTA per target row
 // ------------------------------------------------------------------------------------------
-// shared memory: a[S] doubles | keys[maxc] u64 (later: exact distance keys) | sel[RR_MAXM] i32 |
+// shared memory: a[S] doubles | keys[maxc] u64 (later: exact distance keys) | sel[RR_MAXM] i32 | selv[RR_MAXM] f32 |
 //                pos[RR_MAXM] i32 | plan
 // LEAF: `x` is the leaf-major copy (row stride `sp` doubles, build_leaf_layout), `leaf_g` its descriptors.
 // NULLS: the null ratios of the row (newref_tools.py:210-224) are computed by the same CTA right after its indexes
@@ -507,7 +530,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   uint32_t* vals = reinterpret_cast<uint32_t*>(a_s + ((row_len + 1) & ~1));  // [maxc] orderable keys of the approximate values
   uint32_t* jidx = vals + maxc;                                           // [maxc] candidate bins
   int32_t* sel = reinterpret_cast<int32_t*>(jidx + maxc);                 // [RR_MAXM]
-  int32_t* plan = sel + RR_MAXM;
+  float* selv = reinterpret_cast<float*>(sel + RR_MAXM);                  // [RR_MAXM] approximate values of the selected
+  int32_t* plan = sel + 2 * RR_MAXM;
   // LEAF: leaf descriptors and the per-candidate leaf sums [RR_MAXM][nleaves] follow the plan
   int32_t* leaf_s = plan + ((3 * plan_len + 3) & ~3);
   // vals / jidx are dead once `sel` is built: the exact (distance, position) pairs reuse the space
@@ -520,6 +544,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   __shared__ int s_cs, s_ce;
   __shared__ float s_cut;
   __shared__ uint32_t s_vk, s_mn, s_mx;
+  __shared__ unsigned long long s_ub;
 
   const int tid = threadIdx.x;
   const int64_t lrow = blockIdx.x;
@@ -624,34 +649,86 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   __syncthreads();
   double bound = 1e300, eps = 0.0;
+  bool eps_ok = true;
+  const bool meas = pv.normres != nullptr;
+  const double an = (double)pv.norm[row];
+  const double ra = meas ? (double)pv.normres[row].y : -1.0;
   if (tot > k) {
     const float vk = key_f32_(s_vk);
-    const double an = (double)pv.norm[row];
     const double D = fmax((double)vk + an, 0.0);
-    eps = approx_eps(an, D, pv.k_pad, (double)pv.abs_err);
+    const double rho = meas ? (double)pv.rho_max[0] : 0.0;
+    // eps must hold for the approximate top-k (d~ <= D) AND for the exact top-k (d <= D + eps): fixed point from 1.02 D
+    double Dq = D * 1.02 + 1e-300;
+    for (int it = 0; it < 4; it++) {
+      eps = approx_eps(an, Dq, pv.k_pad, (double)pv.abs_err, ra, rho);
+      if (D + eps <= Dq) break;
+      Dq = (D + eps) * 1.05;
+    }
+    eps_ok = D + eps <= Dq;  // false also for NaN
     bound = (double)vk + 2.0 * eps;
   }
   // every unlisted candidate has v >= cut: the prefix {v <= bound} must lie strictly below it
-  if (!((double)cut > bound)) {
+  if (!eps_ok || !((double)cut > bound)) {
     if (tid == 0) fail_flags[lrow] = 2;
     for (int t = tid; t < k; t += RR_THREADS) oi[t] = 0;  // valid until exact_rows rewrites the row
     return;
   }
   // select the candidates with v <= bound
+  if (tid == 0) s_ub = 0ull;
   for (int i = tid; i < tot; i += RR_THREADS) {
-    if ((double)key_f32_(vals[i]) <= bound) {
+    const float v = key_f32_(vals[i]);
+    if ((double)v <= bound) {
       const int p = atomicAdd(&s_m, 1);
-      if (p < RR_MAXM) sel[p] = (int32_t)jidx[i];
+      if (p < RR_MAXM) { sel[p] = (int32_t)jidx[i]; selv[p] = v; }
     }
   }
   __syncthreads();
-  const int m = s_m;
-  if (tid == 0 && cv.diag) { atomicAdd(cv.diag + 4, m); atomicAdd(cv.diag + 5, tot >> 4); }
+  int m = s_m;
   if (m > RR_MAXM) {
     if (tid == 0) fail_flags[lrow] = 3;
     for (int t = tid; t < k; t += RR_THREADS) oi[t] = 0;  // valid until exact_rows rewrites the row
     return;
   }
+  if (meas && tot > k) {
+    // Per-candidate refinement.  With eps_j >= |v_j - (d_j - |a|^2)| for every selected j: the >= k candidates with
+    // v_j <= v_(k) all have d_j - |a|^2 <= U = max(v_j + eps_j) over them, so d_(k) - |a|^2 <= U, and a member of the
+    // exact top-k has v_j - eps_j <= d_j - |a|^2 <= U.  The exact top-k lies inside the selection (bound above), so
+    // only the selected candidates with v_j - eps_j <= U need their exact distance.
+    const float vk = key_f32_(s_vk);
+    int jj[RR_MAXM / RR_THREADS];
+    double lo[RR_MAXM / RR_THREADS];
+    double umax = -1e300;
+#pragma unroll
+    for (int e = 0; e < RR_MAXM / RR_THREADS; e++) {
+      const int i = tid + e * RR_THREADS;
+      jj[e] = -1;
+      lo[e] = 0.0;
+      if (i < m) {
+        const int j = sel[i];
+        const float v = selv[i];
+        const float2 nr = __ldg(pv.normres + j);
+        const double ej = cand_eps(an, ra, nr, (double)v, pv.k_pad, (double)pv.abs_err);
+        jj[e] = j;
+        lo[e] = (double)v - ej;
+        if (v <= vk) umax = fmax(umax, (double)v + ej);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    if ((tid & 31) == 0) atomicMax(&s_ub, f64_key(umax));
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();  // all reads of sel are done
+    const uint64_t ubk = s_ub;
+    const uint64_t ubu = (ubk & 0x8000000000000000ull) ? (ubk & 0x7fffffffffffffffull) : ~ubk;
+    const double U = __longlong_as_double((long long)ubu);
+#pragma unroll
+    for (int e = 0; e < RR_MAXM / RR_THREADS; e++) {
+      if (jj[e] >= 0 && !(lo[e] > U)) sel[atomicAdd(&s_cnt, 1)] = jj[e];
+    }
+    __syncthreads();
+    m = s_cnt;
+  }
+  if (tid == 0 && cv.diag) { atomicAdd(cv.diag + 4, m); atomicAdd(cv.diag + 5, tot >> 4); }
 
   if (LEAF) {
     // exact distances, leaf-major (leaf_pass); candidates in batches whose leaf sums fit leafres
@@ -705,7 +782,6 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     const uint64_t kk = keys[k - 1];
     const uint64_t u = (kk & 0x8000000000000000ull) ? (kk & 0x7fffffffffffffffull) : ~kk;
     const double dk = __longlong_as_double((long long)u) * (pv.scale ? pv.scale[1] : 1.0);  // into the units of the list values
-    const double an = (double)pv.norm[row];
     if (!(dk - an + eps < bound)) s_fail = 1;
   }
   __syncthreads();
@@ -741,7 +817,7 @@ int launch_rerank(const double* x, const PrepView& pv, CandView cv, int32_t nlis
   // row-major gather of quads
   const bool leaf = xp != nullptr && nleaves >= 1 && nleaves <= 8;
   const int row_len = leaf ? sp : pv.s;
-  size_t smem = sizeof(double) * ((row_len + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 4 + sizeof(int32_t) * ((3 * plan_len + 3) & ~3);
+  size_t smem = sizeof(double) * ((row_len + 1) & ~1) + (size_t)maxc * 8 + RR_MAXM * 8 + sizeof(int32_t) * ((3 * plan_len + 3) & ~3);
   if (leaf) smem += sizeof(int32_t) * 4 * nleaves;
   const bool vec = (pv.s % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   static size_t attr[3] = {0, 0, 0};

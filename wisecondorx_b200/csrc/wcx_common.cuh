@@ -53,6 +53,10 @@ struct PrepView {
   const double* scale;
   float abs_err;       // per-element absolute rounding error bound of the operand conversion (scaled units)
   int32_t f16;
+  // f16 operands: measured conversion residuals.  normres[row] = (norm[row], |x_row - x^_row| rounded up); rho_max[0] =
+  // max over the finite rows of (|x - x^| - tau) / |x^|, tau = 2 sqrt(k_pad) abs_err.  nullptr: worst-case unit round-off.
+  const float2* normres;
+  const float* rho_max;
 };
 
 struct CandView {
@@ -69,8 +73,8 @@ int launch_center_round(const double* x, int64_t n, int32_t s, const double* col
                         float* xc, float* norm, int64_t n_pad, int32_t k_pad, cudaStream_t st);
 // f16 operands: scale[0] = power of two that maps max|x| + max|mean| below 2^14, scale[1] = its square
 int launch_center_round_f16(const double* x, int64_t n, int32_t s, const double* colsum, const double* colcnt,
-                            const unsigned long long* absmax, double* scale, void* xh, float* norm, int64_t n_pad,
-                            int32_t k_pad, cudaStream_t st);
+                            const unsigned long long* absmax, double* scale, void* xh, float* norm, float2* normres,
+                            float* rho_max, double tau, int64_t n_pad, int32_t k_pad, cudaStream_t st);
 int launch_transpose_cols(const double* x, int64_t n, int32_t s, const int32_t* ids, int32_t m,
                           double* xt, cudaStream_t st);
 int launch_dist_topk_simt(const PrepView& pv, const WorkItem* items, int32_t nitems, CandView cv,
