@@ -24,6 +24,10 @@ except Exception as e:
     print("$S failed:", e); print(open("gpurun_out/${TAG}_${S}.err").read()[-1500:])
 PYEOF
       ;;
+    cli|cli_prof) echo "=== command line at config 3 ($S)"
+      EXTRA=""; [ $S == cli_prof ] && EXTRA="--cprofile"
+      timeout 400 python tools/newref_cli_wallclock.py --predict $EXTRA </dev/null 2>gpurun_out/${TAG}_${S}.err | tail -1 | tee gpurun_out/${TAG}_${S}.json | cut -c1-900
+      [ $S == cli_prof ] && grep -A50 "cumulative" gpurun_out/${TAG}_${S}.err | cut -c1-150 | head -60 ;;
     benchref) echo "=== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>>gpurun_out/${TAG}_bench.err | tail -1 | tee gpurun_out/${TAG}_bench_reference.json | cut -c1-600 ;;
     launches) echo "=== ncu launch list"
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1

@@ -20,6 +20,7 @@ def run():
     ap.add_argument("--samples", type=int, default=500)
     ap.add_argument("--binsize", type=int, default=15000)
     ap.add_argument("--predict", action="store_true")
+    ap.add_argument("--cprofile", action="store_true", help="print the cumulative host profile of the newref call to stderr")
     ap.add_argument("--keep", default=None, help="directory to keep the files in (default: a temp dir)")
     a = ap.parse_args()
     d = a.keep or tempfile.mkdtemp(prefix="wcx_cli_")
@@ -36,8 +37,16 @@ def run():
     ref = os.path.join(d, "reference.npz")
     t0 = time.perf_counter()
     args = wmain.build_parser().parse_args(["newref"] + paths[: a.samples] + [ref, "--binsize", str(a.binsize), "--yfrac", "0.006"])
-    timings = args.func(args)
-    t_newref = time.perf_counter() - t0
+    if a.cprofile:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        timings = pr.runcall(args.func, args)
+        t_newref = time.perf_counter() - t0
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
+    else:
+        timings = args.func(args)
+        t_newref = time.perf_counter() - t0
     out = {"samples": a.samples, "binsize": a.binsize, "generate_inputs_s": round(t_gen, 2), "newref_wall_s": round(t_newref, 2),
            "stages_s": {k: round(v, 3) for k, v in (timings or {}).items()}, "reference_npz_mb": os.path.getsize(ref) >> 20}
     if a.predict:

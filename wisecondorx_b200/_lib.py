@@ -116,12 +116,14 @@ class Context:
 
 
 _default_ctx = {}
+_ctx_lock = __import__("threading").RLock()
 
 
 def default_context(device: int = 0) -> Context:
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
+    with _ctx_lock:
+        if device not in _default_ctx:
+            _default_ctx[device] = Context(device)
+        return _default_ctx[device]
 
 
 class PinnedPool:
@@ -130,23 +132,42 @@ class PinnedPool:
     cudaHostAlloc itself costs ~0.1-0.3 ms per MB, more than the copy it speeds up."""
 
     GRAIN = 1 << 20
+    SLACK = 1.25  # a free buffer up to this factor larger than the request is reused (reserve() sizes are upper bounds)
 
     def __init__(self):
         self._free = {}
+
+    def _size(self, nbytes):
+        return max(self.GRAIN, (nbytes + self.GRAIN - 1) // self.GRAIN * self.GRAIN)
+
+    def _alloc(self, size):
+        p = ctypes.c_void_p()
+        check(load().wcx_host_alloc(size, ctypes.byref(p)))
+        return p.value
+
+    def reserve(self, nbytes):
+        """Page-locks a buffer of at least nbytes ahead of its use (e.g. from a background thread while the host is
+        busy with something else) and leaves it in the pool."""
+        size = self._size(int(nbytes))
+        self._free.setdefault(size, []).append(self._alloc(size))
 
     def empty(self, shape, dtype=None):
         import weakref
         import numpy as np
         dtype = np.dtype(dtype or np.float64)
         nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        size = max(self.GRAIN, (nbytes + self.GRAIN - 1) // self.GRAIN * self.GRAIN)
+        size = self._size(nbytes)
+        ptr = None
+        for have in sorted(self._free):
+            if have >= size and have <= size * self.SLACK and self._free[have]:
+                try:
+                    ptr, size = self._free[have].pop(), have
+                    break
+                except IndexError:  # another thread took it
+                    continue
+        if ptr is None:
+            ptr = self._alloc(size)
         lst = self._free.setdefault(size, [])
-        if lst:
-            ptr = lst.pop()
-        else:
-            p = ctypes.c_void_p()
-            check(load().wcx_host_alloc(size, ctypes.byref(p)))
-            ptr = p.value
         buf = (ctypes.c_char * size).from_address(ptr)
         weakref.finalize(buf, lst.append, ptr)
         return np.frombuffer(buf, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
@@ -160,3 +181,24 @@ class PinnedPool:
 
 
 pinned = PinnedPool()
+
+
+def prewarm_async(device: int = 0, pinned_bytes=()):
+    """Creates the CUDA context of `device` and page-locks result buffers on a background thread, so that a command
+    line that starts with seconds of host-only work (reading samples, masks) does not pay for them on its critical
+    path.  Returns the thread (join() is optional: default_context / pinned.empty are safe to call concurrently --
+    the context is created once under a lock, a buffer that is not there yet is simply allocated by the caller)."""
+    import threading
+
+    def work():
+        try:
+            with _ctx_lock:
+                default_context(device)
+            for nb in pinned_bytes:
+                pinned.reserve(nb)
+        except Exception:  # the foreground call will raise the real error
+            pass
+
+    t = threading.Thread(target=work, name="wcx-prewarm", daemon=True)
+    t.start()
+    return t

@@ -51,8 +51,23 @@ def _member_blocks(header: bytes, data):
     return blocks, total
 
 
+def _store_ratio() -> float:
+    try:
+        return float(os.environ.get("WCX_NPZ_STORE_RATIO", "0.85"))
+    except ValueError:
+        return 0.85
+
+
 def _deflate_block(args):
+    """One independently deflated block.  A block whose first 64 KB do not shrink below WCX_NPZ_STORE_RATIO (0.85) at
+    level 1 is emitted as stored deflate blocks (level 0): the float64 distances and null ratios of a reference file
+    only compress to 0.90 / 0.96, and deflating them was the critical path of `newref` (34 core-seconds at 15 kb).  It
+    is still an ordinary deflate stream for every reader.  Ratio >= 1 disables the test."""
     buf, last, level = args
+    if level > 0 and len(buf) >= (1 << 16):
+        ratio = _store_ratio()
+        if ratio < 1.0 and len(zlib.compress(buf[:1 << 16], 1)) > ratio * (1 << 16):
+            level = 0
     c = zlib.compressobj(level, zlib.DEFLATED, -15)
     out = c.compress(buf)
     out += c.flush(zlib.Z_FINISH if last else zlib.Z_FULL_FLUSH)
@@ -98,12 +113,25 @@ def _be_nice():
         pass
 
 
+def default_level() -> int:
+    """Deflate level of the reference files written by `newref`.  np.savez_compressed (the reference,
+    newref_control.py:237) uses zlib's default, 6; on the arrays of a reference file -- float64 distances and null
+    ratios, int32 indexes -- level 1 gives the same compression ratio to within 1 % (0.90 / 0.96 / 0.71) at 1.3x / 1.2x /
+    7x the speed, and the stream is read by np.load exactly like any other.  WCX_NPZ_LEVEL=6 restores NumPy's level."""
+    try:
+        return max(0, min(9, int(os.environ.get("WCX_NPZ_LEVEL", "1"))))
+    except ValueError:
+        return 1
+
+
 class AsyncNpzWriter:
     """savez_compressed in two halves: add(name, array) starts deflating the array on the pool right away (the caller
     goes on computing -- zlib and the CUDA library both release the GIL), close() waits and writes the archive.
     The arrays must not be modified between add() and close().  Same on-disk format as savez_compressed."""
 
-    def __init__(self, file, threads: int | None = None, level: int = 6):
+    def __init__(self, file, threads: int | None = None, level: int | None = None):
+        if level is None:
+            level = default_level()
         if isinstance(file, (str, os.PathLike)):
             file = os.fspath(file)
             if not file.endswith(".npz"):
@@ -114,29 +142,51 @@ class AsyncNpzWriter:
         # background work: the deflate threads run at a lower scheduling priority than the caller, whose host work
         # (NumPy, LAPACK, the next pass's preparation) shares the cores with them
         self.pool = ThreadPoolExecutor(threads or max(1, min(32, len(os.sched_getaffinity(0)) - 2)), initializer=_be_nice)
-        self.members = []  # (name, usize, [futures], keep-alive)
+        # members go to the file in add() order as soon as their blocks are deflated: a writer thread follows the
+        # queue, so that close() only has the tail of the last pass and the central directory left
+        import queue
+        import threading
+        self._q = queue.Queue()
+        self._central = []
+        self._error = None
+        self._fh = open(self.file, "wb")
+        self._thread = threading.Thread(target=self._drain, name="wcx-npz-writer", daemon=True)
+        self._thread.start()
+
+    def _drain(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            if self._error is not None:
+                continue  # keep consuming so that close() never blocks
+            try:
+                name, usize, futs, _keep = item
+                blocks = [f.result() for f in futs]
+                crc = 0
+                for _, c, ln in blocks:
+                    crc = _crc32_combine(crc, c, ln)
+                csize = sum(len(b[0]) for b in blocks)
+                self._central.append(_write_member(self._fh, name, blocks, crc, csize, usize))
+            except BaseException as e:  # re-raised by close()
+                self._error = e
 
     def add(self, name, array):
         header, data = _npy_parts(array)
         blocks, total = _member_blocks(header, data)
         futs = [self.pool.submit(_deflate_block, (blk, b == len(blocks) - 1, self.level)) for b, blk in enumerate(blocks)]
-        self.members.append((name + ".npy", total, futs, (array, data)))
+        self._q.put((name + ".npy", total, futs, (array, data)))
 
     def close(self):
         try:
-            with open(self.file, "wb") as fh:
-                central = []
-                for name, usize, futs, _ in self.members:
-                    blocks = [f.result() for f in futs]
-                    crc = 0
-                    for _, c, ln in blocks:
-                        crc = _crc32_combine(crc, c, ln)
-                    csize = sum(len(b[0]) for b in blocks)
-                    central.append(_write_member(fh, name, blocks, crc, csize, usize))
-                _write_central_directory(fh, central)
+            self._q.put(None)
+            self._thread.join()
+            if self._error is not None:
+                raise self._error
+            _write_central_directory(self._fh, self._central)
         finally:
+            self._fh.close()
             self.pool.shutdown(wait=True)
-            self.members = []
 
 
 def _write_member(fh, name, blocks, crc, csize, usize):
@@ -207,26 +257,39 @@ def _gf2_square(mat):
     return [_gf2_times(mat, mat[i]) for i in range(32)]
 
 
+def _gf2_mul(a, b):
+    """matrix product a . b (columns of b mapped through a)"""
+    return [_gf2_times(a, b[i]) for i in range(32)]
+
+
+_CRC_SHIFT = {}  # len2 -> operator that advances a crc over len2 zero bytes
+
+
+def _crc_shift_matrix(len2):
+    """All blocks of a member but the last have one length, so the operator is built once per distinct length (the
+    squaring chain is ~5 ms of pure Python; per block it added up to most of the final write of a 1 GB reference)."""
+    m = _CRC_SHIFT.get(len2)
+    if m is None:
+        p = [0xEDB88320] + [1 << i for i in range(31)]  # one zero bit
+        for _ in range(3):
+            p = _gf2_square(p)                          # one zero byte
+        m = [1 << i for i in range(32)]                 # identity
+        n = len2
+        while n:
+            if n & 1:
+                m = _gf2_mul(p, m)
+            n >>= 1
+            if n:
+                p = _gf2_square(p)
+        if len(_CRC_SHIFT) < 4096:
+            _CRC_SHIFT[len2] = m
+    return m
+
+
 def _crc32_combine(crc1, crc2, len2):
     if len2 <= 0:
         return crc1
-    odd = [0xEDB88320] + [1 << i for i in range(31)]  # operator for one zero bit
-    even = _gf2_square(odd)   # two zero bits
-    odd = _gf2_square(even)   # four zero bits
-    while True:
-        even = _gf2_square(odd)
-        if len2 & 1:
-            crc1 = _gf2_times(even, crc1)
-        len2 >>= 1
-        if not len2:
-            break
-        odd = _gf2_square(even)
-        if len2 & 1:
-            crc1 = _gf2_times(odd, crc1)
-        len2 >>= 1
-        if not len2:
-            break
-    return crc1 ^ crc2
+    return _gf2_times(_crc_shift_matrix(len2), crc1) ^ crc2
 
 
 def load_samples(paths, threads: int | None = None):
