@@ -203,6 +203,13 @@ int wcx_predict_stage_ms(wcx_ctx* ctx, double* out8);
 int wcx_cbs_segment(wcx_ctx* ctx, const double* y, const double* w, const int64_t* off, int32_t nseries,
                     const int32_t* series_ids, double alpha, int32_t nperm, uint32_t seed,
                     int32_t* ends_out, int32_t* nseg_out);
+/* Sequential stopping boundary of the permutation tests: DNAcopy's segment() passes sbdry = getbdry(eta = 0.05, nperm,
+ * max.ones = floor(nperm * alpha) + 1) to its change-point finder, which declares a test significant as soon as the
+ * number of permutations done reaches sbdry[nrejc (nrejc + 1) / 2 + nrej] (nrej exceedances so far, nrejc tolerated).
+ * The table is host int32 [n]; it stays in the context for the following wcx_cbs_segment calls.  n = 0 (the state of a
+ * fresh context): every test runs all nperm permutations and counts. */
+int wcx_cbs_set_boundary(wcx_ctx* ctx, const int32_t* sbdry, int32_t n);
+
 /* Counters of the last wcx_cbs_segment: rounds, segments tested, permutation tests, edge t-tests
  * with permutations, permutations evaluated, kernel launches. */
 int wcx_cbs_stats(wcx_ctx* ctx, int64_t* out6);

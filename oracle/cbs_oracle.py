@@ -22,9 +22,13 @@ bit for bit (same counter-based RNG, same arithmetic order).
 Deliberate, documented differences from DNAcopy:
   * R's Mersenne-Twister stream cannot be reproduced; permutations use Philox4x32-10 keyed by
     (seed, segment start, segment end, test id, permutation index).
-  * DNAcopy stops a permutation test early through a sequential boundary (``getbdry``, eta=0.05);
-    here all nperm permutations are (conceptually) evaluated and the decision is
-    ``#exceedances <= nrejc`` -- the exact test the boundary approximates.
+  * DNAcopy's sequential boundary (``getbdry``, eta = 0.05: a test is declared significant as soon as the
+    number of permutations seen without the (j + 1)-th exceedance reaches ``sbdry``) is restated from the
+    description in Venkatraman & Olshen 2007 and the structure of ``segment()`` (``max.ones = floor(nperm *
+    alpha) + 1``, triangular table indexed by ``nrejc * (nrejc + 1) / 2 + nrej``) with EXACT hypergeometric
+    crossing probabilities (`seq_boundary`); DNAcopy approximates them beyond three exceedances, so for
+    alpha >= 3 / nperm a boundary value may differ by a permutation or two.  ``sequential=False`` gives the
+    plain count ``#exceedances <= nrejc`` over all nperm permutations.
   * the maximal statistic is found by brute force over all arcs (DNAcopy uses a block algorithm
     with the same result); ties resolve to the smallest (start, end).
 All sums are sequential left-to-right (np.cumsum), no pairwise summation, so the CUDA kernels can
@@ -235,7 +239,93 @@ def t_perm_p(x, ws, rw, n1, n2, alpha_nperm, seed, test, lo, hi):
     return nrej / float(nperm)
 
 
-def find_cpt(xs, ws, alpha, nperm, kmax, nmin, min_width, seed, lo, hi, stats=None):
+# ---------------------------------------------------------------------------------------------
+# sequential stopping boundary of the permutation test (DNAcopy getbdry / etabdry / pexceed)
+# ---------------------------------------------------------------------------------------------
+def _log_choose(n, k):
+    if k < 0 or k > n:
+        return -math.inf
+    return math.lgamma(n + 1.0) - math.lgamma(k + 1.0) - math.lgamma(n - k + 1.0)
+
+
+def _phyper_le(k, m, nperm, i):
+    """P(at most k of the m exceedances fall among the first i of nperm permutations)."""
+    den = _log_choose(nperm, i)
+    return float(sum(math.exp(_log_choose(m, x) + _log_choose(nperm - m, i - x) - den) for x in range(0, min(k, m, i) + 1)))
+
+
+def _eta_boundary(nperm, eta0, m):
+    """etabdry: b[k] = first i with P(<= k exceedances among the first i | m in total) <= eta0, k = 0 .. m - 1."""
+    b, lo = [], 1
+    for k in range(m):
+        a, z = lo, nperm  # P is non-increasing in i: bisection for the first i <= eta0
+        if _phyper_le(k, m, nperm, z) > eta0:
+            b.append(nperm)
+            lo = nperm
+            continue
+        while a < z:
+            mid = (a + z) // 2
+            if _phyper_le(k, m, nperm, mid) <= eta0:
+                z = mid
+            else:
+                a = mid + 1
+        b.append(a)
+        lo = min(nperm, a + 1)  # the Fortran loop advances i once per boundary
+    return b
+
+
+def _p_exceed(nperm, m, b):
+    """pexceed: probability that m exceedances placed uniformly among nperm permutations let the test stop early,
+    i.e. that for some k the (k + 1)-th exceedance comes after permutation b[k].  Exact (counting the placements
+    t_1 < ... < t_m with t_k <= b[k] for all k)."""
+    ways = np.zeros(nperm + 1)  # ways[t]: placements of the first k exceedances with t_k = t (scaled)
+    cum = np.ones(nperm + 1)    # k = 0: one empty placement "ending" at every t >= 0
+    log_scale = 0.0
+    for k in range(m):
+        ways[:] = 0.0
+        ways[1:b[k] + 1] = cum[0:b[k]]
+        cum = np.cumsum(ways)
+        top = cum[-1]
+        if top <= 0.0:
+            return 1.0
+        cum /= top
+        log_scale += math.log(top)
+    return 1.0 - math.exp(log_scale - _log_choose(nperm, m))
+
+
+_SEQ_BOUNDARY = {}
+
+
+def seq_boundary(eta, nperm, max_ones, tol=1e-2):
+    """getbdry: triangular table; row j (1-based, j exceedances allowed to decide 'not significant', i.e.
+    nrejc = j - 1) starts at j (j - 1) / 2 and holds j permutation counts."""
+    key = (eta, nperm, max_ones, tol)
+    if key in _SEQ_BOUNDARY:
+        return _SEQ_BOUNDARY[key]
+    out = [nperm - int(nperm * eta)]
+    eta0 = eta
+    for j in range(2, max_ones + 1):
+        etahi = eta0 * 1.1
+        bh = _eta_boundary(nperm, etahi, j)
+        phi = _p_exceed(nperm, j, bh)
+        etalo = eta0 * 0.25
+        bl = _eta_boundary(nperm, etalo, j)
+        plo = _p_exceed(nperm, j, bl)
+        b = bl
+        while (etahi - etalo) / etalo > tol:
+            eta0 = etalo + (etahi - etalo) * (eta - plo) / (phi - plo)
+            b = _eta_boundary(nperm, eta0, j)
+            pe = _p_exceed(nperm, j, b)
+            if pe > eta:
+                etahi, phi = eta0, pe
+            else:
+                etalo, plo = eta0, pe
+        out.extend(b)
+    _SEQ_BOUNDARY[key] = out
+    return out
+
+
+def find_cpt(xs, ws, alpha, nperm, kmax, nmin, min_width, seed, lo, hi, stats=None, sbdry=None):
     """One call of DNAcopy's weighted change-point finder on a segment -> list of change points
     (offsets inside the segment)."""
     n = len(xs)
@@ -277,12 +367,16 @@ def find_cpt(xs, ws, alpha, nperm, kmax, nmin, min_width, seed, lo, hi, stats=No
             nrejc = int(alpha * float(nperm))
             mw = None
         nrej = 0
+        k0 = nrejc * (nrejc + 1) // 2  # row of the boundary table for this rejection count
+        use_bdry = sbdry is not None and k0 + nrejc < len(sbdry)
         for p in range(nperm):
             px = perm_values(y, rw, PermStream(seed, 0, lo, hi, p))
             if ostat <= perm_stat(px, ws, cw, tss_y, n, min_width, mw, tot_w, rtw):
                 nrej += 1
                 if nrej > nrejc:
                     return []
+            if use_bdry and p + 1 >= sbdry[k0 + nrej]:
+                break  # significant: the remaining permutations cannot change the decision but with probability eta
     if i2 == n:
         return [i1]
     if i1 == 0:
@@ -296,7 +390,7 @@ def find_cpt(xs, ws, alpha, nperm, kmax, nmin, min_width, seed, lo, hi, stats=No
 
 
 def segment_chromosome(y, w, alpha=1e-4, nperm=10000, kmax=25, nmin=200, min_width=2, seed=0, chrom=0,
-                       stats=None):
+                       stats=None, sequential=True, eta=0.05):
     """DNAcopy `changepoints` on the non-NA values of one chromosome -> segment end positions
     (exclusive, in the compacted index space) in ascending order."""
     y = np.asarray(y, dtype=np.float64)
@@ -305,9 +399,10 @@ def segment_chromosome(y, w, alpha=1e-4, nperm=10000, kmax=25, nmin=200, min_wid
     ends = []
     stack = [(0, n)]
     s = (seed * 1000003 + chrom) & _MASK
+    sbdry = seq_boundary(eta, nperm, int(math.floor(nperm * alpha)) + 1) if sequential else None  # segment(): max.ones
     while stack:
         lo, hi = stack.pop()
-        cpts = find_cpt(y[lo:hi], w[lo:hi], alpha, nperm, kmax, nmin, min_width, s, lo, hi, stats)
+        cpts = find_cpt(y[lo:hi], w[lo:hi], alpha, nperm, kmax, nmin, min_width, s, lo, hi, stats, sbdry)
         if not cpts:
             ends.append(hi)
         else:

@@ -49,6 +49,23 @@ def test_permutation_paths_equal_oracle():
         assert g.tolist() == want, (c, g.tolist(), want)
 
 
+def test_sequential_boundary_rule_equals_oracle():
+    """DNAcopy's early-stopping boundary (wcx_cbs_set_boundary) with several tolerated exceedances (alpha * nperm = 8:
+    rows 1 .. 9 of the table) and without it: the same decisions as the sequential loop of the oracle, and the two
+    rules are allowed to differ from each other only by construction."""
+    rng = np.random.default_rng(14)
+    series = []
+    for n, a, b, h in [(180, 60, 100, 0.03), (180, 60, 100, 0.04), (150, 60, 75, 0.05), (150, 60, 75, 0.06), (190, 20, 60, 0.035),
+                       (120, 5, 20, 0.06), (199, 90, 110, 0.05), (500, 200, 230, 0.04), (900, 300, 340, 0.03)]:
+        series.append(_series(rng, n, [(a, b, h)]))
+    for sequential in (True, False):
+        got = cbs.segment_series(series, alpha=0.02, nperm=400, seed=3, sequential=sequential)
+        assert cbs.cbs_stats()["perm_tests"] > 0
+        for c, ((y, w), g) in enumerate(zip(series, got)):
+            want = C.segment_chromosome(y, w, alpha=0.02, nperm=400, seed=3, chrom=c, sequential=sequential)
+            assert g.tolist() == want, (sequential, c, g.tolist(), want)
+
+
 def test_noise_and_planted():
     rng = np.random.default_rng(13)
     noise = [_series(rng, n, []) for n in (60, 190, 1000, 4000)]

@@ -88,3 +88,21 @@ def test_example_bed_chr21_gain(golden_dir):
     got = {(d["chr"], d["s"], d["e"]) for d in out}
     ref = {(int(s[0]), int(s[1]), int(s[2])) for s in g["segments"] if int(s[0]) <= 23}
     assert got == ref, (sorted(ref - got), sorted(got - ref))
+
+
+def test_sequential_boundary_table():
+    """getbdry restated (oracle) == the product's table (wisecondorx_b200.cbs.sequential_boundary); structure of the
+    table: first entry nperm - int(nperm * eta), rows ascending, the early-stop probability of every row about eta."""
+    from wisecondorx_b200 import cbs
+    for eta, nperm, ones in [(0.05, 10000, 2), (0.05, 10000, 5), (0.05, 400, 9), (0.1, 1000, 3)]:
+        t = C.seq_boundary(eta, nperm, ones)
+        assert t == cbs.sequential_boundary(eta, nperm, ones).tolist()
+        assert len(t) == ones * (ones + 1) // 2 and t[0] == nperm - int(nperm * eta)
+        for j in range(1, ones + 1):
+            row = t[j * (j - 1) // 2: j * (j + 1) // 2]
+            assert row == sorted(row) and 1 <= row[0] and row[-1] <= nperm
+            assert abs(C._p_exceed(nperm, j, row) - eta) < 0.02
+    # closed form for one tolerated exceedance (two ones): C(N - b1, 2) + b1 (N - b2) placements stop early
+    from math import comb
+    b1, b2 = C.seq_boundary(0.05, 10000, 2)[1:]
+    assert abs((comb(10000 - b1, 2) + b1 * (10000 - b2)) / comb(10000, 2) - C._p_exceed(10000, 2, [b1, b2])) < 1e-9

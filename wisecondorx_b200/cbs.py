@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import logging
+import math
 
 import numpy as np
 
@@ -17,11 +18,99 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
-def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx: _lib.Context | None = None):
+# ---------------------------------------------------------------------------------------------
+# DNAcopy's sequential stopping boundary: segment() hands `sbdry = getbdry(eta, nperm, max.ones)` (eta = 0.05,
+# max.ones = floor(nperm * alpha) + 1) to the change-point finder.  Row j of the triangular table (nrejc = j - 1
+# tolerated exceedances) holds the permutation counts b_0 <= ... <= b_{j-1}: with k exceedances seen, the test is
+# declared significant once b_k permutations are done.  The b_k of a row share one per-boundary level eta0
+# (b_k = first i with P(at most k of j exceedances among the first i of nperm) <= eta0, a hypergeometric tail) and eta0 is
+# tuned until the probability of stopping early although j exceedances exist equals eta.  Restated from Venkatraman &
+# Olshen 2007 with exact crossing probabilities; the R / Fortran sources are not available here (see oracle/cbs_oracle.py).
+# ---------------------------------------------------------------------------------------------
+_BOUNDARY_CACHE = {}
+
+
+def _lchoose(n, k):
+    if k < 0 or k > n:
+        return -math.inf
+    return math.lgamma(n + 1.0) - math.lgamma(k + 1.0) - math.lgamma(n - k + 1.0)
+
+
+def _hyper_cdf(k, ones, nperm, i):
+    den = _lchoose(nperm, i)
+    return float(sum(math.exp(_lchoose(ones, x) + _lchoose(nperm - ones, i - x) - den) for x in range(min(k, ones, i) + 1)))
+
+
+def _row_for_level(nperm, eta0, ones):
+    row, start = [], 1
+    for k in range(ones):
+        if _hyper_cdf(k, ones, nperm, nperm) > eta0:
+            row.append(nperm)
+            start = nperm
+            continue
+        a, z = start, nperm
+        while a < z:  # the tail probability falls with i
+            mid = (a + z) // 2
+            if _hyper_cdf(k, ones, nperm, mid) <= eta0:
+                z = mid
+            else:
+                a = mid + 1
+        row.append(a)
+        start = min(nperm, a + 1)
+    return row
+
+
+def _early_stop_probability(nperm, ones, row):
+    """P(some exceedance k + 1 of `ones` uniformly placed ones comes after permutation row[k])."""
+    cum = np.ones(nperm + 1)
+    log_scale = 0.0
+    for k in range(ones):
+        ways = np.zeros(nperm + 1)
+        ways[1:row[k] + 1] = cum[0:row[k]]
+        cum = np.cumsum(ways)
+        if cum[-1] <= 0.0:
+            return 1.0
+        log_scale += math.log(cum[-1])
+        cum /= cum[-1]
+    return 1.0 - math.exp(log_scale - _lchoose(nperm, ones))
+
+
+def sequential_boundary(eta, nperm, max_ones, tol=1e-2):
+    key = (float(eta), int(nperm), int(max_ones), float(tol))
+    if key not in _BOUNDARY_CACHE:
+        table = [nperm - int(nperm * eta)]
+        level = eta
+        for ones in range(2, max_ones + 1):
+            hi = level * 1.1
+            p_hi = _early_stop_probability(nperm, ones, _row_for_level(nperm, hi, ones))
+            lo = level * 0.25
+            row = _row_for_level(nperm, lo, ones)
+            p_lo = _early_stop_probability(nperm, ones, row)
+            while (hi - lo) / lo > tol:
+                level = lo + (hi - lo) * (eta - p_lo) / (p_hi - p_lo)
+                row = _row_for_level(nperm, level, ones)
+                p = _early_stop_probability(nperm, ones, row)
+                if p > eta:
+                    hi, p_hi = level, p
+                else:
+                    lo, p_lo = level, p
+            table.extend(row)
+        _BOUNDARY_CACHE[key] = np.ascontiguousarray(table, dtype=np.int32)
+    return _BOUNDARY_CACHE[key]
+
+
+def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx: _lib.Context | None = None,
+                   sequential: bool = True, eta: float = 0.05):
     """Segments a batch of NA-free (y, w) series on the GPU.  Returns a list of int32 arrays with
-    the ascending exclusive segment ends of each series."""
+    the ascending exclusive segment ends of each series.  sequential: DNAcopy's early-stopping decision rule
+    (default, as in segment()); False counts the exceedances over all nperm permutations."""
     ctx = ctx or _lib.default_context(0)
     L = _lib.load()
+    if sequential:
+        table = sequential_boundary(eta, nperm, int(math.floor(nperm * alpha)) + 1)
+        _lib.check(L.wcx_cbs_set_boundary(ctx.handle, _ptr(table), len(table)))
+    else:
+        _lib.check(L.wcx_cbs_set_boundary(ctx.handle, None, 0))
     ns = len(series)
     lens = [len(y) for y, _ in series]
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)

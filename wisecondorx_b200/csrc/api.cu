@@ -1113,6 +1113,15 @@ int wcx_cbs_segment(wcx_ctx* c, const double* y, const double* w, const int64_t*
   return 0;
 }
 
+int wcx_cbs_set_boundary(wcx_ctx* c, const int32_t* sbdry, int32_t n) {
+  if (!c || n < 0 || (n > 0 && !sbdry)) { set_error("wcx_cbs_set_boundary: bad argument"); return 1; }
+  for (int i = 0; i < n; i++)
+    if (sbdry[i] < 1) { set_error("wcx_cbs_set_boundary: boundary values are permutation counts >= 1"); return 1; }
+  if (!c->cbs) c->cbs = cbs_workspace_create();
+  cbs_set_boundary(c->cbs, sbdry, n);
+  return 0;
+}
+
 int wcx_cbs_stats(wcx_ctx* c, int64_t* out6) {
   if (!c || !out6) { set_error("null argument"); return 1; }
   out6[0] = c->cbs_stats.rounds; out6[1] = c->cbs_stats.segments_tested; out6[2] = c->cbs_stats.perm_tests;

@@ -457,14 +457,19 @@ cbs_perm_arcs_kernel(const double* __restrict__ cw, const PermJob* __restrict__ 
 }
 
 __global__ void __launch_bounds__(128)
-cbs_perm_count_kernel(const PermJob* __restrict__ jobs, const double* __restrict__ scratch_all, int* __restrict__ nrej) {
+cbs_perm_count_kernel(const PermJob* __restrict__ jobs, const double* __restrict__ scratch_all, int* __restrict__ nrej,
+                      uint32_t* __restrict__ flags, int flag_words) {
   const PermJob job = jobs[blockIdx.y];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= job.nperm) return;
   const double* bestp = scratch_all + job.scratch_off + 2 * (int64_t)job.n * job.nperm;
   const double best = bestp[p], tss = bestp[job.nperm + p];
   const double pstat = best / ((tss - best) / ((double)job.n - 2.0));
-  if (job.ostat <= pstat) atomicAdd(nrej + blockIdx.y, 1);
+  if (job.ostat <= pstat) {
+    atomicAdd(nrej + blockIdx.y, 1);
+    // WHICH permutations exceed: the sequential boundary (cbs_segment) depends on their order
+    atomicOr(flags + (int64_t)blockIdx.y * flag_words + (p >> 5), 1u << (p & 31));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -673,8 +678,16 @@ struct DBuf {
 }  // namespace
 
 struct CbsWorkspace {
-  DBuf y, w, xc, sx, cw, yy, segs, prep, chunks, partial, scratch, nrej, tjobs, pjobs;
+  DBuf y, w, xc, sx, cw, yy, segs, prep, chunks, partial, scratch, nrej, tjobs, pjobs, flags;
+  std::vector<int32_t> sbdry;  // sequential stopping boundary (cbs_set_boundary); empty: plain count over all permutations
 };
+
+// DNAcopy's sequential boundary (segment(): sbdry = getbdry(eta, nperm, max.ones), a triangular table: the row for a
+// test that tolerates nrejc exceedances starts at nrejc (nrejc + 1) / 2 and holds nrejc + 1 permutation counts).  A
+// permutation test is declared significant as soon as np >= sbdry[row + nrej] (fndcpt's inner loop).
+void cbs_set_boundary(CbsWorkspace* ws, const int32_t* sbdry, int32_t n) {
+  ws->sbdry.assign(sbdry, sbdry + (n > 0 ? n : 0));
+}
 
 CbsWorkspace* cbs_workspace_create() { return new CbsWorkspace(); }
 void cbs_workspace_destroy(CbsWorkspace* ws) { delete ws; }
@@ -780,7 +793,12 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
     // decisions, part 1: gates and the hybrid p-value decide most segments; the rest need a permutation test
     std::vector<char> split_of(nseg, 0);
     std::vector<double> ostat_of(nseg, 0.0);
-    struct PermTest { int seg, nrejc, mw, nrej, done; };
+    struct PermTest {
+      int seg, nrejc, mw, nrej, done;
+      int cur = 0;           // permutations processed by the decision rule (1-based count)
+      const int32_t* bd = nullptr;  // this test's row of the boundary table (nrejc + 1 entries) or nullptr
+      int limit = 0;         // permutations after which the test is decided for certain
+    };
     std::vector<PermTest> tests;
     for (int s = 0; s < nseg; s++) {
       const int n = (int)(work[s].hi - work[s].lo);
@@ -800,6 +818,13 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
         tests.push_back(PermTest{s, (int)((alpha - pval1) * (double)nperm), kmax, 0, 0});
       } else {
         tests.push_back(PermTest{s, (int)(alpha * (double)nperm), -1, 0, 0});
+      }
+      PermTest& t = tests.back();
+      const size_t row = (size_t)t.nrejc * ((size_t)t.nrejc + 1) / 2;
+      t.limit = nperm;
+      if (row + (size_t)t.nrejc < ws->sbdry.size()) {
+        t.bd = ws->sbdry.data() + row;
+        t.limit = std::max(1, std::min(nperm, (int)t.bd[t.nrejc]));  // with nrej <= nrejc the last boundary decides
       }
     }
     // permutation tests of the whole round in escalating batches (256, 1024, then 2048 at a time): all undecided
@@ -826,7 +851,7 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
             PermTest& t = tests[active[g1]];
             const Seg& sg = work[t.seg];
             const int n = (int)(sg.hi - sg.lo);
-            const int nb = std::min(want, nperm - t.done);
+            const int nb = std::min(want, t.limit - t.done);
             const size_t need = 2 * (size_t)n * nb + 2 * (size_t)nb;
             if (!jobs.empty() && (doubles + need) * sizeof(double) > ((size_t)8 << 30)) break;  // scratch budget per launch: 8 GB of the 180
             const int32_t sid = series_ids ? series_ids[sg.series] : sg.series;
@@ -843,9 +868,13 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
             maxn = std::max(maxn, n);
           }
           const int nj = (int)jobs.size();
-          if (ws->scratch.ensure(sizeof(double) * doubles) || ws->pjobs.ensure(sizeof(PermJob) * nj) || ws->nrej.ensure(sizeof(int) * nj)) return 1;
+          const int flag_words = (maxnb + 31) / 32;
+          if (ws->scratch.ensure(sizeof(double) * doubles) || ws->pjobs.ensure(sizeof(PermJob) * nj) || ws->nrej.ensure(sizeof(int) * nj) ||
+              ws->flags.ensure(sizeof(uint32_t) * (size_t)nj * flag_words))
+            return 1;
           WCX_CUDA_OK(cudaMemcpyAsync(ws->pjobs.p, jobs.data(), sizeof(PermJob) * nj, cudaMemcpyHostToDevice, st));
           WCX_CUDA_OK(cudaMemsetAsync(ws->nrej.p, 0, sizeof(int) * nj, st));
+          WCX_CUDA_OK(cudaMemsetAsync(ws->flags.p, 0, sizeof(uint32_t) * (size_t)nj * flag_words, st));
           // shuffle in shared memory (one warp per permutation) when the index array fits, else in global memory
           const int n_stride = (maxn + 7) & ~7;
           const int fy_warps = maxn <= 65535 ? std::min(8, (200 * 1024) / (2 * n_stride)) : 0;
@@ -864,19 +893,41 @@ int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_
           }
           cbs_perm_arcs_kernel<<<dim3((maxnb + 127) / 128, (maxn + PA_ICHUNK - 1) / PA_ICHUNK, nj), 128, 0, st>>>(
               ws->cw.as<double>(), ws->pjobs.as<PermJob>(), al0, ws->scratch.as<double>());
-          cbs_perm_count_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->pjobs.as<PermJob>(), ws->scratch.as<double>(), ws->nrej.as<int>());
+          cbs_perm_count_kernel<<<dim3((maxnb + 127) / 128, nj), 128, 0, st>>>(ws->pjobs.as<PermJob>(), ws->scratch.as<double>(), ws->nrej.as<int>(),
+                                                                               ws->flags.as<uint32_t>(), flag_words);
           WCX_CUDA_OK(cudaGetLastError());
           std::vector<int> h(nj);
+          std::vector<uint32_t> hf((size_t)nj * flag_words);
           WCX_CUDA_OK(cudaMemcpyAsync(h.data(), ws->nrej.p, sizeof(int) * nj, cudaMemcpyDeviceToHost, st));
+          WCX_CUDA_OK(cudaMemcpyAsync(hf.data(), ws->flags.p, sizeof(uint32_t) * hf.size(), cudaMemcpyDeviceToHost, st));
           WCX_CUDA_OK(cudaStreamSynchronize(st));
           if (stats) stats->launches += 3;
           for (int q = 0; q < nj; q++) {
             PermTest& t = tests[jq[q]];
-            t.nrej += h[q];
-            t.done += jobs[q].nperm;
             if (stats) stats->permutations += jobs[q].nperm;
-            if (t.nrej > t.nrejc) continue;                           // not significant: decided, no split
-            if (t.done >= nperm) { split_of[t.seg] = 1; continue; }   // significant
+            // fndcpt's loop over np = 1, 2, ... replayed on the exceedance positions of this batch: an exceedance beyond
+            // nrejc ends the test (not significant); np >= bd[nrej] ends it the other way (significant)
+            const int batch_end = t.done + jobs[q].nperm;
+            int decided = 0;  // 1 significant, -1 not significant
+            const uint32_t* fw = hf.data() + (size_t)q * flag_words;
+            for (int wd = 0; wd < (jobs[q].nperm + 31) / 32 && !decided; wd++) {
+              uint32_t bits = fw[wd];
+              while (bits && !decided) {
+                const int g = wd * 32 + __builtin_ctz(bits);
+                bits &= bits - 1;
+                const int e = t.done + g + 1;  // 1-based permutation count of this exceedance
+                if (t.bd && e - 1 > t.cur && t.bd[t.nrej] <= e - 1) { decided = 1; break; }  // crossed before it
+                t.nrej++;
+                t.cur = e;
+                if (t.nrej > t.nrejc) { decided = -1; break; }
+                if (t.bd && t.bd[t.nrej] <= e) { decided = 1; break; }
+              }
+            }
+            if (!decided && t.bd && batch_end > t.cur && t.bd[t.nrej] <= batch_end) decided = 1;
+            t.cur = std::max(t.cur, batch_end);
+            t.done = batch_end;
+            if (decided < 0) continue;                                           // not significant: no split
+            if (decided > 0 || t.done >= nperm) { split_of[t.seg] = 1; continue; }  // significant
             still.push_back(jq[q]);
           }
           g0 = g1;

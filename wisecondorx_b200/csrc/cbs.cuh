@@ -17,6 +17,9 @@ struct CbsWorkspace;
 CbsWorkspace* cbs_workspace_create();
 void cbs_workspace_destroy(CbsWorkspace* ws);
 
+// sequential stopping boundary of the permutation tests (DNAcopy getbdry table, see cbs.cu); n = 0 switches it off
+void cbs_set_boundary(CbsWorkspace* ws, const int32_t* sbdry, int32_t n);
+
 // y, w: concatenated NA-free series (host); off[nseries + 1]; ends_out capacity = off[nseries]
 int cbs_segment(CbsWorkspace* ws, const double* y, const double* w, const int64_t* off, int32_t nseries,
                 const int32_t* series_ids, double alpha, int32_t nperm, int32_t kmax, int32_t nmin, int32_t min_width,
