@@ -4,6 +4,7 @@ import zipfile
 import zlib
 
 import numpy as np
+import pytest
 
 from wisecondorx_b200 import npz_io
 
@@ -104,3 +105,29 @@ def test_async_writer_and_newref_merge(tmp_path):
         assert bool(z["has_female"]) and bool(z["has_male"]) and not bool(z["is_nipt"]) and float(z["trained_cutoff"]) == 0.0023
         assert "_queued" not in z.files and "gender" not in z.files
         assert len(z.files) == 3 * 10 + 4
+
+
+def test_load_samples_fast_reader_equals_numpy(tmp_path):
+    """Sample files are parsed without the zipfile module (npz_io._read_members); same dicts as np.load, compressed or
+    stored, CRC checked."""
+    from wisecondorx_b200 import synth
+    samples, _ = synth.make_samples(6, 1000000, seed=5)
+    paths = []
+    for i, smp in enumerate(samples):
+        pth = str(tmp_path / ("s%d.npz" % i))
+        (np.savez_compressed if i % 2 == 0 else np.savez)(pth, binsize=1000000, sample=smp, quality={"x": i})
+        paths.append(pth)
+    assert npz_io._read_members(paths[0], ("sample", "binsize")) is not None
+    for pth, (smp, bs) in zip(paths, npz_io.load_samples(paths)):
+        with np.load(pth, encoding="latin1", allow_pickle=True) as z:
+            want = z["sample"].item()
+            assert bs == int(z["binsize"])
+        assert smp.keys() == want.keys()
+        for key in want:
+            assert np.array_equal(smp[key], want[key]) and smp[key].dtype == want[key].dtype
+    raw = bytearray(open(paths[0], "rb").read())
+    raw[80] ^= 0xFF  # inside the first member's deflate stream
+    bad = str(tmp_path / "bad.npz")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(Exception):
+        npz_io.load_samples([bad])

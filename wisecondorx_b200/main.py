@@ -54,22 +54,27 @@ def _row_chunks(total, nthreads):
     return [(a, min(total, a + step)) for a in range(0, total, step)]
 
 
-def get_mask(samples):
+def get_mask(samples, counts=None, cols=None):
     """Bins with more than 5 % of the median (non-zero) summed normalised coverage (reference newref_tools.py:77-102).
     Same arithmetic as the reference, element for element -- exact column totals (integers), one division per element,
     NumPy's pairwise sum along each contiguous row -- but the [bins, samples] float matrix (0.8 GB at 15 kb / 500
-    samples) is never materialised: row chunks go through a thread pool (NumPy releases the GIL in these loops)."""
+    samples) is never materialised: row chunks go through a thread pool (NumPy releases the GIL in these loops).
+    counts / cols: the stacked count matrix of a superset of `samples` with the same bins per chromosome and the columns
+    of `samples` in it (tool_newref stacks the samples once for the three masks and the three passes)."""
     from concurrent.futures import ThreadPoolExecutor
     bins_per_chr = [max(len(s[str(c)]) for s in samples) for c in range(1, 25)]
     total = int(sum(bins_per_chr))
-    ns = len(samples)
     nthreads = max(1, min(16, len(os.sched_getaffinity(0))))
-    counts = newref_tools.stack_counts(samples, range(1, 25))  # int32 [total, S], zero padded
+    if counts is None or counts.shape[0] != total:
+        counts, cols = newref_tools.stack_counts(samples, range(1, 25)), None  # int32 [total, S], zero padded
     col_sum = np.sum(counts, 0, dtype=np.int64).astype(float)   # exact, like the float sum of integer counts
+    if cols is not None:
+        col_sum = col_sum[cols]
 
     def rows(ab):
         a, b = ab
-        return np.sum(counts[a:b].astype(float) / col_sum, 1)
+        block = counts[a:b] if cols is None else counts[a:b][:, cols]  # the subset's own matrix, row block by row block
+        return np.sum(block.astype(float) / col_sum, 1)
 
     with ThreadPoolExecutor(nthreads) as pool:
         sum_per_bin = np.concatenate(list(pool.map(rows, _row_chunks(total, nthreads)))) if total else np.zeros(0)
@@ -132,12 +137,14 @@ def tool_newref(args):
     if not args.nipt:
         for i, sample in enumerate(samples):
             samples[i] = gender_correct(sample, genders[i])
-    total_mask, bins_per_chr = get_mask(samples)
+    # one stacked count matrix [bins, samples] for the three masks and the three passes (each used to stack its own)
+    counts_all = newref_tools.stack_counts(list(samples), range(1, 25)) if len(samples) else None
+    total_mask, bins_per_chr = get_mask(samples, counts_all)
     g = np.array(genders)
     if genders.count("F") > 4:
-        total_mask = total_mask & get_mask(samples[g == "F"])[0]
+        total_mask = total_mask & get_mask(samples[g == "F"], counts_all, np.flatnonzero(g == "F"))[0]
     if genders.count("M") > 4 and not args.nipt:
-        total_mask = total_mask & get_mask(samples[g == "M"])[0]
+        total_mask = total_mask & get_mask(samples[g == "M"], counts_all, np.flatnonzero(g == "M"))[0]
     device = getattr(args, "device", 0)
     gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     devices = [device + g for g in range(gpus)]
@@ -159,7 +166,13 @@ def tool_newref(args):
 
     def one_pass(sample_list, gender, nparts):
         t1 = time.perf_counter()
-        prep = newref_control.tool_newref_prep(sample_list, gender, total_mask, bins_per_chr, device)
+        # the pass's count matrix out of the stacked one: its chromosomes are a row prefix, its samples a column subset
+        last = {"A": 22, "F": 23}.get(gender, 24)
+        pass_counts = None
+        if counts_all is not None and [max(len(s[str(c)]) for s in sample_list) for c in range(1, 25)] == list(bins_per_chr):
+            rows_of_pass = int(sum(bins_per_chr[:last]))
+            pass_counts = counts_all[:rows_of_pass] if gender == "A" else np.ascontiguousarray(counts_all[:rows_of_pass][:, g == gender])
+        prep = newref_control.tool_newref_prep(sample_list, gender, total_mask, bins_per_chr, device, counts=pass_counts)
         t2 = time.perf_counter()
         wait_copier()  # the page-locked staging arrays are free again (the copy ran beside the preparation above)
         res = newref_control.tool_newref_main(prep, args.refsize, nparts, device, devices)
@@ -169,10 +182,15 @@ def tool_newref(args):
             # the GPU wrote into page-locked staging memory that the next pass reuses: move the arrays to ordinary
             # memory (NumPy releases the GIL for the copy) and start deflating them
             try:
-                for key in ("indexes", "distances", "null_ratios"):
-                    dst = np.empty(res[key].shape, res[key].dtype)
-                    np.copyto(dst, res[key])
-                    res[key] = dst
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(4) as pool:  # first touch of 0.9 GB of fresh pages: a few threads, not one
+                    for key in ("indexes", "distances", "null_ratios"):
+                        src = res[key]
+                        dst = np.empty(src.shape, src.dtype)
+                        step = max(1, -(-len(src) // 8))
+                        list(pool.map(lambda a: np.copyto(dst[a:a + step], src[a:a + step]), range(0, len(src), step)))
+                        res[key] = dst
+                        del src
                 newref_control.writer_add_pass(writer, res, args.binsize)
             except Exception as e:  # re-raised on the main thread
                 copier[1] = e

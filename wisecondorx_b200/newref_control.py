@@ -14,18 +14,20 @@ import numpy as np
 from . import _lib, newref_tools, npz_io
 
 
-def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0):
+def tool_newref_prep(samples, gender, mask, bins_per_chr, device: int = 0, counts=None):
     """Numeric body of the reference's tool_newref_prep (newref_control.py:24-80): masking,
     normalisation, PCA correction and the PCA-distance bin filter.  `mask` is edited IN PLACE like in
     the reference (:51-54; the edit leaks into the later F / M passes).
-    Returns a dict with the prep arrays and pca_corrected_data."""
+    Returns a dict with the prep arrays and pca_corrected_data.  counts: the stacked int32 count matrix of exactly these
+    samples and chromosomes (newref_tools.stack_counts) when the caller already has it."""
     last_chr = {"A": 22, "F": 23}.get(gender, 24)
     bins_per_chr = list(bins_per_chr[:last_chr])
     mask = mask[: int(np.sum(bins_per_chr))]  # a view of the caller's total mask
     chrs = range(1, last_chr + 1)
     # the [N, S] matrices stay in HBM from here to get_reference (newref_tools.DevicePrep)
     dp = newref_tools.DevicePrep(device)
-    counts = newref_tools.stack_counts(samples, chrs)
+    if counts is None or counts.shape != (int(np.sum(bins_per_chr)), len(samples)):
+        counts = newref_tools.stack_counts(samples, chrs)
     dp.normalize_and_mask(counts, mask)
     pca = dp.train_pca()
     d, _ = dp.pca_distance()
