@@ -191,9 +191,9 @@ _noted = [False]
 def _note_not_bit_compatible():
     """Once per process: the segmentation follows DNAcopy's algorithm but not R's random stream."""
     if not _noted[0]:
-        logging.info("Segmentation runs on the GPU (circular binary segmentation as in DNAcopy::segment; permutations come "
-                     "from a Philox stream, not R's Mersenne Twister, and the full permutation count replaces DNAcopy's "
-                     "sequential stopping rule): breakpoints of borderline segments can differ from the reference's R run")
+        logging.info("Segmentation runs on the GPU (circular binary segmentation as in DNAcopy::segment, hybrid p-value and "
+                     "sequential stopping boundary included; the permutations come from a Philox stream, not R's Mersenne "
+                     "Twister): breakpoints of borderline segments can differ from the reference's R run")
         _noted[0] = True
 
 
