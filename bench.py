@@ -547,8 +547,8 @@ def run_ours(args, rank, world, local_rank):
                         else "inputs fit in L2 and are not flushed: parity-size workload, not the bench line",
                   "parallelism": f"target-bin parts x{world}",
                   "null_ratios": "separate call after the top-k" if args.unfused else
-                                 "row blocks on a side stream next to the re-rank of the following block "
-                                 "(stages_ms.null_ratios = what they add after the last re-rank block)"},
+                                 "resident outputs: one launch after the re-rank of each region (inside stages_ms.rerank); "
+                                 "host outputs (e2e): row blocks on a side stream next to the re-rank of the following block"},
         "e2e": {"value": e2e_value, "unit": "bin-pair dist/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "equals_resident_result": e2e_same, "path": e2e_path,
                 "phases_ms_cumulative_rank0": {k: round(v, 2) for k, v in e2e_phases.items()} if e2e_phases else None},

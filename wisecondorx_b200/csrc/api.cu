@@ -565,7 +565,12 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
       // issue utilisation, the median selection is issue bound), and with host outputs the D2H copy of a finished
       // block (copy stream) overlaps the kernels of the next one.
       static const bool serial_nulls = std::getenv("WCX_SERIAL_NULLS") != nullptr;
-      const bool side = d_null && !serial_nulls;   // null ratios on the side stream
+      // Device-resident outputs: nothing to copy while the kernels run, so every region is one re-rank launch followed by
+      // one null-ratio launch on the same stream (measured r03o: 79.8 ms per step against 82.0 with eight row blocks and
+      // the null ratios of a finished block on a side stream -- the two kernels take turns on the SMs anyway, and every
+      // extra launch has its own tail).  Host outputs keep the row blocks: the D2H copy of a block hides behind the
+      // kernels of the next one.
+      const bool side = d_null && !serial_nulls && !out_on_device;   // null ratios on the side stream
       int bq = 0;       // block counter over both regions (events)
       int last_blk = -1;
       for (const Region& rg : {regA, regB}) {
@@ -575,7 +580,7 @@ static int topk_impl(wcx_ctx* c, int64_t rb, int64_t re, int32_t k, int32_t kern
         const int nlists = rg.nsplit * lps;
         // >= 4 k rows per block (7 waves of re-rank CTAs); with host outputs the copy of a block hides behind the kernels of
         // the next one, so a part of 24 k rows (8 GPUs) wants more than two blocks
-        const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(rg.nsplit > 1 && pair ? 3 : 8, rrows / 4000));
+        const int nblk = out_on_device ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(rg.nsplit > 1 && pair ? 3 : 8, rrows / 4000));
         for (int bi = 0; bi < nblk; bi++, bq++) {
           const int64_t r0 = rg.r0 + rrows * bi / nblk, r1 = rg.r0 + rrows * (bi + 1) / nblk;
           if (r1 <= r0) continue;

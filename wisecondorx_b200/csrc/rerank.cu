@@ -268,6 +268,9 @@ __device__ void bitonic_sort_dpos(uint64_t* dkey, int32_t* pos, int n_pow2) {
   }
 }
 
+// (Round 2 also measured ordering by rank counting -- every thread counts the pairs that order before its own with a
+// four-instruction borrow chain per compare, no barriers, twice the instructions: 49.8 / 50.2 ms against 49.9 / 50.4 ms
+// for re-rank + null ratios, no difference; this network stays.)
 // Same sort with the elements in registers: element i = e * RR_THREADS + tid lives in slot e of thread tid.  A
 // compare-exchange distance j < 32 is a warp shuffle, j >= RR_THREADS pairs two slots of one thread, only
 // j = 32, 64, 128 go through shared memory (9 of the 45 steps at 512 entries) -- the r01d profile shows the
@@ -360,6 +363,18 @@ __device__ __forceinline__ int __syncthreads_count_sum(int c) {
   }
   __syncthreads();
   return s_total;
+}
+
+// One shared-memory atomic per warp instead of one per passing lane: all 32 lanes call, `pred` lanes get consecutive
+// slots (the order inside a list does not matter to its readers).
+__device__ __forceinline__ int warp_slot(int* counter, bool pred) {
+  const uint32_t m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0u) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ int next_pow2(int v) {
@@ -584,19 +599,21 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     const int64_t slot = lrow * nlists + q;
     const int c = cv.cnt[slot];
     const uint2* le = cv.ent + slot * WCX_CAND_CAP;
-    // four independent loads in flight per thread (the shared-memory atomics would otherwise serialise them)
-    for (int i0 = tid; i0 < c; i0 += 4 * RR_THREADS) {
+    // four independent loads in flight per thread; the loop bound is uniform so that whole warps allocate their list
+    // slots together (warp_slot)
+    for (int b0 = 0; b0 < c; b0 += 4 * RR_THREADS) {
       uint2 e[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int i = i0 + u * RR_THREADS;
+        const int i = b0 + tid + u * RR_THREADS;
         e[u] = i < c ? le[i] : make_uint2(0x7f800000u, 0u);  // +inf is never below the cut
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const float v = __uint_as_float(e[u].x);
-        if (v < cut) {
-          const int p = atomicAdd(&s_tot, 1);
+        const bool pass = v < cut;
+        const int p = warp_slot(&s_tot, pass);
+        if (pass) {
           const uint32_t key = f32_key_(v);
           mn = min(mn, key);
           mx = max(mx, key);
@@ -618,7 +635,8 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
 
   // k-th smallest approximate value: bisection over the key bits below the prefix shared by all keys; stops as
   // soon as the bracket holds a single key (about log2(tot) + 2 rounds instead of 32)
-  if (tot > k) {
+  if (tot > k && tid < 32) {
+    // one warp, no block-wide barriers: ~12 rounds of tot / 32 compares per lane and a warp reduction
     const uint32_t diff = s_mn ^ s_mx;
     int bit = diff ? 31 - __clz(diff) : -1;  // highest differing bit
     uint32_t res = bit >= 31 ? 0u : (s_mn & ~((2u << (bit < 0 ? 0 : bit)) - 1u));
@@ -627,15 +645,15 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     for (; bit >= 0 && inb > 1; bit--) {
       const uint32_t trial = res | (1u << bit);
       int c = 0;
-      for (int i = tid; i < tot; i += RR_THREADS) c += (vals[i] < trial) ? 1 : 0;
-      c = __syncthreads_count_sum(c);
+      for (int i = tid; i < tot; i += 32) c += (vals[i] < trial) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
       if (c < k) { res = trial; inb = below + inb - c; below = c; }
       else inb = c - below;
     }
     if (bit >= 0) {
       // exactly one key left in the bracket and it is the k-th smallest: fetch it
       const uint32_t hi_excl = bit >= 31 ? 0xffffffffu : res + ((2u << bit) - 1u);  // inclusive upper end
-      for (int i = tid; i < tot; i += RR_THREADS) {
+      for (int i = tid; i < tot; i += 32) {
         const uint32_t v = vals[i];
         if (v >= res && v <= hi_excl) s_vk = v;
       }
@@ -675,12 +693,12 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
   }
   // select the candidates with v <= bound
   if (tid == 0) s_ub = 0ull;
-  for (int i = tid; i < tot; i += RR_THREADS) {
-    const float v = key_f32_(vals[i]);
-    if ((double)v <= bound) {
-      const int p = atomicAdd(&s_m, 1);
-      if (p < RR_MAXM) { sel[p] = (int32_t)jidx[i]; selv[p] = v; }
-    }
+  for (int b0 = 0; b0 < tot; b0 += RR_THREADS) {
+    const int i = b0 + tid;
+    const float v = i < tot ? key_f32_(vals[i]) : __int_as_float(0x7f800000);
+    const bool pass = i < tot && (double)v <= bound;
+    const int p = warp_slot(&s_m, pass);
+    if (pass && p < RR_MAXM) { sel[p] = (int32_t)jidx[i]; selv[p] = v; }
   }
   __syncthreads();
   int m = s_m;
@@ -723,7 +741,9 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     const double U = __longlong_as_double((long long)ubu);
 #pragma unroll
     for (int e = 0; e < RR_MAXM / RR_THREADS; e++) {
-      if (jj[e] >= 0 && !(lo[e] > U)) sel[atomicAdd(&s_cnt, 1)] = jj[e];
+      const bool keep = jj[e] >= 0 && !(lo[e] > U);
+      const int p = warp_slot(&s_cnt, keep);
+      if (keep) sel[p] = jj[e];
     }
     __syncthreads();
     m = s_cnt;
@@ -771,6 +791,7 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
       }
     }
   }
+  const uint64_t key_1e10 = f64_key(1e10);
   const int p2m = next_pow2(m < 2 ? 2 : m);
   for (int i = m + tid; i < p2m; i += RR_THREADS) { keys[i] = ~0ull; pos_s[i] = 0x7fffffff; }
   __syncthreads();
@@ -790,7 +811,6 @@ rerank_kernel(const double* __restrict__ x, PrepView pv, CandView cv, int nlists
     for (int t = tid; t < k; t += RR_THREADS) oi[t] = 0;  // valid until exact_rows rewrites the row
     return;
   }
-  const uint64_t key_1e10 = f64_key(1e10);
   for (int t = tid; t < k; t += RR_THREADS) {
     const bool have = t < m && keys[t] < key_1e10;
     if (have) {
