@@ -142,7 +142,6 @@ namespace {
 
 constexpr int RR_THREADS = 256;
 constexpr int RR_MAXM = 1024;  // max candidates whose exact distance is evaluated per row
-constexpr int PLAN_STACK = 8;  // depth of the register stack in exact_sqdist_quad (wcx_newref_load checks the plan)
 
 __device__ __forceinline__ uint64_t f64_key(double d) {
   uint64_t u = (uint64_t)__double_as_longlong(d);
@@ -347,22 +346,6 @@ __device__ void bitonic_sort_dpos_regs(uint64_t* dkey, int32_t* pos, int n_pow2)
     if (e < E && i < n_pow2) { dkey[i] = kk[e]; pos[i] = pp[e]; }
   }
   __syncthreads();
-}
-
-// block-wide sum of a per-thread count; result valid in every thread (two barriers)
-__device__ __forceinline__ int __syncthreads_count_sum(int c) {
-  __shared__ int s_red[RR_THREADS / 32];
-  __shared__ int s_total;
-  c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < RR_THREADS / 32; w++) t += s_red[w];
-    s_total = t;
-  }
-  __syncthreads();
-  return s_total;
 }
 
 // One shared-memory atomic per warp instead of one per passing lane: all 32 lanes call, `pred` lanes get consecutive
