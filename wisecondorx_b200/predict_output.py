@@ -62,6 +62,15 @@ def _generate_bins_bed(rem_input, results):
         for c in range(len(results["results_r"])):
             name = _chr_name(c)
             r, z = results["results_r"][c], results["results_z"][c]
+            if (isinstance(r, np.ndarray) and isinstance(z, np.ndarray) and r.dtype == np.float64 and z.dtype == np.float64
+                    and isinstance(binsize, (int, np.integer))):
+                # 200 k lines at 15 kb: Python floats (repr == str of the NumPy scalar), every integer converted once
+                b, n = int(binsize), len(r)
+                ss = list(map(str, range(1, n * b + 1, b)))
+                es = list(map(str, range(b, n * b + b, b)))
+                fh.write("".join([f"{name}\t{s}\t{e}\t{name}:{s}-{e}\t{'nan' if x == 0 else repr(x)}\t{'nan' if y == 0 else repr(y)}\n"
+                                  for s, e, x, y in zip(ss, es, r.tolist(), z.tolist())]))
+                continue
             lines = []
             for i in range(len(r)):
                 s, e = i * binsize + 1, (i + 1) * binsize
