@@ -33,7 +33,7 @@ PYEOF
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1
       tail -1 gpurun_out/${TAG}_launches.log | cut -c1-300 ;;
     ncu_newref)
-      for K in dist_topk_tc rerank null_ratios; do
+      for K in dist_topk_tc rerank null_fast; do
         timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -f -o gpurun_out/${TAG}_prof_$K python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-predict > gpurun_out/${TAG}_prof_$K.log 2>&1
         python tools/ncu_summary.py gpurun_out/${TAG}_prof_$K.ncu-rep > gpurun_out/${TAG}_ncu_$K.txt 2>&1
       done ;;
