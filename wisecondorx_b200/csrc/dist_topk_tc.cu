@@ -30,8 +30,8 @@
 //                 TMEM buffer is handed back after half a drain while the MMA warp fills the other one; each group keeps
 //                 its own list per row and the two groups exchange thresholds through shared memory.
 // Pipelines: smem full / empty mbarriers (TMA <-> MMA, 5 stages of 32 KB per CTA) and TMEM full / empty mbarriers
-// (MMA <-> epilogue).  All CTA pairs walk the candidate axis in lock-step (tiles inside the rows' own chromosome are
-// still multiplied), so every B tile is fetched from HBM once and served from L2 to the other pairs.
+// (MMA <-> epilogue).  All CTA pairs walk the candidate axis in the same order and within one chromosome of each other
+// (tile_own below), so every B tile is fetched from HBM once and served from L2 to the other pairs.
 // The one-CTA-per-SM variant (PAIR = false) is kept as a cross-check path and for the single-tile test hook; the tf32
 // operand variants of round 1 are gone.
 #include <cuda.h>
@@ -223,11 +223,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// A tile that lies entirely inside the target rows' own chromosome yields no candidates.  It is
-// still loaded and multiplied (5-6 % extra tensor work on a whole genome) so that all CTAs walk
-// the candidate axis in lockstep and every B tile is fetched from HBM once and then served from L2
-// to the other 147 CTAs; skipping it de-phases the CTAs and the sweep becomes HBM-latency bound
-// (profiles/r01b: 209 GB DRAM reads per launch with skipping).  Only the epilogue filter is skipped.
+// A tile that lies entirely inside the target rows' own chromosome yields no candidates.  When that holds for all 256
+// rows of a unit the tile is skipped by all three roles (5.7 % of the tiles on a whole genome; 29.98 vs 30.79 ms in
+// the same run): the CTA pairs then run at most one chromosome (<= 16 MB of operands) apart on the candidate axis, so
+// every B tile is still fetched from HBM once and served from L2 to the other pairs.  (The round-1 kernel was
+// HBM-latency bound when it skipped tiles -- profiles/r01b, 209 GB of DRAM reads -- with a three-stage pipeline and
+// no operand reuse inside a pair.)  A unit whose two halves belong to different chromosomes multiplies the tile and
+// only the epilogue of the half that owns it skips the filter.
 __device__ __forceinline__ bool tile_own(const WorkItem& w, int ct) {
   const int col0 = ct * TN;
   return col0 >= w.chr_s && col0 + TN <= w.chr_e;
