@@ -47,6 +47,20 @@ def test_get_mask_and_gender_model(R):
     want_mask, want_bpc = R.newref_tools.get_mask(arr)
     got_mask, got_bpc = wcx_main.get_mask(arr)
     assert np.array_equal(got_mask, want_mask) and list(got_bpc) == list(want_bpc)
+    # masks of sample subsets out of ONE stacked count matrix (tool_newref: all samples, then the females, then the males)
+    from wisecondorx_b200 import newref_tools
+    counts_all = newref_tools.stack_counts(list(arr), range(1, 25))
+    g = np.array(genders)
+    for sub in (np.ones(len(arr), bool), g == "F", g == "M", np.arange(len(arr)) % 3 == 0):
+        want_sub, want_sub_bpc = R.newref_tools.get_mask(arr[sub])
+        got_sub, got_sub_bpc = wcx_main.get_mask(arr[sub], counts_all, np.flatnonzero(sub))
+        assert np.array_equal(got_sub, want_sub) and list(got_sub_bpc) == list(want_sub_bpc)
+    short = [dict(smp) for smp in arr[:5]]  # a subset with fewer bins than the stacked matrix: falls back to its own stack
+    for smp in short:
+        smp["7"] = smp["7"][:-3]
+    want_sub, _ = R.newref_tools.get_mask(np.array(short))
+    got_sub, _ = wcx_main.get_mask(np.array(short), counts_all, np.arange(5))
+    assert np.array_equal(got_sub, want_sub)
     args = types.SimpleNamespace(yfrac=0.006, plotyfrac=None)
     want_g, want_cut = R.newref_tools.train_gender_model(args, arr)
     got_g, got_cut = wcx_main.train_gender_model(args, arr)
