@@ -110,3 +110,44 @@ def test_exec_cbs_dropin_signature():
     assert all(len(row) == 5 for row in out)
     gain = [row for row in out if row[0] == 1 and row[4] > 0.2]
     assert len(gain) == 1 and abs(gain[0][1] - 20) <= 1 and abs(gain[0][2] - 60) <= 1 and gain[0][3] > 5
+
+
+def test_boundary_arguments_and_reset():
+    """wcx_cbs_set_boundary: the table stays in the context until replaced; n = 0 switches the rule off; values below 1
+    and a NULL table with n > 0 are rejected."""
+    import ctypes
+
+    from wisecondorx_b200 import _lib
+    ctx = _lib.default_context(0)
+    L = _lib.load()
+    bad = np.array([9500, 0, 9864], dtype=np.int32)
+    assert L.wcx_cbs_set_boundary(ctx.handle, ctypes.c_void_p(bad.ctypes.data), 3) != 0
+    assert L.wcx_cbs_set_boundary(ctx.handle, None, 3) != 0
+    rng = np.random.default_rng(15)
+    series = [_series(rng, 260, [(100, 140, 0.05)]), _series(rng, 150, [(60, 75, 0.08)])]
+    a = cbs.segment_series(series, alpha=1e-3, nperm=400, seed=2, sequential=False)
+    # a table whose every entry is 1: any test that reaches the permutations is declared significant after the first one
+    ones = np.ones(3, dtype=np.int32)
+    _lib.check(L.wcx_cbs_set_boundary(ctx.handle, ctypes.c_void_p(ones.ctypes.data), 3))
+    # segment_series sets its own table (or none) on every call: the leftover table above must not leak into it
+    b = cbs.segment_series(series, alpha=1e-3, nperm=400, seed=2, sequential=False)
+    assert [x.tolist() for x in a] == [x.tolist() for x in b]
+
+
+def test_pinned_pool_reserve_and_prewarm():
+    """_lib.pinned: reserve() leaves a page-locked buffer that a slightly smaller request reuses (tool_newref reserves
+    upper bounds on a background thread), a much smaller request does not; prewarm_async is safe to call twice."""
+    from wisecondorx_b200 import _lib
+    t = _lib.prewarm_async(0, [6 << 20])
+    t.join()
+    _lib.prewarm_async(0).join()
+    pool = _lib.pinned
+    have = sum(len(v) for k, v in pool._free.items() if k == 6 << 20)
+    assert have >= 1
+    a = pool.empty((5 << 20,), np.uint8)  # 5 MiB fits the reserved 6 MiB buffer (within the 1.25 slack)
+    assert sum(len(v) for k, v in pool._free.items() if k == 6 << 20) == have - 1
+    a[:] = 7
+    small = pool.empty((1 << 20,), np.uint8)  # 1 MiB must not take a 6 MiB buffer
+    del a
+    assert sum(len(v) for k, v in pool._free.items() if k == 6 << 20) == have
+    del small
