@@ -370,9 +370,11 @@ cbs_perm_fy_kernel(const double* __restrict__ yy, const double* __restrict__ w, 
       j = (uint32_t)(((uint64_t)buf[t & 3] * (uint32_t)(i + 1)) >> 32);
     }
     const int cnt = min(32, ib + 1);
-    for (int q = 0; q < cnt; q++) {
+    // fully unrolled: the 32 shuffles are issued ahead of the swap chain instead of one per (dependent) swap
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
       const uint32_t jq = __shfl_sync(0xffffffffu, j, q);
-      if (lane == 0) {
+      if (lane == 0 && q < cnt) {
         const int iq = ib - q;
         const uint16_t ti = a[iq], tj = a[jq];
         a[jq] = ti;
@@ -391,8 +393,10 @@ cbs_perm_fy_kernel(const double* __restrict__ yy, const double* __restrict__ w, 
       wpx = wsi * px;
     }
     double mine = 0.0;
-    const int cnt = min(32, n - i0);
-    for (int q = 0; q < cnt; q++) {
+    // lanes past the end hold +0.0, which leaves the running sum bit-identical: always 32 steps, fully unrolled, so
+    // that the shuffles run ahead of the chain of ordered additions
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
       acc = acc + __shfl_sync(0xffffffffu, wpx, q);
       if (lane == q) mine = acc;
     }
