@@ -82,9 +82,10 @@ int wcx_newref_null_ratios(wcx_ctx* ctx, const int32_t* idx, int32_t idx_on_devi
 
 /* Top-k and null ratios of rows [row_begin, row_end) in one call -- the body of get_reference
  * (newref_tools.py:176-224) after the matrix is resident.  One sweep over the candidate axis nominates candidates for
- * every row; the rows then go through the exact re-rank in blocks, the null-ratio kernels of a finished block run on
- * a second stream next to the re-rank of the following block, and with host outputs the D2H copy of a finished block
- * overlaps the kernels of the next one.  m == 0 skips the null ratios.  Outputs as wcx_newref_topk /
+ * every row; the rows then go through the exact re-rank and the null-ratio kernels.  With host outputs this happens in
+ * row blocks -- the null-ratio kernels of a finished block run on a second stream next to the re-rank of the following
+ * block and the D2H copy of a finished block overlaps the kernels of the next one; with device outputs every region of
+ * rows is one re-rank launch followed by one null-ratio launch.  m == 0 skips the null ratios.  Outputs as wcx_newref_topk /
  * wcx_newref_null_ratios.  ref_size: 1..400 on the tensor-core path; 401..512 is served by the brute-force float64
  * row kernel (WCX_KERNEL_EXACT) -- same results, much slower. */
 int wcx_newref_reference(wcx_ctx* ctx, int64_t row_begin, int64_t row_end, int32_t k, int32_t kernel,
