@@ -106,3 +106,41 @@ def test_sequential_boundary_table():
     from math import comb
     b1, b2 = C.seq_boundary(0.05, 10000, 2)[1:]
     assert abs((comb(10000 - b1, 2) + b1 * (10000 - b2)) / comb(10000, 2) - C._p_exceed(10000, 2, [b1, b2])) < 1e-9
+
+
+def test_product_postprocessing_equals_oracle():
+    """wisecondorx_b200.cbs._cbs_prepare / _cbs_finish (CBS.R:30-129 restated per chromosome) against the oracle's cbs_r
+    (per segment, like CBS.R) on the same random segment ends: NA runs at chromosome ends, runs longer and shorter than
+    the split threshold, all-NA chromosomes, every bin size class."""
+    from wisecondorx_b200 import cbs
+    rng = np.random.default_rng(5)
+    total = 0
+    for trial in range(24):
+        binsize = [15000.0, 100000.0, 5000.0, 1e6][trial % 4]
+        per = [int(x) for x in rng.integers(5, 1500, 23)]
+        rr = [rng.normal(0, 0.1, n) for n in per]
+        ww = [rng.uniform(0.5, 2, n) for n in per]
+        for r in rr:
+            r[rng.random(len(r)) < [0.0, 0.05, 0.3][trial % 3]] = 0
+            for _ in range(trial % 5):
+                a = int(rng.integers(0, max(1, len(r) - 1)))
+                r[a:a + int(rng.integers(1, 400))] = 0
+        rr[0][:3] = 0
+        rr[0][-2:] = 0
+        rr[7][:] = 0  # CBS.R:56-63: dropped
+        ww[3][::5] = 0  # CBS.R:42
+        ends_of = {}
+
+        def segmenter(yy, wv, c):
+            n = len(yy)
+            ends_of[c] = sorted(set([int(x) for x in rng.integers(1, n + 1, int(rng.integers(0, 6)))] + [n]))
+            return ends_of[c]
+
+        want = [[d["chr"] - 1, d["s"], d["e"], d["r"]] for d in C.cbs_r(rr, ww, "F", 1e-4, binsize, segmenter=segmenter)]
+        prepared, series, ids = cbs._cbs_prepare(rr, ww, "F")
+        got = cbs._cbs_finish(prepared, [np.array(ends_of[c], dtype=np.int32) for c in ids], binsize)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g[:3] == w[:3] and (g[3] == w[3] or (np.isnan(g[3]) and np.isnan(w[3]))), (trial, g, w)
+        total += len(got)
+    assert total > 1000

@@ -156,23 +156,34 @@ def _cbs_prepare(results_r, results_w, ref_gender):
 
 
 def _cbs_finish(prepared, all_ends, binsize):
-    """CBS.R:80-129: split the segments over long NA runs, weighted segment means, 0-based half-open coordinates."""
+    """CBS.R:80-129: split the segments over long NA runs, weighted segment means, 0-based half-open coordinates.
+    The NA runs of a chromosome are located once (CBS.R does it per segment, :86-101, with the same result: a segment
+    starts and ends on a non-NA bin, so a run lies inside it or outside)."""
     na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
     out = []
     for (c, ratio, wts, na, keep), ends in zip(prepared, all_ends):
+        d = np.diff(na.astype(np.int8))
+        run_first = np.flatnonzero(d == 1) + 1   # first NA bin of a run (0-based) = CBS.R's start.pos (1-based last bin before it)
+        run_after = np.flatnonzero(d == -1) + 1  # first bin after a run (0-based)   = CBS.R's end.pos (1-based last NA bin)
+        if len(na) and na[0]:
+            run_after = run_after[1:]  # a run at the chromosome start has no beginning inside any segment
+        if len(na) and na[-1]:
+            run_first = run_first[:-1]
+        long_run = (run_after - run_first) > na_thresh  # CBS.R:95
+        run_first, run_after = run_first[long_run], run_after[long_run]
         starts = np.concatenate([[0], ends[:-1]]).astype(np.int64)
-        for a, b in zip(starts, ends):
+        for a, b in zip(starts.tolist(), np.asarray(ends).tolist()):
             start_i, end_i = int(keep[a]) + 1, int(keep[b - 1]) + 1  # DNAcopy loc.start / loc.end (1-based)
-            seg_na = na[start_i - 1:end_i]
-            d = np.diff(seg_na.astype(np.int8))
-            start_pos = np.flatnonzero(d == 1) + start_i  # CBS.R:92
-            end_pos = np.flatnonzero(d == -1) + start_i  # CBS.R:93
-            sel = (end_pos - start_pos) > na_thresh  # CBS.R:95
-            start_pos, end_pos = start_pos[sel], end_pos[sel]
-            inv_start = np.concatenate([[start_i], end_pos])  # CBS.R:100-101
-            inv_end = np.concatenate([start_pos, [end_i]])
-            ok = (inv_end - inv_start) > 0  # CBS.R:103
-            for s1, e1 in zip(inv_start[ok], inv_end[ok]):
+            lo = int(np.searchsorted(run_first, start_i - 1, "right")) if len(run_first) else 0
+            hi = int(np.searchsorted(run_first, end_i - 1, "left")) if len(run_first) else 0
+            if hi > lo:
+                inv_start = [start_i] + run_after[lo:hi].tolist()  # CBS.R:100-101
+                inv_end = run_first[lo:hi].tolist() + [end_i]
+            else:
+                inv_start, inv_end = [start_i], [end_i]
+            for s1, e1 in zip(inv_start, inv_end):
+                if e1 - s1 <= 0:  # CBS.R:103
+                    continue
                 yy, ww = ratio[s1 - 1:e1], wts[s1 - 1:e1]
                 m = yy != 0
                 r = float(np.sum(yy[m] * ww[m]) / np.sum(ww[m])) if m.any() else float("nan")  # CBS.R:122-127
