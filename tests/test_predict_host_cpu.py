@@ -1,0 +1,185 @@
+"""Host logic of the predict flow without a GPU (rows a15, f2): the flat result assembly against the
+pinned NumPy restatement of the reference (oracle/np_oracle.py, itself checked against the reference's `tool_test`
+golden in test_oracle_golden.py), `flatten`, and the batch plumbing of predict_control.predict_batch around a stand-in
+for the C-ABI library (tests/fake_cabi.py: meaningless numbers of the right shape) -- every sample of a batch must get
+exactly what it gets alone.  The arithmetic of the device calls is the business of the -m gpu tests."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import fake_cabi  # noqa: E402
+from oracle import np_oracle as O  # noqa: E402
+from wisecondorx_b200 import _lib, cbs, predict_control, predict_tools, synth  # noqa: E402
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def test_flatten():
+    f = predict_tools.flatten
+    m = np.arange(24, dtype=np.float64).reshape(2, 12)
+    parts = [m[0, 0:5], m[0, 5:5], m[0, 5:12], m[1, 0:4], m[1, 4:12]]
+    v = f(parts)
+    assert _eq(v, np.arange(24)) and np.shares_memory(v, m)
+    parts[2][1] = -1.0  # writes through the per-chromosome views show in the flat vector
+    assert v[6] == -1.0
+    gap = [m[0, 0:5], m[0, 6:12]]  # not back to back: a copy
+    v = f(gap)
+    assert _eq(v, np.concatenate(gap)) and not np.shares_memory(v, m)
+    assert not np.shares_memory(f([m[0, 0:5], m[0, 0:5]]), m)
+    other = np.ones(3)
+    assert _eq(f([m[0, 0:5], other[0:3]]), np.concatenate([m[0, 0:5], other]))
+    assert _eq(f([np.arange(3), np.arange(2.0)]), [0, 1, 2, 0, 1])  # other dtypes are converted
+    assert f([]).shape == (0,) and f([m[0, 2:2], m[0, 2:2]]).shape == (0,)
+    one = np.arange(4.0)
+    assert f([one]) is one
+    i32 = np.arange(10, dtype=np.int32).reshape(2, 5)
+    v = f([i32[0], i32[1]], np.int32)
+    assert v.dtype == np.int32 and _eq(v, np.arange(10)) and np.shares_memory(v, i32)
+    assert not np.shares_memory(f([m[0, 0:6:2], m[0, 6:12:2]]), m)  # strided views: a copy
+
+
+def _fake_normalize(rng, n, nasty=True):
+    r = 1.0 + 0.05 * rng.standard_normal(n)
+    z = rng.standard_normal(n)
+    w = rng.uniform(0.5, 2.0, n)
+    nref = np.full(n, 300.0)
+    if nasty:
+        r[rng.random(n) < 0.05] = 0.0
+        r[rng.random(n) < 0.01] = np.nan
+        r[rng.random(n) < 0.01] = -1.0
+        r[rng.random(n) < 0.01] = np.inf
+        r[rng.random(n) < 0.02] = 1.0
+        z[rng.random(n) < 0.01] = np.nan
+        nref[rng.random(n) < 0.05] = 3.0
+    return r, z, w, nref, float(rng.normal(0, 0.01)), float(rng.normal(0, 0.1))
+
+
+@pytest.mark.parametrize("g,surplus,bad_weights", [("F", 0, False), ("M", 7, False), ("F", 4, True)])
+def test_assemble_equals_pinned_restatement(tmp_path, g, surplus, bad_weights):
+    """predict_control.assemble (whole genome at once) == np_oracle.assemble_results + log_trans + apply_blacklist (per
+    key and per chromosome like the reference, pinned by test_oracle_golden.py) bit for bit: zero / negative / NaN /
+    infinite ratios, bins with too few reference bins, more results than kept bins, non-numeric
+    weights, a blacklist; stand-alone and as a row of a batch."""
+    rng = np.random.default_rng(11)
+    ref, n_aut = fake_cabi.make_ref_file(binsize=500000, k=4, m=6)
+    sfx = "." + g
+    cnt = int(ref["mask" + sfx].sum())
+    ct = int(ref["masked_bins_per_chr_cum" + sfx][21])
+    n_gon = cnt - ct
+    n_a = cnt - n_gon + surplus  # the autosomal pass saw `surplus` bins the gonosomal mask lost later
+    aut = _fake_normalize(rng, n_a)
+    gon = _fake_normalize(rng, n_gon)
+    if bad_weights:
+        gon = (gon[0], gon[1], np.full(n_gon, np.nan), gon[3], gon[4], gon[5])
+    nr = np.zeros((n_a + n_gon, 6))
+    bl = tmp_path / "bl.bed"
+    bl.write_text("chr1\t1000000\t4200000\nchrX\t0\t900000\nY\t500000\t2500000\n7\t158000000\t999000000\n")
+    args = types.SimpleNamespace(minrefbins=10, blacklist=str(bl))
+    want, sizes = O.assemble_results(aut, gon, None, None, 10, ref["mask" + sfx], ref["bins_per_chr" + sfx])
+    O.log_trans(want, aut[4])
+    O.apply_blacklist(want, bl.read_text(), 500000)
+    pos = np.arange(cnt, dtype=np.int32)
+    pos[sizes[:cnt] < 10] = -1
+    want_inflate = np.full(len(ref["mask" + sfx]), -1, dtype=np.int32)
+    want_inflate[ref["mask" + sfx]] = pos
+
+    rows = predict_control._Rows(3, ref["mask" + sfx])
+    for kw in ({}, {"rows": rows, "row": 1}):
+        rem, got = predict_control.assemble(args, aut, gon, nr, ref, g, g, 123, **kw)
+        assert rem["ref_gender"] == g and rem["n_reads"] == 123 and rem["binsize"] == 500000
+        for key in ("results_r", "results_z", "results_w"):
+            assert len(got[key]) == len(want[key]) == (23 if g == "F" else 24)
+            for c in range(len(want[key])):
+                assert _eq(got[key][c], want[key][c]), (key, c)
+        assert got["results_nr"]["dense"] is nr and _eq(got["results_nr"]["inflate"], want_inflate)
+        if bad_weights:
+            kept = np.concatenate(got["results_w"]) != 0
+            assert kept.any() and np.all(np.concatenate(got["results_w"])[kept] == 1.0)
+    assert not rows.r[0].any() and not rows.r[2].any() and np.all(rows.inflate[0] == -1)  # only the row asked for
+    with pytest.raises(IndexError):  # fewer results than kept bins: the reference's inflate loop runs off its list
+        predict_control.assemble(args, tuple(a[:-20] if isinstance(a, np.ndarray) else a for a in aut), gon, nr, ref, g, g, 1)
+
+
+@pytest.fixture
+def fake_library(monkeypatch):
+    lib = fake_cabi.FakeLib(nasty=True)
+    monkeypatch.setattr(_lib, "_lib", lib)
+    monkeypatch.setattr(_lib, "_default_ctx", {})
+    monkeypatch.setattr(predict_tools, "_engines", {})
+    return lib
+
+
+def test_predict_batch_equals_single_samples(fake_library, tmp_path):
+    """predict_control.predict_batch: one normalize call per reference set, ONE CBS call for every chromosome of every
+    sample, one z-score call per reference gender -- each sample's results (per-bin vectors, null-ratio map, segments,
+    z-scores) are exactly those of a batch of one, for mixed genders, a blacklist and series with long runs without data."""
+    binsize = 200000
+    ref, _ = fake_cabi.make_ref_file(binsize=binsize, k=4, m=6)
+    samples, genders = synth.make_samples(7, binsize, seed=2, depth=2e5)
+    bl = tmp_path / "bl.bed"
+    bl.write_text("chr3\t1000000\t9200000\nchrX\t0\t1900000\n")
+    args = types.SimpleNamespace(maskrepeats=5, minrefbins=150, alpha=1e-4, seed=1, gender=None, blacklist=str(bl), zscore=5, beta=None)
+    eng = predict_tools.PredictEngine(0)
+    batch = predict_control.predict_batch(args, samples, [binsize] * len(samples), ref, eng)
+    assert {rem["ref_gender"] for rem, _ in batch} == {"F", "M"}
+    n_split = 0
+    for i, s in enumerate(samples):
+        rem1, res1 = predict_control.predict_batch(args, [s], [binsize], ref, eng)[0]
+        rem, res = batch[i]
+        assert (rem["gender"], rem["ref_gender"], rem["n_reads"]) == (rem1["gender"], rem1["ref_gender"], rem1["n_reads"])
+        for key in ("results_r", "results_z", "results_w"):
+            assert len(res[key]) == len(res1[key])
+            assert all(_eq(a, b) for a, b in zip(res[key], res1[key])), key
+        assert _eq(res["results_nr"]["inflate"], res1["results_nr"]["inflate"])
+        assert len(res["results_c"]) == len(res1["results_c"]) > 0
+        for a, b in zip(res["results_c"], res1["results_c"]):
+            assert a[:3] == b[:3] and _eq(a[3], b[3]) and _eq(a[4], b[4]), (i, a, b)
+        per_chr = np.bincount([sg[0] for sg in res["results_c"]], minlength=24)
+        n_split += int((per_chr > 1).sum())
+        # the per-chromosome vectors of a sample are views of one row (no copies on the way to the device calls)
+        flat = predict_tools.flatten(res["results_r"])
+        assert np.shares_memory(flat, res["results_r"][0]) and len(flat) == len(rem["mask"])
+    assert n_split > 5
+
+
+def test_cbs_batch_host_side_equals_oracle_postprocessing(fake_library):
+    """cbs.cbs_segments_batch around the stand-in segmenter == the oracle's CBS.R restatement around the SAME
+    segmenter, sample by sample (series with long NA runs, dropped chromosomes, weight 0)."""
+    import ctypes
+    from oracle import cbs_oracle as C
+    rng = np.random.default_rng(3)
+    batch = []
+    for i in range(5):
+        per = [int(x) for x in rng.integers(40, 900, 24)]
+        rr = [rng.normal(0, 0.1, n) for n in per]
+        ww = [rng.uniform(0.5, 2, n) for n in per]
+        for r in rr:
+            r[rng.random(len(r)) < 0.1] = 0
+            a = int(rng.integers(0, len(r) - 1))
+            r[a:a + int(rng.integers(1, 60))] = 0
+        rr[i][:] = 0
+        ww[2][::3] = 0
+        batch.append((rr, ww, "M" if i % 2 else "F"))
+    got = cbs.cbs_segments_batch(batch, 1e-4, 100000.0, seed=1, nperm=100)
+
+    def segmenter(yy, wv, c):  # the stand-in's rule through its C-ABI signature
+        n = len(yy)
+        y = np.ascontiguousarray(yy, dtype=np.float64)
+        off = np.array([0, n], dtype=np.int64)
+        ids = np.array([c], dtype=np.int32)
+        ends, nseg = np.zeros(n, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        p = lambda a: ctypes.c_void_p(a.ctypes.data)
+        fake_library.wcx_cbs_segment(None, p(y), p(y), p(off), 1, p(ids), 1e-4, 100, 1, p(ends), p(nseg))
+        return [int(x) for x in ends[:nseg[0]]]
+
+    for (rr, ww, g), segs in zip(batch, got):
+        want = [[d["chr"] - 1, d["s"], d["e"], d["r"]] for d in C.cbs_r(rr, ww, g, 1e-4, 100000.0, segmenter=segmenter)]
+        assert len(segs) == len(want) > 20
+        for a, b in zip(segs, want):
+            assert a[:3] == b[:3] and _eq(a[3], b[3]), (a, b)

@@ -99,11 +99,9 @@ def sequential_boundary(eta, nperm, max_ones, tol=1e-2):
     return _BOUNDARY_CACHE[key]
 
 
-def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx: _lib.Context | None = None,
-                   sequential: bool = True, eta: float = 0.05):
-    """Segments a batch of NA-free (y, w) series on the GPU.  Returns a list of int32 arrays with
-    the ascending exclusive segment ends of each series.  sequential: DNAcopy's early-stopping decision rule
-    (default, as in segment()); False counts the exceedances over all nperm permutations."""
+def _segment_flat(y, w, off, ids, alpha, nperm, seed, ctx, sequential=True, eta=0.05):
+    """One wcx_cbs_segment call over the series y[off[s]:off[s + 1]] (NA-free, weights w, permutation stream ids[s]).
+    Returns (ends, nseg): the ascending exclusive segment ends of all series back to back and their number per series."""
     ctx = ctx or _lib.default_context(0)
     L = _lib.load()
     if sequential:
@@ -111,23 +109,33 @@ def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx
         _lib.check(L.wcx_cbs_set_boundary(ctx.handle, _ptr(table), len(table)))
     else:
         _lib.check(L.wcx_cbs_set_boundary(ctx.handle, None, 0))
-    ns = len(series)
-    lens = [len(y) for y, _ in series]
-    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ns = len(off) - 1
     total = int(off[-1])
-    y = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a, _ in series]) if ns else np.zeros(0))
-    w = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.float64) for _, b in series]) if ns else np.zeros(0))
-    ids = np.ascontiguousarray(np.arange(ns) if series_ids is None else series_ids, dtype=np.int32)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
     ends = np.zeros(max(total, 1), dtype=np.int32)
     nseg = np.zeros(max(ns, 1), dtype=np.int32)
     _lib.check(L.wcx_cbs_segment(ctx.handle, _ptr(y), _ptr(w), _ptr(off), ns, _ptr(ids), float(alpha), int(nperm),
                                  int(seed) & 0xFFFFFFFF, _ptr(ends), _ptr(nseg)))
     predict_tools.accumulate_ms(ctx, ("cbs",))
-    out, o = [], 0
-    for s in range(ns):
-        out.append(ends[o:o + nseg[s]].copy())
-        o += int(nseg[s])
-    return out
+    return ends, nseg[:ns]
+
+
+def segment_series(series, series_ids=None, alpha=1e-4, nperm=10000, seed=0, ctx: _lib.Context | None = None,
+                   sequential: bool = True, eta: float = 0.05):
+    """Segments a batch of NA-free (y, w) series on the GPU.  Returns a list of int32 arrays with
+    the ascending exclusive segment ends of each series.  sequential: DNAcopy's early-stopping decision rule
+    (default, as in segment()); False counts the exceedances over all nperm permutations."""
+    ns = len(series)
+    off = np.concatenate([[0], np.cumsum([len(y) for y, _ in series])]).astype(np.int64)
+    y = np.concatenate([np.asarray(a, dtype=np.float64) for a, _ in series]) if ns else np.zeros(0)
+    w = np.concatenate([np.asarray(b, dtype=np.float64) for _, b in series]) if ns else np.zeros(0)
+    ends, nseg = _segment_flat(y, w, off, np.arange(ns) if series_ids is None else series_ids, alpha, nperm, seed, ctx,
+                               sequential, eta)
+    cut = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)
+    return [ends[cut[s]:cut[s + 1]].copy() for s in range(ns)]
 
 
 def cbs_stats(ctx: _lib.Context | None = None):
@@ -137,57 +145,92 @@ def cbs_stats(ctx: _lib.Context | None = None):
     return dict(zip(["rounds", "segments_tested", "perm_tests", "t_tests", "permutations", "launches"], out.tolist()))
 
 
+class _Prepared:
+    """CBS.R:30-63 for one sample, on the concatenated bin axis of its chromosomes: `na` (ratio == 0), `cols` (positions
+    of the other bins), `y` / `w` (their ratios and weights, weight 0 -> 1), `base[c]` = first entry of chromosome c in
+    them, `ids` = the chromosomes that are not all NA (the others are dropped, CBS.R:56-63)."""
+    __slots__ = ("offs", "na", "cols", "base", "y", "w", "ids")
+
+
+def _cbs_prepare_flat(r_flat, w_flat, offs):
+    p = _Prepared()
+    p.offs = offs
+    p.na = r_flat == 0  # CBS.R:41
+    p.cols = np.flatnonzero(~p.na)
+    p.y = r_flat[p.cols]
+    p.w = w_flat[p.cols]
+    p.w[p.w == 0] = 1.0  # CBS.R:42 -- 1^-99 is 1 in R
+    p.base = np.searchsorted(p.cols, offs)
+    p.ids = np.flatnonzero(np.diff(p.base) > 0)
+    return p
+
+
 def _cbs_prepare(results_r, results_w, ref_gender):
-    """CBS.R:30-63 for one sample: per chromosome the ratio / weight vectors, the NA mask and the NA-free series."""
+    """CBS.R:30-63 for one sample given as per-chromosome lists.  Returns (prepared, series, ids): the NA-free
+    (ratio, weight) series of the chromosomes `ids` that have any data."""
     nchr = 24 if ref_gender == "M" else 23  # CBS.R:30-34
-    prepared, series, ids = [], [], []
-    for c in range(nchr):
-        ratio = np.asarray(results_r[c], dtype=np.float64)
-        wts = np.asarray(results_w[c], dtype=np.float64).copy()
-        na = ratio == 0  # CBS.R:41
-        wts[wts == 0] = 1.0  # CBS.R:42 -- 1^-99 is 1 in R
-        if na.all():  # CBS.R:56-63
-            continue
-        keep = np.flatnonzero(~na)
-        prepared.append((c, ratio, wts, na, keep))
-        series.append((ratio[keep], wts[keep]))
-        ids.append(c)
-    return prepared, series, ids
+    if len(results_r) < nchr or len(results_w) < nchr:
+        raise IndexError("list index out of range")
+    r_flat = predict_tools.flatten(results_r[:nchr])
+    w_flat = predict_tools.flatten(results_w[:nchr])
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r[:nchr]])]).astype(np.int64)
+    p = _cbs_prepare_flat(r_flat, w_flat, offs)
+    series = [(p.y[p.base[c]:p.base[c + 1]], p.w[p.base[c]:p.base[c + 1]]) for c in p.ids]
+    return p, series, [int(c) for c in p.ids]
 
 
-def _cbs_finish(prepared, all_ends, binsize):
+def _cbs_finish(p, all_ends, binsize):
     """CBS.R:80-129: split the segments over long NA runs, weighted segment means, 0-based half-open coordinates.
-    The NA runs of a chromosome are located once (CBS.R does it per segment, :86-101, with the same result: a segment
-    starts and ends on a non-NA bin, so a run lies inside it or outside)."""
+    all_ends[i] = ascending exclusive ends of the segments of chromosome p.ids[i] in its NA-free series.
+
+    The NA runs of the whole sample are located once (CBS.R does it per segment, :86-101, with the same result: a
+    segment starts and ends on a non-NA bin, so a run lies inside it or outside).  CBS.R only sees runs that begin and
+    end inside the segment, i.e. inside the chromosome: a run that touches a chromosome boundary is no run."""
     na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
+    offs, cols, base = p.offs, p.cols, p.base
+    d = np.diff(p.na.view(np.int8))
+    first = np.flatnonzero(d == 1) + 1   # first NA bin of a run           (CBS.R's start.pos, 1-based: the bin before it)
+    after = np.flatnonzero(d == -1) + 1  # first bin after the run, 0-based (CBS.R's end.pos, 1-based: the last NA bin)
+    if len(p.na) and p.na[0]:
+        after = after[1:]
+    if len(p.na) and p.na[-1]:
+        first = first[:-1]
+    sel = (after - first) > na_thresh  # CBS.R:95
+    first, after = first[sel], after[sel]
+    if len(first):  # no chromosome start inside [first, after]: the run begins and ends within one chromosome
+        inside = np.searchsorted(offs, first, "left") == np.searchsorted(offs, after, "right")
+        first, after = first[inside], after[inside]
+    # segments of all chromosomes: entries [a, b) of the NA-free vectors, first / last bin on the concatenated axis
+    chrom, seg_a, seg_b = [], [], []
+    for c, ends in zip(p.ids, all_ends):
+        ends = np.asarray(ends, dtype=np.int64)
+        seg_b.append(ends + base[c])
+        seg_a.append(np.concatenate([[0], ends[:-1]]) + base[c])
+        chrom.append(np.full(len(ends), c, dtype=np.int64))
+    if not chrom:
+        return []
+    chrom, seg_a, seg_b = np.concatenate(chrom), np.concatenate(seg_a), np.concatenate(seg_b)
+    gs, ge = cols[seg_a], cols[seg_b - 1]  # DNAcopy loc.start / loc.end (here 0-based, concatenated axis)
+    lo = np.searchsorted(first, gs, "right") if len(first) else np.zeros(len(gs), dtype=np.int64)
+    hi = np.searchsorted(first, ge, "left") if len(first) else lo
+    yw = p.y * p.w
     out = []
-    for (c, ratio, wts, na, keep), ends in zip(prepared, all_ends):
-        d = np.diff(na.astype(np.int8))
-        run_first = np.flatnonzero(d == 1) + 1   # first NA bin of a run (0-based) = CBS.R's start.pos (1-based last bin before it)
-        run_after = np.flatnonzero(d == -1) + 1  # first bin after a run (0-based)   = CBS.R's end.pos (1-based last NA bin)
-        if len(na) and na[0]:
-            run_after = run_after[1:]  # a run at the chromosome start has no beginning inside any segment
-        if len(na) and na[-1]:
-            run_first = run_first[:-1]
-        long_run = (run_after - run_first) > na_thresh  # CBS.R:95
-        run_first, run_after = run_first[long_run], run_after[long_run]
-        starts = np.concatenate([[0], ends[:-1]]).astype(np.int64)
-        for a, b in zip(starts.tolist(), np.asarray(ends).tolist()):
-            start_i, end_i = int(keep[a]) + 1, int(keep[b - 1]) + 1  # DNAcopy loc.start / loc.end (1-based)
-            lo = int(np.searchsorted(run_first, start_i - 1, "right")) if len(run_first) else 0
-            hi = int(np.searchsorted(run_first, end_i - 1, "left")) if len(run_first) else 0
-            if hi > lo:
-                inv_start = [start_i] + run_after[lo:hi].tolist()  # CBS.R:100-101
-                inv_end = run_first[lo:hi].tolist() + [end_i]
-            else:
-                inv_start, inv_end = [start_i], [end_i]
-            for s1, e1 in zip(inv_start, inv_end):
-                if e1 - s1 <= 0:  # CBS.R:103
-                    continue
-                yy, ww = ratio[s1 - 1:e1], wts[s1 - 1:e1]
-                m = yy != 0
-                r = float(np.sum(yy[m] * ww[m]) / np.sum(ww[m])) if m.any() else float("nan")  # CBS.R:122-127
-                out.append([c, int(s1) - 1, int(e1), r])  # CBS.R:129, predict_tools.py:266-275
+    for c, a, b, s, e, l, h in zip(chrom.tolist(), seg_a.tolist(), seg_b.tolist(), gs.tolist(), ge.tolist(), lo.tolist(), hi.tolist()):
+        a0 = int(offs[c])
+        if h <= l:
+            if e - s <= 0:  # CBS.R:103
+                continue
+            # the non-zero ratios of bins [s, e] are the entries [a, b) of the NA-free vectors (CBS.R:122-127)
+            out.append([c, s - a0, e - a0 + 1, float(np.sum(yw[a:b]) / np.sum(p.w[a:b]))])  # CBS.R:129, predict_tools.py:266-275
+            continue
+        inv_start = [s + 1] + after[l:h].tolist()  # CBS.R:100-101 (1-based on the concatenated axis)
+        inv_end = first[l:h].tolist() + [e + 1]
+        for s1, e1 in zip(inv_start, inv_end):
+            if e1 - s1 <= 0:  # CBS.R:103
+                continue
+            a1, b1 = np.searchsorted(cols, [s1 - 1, e1])
+            r = float(np.sum(yw[a1:b1]) / np.sum(p.w[a1:b1])) if b1 > a1 else float("nan")
+            out.append([c, s1 - 1 - a0, e1 - a0, r])
     return out
 
 
@@ -215,12 +258,20 @@ def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None
     from .predict_control import _map_threads
     _note_not_bit_compatible()
     seed_i = 0 if seed is None else int(seed)
-    preps, series, ids, counts = [], [], [], []
-    for p, s, i in _map_threads(lambda t: _cbs_prepare(*t), samples):
-        preps.append(p); series += s; ids += i; counts.append(len(s))
-    all_ends = segment_series(series, ids, alpha, nperm, seed_i, ctx)
-    offs = np.concatenate([[0], np.cumsum(counts)]).astype(int)
-    return _map_threads(lambda j: _cbs_finish(preps[j], all_ends[offs[j]:offs[j + 1]], binsize), range(len(preps)))
+    preps = [t[0] for t in _map_threads(lambda t: _cbs_prepare(*t), samples)]
+    lens = [np.diff(p.base)[p.ids] for p in preps]
+    off = np.concatenate([[0], np.cumsum(np.concatenate(lens))]).astype(np.int64) if preps else np.zeros(1, dtype=np.int64)
+    y = np.concatenate([p.y for p in preps]) if preps else np.zeros(0)
+    w = np.concatenate([p.w for p in preps]) if preps else np.zeros(0)
+    ids = np.concatenate([p.ids for p in preps]) if preps else np.zeros(0, dtype=np.int32)
+    ends, nseg = _segment_flat(y, w, off, ids, alpha, nperm, seed_i, ctx)
+    cut = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)  # first segment end of every series
+    first = np.concatenate([[0], np.cumsum([len(p.ids) for p in preps])]).astype(np.int64)  # first series of every sample
+
+    def finish(j):
+        return _cbs_finish(preps[j], [ends[cut[s]:cut[s + 1]] for s in range(first[j], first[j + 1])], binsize)
+
+    return _map_threads(finish, range(len(preps)))
 
 
 def exec_cbs(rem_input, results, engine: predict_tools.PredictEngine | None = None, nperm=10000):

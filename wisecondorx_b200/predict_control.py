@@ -141,9 +141,38 @@ def resolve_genders(args, sample, ref_file):
     return sample, gender, ref_gender
 
 
-def assemble(args, aut, gon, nr, ref_file, ref_gender, gender, n_reads):
+def shared_weights(w_aut, w_gon):
+    """The bin weights of the stacked autosomal + gonosomal result (reference main.py:246-247) and whether they are
+    numeric (:254-259).  They depend on the reference only: once per (reference, gender), not once per sample."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        w = np.append(w_aut * np.nanmean(w_gon), w_gon * np.nanmean(w_aut))
+        w = w / np.nanmean(w)
+    ok = not (np.isnan(w).any() or np.isinf(w).any())
+    return (w if ok else np.ones(len(w))), ok
+
+
+class _Rows:
+    """Output rows of one reference gender: r / z / w [samples, bins] and the bin -> null-ratio-row map, so that the
+    per-chromosome vectors of the samples lie back to back (predict_tools.flatten makes one vector of them for the
+    CBS and z-score calls without a copy)."""
+
+    def __init__(self, b, mask):
+        self.kept = np.flatnonzero(np.asarray(mask, dtype=bool))
+        bins = len(mask)
+        self.r, self.z, self.w = np.zeros((b, bins)), np.zeros((b, bins)), np.zeros((b, bins))
+        self.inflate = np.full((b, bins), -1, dtype=np.int32)
+
+
+def assemble(args, aut, gon, nr, ref_file, ref_gender, gender, n_reads, weights=None, rows=None, row=0):
     """Result assembly of one sample (reference main.py:232-271): aut / gon = (r, z, w, ref_sizes, m_lr, m_z) of the
-    two `normalize` calls, nr = the stacked autosomal + gonosomal null ratios of ref_gender (shared by the batch)."""
+    two `normalize` calls, nr = the stacked autosomal + gonosomal null ratios of ref_gender (shared by the batch).
+
+    get_post_processed_result (predict_control.py:49-63), inflate_results (predict_tools.py:163-170) and log_trans
+    (predict_tools.py:180-193) run here on the kept bins of the whole genome at once instead of per key and per
+    chromosome -- the same elementwise arithmetic, a dozen passes over the bins instead of a hundred NumPy calls per
+    sample.  weights: shared_weights() of the reference gender when the caller has it; rows / row: where a batch
+    wants the sample's vectors (a _Rows of the gender's mask length)."""
     sfx = ".{}".format(ref_gender)
     rem_input = {
         "args": args, "binsize": int(ref_file["binsize"]), "n_reads": n_reads, "ref_gender": ref_gender, "gender": gender,
@@ -153,27 +182,40 @@ def assemble(args, aut, gon, nr, ref_file, ref_gender, gender, n_reads):
     }
     results_r, results_z, results_w, ref_sizes, m_lr, m_z = aut
     r2, z2, w2, n2 = gon[:4]
-    results_r = np.append(results_r, r2)
-    results_z = np.append(results_z, z2) - m_z
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        results_w = np.append(results_w * np.nanmean(w2), w2 * np.nanmean(results_w))
-        results_w = results_w / np.nanmean(results_w)
-    if np.isnan(results_w).any() or np.isinf(results_w).any():
+    w_shared, numeric = weights if weights is not None else shared_weights(results_w, w2)
+    if not numeric:
         logging.warning("Non-numeric values found in weights -- reference too small. Circular binary segmentation and "
                         "z-scoring will be unweighted")
-        results_w = np.ones(len(results_w))
-    ref_sizes = np.append(ref_sizes, n2)
     mask, bpc = rem_input["mask"], rem_input["bins_per_chr"]
-    results = {key: get_post_processed_result(args.minrefbins, val, ref_sizes, mask, bpc)
-               for key, val in (("results_r", results_r), ("results_z", results_z), ("results_w", results_w))}
-    mask_b = np.asarray(mask, dtype=bool)
-    pos = np.arange(int(np.sum(mask_b)), dtype=np.int32)
-    pos[ref_sizes[:len(pos)] < args.minrefbins] = -1  # rows blanked by get_post_processed_result (reference predict_control.py:50-51)
-    inflate = np.full(len(mask_b), -1, dtype=np.int32)
-    inflate[mask_b] = pos
-    results["results_nr"] = {"dense": nr, "inflate": inflate}
-    log_trans(results, m_lr)
+    if rows is None:
+        rows = _Rows(1, mask)
+    kept = rows.kept
+    cnt = len(kept)
+    # the reference's inflate loop hands out results[j] to the j-th kept bin (predict_tools.py:163-170): surplus
+    # results are ignored, missing ones raise.  The counts differ when the gonosomal pass of newref removed
+    # autosomal bins after the autosomal snapshot -- preserved, not fixed.
+    if len(results_r) + len(r2) < cnt:
+        raise IndexError("list index out of range")
+    if len(results_w) + len(w2) != len(results_r) + len(r2):  # the reference's boolean index fails the same way
+        raise IndexError("boolean index did not match indexed array")
+    low = (np.append(ref_sizes, n2) < args.minrefbins)[:cnt]  # predict_control.py:50-51
+    with np.errstate(all="ignore"):
+        lr = np.log2(np.append(results_r, r2)[:cnt])  # predict_tools.py:182
+    bad = ~np.isfinite(lr)
+    bad |= low  # a blanked ratio is 0, its logarithm -inf
+    lr[bad] = 0
+    np.subtract(lr, m_lr, out=lr, where=lr != 0)  # predict_tools.py:189-191
+    z = np.append(results_z, z2)[:cnt] - m_z  # main.py:244
+    z[bad] = 0
+    w = np.array(w_shared[:cnt], dtype=float)
+    w[bad] = 0
+    pos = np.arange(cnt, dtype=np.int32)
+    pos[low] = -1
+    rows.r[row, kept], rows.z[row, kept], rows.w[row, kept], rows.inflate[row, kept] = lr, z, w, pos
+    offs = np.concatenate([[0], np.cumsum(bpc)]).astype(int)
+    results = {key: [val[row, offs[c]:offs[c + 1]] for c in range(len(bpc))]
+               for key, val in (("results_r", rows.r), ("results_z", rows.z), ("results_w", rows.w))}
+    results["results_nr"] = {"dense": nr, "inflate": rows.inflate[row]}
     if getattr(args, "blacklist", None):
         apply_blacklist(args.blacklist, rem_input["binsize"], results)
     return rem_input, results
@@ -222,19 +264,23 @@ def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.Predi
     logging.info("Normalizing autosomes ...")
     r, z, w, n, m_lr, m_z = normalize_batch(args, prepared, ref_file, "A", eng)
     logging.info("Normalizing gonosomes ...")
-    gon = {}
-    nrs = {}
+    gon, nrs, rows, weights, row_of = {}, {}, {}, {}, {}
     for rg in sorted(set(ref_genders)):
         ids = [i for i, x in enumerate(ref_genders) if x == rg]
         r2, z2, w2, n2, _, _ = normalize_batch(args, [prepared[i] for i in ids], ref_file, rg, eng)
         for j, i in enumerate(ids):
             gon[i] = (r2[j], z2[j], w2, n2[j])
+            row_of[i] = j
         nrs[rg] = stacked_null_ratios(ref_file, rg)
+        weights[rg] = shared_weights(w, w2)
+        rows[rg] = _Rows(len(ids), ref_file["mask.{}".format(rg)])
+
     def one(i):
         aut = (r[i], z[i], w, n[i], float(m_lr[i]), float(m_z[i]))
-        return assemble(args, aut, gon[i], nrs[ref_genders[i]], ref_file, ref_genders[i], genders[i], n_reads[i])
+        rg = ref_genders[i]
+        return assemble(args, aut, gon[i], nrs[rg], ref_file, rg, genders[i], n_reads[i], weights[rg], rows[rg], row_of[i])
 
-    out = _map_threads(one, range(len(prepared)))  # ~30 NumPy passes over 2e5 bins per sample: the GIL is released in them
+    out = _map_threads(one, range(len(prepared)))  # a dozen NumPy passes over 2e5 bins per sample: the GIL is released in them
     if timings is not None:
         timings["normalize_and_assemble"] = time.perf_counter() - t0
     t0 = time.perf_counter()

@@ -22,6 +22,36 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def flatten(arrays, dtype=np.float64):
+    """The arrays of a list (the per-chromosome vectors of a sample, of several samples ...) as ONE contiguous vector.
+    No copy when they already lie back to back in one allocation (the result assembly of this package hands out
+    per-chromosome views of one row per sample, the rows of a batch being rows of one matrix): the vector is then a view
+    of that allocation, and writes through the per-chromosome views (blacklisting) show in it."""
+    arrays = list(arrays)
+    dtype = np.dtype(dtype)
+    if not arrays:
+        return np.zeros(0, dtype=dtype)
+    first = arrays[0]
+    if len(arrays) == 1 and isinstance(first, np.ndarray) and first.dtype == dtype and first.ndim == 1 and first.flags.c_contiguous:
+        return first
+    owner = first.base if isinstance(first, np.ndarray) else None
+    if isinstance(owner, np.ndarray) and len(arrays) > 1:
+        nxt, total = first.ctypes.data if first.size else None, 0
+        for a in arrays:
+            if not (isinstance(a, np.ndarray) and a.base is owner and a.dtype == dtype and a.ndim == 1
+                    and (a.size == 0 or (a.strides[0] == dtype.itemsize and (nxt is None or a.ctypes.data == nxt)))):
+                break
+            if a.size:
+                nxt = a.ctypes.data + a.nbytes
+                total += a.size
+        else:
+            if total == 0:
+                return np.zeros(0, dtype=dtype)
+            start = next(a for a in arrays if a.size)
+            return np.lib.stride_tricks.as_strided(start, shape=(total,), strides=(dtype.itemsize,))
+    return np.concatenate([np.asarray(a, dtype=dtype) for a in arrays])
+
+
 def raw_vector(sample, bins_per_chr, out=None):
     """Per-chromosome read counts padded / truncated to the reference's bins_per_chr and
     concatenated (the host half of coverage_normalize_and_mask, predict_tools.py:35-44); the
@@ -183,21 +213,21 @@ def get_z_score_batch(items, engine: PredictEngine | None = None):
     if not items:
         return []
     nr = items[0][1]["results_nr"]["dense"]
-    rs, ws, infl, segs, segr, counts = [], [], [], [], [], []
+    segs, segr, counts = [], [], []
     base = 0
     for results_c, results in items:
         assert results["results_nr"]["dense"] is nr
-        r = np.concatenate([np.asarray(x, dtype=np.float64) for x in results["results_r"]])
         offs = np.concatenate([[0], np.cumsum([len(x) for x in results["results_r"]])]).astype(np.int64)
-        rs.append(r)
-        ws.append(np.concatenate([np.asarray(x, dtype=np.float64) for x in results["results_w"]]))
-        infl.append(results["results_nr"]["inflate"])
-        segs.append(np.array([[base + offs[sg[0]] + sg[1], base + offs[sg[0]] + sg[2]] for sg in results_c], dtype=np.int64).reshape(-1, 2))
-        segr.append(np.array([sg[3] for sg in results_c], dtype=np.float64))
+        sg = np.array([[s[0], s[1], s[2]] for s in results_c], dtype=np.int64).reshape(-1, 3)
+        segs.append(np.stack([base + offs[sg[:, 0]] + sg[:, 1], base + offs[sg[:, 0]] + sg[:, 2]], axis=1))
+        segr.append(np.array([s[3] for s in results_c], dtype=np.float64))
         counts.append(len(results_c))
-        base += len(r)
-    z = (engine or default_engine()).segment_zscore(nr, np.concatenate(infl), np.concatenate(rs), np.concatenate(ws),
-                                                     np.concatenate(segs), np.concatenate(segr))
+        base += int(offs[-1])
+    # (no copies when the samples come from predict_control.assemble_batch: their rows are rows of one matrix)
+    r = flatten([x for _, res in items for x in res["results_r"]])
+    w = flatten([x for _, res in items for x in res["results_w"]])
+    infl = flatten([res["results_nr"]["inflate"] for _, res in items], np.int32)
+    z = (engine or default_engine()).segment_zscore(nr, infl, r, w, np.concatenate(segs), np.concatenate(segr))
     out, o = [], 0
     for c in counts:
         out.append([("nan" if np.isnan(v) else float(v)) for v in z[o:o + c]])
@@ -209,8 +239,8 @@ def get_z_score(results_c, results, engine: PredictEngine | None = None):
     """Drop-in for overall_tools.get_z_score (reference overall_tools.py:88-119): takes the
     reference's per-chromosome list structures and returns a list of floats / the string "nan"."""
     results_nr, results_r, results_w = results["results_nr"], results["results_r"], results["results_w"]
-    r = np.concatenate([np.asarray(x, dtype=np.float64) for x in results_r])
-    w = np.concatenate([np.asarray(x, dtype=np.float64) for x in results_w])
+    r = flatten(results_r)
+    w = flatten(results_w)
     offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r])]).astype(np.int64)
     if isinstance(results_nr, dict):
         # array form used by this package's own pipeline: dense [n_masked, M] rows + unmasked-bin -> row map
