@@ -177,6 +177,23 @@ int wcx_predict_optimal_cutoff(wcx_ctx* ctx, int32_t set_id, int32_t repeats, do
 int wcx_predict_normalize(wcx_ctx* ctx, int32_t set_id, const double* raw, int32_t b, double cutoff,
                           int32_t cp, int64_t ct, double* z, double* r, double* nref, double* m_lr,
                           double* m_z);
+/* Result assembly of a batch of samples that share one reference gender, on HOST threads (no device work, no
+ * context): the stacking of the autosomal and gonosomal `normalize` results with the z-score shift (main.py:242-246),
+ * get_post_processed_result (predict_control.py:49-63), inflate_results (predict_tools.py:163-170) and log_trans
+ * (predict_tools.py:180-193) in one streaming pass per sample.  lr_aut float64 [samples, n_aut]: log2 of the ratios of
+ * the autosomal call (taken by the caller; -inf / NaN where the ratio has no logarithm); z_aut / nref_aut float64
+ * [*, n_aut]: z-scores and reference-bin counts of that call, sample s in row aut_row[s] (the call may have served
+ * samples of the other gender too); lr_gon / z_gon / nref_gon float64 [samples, n_gon]: the same of the gonosomal
+ * call; weights float64 [n_aut + n_gon] (main.py:246-247, shared by the samples); m_lr / m_z float64 [samples]: median
+ * log ratio and median z-score of the autosomal call; mask uint8 [bins]: the reference's mask of this gender.
+ * Outputs [samples, bins]: log ratios, z-scores, weights (0 = no data) and inflate int32 = row of the stacked null
+ * ratios for every bin, -1 where the bin is masked or has fewer than minrefbins reference bins (the map
+ * wcx_segment_zscore takes).  Returns 2 when there are fewer results than kept bins (the reference raises IndexError). */
+int wcx_predict_assemble(const double* lr_aut, const double* z_aut, const double* nref_aut, int64_t n_aut,
+                         const int32_t* aut_row, const double* lr_gon, const double* z_gon, const double* nref_gon,
+                         int64_t n_gon, const double* weights, const double* m_lr, const double* m_z,
+                         int32_t samples, double minrefbins, const uint8_t* mask, int64_t bins, double* out_r,
+                         double* out_z, double* out_w, int32_t* out_inflate, int32_t threads);
 /* get_z_score: nr = null ratios float64 [n_masked, m]; inflate_pos int32 [bins_total] = row of nr
  * for each unmasked bin or -1; r, w float64 [bins_total] = post-processed log2 ratios (0 = no
  * data) and weights; segments as [start, end) offsets into the concatenated bin axis with their

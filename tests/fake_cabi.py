@@ -25,15 +25,25 @@ def _arr(ptr, shape, dtype):
 class FakeLib:
     """See the module docstring."""
 
-    def __init__(self, nasty=False):
+    def __init__(self, nasty=False, real=None):
         self.nasty = nasty
+        if real is None:
+            from wisecondorx_b200 import _lib
+            saved, _lib._lib = _lib._lib, None
+            try:
+                real = _lib.load()
+            finally:
+                _lib._lib = saved
+        # host-only entry points (no device work) are the product's own: the real library serves them
+        self.real = real
+        self.wcx_predict_assemble = real.wcx_predict_assemble
         self.sets = {}
         self.t = 0.0
         self.rng = np.random.default_rng(0)
         self.noise = self.rng.standard_normal(1 << 22)
 
     def wcx_last_error(self):
-        return b"mock"
+        return self.real.wcx_last_error()
 
     def wcx_create(self, device, ref):
         ref._obj.value = 1

@@ -62,10 +62,11 @@ def _fake_normalize(rng, n, nasty=True):
 
 @pytest.mark.parametrize("g,surplus,bad_weights", [("F", 0, False), ("M", 7, False), ("F", 4, True)])
 def test_assemble_equals_pinned_restatement(tmp_path, g, surplus, bad_weights):
-    """predict_control.assemble (whole genome at once) == np_oracle.assemble_results + log_trans + apply_blacklist (per
+    """predict_control.assemble / assemble_batch (one native pass per sample over the bin axis, wcx_predict_assemble:
+    host code, runs here) == np_oracle.assemble_results + log_trans + apply_blacklist (per
     key and per chromosome like the reference, pinned by test_oracle_golden.py) bit for bit: zero / negative / NaN /
     infinite ratios, bins with too few reference bins, more results than kept bins, non-numeric
-    weights, a blacklist; stand-alone and as a row of a batch."""
+    weights, a blacklist; one sample and rows of a batch."""
     rng = np.random.default_rng(11)
     ref, n_aut = fake_cabi.make_ref_file(binsize=500000, k=4, m=6)
     sfx = "." + g
@@ -89,9 +90,12 @@ def test_assemble_equals_pinned_restatement(tmp_path, g, surplus, bad_weights):
     want_inflate = np.full(len(ref["mask" + sfx]), -1, dtype=np.int32)
     want_inflate[ref["mask" + sfx]] = pos
 
-    rows = predict_control._Rows(3, ref["mask" + sfx])
-    for kw in ({}, {"rows": rows, "row": 1}):
-        rem, got = predict_control.assemble(args, aut, gon, nr, ref, g, g, 123, **kw)
+    r5 = lambda x, rows=(1, 3, 4): np.stack([x if i in rows else np.full_like(x, 7.0) for i in range(5)])  # noqa: E731
+    gon3 = lambda x: np.stack([x, x, x])  # noqa: E731
+    batch = predict_control.assemble_batch(args, (r5(aut[0]), r5(aut[1]), aut[2], r5(aut[3]), [9, aut[4], 9, aut[4], aut[4]],
+                                                  [9, aut[5], 9, aut[5], aut[5]]), [3, 1, 4],
+                                           (gon3(gon[0]), gon3(gon[1]), gon[2], gon3(gon[3])), nr, ref, g, [g] * 3, [123] * 3)
+    for rem, got in [predict_control.assemble(args, aut, gon, nr, ref, g, g, 123)] + batch:
         assert rem["ref_gender"] == g and rem["n_reads"] == 123 and rem["binsize"] == 500000
         for key in ("results_r", "results_z", "results_w"):
             assert len(got[key]) == len(want[key]) == (23 if g == "F" else 24)
@@ -101,7 +105,6 @@ def test_assemble_equals_pinned_restatement(tmp_path, g, surplus, bad_weights):
         if bad_weights:
             kept = np.concatenate(got["results_w"]) != 0
             assert kept.any() and np.all(np.concatenate(got["results_w"])[kept] == 1.0)
-    assert not rows.r[0].any() and not rows.r[2].any() and np.all(rows.inflate[0] == -1)  # only the row asked for
     with pytest.raises(IndexError):  # fewer results than kept bins: the reference's inflate loop runs off its list
         predict_control.assemble(args, tuple(a[:-20] if isinstance(a, np.ndarray) else a for a in aut), gon, nr, ref, g, g, 1)
 

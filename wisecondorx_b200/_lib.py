@@ -62,6 +62,7 @@ def load():
     L.wcx_predict_normalize.argtypes = [vp, i32, vp, i32, f64, i32, i64, vp, vp, vp, vp, vp]
     L.wcx_segment_zscore.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, vp, i32, vp]
     L.wcx_predict_stage_ms.argtypes = [vp, vp]
+    L.wcx_predict_assemble.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, i32, f64, vp, i64, vp, vp, vp, vp, i32]
     L.wcx_cbs_segment.argtypes = [vp, vp, vp, vp, i32, vp, f64, i32, ctypes.c_uint32, vp, vp]
     L.wcx_cbs_stats.argtypes = [vp, vp]
     L.wcx_cbs_set_boundary.argtypes = [vp, vp, i32]

@@ -152,17 +152,25 @@ class _Prepared:
     __slots__ = ("offs", "na", "cols", "base", "y", "w", "ids")
 
 
-def _cbs_prepare_flat(r_flat, w_flat, offs):
+def _cbs_prepare_flat(r_flat, w_flat, offs, gather=True):
     p = _Prepared()
     p.offs = offs
     p.na = r_flat == 0  # CBS.R:41
     p.cols = np.flatnonzero(~p.na)
-    p.y = r_flat[p.cols]
-    p.w = w_flat[p.cols]
-    p.w[p.w == 0] = 1.0  # CBS.R:42 -- 1^-99 is 1 in R
     p.base = np.searchsorted(p.cols, offs)
     p.ids = np.flatnonzero(np.diff(p.base) > 0)
+    if gather:
+        _cbs_gather(p, r_flat, w_flat, np.empty(len(p.cols)), np.empty(len(p.cols)))
     return p
+
+
+def _cbs_gather(p, r_flat, w_flat, y_out, w_out):
+    """The NA-free ratios and weights of a prepared sample, written where the caller wants them (a batch lines the
+    samples up in the two vectors of its one device call)."""
+    np.take(r_flat, p.cols, out=y_out, mode="clip")
+    np.take(w_flat, p.cols, out=w_out, mode="clip")
+    w_out[w_out == 0] = 1.0  # CBS.R:42 -- 1^-99 is 1 in R
+    p.y, p.w = y_out, w_out
 
 
 def _cbs_prepare(results_r, results_w, ref_gender):
@@ -201,15 +209,18 @@ def _cbs_finish(p, all_ends, binsize):
         inside = np.searchsorted(offs, first, "left") == np.searchsorted(offs, after, "right")
         first, after = first[inside], after[inside]
     # segments of all chromosomes: entries [a, b) of the NA-free vectors, first / last bin on the concatenated axis
-    chrom, seg_a, seg_b = [], [], []
-    for c, ends in zip(p.ids, all_ends):
-        ends = np.asarray(ends, dtype=np.int64)
-        seg_b.append(ends + base[c])
-        seg_a.append(np.concatenate([[0], ends[:-1]]) + base[c])
-        chrom.append(np.full(len(ends), c, dtype=np.int64))
-    if not chrom:
+    if not len(p.ids):
         return []
-    chrom, seg_a, seg_b = np.concatenate(chrom), np.concatenate(seg_a), np.concatenate(seg_b)
+    counts = np.array([len(e) for e in all_ends], dtype=np.int64)
+    ends = np.concatenate([np.asarray(e, dtype=np.int64) for e in all_ends])
+    if not len(ends):
+        return []
+    chrom = np.repeat(np.asarray(p.ids, dtype=np.int64), counts)
+    seg_a = np.empty(len(ends), dtype=np.int64)
+    seg_a[1:] = ends[:-1]
+    seg_a[(np.cumsum(counts) - counts)[counts > 0]] = 0  # the first segment of a chromosome starts at its first entry
+    seg_a += base[chrom]
+    seg_b = ends + base[chrom]
     gs, ge = cols[seg_a], cols[seg_b - 1]  # DNAcopy loc.start / loc.end (here 0-based, concatenated axis)
     lo = np.searchsorted(first, gs, "right") if len(first) else np.zeros(len(gs), dtype=np.int64)
     hi = np.searchsorted(first, ge, "left") if len(first) else lo
@@ -258,12 +269,27 @@ def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None
     from .predict_control import _map_threads
     _note_not_bit_compatible()
     seed_i = 0 if seed is None else int(seed)
-    preps = [t[0] for t in _map_threads(lambda t: _cbs_prepare(*t), samples)]
+
+    def prepare(t):
+        results_r, results_w, ref_gender = t
+        nchr = 24 if ref_gender == "M" else 23  # CBS.R:30-34
+        if len(results_r) < nchr or len(results_w) < nchr:
+            raise IndexError("list index out of range")
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r[:nchr]])]).astype(np.int64)
+        flat = predict_tools.flatten(results_r[:nchr]), predict_tools.flatten(results_w[:nchr])
+        return _cbs_prepare_flat(flat[0], flat[1], offs, gather=False), flat
+
+    prepared = _map_threads(prepare, samples)
+    preps = [t[0] for t in prepared]
     lens = [np.diff(p.base)[p.ids] for p in preps]
     off = np.concatenate([[0], np.cumsum(np.concatenate(lens))]).astype(np.int64) if preps else np.zeros(1, dtype=np.int64)
-    y = np.concatenate([p.y for p in preps]) if preps else np.zeros(0)
-    w = np.concatenate([p.w for p in preps]) if preps else np.zeros(0)
     ids = np.concatenate([p.ids for p in preps]) if preps else np.zeros(0, dtype=np.int32)
+    # the series of all samples back to back in two page-locked vectors, every sample gathered into its place
+    alloc = _lib.pinned.empty if len(preps) >= 8 else (lambda shape: np.empty(shape, dtype=np.float64))
+    y, w = alloc((max(int(off[-1]), 1),)), alloc((max(int(off[-1]), 1),))
+    at = np.concatenate([[0], np.cumsum([len(p.cols) for p in preps])]).astype(np.int64)
+    _map_threads(lambda j: _cbs_gather(preps[j], prepared[j][1][0], prepared[j][1][1], y[at[j]:at[j + 1]], w[at[j]:at[j + 1]]),
+                 range(len(preps)))
     ends, nseg = _segment_flat(y, w, off, ids, alpha, nperm, seed_i, ctx)
     cut = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)  # first segment end of every series
     first = np.concatenate([[0], np.cumsum([len(p.ids) for p in preps])]).astype(np.int64)  # first series of every sample

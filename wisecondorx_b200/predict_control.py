@@ -6,7 +6,8 @@ import warnings
 
 import numpy as np
 
-from . import predict_tools
+from . import _lib, predict_tools
+from .predict_tools import _ptr
 from .overall_tools import gender_correct, scale_sample
 
 
@@ -152,73 +153,88 @@ def shared_weights(w_aut, w_gon):
     return (w if ok else np.ones(len(w))), ok
 
 
-class _Rows:
-    """Output rows of one reference gender: r / z / w [samples, bins] and the bin -> null-ratio-row map, so that the
-    per-chromosome vectors of the samples lie back to back (predict_tools.flatten makes one vector of them for the
-    CBS and z-score calls without a copy)."""
+def _log2_rows(src, rows):
+    """log2 of the rows `rows` of src into a new matrix (NumPy's log2, one row per task: predict_tools.py:182)."""
+    out = np.empty((len(rows), src.shape[1]))
 
-    def __init__(self, b, mask):
-        self.kept = np.flatnonzero(np.asarray(mask, dtype=bool))
-        bins = len(mask)
-        self.r, self.z, self.w = np.zeros((b, bins)), np.zeros((b, bins)), np.zeros((b, bins))
-        self.inflate = np.full((b, bins), -1, dtype=np.int32)
+    def one(j):
+        with np.errstate(all="ignore"):
+            np.log2(src[rows[j]], out=out[j])
+
+    _map_threads(one, range(len(rows)))
+    return out
 
 
-def assemble(args, aut, gon, nr, ref_file, ref_gender, gender, n_reads, weights=None, rows=None, row=0):
-    """Result assembly of one sample (reference main.py:232-271): aut / gon = (r, z, w, ref_sizes, m_lr, m_z) of the
-    two `normalize` calls, nr = the stacked autosomal + gonosomal null ratios of ref_gender (shared by the batch).
+def assemble_batch(args, aut, aut_rows, gon, nr, ref_file, ref_gender, genders, n_reads, weights=None):
+    """Result assembly (reference main.py:232-271) of the samples of a batch that share the reference gender.
+    aut = (r, z [*, n_aut], w [n_aut], ref_sizes [*, n_aut], m_lr, m_z [*]) of the autosomal normalize_batch call and
+    aut_rows the rows of it these samples occupy; gon = (r2, z2 [b, n_gon], w2 [n_gon], n2 [b, n_gon]) of their
+    gonosomal call; nr = the stacked null ratios of ref_gender; genders / n_reads per sample.  Returns
+    [(rem_input, results), ...].
 
     get_post_processed_result (predict_control.py:49-63), inflate_results (predict_tools.py:163-170) and log_trans
-    (predict_tools.py:180-193) run here on the kept bins of the whole genome at once instead of per key and per
-    chromosome -- the same elementwise arithmetic, a dozen passes over the bins instead of a hundred NumPy calls per
-    sample.  weights: shared_weights() of the reference gender when the caller has it; rows / row: where a batch
-    wants the sample's vectors (a _Rows of the gender's mask length)."""
+    (predict_tools.py:180-193) run as ONE pass per sample over the bin axis on host threads (wcx_predict_assemble,
+    csrc/host_predict.cu) instead of ~100 NumPy calls per sample; the per-chromosome vectors of a sample are views of
+    one row, the rows of the batch rows of one matrix (predict_tools.flatten hands them to the CBS and z-score calls
+    without a copy)."""
+    import os
     sfx = ".{}".format(ref_gender)
-    rem_input = {
-        "args": args, "binsize": int(ref_file["binsize"]), "n_reads": n_reads, "ref_gender": ref_gender, "gender": gender,
-        "mask": ref_file["mask" + sfx], "bins_per_chr": ref_file["bins_per_chr" + sfx],
-        "masked_bins_per_chr": ref_file["masked_bins_per_chr" + sfx],
-        "masked_bins_per_chr_cum": ref_file["masked_bins_per_chr_cum" + sfx],
-    }
-    results_r, results_z, results_w, ref_sizes, m_lr, m_z = aut
+    r, z, w, ref_sizes, m_lr, m_z = aut
     r2, z2, w2, n2 = gon[:4]
-    w_shared, numeric = weights if weights is not None else shared_weights(results_w, w2)
-    if not numeric:
-        logging.warning("Non-numeric values found in weights -- reference too small. Circular binary segmentation and "
-                        "z-scoring will be unweighted")
-    mask, bpc = rem_input["mask"], rem_input["bins_per_chr"]
-    if rows is None:
-        rows = _Rows(1, mask)
-    kept = rows.kept
-    cnt = len(kept)
-    # the reference's inflate loop hands out results[j] to the j-th kept bin (predict_tools.py:163-170): surplus
-    # results are ignored, missing ones raise.  The counts differ when the gonosomal pass of newref removed
-    # autosomal bins after the autosomal snapshot (SURVEY.md A.4) -- preserved, not fixed.
-    if len(results_r) + len(r2) < cnt:
-        raise IndexError("list index out of range")
-    if len(results_w) + len(w2) != len(results_r) + len(r2):  # the reference's boolean index fails the same way
+    b = len(aut_rows)
+    w_shared, numeric = weights if weights is not None else shared_weights(w, w2)
+    mask = np.ascontiguousarray(ref_file["mask" + sfx], dtype=bool)
+    bpc = ref_file["bins_per_chr" + sfx]
+    rows = np.ascontiguousarray(aut_rows, dtype=np.int32)
+    r, z, ref_sizes, r2, z2, n2 = (np.ascontiguousarray(x, dtype=np.float64).reshape(len(x), -1) for x in (r, z, ref_sizes, r2, z2, n2))
+    if len(w_shared) != r.shape[1] + r2.shape[1]:  # the reference's boolean index fails the same way
         raise IndexError("boolean index did not match indexed array")
-    low = (np.append(ref_sizes, n2) < args.minrefbins)[:cnt]  # predict_control.py:50-51
-    with np.errstate(all="ignore"):
-        lr = np.log2(np.append(results_r, r2)[:cnt])  # predict_tools.py:182
-    bad = ~np.isfinite(lr)
-    bad |= low  # a blanked ratio is 0, its logarithm -inf
-    lr[bad] = 0
-    np.subtract(lr, m_lr, out=lr, where=lr != 0)  # predict_tools.py:189-191
-    z = np.append(results_z, z2)[:cnt] - m_z  # main.py:244
-    z[bad] = 0
-    w = np.array(w_shared[:cnt], dtype=float)
-    w[bad] = 0
-    pos = np.arange(cnt, dtype=np.int32)
-    pos[low] = -1
-    rows.r[row, kept], rows.z[row, kept], rows.w[row, kept], rows.inflate[row, kept] = lr, z, w, pos
+    lr = _log2_rows(r, rows)
+    lr2 = _log2_rows(r2, np.arange(b))
+    out_r, out_z, out_w = np.empty((b, len(mask))), np.empty((b, len(mask))), np.empty((b, len(mask)))
+    out_i = np.empty((b, len(mask)), dtype=np.int32)
+    ml = np.ascontiguousarray(np.asarray(m_lr, dtype=np.float64).reshape(-1)[rows])
+    mz = np.ascontiguousarray(np.asarray(m_z, dtype=np.float64).reshape(-1)[rows])
+    w_shared = np.ascontiguousarray(w_shared, dtype=np.float64)
+    mask_u8 = mask.view(np.uint8)
+    rc = _lib.load().wcx_predict_assemble(_ptr(lr), _ptr(z), _ptr(ref_sizes), r.shape[1], _ptr(rows), _ptr(lr2), _ptr(z2), _ptr(n2),
+                                          r2.shape[1], _ptr(w_shared), _ptr(ml), _ptr(mz), b, float(args.minrefbins), _ptr(mask_u8),
+                                          len(mask), _ptr(out_r), _ptr(out_z), _ptr(out_w), _ptr(out_i),
+                                          min(16, max(1, len(os.sched_getaffinity(0)) - 1)))
+    if rc == 2:
+        # the reference's inflate loop hands out results[j] to the j-th kept bin (predict_tools.py:163-170): surplus
+        # results are ignored, missing ones raise.  The counts differ when the gonosomal pass of newref removed
+        # autosomal bins after the autosomal snapshot (SURVEY.md A.4) -- preserved, not fixed.
+        raise IndexError("list index out of range")
+    _lib.check(rc)
     offs = np.concatenate([[0], np.cumsum(bpc)]).astype(int)
-    results = {key: [val[row, offs[c]:offs[c + 1]] for c in range(len(bpc))]
-               for key, val in (("results_r", rows.r), ("results_z", rows.z), ("results_w", rows.w))}
-    results["results_nr"] = {"dense": nr, "inflate": rows.inflate[row]}
-    if getattr(args, "blacklist", None):
-        apply_blacklist(args.blacklist, rem_input["binsize"], results)
-    return rem_input, results
+    out = []
+    for j in range(b):
+        if not numeric:
+            logging.warning("Non-numeric values found in weights -- reference too small. Circular binary segmentation and "
+                            "z-scoring will be unweighted")
+        rem_input = {
+            "args": args, "binsize": int(ref_file["binsize"]), "n_reads": n_reads[j], "ref_gender": ref_gender, "gender": genders[j],
+            "mask": ref_file["mask" + sfx], "bins_per_chr": bpc,
+            "masked_bins_per_chr": ref_file["masked_bins_per_chr" + sfx],
+            "masked_bins_per_chr_cum": ref_file["masked_bins_per_chr_cum" + sfx],
+        }
+        results = {key: [val[j, offs[c]:offs[c + 1]] for c in range(len(bpc))]
+                   for key, val in (("results_r", out_r), ("results_z", out_z), ("results_w", out_w))}
+        results["results_nr"] = {"dense": nr, "inflate": out_i[j]}
+        if getattr(args, "blacklist", None):
+            apply_blacklist(args.blacklist, rem_input["binsize"], results)
+        out.append((rem_input, results))
+    return out
+
+
+def assemble(args, aut, gon, nr, ref_file, ref_gender, gender, n_reads, weights=None):
+    """Result assembly of one sample (reference main.py:232-271): aut / gon = (r, z, w, ref_sizes, m_lr, m_z) of the
+    two `normalize` calls, nr = the stacked autosomal + gonosomal null ratios of ref_gender."""
+    r, z, w, n, m_lr, m_z = aut
+    one = lambda x: np.asarray(x, dtype=np.float64).reshape(1, -1)  # noqa: E731
+    return assemble_batch(args, (one(r), one(z), w, one(n), [m_lr], [m_z]), [0], (one(gon[0]), one(gon[1]), gon[2], one(gon[3])),
+                          nr, ref_file, ref_gender, [gender], [n_reads], weights)[0]
 
 
 def stacked_null_ratios(ref_file, ref_gender):
@@ -226,6 +242,8 @@ def stacked_null_ratios(ref_file, ref_gender):
     dense [rows, M] array (NaN padded when the two sets were built with different numbers of null samples)."""
     nr_aut = ref_file["null_ratios"]
     nr_gon = ref_file["null_ratios.{}".format(ref_gender)][len(nr_aut):]
+    if len(nr_gon) and nr_gon.shape[1] == nr_aut.shape[1]:
+        return np.concatenate([nr_aut, nr_gon]).astype(np.float64, copy=False)
     m = max(nr_aut.shape[1], nr_gon.shape[1] if len(nr_gon) else 0)
     nr = np.full((len(nr_aut) + len(nr_gon), m), np.nan)
     nr[:len(nr_aut), :nr_aut.shape[1]] = nr_aut
@@ -241,7 +259,9 @@ def _map_threads(fn, items, min_items=4):
     items = list(items)
     if len(items) < min_items:
         return [fn(i) for i in items]
-    with ThreadPoolExecutor(min(16, len(items), max(1, len(os.sched_getaffinity(0)) - 1))) as pool:
+    # (more threads than this lose to the interpreter lock between the NumPy calls: 8 cores, batch of 96: 1.26 / 0.87 /
+    # 1.25 s on 2 / 4 / 6 threads)
+    with ThreadPoolExecutor(min(6, len(items), max(1, len(os.sched_getaffinity(0)) // 2))) as pool:
         return list(pool.map(fn, items))
 
 
@@ -264,23 +284,14 @@ def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.Predi
     logging.info("Normalizing autosomes ...")
     r, z, w, n, m_lr, m_z = normalize_batch(args, prepared, ref_file, "A", eng)
     logging.info("Normalizing gonosomes ...")
-    gon, nrs, rows, weights, row_of = {}, {}, {}, {}, {}
+    out = [None] * len(prepared)
     for rg in sorted(set(ref_genders)):
         ids = [i for i, x in enumerate(ref_genders) if x == rg]
         r2, z2, w2, n2, _, _ = normalize_batch(args, [prepared[i] for i in ids], ref_file, rg, eng)
-        for j, i in enumerate(ids):
-            gon[i] = (r2[j], z2[j], w2, n2[j])
-            row_of[i] = j
-        nrs[rg] = stacked_null_ratios(ref_file, rg)
-        weights[rg] = shared_weights(w, w2)
-        rows[rg] = _Rows(len(ids), ref_file["mask.{}".format(rg)])
-
-    def one(i):
-        aut = (r[i], z[i], w, n[i], float(m_lr[i]), float(m_z[i]))
-        rg = ref_genders[i]
-        return assemble(args, aut, gon[i], nrs[rg], ref_file, rg, genders[i], n_reads[i], weights[rg], rows[rg], row_of[i])
-
-    out = _map_threads(one, range(len(prepared)))  # a dozen NumPy passes over 2e5 bins per sample: the GIL is released in them
+        group = assemble_batch(args, (r, z, w, n, m_lr, m_z), ids, (r2, z2, w2, n2), eng.stacked_null_ratios(ref_file, rg),
+                               ref_file, rg, [genders[i] for i in ids], [n_reads[i] for i in ids])
+        for i, res in zip(ids, group):
+            out[i] = res
     if timings is not None:
         timings["normalize_and_assemble"] = time.perf_counter() - t0
     t0 = time.perf_counter()

@@ -56,14 +56,17 @@ def raw_vector(sample, bins_per_chr, out=None):
     """Per-chromosome read counts padded / truncated to the reference's bins_per_chr and
     concatenated (the host half of coverage_normalize_and_mask, predict_tools.py:35-44); the
     division by the total and the masking happen on the device.  `out`: row of a preallocated batch matrix."""
+    total = int(np.sum(bins_per_chr))
     if out is None:
-        out = np.zeros(int(np.sum(bins_per_chr)), dtype=np.float64)
-    else:
-        out[:] = 0.0
+        out = np.empty(total, dtype=np.float64)
+    parts = [np.asarray(sample[str(c + 1)]) for c in range(len(bins_per_chr))]
+    if all(len(a) == int(nb) and a.ndim == 1 for a, nb in zip(parts, bins_per_chr)):
+        np.concatenate(parts, out=out[:total], casting="unsafe")  # the usual case: sample and reference binned alike
+        return out
+    out[:] = 0.0
     off = 0
-    for c, nb in enumerate(bins_per_chr):
+    for a, nb in zip(parts, bins_per_chr):
         nb = int(nb)
-        a = np.asarray(sample[str(c + 1)])
         m = min(nb, len(a))
         out[off:off + m] = a[:m]
         off += nb
@@ -105,6 +108,16 @@ class PredictEngine:
         _lib.check(L.wcx_predict_load_ref(self.ctx.handle, SET_ID[ap], _ptr(idx), _ptr(dist), n, k, _ptr(per), _ptr(cum),
                                           len(cum), _ptr(comps), _ptr(mean), comps.shape[0], _ptr(mask_pos), int(len(mask))))
         sets[ap] = (ref_file, {"n": n, "k": k, "cum": cum, "bins_per_chr": bpc, "bins_total": int(len(mask))})
+
+    def stacked_null_ratios(self, ref_file, ref_gender):
+        """predict_control.stacked_null_ratios, built once per resident reference (165 MB at 15 kb); the same array
+        object on every call also keeps the copy on the device valid (segment_zscore uploads per array object)."""
+        self._ensure_ref(ref_file, "")
+        cache = self.ctx.predict_sets[""][1].setdefault("stacked_nr", {})
+        if ref_gender not in cache:
+            from .predict_control import stacked_null_ratios
+            cache[ref_gender] = stacked_null_ratios(ref_file, ref_gender)
+        return cache[ref_gender]
 
     def get_weights(self, ref_file, ap):
         """get_weights (predict_tools.py:152-155); a function of the reference only: computed once per resident set."""
