@@ -186,3 +186,32 @@ def test_cbs_batch_host_side_equals_oracle_postprocessing(fake_library):
         assert len(segs) == len(want) > 20
         for a, b in zip(segs, want):
             assert a[:3] == b[:3] and _eq(a[3], b[3]), (a, b)
+
+
+def test_segment_batch_series(fake_library):
+    """predict_control.segment_batch hands the device call the same (sample, chromosome) series as the plain
+    per-series construction: bins without a finite non-zero log ratio or with too few reference bins dropped, an empty
+    chromosome, a chromosome without data."""
+    rng = np.random.default_rng(0)
+    b, n = 5, 4000
+    offs = np.array([0, 700, 700, 1500, 2600, 4000])
+    r = 1 + 0.05 * rng.standard_normal((b, n))
+    for p, v in ((0.05, 0.0), (0.01, np.nan), (0.01, -1.0), (0.02, 1.0)):
+        r[rng.random((b, n)) < p] = v
+    r[2, 700:1500] = 0
+    nref = np.full((b, n), 300.0)
+    nref[rng.random((b, n)) < 0.05] = 10
+    w = rng.uniform(0.5, 2, n)
+    m_lr = rng.normal(0, 0.01, b)
+    series = []
+    for i in range(b):
+        with np.errstate(all="ignore"):
+            lr = np.log2(r[i]) - m_lr[i]
+        ok = np.isfinite(lr) & (nref[i] >= 150) & (lr != 0)
+        for c in range(len(offs) - 1):
+            m = ok[offs[c]:offs[c + 1]]
+            series.append((lr[offs[c]:offs[c + 1]][m], w[offs[c]:offs[c + 1]][m]))
+    want = cbs.segment_series(series, [i % 5 for i in range(len(series))], alpha=1e-4, nperm=100, seed=3)
+    got = predict_control.segment_batch(r, w, nref, m_lr, offs, nperm=100, seed=3)
+    assert len(got) == len(want) == 25 and sum(len(x) for x in want) > 30
+    assert all(np.array_equal(a, c) for a, c in zip(got, want))

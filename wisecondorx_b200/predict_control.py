@@ -50,15 +50,26 @@ def segment_batch(r, w, nref, m_lr, chr_offsets, minrefbins=150, alpha=1e-4, npe
     from . import cbs
     offs = np.asarray(chr_offsets, dtype=np.int64)
     nchr = len(offs) - 1
-    series = []
-    for i in range(r.shape[0]):
+    w = np.asarray(w, dtype=np.float64)
+
+    def one(i):  # the kept bins of the whole sample at once; the chromosomes are ranges of them
         with np.errstate(all="ignore"):
             lr = np.log2(r[i]) - m_lr[i]
-        ok = np.isfinite(lr) & (nref[i] >= minrefbins) & (lr != 0)
-        for c in range(nchr):
-            m = ok[offs[c]:offs[c + 1]]
-            series.append((lr[offs[c]:offs[c + 1]][m], w[offs[c]:offs[c + 1]][m]))
-    return cbs.segment_series(series, [i % nchr for i in range(len(series))], alpha=alpha, nperm=nperm, seed=seed, ctx=ctx)
+        ok = np.isfinite(lr)
+        ok &= nref[i] >= minrefbins
+        ok &= lr != 0
+        cols = np.flatnonzero(ok)
+        cols = cols[(cols >= offs[0]) & (cols < offs[-1])]
+        return lr[cols], w[cols], np.diff(np.searchsorted(cols, offs))
+
+    parts = _map_threads(one, range(r.shape[0]))
+    if not parts:
+        return []
+    off = np.concatenate([[0], np.cumsum(np.concatenate([p[2] for p in parts]))]).astype(np.int64)
+    ends, nseg = cbs._segment_flat(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), off,
+                                   np.tile(np.arange(nchr, dtype=np.int32), len(parts)), alpha, nperm, seed, ctx)
+    cut = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)
+    return [ends[cut[s]:cut[s + 1]].copy() for s in range(len(off) - 1)]
 
 
 # ---------------------------------------------------------------------------------------------
