@@ -210,6 +210,7 @@ def cli_and_predict_extras(device, n_train=500, binsize=15000, batch=96, cpu_bas
                       "predict_segments": len(res["results_c"]),
                       "planted_gain_found": any(x[0] == "5" and x[5] == "gain" for x in ab)}
         # ---- predict batches through the library flow
+        out["predict"] = {"error": "not finished"}  # replaced below; what the line shows if this part raises
         ref_file = npz_io.load_npz(ref)
         eng = predict_tools.PredictEngine(device)
         args = types.SimpleNamespace(maskrepeats=5, minrefbins=150, alpha=1e-4, seed=1, gender=None, blacklist=None, zscore=5, beta=None)
@@ -255,6 +256,12 @@ def cli_and_predict_extras(device, n_train=500, binsize=15000, batch=96, cpu_bas
         if cpu_baseline:
             pred["cpu_baseline"] = predict_cpu_baseline(tests[0], ref_file, outs[0] if batches[-1] == 1 else None, args)
         out["predict"] = pred
+    except Exception as e:  # the parts measured so far stay in the line
+        import traceback
+        traceback.print_exc()
+        out.setdefault("cli", {"error": repr(e)})
+        if "error" in out.get("predict", {"error": 1}):
+            out["predict"] = {"error": repr(e)}
     finally:
         shutil.rmtree(d, ignore_errors=True)
     return out
@@ -484,7 +491,12 @@ def run_ours(args, rank, world, local_rank):
                             and np.array_equal(ho[2][rb:re], nr_dev.cpu().numpy(), equal_nan=True))
             predict_sharded = None
             if not args.no_predict:
-                predict_sharded = predict_sharded_extras(eng, x, per, cum, np.array(ho[0]), np.array(ho[1]), local_rank, rank, world)
+                try:  # an extra: its failure must not cost the headline line (every rank runs the same host code)
+                    predict_sharded = predict_sharded_extras(eng, x, per, cum, np.array(ho[0]), np.array(ho[1]), local_rank, rank, world)
+                except Exception as e:
+                    import traceback
+                    traceback.print_exc()
+                    predict_sharded = {"error": repr(e)}
             del ho
             sr.close()
             e2e_path = "sliced H2D + NCCL all-gather of X, row blocks written by every rank into one shared pinned host segment"
@@ -564,7 +576,13 @@ def run_ours(args, rank, world, local_rank):
                      "listed_candidates_per_row": eng.stage_ms()["gathered_entries"] / max(1, rows)},
     }
     if world == 1 and not args.no_predict:
-        out.update(cli_and_predict_extras(local_rank, cpu_baseline=not args.no_cpu_baseline))
+        try:  # extras beside the headline: a failure is reported in their place, not instead of the line
+            out.update(cli_and_predict_extras(local_rank, cpu_baseline=not args.no_cpu_baseline))
+        except (Exception, SystemExit) as e:
+            import traceback
+            traceback.print_exc()
+            out.setdefault("cli", {"error": repr(e)})
+            out.setdefault("predict", {"error": repr(e)})
     if world > 1 and predict_sharded is not None:
         out["predict"] = {"batch96_sharded": predict_sharded}
     # parity of THIS run's result at THIS configuration: the oracle's rows against the GPU arrays (the CPU baseline's
