@@ -266,7 +266,7 @@ def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None
     """CBS.R for a batch of samples [(results_r, results_w, ref_gender), ...] with ONE device call over all
     (sample, chromosome) series.  The permutation streams are keyed by (seed, chromosome), not by the position of a
     series in the batch, so every sample gets the segments it would get alone."""
-    from .predict_control import _map_threads
+    _map_threads = predict_tools.map_threads
     _note_not_bit_compatible()
     seed_i = 0 if seed is None else int(seed)
 

@@ -7,7 +7,7 @@ import warnings
 import numpy as np
 
 from . import _lib, predict_tools
-from .predict_tools import _ptr
+from .predict_tools import _ptr, map_threads as _map_threads
 from .overall_tools import gender_correct, scale_sample
 
 
@@ -263,19 +263,6 @@ def stacked_null_ratios(ref_file, ref_gender):
     return nr
 
 
-def _map_threads(fn, items, min_items=4):
-    """fn over items on a thread pool (host post-processing of a batch: NumPy releases the GIL in its loops)."""
-    import os
-    from concurrent.futures import ThreadPoolExecutor
-    items = list(items)
-    if len(items) < min_items:
-        return [fn(i) for i in items]
-    # (more threads than this lose to the interpreter lock between the NumPy calls: 8 cores, batch of 96: 1.26 / 0.87 /
-    # 1.25 s on 2 / 4 / 6 threads)
-    with ThreadPoolExecutor(min(6, len(items), max(1, len(os.sched_getaffinity(0)) // 2))) as pool:
-        return list(pool.map(fn, items))
-
-
 def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.PredictEngine | None = None, timings=None):
     """Everything `predict` computes before the output writers, for a batch of raw samples against one reference:
     re-binning, gender, both `normalize` calls (the autosomal one for the whole batch at once, the gonosomal one per
@@ -286,12 +273,14 @@ def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.Predi
     from . import cbs
     eng = engine or predict_tools.default_engine()
     t0 = time.perf_counter()
-    prepared, genders, ref_genders, n_reads = [], [], [], []
-    for sample, bs in zip(samples, binsizes):
-        n_reads.append(int(sum(int(np.sum(sample[x], dtype=np.int64)) for x in sample.keys())))
+    def prelude(t):
+        sample, bs = t
+        reads = int(sum(int(np.sum(sample[x], dtype=np.int64)) for x in sample.keys()))
         sample = scale_sample(dict(sample), int(bs), int(ref_file["binsize"]))
-        sample, g, rg = resolve_genders(args, sample, ref_file)
-        prepared.append(sample); genders.append(g); ref_genders.append(rg)
+        return resolve_genders(args, sample, ref_file) + (reads,)
+
+    pre = _map_threads(prelude, list(zip(samples, binsizes)))
+    prepared, genders, ref_genders, n_reads = ([p[i] for p in pre] for i in range(4))
     logging.info("Normalizing autosomes ...")
     r, z, w, n, m_lr, m_z = normalize_batch(args, prepared, ref_file, "A", eng)
     logging.info("Normalizing gonosomes ...")
