@@ -55,6 +55,12 @@ def test_get_mask_and_gender_model(R):
         want_sub, want_sub_bpc = R.newref_tools.get_mask(arr[sub])
         got_sub, got_sub_bpc = wcx_main.get_mask(arr[sub], counts_all, np.flatnonzero(sub))
         assert np.array_equal(got_sub, want_sub) and list(got_sub_bpc) == list(want_sub_bpc)
+        # the count matrix of a gonosomal pass: row prefix + column subset of the stacked matrix (threaded copy)
+        rows = counts_all.shape[0] - 7
+        taken = newref_tools.take_columns(counts_all, rows, np.flatnonzero(sub))
+        assert taken.flags.c_contiguous and taken.dtype == counts_all.dtype
+        assert np.array_equal(taken, counts_all[:rows][:, sub])
+        assert np.array_equal(taken, newref_tools.stack_counts(list(arr[sub]), range(1, 25))[:rows])
     short = [dict(smp) for smp in arr[:5]]  # a subset with fewer bins than the stacked matrix: falls back to its own stack
     for smp in short:
         smp["7"] = smp["7"][:-3]

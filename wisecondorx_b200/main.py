@@ -171,7 +171,7 @@ def tool_newref(args):
         pass_counts = None
         if counts_all is not None and [max(len(s[str(c)]) for s in sample_list) for c in range(1, 25)] == list(bins_per_chr):
             rows_of_pass = int(sum(bins_per_chr[:last]))
-            pass_counts = counts_all[:rows_of_pass] if gender == "A" else np.ascontiguousarray(counts_all[:rows_of_pass][:, g == gender])
+            pass_counts = counts_all[:rows_of_pass] if gender == "A" else newref_tools.take_columns(counts_all, rows_of_pass, np.flatnonzero(g == gender))
         prep = newref_control.tool_newref_prep(sample_list, gender, total_mask, bins_per_chr, device, counts=pass_counts)
         t2 = time.perf_counter()
         wait_copier()  # the page-locked staging arrays are free again (the copy ran beside the preparation above)

@@ -244,6 +244,26 @@ def stack_counts(samples, chrs):
     return out
 
 
+def take_columns(counts, rows, cols):
+    """counts[:rows][:, cols] as a new C-contiguous matrix (the count matrix of a gonosomal pass: a row prefix and a
+    column subset of the stacked matrix of all samples), row blocks on a thread pool: the plain fancy index is one
+    strided gather on one core (0.8 s for 250 of 500 columns at 15 kb, 0.05 s here)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    rows = int(rows)
+    out = np.empty((rows, len(cols)), dtype=counts.dtype)
+    nthreads = max(1, min(16, len(os.sched_getaffinity(0))))
+    step = max(1024, -(-rows // (4 * nthreads)))
+
+    def block(a):
+        np.take(counts[a:min(rows, a + step)], cols, axis=1, out=out[a:min(rows, a + step)])
+
+    with ThreadPoolExecutor(nthreads) as pool:
+        list(pool.map(block, range(0, rows, step)))
+    return out
+
+
 def normalize_and_mask(samples, chrs, mask, device: int = 0):
     """Drop-in for newref_tools.normalize_and_mask (reference :110-129): read-depth normalisation
     (each sample divided by its total) and masking.  Bit-exact with the reference."""
