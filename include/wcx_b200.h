@@ -49,6 +49,19 @@ int wcx_sync(wcx_ctx* ctx);
 int wcx_host_alloc(uint64_t bytes, void** out);
 int wcx_host_free(void* p);
 
+/* ---- host-side preparation of newref (host threads, no device work, no context) -----------
+ * wcx_host_stack_counts: the read counts of all samples as ONE matrix int32 [rows, samples] (the fill of `all_data`,
+ * newref_tools.py:81-92 / :114-122): columns[s * nchr + c] -> the int32 counts of chromosome c of sample s
+ * (lens[s * nchr + c] of them), chromosome c occupies rows offs[c] - offs[0] ... offs[c + 1] - offs[0], shorter
+ * samples are zero padded.
+ * wcx_host_bin_sums: out[b] = sum over the samples j of counts[b, cols[j]] / col_sum[j] (cols == NULL: all columns) --
+ * np.sum(all_data / sum_per_sample, 1) of get_mask (newref_tools.py:94-97) with one division per element and the
+ * additions in the order of NumPy's pairwise summation, i.e. the same float64 value. */
+int wcx_host_stack_counts(const int32_t* const* columns, const int64_t* lens, int32_t samples, int32_t nchr,
+                          const int64_t* offs, int32_t* out, int32_t threads);
+int wcx_host_bin_sums(const int32_t* counts, int64_t bins, int32_t samples, const int32_t* cols, int32_t ncols,
+                      const double* col_sum, double* out, int32_t threads);
+
 /* ---- newref ------------------------------------------------------------------------------
  * Replaces get_reference (newref_tools.py:155-224): get_ref_for_bins (:255-278) and the
  * null-ratio loop (:210-224).

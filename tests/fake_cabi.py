@@ -42,6 +42,11 @@ class FakeLib:
         self.rng = np.random.default_rng(0)
         self.noise = self.rng.standard_normal(1 << 22)
 
+    def __getattr__(self, name):
+        if name in ("wcx_host_stack_counts", "wcx_host_bin_sums"):  # host-only: the real library
+            return getattr(self.real, name)
+        raise AttributeError(name)
+
     def wcx_last_error(self):
         return self.real.wcx_last_error()
 

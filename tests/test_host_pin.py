@@ -54,6 +54,7 @@ def test_get_mask_and_gender_model(R):
     for sub in (np.ones(len(arr), bool), g == "F", g == "M", np.arange(len(arr)) % 3 == 0):
         want_sub, want_sub_bpc = R.newref_tools.get_mask(arr[sub])
         got_sub, got_sub_bpc = wcx_main.get_mask(arr[sub], counts_all, np.flatnonzero(sub))
+        assert np.array_equal(wcx_main.get_mask(arr[sub], counts_all, np.flatnonzero(sub), newref_tools.column_totals(counts_all))[0], want_sub)
         assert np.array_equal(got_sub, want_sub) and list(got_sub_bpc) == list(want_sub_bpc)
         # the count matrix of a gonosomal pass: row prefix + column subset of the stacked matrix (threaded copy)
         rows = counts_all.shape[0] - 7
@@ -233,3 +234,60 @@ def test_ref_qc_matches_reference(R, tmp_path, caplog):
         a = ref_qc.compute_metrics(ref, sfx)
         b = R.ref_qc._compute_metrics(ref, sfx)
         assert a == b
+
+
+def test_stack_counts_native_equals_column_fill():
+    """newref_tools.stack_counts (wcx_host_stack_counts: blocked transposition on host threads) == the reference's
+    column-by-column fill (newref_tools.py:81-92): ragged samples, empty chromosomes, other integer / float dtypes,
+    chromosome subsets; column_totals; take_columns."""
+    from wisecondorx_b200 import newref_tools
+    rng = np.random.default_rng(0)
+
+    def fill(samples, chrs):
+        chrs = list(chrs)
+        lens = [max(len(s[str(c)]) for s in samples) for c in chrs]
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(int)
+        out = np.zeros((offs[-1], len(samples)), dtype=np.int32)
+        for i, s in enumerate(samples):
+            for c, o in zip(chrs, offs[:-1]):
+                out[o:o + len(s[str(c)]), i] = s[str(c)]
+        return out
+
+    for trial in range(12):
+        samples = []
+        for i in range(int(rng.integers(1, 40))):
+            s = {}
+            for c in range(1, 25):
+                n = int(rng.integers(0, 60)) if trial % 3 else 37
+                n = 0 if (trial % 4 == 0 and c == 5) else n
+                dt = [np.int32, np.int64, np.float64, np.uint16][int(rng.integers(0, 4))] if trial % 2 else np.int32
+                s[str(c)] = rng.integers(0, 1000, n).astype(dt)
+            samples.append(s)
+        for chrs in (range(1, 25), range(1, 23), [3], [5, 6]):
+            got = newref_tools.stack_counts(samples, chrs)
+            assert got.dtype == np.int32 and got.flags.c_contiguous and np.array_equal(got, fill(samples, chrs))
+        assert np.array_equal(newref_tools.column_totals(got), got.sum(0, dtype=np.int64))
+    big, _ = synth.make_samples(21, 200000, seed=4)
+    got = newref_tools.stack_counts(big, range(1, 25))
+    assert np.array_equal(got, fill(big, range(1, 25)))
+    assert np.array_equal(newref_tools.column_totals(got), got.sum(0, dtype=np.int64))
+
+
+@pytest.mark.parametrize("s", [1, 5, 8, 9, 64, 127, 128, 129, 255, 256, 257, 500, 777, 1100, 2049])
+def test_bin_sums_native_equals_numpy_row_sums(s):
+    """newref_tools.bin_sums (wcx_host_bin_sums) returns the float64 VALUE of np.sum(counts / col_sum, 1) -- NumPy's
+    pairwise order replayed for every row length class -- for all columns and for a column subset."""
+    from wisecondorx_b200 import newref_tools
+    rng = np.random.default_rng(s)
+    counts = rng.poisson(30.0, (301, s)).astype(np.int32)
+    counts[rng.random(counts.shape) < 0.1] = 0
+    counts[7] = 0
+    col = counts.sum(0, dtype=np.int64).astype(float)
+    want = np.sum(counts.astype(float) / col, 1)
+    assert np.array_equal(newref_tools.bin_sums(counts, col), want, equal_nan=True)
+    cols = np.flatnonzero(rng.random(s) < 0.5)
+    if len(cols):
+        # (the subset's own C-ordered matrix, as the reference builds it: a fancy column index alone is F-ordered and
+        # NumPy then adds column by column)
+        want = np.sum(np.ascontiguousarray(counts[:, cols]).astype(float) / col[cols], 1)
+        assert np.array_equal(newref_tools.bin_sums(counts, col[cols], cols), want, equal_nan=True)

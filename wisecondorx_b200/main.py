@@ -49,35 +49,24 @@ def train_gender_model(args, samples):
     return genders.tolist(), cut_off
 
 
-def _row_chunks(total, nthreads):
-    step = max(4096, -(-total // (4 * nthreads)))
-    return [(a, min(total, a + step)) for a in range(0, total, step)]
-
-
-def get_mask(samples, counts=None, cols=None):
+def get_mask(samples, counts=None, cols=None, totals=None):
     """Bins with more than 5 % of the median (non-zero) summed normalised coverage (reference newref_tools.py:77-102).
     Same arithmetic as the reference, element for element -- exact column totals (integers), one division per element,
-    NumPy's pairwise sum along each contiguous row -- but the [bins, samples] float matrix (0.8 GB at 15 kb / 500
-    samples) is never materialised: row chunks go through a thread pool (NumPy releases the GIL in these loops).
+    the additions of a bin in NumPy's pairwise order -- but the [bins, samples] float matrix (0.8 GB at 15 kb / 500
+    samples) is never materialised: newref_tools.bin_sums walks the int32 count matrix on host threads.
     counts / cols: the stacked count matrix of a superset of `samples` with the same bins per chromosome and the columns
-    of `samples` in it (tool_newref stacks the samples once for the three masks and the three passes)."""
-    from concurrent.futures import ThreadPoolExecutor
+    of `samples` in it (tool_newref stacks the samples once for the three masks and the three passes); totals: the
+    column totals of that matrix (newref_tools.column_totals) when the caller has them."""
     bins_per_chr = [max(len(s[str(c)]) for s in samples) for c in range(1, 25)]
     total = int(sum(bins_per_chr))
-    nthreads = max(1, min(16, len(os.sched_getaffinity(0))))
     if counts is None or counts.shape[0] != total:
-        counts, cols = newref_tools.stack_counts(samples, range(1, 25)), None  # int32 [total, S], zero padded
-    col_sum = np.sum(counts, 0, dtype=np.int64).astype(float)   # exact, like the float sum of integer counts
+        counts, cols, totals = newref_tools.stack_counts(samples, range(1, 25)), None, None  # int32 [total, S], zero padded
+    if totals is None:
+        totals = newref_tools.column_totals(counts)
+    col_sum = np.asarray(totals, dtype=np.int64).astype(float)   # exact, like the float sum of integer counts
     if cols is not None:
         col_sum = col_sum[cols]
-
-    def rows(ab):
-        a, b = ab
-        block = counts[a:b] if cols is None else counts[a:b][:, cols]  # the subset's own matrix, row block by row block
-        return np.sum(block.astype(float) / col_sum, 1)
-
-    with ThreadPoolExecutor(nthreads) as pool:
-        sum_per_bin = np.concatenate(list(pool.map(rows, _row_chunks(total, nthreads)))) if total else np.zeros(0)
+    sum_per_bin = newref_tools.bin_sums(counts, col_sum, cols)
     median_cov = np.median(sum_per_bin[sum_per_bin > 0])
     return sum_per_bin > (0.05 * median_cov), bins_per_chr
 
@@ -139,12 +128,13 @@ def tool_newref(args):
             samples[i] = gender_correct(sample, genders[i])
     # one stacked count matrix [bins, samples] for the three masks and the three passes (each used to stack its own)
     counts_all = newref_tools.stack_counts(list(samples), range(1, 25)) if len(samples) else None
-    total_mask, bins_per_chr = get_mask(samples, counts_all)
+    totals = newref_tools.column_totals(counts_all) if counts_all is not None else None
+    total_mask, bins_per_chr = get_mask(samples, counts_all, None, totals)
     g = np.array(genders)
     if genders.count("F") > 4:
-        total_mask = total_mask & get_mask(samples[g == "F"], counts_all, np.flatnonzero(g == "F"))[0]
+        total_mask = total_mask & get_mask(samples[g == "F"], counts_all, np.flatnonzero(g == "F"), totals)[0]
     if genders.count("M") > 4 and not args.nipt:
-        total_mask = total_mask & get_mask(samples[g == "M"], counts_all, np.flatnonzero(g == "M"))[0]
+        total_mask = total_mask & get_mask(samples[g == "M"], counts_all, np.flatnonzero(g == "M"), totals)[0]
     device = getattr(args, "device", 0)
     gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     devices = [device + g for g in range(gpus)]

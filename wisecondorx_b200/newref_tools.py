@@ -210,37 +210,46 @@ def _finish_components(comps, pcacomp):
 
 def stack_counts(samples, chrs):
     """int32 [bins_total, S]: per-chromosome read counts of every sample, zero padded to the longest
-    sample (host half of normalize_and_mask, newref_tools.py:114-122).  Samples are written by a few threads (every
-    sample is one strided column of the result)."""
+    sample (host half of normalize_and_mask, newref_tools.py:114-122).  One blocked transposition on host threads
+    (wcx_host_stack_counts, csrc/host_newref.cu) instead of one strided column per (chromosome, sample)."""
+    import os
+    chrs = list(chrs)
+    ns, nchr = len(samples), len(chrs)
+    cols = [np.ascontiguousarray(s[str(c)], dtype=np.int32).reshape(-1) for s in samples for c in chrs]  # kept alive below
+    lens = np.array([len(v) for v in cols], dtype=np.int64).reshape(ns, nchr)
+    offs = np.concatenate([[0], np.cumsum(lens.max(axis=0) if ns else np.zeros(nchr, dtype=np.int64))]).astype(np.int64)
+    out = np.empty((int(offs[-1]), ns), dtype=np.int32)
+    if out.size:
+        ptrs = np.array([v.ctypes.data for v in cols], dtype=np.uintp)
+        _lib.check(_lib.load().wcx_host_stack_counts(_ptr(ptrs), _ptr(lens), ns, nchr, _ptr(offs), _ptr(out),
+                                                     max(1, min(16, len(os.sched_getaffinity(0))))))
+    return out
+
+
+def column_totals(counts):
+    """Exact (int64) read total of every sample of a stacked count matrix, row blocks on a thread pool."""
     import os
     from concurrent.futures import ThreadPoolExecutor
-    chrs = list(chrs)
-    lens = [max(len(s[str(c)]) for s in samples) for c in chrs]
-    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    total = int(offs[-1])
-    out = np.zeros((total, len(samples)), dtype=np.int32)
+    rows = counts.shape[0]
+    nthreads = max(1, min(16, len(os.sched_getaffinity(0))))
+    step = max(4096, -(-rows // (2 * nthreads)))
+    with ThreadPoolExecutor(nthreads) as pool:
+        parts = list(pool.map(lambda a: np.sum(counts[a:a + step], 0, dtype=np.int64), range(0, rows, step)))
+    return np.sum(parts, 0, dtype=np.int64) if parts else np.zeros(counts.shape[1], dtype=np.int64)
 
-    def fill(block):
-        # a block of adjacent samples: contiguous row pieces of the result (better than one strided column at a time)
-        a, b = block
-        tmp = np.zeros((total, b - a), dtype=np.int32)
-        for i in range(a, b):
-            s = samples[i]
-            for c, o in zip(chrs, offs[:-1]):
-                v = np.asarray(s[str(c)])
-                tmp[o:o + len(v), i - a] = v
-        out[:, a:b] = tmp
 
-    ns = len(samples)
-    nthreads = max(1, min(8, len(os.sched_getaffinity(0)), ns // 16 or 1))
-    step = max(8, -(-ns // (2 * nthreads)))
-    blocks = [(a, min(ns, a + step)) for a in range(0, ns, step)]
-    if nthreads == 1:
-        for blk in blocks:
-            fill(blk)
-    else:
-        with ThreadPoolExecutor(nthreads) as pool:
-            list(pool.map(fill, blocks))
+def bin_sums(counts, col_sum, cols=None):
+    """np.sum(counts[:, cols] / col_sum, 1) of get_mask (newref_tools.py:94-97), the same float64 values (one division
+    per element, NumPy's pairwise order along the row), on host threads and without the float matrix."""
+    import os
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    col_sum = np.ascontiguousarray(col_sum, dtype=np.float64)
+    cols = None if cols is None else np.ascontiguousarray(cols, dtype=np.int32)
+    assert len(col_sum) == (counts.shape[1] if cols is None else len(cols))
+    out = np.empty(counts.shape[0], dtype=np.float64)
+    _lib.check(_lib.load().wcx_host_bin_sums(_ptr(counts), counts.shape[0], counts.shape[1], None if cols is None else _ptr(cols),
+                                             0 if cols is None else len(cols), _ptr(col_sum), _ptr(out),
+                                             max(1, min(16, len(os.sched_getaffinity(0))))))
     return out
 
 
