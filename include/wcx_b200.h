@@ -62,6 +62,30 @@ int wcx_host_stack_counts(const int32_t* const* columns, const int64_t* lens, in
 int wcx_host_bin_sums(const int32_t* counts, int64_t bins, int32_t samples, const int32_t* cols, int32_t ncols,
                       const double* col_sum, double* out, int32_t threads);
 
+/* ---- host side of the segmentation step (host threads, no device work, no context): include/CBS.R around
+ * DNAcopy::segment, for a batch of samples.  r_rows[s] / w_rows[s] -> the log ratios and weights of sample s on the
+ * concatenated bin axis of its chromosomes (0 = no data), offs[offs_at[s] ... offs_at[s + 1] - 1] its chromosome
+ * offsets (nchr + 1 ascending values); (sample, chromosome) "slots" are numbered in that order.
+ * wcx_cbs_pack_count: counts[slot] = bins with ratio != 0 (CBS.R:41).
+ * wcx_cbs_pack: the NA-free series of all samples back to back, sample s from entry at[s]: y = ratios, w = weights with
+ *   0 replaced by 1 (CBS.R:42), pos int32 = bin of every entry on the sample's axis; long_gaps[slot] = runs of more
+ *   than na_thresh NA bins between two entries of the chromosome (what wcx_cbs_unpack may cut at).
+ * wcx_cbs_unpack (CBS.R:80-129): series i = entries off[i] ... off[i + 1] of y / w / pos (the series handed to
+ *   wcx_cbs_segment, which returned nseg[i] ascending exclusive ends per series, back to back in `ends`); chr_start[i] =
+ *   first bin of its chromosome; output slots slot[i] ... slot[i + 1] (at least nseg[i] + long gaps of the series).
+ *   Every segment is cut at the NA runs longer than na_thresh inside it, pieces of at most one bin are dropped, and each
+ *   piece is written as (out_series = i, out_s 0-based start, out_e exclusive end on the chromosome, out_r = weighted
+ *   mean of its entries, summed in NumPy's pairwise order); unused slots get out_series = -1. */
+int wcx_cbs_pack_count(const double* const* r_rows, const int64_t* offs, const int64_t* offs_at, int32_t samples,
+                       int64_t* counts, int32_t threads);
+int wcx_cbs_pack(const double* const* r_rows, const double* const* w_rows, const int64_t* offs, const int64_t* offs_at,
+                 int32_t samples, const int64_t* at, int64_t na_thresh, double* y, double* w, int32_t* pos,
+                 int64_t* long_gaps, int32_t threads);
+int wcx_cbs_unpack(const int32_t* pos, const double* y, const double* w, const int64_t* off, int32_t series,
+                   const int32_t* ends, const int32_t* nseg, const int64_t* chr_start, const int64_t* slot,
+                   int64_t na_thresh, int32_t* out_series, int64_t* out_s, int64_t* out_e, double* out_r,
+                   int32_t threads);
+
 /* ---- newref ------------------------------------------------------------------------------
  * Replaces get_reference (newref_tools.py:155-224): get_ref_for_bins (:255-278) and the
  * null-ratio loop (:210-224).

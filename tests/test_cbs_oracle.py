@@ -108,16 +108,19 @@ def test_sequential_boundary_table():
     assert abs((comb(10000 - b1, 2) + b1 * (10000 - b2)) / comb(10000, 2) - C._p_exceed(10000, 2, [b1, b2])) < 1e-9
 
 
-def test_product_postprocessing_equals_oracle():
-    """wisecondorx_b200.cbs._cbs_prepare / _cbs_finish (CBS.R:30-129 restated per chromosome) against the oracle's cbs_r
-    (per segment, like CBS.R) on the same random segment ends: NA runs at chromosome ends, runs longer and shorter than
-    the split threshold, all-NA chromosomes, every bin size class."""
+def test_product_postprocessing_equals_oracle(monkeypatch):
+    """wisecondorx_b200.cbs.cbs_segments_batch -- CBS.R:30-129 around the device call, on host threads in the library
+    (csrc/host_cbs.cu: runs here, it needs no GPU) -- against the oracle's cbs_r (per segment, like CBS.R) on the same
+    random segment ends: NA runs at chromosome ends, runs longer and shorter than the split threshold, all-NA
+    chromosomes, weight 0, every bin size class, single samples and a batch."""
     from wisecondorx_b200 import cbs
     rng = np.random.default_rng(5)
     total = 0
+    cases = []
     for trial in range(24):
         binsize = [15000.0, 100000.0, 5000.0, 1e6][trial % 4]
-        per = [int(x) for x in rng.integers(5, 1500, 23)]
+        g = "M" if trial % 5 == 0 else "F"
+        per = [int(x) for x in rng.integers(5, 1500, 24 if g == "M" else 23)]
         rr = [rng.normal(0, 0.1, n) for n in per]
         ww = [rng.uniform(0.5, 2, n) for n in per]
         for r in rr:
@@ -129,18 +132,41 @@ def test_product_postprocessing_equals_oracle():
         rr[0][-2:] = 0
         rr[7][:] = 0  # CBS.R:56-63: dropped
         ww[3][::5] = 0  # CBS.R:42
+        cases.append((rr, ww, g, binsize))
+
+    def run(batch, binsize):
+        """Product and oracle around the same segmenter: ends drawn per (sample, chromosome), remembered by series content."""
         ends_of = {}
 
-        def segmenter(yy, wv, c):
-            n = len(yy)
-            ends_of[c] = sorted(set([int(x) for x in rng.integers(1, n + 1, int(rng.integers(0, 6)))] + [n]))
-            return ends_of[c]
+        def key(yy, c):
+            return (int(c), len(yy), float(np.sum(yy)))
 
-        want = [[d["chr"] - 1, d["s"], d["e"], d["r"]] for d in C.cbs_r(rr, ww, "F", 1e-4, binsize, segmenter=segmenter)]
-        prepared, series, ids = cbs._cbs_prepare(rr, ww, "F")
-        got = cbs._cbs_finish(prepared, [np.array(ends_of[c], dtype=np.int32) for c in ids], binsize)
-        assert len(got) == len(want)
-        for g, w in zip(got, want):
-            assert g[:3] == w[:3] and (g[3] == w[3] or (np.isnan(g[3]) and np.isnan(w[3]))), (trial, g, w)
-        total += len(got)
-    assert total > 1000
+        def fake_segment_flat(y, w, off, ids, alpha, nperm, seed, ctx, sequential=True, eta=0.05):
+            ends, nseg = [], []
+            for s in range(len(off) - 1):
+                yy = y[off[s]:off[s + 1]]
+                n = len(yy)
+                e = sorted(set([int(x) for x in rng.integers(1, n + 1, int(rng.integers(0, 6)))] + [n]))
+                ends_of[key(yy, ids[s])] = e
+                ends += e
+                nseg.append(len(e))
+            return np.array(ends, dtype=np.int32), np.array(nseg, dtype=np.int32)
+
+        monkeypatch.setattr(cbs, "_segment_flat", fake_segment_flat)
+        got = cbs.cbs_segments_batch([(rr, ww, g) for rr, ww, g, _ in batch], 1e-4, binsize, seed=1)
+        n_out = 0
+        for (rr, ww, g, _), segs in zip(batch, got):
+            want = [[d["chr"] - 1, d["s"], d["e"], d["r"]] for d in
+                    C.cbs_r(rr, ww, g, 1e-4, binsize, segmenter=lambda yy, wv, c: ends_of[key(yy, c)])]
+            assert len(segs) == len(want)
+            for a, b in zip(segs, want):
+                assert a[:3] == b[:3] and (a[3] == b[3] or (np.isnan(a[3]) and np.isnan(b[3]))), (a, b)
+                assert type(a[0]) is int and type(a[1]) is int and type(a[2]) is int and type(a[3]) is float
+            n_out += len(segs)
+        return n_out
+
+    for case in cases:
+        total += run([case], case[3])
+    for bs in (15000.0, 100000.0, 5000.0, 1e6):
+        total += run([c for c in cases if c[3] == bs], bs)
+    assert total > 2000

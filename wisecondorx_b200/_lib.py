@@ -68,6 +68,9 @@ def load():
     L.wcx_cbs_segment.argtypes = [vp, vp, vp, vp, i32, vp, f64, i32, ctypes.c_uint32, vp, vp]
     L.wcx_cbs_stats.argtypes = [vp, vp]
     L.wcx_cbs_set_boundary.argtypes = [vp, vp, i32]
+    L.wcx_cbs_pack_count.argtypes = [vp, vp, vp, i32, vp, i32]
+    L.wcx_cbs_pack.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, vp, i32]
+    L.wcx_cbs_unpack.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32]
     L.wcx_newref_normalize_and_mask.argtypes = [vp, vp, i64, i32, vp, i64, vp, i32]
     L.wcx_pca_gram.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.wcx_prep_fetch.argtypes = [vp, i32, i64, i32, vp]

@@ -145,106 +145,6 @@ def cbs_stats(ctx: _lib.Context | None = None):
     return dict(zip(["rounds", "segments_tested", "perm_tests", "t_tests", "permutations", "launches"], out.tolist()))
 
 
-class _Prepared:
-    """CBS.R:30-63 for one sample, on the concatenated bin axis of its chromosomes: `na` (ratio == 0), `cols` (positions
-    of the other bins), `y` / `w` (their ratios and weights, weight 0 -> 1), `base[c]` = first entry of chromosome c in
-    them, `ids` = the chromosomes that are not all NA (the others are dropped, CBS.R:56-63)."""
-    __slots__ = ("offs", "na", "cols", "base", "y", "w", "ids")
-
-
-def _cbs_prepare_flat(r_flat, w_flat, offs, gather=True):
-    p = _Prepared()
-    p.offs = offs
-    p.na = r_flat == 0  # CBS.R:41
-    p.cols = np.flatnonzero(~p.na)
-    p.base = np.searchsorted(p.cols, offs)
-    p.ids = np.flatnonzero(np.diff(p.base) > 0)
-    if gather:
-        _cbs_gather(p, r_flat, w_flat, np.empty(len(p.cols)), np.empty(len(p.cols)))
-    return p
-
-
-def _cbs_gather(p, r_flat, w_flat, y_out, w_out):
-    """The NA-free ratios and weights of a prepared sample, written where the caller wants them (a batch lines the
-    samples up in the two vectors of its one device call)."""
-    np.take(r_flat, p.cols, out=y_out, mode="clip")
-    np.take(w_flat, p.cols, out=w_out, mode="clip")
-    w_out[w_out == 0] = 1.0  # CBS.R:42 -- 1^-99 is 1 in R
-    p.y, p.w = y_out, w_out
-
-
-def _cbs_prepare(results_r, results_w, ref_gender):
-    """CBS.R:30-63 for one sample given as per-chromosome lists.  Returns (prepared, series, ids): the NA-free
-    (ratio, weight) series of the chromosomes `ids` that have any data."""
-    nchr = 24 if ref_gender == "M" else 23  # CBS.R:30-34
-    if len(results_r) < nchr or len(results_w) < nchr:
-        raise IndexError("list index out of range")
-    r_flat = predict_tools.flatten(results_r[:nchr])
-    w_flat = predict_tools.flatten(results_w[:nchr])
-    offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r[:nchr]])]).astype(np.int64)
-    p = _cbs_prepare_flat(r_flat, w_flat, offs)
-    series = [(p.y[p.base[c]:p.base[c + 1]], p.w[p.base[c]:p.base[c + 1]]) for c in p.ids]
-    return p, series, [int(c) for c in p.ids]
-
-
-def _cbs_finish(p, all_ends, binsize):
-    """CBS.R:80-129: split the segments over long NA runs, weighted segment means, 0-based half-open coordinates.
-    all_ends[i] = ascending exclusive ends of the segments of chromosome p.ids[i] in its NA-free series.
-
-    The NA runs of the whole sample are located once (CBS.R does it per segment, :86-101, with the same result: a
-    segment starts and ends on a non-NA bin, so a run lies inside it or outside).  CBS.R only sees runs that begin and
-    end inside the segment, i.e. inside the chromosome: a run that touches a chromosome boundary is no run."""
-    na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
-    offs, cols, base = p.offs, p.cols, p.base
-    d = np.diff(p.na.view(np.int8))
-    first = np.flatnonzero(d == 1) + 1   # first NA bin of a run           (CBS.R's start.pos, 1-based: the bin before it)
-    after = np.flatnonzero(d == -1) + 1  # first bin after the run, 0-based (CBS.R's end.pos, 1-based: the last NA bin)
-    if len(p.na) and p.na[0]:
-        after = after[1:]
-    if len(p.na) and p.na[-1]:
-        first = first[:-1]
-    sel = (after - first) > na_thresh  # CBS.R:95
-    first, after = first[sel], after[sel]
-    if len(first):  # no chromosome start inside [first, after]: the run begins and ends within one chromosome
-        inside = np.searchsorted(offs, first, "left") == np.searchsorted(offs, after, "right")
-        first, after = first[inside], after[inside]
-    # segments of all chromosomes: entries [a, b) of the NA-free vectors, first / last bin on the concatenated axis
-    if not len(p.ids):
-        return []
-    counts = np.array([len(e) for e in all_ends], dtype=np.int64)
-    ends = np.concatenate([np.asarray(e, dtype=np.int64) for e in all_ends])
-    if not len(ends):
-        return []
-    chrom = np.repeat(np.asarray(p.ids, dtype=np.int64), counts)
-    seg_a = np.empty(len(ends), dtype=np.int64)
-    seg_a[1:] = ends[:-1]
-    seg_a[(np.cumsum(counts) - counts)[counts > 0]] = 0  # the first segment of a chromosome starts at its first entry
-    seg_a += base[chrom]
-    seg_b = ends + base[chrom]
-    gs, ge = cols[seg_a], cols[seg_b - 1]  # DNAcopy loc.start / loc.end (here 0-based, concatenated axis)
-    lo = np.searchsorted(first, gs, "right") if len(first) else np.zeros(len(gs), dtype=np.int64)
-    hi = np.searchsorted(first, ge, "left") if len(first) else lo
-    yw = p.y * p.w
-    out = []
-    for c, a, b, s, e, l, h in zip(chrom.tolist(), seg_a.tolist(), seg_b.tolist(), gs.tolist(), ge.tolist(), lo.tolist(), hi.tolist()):
-        a0 = int(offs[c])
-        if h <= l:
-            if e - s <= 0:  # CBS.R:103
-                continue
-            # the non-zero ratios of bins [s, e] are the entries [a, b) of the NA-free vectors (CBS.R:122-127)
-            out.append([c, s - a0, e - a0 + 1, float(np.sum(yw[a:b]) / np.sum(p.w[a:b]))])  # CBS.R:129, predict_tools.py:266-275
-            continue
-        inv_start = [s + 1] + after[l:h].tolist()  # CBS.R:100-101 (1-based on the concatenated axis)
-        inv_end = first[l:h].tolist() + [e + 1]
-        for s1, e1 in zip(inv_start, inv_end):
-            if e1 - s1 <= 0:  # CBS.R:103
-                continue
-            a1, b1 = np.searchsorted(cols, [s1 - 1, e1])
-            r = float(np.sum(yw[a1:b1]) / np.sum(p.w[a1:b1])) if b1 > a1 else float("nan")
-            out.append([c, s1 - 1 - a0, e1 - a0, r])
-    return out
-
-
 def cbs_segments(results_r, results_w, ref_gender, alpha, binsize, seed=None, nperm=10000, ctx=None):
     """CBS.R as a function: [[chr (0-based), s, e (exclusive), r], ...]."""
     return cbs_segments_batch([(results_r, results_w, ref_gender)], alpha, binsize, seed, nperm, ctx)[0]
@@ -265,39 +165,69 @@ def _note_not_bit_compatible():
 def cbs_segments_batch(samples, alpha, binsize, seed=None, nperm=10000, ctx=None):
     """CBS.R for a batch of samples [(results_r, results_w, ref_gender), ...] with ONE device call over all
     (sample, chromosome) series.  The permutation streams are keyed by (seed, chromosome), not by the position of a
-    series in the batch, so every sample gets the segments it would get alone."""
-    _map_threads = predict_tools.map_threads
+    series in the batch, so every sample gets the segments it would get alone.
+
+    CBS.R's own work around DNAcopy::segment runs on host threads in the library (csrc/host_cbs.cu): :30-63 (ratio == 0
+    -> NA, weight == 0 -> 1, the NA-free series of every chromosome, chromosomes without data dropped) before the device
+    call, :80-129 (segments cut at NA runs longer than int(2e6 / binsize), weighted means, 0-based half-open coordinates)
+    after it."""
+    import os
     _note_not_bit_compatible()
     seed_i = 0 if seed is None else int(seed)
-
-    def prepare(t):
-        results_r, results_w, ref_gender = t
+    L = _lib.load()
+    threads = max(1, min(16, len(os.sched_getaffinity(0))))
+    n = len(samples)
+    if n == 0:
+        return []
+    flat_r, flat_w, offs_s = [], [], []
+    for results_r, results_w, ref_gender in samples:
         nchr = 24 if ref_gender == "M" else 23  # CBS.R:30-34
         if len(results_r) < nchr or len(results_w) < nchr:
             raise IndexError("list index out of range")
-        offs = np.concatenate([[0], np.cumsum([len(x) for x in results_r[:nchr]])]).astype(np.int64)
-        flat = predict_tools.flatten(results_r[:nchr]), predict_tools.flatten(results_w[:nchr])
-        return _cbs_prepare_flat(flat[0], flat[1], offs, gather=False), flat
-
-    prepared = _map_threads(prepare, samples)
-    preps = [t[0] for t in prepared]
-    lens = [np.diff(p.base)[p.ids] for p in preps]
-    off = np.concatenate([[0], np.cumsum(np.concatenate(lens))]).astype(np.int64) if preps else np.zeros(1, dtype=np.int64)
-    ids = np.concatenate([p.ids for p in preps]) if preps else np.zeros(0, dtype=np.int32)
-    # the series of all samples back to back in two page-locked vectors, every sample gathered into its place
-    alloc = _lib.pinned.empty if len(preps) >= 8 else (lambda shape: np.empty(shape, dtype=np.float64))
-    y, w = alloc((max(int(off[-1]), 1),)), alloc((max(int(off[-1]), 1),))
-    at = np.concatenate([[0], np.cumsum([len(p.cols) for p in preps])]).astype(np.int64)
-    _map_threads(lambda j: _cbs_gather(preps[j], prepared[j][1][0], prepared[j][1][1], y[at[j]:at[j + 1]], w[at[j]:at[j + 1]]),
-                 range(len(preps)))
-    ends, nseg = _segment_flat(y, w, off, ids, alpha, nperm, seed_i, ctx)
-    cut = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)  # first segment end of every series
-    first = np.concatenate([[0], np.cumsum([len(p.ids) for p in preps])]).astype(np.int64)  # first series of every sample
-
-    def finish(j):
-        return _cbs_finish(preps[j], [ends[cut[s]:cut[s + 1]] for s in range(first[j], first[j + 1])], binsize)
-
-    return _map_threads(finish, range(len(preps)))
+        offs_s.append(np.concatenate([[0], np.cumsum([len(x) for x in results_r[:nchr]])]).astype(np.int64))
+        # (views of the rows the result assembly wrote: no copies)
+        flat_r.append(np.ascontiguousarray(predict_tools.flatten(results_r[:nchr])))
+        flat_w.append(np.ascontiguousarray(predict_tools.flatten(results_w[:nchr])))
+        if len(flat_w[-1]) != len(flat_r[-1]):
+            raise ValueError("results_r and results_w differ in length")
+    nchr_s = np.array([len(o) - 1 for o in offs_s], dtype=np.int64)
+    offs_all = np.ascontiguousarray(np.concatenate(offs_s))
+    offs_at = np.concatenate([[0], np.cumsum(nchr_s + 1)]).astype(np.int64)
+    slot_first = np.concatenate([[0], np.cumsum(nchr_s)]).astype(np.int64)  # first (sample, chromosome) slot of a sample
+    r_ptrs = np.array([a.ctypes.data for a in flat_r], dtype=np.uintp)
+    w_ptrs = np.array([a.ctypes.data for a in flat_w], dtype=np.uintp)
+    na_thresh = int((binsize / 2000000.0) ** -1)  # CBS.R:95
+    counts = np.zeros(int(slot_first[-1]), dtype=np.int64)
+    _lib.check(L.wcx_cbs_pack_count(_ptr(r_ptrs), _ptr(offs_all), _ptr(offs_at), n, _ptr(counts), threads))
+    at = np.concatenate([[0], np.cumsum(np.add.reduceat(counts, slot_first[:-1]))]).astype(np.int64)  # every sample has >= 23 slots
+    total = int(at[-1])
+    # the series of all samples back to back in two page-locked vectors (they cross PCIe in the device call)
+    alloc = _lib.pinned.empty if n >= 8 else (lambda shape: np.empty(shape, dtype=np.float64))
+    y, w = alloc((max(total, 1),)), alloc((max(total, 1),))
+    pos = np.empty(max(total, 1), dtype=np.int32)
+    gaps = np.zeros(len(counts), dtype=np.int64)
+    _lib.check(L.wcx_cbs_pack(_ptr(r_ptrs), _ptr(w_ptrs), _ptr(offs_all), _ptr(offs_at), n, _ptr(at), na_thresh, _ptr(y), _ptr(w),
+                              _ptr(pos), _ptr(gaps), threads))
+    series = np.flatnonzero(counts > 0)  # chromosomes without data are dropped (CBS.R:56-63)
+    off = np.concatenate([[0], np.cumsum(counts[series])]).astype(np.int64)
+    chrom = np.concatenate([np.arange(k) for k in nchr_s])[series]
+    sample_of = np.repeat(np.arange(n), nchr_s)[series]
+    chr_start = np.ascontiguousarray(np.concatenate([o[:-1] for o in offs_s])[series], dtype=np.int64)
+    ends, nseg = _segment_flat(y[:total], w[:total], off, chrom, alpha, nperm, seed_i, ctx)
+    ends, nseg = np.ascontiguousarray(ends, dtype=np.int32), np.ascontiguousarray(nseg, dtype=np.int32)
+    if len(series) and int(nseg.min()) < 1:
+        raise _lib.WcxError("wcx_cbs_segment returned a series without segments")
+    slot = np.concatenate([[0], np.cumsum(nseg.astype(np.int64) + gaps[series])]).astype(np.int64)
+    cap = max(int(slot[-1]), 1)
+    out_series = np.full(cap, -1, dtype=np.int32)
+    out_s, out_e, out_r = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.float64)
+    _lib.check(L.wcx_cbs_unpack(_ptr(pos), _ptr(y), _ptr(w), _ptr(off), len(series), _ptr(ends), _ptr(nseg), _ptr(chr_start), _ptr(slot),
+                                na_thresh, _ptr(out_series), _ptr(out_s), _ptr(out_e), _ptr(out_r), threads))
+    used = np.flatnonzero(out_series >= 0)
+    ser = out_series[used]
+    rows = [list(t) for t in zip(chrom[ser].tolist(), out_s[used].tolist(), out_e[used].tolist(), out_r[used].tolist())]
+    cut = np.concatenate([[0], np.cumsum(np.bincount(sample_of[ser], minlength=n))]).astype(int)
+    return [rows[cut[j]:cut[j + 1]] for j in range(n)]  # [[chr (0-based), s, e (exclusive), r], ...] per sample
 
 
 def exec_cbs(rem_input, results, engine: predict_tools.PredictEngine | None = None, nperm=10000):

@@ -9,8 +9,7 @@
 //
 // wcx_host_bin_sums returns exactly what NumPy returns for np.sum(counts[:, cols] / col_sum, 1): one division per
 // element, and the additions in the order of NumPy's pairwise summation of a contiguous float64 row
-// (numpy/_core/src/umath/loops_utils.h.src: blocks of at most 128 elements, eight running sums combined as
-// ((0+1)+(2+3))+((4+5)+(6+7)), a sequential tail; longer rows split at a multiple of eight nearest to the middle).
+// (host_sums.h).
 // tests/test_host_pin.py compares the resulting masks with the live reference's get_mask.
 #include <algorithm>
 #include <cstdint>
@@ -19,47 +18,9 @@
 #include <thread>
 #include <vector>
 
+#include "host_sums.h"
 #include "wcx_common.cuh"
 
-namespace {
-
-template <class F>
-void parallel_ranges(int64_t total, int64_t grain, int32_t threads, F&& fn) {
-  const int64_t chunks = std::max<int64_t>(1, (total + grain - 1) / grain);
-  const int32_t nt = (int32_t)std::max<int64_t>(1, std::min<int64_t>(threads, chunks));
-  if (nt == 1) { fn(0, total); return; }
-  std::vector<std::thread> pool;
-  pool.reserve(nt);
-  for (int32_t t = 0; t < nt; ++t)
-    pool.emplace_back([=, &fn]() {
-      for (int64_t c = t; c < chunks; c += nt) fn(c * grain, std::min(total, (c + 1) * grain));
-    });
-  for (auto& th : pool) th.join();
-}
-
-// NumPy's pairwise sum of n contiguous doubles (see the header comment)
-double pairwise_sum(const double* a, int64_t n) {
-  if (n < 8) {
-    double res = 0.;
-    for (int64_t i = 0; i < n; ++i) res += a[i];
-    return res;
-  }
-  if (n <= 128) {
-    double r[8];
-    for (int j = 0; j < 8; ++j) r[j] = a[j];
-    int64_t i;
-    for (i = 8; i < n - (n % 8); i += 8)
-      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; ++i) res += a[i];
-    return res;
-  }
-  int64_t n2 = n / 2;
-  n2 -= n2 % 8;
-  return pairwise_sum(a, n2) + pairwise_sum(a + n2, n - n2);
-}
-
-}  // namespace
 
 extern "C" int wcx_host_stack_counts(const int32_t* const* columns, const int64_t* lens, int32_t samples, int32_t nchr,
                                      const int64_t* offs, int32_t* out, int32_t threads) {
@@ -78,7 +39,7 @@ extern "C" int wcx_host_stack_counts(const int32_t* const* columns, const int64_
   }
   const int64_t total = offs[nchr] - offs[0];
   // rows [a, b) of the result, 16 samples at a time: 16 sequential input streams, one 64-byte line per output row piece
-  parallel_ranges(total, 4096, threads, [=](int64_t a, int64_t b) {
+  wcx::host_parallel(total, 4096, threads, [=](int64_t a, int64_t b) {
     int32_t c = 0;
     while (c + 1 < nchr && offs[c + 1] - offs[0] <= a) ++c;
     for (int64_t row = a; row < b;) {
@@ -114,7 +75,7 @@ extern "C" int wcx_host_bin_sums(const int32_t* counts, int64_t bins, int32_t sa
   if (cols)
     for (int32_t j = 0; j < ncols; ++j)
       if (cols[j] < 0 || cols[j] >= samples) { wcx::set_error("wcx_host_bin_sums: column index out of range"); return 1; }
-  parallel_ranges(bins, 2048, threads, [=](int64_t a, int64_t b) {
+  wcx::host_parallel(bins, 2048, threads, [=](int64_t a, int64_t b) {
     std::vector<double> row((size_t)std::max(n, 1));
     for (int64_t r = a; r < b; ++r) {
       const int32_t* src = counts + r * samples;
@@ -122,7 +83,7 @@ extern "C" int wcx_host_bin_sums(const int32_t* counts, int64_t bins, int32_t sa
         for (int32_t j = 0; j < n; ++j) row[j] = (double)src[cols[j]] / col_sum[j];
       else
         for (int32_t j = 0; j < n; ++j) row[j] = (double)src[j] / col_sum[j];
-      out[r] = pairwise_sum(row.data(), n);
+      out[r] = wcx::numpy_pairwise_sum(row.data(), n);
     }
   });
   return 0;
