@@ -13,6 +13,10 @@
  *   - all work of a context is issued on one CUDA stream (own stream by default, or the one given
  *     to wcx_set_stream, e.g. torch's current stream); calls with host outputs synchronise it.
  *   - a context is not re-entrant; use one context per host thread / per GPU.
+ *   - entry points WITHOUT a wcx_ctx argument (wcx_host_*, wcx_predict_assemble, wcx_cbs_pack_count / _pack / _unpack)
+ *     run on host threads and touch no device: they are the native form of Python glue the reference runs between
+ *     the functions above (stacking the samples, result assembly, CBS.R around DNAcopy::segment), not substitutes
+ *     for any kernel.  `threads` caps the host threads of a call.
  */
 #ifndef WCX_B200_H
 #define WCX_B200_H
