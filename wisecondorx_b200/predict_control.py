@@ -164,9 +164,11 @@ def shared_weights(w_aut, w_gon):
     return (w if ok else np.ones(len(w))), ok
 
 
-def _log2_rows(src, rows):
-    """log2 of the rows `rows` of src into a new matrix (NumPy's log2, one row per task: predict_tools.py:182)."""
-    out = np.empty((len(rows), src.shape[1]))
+def _log2_rows(src, rows, inplace=False):
+    """log2 of the rows `rows` of src (NumPy's log2, one row per task: predict_tools.py:182) as a [len(rows), n] matrix;
+    inplace: the rows are overwritten and the matrix is src itself when `rows` are all its rows in order (no new pages)."""
+    same = inplace and len(rows) == len(src) and np.array_equal(rows, np.arange(len(src)))
+    out = src if same else np.empty((len(rows), src.shape[1]))
 
     def one(j):
         with np.errstate(all="ignore"):
@@ -176,12 +178,13 @@ def _log2_rows(src, rows):
     return out
 
 
-def assemble_batch(args, aut, aut_rows, gon, nr, ref_file, ref_gender, genders, n_reads, weights=None):
+def assemble_batch(args, aut, aut_rows, gon, nr, ref_file, ref_gender, genders, n_reads, weights=None, consume=False):
     """Result assembly (reference main.py:232-271) of the samples of a batch that share the reference gender.
     aut = (r, z [*, n_aut], w [n_aut], ref_sizes [*, n_aut], m_lr, m_z [*]) of the autosomal normalize_batch call and
     aut_rows the rows of it these samples occupy; gon = (r2, z2 [b, n_gon], w2 [n_gon], n2 [b, n_gon]) of their
     gonosomal call; nr = the stacked null ratios of ref_gender; genders / n_reads per sample.  Returns
-    [(rem_input, results), ...].
+    [(rem_input, results), ...].  consume: the ratio matrices may be overwritten with their logarithms (the caller
+    drops them anyway).
 
     get_post_processed_result (predict_control.py:49-63), inflate_results (predict_tools.py:163-170) and log_trans
     (predict_tools.py:180-193) run as ONE pass per sample over the bin axis on host threads (wcx_predict_assemble,
@@ -200,8 +203,8 @@ def assemble_batch(args, aut, aut_rows, gon, nr, ref_file, ref_gender, genders, 
     r, z, ref_sizes, r2, z2, n2 = (np.ascontiguousarray(x, dtype=np.float64).reshape(len(x), -1) for x in (r, z, ref_sizes, r2, z2, n2))
     if len(w_shared) != r.shape[1] + r2.shape[1]:  # the reference's boolean index fails the same way
         raise IndexError("boolean index did not match indexed array")
-    lr = _log2_rows(r, rows)
-    lr2 = _log2_rows(r2, np.arange(b))
+    lr = _log2_rows(r, rows, consume)
+    lr2 = _log2_rows(r2, np.arange(b), consume)
     out_r, out_z, out_w = np.empty((b, len(mask))), np.empty((b, len(mask))), np.empty((b, len(mask)))
     out_i = np.empty((b, len(mask)), dtype=np.int32)
     ml = np.ascontiguousarray(np.asarray(m_lr, dtype=np.float64).reshape(-1)[rows])
@@ -289,7 +292,7 @@ def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.Predi
         ids = [i for i, x in enumerate(ref_genders) if x == rg]
         r2, z2, w2, n2, _, _ = normalize_batch(args, [prepared[i] for i in ids], ref_file, rg, eng)
         group = assemble_batch(args, (r, z, w, n, m_lr, m_z), ids, (r2, z2, w2, n2), eng.stacked_null_ratios(ref_file, rg),
-                               ref_file, rg, [genders[i] for i in ids], [n_reads[i] for i in ids])
+                               ref_file, rg, [genders[i] for i in ids], [n_reads[i] for i in ids], consume=True)
         for i, res in zip(ids, group):
             out[i] = res
     if timings is not None:
