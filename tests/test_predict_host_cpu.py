@@ -215,3 +215,26 @@ def test_segment_batch_series(fake_library):
     got = predict_control.segment_batch(r, w, nref, m_lr, offs, nperm=100, seed=3)
     assert len(got) == len(want) == 25 and sum(len(x) for x in want) > 30
     assert all(np.array_equal(a, c) for a, c in zip(got, want))
+
+
+def test_predict_command_line_host_flow(fake_library, tmp_path):
+    """`WisecondorX predict --bed` end to end around the stand-in library: reference and sample files read, genders,
+    batch-of-one flow, tables written -- the plumbing between the command line and the device calls (the numbers in the
+    tables are the stand-in's)."""
+    from wisecondorx_b200 import main as wmain
+    binsize = 500000
+    ref, _ = fake_cabi.make_ref_file(binsize=binsize, k=4, m=6)
+    np.savez(tmp_path / "ref.npz", **ref)
+    samples, _ = synth.make_samples(2, binsize, seed=9, depth=3e5)
+    np.savez_compressed(tmp_path / "s.npz", binsize=binsize, sample=samples[1], quality={})
+    parser = wmain.build_parser()
+    a = parser.parse_args(["predict", str(tmp_path / "s.npz"), str(tmp_path / "ref.npz"), str(tmp_path / "out"), "--bed", "--seed", "3",
+                           "--minrefbins", "150"])
+    res = a.func(a)
+    assert len(res["results_c"]) > 0 and set(res["timings"]) >= {"load_reference", "normalize_and_assemble", "cbs_and_segment_z", "write_tables"}
+    bins = (tmp_path / "out_bins.bed").read_text().splitlines()
+    assert bins[0].split("\t")[:4] == ["chr", "start", "end", "id"] and len(bins) == 1 + int(np.sum(ref["bins_per_chr.M"]))
+    segs = (tmp_path / "out_segments.bed").read_text().splitlines()
+    assert len(segs) == 1 + len(res["results_c"])
+    for name in ("out_aberrations.bed", "out_statistics.txt"):
+        assert (tmp_path / name).stat().st_size > 0
