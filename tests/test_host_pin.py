@@ -291,3 +291,31 @@ def test_bin_sums_native_equals_numpy_row_sums(s):
         # NumPy then adds column by column)
         want = np.sum(np.ascontiguousarray(counts[:, cols]).astype(float) / col[cols], 1)
         assert np.array_equal(newref_tools.bin_sums(counts, col[cols], cols), want, equal_nan=True)
+
+
+def test_stacked_counts_gender_path(R):
+    """main.stacked_counts: Y fractions, genders and the gender-corrected count matrix from ONE stacked matrix == the
+    reference's per-sample route (train_gender_model on the dicts, gender_correct, stacking the corrected samples)."""
+    from wisecondorx_b200 import newref_tools
+    samples, _ = synth.make_samples(18, 1_000_000, seed=21, depth=2e6)
+    st = wcx_main.stacked_counts(np.array(samples))
+    assert st.y_fractions is not None
+    assert st.y_fractions.tolist() == [wcx_main._y_fraction(s) for s in samples]
+    args = types.SimpleNamespace(yfrac=0.006, plotyfrac=None)
+    want_g, want_cut = R.newref_tools.train_gender_model(args, np.array(samples))
+    got_g, got_cut = wcx_main.train_gender_model(args, np.array(samples), st.y_fractions)
+    assert got_g == want_g and got_cut == want_cut and {"F", "M"} <= set(got_g)
+    corrected = [R.overall_tools.gender_correct(dict(s), g) for s, g in zip(samples, want_g)]
+    st.gender_correct(got_g)
+    want = newref_tools.stack_counts(corrected, range(1, 25))
+    assert np.array_equal(st.counts, want)
+    assert np.array_equal(st.totals, want.sum(0, dtype=np.int64))
+    want_mask, _ = R.newref_tools.get_mask(np.array(corrected))
+    assert np.array_equal(wcx_main.get_mask(np.array(corrected), st.counts, None, st.totals)[0], want_mask)
+    # a sample with an extra key or without reads: the per-sample route decides
+    odd = [dict(s) for s in samples]
+    odd[0]["extra"] = np.ones(3, dtype=np.int32)
+    assert wcx_main.stacked_counts(np.array(odd)).y_fractions is None
+    empty = [dict(s) for s in samples]
+    empty[1] = {k: np.zeros_like(v) for k, v in empty[1].items()}
+    assert wcx_main.stacked_counts(np.array(empty)).y_fractions is None

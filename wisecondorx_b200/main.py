@@ -28,10 +28,11 @@ def _y_fraction(sample):
     return float(np.sum(sample["24"])) / float(np.sum([np.sum(sample[x]) for x in sample.keys()]))
 
 
-def train_gender_model(args, samples):
+def train_gender_model(args, samples, y_fractions=None):
     """Two-component Gaussian mixture on the Y-read fraction; the first local minimum of the mixture
-    density on [0, 0.02] is the male/female cutoff unless --yfrac is given (reference :21-68)."""
-    y = np.array([_y_fraction(s) for s in samples])
+    density on [0, 0.02] is the male/female cutoff unless --yfrac is given (reference :21-68).
+    y_fractions: the fractions when the caller has them (stacked_counts below)."""
+    y = np.array([_y_fraction(s) for s in samples]) if y_fractions is None else np.asarray(y_fractions, dtype=float)
     if args.yfrac is not None:
         cut_off = args.yfrac
     else:
@@ -47,6 +48,35 @@ def train_gender_model(args, samples):
     genders[y > cut_off] = "M"
     genders[y < cut_off] = "F"
     return genders.tolist(), cut_off
+
+
+class stacked_counts:
+    """The read counts of all samples as one int32 matrix [bins, samples] (newref_tools.stack_counts) with the exact
+    read totals per sample, built ONCE for the Y fractions of the gender model, the three coverage masks and the three
+    passes of `newref`.  The reference recomputes all of these from the per-sample dicts (newref_tools.py:21-30,
+    :77-102, :110-129); the integer sums are the same, so are the float64 quotients."""
+
+    def __init__(self, samples):
+        self.bins_per_chr = [max(len(s[str(c)]) for s in samples) for c in range(1, 25)]
+        self.offs = np.concatenate([[0], np.cumsum(self.bins_per_chr)]).astype(np.int64)
+        self.counts = newref_tools.stack_counts(list(samples), range(1, 25))
+        self.totals = newref_tools.column_totals(self.counts)
+        self.x_totals = newref_tools.column_totals(self.counts[self.offs[22]:self.offs[23]])
+        self.y_totals = newref_tools.column_totals(self.counts[self.offs[23]:self.offs[24]])
+        # the reference's denominator adds up EVERY key of the sample dict (predict_tools.py:17-24, newref_tools.py:24-27):
+        # identical to the column total when the keys are the 24 chromosomes and no sample is empty
+        self.y_fractions = None
+        if all(len(s) == 24 for s in samples) and not np.any(self.totals == 0):
+            self.y_fractions = self.y_totals.astype(float) / self.totals.astype(float)
+
+    def gender_correct(self, genders):
+        """overall_tools.gender_correct for every male column: X and Y counts doubled (reference overall_tools.py:48-53)."""
+        male = np.flatnonzero(np.array(genders, dtype=object) == "M")
+        if len(male):
+            self.counts[self.offs[22]:self.offs[24], male] *= 2
+            self.totals[male] += self.x_totals[male] + self.y_totals[male]
+            self.x_totals[male] *= 2
+            self.y_totals[male] *= 2
 
 
 def get_mask(samples, counts=None, cols=None, totals=None):
@@ -119,16 +149,19 @@ def tool_newref(args):
     samples = np.array(samples)
     timings["load_samples"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    genders, trained_cutoff = train_gender_model(args, samples)
+    # one stacked count matrix [bins, samples] for the Y fractions, the three masks and the three passes
+    stacked = stacked_counts(samples) if len(samples) else None
+    genders, trained_cutoff = train_gender_model(args, samples, stacked.y_fractions if stacked else None)
     if genders.count("F") < 5 and args.nipt:
         logging.warning("A NIPT reference should have at least 5 female feti samples. Removing --nipt flag.")
         args.nipt = False
     if not args.nipt:
         for i, sample in enumerate(samples):
             samples[i] = gender_correct(sample, genders[i])
-    # one stacked count matrix [bins, samples] for the three masks and the three passes (each used to stack its own)
-    counts_all = newref_tools.stack_counts(list(samples), range(1, 25)) if len(samples) else None
-    totals = newref_tools.column_totals(counts_all) if counts_all is not None else None
+        if stacked:
+            stacked.gender_correct(genders)
+    counts_all = stacked.counts if stacked else None
+    totals = stacked.totals if stacked else None
     total_mask, bins_per_chr = get_mask(samples, counts_all, None, totals)
     g = np.array(genders)
     if genders.count("F") > 4:
