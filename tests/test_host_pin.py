@@ -319,3 +319,15 @@ def test_stacked_counts_gender_path(R):
     empty = [dict(s) for s in samples]
     empty[1] = {k: np.zeros_like(v) for k, v in empty[1].items()}
     assert wcx_main.stacked_counts(np.array(empty)).y_fractions is None
+
+
+def test_ref_qc_row_blocks_equal_whole_array():
+    """ref_qc.compute_per_bin_stats on row blocks (thread pool, above 32 768 bins) == the whole-array reductions."""
+    from wisecondorx_b200 import ref_qc
+    rng = np.random.default_rng(2)
+    d = rng.random((70001, 37)) * 3
+    idx = np.zeros(d.shape, dtype=np.int32)
+    mean_d, max_d, n_refs = ref_qc.compute_per_bin_stats(idx, d)
+    assert np.array_equal(mean_d, np.mean(d, axis=1)) and np.array_equal(max_d, np.max(d, axis=1)) and np.all(n_refs == 37)
+    mean_d, max_d, _ = ref_qc.compute_per_bin_stats(idx, d, need_max=False)
+    assert max_d is None and np.array_equal(mean_d, np.mean(d, axis=1))
