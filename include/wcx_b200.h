@@ -90,6 +90,16 @@ int wcx_cbs_unpack(const int32_t* pos, const double* y, const double* w, const i
                    int64_t na_thresh, int32_t* out_series, int64_t* out_s, int64_t* out_e, double* out_r,
                    int32_t threads);
 
+/* ---- host-side text of the per-bin table of predict (no device work, no context) ------------
+ * wcx_host_format_bins: the lines of <outid>_bins.bed for one chromosome (_generate_bins_bed, predict_output.py:59-84):
+ * "chr \t start \t end \t chr:start-end \t ratio \t zscore \n" for bins i = 0 .. n - 1 with start = i * binsize + 1,
+ * end = (i + 1) * binsize; a value of 0 prints as "nan", any other as Python's repr(float) (= str of the NumPy scalar
+ * the reference prints).  out: at least n * (2 * strlen(chr_name) + 138) bytes; *len = bytes written.
+ * wcx_host_format_repr: repr(x[i]) + "\n" for every value (26 bytes per value needed); test hook of the formatter. */
+int wcx_host_format_bins(const char* chr_name, int64_t binsize, const double* r, const double* z, int64_t n, char* out,
+                         int64_t cap, int64_t* len);
+int wcx_host_format_repr(const double* x, int64_t n, char* out, int64_t cap, int64_t* len);
+
 /* ---- newref ------------------------------------------------------------------------------
  * Replaces get_reference (newref_tools.py:155-224): get_ref_for_bins (:255-278) and the
  * null-ratio loop (:210-224).

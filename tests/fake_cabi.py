@@ -43,7 +43,8 @@ class FakeLib:
         self.noise = self.rng.standard_normal(1 << 22)
 
     def __getattr__(self, name):
-        if name in ("wcx_host_stack_counts", "wcx_host_bin_sums", "wcx_cbs_pack_count", "wcx_cbs_pack", "wcx_cbs_unpack"):  # host-only: the real library
+        if name in ("wcx_host_stack_counts", "wcx_host_bin_sums", "wcx_cbs_pack_count", "wcx_cbs_pack", "wcx_cbs_unpack",
+                    "wcx_host_format_bins", "wcx_host_format_repr"):  # host-only: the real library
             return getattr(self.real, name)
         raise AttributeError(name)
 

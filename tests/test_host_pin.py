@@ -331,3 +331,42 @@ def test_ref_qc_row_blocks_equal_whole_array():
     assert np.array_equal(mean_d, np.mean(d, axis=1)) and np.array_equal(max_d, np.max(d, axis=1)) and np.all(n_refs == 37)
     mean_d, max_d, _ = ref_qc.compute_per_bin_stats(idx, d, need_max=False)
     assert max_d is None and np.array_equal(mean_d, np.mean(d, axis=1))
+
+
+def test_native_float_text_equals_python_repr(tmp_path):
+    """wcx_host_format_repr / wcx_host_format_bins (csrc/host_tables.cu): the text of a float64 is Python's repr -- what
+    the reference's str(np.float64) prints -- for normal, tiny, huge, subnormal, integral and special values and for
+    random bit patterns; the bins table equals the line-by-line Python formatting of the reference
+    (predict_output.py:59-84)."""
+    import ctypes
+
+    from wisecondorx_b200 import _lib, predict_output
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+    sets = [rng.standard_normal(100000), rng.standard_normal(100000) * 0.05,
+            2.0 ** rng.integers(-1074, 1024, 50000) * rng.random(50000),
+            rng.integers(-10 ** 6, 10 ** 6, 20000).astype(float),
+            10.0 ** rng.integers(-30, 30, 20000) * rng.integers(1, 1000, 20000),
+            np.array([0.0, -0.0, 1.0, -1.0, 1e16, 9999999999999998.0, 1e-4, 9.999e-5, 1e-5, 1e22, 1e23, 5e-324,
+                      1.7976931348623157e308, np.nan, np.inf, -np.inf, 0.1, 0.30000000000000004, 123456789012345678.0,
+                      1e15, 1.5e16, 100.0, 1e100, 1e-100, 2.5e-5, 12345.678]),
+            np.frombuffer(rng.bytes(8 * 100000), dtype=np.float64)]
+    for x in sets:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty(len(x) * 26, dtype=np.uint8)
+        n = ctypes.c_int64()
+        _lib.check(L.wcx_host_format_repr(ctypes.c_void_p(x.ctypes.data), len(x), ctypes.c_void_p(out.ctypes.data), out.nbytes, ctypes.byref(n)))
+        got = out[:n.value].tobytes().decode("ascii").split("\n")[:-1]
+        assert got == [repr(v) for v in x.tolist()]
+    # the whole table: native fast path (float64 arrays) against the generic per-line path (lists)
+    r = [rng.standard_normal(n) * 0.1 for n in (300, 1, 0, 57)]
+    z = [rng.standard_normal(n) * 2 for n in (300, 1, 0, 57)]
+    for a in r + z:
+        a[rng.random(len(a)) < 0.2] = 0
+    r[0][5], z[0][6] = np.nan, np.inf
+    for binsize in (15000, np.int64(100000), 1):
+        rem = {"binsize": binsize, "args": types.SimpleNamespace(outid=str(tmp_path / "a"))}
+        predict_output._generate_bins_bed(rem, {"results_r": r, "results_z": z})
+        rem["args"].outid = str(tmp_path / "b")
+        predict_output._generate_bins_bed(rem, {"results_r": [list(a) for a in r], "results_z": [list(a) for a in z]})
+        assert (tmp_path / "a_bins.bed").read_text() == (tmp_path / "b_bins.bed").read_text()

@@ -46,6 +46,8 @@ def load():
     L.wcx_host_free.argtypes = [vp]
     L.wcx_host_stack_counts.argtypes = [vp, vp, i32, i32, vp, vp, i32]
     L.wcx_host_bin_sums.argtypes = [vp, i64, i32, vp, i32, vp, vp, i32]
+    L.wcx_host_format_bins.argtypes = [ctypes.c_char_p, i64, vp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.wcx_host_format_repr.argtypes = [vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.wcx_newref_load.argtypes = [vp, dp, i64, i32, vp, vp, i32, i32]
     L.wcx_newref_topk.argtypes = [vp, i64, i64, i32, i32, vp, vp, i32]
     L.wcx_newref_null_ratios.argtypes = [vp, vp, i32, i64, i64, i32, vp, i32, vp, i32]

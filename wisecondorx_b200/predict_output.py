@@ -55,6 +55,17 @@ def _generate_regions_bed(rem_input, results):
                                                 _fmt(np.ma.average(z, weights=w))]) + "\n")
 
 
+def _format_bins(name, binsize, r, z):
+    import ctypes
+    from . import _lib
+    r, z = np.ascontiguousarray(r), np.ascontiguousarray(z)
+    out = np.empty(len(r) * (2 * len(name) + 138) + 16, dtype=np.uint8)
+    n = ctypes.c_int64()
+    _lib.check(_lib.load().wcx_host_format_bins(name.encode("ascii"), binsize, ctypes.c_void_p(r.ctypes.data), ctypes.c_void_p(z.ctypes.data),
+                                                len(r), ctypes.c_void_p(out.ctypes.data), out.nbytes, ctypes.byref(n)))
+    return out[:n.value].tobytes().decode("ascii")
+
+
 def _generate_bins_bed(rem_input, results):
     binsize = rem_input["binsize"]
     with open("{}_bins.bed".format(rem_input["args"].outid), "w") as fh:
@@ -63,13 +74,10 @@ def _generate_bins_bed(rem_input, results):
             name = _chr_name(c)
             r, z = results["results_r"][c], results["results_z"][c]
             if (isinstance(r, np.ndarray) and isinstance(z, np.ndarray) and r.dtype == np.float64 and z.dtype == np.float64
-                    and isinstance(binsize, (int, np.integer))):
-                # 200 k lines at 15 kb: Python floats (repr == str of the NumPy scalar), every integer converted once
-                b, n = int(binsize), len(r)
-                ss = list(map(str, range(1, n * b + 1, b)))
-                es = list(map(str, range(b, n * b + b, b)))
-                fh.write("".join([f"{name}\t{s}\t{e}\t{name}:{s}-{e}\t{'nan' if x == 0 else repr(x)}\t{'nan' if y == 0 else repr(y)}\n"
-                                  for s, e, x, y in zip(ss, es, r.tolist(), z.tolist())]))
+                    and r.ndim == 1 and z.shape == r.shape and isinstance(binsize, (int, np.integer))):
+                # 200 k lines at 15 kb: formatted by the library on the host (wcx_host_format_bins, csrc/host_tables.cu:
+                # Python's repr of every value = str of the NumPy scalar the reference prints)
+                fh.write(_format_bins(name, int(binsize), r, z))
                 continue
             lines = []
             for i in range(len(r)):
