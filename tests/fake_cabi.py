@@ -67,6 +67,52 @@ class FakeLib:
     def wcx_host_free(self, p):
         return 0
 
+    # ---- newref: shapes only (ones, noise, a few far-off bins so that the PCA-distance filter and its redo run) ----------
+    def wcx_newref_normalize_and_mask(self, h, counts, rows, s, pos, npos, out, keep):
+        self.prep_shape = (int(npos), int(s))
+        return 0
+
+    def wcx_pca_gram(self, h, x, n, s, on_device, mean, gram):
+        _arr(mean, (n,), np.float64)[:] = 1.0 / max(n, 1)
+        a = self.noise[:s * (s + 3)].reshape(s, s + 3)
+        _arr(gram, (s, s), np.float64)[:] = a @ a.T
+        return 0
+
+    def wcx_pca_apply(self, h, u, sigma, n_eff, comps, corrected, flag):
+        n = self.prep_shape[0]
+        _arr(comps, (n_eff, n), np.float64)[:] = self.noise[:n_eff * n].reshape(n_eff, n)
+        return 0
+
+    def wcx_pca_distance(self, h, x, n, s, on_device, med, d):
+        _arr(med, (s,), np.float64)[:] = 1.0
+        dd = _arr(d, (n,), np.float64)
+        dd[:] = 1.0 + 0.01 * self.noise[:n]
+        dd[5::97] = 100.0
+        return 0
+
+    def wcx_newref_load(self, h, x, n, s, per, cum, nchr, mode):
+        self.loaded = (int(n), int(s))
+        return 0
+
+    def wcx_newref_reference(self, h, a, b, refsize, kernel, ids, nids, idx, dist, nr, on_device):
+        rows = int(b - a)
+        _arr(idx, (rows, refsize), np.int32)[:] = np.arange(refsize, dtype=np.int32)
+        _arr(dist, (rows, refsize), np.float64)[:] = 1.0 + np.arange(refsize) * 0.01
+        _arr(nr, (rows, nids), np.float64)[:] = 0.03 * self.noise[:rows * nids].reshape(rows, nids)
+        return 0
+
+    def wcx_newref_stats(self, h, out):
+        return 0
+
+    def wcx_newref_stage_ms(self, h, out):
+        return 0
+
+    def wcx_newref_prep_stage_ms(self, h, out):
+        return 0
+
+    def wcx_sync(self, h):
+        return 0
+
     def wcx_predict_load_ref(self, h, sid, idx, dist, n, k, per, cum, nchr, comps, mean, ncomp, mask_pos, bins_total):
         self.sets[sid] = (int(n), int(k), int(bins_total))
         return 0

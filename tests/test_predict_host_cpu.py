@@ -238,3 +238,39 @@ def test_predict_command_line_host_flow(fake_library, tmp_path):
     assert len(segs) == 1 + len(res["results_c"])
     for name in ("out_aberrations.bed", "out_statistics.txt"):
         assert (tmp_path / name).stat().st_size > 0
+
+
+def test_newref_command_line_host_flow(fake_library, tmp_path):
+    """`WisecondorX newref` end to end around the stand-in library: sample files read, one stacked count matrix for the
+    Y fractions / masks / passes, the A, F and M passes with the PCA-distance filter and its redo, results copied out and
+    deflated in the background, merge, QC -- then `predict` against the file it wrote.  The plumbing, not the numbers."""
+    from wisecondorx_b200 import main as wmain, npz_io
+    binsize = 1_000_000
+    samples, genders = synth.make_samples(15, binsize, seed=6, depth=1e6)
+    paths = []
+    for i, s in enumerate(samples[:14]):
+        paths.append(str(tmp_path / ("s%02d.npz" % i)))
+        np.savez_compressed(paths[-1], binsize=binsize, sample=s, quality={})
+    parser = wmain.build_parser()
+    ref_path = str(tmp_path / "ref.npz")
+    a = parser.parse_args(["newref"] + paths + [ref_path, "--binsize", str(binsize), "--yfrac", "0.006", "--refsize", "10", "--cpus", "2"])
+    timings = a.func(a)
+    assert {"prep.A", "prep.F", "prep.M", "get_reference.M", "write_reference", "qc_reference"} <= set(timings)
+    ref = npz_io.load_npz(ref_path)
+    plain = np.load(ref_path, allow_pickle=True)
+    assert set(plain.files) == set(ref) and bool(ref["has_female"]) and bool(ref["has_male"]) and not bool(ref["is_nipt"])
+    for sfx, nchr, ns in (("", 22, 14), (".F", 23, 7), (".M", 24, 7)):
+        n = int(np.sum(ref["mask" + sfx]))
+        assert len(ref["bins_per_chr" + sfx]) == nchr and int(ref["masked_bins_per_chr_cum" + sfx][-1]) == n
+        assert ref["indexes" + sfx].shape == (n, 10) and ref["indexes" + sfx].dtype == np.int32
+        assert ref["distances" + sfx].shape == (n, 10) and ref["null_ratios" + sfx].shape == (n, ns)
+        assert ref["pca_components" + sfx].shape == (5, n) and ref["pca_mean" + sfx].shape == (n,)
+        assert np.array_equal(plain["null_ratios" + sfx], ref["null_ratios" + sfx])
+    # the in-place mask edit leaks from pass to pass (SURVEY.md A.4): bins the filter removed stay removed
+    la, lf = len(ref["mask"]), len(ref["mask.F"])
+    assert not np.any(ref["mask.F"][:la] & ~ref["mask"]) and not np.any(ref["mask.M"][:lf] & ~ref["mask.F"])
+    assert int(np.sum(ref["mask.M"][:la])) < int(np.sum(ref["mask"]))  # the redo ran in the later passes too
+    np.savez_compressed(tmp_path / "t.npz", binsize=binsize, sample=samples[14], quality={})
+    b = parser.parse_args(["predict", str(tmp_path / "t.npz"), ref_path, str(tmp_path / "out"), "--bed", "--minrefbins", "5"])
+    res = b.func(b)
+    assert len(res["results_c"]) > 0 and (tmp_path / "out_bins.bed").stat().st_size > 0
