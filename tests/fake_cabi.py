@@ -98,7 +98,13 @@ class FakeLib:
         rows = int(b - a)
         _arr(idx, (rows, refsize), np.int32)[:] = np.arange(refsize, dtype=np.int32)
         _arr(dist, (rows, refsize), np.float64)[:] = 1.0 + np.arange(refsize) * 0.01
-        _arr(nr, (rows, nids), np.float64)[:] = 0.03 * self.noise[:rows * nids].reshape(rows, nids)
+        # a function of the absolute row, so that any split of the rows over calls / devices gives the same arrays
+        k = (np.arange(int(a), int(b))[:, None] * nids + np.arange(nids)[None, :]) % len(self.noise)
+        _arr(nr, (rows, nids), np.float64)[:] = 0.03 * self.noise[k]
+        return 0
+
+    def wcx_prep_device_ptr(self, h, which, n, s, ref):
+        ref._obj.value = 4096
         return 0
 
     def wcx_newref_stats(self, h, out):

@@ -270,6 +270,17 @@ def test_newref_command_line_host_flow(fake_library, tmp_path):
     la, lf = len(ref["mask"]), len(ref["mask.F"])
     assert not np.any(ref["mask.F"][:la] & ~ref["mask"]) and not np.any(ref["mask.M"][:lf] & ~ref["mask.F"])
     assert int(np.sum(ref["mask.M"][:la])) < int(np.sum(ref["mask"]))  # the redo ran in the later passes too
+    # `newref --gpus 3`: every part cut into one row range per device, one context + host thread per device
+    import random
+    ref3_path = str(tmp_path / "ref3.npz")
+    for pth, extra in ((ref_path, []), (ref3_path, ["--gpus", "3"])):
+        random.seed(11)
+        a = parser.parse_args(["newref"] + paths + [pth, "--binsize", str(binsize), "--yfrac", "0.006", "--refsize", "10", "--cpus", "2"] + extra)
+        a.func(a)
+    one, three = npz_io.load_npz(ref_path), npz_io.load_npz(ref3_path)
+    assert set(one) == set(three)
+    for key in one:
+        assert np.array_equal(np.asarray(one[key]), np.asarray(three[key]), equal_nan=True), key
     np.savez_compressed(tmp_path / "t.npz", binsize=binsize, sample=samples[14], quality={})
     b = parser.parse_args(["predict", str(tmp_path / "t.npz"), ref_path, str(tmp_path / "out"), "--bed", "--minrefbins", "5"])
     res = b.func(b)
