@@ -166,13 +166,31 @@ class _PCAModel:
         self.n_components_ = components.shape[0]
 
 
+_blas_controller = []
+
+
+def _eigh_one_thread(gram):
+    """np.linalg.eigh of the S x S Gram matrix on ONE BLAS thread.  For S <= 500 the threaded LAPACK path buys nothing
+    (11 / 49 ms at S = 250 / 500 either way), but while the previous pass is still being copied out and deflated on the
+    other cores its spinning worker threads make the call 10 - 30 times slower (0.24 - 0.33 s measured in the F / M
+    passes of `newref` at 500 samples: most of `prep.F` / `prep.M`)."""
+    try:
+        if not _blas_controller:
+            from threadpoolctl import ThreadpoolController
+            _blas_controller.append(ThreadpoolController())
+        with _blas_controller[0].limit(limits=1, user_api="blas"):
+            return np.linalg.eigh(gram)
+    except ImportError:  # threadpoolctl comes with scikit-learn (a dependency of the reference); without it: plain call
+        return np.linalg.eigh(gram)
+
+
 def _pca_spectrum(gram, pcacomp):
     """Top eigenpairs of the S x S Gram matrix of the centred data -> (u [S, n_eff], sigma [n_eff], lam [pcacomp],
     n_eff).  The centred matrix has rank <= S - 1: with S <= pcacomp samples (the reference allows gonosomal passes
     with exactly 5, main.py:104,119) the trailing eigenvalues are round-off, and dividing by their square root would
     blow the stored components up to ~1e130.  Only the numerically non-zero part of the spectrum (relative 1e-12) is
     sent to the device; _finish_components pads the rest."""
-    w, u = np.linalg.eigh(gram)
+    w, u = _eigh_one_thread(gram)
     order = np.argsort(w)[::-1][:pcacomp]
     lam = np.clip(w[order], 0.0, None)
     lam_full = np.zeros(pcacomp)
