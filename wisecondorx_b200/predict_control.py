@@ -282,7 +282,7 @@ def predict_batch(args, samples, binsizes, ref_file, engine: predict_tools.Predi
         sample = scale_sample(dict(sample), int(bs), int(ref_file["binsize"]))
         return resolve_genders(args, sample, ref_file) + (reads,)
 
-    pre = _map_threads(prelude, list(zip(samples, binsizes)))
+    pre = [prelude(t) for t in zip(samples, binsizes)]  # ~25 tiny NumPy calls per sample: a thread pool only adds lock traffic (measured)
     prepared, genders, ref_genders, n_reads = ([p[i] for p in pre] for i in range(4))
     logging.info("Normalizing autosomes ...")
     r, z, w, n, m_lr, m_z = normalize_batch(args, prepared, ref_file, "A", eng)
