@@ -174,13 +174,15 @@ def _eigh_one_thread(gram):
     (11 / 49 ms at S = 250 / 500 either way), but while the previous pass is still being copied out and deflated on the
     other cores its spinning worker threads make the call 10 - 30 times slower (0.24 - 0.33 s measured in the F / M
     passes of `newref` at 500 samples: most of `prep.F` / `prep.M`)."""
+    import contextlib
     try:
         if not _blas_controller:
             from threadpoolctl import ThreadpoolController
             _blas_controller.append(ThreadpoolController())
-        with _blas_controller[0].limit(limits=1, user_api="blas"):
-            return np.linalg.eigh(gram)
-    except ImportError:  # threadpoolctl comes with scikit-learn (a dependency of the reference); without it: plain call
+        limit = _blas_controller[0].limit(limits=1, user_api="blas")
+    except Exception:  # threadpoolctl comes with scikit-learn (a dependency of the reference); without it: the plain call
+        limit = contextlib.nullcontext()
+    with limit:
         return np.linalg.eigh(gram)
 
 
