@@ -15,3 +15,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """The host-logic tests call the library's host-side entry points (no GPU needed): build it when the tree has no
+    .so yet (a fresh clone; nvcc cross-compiles without a GPU).  A .so that is there is left alone -- on the GPU box the
+    one that travelled with the snapshot is the one under test."""
+    from wisecondorx_b200 import _lib, build
+    if not os.path.exists(_lib.SO_PATH):
+        build.build()
